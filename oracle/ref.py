@@ -1,0 +1,248 @@
+"""TEST INFRASTRUCTURE ONLY — ctypes binding of oracle/_ref/libsatref.so (the unmodified reference
+translation units + oracle/ref_harness.cpp).  See oracle/__init__.py."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_PATH = os.path.join(_HERE, "_ref", "libsatref.so")
+
+CONST = {"bpsk": 0, "qpsk": 1, "oqpsk": 2, "8psk": 3, "none": 4, "bpsk_90": 5}
+FMT = {"cf32": 0, "cs16": 1, "cs8": 2}
+
+
+class DemodCfg(C.Structure):
+    _fields_ = [("samplerate", C.c_double), ("symbolrate", C.c_double), ("constellation", C.c_int),
+                ("rrc_alpha", C.c_float), ("rrc_taps", C.c_int), ("pll_bw", C.c_float), ("agc_rate", C.c_float),
+                ("clock_gain_omega", C.c_float), ("clock_mu", C.c_float), ("clock_gain_mu", C.c_float),
+                ("clock_omega_limit", C.c_float), ("costas_max_offset", C.c_float), ("format", C.c_int),
+                ("buffer_size", C.c_int)]
+
+
+class FecCfg(C.Structure):
+    _fields_ = [("kind", C.c_int), ("constellation", C.c_int), ("cadu_size", C.c_int), ("outsync_after", C.c_int),
+                ("ber_thresold", C.c_float), ("nrzm", C.c_int), ("derandomize", C.c_int), ("derand_after_rs", C.c_int),
+                ("derand_start", C.c_int), ("rs_i", C.c_int), ("rs_dualbasis", C.c_int), ("rs_fill_bytes", C.c_int),
+                ("rs_usecheck", C.c_int), ("rs_type", C.c_int), ("iq_invert", C.c_int), ("asm_sync", C.c_uint)]
+
+
+def available():
+    return os.path.exists(_PATH)
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(_PATH)
+        L.ref_demod_create.restype = C.c_void_p
+        L.ref_demod_create.argtypes = [C.POINTER(DemodCfg)]
+        L.ref_demod_destroy.argtypes = [C.c_void_p]
+        L.ref_demod_buffer_size.argtypes = [C.c_void_p]
+        L.ref_demod_sps.argtypes = [C.c_void_p]
+        L.ref_demod_sps.restype = C.c_float
+        L.ref_demod_rrc_taps.argtypes = [C.c_void_p, C.c_void_p]
+        L.ref_mm_taps.argtypes = [C.c_void_p]
+        L.ref_rrc_design.argtypes = [C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_void_p]
+        L.ref_demod_run.restype = C.c_long
+        L.ref_demod_run.argtypes = [C.c_void_p, C.c_void_p, C.c_long] + [C.c_void_p] * 5 + [C.c_long]
+        L.ref_demod_state.argtypes = [C.c_void_p, C.c_void_p]
+        L.ref_fec_create.restype = C.c_void_p
+        L.ref_fec_create.argtypes = [C.POINTER(FecCfg)]
+        L.ref_fec_destroy.argtypes = [C.c_void_p]
+        L.ref_fec_chunk_size.argtypes = [C.c_void_p]
+        L.ref_fec_cadu_bytes.argtypes = [C.c_void_p]
+        L.ref_fec_run.restype = C.c_long
+        L.ref_fec_run.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_long] + [C.c_void_p] * 7
+        L.ref_rs_encode_interleaved.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.ref_rs_decode_interleaved.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.ref_derand.argtypes = [C.c_void_p, C.c_int]
+        L.ref_cc_encode.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.ref_cc_decode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.ref_rotate_soft.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.ref_deframe.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.ref_pipeline_timed.restype = C.c_double
+        L.ref_pipeline_timed.argtypes = [C.POINTER(DemodCfg), C.POINTER(FecCfg), C.c_void_p, C.c_long, C.c_void_p, C.c_long,
+                                         C.POINTER(C.c_long), C.POINTER(C.c_int)]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def demod_cfg(samplerate, symbolrate, constellation, rrc_alpha, pll_bw=0.003, fmt="cs16", rrc_taps=31, agc_rate=1e-2,
+              clock_alpha=None, clock_gain_omega=None, clock_mu=0.5, clock_gain_mu=8.7e-3, clock_omega_limit=0.005,
+              costas_max_offset=1.0, buffer_size=0):
+    """Defaults follow module_psk_demod.h:31-39 and module_demod_base.h:54."""
+    if clock_alpha is not None:  # module_psk_demod.cpp:36-41 ; DVB-S2 REC_ALPHA module_dvbs2_demod.h:49-53
+        clock_gain_omega = np.float32(clock_alpha) ** 2 / 4.0
+        clock_gain_mu = clock_alpha
+    if clock_gain_omega is None:
+        clock_gain_omega = float(np.float32(pow(8.7e-3, 2) / 4.0))
+    return DemodCfg(float(samplerate), float(symbolrate), CONST[constellation], rrc_alpha, rrc_taps, pll_bw, agc_rate,
+                    float(clock_gain_omega), clock_mu, float(clock_gain_mu), clock_omega_limit, costas_max_offset, FMT[fmt],
+                    buffer_size)
+
+
+def metop_cfg(ber_thresold=0.28, outsync_after=10):
+    return FecCfg(0, 1, 8192, outsync_after, ber_thresold, 0, 1, 0, 4, 4, 1, -1, 0, 0, 0, 0x1ACFFC1D)
+
+
+def ccsds_cfg(constellation, cadu_size, ber_thresold, outsync_after, rs_i, nrzm=False, derandomize=True, rs_usecheck=False,
+              rs_dualbasis=True, rs_fill_bytes=-1, derand_after_rs=False, derand_start=4, iq_invert=False, rs_type=0,
+              asm_sync=0x1ACFFC1D):
+    return FecCfg(1, CONST[constellation], cadu_size, outsync_after, ber_thresold, int(nrzm), int(derandomize),
+                  int(derand_after_rs), derand_start, rs_i, int(rs_dualbasis), rs_fill_bytes, int(rs_usecheck), rs_type,
+                  int(iq_invert), asm_sync)
+
+
+class Demod:
+    def __init__(self, cfg):
+        self.cfg = cfg
+        self.h = lib().ref_demod_create(C.byref(cfg))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().ref_demod_destroy(self.h)
+            self.h = None
+
+    @property
+    def buffer_size(self):
+        return lib().ref_demod_buffer_size(self.h)
+
+    @property
+    def sps(self):
+        return lib().ref_demod_sps(self.h)
+
+    def rrc_taps(self):
+        out = np.zeros(256, np.float32)
+        n = lib().ref_demod_rrc_taps(self.h, _p(out))
+        return out[:n].copy()
+
+    def state(self):
+        out = np.zeros(8, np.float32)
+        lib().ref_demod_state(self.h, _p(out))
+        return dict(gain=out[0], phase=out[1], freq=out[2], mu=out[3], omega=out[4], inc=int(out[5]), alpha=out[6], beta=out[7])
+
+    def run(self, raw, stages=True):
+        """raw: cf32 (complex64) / cs16 (int16 pairs) / cs8 (int8 pairs) array. Returns dict of stage dumps."""
+        raw = np.ascontiguousarray(raw)
+        n = raw.size if self.cfg.format == 0 and np.iscomplexobj(raw) else raw.size // 2
+        bps = 1 if self.cfg.constellation == 0 else 2
+        cap = int(n / max(1.0, self.sps) * 1.1) + 64
+        agc = np.zeros(n, np.complex64) if stages else None
+        fir = np.zeros(n, np.complex64) if stages else None
+        cos = np.zeros(n, np.complex64) if (stages and self.cfg.constellation != 4) else None
+        mm = np.zeros(cap, np.complex64)
+        soft = np.zeros(cap * bps, np.int8)
+        ns = lib().ref_demod_run(self.h, _p(raw), n, _p(agc), _p(fir), _p(cos), _p(mm), _p(soft), cap)
+        return dict(agc=agc, fir=fir, costas=cos, mm=mm[:ns].copy(), soft=soft[:ns * bps].copy())
+
+
+class Fec:
+    def __init__(self, cfg):
+        self.cfg = cfg
+        self.h = lib().ref_fec_create(C.byref(cfg))
+        self.chunk = lib().ref_fec_chunk_size(self.h)
+        self.cadu_bytes = lib().ref_fec_cadu_bytes(self.h)
+        self.rate_num = 3 if cfg.kind == 0 else 1  # decoded bits per 2 soft (x rate)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().ref_fec_destroy(self.h)
+            self.h = None
+
+    def run(self, soft):
+        soft = np.ascontiguousarray(soft, np.int8)
+        nch = soft.size // self.chunk
+        bits_per_chunk = self.chunk * 3 // 4 if self.cfg.kind == 0 else self.chunk // 2
+        cap = (nch * bits_per_chunk // max(1, self.cfg.cadu_size) + 2) * self.cadu_bytes
+        cadu = np.zeros(cap, np.uint8)
+        vs = np.zeros(nch, np.int32)
+        vb = np.zeros(nch, np.float32)
+        ds = np.zeros(nch, np.int32)
+        bits = np.zeros(nch * bits_per_chunk + 8, np.uint8)
+        rs_i = max(1, self.cfg.rs_i)
+        rse = np.zeros((cap // self.cadu_bytes + 2) * rs_i, np.int32)
+        nbits = C.c_long(0)
+        nfr = C.c_long(0)
+        w = lib().ref_fec_run(self.h, _p(soft), soft.size, _p(cadu), cap, _p(vs), _p(vb), _p(ds), _p(bits), C.byref(nbits),
+                              _p(rse), C.byref(nfr))
+        return dict(cadu=cadu[:w].copy(), vit_state=vs, vit_ber=vb, defr_state=ds, bits=bits[:nbits.value].copy(),
+                    rs_err=rse[:nfr.value * rs_i].reshape(-1, rs_i).copy(), nframes=nfr.value)
+
+
+def rrc_design(gain, fs, rs, alpha, ntaps):
+    out = np.zeros(ntaps + 2, np.float32)
+    n = lib().ref_rrc_design(gain, fs, rs, alpha, ntaps, _p(out))
+    return out[:n].copy()
+
+
+def mm_taps():
+    out = np.zeros(128 * 8, np.float32)
+    lib().ref_mm_taps(_p(out))
+    return out.reshape(128, 8)
+
+
+def rs_encode_interleaved(data, dual=True, interleave=4, rs_type=0):
+    d = np.ascontiguousarray(data, np.uint8).copy()
+    lib().ref_rs_encode_interleaved(_p(d), int(dual), interleave, rs_type)
+    return d
+
+
+def rs_decode_interleaved(data, dual=True, interleave=4, rs_type=0, fill_bytes=-1):
+    d = np.ascontiguousarray(data, np.uint8).copy()
+    err = np.zeros(interleave, np.int32)
+    lib().ref_rs_decode_interleaved(_p(d), int(dual), interleave, rs_type, fill_bytes, _p(err))
+    return d, err
+
+
+def derand(data):
+    d = np.ascontiguousarray(data, np.uint8).copy()
+    lib().ref_derand(_p(d), d.size)
+    return d
+
+
+def cc_encode(bits):
+    b = np.ascontiguousarray(bits, np.uint8)
+    out = np.zeros(2 * b.size, np.uint8)
+    lib().ref_cc_encode(_p(b), b.size, _p(out))
+    return out
+
+
+def cc_decode(syms, frame, ncalls):
+    s = np.ascontiguousarray(syms, np.uint8)
+    assert s.size >= ncalls * 2 * frame + 12
+    out = np.zeros(ncalls * frame, np.uint8)
+    lib().ref_cc_decode(_p(s), frame, ncalls, _p(out))
+    return out
+
+
+def rotate_soft(soft, phase, iqswap=False):
+    s = np.ascontiguousarray(soft, np.int8).copy()
+    lib().ref_rotate_soft(_p(s), s.size, phase, int(iqswap))
+    return s
+
+
+def deframe(bits, cadu_size=8192, state_synced=12):
+    b = np.ascontiguousarray(bits, np.uint8)
+    out = np.zeros((b.size // cadu_size + 2) * (cadu_size // 8), np.uint8)
+    n = lib().ref_deframe(_p(b), b.size, cadu_size, state_synced, _p(out))
+    return out[:n * (cadu_size // 8)].reshape(n, cadu_size // 8).copy()
+
+
+def pipeline_timed(dcfg, fcfg, raw):
+    """The reference's own threaded execution model (one thread per block). Returns (seconds, cadu bytes, threads)."""
+    raw = np.ascontiguousarray(raw)
+    n = raw.size if dcfg.format == 0 and np.iscomplexobj(raw) else raw.size // 2
+    cap = int(n * 0.2) + 65536
+    cadu = np.zeros(cap, np.uint8)
+    nb = C.c_long(0)
+    nt = C.c_int(0)
+    secs = lib().ref_pipeline_timed(C.byref(dcfg), C.byref(fcfg), _p(raw), n, _p(cadu), cap, C.byref(nb), C.byref(nt))
+    return secs, cadu[:nb.value].copy(), nt.value

@@ -1,0 +1,598 @@
+/*
+ * TEST INFRASTRUCTURE ONLY — never linked into or called from the product path.
+ *
+ * oracle/_ref harness: wires the UNMODIFIED reference translation units (compiled from
+ * /root/reference by oracle/Makefile, with oracle/shim standing in for VOLK + logger) exactly
+ * like the reference modules do, and exposes them through a small C ABI for the Python tests
+ * and for bench.py's cpu_baseline / --impl reference arm.
+ *
+ * Wiring mirrors (reference file:line):
+ *   BaseDemodModule::initb            src-core/pipeline/modules/demod/module_demod_base.cpp:59-208
+ *   PSKDemodModule::init / process    src-core/pipeline/modules/demod/module_psk_demod.cpp:86-236
+ *   DVBS2DemodModule front half       plugins/dvb_support/dvbs2/module_dvbs2_demod.cpp:98-102
+ *   MetOpAHRPTDecoderModule::process  plugins/noaa_metop_support/metop/module_metop_ahrpt_decoder.cpp:34-90
+ *   CCSDSConvConcatDecoderModule      src-core/pipeline/modules/ccsds/module_ccsds_conv_concat_decoder.cpp:16-200
+ *   Pipeline::run two-module mode     src-core/pipeline/pipeline_run.cpp:44-117
+ *
+ * No reference source is copied here: this file only *calls* the reference classes.
+ */
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <complex>
+#include <condition_variable>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <vector>
+#include <volk/volk.h>
+#include "logger.h"
+/* work() and the loop state are private/protected in the block classes; the harness drives the
+ * blocks synchronously and reads their state, so it opens the access specifiers for ITS view of
+ * the headers only (the reference .cpp files are compiled untouched; GCC layout is unaffected). */
+#define protected public
+#define private public
+#include "common/dsp/block.h"
+#include "common/dsp/utils/agc.h"
+#include "common/dsp/filter/fir.h"
+#include "common/dsp/filter/firdes.h"
+#include "common/dsp/pll/costas_loop.h"
+#include "common/dsp/demod/delay_one_imag.h"
+#include "common/dsp/clock_recovery/clock_recovery_mm.h"
+#undef private
+#undef protected
+#include "common/dsp/resamp/polyphase_bank.h"
+#include "common/dsp/window/window.h"
+#include "common/codings/viterbi/viterbi_3_4.h"
+#include "common/codings/viterbi/viterbi_1_2.h"
+#include "common/codings/viterbi/cc_encoder.h"
+#include "common/codings/viterbi/cc_decoder.h"
+#include "common/codings/deframing/bpsk_ccsds_deframer.h"
+#include "common/codings/randomization.h"
+#include "common/codings/reedsolomon/reedsolomon.h"
+#include "common/codings/differential/nrzm.h"
+#include "common/codings/rotation.h"
+
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+std::shared_ptr<slog::Logger> logger = std::make_shared<slog::Logger>();
+
+extern "C"
+{
+    /* ------------------------------------------------------------------ configuration */
+    typedef struct
+    {
+        double samplerate;       /* Hz (module param "samplerate", parsed as long)            */
+        double symbolrate;       /* Hz (module param "symbolrate", parsed as long)            */
+        int constellation;       /* 0 bpsk, 1 qpsk, 2 oqpsk, 3 8psk, 4 = no Costas (DVB-S2 front half) */
+        float rrc_alpha;
+        int rrc_taps;            /* default 31 */
+        float pll_bw;
+        float agc_rate;          /* default 1e-2 */
+        float clock_gain_omega;  /* default pow(8.7e-3,2)/4 */
+        float clock_mu;          /* default 0.5 */
+        float clock_gain_mu;     /* default 8.7e-3 */
+        float clock_omega_limit; /* default 0.005 */
+        float costas_max_offset; /* rad/sample, default 1.0 */
+        int format;              /* 0 cf32, 1 cs16, 2 cs8 */
+        int buffer_size;         /* 0 = reference default rule */
+    } ref_demod_cfg;
+
+    typedef struct
+    {
+        int kind;           /* 0 = metop_ahrpt_decoder, 1 = ccsds_conv_concat_decoder (r=1/2) */
+        int constellation;  /* ccsds: 0 bpsk, 1 qpsk, 2 oqpsk, 5 bpsk_90 */
+        int cadu_size;      /* bits */
+        int outsync_after;
+        float ber_thresold;
+        int nrzm, derandomize, derand_after_rs, derand_start;
+        int rs_i, rs_dualbasis, rs_fill_bytes, rs_usecheck, rs_type; /* rs_type 0 rs223 1 rs239 */
+        int iq_invert;
+        unsigned int asm_sync;
+    } ref_fec_cfg;
+}
+
+namespace
+{
+    struct RefDemod
+    {
+        ref_demod_cfg cfg;
+        int buffer_size;
+        float final_samplerate, final_sps;
+        std::shared_ptr<dsp::stream<complex_t>> in;
+        std::shared_ptr<dsp::AGCBlock<complex_t>> agc;
+        std::shared_ptr<dsp::FIRBlock<complex_t>> rrc;
+        std::shared_ptr<dsp::CostasLoopBlock> pll;
+        std::shared_ptr<dsp::DelayOneImagBlock> delay;
+        std::shared_ptr<dsp::MMClockRecoveryBlock<complex_t>> rec;
+        std::vector<float> rrc_taps;
+    };
+
+    int8_t soft_clamp(float x) /* module_demod_base.h:106-113 semantics */
+    {
+        if (x < -128.0)
+            return -127;
+        if (x > 127.0)
+            return 127;
+        return x;
+    }
+
+    void convert_block(const ref_demod_cfg &cfg, const void *raw, long off, int n, complex_t *dst)
+    {
+        /* baseband_interface.h:170-190 */
+        if (cfg.format == 0)
+            memcpy(dst, (const complex_t *)raw + off, n * sizeof(complex_t));
+        else if (cfg.format == 1)
+            volk_16i_s32f_convert_32f_u((float *)dst, (const int16_t *)raw + off * 2, 32767, n * 2);
+        else
+            volk_8i_s32f_convert_32f_u((float *)dst, (const int8_t *)raw + off * 2, 127, n * 2);
+    }
+
+    struct RefFec
+    {
+        ref_fec_cfg cfg;
+        int buffer_size, cadu_bytes;
+        std::shared_ptr<viterbi::Viterbi3_4> v34;
+        std::shared_ptr<viterbi::Viterbi1_2> v12;
+        std::shared_ptr<deframing::BPSK_CCSDS_Deframer> deframer;
+        std::shared_ptr<reedsolomon::ReedSolomon> rs;
+        diff::NRZMDiff diff;
+        int errors[16];
+        int noSyncsRuns = 0;
+        std::vector<uint8_t> viterbi_out, frame_buffer;
+        std::vector<int8_t> soft;
+    };
+}
+
+extern "C"
+{
+    void *ref_demod_create(const ref_demod_cfg *c)
+    {
+        RefDemod *d = new RefDemod();
+        d->cfg = *c;
+        long samplerate = (long)c->samplerate, symbolrate = (long)c->symbolrate;
+        d->buffer_size = c->buffer_size > 0 ? c->buffer_size : std::min<int>(dsp::STREAM_BUFFER_SIZE, std::max<int>(8192 + 1, samplerate / 200));
+        d->final_samplerate = samplerate; /* sps inside the window: no resampler */
+        d->final_sps = d->final_samplerate / (float)symbolrate;
+        d->in = std::make_shared<dsp::stream<complex_t>>();
+        d->agc = std::make_shared<dsp::AGCBlock<complex_t>>(d->in, c->agc_rate, 1.0f, 1.0f, 65536);
+        d->rrc_taps = dsp::firdes::root_raised_cosine(1, d->final_samplerate, (int)symbolrate, c->rrc_alpha, c->rrc_taps);
+        d->rrc = std::make_shared<dsp::FIRBlock<complex_t>>(d->agc->output_stream, d->rrc_taps);
+        std::shared_ptr<dsp::stream<complex_t>> last = d->rrc->output_stream;
+        if (c->constellation != 4)
+        {
+            int order = c->constellation == 0 ? 2 : (c->constellation == 3 ? 8 : 4);
+            d->pll = std::make_shared<dsp::CostasLoopBlock>(last, c->pll_bw, order, c->costas_max_offset);
+            last = d->pll->output_stream;
+            if (c->constellation == 2)
+            {
+                d->delay = std::make_shared<dsp::DelayOneImagBlock>(last);
+                last = d->delay->output_stream;
+            }
+        }
+        d->rec = std::make_shared<dsp::MMClockRecoveryBlock<complex_t>>(last, d->final_sps, c->clock_gain_omega, c->clock_mu, c->clock_gain_mu, c->clock_omega_limit);
+        return d;
+    }
+
+    void ref_demod_destroy(void *h) { delete (RefDemod *)h; }
+    int ref_demod_buffer_size(void *h) { return ((RefDemod *)h)->buffer_size; }
+    float ref_demod_sps(void *h) { return ((RefDemod *)h)->final_sps; }
+
+    int ref_demod_rrc_taps(void *h, float *out)
+    {
+        RefDemod *d = (RefDemod *)h;
+        memcpy(out, d->rrc_taps.data(), d->rrc_taps.size() * sizeof(float));
+        return (int)d->rrc_taps.size();
+    }
+
+    /* Polyphase interpolator bank of the M&M block: out[arm*8 + k] (clock_recovery_mm.cpp:18, polyphase_bank.cpp:6-39) */
+    int ref_mm_taps(float *out)
+    {
+        dsp::PolyphaseBank pfb;
+        pfb.init(dsp::windowed_sinc(128 * 8, dsp::hz_to_rad(0.5 / 128.0, 1.0), dsp::window::nuttall, 128), 128);
+        for (int a = 0; a < pfb.nfilt; a++)
+            for (int k = 0; k < pfb.ntaps; k++)
+                out[a * pfb.ntaps + k] = pfb.taps[a][k];
+        return pfb.nfilt * pfb.ntaps;
+    }
+
+    int ref_rrc_design(double gain, double fs, double rs, double alpha, int ntaps, float *out)
+    {
+        std::vector<float> t = dsp::firdes::root_raised_cosine(gain, fs, rs, alpha, ntaps);
+        memcpy(out, t.data(), t.size() * sizeof(float));
+        return (int)t.size();
+    }
+
+    /*
+     * Synchronous run over `nsamples` raw samples, in reference-sized buffers. Any of the dump
+     * pointers may be NULL. agc/fir/costas dumps hold nsamples complex values (costas = after the
+     * OQPSK delay when present); mm_out / soft_out hold the recovered symbols / int8 soft stream.
+     * Returns the number of symbols produced. State persists across calls (streaming).
+     */
+    long ref_demod_run(void *h, const void *raw, long nsamples, float *agc_out, float *fir_out, float *costas_out, float *mm_out, int8_t *soft_out,
+                       long sym_cap)
+    {
+        RefDemod *d = (RefDemod *)h;
+        long nsym = 0;
+        for (long off = 0; off < nsamples; off += d->buffer_size)
+        {
+            int n = (int)std::min<long>(d->buffer_size, nsamples - off);
+            convert_block(d->cfg, raw, off, n, d->in->writeBuf);
+            d->in->swap(n);
+            d->agc->work();
+            if (agc_out)
+                memcpy(agc_out + off * 2, d->agc->output_stream->readBuf, n * sizeof(complex_t));
+            d->rrc->work();
+            if (fir_out)
+                memcpy(fir_out + off * 2, d->rrc->output_stream->readBuf, n * sizeof(complex_t));
+            if (d->pll)
+            {
+                d->pll->work();
+                if (d->delay)
+                    d->delay->work();
+                if (costas_out)
+                    memcpy(costas_out + off * 2, (d->delay ? d->delay->output_stream : d->pll->output_stream)->readBuf, n * sizeof(complex_t));
+            }
+            d->rec->work();
+            int m = d->rec->output_stream->getDataSize();
+            complex_t *sym = d->rec->output_stream->readBuf;
+            if (nsym + m > sym_cap)
+                m = (int)(sym_cap - nsym);
+            if (mm_out)
+                memcpy(mm_out + nsym * 2, sym, m * sizeof(complex_t));
+            if (soft_out)
+            {
+                if (d->cfg.constellation == 0) /* module_psk_demod.cpp:199-205 */
+                    for (int i = 0; i < m; i++)
+                        soft_out[nsym + i] = soft_clamp(sym[i].real * 50);
+                else /* module_psk_demod.cpp:207-213 */
+                    for (int i = 0; i < m; i++)
+                    {
+                        soft_out[(nsym + i) * 2] = soft_clamp(sym[i].real * 100);
+                        soft_out[(nsym + i) * 2 + 1] = soft_clamp(sym[i].imag * 100);
+                    }
+            }
+            d->rec->output_stream->flush();
+            nsym += m;
+        }
+        return nsym;
+    }
+
+    /* Carried loop state, for stage-isolated tests */
+    void ref_demod_state(void *h, float *out8)
+    {
+        RefDemod *d = (RefDemod *)h;
+        out8[0] = d->agc->gain;
+        out8[1] = d->pll ? d->pll->phase : 0;
+        out8[2] = d->pll ? d->pll->freq : 0;
+        out8[3] = d->rec->mu;
+        out8[4] = d->rec->omega;
+        out8[5] = (float)d->rec->inc;
+        out8[6] = d->pll ? d->pll->alpha : 0;
+        out8[7] = d->pll ? d->pll->beta : 0;
+    }
+
+    /* ------------------------------------------------------------------ FEC side */
+    void *ref_fec_create(const ref_fec_cfg *c)
+    {
+        RefFec *f = new RefFec();
+        f->cfg = *c;
+        memset(f->errors, 0, sizeof(f->errors));
+        if (c->kind == 0)
+        {
+            f->buffer_size = 8192 * 2;
+            f->cadu_bytes = 1024;
+            f->v34 = std::make_shared<viterbi::Viterbi3_4>(c->ber_thresold, c->outsync_after, f->buffer_size);
+            f->deframer = std::make_shared<deframing::BPSK_CCSDS_Deframer>();
+            f->deframer->STATE_SYNCED = 18;
+            f->rs = std::make_shared<reedsolomon::ReedSolomon>(reedsolomon::RS223);
+        }
+        else
+        {
+            f->buffer_size = std::max<int>(c->cadu_size, 8192);
+            f->cadu_bytes = (int)ceil(c->cadu_size / 8.0);
+            std::vector<phase_t> phases;
+            bool oqpsk = c->constellation == 2;
+            if (c->constellation == 0)
+                phases = {PHASE_0};
+            else if (c->constellation == 5)
+                phases = {PHASE_90};
+            else
+                phases = {PHASE_0, PHASE_90};
+            f->v12 = std::make_shared<viterbi::Viterbi1_2>(c->ber_thresold, c->outsync_after, f->buffer_size, phases, oqpsk);
+            f->deframer = std::make_shared<deframing::BPSK_CCSDS_Deframer>(c->cadu_size, c->asm_sync);
+            if (c->cadu_size % 8 != 0)
+                f->deframer->CADU_PADDING = c->cadu_size % 8;
+            if (c->rs_i != 0)
+                f->rs = std::make_shared<reedsolomon::ReedSolomon>(c->rs_type == 1 ? reedsolomon::RS239 : reedsolomon::RS223, c->rs_fill_bytes);
+        }
+        f->viterbi_out.resize(f->buffer_size * 8);
+        f->frame_buffer.resize(f->buffer_size * 8 + 1024 * 10);
+        f->soft.resize(f->buffer_size);
+        return f;
+    }
+    void ref_fec_destroy(void *h) { delete (RefFec *)h; }
+    int ref_fec_chunk_size(void *h) { return ((RefFec *)h)->buffer_size; }
+    int ref_fec_cadu_bytes(void *h) { return ((RefFec *)h)->cadu_bytes; }
+
+    /*
+     * Runs whole chunks of the int8 soft stream (nsoft must be a multiple of the chunk size; the
+     * remainder is ignored). Per chunk diagnostics (optional): vit_state[c], vit_ber[c],
+     * defr_state[c] (state after the chunk), bits_out (decoded bits, 1 per byte, only for chunks
+     * that produced output) and *nbits. rs_err (optional) gets rs_i ints per written frame...
+     * Returns number of CADU bytes written to cadu_out.
+     */
+    long ref_fec_run(void *h, const int8_t *soft, long nsoft, uint8_t *cadu_out, long cadu_cap, int *vit_state, float *vit_ber, int *defr_state,
+                     uint8_t *bits_out, long *nbits, int *rs_err, long *nframes_seen)
+    {
+        RefFec *f = (RefFec *)h;
+        long outp = 0, bitp = 0, frames_seen = 0;
+        long nchunks = nsoft / f->buffer_size;
+        for (long c = 0; c < nchunks; c++)
+        {
+            memcpy(f->soft.data(), soft + c * f->buffer_size, f->buffer_size);
+            int vout = 0;
+            if (f->cfg.kind == 0)
+            {
+                vout = f->v34->work(f->soft.data(), f->buffer_size, f->viterbi_out.data());
+                if (vit_state)
+                    vit_state[c] = f->v34->getState();
+                if (vit_ber)
+                    vit_ber[c] = f->v34->ber();
+                if (vout > 0)
+                {
+                    if (bits_out)
+                        memcpy(bits_out + bitp, f->viterbi_out.data(), vout);
+                    bitp += vout;
+                    int frames = f->deframer->work(f->viterbi_out.data(), vout, f->frame_buffer.data());
+                    if (f->deframer->getState() == f->deframer->STATE_NOSYNC)
+                    {
+                        f->noSyncsRuns++;
+                        if (f->noSyncsRuns >= 10)
+                        {
+                            f->v34->reset();
+                            f->noSyncsRuns = 0;
+                        }
+                    }
+                    else
+                        f->noSyncsRuns = 0;
+                    for (int i = 0; i < frames; i++)
+                    {
+                        uint8_t *cadu = &f->frame_buffer[i * 1024];
+                        derand_ccsds(&cadu[4], 1024 - 4);
+                        f->rs->decode_interlaved(&cadu[4], true, 4, f->errors);
+                        if (rs_err)
+                            memcpy(rs_err + frames_seen * 4, f->errors, 4 * sizeof(int));
+                        frames_seen++;
+                        if (outp + 1024 <= cadu_cap)
+                        {
+                            memcpy(cadu_out + outp, cadu, 1024);
+                            outp += 1024;
+                        }
+                    }
+                }
+            }
+            else
+            {
+                const ref_fec_cfg &k = f->cfg;
+                if (k.constellation == 5 || k.iq_invert)
+                    rotate_soft(f->soft.data(), f->buffer_size, PHASE_0, true);
+                vout = f->v12->work(f->soft.data(), f->buffer_size, f->viterbi_out.data());
+                if (vit_state)
+                    vit_state[c] = f->v12->getState();
+                if (vit_ber)
+                    vit_ber[c] = f->v12->ber();
+                if (k.nrzm)
+                    f->diff.decode_bits(f->viterbi_out.data(), vout);
+                if (bits_out && vout > 0)
+                    memcpy(bits_out + bitp, f->viterbi_out.data(), vout);
+                bitp += vout;
+                int frames = f->deframer->work(f->viterbi_out.data(), vout, f->frame_buffer.data());
+                for (int i = 0; i < frames; i++)
+                {
+                    uint8_t *cadu = &f->frame_buffer[i * f->cadu_bytes];
+                    if (k.derandomize && !k.derand_after_rs)
+                        derand_ccsds(&cadu[k.derand_start], f->cadu_bytes - k.derand_start);
+                    if (k.rs_i != 0)
+                        f->rs->decode_interlaved(&cadu[4], k.rs_dualbasis, k.rs_i, f->errors);
+                    bool valid = true;
+                    for (int j = 0; j < k.rs_i; j++)
+                        if (f->errors[j] == -1)
+                            valid = false;
+                    if (k.derandomize && k.derand_after_rs)
+                        derand_ccsds(&cadu[k.derand_start], f->cadu_bytes - k.derand_start);
+                    if (rs_err)
+                        memcpy(rs_err + frames_seen * k.rs_i, f->errors, k.rs_i * sizeof(int));
+                    frames_seen++;
+                    if (!k.rs_usecheck || valid)
+                        if (outp + f->cadu_bytes <= cadu_cap)
+                        {
+                            memcpy(cadu_out + outp, cadu, f->cadu_bytes);
+                            outp += f->cadu_bytes;
+                        }
+                }
+            }
+            if (defr_state)
+                defr_state[c] = f->deframer->getState();
+        }
+        if (nbits)
+            *nbits = bitp;
+        if (nframes_seen)
+            *nframes_seen = frames_seen;
+        return outp;
+    }
+
+    /* ------------------------------------------------------------------ encoders / primitives (for the synthetic transmitter cross-check) */
+    void ref_rs_encode_interleaved(uint8_t *data, int dual, int interleave, int rs_type)
+    {
+        reedsolomon::ReedSolomon rs(rs_type == 1 ? reedsolomon::RS239 : reedsolomon::RS223);
+        rs.encode_interlaved(data, dual, interleave);
+    }
+    /* returns errors[] like ReedSolomon::decode_interlaved */
+    void ref_rs_decode_interleaved(uint8_t *data, int dual, int interleave, int rs_type, int fill_bytes, int *errors)
+    {
+        reedsolomon::ReedSolomon rs(rs_type == 1 ? reedsolomon::RS239 : reedsolomon::RS223, fill_bytes);
+        rs.decode_interlaved(data, dual, interleave, errors);
+    }
+    void ref_derand(uint8_t *data, int len) { derand_ccsds(data, len); }
+    void ref_cc_encode(const uint8_t *bits, int n, uint8_t *out /* 2n */)
+    {
+        viterbi::CCEncoder enc(n, 7, 2, {79, 109});
+        enc.work((uint8_t *)bits, out);
+    }
+    /* One CCDecoder object decoding `ncalls` consecutive frames of `frame` bits; syms holds
+     * ncalls * 2*frame symbols followed by >= 12 bytes the caller controls (tail reads). */
+    void ref_cc_decode(const uint8_t *syms, int frame, int ncalls, uint8_t *out_bits)
+    {
+        viterbi::CCDecoder dec(frame, 7, 2, {79, 109});
+        for (int c = 0; c < ncalls; c++)
+            dec.work((uint8_t *)syms + (long)c * 2 * frame, out_bits + (long)c * frame);
+    }
+    void ref_rotate_soft(int8_t *soft, int size, int phase, int iqswap) { rotate_soft(soft, size, (phase_t)phase, iqswap); }
+    int ref_deframe(const uint8_t *bits, int nbits, int cadu_size, int state_synced, uint8_t *out)
+    {
+        deframing::BPSK_CCSDS_Deframer d(cadu_size);
+        d.STATE_SYNCED = state_synced;
+        std::vector<uint8_t> tmp((size_t)(nbits / cadu_size + 2) * (cadu_size / 8 + 1) + cadu_size);
+        int total = 0;
+        /* feed in 8192-bit slices like a module would (the deframer keeps state across calls) */
+        for (int off = 0; off < nbits; off += 8192)
+        {
+            int n = std::min(8192, nbits - off);
+            int fr = d.work((uint8_t *)bits + off, n, tmp.data());
+            memcpy(out + (size_t)total * (cadu_size / 8), tmp.data(), (size_t)fr * (cadu_size / 8));
+            total += fr;
+        }
+        return total;
+    }
+
+    /* ------------------------------------------------------------------ threaded pipeline (the reference's own execution model) for CPU timing */
+    /*
+     * One std::thread per DSP block (Block::start), demod module thread, decoder thread joined by a
+     * 1 000 000-byte RingBuffer — pipeline_run.cpp:72-104. Returns wall seconds from first sample
+     * to decoder exit; *cadu_bytes gets the number of CADU bytes produced, threads_used the count.
+     */
+    double ref_pipeline_timed(const ref_demod_cfg *dc, const ref_fec_cfg *fc, const void *raw, long nsamples, uint8_t *cadu_out, long cadu_cap,
+                              long *cadu_bytes, int *threads_used)
+    {
+        RefDemod *d = (RefDemod *)ref_demod_create(dc);
+        RefFec *f = (RefFec *)ref_fec_create(fc);
+        auto fifo = std::make_shared<dsp::RingBuffer<uint8_t>>(1000000);
+        std::atomic<bool> demod_done{false};
+        std::atomic<long> out_bytes{0};
+        auto t0 = std::chrono::steady_clock::now();
+
+        d->agc->start();
+        d->rrc->start();
+        if (d->pll)
+            d->pll->start();
+        if (d->delay)
+            d->delay->start();
+        d->rec->start();
+        int nthreads = 3 + (d->pll ? 1 : 0) + (d->delay ? 1 : 0);
+
+        std::thread feeder([&]() { /* stands for FileSourceBlock::work */
+            for (long off = 0; off < nsamples; off += d->buffer_size)
+            {
+                int n = (int)std::min<long>(d->buffer_size, nsamples - off);
+                convert_block(d->cfg, raw, off, n, d->in->writeBuf);
+                if (!d->in->swap(n))
+                    break;
+            }
+        });
+        long expected_in = nsamples;
+        std::thread demod_mod([&]() { /* PSKDemodModule::process loop */
+            std::vector<int8_t> sym_buffer((size_t)d->buffer_size * 4);
+            /* we stop once the M&M block has consumed every input sample: count via omega is
+               not observable, so the feeder pads and we stop on a sentinel below */
+            while (true)
+            {
+                int m = d->rec->output_stream->read();
+                if (m <= 0)
+                    break;
+                complex_t *sym = d->rec->output_stream->readBuf;
+                int nb;
+                if (d->cfg.constellation == 0)
+                {
+                    for (int i = 0; i < m; i++)
+                        sym_buffer[i] = soft_clamp(sym[i].real * 50);
+                    nb = m;
+                }
+                else
+                {
+                    for (int i = 0; i < m; i++)
+                    {
+                        sym_buffer[i * 2] = soft_clamp(sym[i].real * 100);
+                        sym_buffer[i * 2 + 1] = soft_clamp(sym[i].imag * 100);
+                    }
+                    nb = m * 2;
+                }
+                d->rec->output_stream->flush();
+                if (fifo->write((uint8_t *)sym_buffer.data(), nb) < 0)
+                    break;
+            }
+            demod_done = true;
+        });
+        std::thread decoder([&]() {
+            std::vector<int8_t> chunk(f->buffer_size);
+            while (true)
+            {
+                if (fifo->read((uint8_t *)chunk.data(), f->buffer_size) < 0)
+                    break;
+                long w = ref_fec_run(f, chunk.data(), f->buffer_size, cadu_out + out_bytes, cadu_cap - out_bytes, 0, 0, 0, 0, 0, 0, 0);
+                out_bytes += w;
+            }
+        });
+        nthreads += 3;
+
+        feeder.join();
+        /* Wait until every block has drained: poll block idleness through stream readiness */
+        auto idle = [&]() {
+            return !d->in->getReady() && !d->agc->output_stream->getReady() && !d->rrc->output_stream->getReady() &&
+                   (!d->pll || !d->pll->output_stream->getReady()) && (!d->delay || !d->delay->output_stream->getReady()) &&
+                   !d->rec->output_stream->getReady();
+        };
+        int calm = 0;
+        while (calm < 20)
+        {
+            std::this_thread::sleep_for(std::chrono::milliseconds(1));
+            calm = idle() ? calm + 1 : 0;
+        }
+        (void)expected_in;
+        /* stop blocks like PSKDemodModule::stop() */
+        d->agc->stop();
+        d->rrc->stop();
+        if (d->pll)
+            d->pll->stop();
+        if (d->delay)
+            d->delay->stop();
+        d->rec->stop();
+        d->rec->output_stream->stopReader();
+        demod_mod.join();
+        while (fifo->getReadable() >= f->buffer_size)
+            std::this_thread::sleep_for(std::chrono::milliseconds(1));
+        fifo->stopReader();
+        fifo->stopWriter();
+        decoder.join();
+        auto t1 = std::chrono::steady_clock::now();
+        double secs = std::chrono::duration<double>(t1 - t0).count() - 0.020; /* minus the 20 ms idle-detection window */
+        if (cadu_bytes)
+            *cadu_bytes = out_bytes;
+        if (threads_used)
+            *threads_used = nthreads;
+        ref_demod_destroy(d);
+        ref_fec_destroy(f);
+        return secs;
+    }
+}

@@ -1,0 +1,311 @@
+"""Synthetic CCSDS transmitter + channel: the workload generator for tests, smoke() and bench.py.
+
+NOT part of the receive hot path (nothing here is timed or shipped as the product): it manufactures
+the baseband the hot path consumes, following SURVEY.md §8(d):
+
+  payload -> CADU (ASM 1ACFFC1D | I x RS(255,223) dual-basis, byte interleaved) -> CCSDS randomiser from byte 4
+          -> [NRZ-M] -> conv. code k=7 (polys 79,109 = the reference CCEncoder convention, cc_encoder.cpp:92-104)
+          -> [puncture 3/4 in MetOp order: inverse of viterbi_3_4.cpp:84-104] -> BPSK/QPSK/OQPSK mapping
+          -> RRC pulse shaping at a fractional samples-per-symbol -> carrier offset/phase, clock offset, AWGN
+          -> cf32 / cs16 / cs8.
+
+All coding is written from the CCSDS definitions (GF(256) poly 0x187, generator roots alpha^(11*(112+i)),
+dual basis, PN h(x)=x^8+x^7+x^5+x^3+1); tests/test_synth.py cross-checks every encoder against the
+reference's own encoders (oracle/_ref) and checks that the reference receiver recovers the payload.
+"""
+from dataclasses import dataclass, field
+
+import numpy as np
+
+ASM = bytes([0x1A, 0xCF, 0xFC, 0x1D])
+
+# ----------------------------------------------------------------------------- GF(256), RS(255,223)
+_GF_POLY = 0x187
+
+
+def _gf_tables():
+    exp = np.zeros(512, np.int32)
+    log = np.zeros(256, np.int32)
+    x = 1
+    for i in range(255):
+        exp[i] = x
+        log[x] = i
+        x <<= 1
+        if x & 0x100:
+            x ^= _GF_POLY
+    exp[255:510] = exp[0:255]
+    return exp, log
+
+
+GF_EXP, GF_LOG = _gf_tables()
+
+
+def gf_mul(a, b):
+    a = np.asarray(a, np.int32)
+    b = np.asarray(b, np.int32)
+    r = GF_EXP[(GF_LOG[a] + GF_LOG[b]) % 255]
+    return np.where((a == 0) | (b == 0), 0, r)
+
+
+def rs_generator(nroots=32, fcr=112, gap=11):
+    """g(x) = prod_i (x - alpha^(gap*(fcr+i))), returned lowest order first, g[nroots] = 1."""
+    g = np.array([1], np.int32)
+    for i in range(nroots):
+        root = GF_EXP[(gap * (fcr + i)) % 255]
+        g = np.concatenate([[0], g]) ^ np.concatenate([gf_mul(g, root), [0]])
+    return g
+
+
+# CCSDS dual-basis map is GF(2)-linear: images of the 8 unit vectors of the conventional basis
+_TO_DUAL_BASIS_IMAGES = [0x7B, 0xAF, 0x99, 0xFA, 0x86, 0xEC, 0xEF, 0x8D]
+
+
+def _dual_tables():
+    to = np.zeros(256, np.uint8)
+    for v in range(256):
+        r = 0
+        for b in range(8):
+            if v >> b & 1:
+                r ^= _TO_DUAL_BASIS_IMAGES[b]
+        to[v] = r
+    frm = np.zeros(256, np.uint8)
+    frm[to] = np.arange(256, dtype=np.uint8)
+    return to, frm
+
+
+TO_DUAL, FROM_DUAL = _dual_tables()
+
+
+def rs_encode(msg, dual=True, nroots=32):
+    """msg: (ncw, 255-nroots) uint8 -> (ncw, 255) codewords (message then parity, highest order first)."""
+    msg = np.asarray(msg, np.uint8)
+    m = FROM_DUAL[msg] if dual else msg
+    g = rs_generator(nroots, 112 if nroots == 32 else 120)
+    glog = GF_LOG[g[:nroots]][::-1].copy()  # reg[0] is the highest-order remainder coefficient
+    gz = (g[:nroots][::-1] == 0)
+    reg = np.zeros((m.shape[0], nroots), np.int32)
+    for i in range(m.shape[1]):
+        fb = m[:, i].astype(np.int32) ^ reg[:, 0]
+        reg = np.concatenate([reg[:, 1:], np.zeros((reg.shape[0], 1), np.int32)], axis=1)
+        prod = GF_EXP[(GF_LOG[fb][:, None] + glog[None, :]) % 255]
+        prod[fb == 0, :] = 0
+        prod[:, gz] = 0
+        reg ^= prod
+    cw = np.concatenate([m, reg.astype(np.uint8)], axis=1)
+    return TO_DUAL[cw] if dual else cw
+
+
+def ccsds_pn(n):
+    """CCSDS pseudo-randomiser bytes (h(x)=x^8+x^7+x^5+x^3+1, all-ones start), period 255 bytes... tiled to n."""
+    reg = [1] * 8
+    bits = []
+    for _ in range(255 * 8):
+        bits.append(reg[0])
+        nb = reg[0] ^ reg[3] ^ reg[5] ^ reg[7]
+        reg = reg[1:] + [nb]
+    pn = np.packbits(np.array(bits, np.uint8))
+    return np.resize(pn, n)
+
+
+def build_cadus(payload, interleave, dual=True, randomize=True):
+    """payload: (nframes, interleave*223) -> (nframes, 4 + interleave*255) CADUs and the clear (pre-randomiser) frames."""
+    nf = payload.shape[0]
+    msg = payload.reshape(nf, 223, interleave).transpose(0, 2, 1).reshape(nf * interleave, 223)
+    cw = rs_encode(msg, dual).reshape(nf, interleave, 255).transpose(0, 2, 1).reshape(nf, 255 * interleave)
+    clear = np.concatenate([np.tile(np.frombuffer(ASM, np.uint8), (nf, 1)), cw], axis=1)
+    tx = clear.copy()
+    if randomize:
+        tx[:, 4:] ^= ccsds_pn(255 * interleave)[None, :]
+    return tx, clear
+
+
+# ----------------------------------------------------------------------------- convolutional code
+def conv_encode(bits):
+    """k=7, polys 79 (taps 0,1,2,3,6) and 109 (taps 0,2,3,5,6), register = (state<<1)|bit, start state 0."""
+    b = np.concatenate([np.zeros(6, np.uint8), np.asarray(bits, np.uint8)])
+    n = b.size - 6
+    s = lambda k: b[6 - k:6 - k + n]
+    o0 = s(0) ^ s(1) ^ s(2) ^ s(3) ^ s(6)
+    o1 = s(0) ^ s(2) ^ s(3) ^ s(5) ^ s(6)
+    return np.stack([o0, o1], axis=1).reshape(-1)
+
+
+def puncture_34_metop(coded):
+    """From each 6 coded symbols e0..e5 transmit e0,e1,e4,e3 (inverse of Viterbi3_4::depuncture, shift=0)."""
+    n = coded.size // 6 * 6
+    e = coded[:n].reshape(-1, 6)
+    return e[:, [0, 1, 4, 3]].reshape(-1)
+
+
+def nrzm_encode(bits):
+    return (np.cumsum(bits.astype(np.int64)) & 1).astype(np.uint8)
+
+
+# ----------------------------------------------------------------------------- waveform
+def rrc_pulse(t, alpha):
+    """Unit-energy root-raised-cosine impulse response at times t (in symbols)."""
+    t = np.asarray(t, np.float64)
+    out = np.empty_like(t)
+    eps = 1e-9
+    z = np.abs(t) < eps
+    s = np.abs(np.abs(t) - 1.0 / (4 * alpha)) < eps
+    r = ~(z | s)
+    tr = t[r]
+    out[r] = (np.sin(np.pi * tr * (1 - alpha)) + 4 * alpha * tr * np.cos(np.pi * tr * (1 + alpha))) / (np.pi * tr * (1 - (4 * alpha * tr) ** 2))
+    out[z] = 1 - alpha + 4 * alpha / np.pi
+    out[s] = alpha / np.sqrt(2) * ((1 + 2 / np.pi) * np.sin(np.pi / (4 * alpha)) + (1 - 2 / np.pi) * np.cos(np.pi / (4 * alpha)))
+    return out
+
+
+@dataclass
+class SignalCfg:
+    """One of the BASELINE.json configurations."""
+    name: str = "metop_ahrpt"
+    samplerate: float = 6e6
+    symbolrate: float = 2333333
+    constellation: str = "qpsk"     # bpsk | qpsk | oqpsk
+    conv: str = "3/4"               # "1/2" | "3/4" (MetOp order) | "none"
+    interleave: int = 4             # RS interleaving depth I
+    nrzm: bool = False
+    rrc_alpha: float = 0.5
+    pll_bw: float = 0.003
+    fmt: str = "cs16"
+    esn0_db: float = 10.0
+    carrier_rad: float = 1e-3       # rad / sample
+    phase0: float = 0.7
+    clock_ppm: float = 20.0
+    rms: float = 0.25
+    clock_alpha: float = None       # M&M gains override (DVB-S2 front half uses 1.7e-3)
+    # receiver-side decoder parameters (pipeline JSON values)
+    decoder: str = "metop"          # metop | ccsds | none
+    ber_thresold: float = 0.28
+    outsync_after: int = 10
+    rs_usecheck: bool = False
+
+    @property
+    def cadu_bytes(self):
+        return 4 + 255 * self.interleave
+
+    @property
+    def sps(self):
+        return float(np.float32(np.float32(self.samplerate) / np.float32(int(self.symbolrate))))
+
+
+CONFIGS = {
+    # C1/C3: resources/pipelines/MetOp.json:30-47
+    "metop_ahrpt": SignalCfg(),
+    # C2: BPSK + r=1/2 + RS I=4 (ccsds_conv_concat_decoder), cf32 @3 MS/s, symbolrate chosen so sps=2.5
+    "bpsk_half": SignalCfg(name="bpsk_half", samplerate=3e6, symbolrate=1200000, constellation="bpsk", conv="1/2", interleave=4,
+                           fmt="cf32", decoder="ccsds", ber_thresold=0.3, outsync_after=20, esn0_db=7.0),
+    # C4: JPSS-HRD-type OQPSK r=1/2 NRZ-M RS I=5, cs16 @30 MS/s, 15 Msym/s (sps 2.0) (resources/pipelines/JPSS.json npp_hrd/jpss_hrd)
+    "jpss_hrd": SignalCfg(name="jpss_hrd", samplerate=30e6, symbolrate=15000000, constellation="oqpsk", conv="1/2", interleave=5,
+                          nrzm=True, pll_bw=0.002, fmt="cs16", decoder="ccsds", ber_thresold=0.3, outsync_after=20, rs_usecheck=True,
+                          esn0_db=7.0),
+    # C5: DVB-S2 front half AGC->RRC->M&M, cs8, 45 Msym/s @ 90 MS/s (sps 2.0), alpha 0.25 (DVB_Test.json:132-137), REC_ALPHA 1.7e-3
+    "dvbs2_front": SignalCfg(name="dvbs2_front", samplerate=90e6, symbolrate=45000000, constellation="qpsk", conv="none", interleave=4,
+                             rrc_alpha=0.25, fmt="cs8", decoder="none", clock_alpha=1.7e-3, carrier_rad=0.0, phase0=0.0, esn0_db=12.0),
+}
+
+
+def make_bitstream(cfg: SignalCfg, nframes, seed):
+    rng = np.random.default_rng(seed)
+    payload = rng.integers(0, 256, size=(nframes, cfg.interleave * 223), dtype=np.uint8)
+    tx, clear = build_cadus(payload, cfg.interleave)
+    bits = np.unpackbits(tx.reshape(-1))
+    if cfg.nrzm:
+        bits = nrzm_encode(bits)
+    if cfg.conv == "none":
+        coded = bits
+    else:
+        coded = conv_encode(bits)
+        if cfg.conv == "3/4":
+            coded = puncture_34_metop(coded)
+    return coded, clear
+
+
+def modulate(cfg: SignalCfg, coded, seed, nsamples=None, device="cpu"):
+    """coded bits -> raw IQ in cfg.fmt. Heavy lifting in torch so bench-sized signals are made on the GPU."""
+    import torch
+    dev = torch.device(device)
+    bps = 1 if cfg.constellation == "bpsk" else 2
+    nsym = coded.size // bps
+    a = torch.from_numpy((coded[:nsym * bps].astype(np.float32) * 2 - 1)).to(dev)
+    if bps == 2:
+        ai, aq = a[0::2].contiguous(), a[1::2].contiguous()
+    else:
+        ai, aq = a, None
+    sps = cfg.samplerate / cfg.symbolrate * (1.0 + cfg.clock_ppm * 1e-6)  # samples per symbol seen by the receiver
+    span = 10
+    total = int((nsym - 2 * span) * sps)
+    if nsamples is None or nsamples > total:
+        nsamples = total
+    # pulse table, 1/2048-symbol grid, linear interpolation
+    res = 2048
+    tgrid = np.arange(-span * res, span * res + 2) / res
+    tab = torch.from_numpy(rrc_pulse(tgrid, cfg.rrc_alpha).astype(np.float32)).to(dev)
+    out_i = torch.empty(nsamples, dtype=torch.float32, device=dev)
+    out_q = torch.empty(nsamples, dtype=torch.float32, device=dev)
+    step = 1 << 20
+    qoff = 0.5 if cfg.constellation == "oqpsk" else 0.0
+
+    def shape(sym, t):  # t: symbol-time of each output sample (float64)
+        k0 = torch.floor(t)
+        d = (t - k0)  # [0,1)
+        k0 = k0.to(torch.int64)
+        pos = d * res
+        pb = torch.floor(pos)
+        fr = (pos - pb).to(torch.float32)
+        pb = pb.to(torch.int64)
+        acc = torch.zeros(t.shape, dtype=torch.float32, device=t.device)
+        for j in range(-span + 1, span + 1):
+            p0 = pb + (span - j) * res  # table index of (t - (k0 + j)) on the 1/res grid
+            h = tab[p0] * (1 - fr) + tab[p0 + 1] * fr
+            acc += sym[k0 + j] * h
+        return acc
+
+    for s in range(0, nsamples, step):
+        e = min(nsamples, s + step)
+        n = torch.arange(s, e, device=dev, dtype=torch.float64)
+        t = n / sps + span + 0.37
+        out_i[s:e] = shape(ai, t)
+        if aq is not None:
+            out_q[s:e] = shape(aq, t - qoff)
+        else:
+            out_q[s:e] = 0
+    x = torch.complex(out_i, out_q)
+    p = float((x.real ** 2 + x.imag ** 2).mean())
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(int(seed) + 7)
+    sigma2 = p * (cfg.samplerate / cfg.symbolrate) / (10 ** (cfg.esn0_db / 10))
+    for s in range(0, nsamples, step * 8):
+        e = min(nsamples, s + step * 8)
+        n = torch.arange(s, e, device=dev, dtype=torch.float64)
+        ph = (cfg.carrier_rad * n + cfg.phase0) % (2 * np.pi)
+        rot = torch.complex(torch.cos(ph).float(), torch.sin(ph).float())
+        noise = torch.randn(e - s, 2, generator=gen, device=dev, dtype=torch.float32) * float(np.sqrt(sigma2 / 2))
+        x[s:e] = x[s:e] * rot + torch.complex(noise[:, 0], noise[:, 1])
+    scale = cfg.rms / float(np.sqrt(p + sigma2))
+    x = x * scale
+    v = torch.view_as_real(x).reshape(-1)
+    if cfg.fmt == "cf32":
+        return torch.view_as_complex(v.reshape(-1, 2).contiguous())
+    if cfg.fmt == "cs16":
+        return torch.clamp(torch.round(v * 32767), -32767, 32767).to(torch.int16)
+    if cfg.fmt == "cs8":
+        return torch.clamp(torch.round(v * 127), -127, 127).to(torch.int8)
+    raise ValueError(cfg.fmt)
+
+
+def frames_for_samples(cfg: SignalCfg, nsamples):
+    bps = 1 if cfg.constellation == "bpsk" else 2
+    rate = {"1/2": 0.5, "3/4": 0.75, "none": 1.0}[cfg.conv]
+    bits_per_sample = bps * rate / (cfg.samplerate / cfg.symbolrate)
+    return int(nsamples * bits_per_sample / (cfg.cadu_bytes * 8)) + 4
+
+
+def make_signal(cfg: SignalCfg, nsamples, seed=0xB2000000, device="cpu"):
+    """Returns (raw torch tensor in cfg.fmt with exactly <= nsamples samples, clear CADUs (nframes, cadu_bytes) numpy)."""
+    nframes = frames_for_samples(cfg, nsamples)
+    coded, clear = make_bitstream(cfg, nframes, seed)
+    raw = modulate(cfg, coded, seed, nsamples, device)
+    return raw, clear
