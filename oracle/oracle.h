@@ -1,0 +1,74 @@
+/*
+ * TEST INFRASTRUCTURE ONLY — the CPU oracle ("port") for the B200 baseband->CADU hot path.
+ *
+ * A from-scratch C restatement of the algorithms of the reference's CPU path. Every function cites
+ * the reference file:line whose behaviour it follows. It is pinned bit-for-bit against the reference's
+ * own code compiled into oracle/_ref (tests/test_oracle_*.py) and against tests/golden fixtures made
+ * from it. Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+ * may load this; the product (libb200dsp.so) never does.
+ */
+#ifndef ORACLE_H
+#define ORACLE_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct
+{
+    double samplerate, symbolrate;
+    int constellation; /* 0 bpsk, 1 qpsk, 2 oqpsk, 3 8psk, 4 none (AGC->RRC->M&M only) */
+    float rrc_alpha;
+    int rrc_taps;
+    float pll_bw, agc_rate;
+    float clock_gain_omega, clock_mu, clock_gain_mu, clock_omega_limit;
+    float costas_max_offset;
+    int format; /* 0 cf32, 1 cs16, 2 cs8 */
+    int buffer_size;
+} orc_demod_cfg;
+
+typedef struct
+{
+    int kind;          /* 0 metop_ahrpt_decoder, 1 ccsds_conv_concat_decoder r=1/2 */
+    int constellation; /* 0 bpsk, 1 qpsk, 2 oqpsk, 5 bpsk_90 */
+    int cadu_size, outsync_after;
+    float ber_thresold;
+    int nrzm, derandomize, derand_after_rs, derand_start;
+    int rs_i, rs_dualbasis, rs_fill_bytes, rs_usecheck, rs_type;
+    int iq_invert;
+    unsigned int asm_sync;
+} orc_fec_cfg;
+
+int orc_rrc_taps(double gain, double fs, double rs, double alpha, int ntaps, float *out);
+void orc_mm_bank(float *out /* 128*8 */);
+
+void *orc_demod_create(const orc_demod_cfg *cfg);
+void orc_demod_destroy(void *h);
+float orc_demod_sps(void *h);
+long orc_demod_run(void *h, const void *raw, long nsamples, float *agc_out, float *fir_out, float *costas_out, float *mm_out,
+                   int8_t *soft_out, long sym_cap);
+void orc_demod_state(void *h, float *out8);
+
+void *orc_fec_create(const orc_fec_cfg *cfg);
+void orc_fec_destroy(void *h);
+int orc_fec_chunk_size(void *h);
+int orc_fec_cadu_bytes(void *h);
+long orc_fec_run(void *h, const int8_t *soft, long nsoft, uint8_t *cadu_out, long cadu_cap, int *vit_state, float *vit_ber,
+                 int *defr_state, uint8_t *bits_out, long *nbits, int *rs_err, long *nframes_seen);
+
+/* primitives for stage-isolated checks */
+void orc_cc_decode(const uint8_t *syms, int frame, int ncalls, uint8_t *out_bits);
+void orc_cc_encode(const uint8_t *bits, int n, uint8_t *out);
+void orc_derand(uint8_t *data, int len);
+void orc_rs_decode_interleaved(uint8_t *data, int dual, int interleave, int rs_type, int fill_bytes, int *errors);
+int orc_deframe(const uint8_t *bits, int nbits, int cadu_size, int state_synced, uint8_t *out);
+void orc_rotate_soft(int8_t *soft, int size, int phase, int iqswap);
+
+/* single-thread end-to-end (demod + FEC) used as the CPU "port" baseline; returns CADU bytes */
+long orc_pipeline_run(const orc_demod_cfg *dc, const orc_fec_cfg *fc, const void *raw, long nsamples, uint8_t *cadu_out, long cadu_cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -7,6 +7,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _PATH = os.path.join(_HERE, "_ref", "libsatref.so")
+_PFX = "ref_"
 
 CONST = {"bpsk": 0, "qpsk": 1, "oqpsk": 2, "8psk": 3, "none": 4, "bpsk_90": 5}
 FMT = {"cf32": 0, "cs16": 1, "cs8": 2}
@@ -27,6 +28,23 @@ class FecCfg(C.Structure):
                 ("rs_usecheck", C.c_int), ("rs_type", C.c_int), ("iq_invert", C.c_int), ("asm_sync", C.c_uint)]
 
 
+class _Prefixed:
+    """Resolve ref_xxx names against a library exporting <prefix>xxx (shared by oracle.ref and oracle.port)."""
+
+    def __init__(self, cdll, prefix):
+        self._l, self._p = cdll, prefix
+
+    def __getattr__(self, name):
+        if name.startswith("ref_"):
+            try:
+                f = getattr(self._l, self._p + name[4:])
+            except AttributeError:
+                raise AttributeError(name)
+            setattr(self, name, f)
+            return f
+        raise AttributeError(name)
+
+
 def available():
     return os.path.exists(_PATH)
 
@@ -37,7 +55,7 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        L = C.CDLL(_PATH)
+        L = _Prefixed(C.CDLL(_PATH), _PFX)
         L.ref_demod_create.restype = C.c_void_p
         L.ref_demod_create.argtypes = [C.POINTER(DemodCfg)]
         L.ref_demod_destroy.argtypes = [C.c_void_p]
