@@ -1,0 +1,156 @@
+/*
+ * b200dsp — C ABI of the B200-native (sm_100a) SatDump baseband -> CADU hot path.
+ *
+ * This is the boundary a SatDump plugin binds (INTEGRATION.md shows the ProcessingModule shim). It
+ * sits one level below SatDump's C++ plugin ABI so that the CUDA library is independent of the host
+ * compiler / STL: plain pointers, sizes and POD structs only, caller-owned host buffers, opaque handles.
+ *
+ * Each entry point names the reference interface it replaces (paths relative to the SatDump tree):
+ *
+ *   b200_demod_*   the DSP chain PSKDemodModule builds and runs
+ *                    src-core/pipeline/modules/demod/module_psk_demod.cpp:86-236   (init / process)
+ *                    src-core/pipeline/modules/demod/module_demod_base.cpp:59-208   (initb: source, AGC)
+ *                    plugins/dvb_support/dvbs2/module_dvbs2_demod.cpp:98-102        (AGC->RRC->M&M front half; constellation NONE)
+ *   b200_fec_*     the decoder modules
+ *                    plugins/noaa_metop_support/metop/module_metop_ahrpt_decoder.cpp:34-90      (kind METOP)
+ *                    src-core/pipeline/modules/ccsds/module_ccsds_conv_concat_decoder.cpp:140-200 (kind CCSDS, r=1/2)
+ *   b200_chain_*   both modules joined the way Pipeline::run joins them with a byte FIFO
+ *                    src-core/pipeline/pipeline_run.cpp:44-117 — here the int8 soft stream never leaves HBM.
+ *
+ * All functions return 0 on success or a negative B200_E* code; b200_last_error() gives the text.
+ * There is no CPU fallback: without a CUDA device every create() fails with B200_ENODEV.
+ */
+#ifndef B200DSP_H
+#define B200DSP_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_OK 0
+#define B200_EINVAL -1     /* bad / unsupported parameter (the C++ module turns this into satdump_exception) */
+#define B200_ENODEV -2     /* no CUDA device / wrong architecture */
+#define B200_ECUDA -3      /* CUDA runtime failure */
+#define B200_ENOMEM -4
+#define B200_ESTATE -5     /* e.g. pull before push, batch larger than max_batch */
+#define B200_EUNSUPPORTED -6 /* signal condition the parallel formulation does not cover (AGC gain clamp hit, ...) */
+
+/* constellation (module param "constellation", module_psk_demod.cpp:17-21; NONE = no Costas loop) */
+enum { B200_BPSK = 0, B200_QPSK = 1, B200_OQPSK = 2, B200_8PSK = 3, B200_NONE = 4, B200_BPSK_90 = 5 };
+/* baseband_format (common/dsp/io/baseband_type.h:7-21) */
+enum { B200_CF32 = 0, B200_CS16 = 1, B200_CS8 = 2 };
+/* decoder kind */
+enum { B200_FEC_METOP = 0, B200_FEC_CCSDS = 1 };
+/* debug stage ids for b200_demod_debug_stage */
+enum { B200_STAGE_AGC = 0, B200_STAGE_FIR = 1, B200_STAGE_COSTAS = 2 };
+
+typedef struct b200_demod_cfg
+{
+    double samplerate;        /* "samplerate"  (module_demod_base.cpp:17-20)                     */
+    double symbolrate;        /* "symbolrate"  (:26-27)                                          */
+    int constellation;        /* "constellation"                                                 */
+    float rrc_alpha;          /* "rrc_alpha"   (module_psk_demod.cpp:23-26)                      */
+    int rrc_taps;             /* "rrc_taps", default 31 (module_psk_demod.h:31); only 31 built   */
+    float pll_bw;             /* "pll_bw"                                                        */
+    float agc_rate;           /* "agc_rate", default 1e-2 (module_demod_base.h:54)               */
+    float clock_gain_omega;   /* default pow(8.7e-3,2)/4 (module_psk_demod.h:36)                 */
+    float clock_mu;           /* default 0.5                                                     */
+    float clock_gain_mu;      /* default 8.7e-3                                                  */
+    float clock_omega_limit;  /* "clock_omega_relative_limit", default 0.005                     */
+    float costas_max_offset;  /* rad/sample, default 1.0 (module_psk_demod.cpp:116-118)          */
+    int format;               /* "baseband_format": B200_CF32 / CS16 / CS8                       */
+    int device;               /* CUDA device ordinal                                             */
+    long max_batch;           /* largest nsamples of one push (device buffers are sized for it)  */
+    int keep_stages;          /* !=0: keep AGC/FIR/Costas stage outputs for b200_demod_debug_stage */
+} b200_demod_cfg;
+
+typedef struct b200_fec_cfg
+{
+    int kind;                 /* B200_FEC_METOP | B200_FEC_CCSDS                                 */
+    int constellation;        /* ccsds: B200_BPSK / BPSK_90 / QPSK / OQPSK                       */
+    int cadu_size;            /* bits ("cadu_size"); METOP: 8192                                 */
+    int outsync_after;        /* "viterbi_outsync_after"                                         */
+    float ber_thresold;       /* "viterbi_ber_thresold"                                          */
+    int nrzm, derandomize, derand_after_rs, derand_start;
+    int rs_i, rs_dualbasis, rs_fill_bytes, rs_usecheck, rs_type;
+    int iq_invert;
+    unsigned int asm_sync;    /* "asm", default 0x1ACFFC1D                                       */
+    int device;
+    long max_soft;            /* largest number of soft bytes of one push                        */
+} b200_fec_cfg;
+
+typedef struct b200_demod_stats
+{
+    long samples_in, symbols_out;
+    float agc_gain, costas_phase, costas_freq, mm_mu, mm_omega;
+    long costas_unconverged;  /* segment junctions whose warm-up had not converged (expected 0)  */
+    long mm_unconverged;      /* M&M segment junctions that disagreed (expected 0)               */
+    int agc_clamped;          /* AGC hit max_gain: outside the parallel formulation              */
+    long kernel_launches;     /* CUDA kernels launched by this object so far                     */
+} b200_demod_stats;
+
+typedef struct b200_fec_stats
+{
+    long soft_in, chunks, bits_out, frames_out;
+    int viterbi_state;        /* 0 NOSYNC 1 SYNCED  (Viterbi3_4::getState)                       */
+    float viterbi_ber;
+    int deframer_state;       /* 2 NOSYNC / 6 SYNCING / 12|18 SYNCED (BPSK_CCSDS_Deframer)       */
+    long rs_corrected, rs_failed;
+    long replays;             /* slow-path re-decodes (lock changes, start-state mis-speculation) */
+    long kernel_launches;
+} b200_fec_stats;
+
+typedef struct b200_demod b200_demod;
+typedef struct b200_fec b200_fec;
+typedef struct b200_chain b200_chain;
+
+const char *b200_last_error(void);
+int b200_device_count(void);
+
+/* ---- demodulator: raw IQ -> soft symbols ---------------------------------------------------------- */
+b200_demod *b200_demod_create(const b200_demod_cfg *cfg);
+void b200_demod_destroy(b200_demod *d);
+/* One batch of the stream from HOST memory (copied to the device inside the call). Loop state carries over. */
+int b200_demod_push_iq(b200_demod *d, const void *host_iq, long nsamples);
+/* Same, samples already in device memory of cfg.device (no copy). */
+int b200_demod_push_iq_device(b200_demod *d, const void *dev_iq, long nsamples);
+/* int8 soft symbols of the LAST push (I,Q interleaved; BPSK: I only) — the bytes PSKDemodModule writes to .soft / the FIFO */
+int b200_demod_pull_soft(b200_demod *d, int8_t *host_out, long cap, long *n_out);
+/* float symbols of the LAST push (M&M output, interleaved re,im) */
+int b200_demod_pull_symbols(b200_demod *d, float *host_out, long cap_symbols, long *n_out);
+/* stage outputs of the LAST push (needs keep_stages): nsamples complex values, interleaved re,im */
+int b200_demod_debug_stage(b200_demod *d, int stage, float *host_out, long cap_samples);
+int b200_demod_get_stats(b200_demod *d, b200_demod_stats *out);
+/* RRC taps / M&M polyphase bank as designed on the host (for parity tests against firdes / PolyphaseBank) */
+int b200_demod_get_taps(b200_demod *d, float *rrc_out, int rrc_cap, float *bank_out /* 128*8 or NULL */);
+
+/* ---- decoder: soft symbols -> CADUs --------------------------------------------------------------- */
+b200_fec *b200_fec_create(const b200_fec_cfg *cfg);
+void b200_fec_destroy(b200_fec *f);
+int b200_fec_push_soft(b200_fec *f, const int8_t *host_soft, long n);
+int b200_fec_push_soft_device(b200_fec *f, const int8_t *dev_soft, long n);
+/* frames completed by the pushes since the last pull, cadu_bytes each, in stream order */
+int b200_fec_pull_frames(b200_fec *f, uint8_t *host_out, long cap, long *nbytes_out);
+/* Viterbi output bits (1 bit per byte, after NRZ-M when enabled) of the LAST push, for stage tests */
+int b200_fec_debug_bits(b200_fec *f, uint8_t *host_out, long cap, long *n_out);
+int b200_fec_get_stats(b200_fec *f, b200_fec_stats *out);
+int b200_fec_cadu_bytes(b200_fec *f);
+int b200_fec_chunk_size(b200_fec *f);
+
+/* ---- fused chain: raw IQ -> CADUs, soft stream stays in HBM ---------------------------------------- */
+b200_chain *b200_chain_create(const b200_demod_cfg *dcfg, const b200_fec_cfg *fcfg);
+void b200_chain_destroy(b200_chain *c);
+int b200_chain_push_iq(b200_chain *c, const void *host_iq, long nsamples);
+int b200_chain_push_iq_device(b200_chain *c, const void *dev_iq, long nsamples);
+int b200_chain_pull_frames(b200_chain *c, uint8_t *host_out, long cap, long *nbytes_out);
+/* device-resident result access (no D2H): pointer to the frames produced since the last pull/reset */
+int b200_chain_frames_device(b200_chain *c, const uint8_t **dev_ptr, long *nbytes);
+int b200_chain_get_stats(b200_chain *c, b200_demod_stats *ds, b200_fec_stats *fs);
+/* timing taps used by bench.py: elapsed device milliseconds of the last push per stage (CUDA events on the chain's stream) */
+int b200_chain_last_timing(b200_chain *c, float *ms_out, int n); /* [0]=total [1]=agc+fir [2]=costas [3]=m&m [4]=viterbi [5]=deframe+rs */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,311 @@
+"""ctypes binding of the C ABI in include/b200dsp.h (libb200dsp.so, built in satdump_b200/csrc).
+
+This is the same boundary a SatDump plugin links; Python is only the test/bench driver.
+There is no fallback of any kind: if the library is missing the import of `lib()` raises, and without a B200 every
+create() fails with B200_ENODEV.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libb200dsp.so")
+
+CONST = {"bpsk": 0, "qpsk": 1, "oqpsk": 2, "8psk": 3, "none": 4, "bpsk_90": 5}
+FMT = {"cf32": 0, "cs16": 1, "cs8": 2}
+FMT_BYTES = {0: 8, 1: 4, 2: 2}
+E_NAMES = {0: "OK", -1: "EINVAL", -2: "ENODEV", -3: "ECUDA", -4: "ENOMEM", -5: "ESTATE", -6: "EUNSUPPORTED"}
+
+# every symbol include/b200dsp.h declares (tests check the built library exports all of them)
+SYMBOLS = [
+    "b200_last_error", "b200_device_count",
+    "b200_demod_create", "b200_demod_destroy", "b200_demod_push_iq", "b200_demod_push_iq_device", "b200_demod_pull_soft",
+    "b200_demod_pull_symbols", "b200_demod_debug_stage", "b200_demod_get_stats", "b200_demod_get_taps",
+    "b200_fec_create", "b200_fec_destroy", "b200_fec_push_soft", "b200_fec_push_soft_device", "b200_fec_pull_frames",
+    "b200_fec_debug_bits", "b200_fec_get_stats", "b200_fec_cadu_bytes", "b200_fec_chunk_size",
+    "b200_chain_create", "b200_chain_destroy", "b200_chain_push_iq", "b200_chain_push_iq_device", "b200_chain_pull_frames",
+    "b200_chain_frames_device", "b200_chain_get_stats", "b200_chain_last_timing",
+]
+
+
+class DemodCfg(C.Structure):
+    _fields_ = [("samplerate", C.c_double), ("symbolrate", C.c_double), ("constellation", C.c_int), ("rrc_alpha", C.c_float),
+                ("rrc_taps", C.c_int), ("pll_bw", C.c_float), ("agc_rate", C.c_float), ("clock_gain_omega", C.c_float),
+                ("clock_mu", C.c_float), ("clock_gain_mu", C.c_float), ("clock_omega_limit", C.c_float),
+                ("costas_max_offset", C.c_float), ("format", C.c_int), ("device", C.c_int), ("max_batch", C.c_long),
+                ("keep_stages", C.c_int)]
+
+
+class FecCfg(C.Structure):
+    _fields_ = [("kind", C.c_int), ("constellation", C.c_int), ("cadu_size", C.c_int), ("outsync_after", C.c_int),
+                ("ber_thresold", C.c_float), ("nrzm", C.c_int), ("derandomize", C.c_int), ("derand_after_rs", C.c_int),
+                ("derand_start", C.c_int), ("rs_i", C.c_int), ("rs_dualbasis", C.c_int), ("rs_fill_bytes", C.c_int),
+                ("rs_usecheck", C.c_int), ("rs_type", C.c_int), ("iq_invert", C.c_int), ("asm_sync", C.c_uint),
+                ("device", C.c_int), ("max_soft", C.c_long)]
+
+
+class DemodStats(C.Structure):
+    _fields_ = [("samples_in", C.c_long), ("symbols_out", C.c_long), ("agc_gain", C.c_float), ("costas_phase", C.c_float),
+                ("costas_freq", C.c_float), ("mm_mu", C.c_float), ("mm_omega", C.c_float), ("costas_unconverged", C.c_long),
+                ("mm_unconverged", C.c_long), ("agc_clamped", C.c_int), ("kernel_launches", C.c_long)]
+
+
+class FecStats(C.Structure):
+    _fields_ = [("soft_in", C.c_long), ("chunks", C.c_long), ("bits_out", C.c_long), ("frames_out", C.c_long),
+                ("viterbi_state", C.c_int), ("viterbi_ber", C.c_float), ("deframer_state", C.c_int), ("rs_corrected", C.c_long),
+                ("rs_failed", C.c_long), ("replays", C.c_long), ("kernel_launches", C.c_long)]
+
+
+class B200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"{E_NAMES.get(code, code)}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` (no fallback exists)")
+        L = C.CDLL(LIB_PATH)
+        vp, ci, cl = C.c_void_p, C.c_int, C.c_long
+        L.b200_last_error.restype = C.c_char_p
+        L.b200_demod_create.restype = vp
+        L.b200_demod_create.argtypes = [C.POINTER(DemodCfg)]
+        L.b200_demod_destroy.argtypes = [vp]
+        L.b200_demod_push_iq.argtypes = [vp, vp, cl]
+        L.b200_demod_push_iq_device.argtypes = [vp, vp, cl]
+        L.b200_demod_pull_soft.argtypes = [vp, vp, cl, C.POINTER(cl)]
+        L.b200_demod_pull_symbols.argtypes = [vp, vp, cl, C.POINTER(cl)]
+        L.b200_demod_debug_stage.argtypes = [vp, ci, vp, cl]
+        L.b200_demod_get_stats.argtypes = [vp, C.POINTER(DemodStats)]
+        L.b200_demod_get_taps.argtypes = [vp, vp, ci, vp]
+        L.b200_fec_create.restype = vp
+        L.b200_fec_create.argtypes = [C.POINTER(FecCfg)]
+        L.b200_fec_destroy.argtypes = [vp]
+        L.b200_fec_push_soft.argtypes = [vp, vp, cl]
+        L.b200_fec_push_soft_device.argtypes = [vp, vp, cl]
+        L.b200_fec_pull_frames.argtypes = [vp, vp, cl, C.POINTER(cl)]
+        L.b200_fec_debug_bits.argtypes = [vp, vp, cl, C.POINTER(cl)]
+        L.b200_fec_get_stats.argtypes = [vp, C.POINTER(FecStats)]
+        L.b200_fec_cadu_bytes.argtypes = [vp]
+        L.b200_fec_chunk_size.argtypes = [vp]
+        L.b200_chain_create.restype = vp
+        L.b200_chain_create.argtypes = [C.POINTER(DemodCfg), C.POINTER(FecCfg)]
+        L.b200_chain_destroy.argtypes = [vp]
+        L.b200_chain_push_iq.argtypes = [vp, vp, cl]
+        L.b200_chain_push_iq_device.argtypes = [vp, vp, cl]
+        L.b200_chain_pull_frames.argtypes = [vp, vp, cl, C.POINTER(cl)]
+        L.b200_chain_frames_device.argtypes = [vp, C.POINTER(vp), C.POINTER(cl)]
+        L.b200_chain_get_stats.argtypes = [vp, C.POINTER(DemodStats), C.POINTER(FecStats)]
+        L.b200_chain_last_timing.argtypes = [vp, vp, ci]
+        _lib = L
+    return _lib
+
+
+def last_error():
+    return lib().b200_last_error().decode()
+
+
+def _chk(rc):
+    if rc != 0:
+        raise B200Error(rc, last_error())
+
+
+def demod_cfg(samplerate, symbolrate, constellation, rrc_alpha, pll_bw=0.003, fmt="cs16", rrc_taps=31, agc_rate=1e-2, clock_alpha=None,
+              clock_gain_omega=None, clock_mu=0.5, clock_gain_mu=8.7e-3, clock_omega_limit=0.005, costas_max_offset=1.0, device=0,
+              max_batch=1 << 24, keep_stages=False):
+    """Parameter defaults = module_psk_demod.h:31-39, module_demod_base.h:54."""
+    if clock_alpha is not None:
+        clock_gain_omega = float(np.float32(clock_alpha) ** 2 / 4.0)
+        clock_gain_mu = clock_alpha
+    if clock_gain_omega is None:
+        clock_gain_omega = float(np.float32(pow(8.7e-3, 2) / 4.0))
+    return DemodCfg(float(samplerate), float(symbolrate), CONST[constellation], rrc_alpha, rrc_taps, pll_bw, agc_rate, clock_gain_omega,
+                    clock_mu, clock_gain_mu, clock_omega_limit, costas_max_offset, FMT[fmt], device, max_batch, int(keep_stages))
+
+
+def metop_cfg(ber_thresold=0.28, outsync_after=10, device=0, max_soft=1 << 24):
+    return FecCfg(0, 1, 8192, outsync_after, ber_thresold, 0, 1, 0, 4, 4, 1, -1, 0, 0, 0, 0x1ACFFC1D, device, max_soft)
+
+
+def ccsds_cfg(constellation, cadu_size, ber_thresold, outsync_after, rs_i, nrzm=False, derandomize=True, rs_usecheck=False, rs_dualbasis=True,
+              rs_fill_bytes=-1, derand_after_rs=False, derand_start=4, iq_invert=False, rs_type=0, asm_sync=0x1ACFFC1D, device=0,
+              max_soft=1 << 24):
+    return FecCfg(1, CONST[constellation], cadu_size, outsync_after, ber_thresold, int(nrzm), int(derandomize), int(derand_after_rs),
+                  derand_start, rs_i, int(rs_dualbasis), rs_fill_bytes, int(rs_usecheck), rs_type, int(iq_invert), asm_sync, device, max_soft)
+
+
+def _nsamples(raw, fmt):
+    raw = np.ascontiguousarray(raw)
+    if fmt == 0:
+        return raw, (raw.size if np.iscomplexobj(raw) else raw.size // 2)
+    return raw, raw.size // 2
+
+
+def _struct_dict(s):
+    return {k: getattr(s, k) for k, _ in s._fields_}
+
+
+class Demod:
+    """Host mirror of PSKDemodModule's DSP chain for one stream (module_psk_demod.cpp:86-236)."""
+
+    def __init__(self, cfg):
+        self.cfg = cfg
+        self.h = lib().b200_demod_create(C.byref(cfg))
+        if not self.h:
+            raise B200Error(-1 if "device" not in last_error().lower() else -2, last_error())
+        self.bps = 1 if cfg.constellation == 0 else 2
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().b200_demod_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def push(self, raw):
+        raw, n = _nsamples(raw, self.cfg.format)
+        _chk(lib().b200_demod_push_iq(self.h, raw.ctypes.data, n))
+        self._n = n
+        return self
+
+    def push_device(self, ptr, n):
+        _chk(lib().b200_demod_push_iq_device(self.h, ptr, n))
+        self._n = n
+        return self
+
+    def soft(self):
+        cap = int(self._n * self.bps) + 1024
+        out = np.zeros(cap, np.int8)
+        n = C.c_long(0)
+        _chk(lib().b200_demod_pull_soft(self.h, out.ctypes.data, cap, C.byref(n)))
+        return out[:n.value].copy()
+
+    def symbols(self):
+        cap = int(self._n) + 1024
+        out = np.zeros(cap, np.complex64)
+        n = C.c_long(0)
+        _chk(lib().b200_demod_pull_symbols(self.h, out.ctypes.data, cap, C.byref(n)))
+        return out[:n.value].copy()
+
+    def stage(self, which):
+        out = np.zeros(self._n, np.complex64)
+        _chk(lib().b200_demod_debug_stage(self.h, {"agc": 0, "fir": 1, "costas": 2}[which], out.ctypes.data, self._n))
+        return out
+
+    def stats(self):
+        s = DemodStats()
+        _chk(lib().b200_demod_get_stats(self.h, C.byref(s)))
+        return _struct_dict(s)
+
+    def taps(self):
+        rrc = np.zeros(64, np.float32)
+        bank = np.zeros(128 * 8, np.float32)
+        _chk(lib().b200_demod_get_taps(self.h, rrc.ctypes.data, 64, bank.ctypes.data))
+        return rrc[:self.cfg.rrc_taps | 1].copy(), bank.reshape(128, 8)
+
+
+class Fec:
+    """Host mirror of MetOpAHRPTDecoderModule / CCSDSConvConcatDecoderModule for one stream."""
+
+    def __init__(self, cfg):
+        self.cfg = cfg
+        self.h = lib().b200_fec_create(C.byref(cfg))
+        if not self.h:
+            raise B200Error(-1 if "device" not in last_error().lower() else -2, last_error())
+        self.cadu_bytes = lib().b200_fec_cadu_bytes(self.h)
+        self.chunk = lib().b200_fec_chunk_size(self.h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().b200_fec_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def push(self, soft):
+        soft = np.ascontiguousarray(soft, np.int8)
+        _chk(lib().b200_fec_push_soft(self.h, soft.ctypes.data, soft.size))
+        self._n = soft.size
+        return self
+
+    def frames(self):
+        cap = int(self._n) + 65536
+        out = np.zeros(cap, np.uint8)
+        n = C.c_long(0)
+        _chk(lib().b200_fec_pull_frames(self.h, out.ctypes.data, cap, C.byref(n)))
+        return out[:n.value].reshape(-1, self.cadu_bytes).copy()
+
+    def bits(self):
+        cap = int(self._n) + self.chunk
+        out = np.zeros(cap, np.uint8)
+        n = C.c_long(0)
+        _chk(lib().b200_fec_debug_bits(self.h, out.ctypes.data, cap, C.byref(n)))
+        return out[:n.value].copy()
+
+    def stats(self):
+        s = FecStats()
+        _chk(lib().b200_fec_get_stats(self.h, C.byref(s)))
+        return _struct_dict(s)
+
+
+class Chain:
+    """Demodulator + decoder of one stream on one GPU; the soft stream stays in HBM."""
+
+    def __init__(self, dcfg, fcfg):
+        self.dcfg, self.fcfg = dcfg, fcfg
+        self.h = lib().b200_chain_create(C.byref(dcfg), C.byref(fcfg))
+        if not self.h:
+            raise B200Error(-1 if "device" not in last_error().lower() else -2, last_error())
+        self.cadu_bytes = (fcfg.cadu_size + 7) // 8 if fcfg.kind == 1 else 1024
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().b200_chain_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def push(self, raw):
+        raw, n = _nsamples(raw, self.dcfg.format)
+        _chk(lib().b200_chain_push_iq(self.h, raw.ctypes.data, n))
+        self._n = n
+        return self
+
+    def push_ptr(self, host_ptr, n):
+        _chk(lib().b200_chain_push_iq(self.h, host_ptr, n))
+        self._n = n
+        return self
+
+    def push_device(self, dev_ptr, n):
+        _chk(lib().b200_chain_push_iq_device(self.h, dev_ptr, n))
+        self._n = n
+        return self
+
+    def frames(self, cap=None):
+        cap = cap or int(self._n) + 65536
+        out = np.zeros(cap, np.uint8)
+        n = C.c_long(0)
+        _chk(lib().b200_chain_pull_frames(self.h, out.ctypes.data, cap, C.byref(n)))
+        return out[:n.value].reshape(-1, self.cadu_bytes).copy()
+
+    def frames_device(self):
+        p = C.c_void_p(0)
+        n = C.c_long(0)
+        _chk(lib().b200_chain_frames_device(self.h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def stats(self):
+        d, f = DemodStats(), FecStats()
+        _chk(lib().b200_chain_get_stats(self.h, C.byref(d), C.byref(f)))
+        return _struct_dict(d), _struct_dict(f)
+
+    def timing(self):
+        ms = np.zeros(6, np.float32)
+        _chk(lib().b200_chain_last_timing(self.h, ms.ctypes.data, 6))
+        return dict(zip(["total", "agc_fir", "costas", "mm", "viterbi", "deframe_rs"], ms.tolist()))

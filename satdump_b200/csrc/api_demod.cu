@@ -1,0 +1,435 @@
+// C ABI + host driver of the demodulator (see include/b200dsp.h, demod_host.h).
+#define B200_DEFINE_KERNELS
+#include "demod_host.h"
+#include <algorithm>
+#include <cmath>
+#include <mutex>
+
+namespace b200
+{
+static thread_local std::string g_err;
+void set_error(const char *fmt, ...)
+{
+    char b[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(b, sizeof(b), fmt, ap);
+    va_end(ap);
+    g_err = b;
+}
+const char *last_error_cstr() { return g_err.c_str(); }
+
+void check_device(int device)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        throw ApiError(B200_ENODEV, std::string("no CUDA device: ") + cudaGetErrorString(e) + " (this library has no CPU fallback)");
+    if (device < 0 || device >= n)
+        throw ApiError(B200_ENODEV, "CUDA device ordinal out of range");
+    cudaDeviceProp p;
+    B200_CUDA(cudaGetDeviceProperties(&p, device));
+    if (p.major != 10)
+        throw ApiError(B200_ENODEV, std::string("device ") + p.name + " is not sm_100: the kernels are built for sm_100a only");
+}
+
+// Root-raised-cosine design, double precision, odd length, normalised to unit DC gain.
+// Formula and evaluation order follow firdes::root_raised_cosine (src-core/common/dsp/filter/firdes.cpp:34-78) so the
+// float taps come out identical.
+void design_rrc(double gain, double fs, double rs, double alpha, int ntaps, std::vector<float> &out)
+{
+    ntaps |= 1;
+    out.assign(ntaps, 0.f);
+    const double spb = fs / rs;
+    double sum = 0;
+    for (int i = 0; i < ntaps; i++) {
+        const double xi = i - ntaps / 2;
+        double x1 = M_PI * xi / spb, x2 = 4 * alpha * xi / spb, x3 = x2 * x2 - 1;
+        double num, den;
+        if (fabs(x3) >= 0.000001) {
+            num = (i != ntaps / 2) ? cos((1 + alpha) * x1) + sin((1 - alpha) * x1) / (4 * alpha * xi / spb)
+                                   : cos((1 + alpha) * x1) + (1 - alpha) * M_PI / (4 * alpha);
+            den = x3 * M_PI;
+        } else {
+            if (alpha == 1) {
+                out[i] = -1;
+                sum += out[i];
+                continue;
+            }
+            x3 = (1 - alpha) * x1;
+            x2 = (1 + alpha) * x1;
+            num = (sin(x2) * (1 + alpha) * M_PI - cos(x3) * ((1 - alpha) * M_PI * spb) / (4 * alpha * xi) + sin(x3) * spb * spb / (4 * alpha * xi * xi));
+            den = -32 * M_PI * alpha * alpha * xi / spb;
+        }
+        out[i] = (float)(4 * alpha * num / den);
+        sum += out[i];
+    }
+    for (int i = 0; i < ntaps; i++)
+        out[i] = (float)(out[i] * gain / sum);
+}
+
+// 128-arm x 8-tap polyphase interpolator of the M&M block: Nuttall-windowed sinc prototype of 1024 taps
+// (src-core/common/dsp/window/window.cpp:9-50), arm a / tap k = prototype[(127-a) + 128k] (polyphase_bank.cpp:35-36).
+void design_mm_bank(std::vector<float> &out)
+{
+    const int arms = 128, per = 8, count = arms * per;
+    out.assign(count, 0.f);
+    const double w[4] = {0.355768, 0.487396, 0.144232, 0.012604};
+    const double omega = 2.0 * M_PI * ((0.5 / (double)arms) / 1.0), half = count / 2.0, corr = arms * omega / M_PI;
+    for (int i = 0; i < count; i++) {
+        const double t = (double)i - half + 0.5, x = t * omega;
+        const double sinc = (x == 0.0) ? 1.0 : sin(x) / x;
+        double win = 0, sign = 1;
+        for (int c = 0; c < 4; c++) {
+            win += sign * w[c] * cos((double)c * 2.0 * M_PI * (t - half) / count);
+            sign = -sign;
+        }
+        out[((arms - 1) - (i % arms)) * per + i / arms] = (float)(sinc * win * corr);
+    }
+}
+
+static int round_up16(double v) { return ((int)std::ceil(v / 16.0)) * 16; }
+
+Demod::Demod(const b200_demod_cfg &c) : cfg(c)
+{
+    B200_REQUIRE(c.samplerate > 0 && c.symbolrate > 0, B200_EINVAL, "samplerate / symbolrate must be present and positive");
+    B200_REQUIRE(c.constellation >= B200_BPSK && c.constellation <= B200_NONE, B200_EINVAL, "unknown constellation %d", c.constellation);
+    B200_REQUIRE(c.format >= B200_CF32 && c.format <= B200_CS8, B200_EINVAL, "unsupported baseband_format %d (cf32/cs16/cs8 only)", c.format);
+    B200_REQUIRE((c.rrc_taps | 1) == FIR_NT, B200_EINVAL, "rrc_taps=%d: only the 31-tap RRC kernel is built", c.rrc_taps);
+    B200_REQUIRE(c.max_batch >= 4096, B200_EINVAL, "max_batch must be >= 4096 samples");
+    B200_REQUIRE(c.agc_rate > 0 && c.agc_rate < 0.5f, B200_EINVAL, "agc_rate out of range");
+    B200_REQUIRE(c.clock_gain_mu > 0 && c.pll_bw > 0, B200_EINVAL, "loop gains must be positive");
+    const long fs = (long)c.samplerate, rs = (long)c.symbolrate;
+    const float final_fs = (float)fs;
+    sps = final_fs / (float)rs;
+    // the reference resamples outside [MIN_SPS, MAX_SPS] (module_demod_base.cpp:66-80, module_psk_demod.cpp:65-70): not built here
+    const float lo = c.constellation == B200_OQPSK ? 1.6f : 1.1f, hi = c.constellation == B200_OQPSK ? 2.4f : 4.0f;
+    B200_REQUIRE(sps >= lo && sps <= hi, B200_EINVAL, "samples per symbol %.4f outside [%.1f, %.1f]: the resampler front-end is not part of this build", sps,
+                 lo, hi);
+    check_device(c.device);
+    DeviceGuard g(c.device);
+    bps = c.constellation == B200_BPSK ? 1 : 2;
+    order = c.constellation == B200_BPSK ? 2 : (c.constellation == B200_8PSK ? 8 : (c.constellation == B200_NONE ? 0 : 4));
+    max_batch = c.max_batch;
+    design_rrc(1, final_fs, (double)(int)rs, c.rrc_alpha, c.rrc_taps, rrc);
+    design_mm_bank(bank);
+    Wc = round_up16(24.0 / c.pll_bw);
+    Wm = round_up16(70.0 / c.clock_gain_mu);
+    int dev_sms = 148;
+    cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, c.device);
+    seg_cap_threads = dev_sms * 3 * SEG_THREADS;
+
+    B200_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    for (auto &e : ev)
+        B200_CUDA(cudaEventCreate(&e));
+    const int fmt_bytes = c.format == B200_CF32 ? 8 : (c.format == B200_CS16 ? 4 : 2);
+    raw.alloc((size_t)max_batch * fmt_bytes + 64);
+    bufA.alloc(max_batch + 64);
+    bufB.alloc(max_batch + 64);
+    if (c.keep_stages) {
+        agc_dump.alloc(max_batch);
+        fir_dump.alloc(max_batch);
+    }
+    const int ntiles_max = (int)((max_batch + FIR_TO - 1) / FIR_TO);
+    tile_map.alloc(ntiles_max + 1);
+    seeds.alloc(ntiles_max + 2);
+    // worst-case segment count / slot storage: L >= 1024
+    const int lmin = 1024;
+    const long nseg_max = (max_batch + lmin - 1) / lmin + 1;
+    crec.alloc(nseg_max);
+    mrec.alloc(nseg_max);
+    quad.alloc(nseg_max);
+    offs.alloc(nseg_max + 1);
+    const double omin = sps * (1.0 - c.clock_omega_limit) - 0.01;
+    slots.alloc((size_t)(max_batch / omin) + nseg_max * 16 + 1024);
+    sym_out.alloc((size_t)(max_batch / omin) + 1024);
+    soft.alloc(((size_t)(max_batch / omin) + 1024) * bps);
+    d_bank.alloc(128 * 8);
+    st.alloc(1);
+    B200_CUDA(cudaMemcpyAsync(d_bank.p, bank.data(), 128 * 8 * sizeof(float), cudaMemcpyHostToDevice, stream));
+    B200_CUDA(cudaMallocHost((void **)&h_total, sizeof(long)));
+    B200_CUDA(cudaMallocHost((void **)&h_state, sizeof(DemodDevState)));
+    // initial loop state: AGC gain 1 (module_demod_base.cpp:207), Costas 0/0, M&M mu / omega (clock_recovery_mm.cpp:11)
+    memset(h_state, 0, sizeof(DemodDevState));
+    h_state->gain[0] = h_state->gain[1] = 1.0f;
+    for (int i = 0; i < 2; i++) {
+        h_state->mm[i].mu = c.clock_mu;
+        h_state->mm[i].omega = sps;
+    }
+    B200_CUDA(cudaMemcpyAsync(st.p, h_state, sizeof(DemodDevState), cudaMemcpyHostToDevice, stream));
+    bufA.zero(stream);
+    bufB.zero(stream);
+    B200_CUDA(cudaFuncSetAttribute(k_mm, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM_BYTES));
+    B200_CUDA(cudaStreamSynchronize(stream));
+}
+
+Demod::~Demod()
+{
+    DeviceGuard g(cfg.device);
+    if (stream)
+        cudaStreamSynchronize(stream);
+    for (auto &e : ev)
+        cudaEventDestroy(e);
+    if (h_total)
+        cudaFreeHost(h_total);
+    if (h_state)
+        cudaFreeHost(h_state);
+    if (stream)
+        cudaStreamDestroy(stream);
+}
+
+int Demod::choose_L(long n) const
+{
+    // one segment per thread; aim at one full wave of resident threads, but keep segments within [1024, 16384] samples
+    long L = (n + seg_cap_threads - 1) / seg_cap_threads;
+    L = std::max<long>(1024, std::min<long>(16384, L));
+    return (int)((L + 15) / 16 * 16);
+}
+
+int Demod::slot_cap_for(int L) const
+{
+    const double omin = sps * (1.0 - cfg.clock_omega_limit) - 0.01;
+    return (int)(L / omin) + 8;
+}
+
+template <int FMT> static void launch_front(Demod &d, const void *raw, long n, int ntiles, FirTaps taps, int cur, bool dump)
+{
+    DemodDevState *S = d.st.p;
+    float2 *fir_out = d.bufA.p + 16;
+    k_agc_compose<FMT><<<ntiles, FIR_THREADS, 0, d.stream>>>(raw, n, d.cfg.agc_rate, d.tile_map.p);
+    k_agc_scan<<<1, 1024, 0, d.stream>>>(d.tile_map.p, ntiles, &S->gain[cur], d.seeds.p);
+    if (dump)
+        k_agc_fir<FMT, true><<<ntiles, FIR_THREADS, 0, d.stream>>>(raw, n, d.cfg.agc_rate, d.seeds.p, taps, S->agc_tail[cur], S->agc_tail[cur ^ 1], fir_out,
+                                                                  d.agc_dump.p, &S->gain[cur ^ 1], &S->flags);
+    else
+        k_agc_fir<FMT, false><<<ntiles, FIR_THREADS, 0, d.stream>>>(raw, n, d.cfg.agc_rate, d.seeds.p, taps, S->agc_tail[cur], S->agc_tail[cur ^ 1], fir_out,
+                                                                   nullptr, &S->gain[cur ^ 1], &S->flags);
+    d.launches += 3;
+}
+
+long Demod::process(const void *d_raw, long n, int8_t *soft_dst)
+{
+    B200_REQUIRE(n >= 64, B200_ESTATE, "a batch needs at least 64 samples (got %ld)", n);
+    B200_REQUIRE(n <= max_batch, B200_ESTATE, "batch of %ld samples exceeds max_batch %ld", n, max_batch);
+    DeviceGuard g(cfg.device);
+    const int cur = parity, nxt = parity ^ 1;
+    DemodDevState *S = st.p;
+    const int ntiles = (int)((n + FIR_TO - 1) / FIR_TO);
+    FirTaps taps;
+    memset(&taps, 0, sizeof(taps));
+    for (int i = 0; i < FIR_NT; i++)
+        taps.h[i] = rrc[i];
+    B200_CUDA(cudaEventRecord(ev[0], stream));
+    const bool dump = cfg.keep_stages != 0;
+    if (cfg.format == B200_CF32)
+        launch_front<0>(*this, d_raw, n, ntiles, taps, cur, dump);
+    else if (cfg.format == B200_CS16)
+        launch_front<1>(*this, d_raw, n, ntiles, taps, cur, dump);
+    else
+        launch_front<2>(*this, d_raw, n, ntiles, taps, cur, dump);
+    B200_CUDA(cudaEventRecord(ev[1], stream));
+    float2 *fir_out = bufA.p + 16, *cos_out = bufB.p + 16;
+    if (dump)
+        B200_CUDA(cudaMemcpyAsync(fir_dump.p, fir_out, n * sizeof(float2), cudaMemcpyDeviceToDevice, stream));
+
+    const int L = choose_L(n);
+    const int nseg = (int)((n + L - 1) / L);
+    const int nblk = (nseg + SEG_THREADS - 1) / SEG_THREADS;
+    float2 *mmin;
+    if (order) {
+        CostasParams P;
+        P.order = order;
+        { // costas_loop.cpp:5-12
+            float damping = sqrtf(2.0f) / 2.0f;
+            float denom = (float)(1.0 + 2.0 * damping * cfg.pll_bw + cfg.pll_bw * cfg.pll_bw);
+            P.alpha = (4 * damping * cfg.pll_bw) / denom;
+            P.beta = (4 * cfg.pll_bw * cfg.pll_bw) / denom;
+        }
+        P.fmin = -cfg.costas_max_offset;
+        P.fmax = cfg.costas_max_offset;
+        k_costas<<<nblk, SEG_THREADS, 0, stream>>>(fir_out, n, L, Wc, nseg, P, S->costas[cur], cos_out, crec.p);
+        k_costas_fix<<<1, 1024, 0, stream>>>(crec.p, nseg, order, 2e-3f, 1e-4f, quad.p, S->costas[nxt], &S->costas_unconv);
+        mmin = bufA.p; // FIR output is dead now: reuse its buffer (in place compatible: same index mapping)
+        k_rotate<<<2048, 256, 0, stream>>>(cos_out, n, L, order, cfg.constellation == B200_OQPSK, quad.p, S->mm_hist[cur], S->mm_hist[nxt], mmin);
+        launches += 3;
+    } else {
+        mmin = bufB.p;
+        k_rotate<<<2048, 256, 0, stream>>>(fir_out, n, L, 0, 0, quad.p, S->mm_hist[cur], S->mm_hist[nxt], mmin);
+        launches += 1;
+    }
+    B200_CUDA(cudaEventRecord(ev[2], stream));
+    MMParams MP;
+    MP.omega_mid = sps;
+    MP.omega_limit = cfg.clock_omega_limit * sps;
+    MP.omega_gain = cfg.clock_gain_omega;
+    MP.mu_gain = cfg.clock_gain_mu;
+    const int cap = slot_cap_for(L);
+    B200_REQUIRE((size_t)nseg * cap <= slots.n, B200_ENOMEM, "internal: symbol slot storage too small");
+    k_mm<<<nblk, SEG_THREADS, MM_SMEM_BYTES, stream>>>(mmin, n, L, Wm, nseg, MP, &S->mm[cur], &S->mm[nxt], d_bank.p, slots.p, cap, mrec.p);
+    k_mm_scan<<<1, 1024, 0, stream>>>(mrec.p, nseg, 1e-3f, offs.p, &S->mm_unconv, cap, &S->flags);
+    int8_t *sdst = soft_dst ? soft_dst : soft.p;
+    k_mm_compact<<<std::min(nseg, 148 * 8), 256, 0, stream>>>(slots.p, cap, mrec.p, offs.p, nseg, bps == 1, sym_out.p, sdst);
+    launches += 3;
+    B200_CUDA(cudaEventRecord(ev[3], stream));
+    B200_CUDA(cudaMemcpyAsync(h_total, offs.p + nseg, sizeof(long), cudaMemcpyDeviceToHost, stream));
+    B200_CUDA(cudaMemcpyAsync(h_state, st.p, sizeof(DemodDevState), cudaMemcpyDeviceToHost, stream));
+    B200_CUDA(cudaStreamSynchronize(stream));
+    B200_CUDA(cudaGetLastError());
+    cudaEventElapsedTime(&t_agcfir, ev[0], ev[1]);
+    cudaEventElapsedTime(&t_costas, ev[1], ev[2]);
+    cudaEventElapsedTime(&t_mm, ev[2], ev[3]);
+    parity = nxt;
+    last_n = n;
+    last_syms = *h_total;
+    total_in += n;
+    total_syms += last_syms;
+    if (h_state->flags & 1)
+        throw ApiError(B200_EUNSUPPORTED, "AGC gain reached max_gain (65536): input is (near) silent; the scan formulation does not cover the clamp");
+    if (h_state->flags & 2)
+        throw ApiError(B200_EUNSUPPORTED, "M&M produced more symbols per segment than the omega limit allows (slot overflow)");
+    return last_syms;
+}
+
+long Demod::push_host(const void *h_raw, long n, int8_t *soft_dst)
+{
+    B200_REQUIRE(n <= max_batch, B200_ESTATE, "batch of %ld samples exceeds max_batch %ld", n, max_batch);
+    DeviceGuard g(cfg.device);
+    const int fmt_bytes = cfg.format == B200_CF32 ? 8 : (cfg.format == B200_CS16 ? 4 : 2);
+    B200_CUDA(cudaMemcpyAsync(raw.p, h_raw, (size_t)n * fmt_bytes, cudaMemcpyHostToDevice, stream));
+    return process(raw.p, n, soft_dst);
+}
+
+void Demod::stats(b200_demod_stats *o)
+{
+    memset(o, 0, sizeof(*o));
+    o->samples_in = total_in;
+    o->symbols_out = total_syms;
+    o->agc_gain = h_state->gain[parity];
+    o->costas_phase = h_state->costas[parity][0];
+    o->costas_freq = h_state->costas[parity][1];
+    o->mm_mu = h_state->mm[parity].mu;
+    o->mm_omega = h_state->mm[parity].omega;
+    o->costas_unconverged = h_state->costas_unconv;
+    o->mm_unconverged = h_state->mm_unconv;
+    o->agc_clamped = h_state->flags & 1;
+    o->kernel_launches = launches;
+}
+
+} // namespace b200
+
+using namespace b200;
+struct b200_demod
+{
+    Demod *d;
+};
+
+extern "C" {
+const char *b200_last_error(void) { return b200::last_error_cstr(); }
+int b200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess)
+        return 0;
+    return n;
+}
+
+b200_demod *b200_demod_create(const b200_demod_cfg *cfg)
+{
+    b200_demod *h = nullptr;
+    int rc = guarded([&] {
+        B200_REQUIRE(cfg != nullptr, B200_EINVAL, "cfg is NULL");
+        h = new b200_demod{new Demod(*cfg)};
+    });
+    (void)rc;
+    return h;
+}
+void b200_demod_destroy(b200_demod *h)
+{
+    if (!h)
+        return;
+    delete h->d;
+    delete h;
+}
+int b200_demod_push_iq(b200_demod *h, const void *host_iq, long n)
+{
+    return guarded([&] {
+        B200_REQUIRE(h && host_iq, B200_EINVAL, "NULL argument");
+        h->d->push_host(host_iq, n, nullptr);
+    });
+}
+int b200_demod_push_iq_device(b200_demod *h, const void *dev_iq, long n)
+{
+    return guarded([&] {
+        B200_REQUIRE(h && dev_iq, B200_EINVAL, "NULL argument");
+        h->d->process(dev_iq, n, nullptr);
+    });
+}
+int b200_demod_pull_soft(b200_demod *h, int8_t *out, long cap, long *n_out)
+{
+    return guarded([&] {
+        B200_REQUIRE(h && out && n_out, B200_EINVAL, "NULL argument");
+        Demod &d = *h->d;
+        long nb = d.last_syms * d.bps;
+        B200_REQUIRE(nb <= cap, B200_ESTATE, "output buffer too small: need %ld bytes", nb);
+        DeviceGuard g(d.cfg.device);
+        B200_CUDA(cudaMemcpyAsync(out, d.soft.p, nb, cudaMemcpyDeviceToHost, d.stream));
+        B200_CUDA(cudaStreamSynchronize(d.stream));
+        *n_out = nb;
+    });
+}
+int b200_demod_pull_symbols(b200_demod *h, float *out, long cap_symbols, long *n_out)
+{
+    return guarded([&] {
+        B200_REQUIRE(h && out && n_out, B200_EINVAL, "NULL argument");
+        Demod &d = *h->d;
+        B200_REQUIRE(d.last_syms <= cap_symbols, B200_ESTATE, "output buffer too small: need %ld symbols", d.last_syms);
+        DeviceGuard g(d.cfg.device);
+        B200_CUDA(cudaMemcpyAsync(out, d.sym_out.p, d.last_syms * sizeof(float2), cudaMemcpyDeviceToHost, d.stream));
+        B200_CUDA(cudaStreamSynchronize(d.stream));
+        *n_out = d.last_syms;
+    });
+}
+int b200_demod_debug_stage(b200_demod *h, int stage, float *out, long cap_samples)
+{
+    return guarded([&] {
+        B200_REQUIRE(h && out, B200_EINVAL, "NULL argument");
+        Demod &d = *h->d;
+        B200_REQUIRE(d.cfg.keep_stages, B200_ESTATE, "create the demodulator with keep_stages=1 to read stage outputs");
+        B200_REQUIRE(d.last_n <= cap_samples, B200_ESTATE, "output buffer too small");
+        const float2 *src = nullptr;
+        if (stage == B200_STAGE_AGC)
+            src = d.agc_dump.p;
+        else if (stage == B200_STAGE_FIR)
+            src = d.fir_dump.p;
+        else if (stage == B200_STAGE_COSTAS)
+            src = (d.order ? d.bufA.p : d.bufB.p) + 16; // M&M input = Costas output after rotation fix-up (+ OQPSK delay)
+        B200_REQUIRE(src, B200_EINVAL, "unknown stage %d", stage);
+        DeviceGuard g(d.cfg.device);
+        B200_CUDA(cudaMemcpyAsync(out, src, d.last_n * sizeof(float2), cudaMemcpyDeviceToHost, d.stream));
+        B200_CUDA(cudaStreamSynchronize(d.stream));
+    });
+}
+int b200_demod_get_stats(b200_demod *h, b200_demod_stats *out)
+{
+    return guarded([&] {
+        B200_REQUIRE(h && out, B200_EINVAL, "NULL argument");
+        h->d->stats(out);
+    });
+}
+int b200_demod_get_taps(b200_demod *h, float *rrc_out, int rrc_cap, float *bank_out)
+{
+    return guarded([&] {
+        B200_REQUIRE(h && rrc_out, B200_EINVAL, "NULL argument");
+        B200_REQUIRE((int)h->d->rrc.size() <= rrc_cap, B200_ESTATE, "rrc_out too small");
+        memcpy(rrc_out, h->d->rrc.data(), h->d->rrc.size() * sizeof(float));
+        if (bank_out)
+            memcpy(bank_out, h->d->bank.data(), 128 * 8 * sizeof(float));
+    });
+}
+}
+
+// exposed to api_chain.cu
+namespace b200
+{
+Demod *demod_of(b200_demod *h) { return h->d; }
+}

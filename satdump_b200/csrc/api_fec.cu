@@ -1,0 +1,535 @@
+// C ABI + host driver of the decoder (see include/b200dsp.h, fec_host.h).
+#define B200_DEFINE_KERNELS
+#include "fec_host.h"
+#include <algorithm>
+#include <cmath>
+
+namespace b200
+{
+
+// GF(256) tables exactly as libcorrect builds them (libs/correct/reed-solomon/field.h:26-62: log[1] ends up 255, log[0] = 0),
+// CCSDS dual-basis maps (GF(2)-linear, generated from the images of the unit vectors) and the CCSDS randomiser bytes
+// (LFSR h(x) = x^8+x^7+x^5+x^3+1 from all ones).
+void build_rs_tables(RsTables &T)
+{
+    memset(&T, 0, sizeof(T));
+    unsigned e = 1;
+    T.exp[0] = 1;
+    T.log[0] = 0;
+    for (int i = 1; i < 512; i++) {
+        e <<= 1;
+        if (e > 255)
+            e ^= 0x187;
+        T.exp[i] = (uint8_t)e;
+        if (i < 256)
+            T.log[e] = (uint8_t)i;
+    }
+    static const uint8_t img[8] = {0x7B, 0xAF, 0x99, 0xFA, 0x86, 0xEC, 0xEF, 0x8D};
+    for (int v = 0; v < 256; v++) {
+        uint8_t r = 0;
+        for (int b = 0; b < 8; b++)
+            if (v >> b & 1)
+                r ^= img[b];
+        T.to_dual[v] = r;
+    }
+    for (int v = 0; v < 256; v++)
+        T.from_dual[T.to_dual[v]] = (uint8_t)v;
+    uint8_t reg = 0xFF;
+    for (int i = 0; i < 255; i++) {
+        uint8_t byte = 0;
+        for (int k = 0; k < 8; k++) {
+            byte = (uint8_t)((byte << 1) | (reg >> 7));
+            uint8_t nb = ((reg >> 7) ^ (reg >> 4) ^ (reg >> 2) ^ reg) & 1;
+            reg = (uint8_t)((reg << 1) | nb);
+        }
+        T.pn[i] = byte;
+    }
+}
+
+Fec::Fec(const b200_fec_cfg &c) : cfg(c)
+{
+    B200_REQUIRE(c.kind == B200_FEC_METOP || c.kind == B200_FEC_CCSDS, B200_EINVAL, "unknown decoder kind %d", c.kind);
+    B200_REQUIRE(c.max_soft >= 65536, B200_EINVAL, "max_soft must be >= 65536");
+    memset(&geom, 0, sizeof(geom));
+    if (c.kind == B200_FEC_METOP) {
+        // module_metop_ahrpt_decoder.cpp:10,17-25: 16384-byte chunks, r=3/4, phases {0,90}, deframer SYNCED threshold 18, RS223 I=4
+        geom.rate34 = 1;
+        geom.chunk = 8192 * 2;
+        geom.F = geom.chunk * 3 / 4;
+        cfg.cadu_size = 8192;
+        cfg.rs_i = 4;
+        cfg.rs_dualbasis = 1;
+        cfg.rs_type = 0;
+        cfg.derandomize = 1;
+        cfg.derand_after_rs = 0;
+        cfg.derand_start = 4;
+        cfg.rs_usecheck = 0;
+        cfg.nrzm = 0;
+        cfg.asm_sync = 0x1ACFFC1D;
+        nphases = 2; ph0 = 0; ph1 = 1; nswap = 1;
+        st_synced = 18;
+        spec_steps = VIT_SPEC_STEPS_34;
+    } else {
+        // module_ccsds_conv_concat_decoder.cpp:16-131 (conv_rate 1/2 only; the Viterbi_Depunc rates are not built)
+        B200_REQUIRE(c.cadu_size >= 64 && c.cadu_size <= 65536, B200_EINVAL, "cadu_size out of range");
+        B200_REQUIRE(c.cadu_size % 8 == 0, B200_EINVAL, "cadu_size must be a multiple of 8 (frame padding is not built)");
+        B200_REQUIRE(c.rs_i >= 0 && c.rs_i <= RS_MAX_I, B200_EINVAL, "rs_i out of range (0..%d)", RS_MAX_I);
+        B200_REQUIRE(c.rs_i == 0 || c.cadu_size / 8 >= 4 + 255 * c.rs_i, B200_EINVAL, "cadu_size too small for rs_i interleaved codewords");
+        B200_REQUIRE(c.rs_fill_bytes <= 0, B200_EINVAL, "rs_fill_bytes (shortened codes) is not built");
+        geom.rate34 = 0;
+        geom.chunk = std::max(c.cadu_size, 8192);
+        B200_REQUIRE(geom.chunk % 2 == 0, B200_EINVAL, "chunk size must be even");
+        geom.F = geom.chunk / 2;
+        if (c.constellation == B200_BPSK) { nphases = 1; ph0 = 0; ph1 = 0; }
+        else if (c.constellation == B200_BPSK_90) { nphases = 1; ph0 = 1; ph1 = 1; }
+        else if (c.constellation == B200_QPSK || c.constellation == B200_OQPSK) { nphases = 2; ph0 = 0; ph1 = 1; }
+        else B200_REQUIRE(false, B200_EINVAL, "CCSDS Concatenated 1/2 Decoder : invalid constellation type!");
+        nswap = c.constellation == B200_OQPSK ? 2 : 1;
+        st_synced = 12;
+        spec_steps = VIT_SPEC_STEPS_12;
+        if (cfg.asm_sync == 0)
+            cfg.asm_sync = 0x1ACFFC1D;
+    }
+    geom.dec_stride = (geom.F + 6 + 7) & ~7;
+    geom.bit_words = (geom.F + 31) / 32 + 1;
+    cadu_bytes = (cfg.cadu_size + 7) / 8;
+    check_device(c.device);
+    DeviceGuard g(c.device);
+    B200_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    for (auto &e : ev)
+        B200_CUDA(cudaEventCreate(&e));
+    max_chunks = c.max_soft / geom.chunk + 2;
+    softbuf.alloc((size_t)c.max_soft + 2 * geom.chunk);
+    dec.alloc((size_t)max_chunks * geom.dec_stride);
+    idle_dec.alloc(VIT_TESTLEN + 64);
+    chunk_bits.alloc((size_t)max_chunks * geom.bit_words + 4);
+    const long max_new_bits = max_chunks * (long)geom.F;
+    fifo.alloc((size_t)((max_new_bits + 2L * cfg.cadu_size + 4096) / 32 + 8));
+    start_state.alloc(max_chunks + 1);
+    rec.alloc(max_chunks + 1);
+    idle_out.alloc(1);
+    dstate.alloc(2);
+    devents.alloc(4096);
+    max_frames_push = max_new_bits / cfg.cadu_size + 4;
+    frames.alloc(max_frames_push);
+    frames_out.alloc((size_t)(2 * max_frames_push + 4) * cadu_bytes);
+    frames_tmp.alloc((size_t)(max_frames_push + 4) * cadu_bytes);
+    rs_err.alloc((size_t)(max_frames_push + 4) * std::max(1, cfg.rs_i));
+    counters.alloc(8);
+    tables.alloc(1);
+    B200_CUDA(cudaMallocHost((void **)&h_rec, sizeof(VitRec) * (max_chunks + 1)));
+    B200_CUDA(cudaMallocHost((void **)&h_idle, sizeof(VitIdleOut)));
+    B200_CUDA(cudaMallocHost((void **)&h_counters, sizeof(int) * 8));
+    B200_CUDA(cudaMallocHost((void **)&h_dstate, sizeof(DefrState) * 2));
+    B200_CUDA(cudaMallocHost((void **)&h_events, sizeof(DefrEvent) * 4096));
+    B200_CUDA(cudaMallocHost((void **)&h_rs_err, sizeof(int) * (max_frames_push + 4) * std::max(1, cfg.rs_i)));
+    RsTables T;
+    build_rs_tables(T);
+    B200_CUDA(cudaMemcpyAsync(tables.p, &T, sizeof(T), cudaMemcpyHostToDevice, stream));
+    fifo.zero(stream);
+    rec.zero(stream);
+    h_dstate[0].state = 2;
+    h_dstate[0].inversion = h_dstate[0].good = h_dstate[0].bad = 0;
+    h_dstate[0].pos = 32; // the FIFO starts with 32 zero bits = the deframer's empty shifter
+    h_dstate[0].frame_pay = -1;
+    B200_CUDA(cudaMemcpyAsync(dstate.p, h_dstate, sizeof(DefrState), cudaMemcpyHostToDevice, stream));
+    const int fr_smem = (int)sizeof(RsTables) + ((cadu_bytes + 15) & ~15) + RS_MAX_I * 704;
+    B200_CUDA(cudaFuncSetAttribute(k_frames, cudaFuncAttributeMaxDynamicSharedMemorySize, fr_smem));
+    B200_CUDA(cudaStreamSynchronize(stream));
+}
+
+Fec::~Fec()
+{
+    DeviceGuard g(cfg.device);
+    if (stream)
+        cudaStreamSynchronize(stream);
+    for (auto &e : ev)
+        cudaEventDestroy(e);
+    for (void *p : {(void *)h_rec, (void *)h_idle, (void *)h_counters, (void *)h_dstate, (void *)h_events, (void *)h_rs_err})
+        if (p)
+            cudaFreeHost(p);
+    if (stream)
+        cudaStreamDestroy(stream);
+}
+
+void Fec::push_host(const int8_t *h, long n)
+{
+    B200_REQUIRE(n <= append_room(), B200_ESTATE, "push of %ld soft bytes exceeds the FIFO room %ld (max_soft too small)", n, append_room());
+    DeviceGuard g(cfg.device);
+    B200_CUDA(cudaMemcpyAsync(append_ptr(), h, n, cudaMemcpyHostToDevice, stream));
+    commit(n);
+    process();
+}
+void Fec::push_device(const int8_t *d, long n)
+{
+    B200_REQUIRE(n <= append_room(), B200_ESTATE, "push of %ld soft bytes exceeds the FIFO room %ld (max_soft too small)", n, append_room());
+    DeviceGuard g(cfg.device);
+    B200_CUDA(cudaMemcpyAsync(append_ptr(), d, n, cudaMemcpyDeviceToDevice, stream));
+    commit(n);
+    process();
+}
+
+struct OutChunk { long soft_chunk; int next_start, enc_tail, invalid_after, state_after; VitIdleState idle_st; };
+
+// Viterbi over soft chunks [c0, nch): lock search while IDLE, optimistic parallel decode while SYNCED. Decoded chunks land in
+// chunk_bits[0 .. nout). Returns per-output-chunk bookkeeping in `outs`.
+static void viterbi_segment(Fec &f, long c0, long nch, std::vector<OutChunk> &outs)
+{
+    outs.clear();
+    long c = c0, out_base = 0;
+    const float kber = f.geom.rate34 ? 5.0f : 2.5f;
+    while (c < nch) {
+        if (f.vit_state == 0) {
+            k_vit_idle<<<1, 32, 0, f.stream>>>(f.softbuf.p, c, (int)(nch - c), f.geom, f.nswap, f.nphases, f.ph0, f.ph1, f.cfg.ber_thresold, f.idle_st,
+                                              f.idle_dec.p, f.idle_out.p);
+            f.launches++;
+            B200_CUDA(cudaMemcpyAsync(f.h_idle, f.idle_out.p, sizeof(VitIdleOut), cudaMemcpyDeviceToHost, f.stream));
+            B200_CUDA(cudaStreamSynchronize(f.stream));
+            f.idle_st = f.h_idle->st;
+            float bb = 10.f;
+            for (int i = 0; i < 16; i++)
+                bb = std::min(bb, f.h_idle->bers[i]);
+            f.last_ber = bb;
+            if (f.h_idle->lock_chunk < 0)
+                break;
+            c += f.h_idle->lock_chunk;
+            f.vit_state = 1;
+            f.hyp = VitHyp{f.h_idle->swap, f.h_idle->phase, f.h_idle->shift};
+            f.invalid = 0;
+            f.enc_state = f.idle_st.enc_state;
+        }
+        const int n = (int)(nch - c);
+        B200_CUDA(cudaMemcpyAsync(f.start_state.p, &f.main_next_start, sizeof(int), cudaMemcpyHostToDevice, f.stream));
+        const int wpb = 4, nb_main = (n + wpb - 1) / wpb;
+        if (n > 1) {
+            k_vit_spec<<<(n - 1 + wpb - 1) / wpb, 32 * wpb, 0, f.stream>>>(f.softbuf.p, c, n, f.geom, f.hyp, f.spec_steps, f.start_state.p);
+            f.launches++;
+        }
+        k_vit_main<<<nb_main, 32 * wpb, 0, f.stream>>>(f.softbuf.p, c, n, f.geom, f.hyp, f.start_state.p, f.dec.p, f.chunk_bits.p, out_base, f.rec.p);
+        k_vit_ber<<<nb_main, 32 * wpb, 0, f.stream>>>(f.softbuf.p, c, n, f.geom, f.hyp, f.chunk_bits.p, out_base, f.enc_state, f.rec.p);
+        f.launches += 2;
+        B200_CUDA(cudaMemcpyAsync(f.h_rec, f.rec.p, sizeof(VitRec) * n, cudaMemcpyDeviceToHost, f.stream));
+        B200_CUDA(cudaStreamSynchronize(f.stream));
+        int accepted = 0;
+        for (int i = 0; i < n; i++) {
+            if (i > 0 && f.h_rec[i].start_used != f.h_rec[i - 1].next_start) {
+                f.replays++; // start state mis-speculated: decode again from here with the true state
+                break;
+            }
+            accepted = i + 1;
+            const float ber = ((float)f.h_rec[i].ber_errors / (float)f.h_rec[i].ber_total) * kber;
+            f.last_ber = ber;
+            bool lost = false;
+            if (ber > f.cfg.ber_thresold) { // viterbi_3_4.cpp:160-169
+                f.invalid++;
+                if (f.invalid > f.cfg.outsync_after) {
+                    f.vit_state = 0;
+                    lost = true;
+                }
+            } else
+                f.invalid = 0;
+            outs.push_back(OutChunk{c + i, f.h_rec[i].next_start, f.h_rec[i].enc_tail, f.invalid, f.vit_state, f.idle_st});
+            if (lost)
+                break;
+        }
+        f.main_next_start = f.h_rec[accepted - 1].next_start;
+        f.enc_state = f.h_rec[accepted - 1].enc_tail;
+        out_base += accepted;
+        c += accepted;
+    }
+}
+
+void Fec::deframe_and_rs(long new_bits)
+{
+    const long nbits = fifo_bits + new_bits;
+    k_deframe<<<1, 32, 0, stream>>>(fifo.p, nbits, cfg.cadu_size, st_synced, cfg.asm_sync, dstate.p, frames.p, (int)max_frames_push,
+                                   reinterpret_cast<DefrEventDev *>(devents.p), 4096, counters.p);
+    launches++;
+    B200_CUDA(cudaMemcpyAsync(h_counters, counters.p, sizeof(int) * 2, cudaMemcpyDeviceToHost, stream));
+    B200_CUDA(cudaMemcpyAsync(h_dstate, dstate.p, sizeof(DefrState), cudaMemcpyDeviceToHost, stream));
+    B200_CUDA(cudaMemcpyAsync(h_events, devents.p, sizeof(DefrEvent) * 4096, cudaMemcpyDeviceToHost, stream));
+    B200_CUDA(cudaStreamSynchronize(stream));
+    const int nf = h_counters[0];
+    B200_REQUIRE(nf <= max_frames_push, B200_ESTATE, "internal: frame list overflow");
+    B200_REQUIRE(h_counters[1] <= 4096, B200_EUNSUPPORTED, "deframer changed state more than 4096 times in one push (noise input?): push smaller batches");
+    if (nf > 0) {
+        B200_REQUIRE((size_t)(out_frames + nf) * cadu_bytes <= frames_out.n, B200_ESTATE, "frame output buffer full: call pull_frames");
+        FrameCfg fc;
+        fc.cadu_bytes = cadu_bytes;
+        fc.cadu_size = cfg.cadu_size;
+        fc.derandomize = cfg.derandomize;
+        fc.derand_after_rs = cfg.derand_after_rs;
+        fc.derand_start = cfg.derand_start;
+        fc.rs_i = cfg.rs_i;
+        fc.rs_dual = cfg.rs_dualbasis;
+        fc.rs_nroots = cfg.rs_type == 1 ? 16 : 32;
+        fc.rs_fcr = cfg.rs_type == 1 ? 120 : 112;
+        fc.sync = cfg.asm_sync;
+        const int fr_smem = (int)sizeof(RsTables) + ((cadu_bytes + 15) & ~15) + RS_MAX_I * 704;
+        const bool filter = cfg.rs_usecheck && cfg.rs_i > 0;
+        uint8_t *dst = filter ? frames_tmp.p : frames_out.p + out_frames * cadu_bytes;
+        k_frames<<<std::min(nf, 148 * 8), 256, fr_smem, stream>>>(fifo.p, frames.p, nf, fc, tables.p, dst, rs_err.p);
+        launches++;
+        int kept = nf;
+        if (filter) {
+            k_frames_filter<<<1, 1024, 0, stream>>>(frames_tmp.p, rs_err.p, nf, cfg.rs_i, cadu_bytes, frames_out.p + out_frames * cadu_bytes, counters.p + 2);
+            launches++;
+            B200_CUDA(cudaMemcpyAsync(h_counters + 2, counters.p + 2, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        }
+        if (cfg.rs_i > 0)
+            B200_CUDA(cudaMemcpyAsync(h_rs_err, rs_err.p, sizeof(int) * nf * cfg.rs_i, cudaMemcpyDeviceToHost, stream));
+        B200_CUDA(cudaStreamSynchronize(stream));
+        if (filter)
+            kept = h_counters[2];
+        for (long i = 0; i < (long)nf * cfg.rs_i; i++) {
+            if (h_rs_err[i] < 0)
+                rs_failed++;
+            else
+                rs_corrected += h_rs_err[i];
+        }
+        out_frames += kept;
+        total_frames += kept;
+    }
+    fifo_bits = nbits;
+    defr_state_now = h_dstate->state;
+}
+
+void Fec::process()
+{
+    DeviceGuard g(cfg.device);
+    const long nch = soft_have / geom.chunk;
+    B200_REQUIRE(nch <= max_chunks, B200_ESTATE, "internal: too many chunks");
+    // (lazy, so that b200_fec_debug_bits can still read the previous push's bits until now)
+    // compact the bit FIFO: keep from the open frame's payload, or the 31 bits of shifter history
+    {
+        DefrState S = *h_dstate;
+        long keep = S.frame_pay >= 0 ? S.frame_pay : S.pos - 31;
+        keep = std::max<long>(0, std::min<long>(keep, fifo_bits));
+        const long keep_al = keep & ~31L;
+        if (keep_al > 0) {
+            const long nwords = ((fifo_bits - keep_al) + 31) / 32 + 1;
+            k_words_move<<<1, 1024, 0, stream>>>(fifo.p, fifo.p + keep_al / 32, nwords);
+            launches++;
+            S.pos -= keep_al;
+            if (S.frame_pay >= 0)
+                S.frame_pay -= keep_al;
+            fifo_bits -= keep_al;
+            *h_dstate = S;
+            B200_CUDA(cudaMemcpyAsync(dstate.p, h_dstate, sizeof(DefrState), cudaMemcpyHostToDevice, stream));
+        }
+    }
+    last_bits0 = fifo_bits;
+    last_nbits = 0;
+    B200_CUDA(cudaEventRecord(ev[0], stream));
+    float acc_frames_ms = 0;
+    long c = 0;
+    std::vector<OutChunk> outs;
+    while (c < nch) {
+        // snapshot for the (rare) MetOp "deframer stuck in NOSYNC -> viterbi.reset()" rollback
+        B200_CUDA(cudaMemcpyAsync(dstate.p + 1, dstate.p, sizeof(DefrState), cudaMemcpyDeviceToDevice, stream));
+        const long fifo_bits0 = fifo_bits, out_frames0 = out_frames, total_frames0 = total_frames, rs_c0 = rs_corrected, rs_f0 = rs_failed;
+        const int nosync0 = nosync_runs;
+        viterbi_segment(*this, c, nch, outs);
+        const long nout = (long)outs.size();
+        long next_c = nch;
+        if (nout > 0) {
+            B200_REQUIRE(((fifo_bits + nout * geom.F + 64) >> 5) + 2 < (long)fifo.n, B200_ESTATE, "internal: bit FIFO too small");
+            int last_raw = 0;
+            if (cfg.nrzm) {
+                uint32_t w;
+                const int k = geom.F - 1;
+                B200_CUDA(cudaMemcpyAsync(&w, chunk_bits.p + (nout - 1) * geom.bit_words + (k >> 5), 4, cudaMemcpyDeviceToHost, stream));
+                B200_CUDA(cudaStreamSynchronize(stream));
+                last_raw = (w >> (31 - (k & 31))) & 1;
+            }
+            k_bits_append<<<1024, 256, 0, stream>>>(chunk_bits.p, nout, geom.F, geom.bit_words, cfg.nrzm, nrzm_last, fifo.p, fifo_bits);
+            launches++;
+            deframe_and_rs(nout * (long)geom.F);
+            long redo_from = -1;
+            if (cfg.kind == B200_FEC_METOP) {
+                // module_metop_ahrpt_decoder.cpp:59-72: ten consecutive decoder calls that end with the deframer in NOSYNC reset the Viterbi
+                const int ne = h_counters[1];
+                int ei = 0, st = 0;
+                {   // state before this segment = snapshot
+                    DefrState snap;
+                    B200_CUDA(cudaMemcpyAsync(&snap, dstate.p + 1, sizeof(DefrState), cudaMemcpyDeviceToHost, stream));
+                    B200_CUDA(cudaStreamSynchronize(stream));
+                    st = snap.state;
+                }
+                for (long k = 0; k < nout; k++) {
+                    const long end = fifo_bits0 + (k + 1) * (long)geom.F; // exclusive
+                    while (ei < ne && h_events[ei].pos < end)
+                        st = h_events[ei++].state;
+                    if (st == 2) {
+                        if (++nosync_runs >= 10) {
+                            nosync_runs = 0;
+                            redo_from = k;
+                            break;
+                        }
+                    } else
+                        nosync_runs = 0;
+                }
+            }
+            if (redo_from >= 0 && redo_from < nout - 1) {
+                // roll back to just after output chunk redo_from, with the Viterbi forced to IDLE
+                replays++;
+                const OutChunk &oc = outs[redo_from];
+                B200_CUDA(cudaMemcpyAsync(dstate.p, dstate.p + 1, sizeof(DefrState), cudaMemcpyDeviceToDevice, stream));
+                fifo_bits = fifo_bits0;
+                out_frames = out_frames0;
+                total_frames = total_frames0;
+                rs_corrected = rs_c0;
+                rs_failed = rs_f0;
+                deframe_and_rs((redo_from + 1) * (long)geom.F);
+                vit_state = 0;
+                main_next_start = oc.next_start;
+                enc_state = oc.enc_tail;
+                idle_st = oc.idle_st;
+                invalid = oc.invalid_after;
+                nosync_runs = 0;
+                next_c = oc.soft_chunk + 1;
+                if (cfg.nrzm) { /* METOP has no NRZ-M */ }
+                total_bits += (redo_from + 1) * (long)geom.F;
+                last_nbits += (redo_from + 1) * (long)geom.F;
+            } else {
+                if (redo_from >= 0)
+                    vit_state = 0; // reset after the last chunk: nothing to redo
+                if (cfg.nrzm)
+                    nrzm_last = last_raw;
+                total_bits += nout * (long)geom.F;
+                last_nbits += nout * (long)geom.F;
+            }
+            (void)nosync0;
+        }
+        c = next_c;
+    }
+    total_chunks += nch;
+    // keep the undecoded tail of the soft FIFO
+    const long used = nch * (long)geom.chunk, left = soft_have - used;
+    if (used > 0 && left > 0) {
+        // regions may overlap only if left > used; chunks are large, so copy through the head of the decision buffer when needed
+        if (left <= used)
+            B200_CUDA(cudaMemcpyAsync(softbuf.p, softbuf.p + used, left, cudaMemcpyDeviceToDevice, stream));
+        else {
+            B200_CUDA(cudaMemcpyAsync(dec.p, softbuf.p + used, left, cudaMemcpyDeviceToDevice, stream));
+            B200_CUDA(cudaMemcpyAsync(softbuf.p, dec.p, left, cudaMemcpyDeviceToDevice, stream));
+        }
+    }
+    soft_have = left;
+    B200_CUDA(cudaEventRecord(ev[1], stream));
+    B200_CUDA(cudaStreamSynchronize(stream));
+    B200_CUDA(cudaGetLastError());
+    cudaEventElapsedTime(&t_vit, ev[0], ev[1]);
+    (void)acc_frames_ms;
+}
+
+long Fec::pull(uint8_t *host_out, long cap)
+{
+    DeviceGuard g(cfg.device);
+    const long nb = out_frames * cadu_bytes;
+    B200_REQUIRE(nb <= cap, B200_ESTATE, "output buffer too small: need %ld bytes", nb);
+    if (nb > 0) {
+        B200_CUDA(cudaMemcpyAsync(host_out, frames_out.p, nb, cudaMemcpyDeviceToHost, stream));
+        B200_CUDA(cudaStreamSynchronize(stream));
+    }
+    out_frames = 0;
+    return nb;
+}
+
+void Fec::stats(b200_fec_stats *o)
+{
+    memset(o, 0, sizeof(*o));
+    o->soft_in = total_soft;
+    o->chunks = total_chunks;
+    o->bits_out = total_bits;
+    o->frames_out = total_frames;
+    o->viterbi_state = vit_state;
+    o->viterbi_ber = last_ber;
+    o->deframer_state = defr_state_now;
+    o->rs_corrected = rs_corrected;
+    o->rs_failed = rs_failed;
+    o->replays = replays;
+    o->kernel_launches = launches;
+}
+
+} // namespace b200
+
+using namespace b200;
+struct b200_fec
+{
+    Fec *f;
+};
+namespace b200
+{
+Fec *fec_of(b200_fec *h) { return h->f; }
+}
+
+extern "C" {
+b200_fec *b200_fec_create(const b200_fec_cfg *cfg)
+{
+    b200_fec *h = nullptr;
+    guarded([&] {
+        B200_REQUIRE(cfg != nullptr, B200_EINVAL, "cfg is NULL");
+        h = new b200_fec{new Fec(*cfg)};
+    });
+    return h;
+}
+void b200_fec_destroy(b200_fec *h)
+{
+    if (!h)
+        return;
+    delete h->f;
+    delete h;
+}
+int b200_fec_push_soft(b200_fec *h, const int8_t *host_soft, long n)
+{
+    return guarded([&] {
+        B200_REQUIRE(h && host_soft && n >= 0, B200_EINVAL, "bad argument");
+        h->f->push_host(host_soft, n);
+    });
+}
+int b200_fec_push_soft_device(b200_fec *h, const int8_t *dev_soft, long n)
+{
+    return guarded([&] {
+        B200_REQUIRE(h && dev_soft && n >= 0, B200_EINVAL, "bad argument");
+        h->f->push_device(dev_soft, n);
+    });
+}
+int b200_fec_pull_frames(b200_fec *h, uint8_t *out, long cap, long *nbytes)
+{
+    return guarded([&] {
+        B200_REQUIRE(h && out && nbytes, B200_EINVAL, "NULL argument");
+        *nbytes = h->f->pull(out, cap);
+    });
+}
+int b200_fec_debug_bits(b200_fec *h, uint8_t *out, long cap, long *n_out)
+{
+    return guarded([&] {
+        B200_REQUIRE(h && out && n_out, B200_EINVAL, "NULL argument");
+        Fec &f = *h->f;
+        B200_REQUIRE(f.last_nbits <= cap, B200_ESTATE, "output buffer too small: need %ld", f.last_nbits);
+        B200_REQUIRE(f.last_bits0 >= 0, B200_ESTATE, "the bits of the last push are no longer in the FIFO");
+        DeviceGuard g(f.cfg.device);
+        const long w0 = f.last_bits0 >> 5, w1 = (f.last_bits0 + f.last_nbits + 31) >> 5;
+        std::vector<uint32_t> tmp(w1 - w0 + 1);
+        if (w1 > w0) {
+            B200_CUDA(cudaMemcpyAsync(tmp.data(), f.fifo.p + w0, (w1 - w0) * 4, cudaMemcpyDeviceToHost, f.stream));
+            B200_CUDA(cudaStreamSynchronize(f.stream));
+        }
+        for (long i = 0; i < f.last_nbits; i++) {
+            const long b = f.last_bits0 + i - (w0 << 5);
+            out[i] = (tmp[b >> 5] >> (31 - (b & 31))) & 1;
+        }
+        *n_out = f.last_nbits;
+    });
+}
+int b200_fec_get_stats(b200_fec *h, b200_fec_stats *out)
+{
+    return guarded([&] {
+        B200_REQUIRE(h && out, B200_EINVAL, "NULL argument");
+        h->f->stats(out);
+    });
+}
+int b200_fec_cadu_bytes(b200_fec *h) { return h ? h->f->cadu_bytes : B200_EINVAL; }
+int b200_fec_chunk_size(b200_fec *h) { return h ? h->f->geom.chunk : B200_EINVAL; }
+}

@@ -1,0 +1,809 @@
+// Demodulator kernels (sm_100a): raw IQ -> AGC -> 31-tap RRC FIR -> Costas -> [OQPSK delay] -> M&M -> int8 soft.
+//
+// Reference semantics being reproduced (SatDump tree):
+//   sample conversion   src-core/common/dsp/io/baseband_interface.h:170-190
+//   AGC                 src-core/common/dsp/utils/agc.cpp:25-39
+//   RRC FIR             src-core/common/dsp/filter/fir.cpp:47-89, firdes.cpp:34-78
+//   Costas loop         src-core/common/dsp/pll/costas_loop.cpp:23-65
+//   OQPSK delay         src-core/common/dsp/demod/delay_one_imag.cpp:18-25
+//   M&M clock recovery  src-core/common/dsp/clock_recovery/clock_recovery_mm.cpp:52-121
+//   soft quantiser      src-core/pipeline/modules/demod/module_psk_demod.cpp:199-213
+//
+// The reference runs every stage as a serial per-sample loop. Here:
+//   * AGC: g' = g(1-r|x|) + r is an affine map -> per-tile composition (k_agc_compose), a scan over tiles
+//     (k_agc_scan) and an in-tile block scan in fp64, then an 8-sample replay of the reference's float recurrence.
+//   * FIR: data parallel, fused with conversion + AGC scale (k_agc_fir).
+//   * Costas / M&M: contracting feedback loops -> one thread per stream segment, started W samples early
+//     (warm-up) so it has converged onto the sequential trajectory at its first owned sample; the first segment
+//     starts from the exact carried state. Costas segments converge up to a k*2pi/order rotation, which
+//     k_costas_fix resolves as a prefix sum; k_rotate applies it (exactly) before M&M, whose TED is not
+//     rotation invariant. Junction consistency is checked on the device and reported in the stats.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200
+{
+
+constexpr int FIR_NT = 31;           // taps
+constexpr int FIR_TO = 2016;         // outputs per CTA
+constexpr int FIR_TL = 2048;         // samples loaded per CTA (32 halo + 2016)
+constexpr int FIR_THREADS = 256;
+constexpr int SEG_THREADS = 128;     // threads (= stream segments) per CTA in the loop kernels
+constexpr int MM_SMEM_BYTES = 64 * SEG_THREADS * 8 + 128 * 8 * 4;
+
+struct FirTaps { float h[32]; };
+
+struct Affine { double a, b; };     // g -> a*g + b
+#ifdef B200_DEFINE_KERNELS
+__device__ __forceinline__ Affine compose(const Affine &first, const Affine &second)
+{
+    Affine r;
+    r.a = second.a * first.a;
+    r.b = fma(second.a, first.b, second.b);
+    return r;
+}
+
+#endif // B200_DEFINE_KERNELS
+template <int FMT> struct RawBytes;
+template <> struct RawBytes<0> { static constexpr int v = 8; };
+template <> struct RawBytes<1> { static constexpr int v = 4; };
+template <> struct RawBytes<2> { static constexpr int v = 2; };
+
+// load 8 consecutive complex samples starting at sample index s0 (multiple of 8 relative to a 16-aligned base) and convert
+#ifdef B200_DEFINE_KERNELS
+template <int FMT>
+__device__ __forceinline__ void load8(const void *__restrict__ raw, long s0, long n_valid, float2 (&x)[8])
+{
+    if (s0 + 8 <= n_valid) {
+        if (FMT == 1) {
+            const int4 *p = reinterpret_cast<const int4 *>(reinterpret_cast<const int16_t *>(raw) + 2 * s0);
+            int4 v0 = __ldg(p), v1 = __ldg(p + 1);
+            int w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                x[i].x = __fdiv_rn((float)(short)(w[i] & 0xFFFF), 32767.0f);
+                x[i].y = __fdiv_rn((float)(short)(w[i] >> 16), 32767.0f);
+            }
+        } else if (FMT == 2) {
+            const int4 *p = reinterpret_cast<const int4 *>(reinterpret_cast<const int8_t *>(raw) + 2 * s0);
+            int4 v0 = __ldg(p);
+            int w[4] = {v0.x, v0.y, v0.z, v0.w};
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                x[2 * i].x = __fdiv_rn((float)(signed char)(w[i] & 0xFF), 127.0f);
+                x[2 * i].y = __fdiv_rn((float)(signed char)((w[i] >> 8) & 0xFF), 127.0f);
+                x[2 * i + 1].x = __fdiv_rn((float)(signed char)((w[i] >> 16) & 0xFF), 127.0f);
+                x[2 * i + 1].y = __fdiv_rn((float)(signed char)((w[i] >> 24) & 0xFF), 127.0f);
+            }
+        } else {
+            const float4 *p = reinterpret_cast<const float4 *>(reinterpret_cast<const float2 *>(raw) + s0);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                float4 v = __ldg(p + i);
+                x[2 * i] = make_float2(v.x, v.y);
+                x[2 * i + 1] = make_float2(v.z, v.w);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            long s = s0 + i;
+            float2 v = make_float2(0.f, 0.f);
+            if (s < n_valid) {
+                if (FMT == 1) {
+                    const int16_t *p = reinterpret_cast<const int16_t *>(raw) + 2 * s;
+                    v.x = __fdiv_rn((float)p[0], 32767.0f);
+                    v.y = __fdiv_rn((float)p[1], 32767.0f);
+                } else if (FMT == 2) {
+                    const int8_t *p = reinterpret_cast<const int8_t *>(raw) + 2 * s;
+                    v.x = __fdiv_rn((float)p[0], 127.0f);
+                    v.y = __fdiv_rn((float)p[1], 127.0f);
+                } else
+                    v = reinterpret_cast<const float2 *>(raw)[s];
+            }
+            x[i] = v;
+        }
+    }
+}
+
+// affine map of one AGC step for input sample x:  g' = g*(1 - rate*|x|) + rate*ref   (agc.cpp:30-33 rewritten)
+__device__ __forceinline__ Affine agc_map(float2 x, float rate)
+{
+    float mag = sqrtf(x.x * x.x + x.y * x.y);
+    Affine m;
+    m.a = 1.0 - (double)rate * (double)mag;
+    m.b = (double)rate;
+    return m;
+}
+
+__device__ __forceinline__ Affine warp_scan_inclusive(Affine v, int lane)
+{
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        double pa = __shfl_up_sync(0xffffffffu, v.a, off);
+        double pb = __shfl_up_sync(0xffffffffu, v.b, off);
+        if (lane >= off) {
+            Affine p{pa, pb};
+            v = compose(p, v);
+        }
+    }
+    return v;
+}
+
+// Tile geometry shared by k_agc_compose and k_agc_fir: tile k holds local samples 0..2047 <-> stream samples
+// lstart+i with lstart = k*FIR_TO - 32. Its AGC seed is the gain before local sample (k==0 ? 32 : 0); tile 0's first
+// 32 local samples are the previous batch's AGC outputs (FIR history), not scanned.
+__device__ __forceinline__ long tile_lstart(int k) { return (long)k * FIR_TO - 32; }
+
+// ---------------------------------------------------------------- K0a: per-tile affine composition
+template <int FMT>
+__global__ void __launch_bounds__(FIR_THREADS) k_agc_compose(const void *__restrict__ raw, long N, float rate, Affine *__restrict__ tile_map)
+{
+    const int k = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const long lstart = tile_lstart(k);
+    __shared__ Affine wsum[FIR_THREADS / 32];
+    Affine m{1.0, 0.0};
+    // tile k's map covers stream samples [seed_pos(k), seed_pos(k+1)) = local [k?0:32, 2016)
+    const int l0 = 8 * t;
+    if (l0 < FIR_TO && (k > 0 || l0 >= 32)) {
+        float2 x[8];
+        load8<FMT>(raw, lstart + l0, N, x);
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            if (lstart + l0 + i < N)
+                m = compose(m, agc_map(x[i], rate));
+    }
+    m = warp_scan_inclusive(m, lane);
+    if (lane == 31)
+        wsum[warp] = m;
+    __syncthreads();
+    if (t == 0) {
+        Affine tot = wsum[0];
+        for (int w = 1; w < FIR_THREADS / 32; w++)
+            tot = compose(tot, wsum[w]);
+        tile_map[k] = tot;
+    }
+}
+
+// ---------------------------------------------------------------- K0b: scan over tiles -> gain seed of every tile
+__global__ void __launch_bounds__(1024) k_agc_scan(const Affine *__restrict__ tile_map, int ntiles, const float *__restrict__ gain_in,
+                                                  double *__restrict__ seeds)
+{
+    __shared__ Affine wsum[32];
+    __shared__ double g_run;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    if (t == 0)
+        g_run = (double)*gain_in;
+    __syncthreads();
+    for (int base = 0; base < ntiles; base += 1024) {
+        int k = base + t;
+        Affine m{1.0, 0.0};
+        if (k < ntiles)
+            m = tile_map[k];
+        Affine inc = warp_scan_inclusive(m, lane);
+        if (lane == 31)
+            wsum[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            Affine w = wsum[lane];
+            w = warp_scan_inclusive(w, lane);
+            wsum[lane] = w;
+        }
+        __syncthreads();
+        Affine pre{1.0, 0.0}; // composition of everything before this thread's tile in this round
+        if (warp > 0)
+            pre = wsum[warp - 1];
+        // exclusive = pre o (inclusive of previous lane)
+        double ea = __shfl_up_sync(0xffffffffu, inc.a, 1), eb = __shfl_up_sync(0xffffffffu, inc.b, 1);
+        Affine excl = pre;
+        if (lane > 0)
+            excl = compose(pre, Affine{ea, eb});
+        double g0 = g_run;
+        if (k < ntiles)
+            seeds[k] = fma(excl.a, g0, excl.b);
+        __syncthreads();
+        if (t == 1023) {
+            Affine tot = compose(pre, inc);
+            g_run = fma(tot.a, g0, tot.b);
+        }
+        __syncthreads();
+    }
+    if (t == 0)
+        seeds[ntiles] = g_run;
+}
+
+// padded smem index: conflict-free 64-bit accesses at a thread stride of 8 samples
+__device__ __forceinline__ int pidx(int i) { return i + (i >> 3); }
+
+// ---------------------------------------------------------------- K1: convert + AGC + 31-tap FIR
+// state_io[0] = carried gain (in: unused here, out: gain after the last sample), flags: bit0 = AGC clamp hit
+template <int FMT, bool DUMP>
+__global__ void __launch_bounds__(FIR_THREADS) k_agc_fir(const void *__restrict__ raw, long N, float rate, const double *__restrict__ seeds,
+                                                         const FirTaps taps, const float2 *__restrict__ tail_in, float2 *__restrict__ tail_out,
+                                                         float2 *__restrict__ fir_out, float2 *__restrict__ agc_dump, float *__restrict__ gain_out,
+                                                         int *__restrict__ flags)
+{
+    __shared__ float2 xs[FIR_TL + FIR_TL / 8 + 8];
+    __shared__ Affine wsum[FIR_THREADS / 32];
+    const int k = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const long lstart = tile_lstart(k);
+    const int l0 = 8 * t;
+    const bool hist = (k == 0 && l0 < 32); // previous batch's AGC outputs, passed through
+    float2 x[8];
+    Affine m{1.0, 0.0};
+    if (hist) {
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            x[i] = tail_in[l0 + i];
+    } else {
+        load8<FMT>(raw, lstart + l0, N, x);
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            if (lstart + l0 + i < N)
+                m = compose(m, agc_map(x[i], rate));
+    }
+    Affine inc = warp_scan_inclusive(m, lane);
+    if (lane == 31)
+        wsum[warp] = inc;
+    __syncthreads();
+    Affine pre{1.0, 0.0};
+    for (int w = 0; w < warp; w++)
+        pre = compose(pre, wsum[w]);
+    double ea = __shfl_up_sync(0xffffffffu, inc.a, 1), eb = __shfl_up_sync(0xffffffffu, inc.b, 1);
+    Affine excl = pre;
+    if (lane > 0)
+        excl = compose(pre, Affine{ea, eb});
+    if (!hist) {
+        // replay the reference's float recurrence over this thread's 8 samples from the scanned seed
+        float g = (float)fma(excl.a, seeds[k], excl.b);
+        bool clamped = false;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            long s = lstart + l0 + i;
+            float2 o = make_float2(x[i].x * g, x[i].y * g);
+            if (s < N) {
+                float mag = sqrtf(__fadd_rn(__fmul_rn(o.x, o.x), __fmul_rn(o.y, o.y)));
+                g = (float)((double)g + (double)rate * (1.0 - (double)mag));
+                if (g > 65536.0f) {
+                    g = 65536.0f;
+                    clamped = true;
+                }
+                if (DUMP)
+                    agc_dump[s] = o;
+                if (s >= N - 32)
+                    tail_out[s - (N - 32)] = o;
+                if (s == N - 1)
+                    *gain_out = g;
+            }
+            x[i] = o;
+        }
+        if (clamped)
+            atomicOr(flags, 1);
+    } else if (N < 32) {
+        // degenerate tiny batch: keep the still-needed part of the old history in the new tail
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            long d = (long)(l0 + i) - N; // old tail index l0+i moves to position l0+i-N
+            if (d >= 0)
+                tail_out[d] = x[i];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+        xs[pidx(l0 + i)] = x[i];
+    __syncthreads();
+
+    // FIR: thread t (< 252) -> outputs local 32+8t .. +7 ; y[i] = sum_j x[i-30+j] * h[30-j], oldest first (fir.cpp:74-83)
+    if (t < FIR_TO / 8) {
+        float2 acc[8];
+#pragma unroll
+        for (int o = 0; o < 8; o++)
+            acc[o] = make_float2(0.f, 0.f);
+        const int first = 8 * t + 2; // local index of the oldest input of output 0
+#pragma unroll
+        for (int mI = 0; mI < 38; mI++) {
+            float2 v = xs[pidx(first + mI)];
+#pragma unroll
+            for (int o = 0; o < 8; o++) {
+                const int j = mI - o; // tap position (0 = oldest)
+                if (j >= 0 && j < FIR_NT) {
+                    acc[o].x = fmaf(v.x, taps.h[FIR_NT - 1 - j], acc[o].x);
+                    acc[o].y = fmaf(v.y, taps.h[FIR_NT - 1 - j], acc[o].y);
+                }
+            }
+        }
+        const long s0 = (long)k * FIR_TO + 8 * t;
+        if (s0 + 8 <= N) {
+            float4 *p = reinterpret_cast<float4 *>(fir_out + s0);
+#pragma unroll
+            for (int o = 0; o < 4; o++)
+                p[o] = make_float4(acc[2 * o].x, acc[2 * o].y, acc[2 * o + 1].x, acc[2 * o + 1].y);
+        } else {
+#pragma unroll
+            for (int o = 0; o < 8; o++)
+                if (s0 + o < N)
+                    fir_out[s0 + o] = acc[o];
+        }
+    }
+}
+
+// ---------------------------------------------------------------- cp.async helpers (8-byte granules)
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src)
+{
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// ---------------------------------------------------------------- K2: Costas loop, one thread per segment
+#endif // B200_DEFINE_KERNELS
+struct CostasParams
+{
+    int order;          // 2, 4, 8
+    float alpha, beta, fmin, fmax;
+};
+struct LoopRec { float ph_start, fr_start, ph_end, fr_end; };
+
+#ifdef B200_DEFINE_KERNELS
+__device__ __forceinline__ float costas_error(float vr, float vi, int order)
+{
+    float err;
+    if (order == 4)
+        err = (vr > 0.0f ? 1.0f : -1.0f) * vi - (vi > 0.0f ? 1.0f : -1.0f) * vr;
+    else if (order == 2)
+        err = vr * vi;
+    else {
+        const float K = 0.41421356237309515f; // sqrtf(2.0) - 1 rounded to float
+        if (fabsf(vr) >= fabsf(vi))
+            err = ((vr > 0.0f ? 1.0f : -1.0f) * vi - (vi > 0.0f ? 1.0f : -1.0f) * vr * K);
+        else
+            err = ((vr > 0.0f ? 1.0f : -1.0f) * vi * K - (vi > 0.0f ? 1.0f : -1.0f) * vr);
+    }
+    return 0.5f * (fabsf(err + 1.0f) - fabsf(err - 1.0f)); // branchless_clip(err, 1)
+}
+
+// in/out: N samples. Segment s owns samples [s*L, min((s+1)L, N)); thread warms up from max(0, s*L - W).
+// state_in = {phase, freq} carried from the previous batch (exact start of segment 0 and of any clipped warm-up).
+__global__ void __launch_bounds__(SEG_THREADS) k_costas(const float2 *__restrict__ in, long N, int L, int W, int nseg, CostasParams P,
+                                                         const float *__restrict__ state_in, float2 *__restrict__ out, LoopRec *__restrict__ rec)
+{
+    __shared__ float2 ring[32][SEG_THREADS];
+    const int t = threadIdx.x;
+    const int s = blockIdx.x * SEG_THREADS + t;
+    if (s >= nseg)
+        return;
+    const long own0 = (long)s * L;
+    const long own1 = min(own0 + L, N);
+    long start = own0 - W;
+    float phase = 0.f, freq = state_in[1];
+    if (start <= 0) {
+        start = 0;
+        phase = state_in[0];
+    }
+    const long row0 = start >> 4, row1 = (own1 + 15) >> 4; // rows of 16 samples, [row0, row1)
+    auto issue = [&](long r) {
+        if (r < row1) {
+            const long b = r << 4;
+            const int slot0 = (int)(r & 1) << 4;
+#pragma unroll
+            for (int j = 0; j < 16; j++)
+                if (b + j < N)
+                    cp_async8(&ring[slot0 + j][t], in + b + j);
+        }
+        cp_async_commit();
+    };
+    issue(row0);
+    LoopRec lr;
+    lr.ph_start = phase;
+    lr.fr_start = freq;
+    for (long r = row0; r < row1; r++) {
+        issue(r + 1);
+        cp_async_wait<1>();
+        const long b = r << 4;
+        const int slot0 = (int)(r & 1) << 4;
+        float2 o[16];
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            const long n = b + j;
+            float2 x = ring[slot0 + j][t];
+            if (n == own0) {
+                lr.ph_start = phase;
+                lr.fr_start = freq;
+            }
+            if (n >= start && n < own1) {
+                float sn, cs;
+                sincosf(phase, &sn, &cs);
+                // in * (cos(-phase) + j sin(-phase))  (costas_loop.cpp:26)
+                float vr = x.x * cs + x.y * sn;
+                float vi = x.y * cs - x.x * sn;
+                o[j] = make_float2(vr, vi);
+                float err = costas_error(vr, vi, P.order);
+                freq = freq + P.beta * err;
+                phase = phase + (freq + P.alpha * err);
+                while (phase > 6.283185307179586)
+                    phase = (float)((double)phase - 6.283185307179586);
+                while (phase < -6.283185307179586)
+                    phase = (float)((double)phase + 6.283185307179586);
+                if (freq > P.fmax)
+                    freq = P.fmax;
+                if (freq < P.fmin)
+                    freq = P.fmin;
+            } else
+                o[j] = make_float2(0.f, 0.f);
+        }
+        if (b >= own0 && b + 16 <= own1) {
+            float4 *p = reinterpret_cast<float4 *>(out + b);
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                p[j] = make_float4(o[2 * j].x, o[2 * j].y, o[2 * j + 1].x, o[2 * j + 1].y);
+        } else if (b + 16 > own0 && b < own1) {
+#pragma unroll
+            for (int j = 0; j < 16; j++)
+                if (b + j >= own0 && b + j < own1)
+                    out[b + j] = o[j];
+        }
+    }
+    cp_async_wait<0>();
+    lr.ph_end = phase;
+    lr.fr_end = freq;
+    rec[s] = lr;
+}
+
+// ---------------------------------------------------------------- K2b: resolve per-segment rotation (prefix sum mod order)
+// quad[s] = number of 2pi/order steps segment s's phase runs AHEAD of the sequential loop. Also publishes the true
+// carried loop state. unconv counts junctions whose residual exceeds tol.
+__global__ void __launch_bounds__(1024) k_costas_fix(const LoopRec *__restrict__ rec, int nseg, int order, float tol_phase, float tol_freq,
+                                                    uint8_t *__restrict__ quad, float *__restrict__ state_out, int *__restrict__ unconv)
+{
+    __shared__ int wsum[32];
+    __shared__ int run;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const float step = 6.283185307179586f / (float)order;
+    if (t == 0)
+        run = 0;
+    __syncthreads();
+    int bad = 0;
+    for (int base = 0; base < nseg; base += 1024) {
+        int s = base + t, k = 0;
+        if (s > 0 && s < nseg) {
+            float d = rec[s].ph_start - rec[s - 1].ph_end;
+            float q = rintf(d / step);
+            float resid = fabsf(d - q * step);
+            k = ((int)q % order + order) % order;
+            if (resid > tol_phase || fabsf(rec[s].fr_start - rec[s - 1].fr_end) > tol_freq)
+                bad++;
+        }
+        int v = k;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            int p = __shfl_up_sync(0xffffffffu, v, off);
+            if (lane >= off)
+                v += p;
+        }
+        if (lane == 31)
+            wsum[warp] = v;
+        __syncthreads();
+        if (warp == 0) {
+            int w = wsum[lane];
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                int p = __shfl_up_sync(0xffffffffu, w, off);
+                if (lane >= off)
+                    w += p;
+            }
+            wsum[lane] = w;
+        }
+        __syncthreads();
+        int tot = run + v + (warp > 0 ? wsum[warp - 1] : 0);
+        if (s < nseg)
+            quad[s] = (uint8_t)(tot % order);
+        __syncthreads();
+        if (t == 1023)
+            run = tot % order;
+        __syncthreads();
+    }
+    // reduce bad count
+    for (int off = 16; off; off >>= 1)
+        bad += __shfl_xor_sync(0xffffffffu, bad, off);
+    if (lane == 0 && bad)
+        atomicAdd(unconv, bad);
+    if (t == 0) {
+        int q = quad[nseg - 1];
+        float ph = (float)((double)rec[nseg - 1].ph_end - (double)q * (6.283185307179586 / order));
+        while (ph > 6.283185307179586)
+            ph = (float)((double)ph - 6.283185307179586);
+        while (ph < -6.283185307179586)
+            ph = (float)((double)ph + 6.283185307179586);
+        state_out[0] = ph;
+        state_out[1] = rec[nseg - 1].fr_end;
+    }
+}
+
+__device__ __forceinline__ float2 rot_steps(float2 v, int q, int order)
+{
+    // multiply by e^{+j q 2pi/order}
+    if (order == 4) {
+        if (q == 1) return make_float2(-v.y, v.x);
+        if (q == 2) return make_float2(-v.x, -v.y);
+        if (q == 3) return make_float2(v.y, -v.x);
+        return v;
+    } else if (order == 2) {
+        return q ? make_float2(-v.x, -v.y) : v;
+    } else {
+        if (q == 0) return v;
+        float sn, cs;
+        sincospif(2.0f * (float)q / (float)order, &sn, &cs);
+        return make_float2(v.x * cs - v.y * sn, v.y * cs + v.x * sn);
+    }
+}
+
+// ---------------------------------------------------------------- K2c: apply rotation (+ OQPSK delay) -> M&M input
+// mmin has a 16-sample front pad: mmin[16 + n]; mmin[8..15] = last 8 inputs of the previous batch (hist_in).
+// `src` is the Costas output (or, with order == 0, the FIR output passed straight through).
+__global__ void k_rotate(const float2 *__restrict__ src, long N, int L, int order, int oqpsk, const uint8_t *__restrict__ quad,
+                         const float2 *__restrict__ hist_in /*8: true pre-delay values*/, float2 *__restrict__ hist_out,
+                         float2 *__restrict__ mmin)
+{
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long n = (long)blockIdx.x * blockDim.x + threadIdx.x - 8; n < N; n += stride) {
+        float2 cur, prev;
+        if (n >= 0) {
+            cur = src[n];
+            if (order)
+                cur = rot_steps(cur, quad[n / L], order);
+        } else
+            cur = hist_in[8 + n];
+        if (n >= N - 8 && n >= 0) // (the host rejects batches below 64 samples)
+            hist_out[n - (N - 8)] = cur;
+        float2 v = cur;
+        if (oqpsk) {
+            if (n - 1 >= 0) {
+                prev = src[n - 1];
+                if (order)
+                    prev = rot_steps(prev, quad[(n - 1) / L], order);
+            } else if (n - 1 >= -8)
+                prev = hist_in[8 + n - 1];
+            else
+                prev = make_float2(0.f, 0.f);
+            v.y = prev.y;
+        }
+        mmin[16 + n] = v;
+    }
+}
+
+// ---------------------------------------------------------------- K3: Mueller & Mueller clock recovery, one thread per segment
+#endif // B200_DEFINE_KERNELS
+struct MMParams
+{
+    float omega_mid, omega_limit, omega_gain, mu_gain;
+};
+struct MMState // carried between batches (exact for segment 0)
+{
+    float mu, omega;
+    float2 p0, p1, p2, c0, c1, c2;
+    int inc; // window start of the next symbol, relative to the batch start, in buffer coordinates
+    int pad;
+};
+struct MMRec { int u_first, u_final, count, pad; float mu_first, mu_final, omega_first, omega_final; };
+
+#ifdef B200_DEFINE_KERNELS
+__global__ void __launch_bounds__(SEG_THREADS) k_mm(const float2 *__restrict__ mmin /* 16-sample front pad */, long N, int L, int W, int nseg,
+                                                     MMParams P, const MMState *__restrict__ st_in, MMState *__restrict__ st_out,
+                                                     const float *__restrict__ bank /*128x8*/, float2 *__restrict__ slots, int cap,
+                                                     MMRec *__restrict__ rec)
+{
+    extern __shared__ __align__(16) unsigned char mm_smem[];
+    float2(*ring)[SEG_THREADS] = reinterpret_cast<float2(*)[SEG_THREADS]>(mm_smem);      // [64][SEG_THREADS]
+    float *sbank = reinterpret_cast<float *>(mm_smem + 64 * SEG_THREADS * sizeof(float2)); // [128*8]
+    const int t = threadIdx.x;
+    for (int i = t; i < 128 * 8; i += SEG_THREADS)
+        sbank[i] = bank[i];
+    __syncthreads();
+    const int s = blockIdx.x * SEG_THREADS + t;
+    if (s >= nseg)
+        return;
+    const long own0 = (long)s * L, own1 = min(own0 + L, N);
+    // buffer coordinate u: window = input samples u-7 .. u
+    long u;
+    float mu, omega;
+    float2 p0, p1, p2, c0, c1, c2;
+    long ustart = own0 - W;
+    if (ustart <= 0) {
+        MMState st = *st_in;
+        mu = st.mu; omega = st.omega; p0 = st.p0; p1 = st.p1; p2 = st.p2; c0 = st.c0; c1 = st.c1; c2 = st.c2;
+        u = st.inc;
+    } else {
+        mu = 0.5f; omega = st_in->omega;
+        p0 = p1 = p2 = c0 = c1 = c2 = make_float2(0.f, 0.f);
+        u = ustart;
+    }
+    // rows of 16 samples; sample n lives in ring[(n + 64) & 63]; rows cover n in [16r, 16r+16)
+    long r; // floor((u-7)/16): row holding the oldest sample of the first window
+    {
+        long a = u - 7;
+        r = (a >= 0) ? (a >> 4) : -((-a + 15) >> 4);
+    }
+    const long rend = (own1 + 15) >> 4; // exclusive: samples < own1 <= N are ever needed
+    auto issue = [&](long row) {
+        if (row < rend) {
+            const long b = row << 4;
+#pragma unroll
+            for (int j = 0; j < 16; j++)
+                if (b + j < N)
+                    cp_async8(&ring[(int)((b + j + 64) & 63)][t], mmin + 16 + b + j);
+        }
+        cp_async_commit();
+    };
+    issue(r);
+    issue(r + 1);
+    int count = 0, u_first = -1;
+    float mu_first = 0.f, omega_first = 0.f;
+    float2 *my = slots + (long)s * cap;
+    // row loop: with rows <= rr+... loaded we may process every symbol whose newest sample u < 16*(rr+1)
+    for (long rr = r + 1; rr < rend + 1; rr++) {
+        issue(rr + 1);
+        cp_async_wait<1>(); // rows <= rr complete
+        const long lim = min((rr + 1) << 4, own1);
+        while (u < lim) {
+            if (u >= own0 && u_first < 0) {
+                u_first = (int)u;
+                mu_first = mu;
+                omega_first = omega;
+            }
+            p2 = p1; p1 = p0; c2 = c1; c1 = c0;
+            int imu = (int)rintf(mu * 128.0f);
+            imu = max(0, min(127, imu));
+            const float *tp = &sbank[imu * 8];
+            float ar = 0.f, ai = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                float2 x = ring[(int)((u - 7 + k + 64) & 63)][t];
+                ar = fmaf(x.x, tp[k], ar);
+                ai = fmaf(x.y, tp[k], ai);
+            }
+            p0 = make_float2(ar, ai);
+            c0 = make_float2(ar > 0.0f ? 1.0f : 0.0f, ai > 0.0f ? 1.0f : 0.0f);
+            // Re[(p0-p2) conj(c1) - (c0-c2) conj(p1)]  (clock_recovery_mm.cpp:103)
+            float xr = (p0.x - p2.x) * c1.x + (p0.y - p2.y) * c1.y;
+            float yr = (c0.x - c2.x) * p1.x + (c0.y - c2.y) * p1.y;
+            float pe = xr - yr;
+            pe = fminf(1.0f, fmaxf(-1.0f, pe));
+            if (u >= own0) {
+                if (count < cap)
+                    my[count] = p0;
+                count++;
+            }
+            omega = omega + P.omega_gain * pe;
+            float dev = omega - P.omega_mid;
+            dev = fminf(P.omega_limit, fmaxf(-P.omega_limit, dev));
+            omega = P.omega_mid + dev;
+            mu = (mu + omega) + P.mu_gain * pe;
+            float fl = floorf(mu);
+            u += (long)fl;
+            mu -= fl;
+        }
+        if (u >= own1)
+            break;
+    }
+    cp_async_wait<0>();
+    MMRec mr;
+    mr.u_first = u_first < 0 ? (int)u : u_first; // segment without symbols: report where the next one lies
+    mr.mu_first = u_first < 0 ? mu : mu_first;
+    mr.omega_first = u_first < 0 ? omega : omega_first;
+    mr.u_final = (int)u;
+    mr.mu_final = mu;
+    mr.omega_final = omega;
+    mr.count = count;
+    mr.pad = 0;
+    rec[s] = mr;
+    if (s == nseg - 1) {
+        MMState st;
+        st.mu = mu; st.omega = omega; st.p0 = p0; st.p1 = p1; st.p2 = p2; st.c0 = c0; st.c1 = c1; st.c2 = c2;
+        st.inc = (int)(u - N);
+        st.pad = 0;
+        *st_out = st;
+    }
+}
+
+// ---------------------------------------------------------------- K3b: symbol offsets (exclusive scan) + junction check
+__global__ void __launch_bounds__(1024) k_mm_scan(const MMRec *__restrict__ rec, int nseg, float tol_mu, long *__restrict__ offs /*nseg+1*/,
+                                                 int *__restrict__ unconv, int cap, int *__restrict__ flags)
+{
+    __shared__ long wsum[32];
+    __shared__ long run;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    if (t == 0)
+        run = 0;
+    __syncthreads();
+    int bad = 0, over = 0;
+    for (int base = 0; base < nseg; base += 1024) {
+        int s = base + t;
+        long c = 0;
+        if (s < nseg) {
+            c = rec[s].count;
+            if (c > cap)
+                over = 1;
+            if (s > 0) {
+                MMRec a = rec[s - 1], b = rec[s];
+                if (a.u_final != b.u_first || fabsf(a.mu_final - b.mu_first) > tol_mu)
+                    bad++;
+            }
+        }
+        long v = c;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            long p = __shfl_up_sync(0xffffffffu, v, off);
+            if (lane >= off)
+                v += p;
+        }
+        if (lane == 31)
+            wsum[warp] = v;
+        __syncthreads();
+        if (warp == 0) {
+            long w = wsum[lane];
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                long p = __shfl_up_sync(0xffffffffu, w, off);
+                if (lane >= off)
+                    w += p;
+            }
+            wsum[lane] = w;
+        }
+        __syncthreads();
+        long incl = run + v + (warp > 0 ? wsum[warp - 1] : 0);
+        if (s < nseg)
+            offs[s] = incl - c;
+        __syncthreads();
+        if (t == 1023)
+            run = incl;
+        __syncthreads();
+    }
+    for (int off = 16; off; off >>= 1) {
+        bad += __shfl_xor_sync(0xffffffffu, bad, off);
+        over |= __shfl_xor_sync(0xffffffffu, over, off);
+    }
+    if (lane == 0 && bad)
+        atomicAdd(unconv, bad);
+    if (lane == 0 && over)
+        atomicOr(flags, 2);
+    if (t == 0)
+        offs[nseg] = run;
+}
+
+// module_demod_base.h:106-113 (clamp) applied to re*scale / im*scale
+__device__ __forceinline__ int8_t soft_quant(float x)
+{
+    if (x < -128.0f) return -127;
+    if (x > 127.0f) return 127;
+    return (int8_t)(int)x;
+}
+
+// ---------------------------------------------------------------- K3c: compact per-segment symbol slots -> contiguous symbols + int8 soft
+__global__ void __launch_bounds__(256) k_mm_compact(const float2 *__restrict__ slots, int cap, const MMRec *__restrict__ rec,
+                                                   const long *__restrict__ offs, int nseg, int bpsk, float2 *__restrict__ sym_out,
+                                                   int8_t *__restrict__ soft_out)
+{
+    for (int s = blockIdx.x; s < nseg; s += gridDim.x) {
+        const int c = min(rec[s].count, cap);
+        const long o = offs[s];
+        const float2 *src = slots + (long)s * cap;
+        for (int i = threadIdx.x; i < c; i += blockDim.x) {
+            float2 v = src[i];
+            if (sym_out)
+                sym_out[o + i] = v;
+            if (bpsk)
+                soft_out[o + i] = soft_quant(v.x * 50.0f);
+            else {
+                char2 q;
+                q.x = soft_quant(v.x * 100.0f);
+                q.y = soft_quant(v.y * 100.0f);
+                reinterpret_cast<char2 *>(soft_out)[o + i] = q;
+            }
+        }
+    }
+}
+
+#endif // B200_DEFINE_KERNELS
+} // namespace b200

@@ -1,0 +1,70 @@
+// Host side of the demodulator: owns the device buffers / carried loop state of ONE baseband stream and launches
+// the kernels of demod.cuh for each pushed batch. Mirrors what PSKDemodModule::init() builds
+// (src-core/pipeline/modules/demod/module_psk_demod.cpp:86-136, module_demod_base.cpp:59-208).
+#pragma once
+#include "demod.cuh"
+#include "host_common.h"
+#include <vector>
+
+namespace b200
+{
+
+// carried loop state, double buffered by batch parity (kernels read [cur], write [cur^1])
+struct DemodDevState
+{
+    float gain[2];
+    float costas[2][2]; // phase, freq
+    MMState mm[2];
+    float2 agc_tail[2][32];
+    float2 mm_hist[2][8];
+    int flags;          // bit0 AGC clamp, bit1 M&M slot overflow
+    int costas_unconv;
+    int mm_unconv;
+    int pad;
+};
+
+class Demod
+{
+  public:
+    explicit Demod(const b200_demod_cfg &cfg);
+    ~Demod();
+    // Processes one batch already resident on the device. If soft_dst != nullptr the int8 soft symbols are appended
+    // there (device pointer), otherwise into the object's own soft buffer. Returns the number of symbols produced.
+    long process(const void *d_raw, long nsamples, int8_t *soft_dst);
+    long push_host(const void *h_raw, long nsamples, int8_t *soft_dst);
+    void stats(b200_demod_stats *out);
+
+    b200_demod_cfg cfg;
+    cudaStream_t stream = nullptr;
+    int bps;       // soft bytes per symbol (1 BPSK, else 2)
+    int order;     // Costas order, 0 = none
+    float sps;
+    std::vector<float> rrc, bank;
+    long last_n = 0, last_syms = 0;
+    long total_in = 0, total_syms = 0, launches = 0;
+    int parity = 0;
+    float t_agcfir = 0, t_costas = 0, t_mm = 0; // ms of the last batch
+    DevBuf<unsigned char> raw;
+    DevBuf<float2> bufA, bufB, agc_dump, fir_dump, slots, sym_out;
+    DevBuf<int8_t> soft;
+    DevBuf<Affine> tile_map;
+    DevBuf<double> seeds;
+    DevBuf<LoopRec> crec;
+    DevBuf<MMRec> mrec;
+    DevBuf<uint8_t> quad;
+    DevBuf<long> offs;
+    DevBuf<float> d_bank;
+    DevBuf<DemodDevState> st;
+    long *h_total = nullptr; // pinned
+    DemodDevState *h_state = nullptr; // pinned snapshot for stats
+    cudaEvent_t ev[4];
+    int Wc, Wm, seg_cap_threads;
+    long max_batch;
+    int slot_cap_for(int L) const;
+    int choose_L(long n) const;
+};
+
+void design_rrc(double gain, double fs, double rs, double alpha, int ntaps, std::vector<float> &out);
+void design_mm_bank(std::vector<float> &out);
+
+} // namespace b200

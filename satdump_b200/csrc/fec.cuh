@@ -1,0 +1,782 @@
+// FEC kernels (sm_100a): int8 soft symbols -> Viterbi k=7 (r=1/2, MetOp-punctured 3/4) -> ASM deframer -> derandomiser
+// -> RS(255,223|239) -> CADUs. All integer; results are bit-exact with the reference given the same soft bytes.
+//
+// Reference semantics being reproduced (SatDump tree):
+//   rotate_soft                      src-core/common/codings/rotation.cpp:4-63
+//   signed_soft_to_unsigned          src-core/common/codings/viterbi/utils.cpp:3-11
+//   Viterbi3_4::depuncture (MetOp)   src-core/common/codings/viterbi/viterbi_3_4.cpp:84-104
+//   ACS kernel                       src-core/common/codings/viterbi/volk_k7_r2_generic_fixed.h:80-163
+//   CCDecoder chunk semantics        src-core/common/codings/viterbi/cc_decoder.cpp:159-209,228-302
+//   lock machines / BER              viterbi_3_4.cpp:36-49,110-173 ; viterbi_1_2.cpp:36-116
+//   NRZ-M                            src-core/common/codings/differential/nrzm.cpp:24-33
+//   deframer                         src-core/common/codings/deframing/bpsk_ccsds_deframer.cpp:24-122
+//   derandomiser                     src-core/common/codings/randomization.cpp:72-78
+//   Reed-Solomon                     src-core/common/codings/reedsolomon/reedsolomon.cpp:53-116 + libs/correct/reed-solomon/decode.c
+//
+// Parallel formulation: one warp per Viterbi chunk (lane i owns butterfly i = states i, i+32; path metrics move with
+// two __shfl_sync per step; the per-step renormalisation is a warp min; decisions are the two __ballot_sync words).
+// A chunk depends on its predecessor only through a 6-bit start state, which k_vit_spec predicts from the tail of the
+// previous chunk and the host verifies against the real chainback result. Lock search (rare) runs as a serial warp.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200
+{
+
+constexpr int VIT_TESTLEN = 2048; // TEST_BITS_LENGTH (viterbi_3_4.h:3)
+constexpr int VIT_SPEC_STEPS_34 = 768;
+constexpr int VIT_SPEC_STEPS_12 = 512;
+
+struct VitGeom
+{
+    int rate34;   // 1: MetOp punctured 3/4, 0: rate 1/2
+    int chunk;    // soft bytes per decoder call
+    int F;        // decoded bits per chunk
+    int dec_stride; // decision rows per chunk (F + 6 rounded up to 8)
+    int bit_words;  // 32-bit words per chunk in the raw bit store
+};
+
+struct VitHyp { int swap, phase, shift; };
+
+// soft byte k of the chunk after rotate_soft(swap, phase) and signed_soft_to_unsigned
+#ifdef B200_DEFINE_KERNELS
+__device__ __forceinline__ int soft_u8(const int8_t *__restrict__ c, int k, const VitHyp h)
+{
+    const int pair = k & ~1, isq = k & 1;
+    int vi = c[pair], vq = c[pair + 1];
+    if (vi == -128) vi = -127;
+    if (vq == -128) vq = -127;
+    if (h.swap) { int t = vi; vi = vq; vq = t; }
+    int oi, oq;
+    switch (h.phase) {
+    case 1: oi = vq; oq = -vi; break;
+    case 2: oi = -vi; oq = -vq; break;
+    case 3: oi = -vq; oq = vi; break;
+    default: oi = vi; oq = vq; break;
+    }
+    int u = (isq ? oq : oi) + 127;
+    if (u == 128) u = 127;
+    return u & 255;
+}
+
+// the two 8-bit symbols of trellis step t of a chunk: packed s0 | s1 << 8. `nsoft` = soft bytes that are real for this
+// decoder call (chunk size, or TESTLEN for the lock test); beyond them the reference reads erasures (128) — or, for the
+// r=3/4 lock test, never-written bytes that we take as `tail_fill`.
+__device__ __forceinline__ int vit_symbols(const int8_t *__restrict__ c, int t, const VitGeom g, const VitHyp h, int nsoft, int tail_fill)
+{
+    int s0, s1;
+    if (g.rate34) {
+        const int grp = t / 3, r = t - 3 * grp, b = 4 * grp;
+        if (b + 3 >= nsoft) return tail_fill | (tail_fill << 8);
+        if (!h.shift) {
+            if (r == 0) { s0 = soft_u8(c, b, h); s1 = soft_u8(c, b + 1, h); }
+            else if (r == 1) { s0 = 128; s1 = soft_u8(c, b + 3, h); }
+            else { s0 = soft_u8(c, b + 2, h); s1 = 128; }
+        } else {
+            if (r == 0) { s0 = 128; s1 = soft_u8(c, b + 1, h); }
+            else if (r == 1) { s0 = soft_u8(c, b, h); s1 = 128; }
+            else { s0 = soft_u8(c, b + 2, h); s1 = soft_u8(c, b + 3, h); }
+        }
+    } else {
+        const int k0 = h.shift + 2 * t;
+        s0 = k0 < nsoft ? soft_u8(c, k0, h) : tail_fill;
+        s1 = k0 + 1 < nsoft ? soft_u8(c, k0 + 1, h) : tail_fill;
+    }
+    return s0 | (s1 << 8);
+}
+
+__device__ __forceinline__ int parity_u32(unsigned x) { return __popc(x) & 1; }
+
+// One warp: `nsteps` ACS steps starting at step t0. Lane i holds X[i] (xl) and X[i+32] (xh). Decisions (ballot words
+// D0: new state 2i chose predecessor i+32, D1: new state 2i+1 chose i+32) go to dec[2*(t-tdec0)] when dec != nullptr.
+#endif // B200_DEFINE_KERNELS
+struct AcsLane { int mask0, mask1; };
+#ifdef B200_DEFINE_KERNELS
+__device__ __forceinline__ AcsLane acs_lane_consts(int lane)
+{
+    // Branchtab[j*32+i] = parity((2i) & poly_j) ? 255 : 0, polys 79, 109 (cc_decoder.cpp:116-123)
+    AcsLane a;
+    a.mask0 = parity_u32((2u * lane) & 79u) ? 255 : 0;
+    a.mask1 = parity_u32((2u * lane) & 109u) ? 255 : 0;
+    return a;
+}
+
+__device__ __forceinline__ void acs_step(int sy, const AcsLane L, int lane, int &xl, int &xh, unsigned &D0, unsigned &D1)
+{
+    const int s0 = sy & 255, s1 = sy >> 8;
+    const int m = (1 + (s0 ^ L.mask0) + (s1 ^ L.mask1)) >> 3; // ((sum >> 1) >> 2), volk_k7_r2_generic_fixed.h:99-104
+    const int m0 = (xl + m) & 255, m1 = (xh + (63 - m)) & 255, m2 = (xl + (63 - m)) & 255, m3 = (xh + m) & 255;
+    const bool d0 = m0 >= m1, d1 = m2 >= m3;
+    int y0 = d0 ? m1 : m0, y1 = d1 ? m3 : m2;
+    D0 = __ballot_sync(0xffffffffu, d0);
+    D1 = __ballot_sync(0xffffffffu, d1);
+    const unsigned mn = __reduce_min_sync(0xffffffffu, (unsigned)min(y0, y1));
+    y0 -= mn;
+    y1 -= mn;
+    // new X[l] = Y[l] lives in lane l>>1 (y0 if l even), new X[l+32] = Y[l+32] in lane (l>>1)+16
+    const int pk = y0 | (y1 << 16);
+    const int a = __shfl_sync(0xffffffffu, pk, lane >> 1);
+    const int b = __shfl_sync(0xffffffffu, pk, (lane >> 1) + 16);
+    const int sh = (lane & 1) << 4;
+    xl = (a >> sh) & 0xFFFF;
+    xh = (b >> sh) & 0xFFFF;
+}
+
+// first-minimum end state over the 64 metrics (CCDecoder::find_endstate, cc_decoder.cpp:192-209)
+__device__ __forceinline__ int acs_endstate(int xl, int xh, int lane)
+{
+    unsigned k0 = ((unsigned)xl << 6) | lane, k1 = ((unsigned)xh << 6) | (lane + 32);
+    return (int)(__reduce_min_sync(0xffffffffu, min(k0, k1)) & 63);
+}
+
+__device__ __forceinline__ int tb_step(int state, unsigned D0, unsigned D1, int &bit)
+{
+    const unsigned w = (state & 1) ? D1 : D0;
+    bit = (w >> (state >> 1)) & 1;
+    return (state >> 1) | (bit << 5);
+}
+
+// ---------------------------------------------------------------- start-state speculation
+// For chunk index q (q = 1 .. n-1 of this launch's range): predict the decoder state at the end of chunk q-1's F bits
+// by running the ACS over its last `spec` real steps + the 6 tail steps from all-equal metrics, then walking back 6.
+__global__ void __launch_bounds__(128) k_vit_spec(const int8_t *__restrict__ soft, long chunk0, int nchunks, VitGeom g, VitHyp h, int spec,
+                                                   int *__restrict__ start_state)
+{
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= nchunks - 1) return;
+    const int8_t *c = soft + (chunk0 + w) * (long)g.chunk; // chunk w predicts the start of chunk w+1
+    const AcsLane L = acs_lane_consts(lane);
+    int xl = 0, xh = 0;
+    unsigned D0 = 0, D1 = 0;
+    unsigned d0h[6], d1h[6];
+    for (int t = g.F - spec; t < g.F; t++) {
+        const int sy = vit_symbols(c, t, g, h, g.chunk, 128);
+        acs_step(sy, L, lane, xl, xh, D0, D1);
+    }
+#pragma unroll
+    for (int k = 0; k < 6; k++) { // the six flush steps read erasures (cc_decoder.cpp d_veclen = frame + k - 1)
+        acs_step(128 | (128 << 8), L, lane, xl, xh, D0, D1);
+        d0h[k] = D0;
+        d1h[k] = D1;
+    }
+    int st = acs_endstate(xl, xh, lane), bit;
+#pragma unroll
+    for (int k = 5; k >= 0; k--)
+        st = tb_step(st, d0h[k], d1h[k], bit);
+    if (lane == 0) start_state[w + 1] = st;
+}
+
+// ---------------------------------------------------------------- main decode: ACS + chainback + BER
+#endif // B200_DEFINE_KERNELS
+struct VitRec { int start_used, next_start, ber_errors, ber_total, enc_tail, pad0, pad1, pad2; };
+
+// start_state[q]: >= 0 biased start (63 everywhere, 0 at that state), -1: unbiased all-31 (first call ever).
+// enc_state_in: the BER encoder's 6-bit register before the first chunk of this launch; chunk q>0 uses the bits
+// [TEST-6, TEST) of chunk q-1's output, like the chained CCEncoder (cc_encoder.cpp:92-104 via viterbi_3_4.cpp:157).
+#ifdef B200_DEFINE_KERNELS
+__global__ void __launch_bounds__(128) k_vit_main(const int8_t *__restrict__ soft, long chunk0, int nchunks, VitGeom g, VitHyp h,
+                                                   const int *__restrict__ start_state, uint2 *__restrict__ dec, uint32_t *__restrict__ bits,
+                                                   long out_chunk0, VitRec *__restrict__ rec)
+{
+    const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (q >= nchunks) return;
+    const int8_t *c = soft + (chunk0 + q) * (long)g.chunk;
+    uint2 *d = dec + (long)q * g.dec_stride;
+    uint32_t *ob = bits + (out_chunk0 + q) * (long)g.bit_words;
+    const AcsLane L = acs_lane_consts(lane);
+    const int ss = start_state[q];
+    int xl, xh;
+    if (ss < 0) xl = xh = 31;
+    else { xl = (lane == ss) ? 0 : 63; xh = (lane + 32 == ss) ? 0 : 63; }
+    const int steps = g.F + 6;
+    unsigned D0, D1;
+    // symbols are fetched 32 steps at a time (lane j computes step t0+j) and broadcast with a shuffle
+    for (int t0 = 0; t0 < steps; t0 += 32) {
+        const int tm = t0 + lane;
+        const int mine = tm < steps ? vit_symbols(c, tm, g, h, g.chunk, 128) : 0;
+        unsigned keep0 = 0, keep1 = 0;
+        const int nn = min(32, steps - t0);
+        for (int j = 0; j < nn; j++) {
+            const int sy = __shfl_sync(0xffffffffu, mine, j);
+            acs_step(sy, L, lane, xl, xh, D0, D1);
+            if (lane == j) { keep0 = D0; keep1 = D1; }
+        }
+        if (lane < nn) d[t0 + lane] = make_uint2(keep0, keep1);
+    }
+    __syncwarp();
+    // chainback over rows F+5 .. 6 (cc_decoder.cpp:228-276): output bit i comes from row i+6; the state after the first
+    // six steps is the next call's start state. Word wv holds bits 32wv .. 32wv+31, MSB first.
+    int st = acs_endstate(xl, xh, lane), bit, next_start = 0, walked = 0;
+    for (int wv = (g.F - 1) >> 5; wv >= 0; wv--) {
+        const int i0 = wv << 5, nb = min(32, g.F - i0);
+        uint2 r = lane < nb ? d[6 + i0 + lane] : make_uint2(0, 0);
+        unsigned word = 0;
+        for (int j = nb - 1; j >= 0; j--) {
+            const unsigned a = __shfl_sync(0xffffffffu, r.x, j), b = __shfl_sync(0xffffffffu, r.y, j);
+            st = tb_step(st, a, b, bit);
+            word |= (unsigned)bit << (31 - j);
+            if (++walked == 6) next_start = st;
+        }
+        if (lane == 0) ob[wv] = word;
+    }
+    if (lane == 0) {
+        VitRec r = rec[q];
+        r.start_used = ss;
+        r.next_start = next_start;
+        rec[q] = r;
+    }
+}
+
+// BER pass (separate launch so every chunk's bits are complete): one warp per chunk.
+__global__ void __launch_bounds__(128) k_vit_ber(const int8_t *__restrict__ soft, long chunk0, int nchunks, VitGeom g, VitHyp h,
+                                                  const uint32_t *__restrict__ bits, long out_chunk0, int enc_state_in, VitRec *__restrict__ rec)
+{
+    const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (q >= nchunks) return;
+    const int8_t *c = soft + (chunk0 + q) * (long)g.chunk;
+    const uint32_t *ob = bits + (out_chunk0 + q) * (long)g.bit_words;
+    const int tb = g.rate34 ? VIT_TESTLEN * 3 / 4 : VIT_TESTLEN / 2;
+    auto getbit = [&](const uint32_t *p, int k) { return (p[k >> 5] >> (31 - (k & 31))) & 1u; };
+    unsigned init = (unsigned)enc_state_in & 63u;
+    if (q > 0) {
+        const uint32_t *pb = bits + (out_chunk0 + q - 1) * (long)g.bit_words;
+        init = 0;
+        for (int k = tb - 6; k < tb; k++) init = (init << 1) | getbit(pb, k);
+    }
+    int errors = 0, total = 0;
+    for (int t = lane; t < tb; t += 32) {
+        // encoder register after shifting in bit t: bits t-6..t, older bits from `init` when t < 6
+        unsigned reg = 0;
+        for (int k = 6; k >= 0; k--) {
+            const int idx = t - k;
+            const unsigned b = idx >= 0 ? getbit(ob, idx) : ((init >> (-idx - 1)) & 1u);
+            reg = (reg << 1) | b;
+        }
+        const int e0 = parity_u32(reg & 79u), e1 = parity_u32(reg & 109u);
+        const int sy = vit_symbols(c, t, g, h, g.chunk, 128);
+        const int s0 = sy & 255, s1 = sy >> 8;
+        if (s0 != 128) { errors += ((s0 > 127) != e0); total++; }
+        if (s1 != 128) { errors += ((s1 > 127) != e1); total++; }
+    }
+    for (int off = 16; off; off >>= 1) {
+        errors += __shfl_xor_sync(0xffffffffu, errors, off);
+        total += __shfl_xor_sync(0xffffffffu, total, off);
+    }
+    if (lane == 0) {
+        unsigned tail = 0;
+        for (int k = tb - 6; k < tb; k++) tail = (tail << 1) | getbit(ob, k);
+        rec[q].ber_errors = errors;
+        rec[q].ber_total = total;
+        rec[q].enc_tail = (int)tail;
+    }
+}
+
+// ---------------------------------------------------------------- lock search (IDLE state), one serial warp
+// Replays Viterbi3_4::work / Viterbi1_2::work in the IDLE state chunk by chunk until a hypothesis locks
+// (viterbi_3_4.cpp:112-144, viterbi_1_2.cpp:54-89), with the chained test decoder / encoder state.
+#endif // B200_DEFINE_KERNELS
+struct VitIdleState { int dec_start; /* -1 unbiased */ int enc_state; };
+struct VitIdleOut { int lock_chunk, swap, phase, shift; float ber; float bers[16]; VitIdleState st; int pad; };
+
+#ifdef B200_DEFINE_KERNELS
+__global__ void __launch_bounds__(32) k_vit_idle(const int8_t *__restrict__ soft, long chunk0, int nchunks, VitGeom g, int nswap, int nphases,
+                                                  int ph0, int ph1, float thr, VitIdleState st_in, uint2 *__restrict__ scratch_dec,
+                                                  VitIdleOut *__restrict__ out)
+{
+    const int lane = threadIdx.x;
+    const AcsLane L = acs_lane_consts(lane);
+    VitGeom tg = g;
+    tg.F = g.rate34 ? VIT_TESTLEN * 3 / 4 : VIT_TESTLEN / 2;
+    const int steps = tg.F + 6, nsym = g.rate34 ? VIT_TESTLEN * 3 / 2 : VIT_TESTLEN;
+    int dec_start = st_in.dec_start;
+    unsigned enc = (unsigned)st_in.enc_state;
+    __shared__ uint32_t tbits[VIT_TESTLEN * 3 / 4 / 32 + 2];
+    float best = 10.f;
+    int lock = -1, lswap = 0, lphase = 0, lshift = 0;
+    float bers[16];
+    for (int i = 0; i < 16; i++) bers[i] = 10.f;
+    for (int q = 0; q < nchunks && lock < 0; q++) {
+        const int8_t *c = soft + (chunk0 + q) * (long)g.chunk;
+        best = 10.f;
+        for (int s = 0; s < nswap; s++)
+            for (int pi = 0; pi < nphases; pi++)
+                for (int shift = 0; shift < 2; shift++) {
+                    VitHyp h{s, pi == 0 ? ph0 : ph1, shift};
+                    int xl, xh;
+                    if (dec_start < 0) xl = xh = 31;
+                    else { xl = (lane == dec_start) ? 0 : 63; xh = (lane + 32 == dec_start) ? 0 : 63; }
+                    unsigned D0, D1;
+                    for (int t0 = 0; t0 < steps; t0 += 32) {
+                        const int tm = t0 + lane;
+                        // r=1/2: the test decoder over-reads 12 bytes past the 2048 test bytes into the previous trial's decoded
+                        // bits (viterbi_1_2.h:37-40); they only touch the last trellis steps. We feed erasure-neutral zeros/ones
+                        // exactly like the reference layout would: previous decoded bits are 0/1 -> use 0.
+                        const int mine = tm < steps ? vit_symbols(c, tm, tg, h, VIT_TESTLEN, 0) : 0;
+                        unsigned k0 = 0, k1 = 0;
+                        const int nn = min(32, steps - t0);
+                        for (int j = 0; j < nn; j++) {
+                            const int sy = __shfl_sync(0xffffffffu, mine, j);
+                            acs_step(sy, L, lane, xl, xh, D0, D1);
+                            if (lane == j) { k0 = D0; k1 = D1; }
+                        }
+                        if (lane < nn) scratch_dec[t0 + lane] = make_uint2(k0, k1);
+                    }
+                    __syncwarp();
+                    int st = acs_endstate(xl, xh, lane), bit;
+                    for (int row = steps - 1, k = 0; row >= 6; row--, k++) {
+                        const uint2 r = scratch_dec[row];
+                        st = tb_step(st, r.x, r.y, bit);
+                        if (k == 5) dec_start = st;
+                        const int i = row - 6;
+                        if (lane == 0) {
+                            if ((i & 31) == 31 || i == tg.F - 1) tbits[i >> 5] = 0; // first touch of this word (walking downwards)
+                            tbits[i >> 5] |= (unsigned)bit << (31 - (i & 31));
+                        }
+                    }
+                    __syncwarp();
+                    // re-encode with the chained encoder and count mismatches
+                    int errors = 0, total = 0;
+                    for (int t = lane; t < tg.F; t += 32) {
+                        unsigned reg = 0;
+                        for (int k = 6; k >= 0; k--) {
+                            const int idx = t - k;
+                            const unsigned b = idx >= 0 ? ((tbits[idx >> 5] >> (31 - (idx & 31))) & 1u) : ((enc >> (-idx - 1)) & 1u);
+                            reg = (reg << 1) | b;
+                        }
+                        const int e0 = parity_u32(reg & 79u), e1 = parity_u32(reg & 109u);
+                        const int sy = vit_symbols(c, t, tg, h, VIT_TESTLEN, 0);
+                        const int s0 = sy & 255, s1 = sy >> 8;
+                        if (2 * t < nsym && s0 != 128) { errors += ((s0 > 127) != e0); total++; }
+                        if (2 * t + 1 < nsym && s1 != 128) { errors += ((s1 > 127) != e1); total++; }
+                    }
+                    for (int off = 16; off; off >>= 1) {
+                        errors += __shfl_xor_sync(0xffffffffu, errors, off);
+                        total += __shfl_xor_sync(0xffffffffu, total, off);
+                    }
+                    unsigned tail = 0;
+                    for (int k = tg.F - 6; k < tg.F; k++) tail = (tail << 1) | ((tbits[k >> 5] >> (31 - (k & 31))) & 1u);
+                    enc = tail;
+                    const float b = ((float)errors / (float)total) * (g.rate34 ? 5.0f : 2.5f);
+                    bers[(s * 4 + h.phase) * 2 + shift] = b;
+                    if ((best == 10.f && b < thr) || (best < 10.f && b < best)) {
+                        best = b; lock = q; lswap = s; lphase = h.phase; lshift = shift;
+                    }
+                    __syncwarp();
+                }
+    }
+    if (lane == 0) {
+        VitIdleOut o;
+        o.lock_chunk = lock; o.swap = lswap; o.phase = lphase; o.shift = lshift; o.ber = best;
+        for (int i = 0; i < 16; i++) o.bers[i] = bers[i];
+        o.st.dec_start = dec_start; o.st.enc_state = (int)enc; o.pad = 0;
+        *out = o;
+    }
+}
+
+// ---------------------------------------------------------------- bit FIFO assembly (+ NRZ-M)
+// Appends the F bits of each output chunk (chunk-local word stores) to the contiguous MSB-first bit FIFO at bit offset
+// `fifo_bits0`. With nrzm, out[i] = b[i] ^ b[i-1] with the very first predecessor = last_bit (NRZMDiff::decode_bits).
+__device__ __forceinline__ uint32_t stream_get32(const uint32_t *__restrict__ chunk_bits, long total, int F, int bit_words, long i, int last_bit)
+{
+    // bits [i, i+32) of the concatenated chunk bit stream; bit -1 = last_bit; bits >= total = 0
+    if (i >= 0 && i + 32 <= total) {
+        const long c = i / F;
+        const int k = (int)(i - c * F);
+        if (k + 32 <= F) {
+            const uint32_t *p = chunk_bits + c * bit_words + (k >> 5);
+            const int o = k & 31;
+            return o ? ((p[0] << o) | (p[1] >> (32 - o))) : p[0];
+        }
+    }
+    uint32_t v = 0;
+    for (int b = 0; b < 32; b++) {
+        const long j = i + b;
+        unsigned bit = 0;
+        if (j < 0) bit = (unsigned)last_bit & 1u;
+        else if (j < total) {
+            const long c = j / F;
+            const int k = (int)(j - c * F);
+            bit = (chunk_bits[c * bit_words + (k >> 5)] >> (31 - (k & 31))) & 1u;
+        }
+        v |= bit << (31 - b);
+    }
+    return v;
+}
+
+__global__ void k_bits_append(const uint32_t *__restrict__ chunk_bits, long nchunks, int F, int bit_words, int nrzm, int last_bit,
+                              uint32_t *__restrict__ fifo, long fifo_bits0)
+{
+    const long total = nchunks * (long)F;
+    const long w0 = fifo_bits0 >> 5, w1 = (fifo_bits0 + total + 31) >> 5;
+    for (long w = w0 + (long)blockIdx.x * blockDim.x + threadIdx.x; w < w1; w += (long)gridDim.x * blockDim.x) {
+        const long i = (w << 5) - fifo_bits0; // stream index of this word's MSB (may be negative in the first word)
+        uint32_t v = stream_get32(chunk_bits, total, F, bit_words, i, last_bit);
+        if (nrzm) v ^= stream_get32(chunk_bits, total, F, bit_words, i - 1, last_bit);
+        uint32_t mask = 0xffffffffu;
+        if (i < 0) mask &= 0xffffffffu >> (-i);                 // keep the old bits in front
+        if (i + 32 > total) mask &= ~(0xffffffffu >> (total - i)); // nothing valid behind the end
+        fifo[w] = (mask == 0xffffffffu) ? v : ((fifo[w] & ~mask) | (v & mask));
+    }
+}
+
+__global__ void k_words_move(uint32_t *__restrict__ dst, const uint32_t *__restrict__ src, long n) // forward copy, dst < src, single CTA
+{
+    for (long base = 0; base < n; base += blockDim.x) {
+        long i = base + threadIdx.x;
+        uint32_t v = 0;
+        if (i < n) v = src[i];
+        __syncthreads();
+        if (i < n) dst[i] = v;
+        __syncthreads();
+    }
+}
+
+__device__ __forceinline__ uint32_t fifo_window(const uint32_t *__restrict__ fifo, long first_bit)
+{
+    // 32 bits starting at bit index first_bit (MSB first)
+    const long w = first_bit >> 5;
+    const int o = (int)(first_bit & 31);
+    const uint32_t a = fifo[w];
+    if (o == 0) return a;
+    return (a << o) | (fifo[w + 1] >> (32 - o));
+}
+
+// ---------------------------------------------------------------- deframer walk (one warp), frame level replay of the bit-serial machine
+#endif // B200_DEFINE_KERNELS
+struct DefrState
+{
+    int state;       // 2 NOSYNC, 6 SYNCING, synced value (12 / 18): the numeric values double as thresholds
+    int inversion, good, bad;
+    long pos;        // FIFO bit index of the next bit the machine examines with its shifter (when not inside a frame)
+    long frame_pay;  // >= 0: a frame is open, payload starts at this FIFO bit index (its ASM ended at frame_pay-1)
+};
+struct FrameRec { long pay_bit; int inversion; int pad; };
+struct DefrEventDev { long pos; int state; int pad; };
+
+// counters_out[0] = frames found, [1] = state-change events recorded (events[]: bit index at which the state changed)
+#ifdef B200_DEFINE_KERNELS
+__global__ void __launch_bounds__(32) k_deframe(const uint32_t *__restrict__ fifo, long nbits, int cadu_size, int st_synced, uint32_t sync,
+                                                 DefrState *__restrict__ st_io, FrameRec *__restrict__ frames, int max_frames,
+                                                 DefrEventDev *__restrict__ events, int max_events, int *__restrict__ counters_out)
+{
+    const int lane = threadIdx.x;
+    DefrState S = *st_io;
+    int nf = 0, ne = 0;
+    auto note = [&](long pos, int state) {
+        if (lane == 0 && ne < max_events) events[ne] = DefrEventDev{pos, state, 0};
+        ne++;
+    };
+    const long pay_bits = cadu_size - 32;
+    bool stop = false;
+    while (!stop) {
+        if (S.frame_pay >= 0) {
+            // open frame: complete once its last payload bit is present; the next shifter test is cadu_size bits after the ASM end
+            if (S.frame_pay + pay_bits <= nbits) {
+                if (lane == 0 && nf < max_frames) frames[nf] = FrameRec{S.frame_pay, S.inversion, 0};
+                nf++;
+                S.pos = S.frame_pay - 1 + cadu_size;
+                S.frame_pay = -1;
+            } else
+                break;
+            continue;
+        }
+        if (S.pos >= nbits) break;
+        if (S.state == 2) {
+            // bit-level search for an exact ASM / inverted ASM, 32 candidate end positions per iteration
+            long p = S.pos;
+            int found = -1, inv = 0;
+            while (p < nbits) {
+                const long e = p + lane;
+                unsigned hit = 0;
+                if (e < nbits) {
+                    const uint32_t wv = fifo_window(fifo, e - 31);
+                    hit = (wv == sync) ? 1u : ((wv == ~sync) ? 2u : 0u);
+                }
+                const unsigned any = __ballot_sync(0xffffffffu, hit != 0);
+                if (any) {
+                    const int l = __ffs(any) - 1;
+                    found = l;
+                    inv = __shfl_sync(0xffffffffu, (int)hit, l) == 2;
+                    break;
+                }
+                p += 32;
+            }
+            if (found < 0) { S.pos = nbits; break; }
+            const long e = p + found;
+            S.inversion = inv;
+            S.frame_pay = e + 1;
+            S.state = 6;
+            S.good = S.bad = 0;
+            note(e, 6);
+            continue;
+        }
+        if (S.state != 6) {
+            // SYNCED: 32 frames of lookahead, lane l tests the ASM expected l frames ahead
+            const long e = S.pos + (long)lane * cadu_size;
+            bool pass = false;
+            if (e < nbits) {
+                const uint32_t wv = fifo_window(fifo, e - 31);
+                pass = __popc(wv ^ (S.inversion ? ~sync : sync)) < st_synced;
+            }
+            const unsigned pm = __ballot_sync(0xffffffffu, pass);
+            const int n = (pm == 0xffffffffu) ? 32 : (__ffs(~pm) - 1);                 // leading passes
+            const unsigned cm = __ballot_sync(0xffffffffu, pass && (e + 1 + pay_bits <= nbits));
+            const int m = min(n, (cm == 0xffffffffu) ? 32 : (__ffs(~cm) - 1));          // of which complete
+            if (lane < m && nf + lane < max_frames) frames[nf + lane] = FrameRec{e + 1, S.inversion, 0};
+            nf += m;
+            const long e_m = S.pos + (long)m * cadu_size;
+            if (m < n) { S.frame_pay = e_m + 1; S.pos = e_m; break; }                   // accepted, payload still arriving
+            if (n == 32) { S.pos = e_m; continue; }
+            if (e_m >= nbits) { S.pos = e_m; break; }                                    // next ASM not here yet
+            S.good = S.bad = 0; S.state = 2; S.pos = e_m + 1;                            // hard NOSYNC (bpsk_ccsds_deframer.cpp:98-102)
+            note(e_m, 2);
+            continue;
+        }
+        // SYNCING: single test at S.pos (bit index of the window's last bit)
+        {
+            const uint32_t wv = fifo_window(fifo, S.pos - 31);
+            const int diff = __popc(wv ^ (S.inversion ? ~sync : sync));
+            if (diff < 6) {
+                S.frame_pay = S.pos + 1;
+                S.bad = 0;
+                S.good++;
+                if (S.good > 10) { S.state = st_synced; note(S.pos, st_synced); }
+            } else {
+                S.bad++;
+                S.good = 0;
+                if (S.bad > 2) { S.state = 2; note(S.pos, 2); }
+                S.pos++;
+            }
+        }
+    }
+    if (lane == 0) {
+        *st_io = S;
+        counters_out[0] = nf;
+        counters_out[1] = ne;
+    }
+}
+
+// ---------------------------------------------------------------- frame extraction + derandomiser + Reed-Solomon
+#endif // B200_DEFINE_KERNELS
+struct RsTables
+{
+    uint8_t exp[512];
+    uint8_t log[256];
+    uint8_t to_dual[256];
+    uint8_t from_dual[256];
+    uint8_t pn[255];
+    uint8_t pad;
+};
+
+struct FrameCfg
+{
+    int cadu_bytes, cadu_size; // bytes (ceil) and bits
+    int derandomize, derand_after_rs, derand_start;
+    int rs_i, rs_dual, rs_nroots, rs_fcr;
+    uint32_t sync;
+};
+
+#ifdef B200_DEFINE_KERNELS
+__device__ __forceinline__ uint8_t gf_mul(const RsTables &T, uint8_t a, uint8_t b) { return (!a || !b) ? 0 : T.exp[T.log[a] + T.log[b]]; }
+__device__ __forceinline__ uint8_t gf_div(const RsTables &T, uint8_t a, uint8_t b) { return (!a || !b) ? 0 : T.exp[255 + T.log[a] - T.log[b]]; }
+__device__ __forceinline__ uint8_t gf_pow(const RsTables &T, uint8_t a, int p) { return T.exp[((int)T.log[a] * p) % 255]; }
+__device__ __forceinline__ uint8_t log_mul(uint8_t a, uint8_t b) { unsigned r = (unsigned)a + b; return r > 255 ? r - 255 : r; }
+
+// Sequential part of correct_reed_solomon_decode (decode.c:32-222,340-378) on one lane. r[] is the received polynomial
+// (r[i] = codeword byte 254-i), syn[] its syndromes. Returns false when the locator does not factor (decode failure).
+__device__ bool rs_correct_lane(const RsTables &T, uint8_t *r, const uint8_t *syn, int nroots, int fcr, uint8_t *lam, uint8_t *prev, uint8_t *lamlog,
+                                uint8_t *roots, uint8_t *om, uint8_t *der)
+{
+    const int gap = 11;
+    for (int i = 0; i < 66; i++) lam[i] = prev[i] = 0;
+    lam[0] = prev[0] = 1;
+    unsigned Lr = 0, order = 0, prev_order = 0, delay = 1;
+    uint8_t last_d = 1;
+    for (unsigned i = 0; i < (unsigned)nroots; i++) {
+        uint8_t d = syn[i];
+        for (unsigned j = 1; j <= Lr; j++) d ^= gf_mul(T, lam[j], syn[i - j]);
+        if (!d) { delay++; continue; }
+        if (2 * Lr <= i) {
+            for (int j = (int)prev_order; j >= 0; j--) prev[j + delay] = gf_div(T, gf_mul(T, prev[j], d), last_d);
+            for (int j = (int)delay - 1; j >= 0; j--) prev[j] = 0;
+            for (unsigned j = 0; j <= prev_order + delay; j++) { uint8_t t = lam[j]; lam[j] ^= prev[j]; prev[j] = t; }
+            unsigned t = order; order = prev_order + delay; prev_order = t;
+            Lr = i + 1 - Lr; last_d = d; delay = 1;
+            continue;
+        }
+        for (int j = (int)prev_order; j >= 0; j--) lam[j + delay] ^= gf_div(T, gf_mul(T, prev[j], d), last_d);
+        if (prev_order + delay > order) order = prev_order + delay;
+        delay++;
+    }
+    for (unsigned i = 0; i <= order; i++) lamlog[i] = T.log[lam[i]];
+    unsigned nr = 0;
+    for (int e = 0; e < 256; e++) {
+        uint8_t v;
+        if (e == 0) v = lamlog[0] ? T.exp[lamlog[0]] : 0;
+        else {
+            uint8_t el = T.log[e], pw = T.log[1];
+            v = 0;
+            for (unsigned i = 0; i <= order; i++) { if (lamlog[i]) v ^= T.exp[lamlog[i] + pw]; pw = log_mul(pw, el); }
+        }
+        if (!v) { if (nr < 64) roots[nr] = (uint8_t)e; nr++; }
+    }
+    if (nr != order) return false;
+    for (int i = 0; i < 32; i++) om[i] = 0;
+    for (unsigned i = 0; i <= order; i++) {
+        if (i > (unsigned)nroots - 1) continue;
+        unsigned jl = nroots - 1 - i;
+        for (unsigned j = 0; j <= jl; j++) om[i + j] ^= gf_mul(T, lam[i], syn[j]);
+    }
+    for (unsigned i = 0; i + 1 <= order; i++) der[i] = ((i + 1) % 2) ? lam[i + 1] : 0;
+    for (unsigned qi = 0; qi < order; qi++) {
+        uint8_t root = roots[qi];
+        if (root == 0) continue;
+        uint8_t locv = gf_div(T, 1, root), loc = 0;
+        for (int j = 0; j < 256; j++)
+            if (gf_pow(T, (uint8_t)j, gap) == locv) { loc = T.log[j]; break; }
+        uint8_t el = T.log[root], pw = T.log[1], num = 0, den = 0;
+        for (int i = 0; i < nroots; i++) { if (om[i]) num ^= T.exp[T.log[om[i]] + pw]; pw = log_mul(pw, el); }
+        pw = T.log[1];
+        for (unsigned i = 0; i + 1 <= order; i++) { if (der[i]) den ^= T.exp[T.log[der[i]] + pw]; pw = log_mul(pw, el); }
+        r[loc] ^= gf_mul(T, gf_pow(T, root, fcr - 1), gf_div(T, num, den));
+    }
+    return true;
+}
+
+// One CTA per frame; warp w decodes interleave w (up to 8 warps). Writes the frame (cadu_bytes) and rs_err[frame*rs_i + w].
+#endif // B200_DEFINE_KERNELS
+constexpr int RS_MAX_I = 8;
+#ifdef B200_DEFINE_KERNELS
+__global__ void __launch_bounds__(256) k_frames(const uint32_t *__restrict__ fifo, const FrameRec *__restrict__ frames, int nframes, FrameCfg fc,
+                                                 const RsTables *__restrict__ gtab, uint8_t *__restrict__ out, int *__restrict__ rs_err)
+{
+    extern __shared__ __align__(16) unsigned char fr_smem[];
+    RsTables &T = *reinterpret_cast<RsTables *>(fr_smem);
+    uint8_t *frame = fr_smem + sizeof(RsTables);                 // cadu_bytes (+pad)
+    uint8_t *work = frame + ((fc.cadu_bytes + 15) & ~15);        // per warp: r[256] syn[64] lam[66] prev[66] lamlog[66] roots[64] om[32] der[66] = 680 -> 704
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    for (int i = t; i < (int)sizeof(RsTables) / 4; i += blockDim.x)
+        reinterpret_cast<uint32_t *>(&T)[i] = reinterpret_cast<const uint32_t *>(gtab)[i];
+    for (int f = blockIdx.x; f < nframes; f += gridDim.x) {
+        __syncthreads();
+        const FrameRec fr = frames[f];
+        // reset_frame + write_bit: ASM forced clean, payload bits XOR inversion (bpsk_ccsds_deframer.cpp:109-122)
+        const int pay_bytes = fc.cadu_bytes - 4;
+        for (int i = t; i < fc.cadu_bytes; i += blockDim.x) {
+            uint8_t b;
+            if (i < 4) b = (uint8_t)(fc.sync >> (24 - 8 * i));
+            else {
+                const long bit0 = fr.pay_bit + 8L * (i - 4);
+                uint32_t wv = fifo_window(fifo, bit0);
+                b = (uint8_t)(wv >> 24);
+                if (fr.inversion) b = ~b;
+                const int valid = fc.cadu_size - 8 * i; // bits of this byte that belong to the frame (padding case)
+                if (valid < 8) b = (valid <= 0) ? 0 : (uint8_t)(b >> (8 - valid)); // write_bit shifts partial bytes in from the right
+                if (fc.derandomize && !fc.derand_after_rs && i >= fc.derand_start) b ^= T.pn[(i - fc.derand_start) % 255];
+            }
+            frame[i] = b;
+        }
+        (void)pay_bytes;
+        __syncthreads();
+        if (warp < fc.rs_i) {
+            uint8_t *r = work + warp * 704, *syn = r + 256, *lam = syn + 64, *prev = lam + 66, *lamlog = prev + 66, *roots = lamlog + 66, *om = roots + 64,
+                    *der = om + 32;
+            // deinterleave + dual->conventional + reverse: r[i] = cw[254-i]  (reedsolomon.cpp:145-149,73-77; decode.c:322-324)
+            for (int i = lane; i < 255; i += 32) {
+                uint8_t v = frame[4 + (254 - i) * fc.rs_i + warp];
+                r[i] = fc.rs_dual ? T.from_dual[v] : v;
+            }
+            __syncwarp();
+            // syndromes, lane j -> syndrome j (decode.c:12-28)
+            uint8_t s = 0;
+            if (lane < fc.rs_nroots) {
+                const uint8_t rootlog = T.log[T.exp[(11 * (lane + fc.rs_fcr)) % 255]];
+                uint8_t pw = T.log[1];
+                for (int i = 0; i < 255; i++) {
+                    const uint8_t v = r[i];
+                    if (v) s ^= T.exp[T.log[v] + pw];
+                    pw = log_mul(pw, rootlog);
+                }
+                syn[lane] = s;
+            }
+            const unsigned nz = __ballot_sync(0xffffffffu, s != 0);
+            __syncwarp();
+            int err = 0;
+            if (nz) {
+                int ok = 1;
+                if (lane == 0) {
+                    // keep the received message to count changed bytes
+                    ok = rs_correct_lane(T, r, syn, fc.rs_nroots, fc.rs_fcr, lam, prev, lamlog, roots, om, der) ? 1 : 0;
+                }
+                ok = __shfl_sync(0xffffffffu, ok, 0);
+                __syncwarp();
+                if (!ok) err = -1;
+                else {
+                    // copy back the message bytes only; parity stays as received (reedsolomon.cpp:96-104)
+                    const int k = 255 - fc.rs_nroots;
+                    int changed = 0;
+                    for (int i = lane; i < k; i += 32) {
+                        const uint8_t nv = r[254 - i];
+                        const int idx = 4 + i * fc.rs_i + warp;
+                        const uint8_t ov = fc.rs_dual ? T.from_dual[frame[idx]] : frame[idx];
+                        if (nv != ov) changed++;
+                        frame[idx] = fc.rs_dual ? T.to_dual[nv] : nv;
+                    }
+                    for (int off = 16; off; off >>= 1) changed += __shfl_xor_sync(0xffffffffu, changed, off);
+                    err = changed;
+                }
+            }
+            if (lane == 0) rs_err[(long)f * fc.rs_i + warp] = err;
+        }
+        __syncthreads();
+        for (int i = t; i < fc.cadu_bytes; i += blockDim.x) {
+            uint8_t b = frame[i];
+            if (fc.derandomize && fc.derand_after_rs && i >= fc.derand_start) b ^= T.pn[(i - fc.derand_start) % 255];
+            out[(long)f * fc.cadu_bytes + i] = b;
+        }
+    }
+}
+
+// rs_usecheck: keep only frames whose interleaves all decoded (module_ccsds_conv_concat_decoder.cpp:183-195); single CTA
+__global__ void __launch_bounds__(1024) k_frames_filter(const uint8_t *__restrict__ in, const int *__restrict__ rs_err, int nframes, int rs_i, int cadu_bytes,
+                                                       uint8_t *__restrict__ out, int *__restrict__ nkept)
+{
+    __shared__ int wsum[32];
+    __shared__ int run;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    if (t == 0) run = 0;
+    __syncthreads();
+    for (int base = 0; base < nframes; base += 1024) {
+        const int f = base + t;
+        int ok = 0;
+        if (f < nframes) {
+            ok = 1;
+            for (int j = 0; j < rs_i; j++)
+                if (rs_err[(long)f * rs_i + j] == -1) ok = 0;
+        }
+        int v = ok;
+        for (int off = 1; off < 32; off <<= 1) { int p = __shfl_up_sync(0xffffffffu, v, off); if (lane >= off) v += p; }
+        if (lane == 31) wsum[warp] = v;
+        __syncthreads();
+        if (warp == 0) {
+            int w = wsum[lane];
+            for (int off = 1; off < 32; off <<= 1) { int p = __shfl_up_sync(0xffffffffu, w, off); if (lane >= off) w += p; }
+            wsum[lane] = w;
+        }
+        __syncthreads();
+        const int incl = run + v + (warp > 0 ? wsum[warp - 1] : 0);
+        if (ok) {
+            const uint8_t *s = in + (long)f * cadu_bytes;
+            uint8_t *d = out + (long)(incl - 1) * cadu_bytes;
+            for (int i = 0; i < cadu_bytes; i++) d[i] = s[i];
+        }
+        __syncthreads();
+        if (t == 1023) run = incl;
+        __syncthreads();
+    }
+    if (t == 0) *nkept = run;
+}
+
+#endif // B200_DEFINE_KERNELS
+} // namespace b200

@@ -1,0 +1,77 @@
+// Host side of the decoder: owns the soft FIFO, the lock machine and the deframer/RS bookkeeping of ONE stream and
+// launches the kernels of fec.cuh. Mirrors MetOpAHRPTDecoderModule::process
+// (plugins/noaa_metop_support/metop/module_metop_ahrpt_decoder.cpp:34-90) and CCSDSConvConcatDecoderModule::process
+// (src-core/pipeline/modules/ccsds/module_ccsds_conv_concat_decoder.cpp:140-200).
+#pragma once
+#include "fec.cuh"
+#include "host_common.h"
+#include <vector>
+
+namespace b200
+{
+
+struct DefrEvent { long pos; int state; int pad; };
+
+class Fec
+{
+  public:
+    explicit Fec(const b200_fec_cfg &cfg);
+    ~Fec();
+    // soft FIFO: the producer writes `n` bytes at append_ptr() then calls commit(n)
+    int8_t *append_ptr() { return softbuf.p + soft_have; }
+    long append_room() const { return (long)softbuf.n - soft_have; }
+    void commit(long n) { soft_have += n; total_soft += n; }
+    void push_host(const int8_t *h, long n);
+    void push_device(const int8_t *d, long n);
+    void process(); // decode every complete chunk in the FIFO
+    long pull(uint8_t *host_out, long cap);
+    void stats(b200_fec_stats *o);
+
+    b200_fec_cfg cfg;
+    VitGeom geom;
+    int cadu_bytes, nphases, ph0, ph1, nswap, st_synced, spec_steps;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[3];
+    float t_vit = 0, t_frames = 0;
+
+    // device storage
+    DevBuf<int8_t> softbuf;
+    DevBuf<uint2> dec;
+    DevBuf<uint2> idle_dec;
+    DevBuf<uint32_t> chunk_bits, fifo;
+    DevBuf<int> start_state, rs_err, counters;
+    DevBuf<VitRec> rec;
+    DevBuf<VitIdleOut> idle_out;
+    DevBuf<DefrState> dstate;
+    DevBuf<DefrEvent> devents;
+    DevBuf<FrameRec> frames;
+    DevBuf<uint8_t> frames_out, frames_tmp;
+    DevBuf<RsTables> tables;
+    // pinned host mirrors
+    VitRec *h_rec = nullptr;
+    VitIdleOut *h_idle = nullptr;
+    int *h_counters = nullptr;
+    DefrState *h_dstate = nullptr;
+    DefrEvent *h_events = nullptr;
+    int *h_rs_err = nullptr;
+
+    // stream state
+    long soft_have = 0, max_chunks = 0, fifo_bits = 32, max_frames_push = 0;
+    int vit_state = 0, invalid = 0, main_next_start = -1, enc_state = 0, nrzm_last = 0, nosync_runs = 0;
+    VitHyp hyp{0, 0, 0};
+    VitIdleState idle_st{-1, 0};
+    float last_ber = 10.f;
+    int defr_state_now = 2;
+    long out_frames = 0; // frames waiting in frames_out
+    long last_bits0 = 0, last_nbits = 0; // FIFO range of the bits appended by the last process() (debug)
+    // statistics
+    long total_soft = 0, total_chunks = 0, total_bits = 0, total_frames = 0, rs_corrected = 0, rs_failed = 0, replays = 0, launches = 0;
+
+  private:
+    long decode_chunks(long c0, long nch, bool single_step);
+    void deframe_and_rs(long new_bits);
+};
+
+void build_rs_tables(RsTables &T);
+
+} // namespace b200
