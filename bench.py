@@ -1,0 +1,252 @@
+#!/usr/bin/env python
+"""Headline benchmark: baseband MS/s end-to-end IQ -> CADU, METOP AHRPT (QPSK + Viterbi r=3/4 + RS(255,223) I=4, cs16).
+
+  python bench.py --gpus N --steps K --warmup W                 one independent stream per GPU (weak scaling)
+  python bench.py --impl reference ...                          the reference's own CPU code (oracle/_ref) on the host cores
+
+A step = one pass of the whole hot path over one batch of `2**log2_samples` synthetic samples per GPU.
+  value : samples/s with the batch already resident in HBM when the timed region starts (device timed, max over ranks)
+  e2e   : the same through the public C ABI with HOST (pinned) buffers: H2D of the batch and D2H of the CADUs inside the timed region
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALG_BYTES_PER_CHUNK = 16384 + 12288 // 8  # k_vit_main: int8 soft in + packed decoded bits out
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def make_workload(log2n, rank, device):
+    from satdump_b200 import synth
+    cfg = synth.CONFIGS["metop_ahrpt"]
+    n = 1 << log2n
+    from satdump_b200 import shard
+    raw, clear = synth.make_signal(cfg, n, seed=shard.stream_seed(3, rank), device=device)  # BASELINE config C3, stream = rank
+    return cfg, raw, clear
+
+
+def run_reference(args):
+    """The reference's own execution model (one thread per DSP block + module threads) from oracle/_ref on host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from oracle import ref, port
+    use_ref = ref.available()
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    log2n = min(args.log2_samples, 25)  # bounded sample of the same workload: ~2-3 s of host work per step
+    cfg, raw, _ = make_workload(log2n, 0, dev)
+    raw = raw.cpu().numpy()
+    n = raw.size // 2
+    O = ref if use_ref else port
+    dcfg = O.demod_cfg(cfg.samplerate, cfg.symbolrate, cfg.constellation, cfg.rrc_alpha, cfg.pll_bw, cfg.fmt)
+    fcfg = O.metop_cfg(cfg.ber_thresold, cfg.outsync_after)
+    times, threads, frames = [], 1, 0
+    for i in range(args.warmup + args.steps):
+        if use_ref:
+            secs, cadu, threads = ref.pipeline_timed(dcfg, fcfg, raw)
+        else:
+            t = time.time()
+            cadu = port.pipeline_run(dcfg, fcfg, raw)
+            secs = time.time() - t
+        frames = cadu.size // 1024
+        if i >= args.warmup:
+            times.append(secs)
+    tot = sum(times)
+    val = n * len(times) / tot / 1e6
+    line = {"impl": "reference", "metric": "baseband MS/s end-to-end IQ->CADU (METOP AHRPT)", "value": val, "unit": "MS/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot / len(times) * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32+u8", "data": "synthetic",
+            "config": {"workload": "METOP AHRPT QPSK + Viterbi r=3/4 + RS(255,223) I=4, cs16 @6 MS/s signal, single stream",
+                       "samples_per_step": n, "cadus_per_step": frames},
+            "cpu_baseline": {"value": val, "unit": "MS/s", "cores": threads, "kind": "reference" if use_ref else "port",
+                             "sample": f"2^{log2n} samples of the bench signal per step; reference threading model ({threads} threads, generic non-SIMD VOLK shim; host has {os.cpu_count()} cores)"},
+            "e2e": {"value": val, "unit": "MS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--log2-samples", dest="log2_samples", type=int, default=27)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from satdump_b200 import capi
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the CUDA path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = f"cuda:{local}"
+    n = 1 << args.log2_samples
+    cfg, raw, clear = make_workload(args.log2_samples, rank, dev)
+    n = raw.numel() // 2
+    host = torch.empty(raw.shape, dtype=raw.dtype, pin_memory=True)
+    host.copy_(raw)
+    torch.cuda.synchronize()
+    max_soft = int(n * 0.8) + (1 << 20)
+    ch = capi.Chain(capi.demod_cfg(cfg.samplerate, cfg.symbolrate, cfg.constellation, cfg.rrc_alpha, cfg.pll_bw, cfg.fmt, device=local, max_batch=n),
+                    capi.metop_cfg(cfg.ber_thresold, cfg.outsync_after, device=local, max_soft=max_soft))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_dev():
+        ch.reset()
+        ch.push_device(raw.data_ptr(), n)
+        ch.frames_device()
+        return ch.timing()["push_events"]  # ms, CUDA events on the chain's own streams (torch events cannot see them)
+
+    out_host = np.zeros(max_soft // 8 + (1 << 20), np.uint8)
+
+    def step_host():
+        ch.reset()
+        ch.push_ptr(host.data_ptr(), n)
+        fr = ch.frames(cap=out_host.size)
+        return fr
+
+    # warm-up (also the full-size correctness gate: every CADU must be one of the transmitted frames, in order)
+    for _ in range(max(args.warmup, 3)):
+        step_dev()
+    fr = step_host()
+    nfr = fr.shape[0]
+    first = next((i for i in range(min(64, clear.shape[0])) if np.array_equal(clear[i], fr[0])), None) if nfr else None
+    frames_ok = first is not None and nfr > 0 and np.array_equal(fr, clear[first:first + nfr])
+    launches0 = sum(s["kernel_launches"] for s in ch.stats())
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    # ---- value: inputs resident in HBM
+    barrier()
+    t0 = time.perf_counter()
+    ev_ms = 0.0
+    for _ in range(args.steps):
+        ev_ms += step_dev()
+    torch.cuda.synchronize()
+    wall_dev_host = time.perf_counter() - t0
+    wall_dev = ev_ms * 1e-3  # device time of the K steps (sum of per-push event intervals)
+    tim = ch.timing()
+    launches1 = sum(s["kernel_launches"] for s in ch.stats())
+    barrier()
+    # ---- e2e: host buffers, H2D + D2H inside
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        fr = step_host()
+    torch.cuda.synchronize()
+    wall_e2e = time.perf_counter() - t0
+    barrier()
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    t = torch.tensor([wall_dev, wall_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    wall_dev, wall_e2e = float(t[0]), float(t[1])
+    okt = torch.tensor([1 if frames_ok else 0], device=dev)
+    if world > 1:
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        hbm, which = peaks()
+        value = n * args.steps * world / wall_dev / 1e6
+        e2e = n * args.steps * world / wall_e2e / 1e6
+        vit_ms = tim["k_vit_main"]
+        achieved = tim["vit_chunks"] * ALG_BYTES_PER_CHUNK / (vit_ms * 1e-3) / 1e9 if vit_ms > 0 else 0.0
+        fir_ms = tim["agc_fir"]
+        line = {"metric": "baseband MS/s end-to-end IQ->CADU (METOP AHRPT)", "value": value, "unit": "MS/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": wall_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32+u8", "data": "synthetic",
+                "config": {"workload": "METOP AHRPT QPSK + Viterbi r=3/4 + RS(255,223) I=4, cs16 @6 MS/s signal (BASELINE configs[2]), one stream per GPU",
+                           "samples_per_step_per_gpu": n, "cadus_per_step_per_gpu": int(nfr), "cadus_bit_exact_vs_transmitted": bool(int(okt[0])),
+                           "l2": "input batch (%.0f MiB) larger than L2" % (n * 4 / 2 ** 20), "esn0_db": cfg.esn0_db},
+                "e2e": {"value": e2e, "unit": "MS/s", "h2d_bytes_per_step": n * 4 * world, "d2h_bytes_per_step": int(nfr) * 1024 * world},
+                "gpu_launches": int(launches1 - launches0), "host_wall_ms_per_step": wall_dev_host / args.steps * 1e3,
+                "stage_ms_last_step": {k: round(v, 4) for k, v in tim.items() if k != "vit_chunks"},
+                "roofline": {"kernel": "k_vit_main (warp-per-chunk ACS + chainback)", "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
+                             "frac": achieved / hbm, "traffic": None, "peak_source": which},
+                "roofline_fir_stage": {"kernels": "k_agc_compose + k_agc_scan + k_agc_fir", "bound": "hbm",
+                                       "achieved": n * 12 / (fir_ms * 1e-3) / 1e9 if fir_ms > 0 else 0.0, "peak": hbm, "unit": "GB/s",
+                                       "frac": (n * 12 / (fir_ms * 1e-3) / 1e9 / hbm) if fir_ms > 0 else 0.0},
+                "clocks": sampler.summary()}
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                from oracle import ref, port
+                O = ref if ref.available() else port
+                m = min(n, 1 << 25)
+                hraw = host.numpy()[:2 * m]
+                dcfg = O.demod_cfg(cfg.samplerate, cfg.symbolrate, cfg.constellation, cfg.rrc_alpha, cfg.pll_bw, cfg.fmt)
+                fcfg = O.metop_cfg(cfg.ber_thresold, cfg.outsync_after)
+                if O is ref:
+                    secs, _, threads = ref.pipeline_timed(dcfg, fcfg, hraw)
+                else:
+                    t0 = time.time()
+                    port.pipeline_run(dcfg, fcfg, hraw)
+                    secs, threads = time.time() - t0, 1
+                line["cpu_baseline"] = {"value": m / secs / 1e6, "unit": "MS/s", "cores": threads, "kind": "reference" if O is ref else "port",
+                                        "sample": f"first 2^25 samples of the bench signal, reference threading model ({threads} threads, generic VOLK shim); host has {os.cpu_count()} cores"}
+            except Exception as ex:  # the oracle is test infrastructure: its absence must not break the product bench
+                line["cpu_baseline"] = {"value": None, "unit": "MS/s", "cores": 0, "kind": "unavailable", "sample": str(ex)[:200]}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

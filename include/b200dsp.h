@@ -148,7 +148,9 @@ int b200_chain_pull_frames(b200_chain *c, uint8_t *host_out, long cap, long *nby
 int b200_chain_frames_device(b200_chain *c, const uint8_t **dev_ptr, long *nbytes);
 int b200_chain_get_stats(b200_chain *c, b200_demod_stats *ds, b200_fec_stats *fs);
 /* timing taps used by bench.py: elapsed device milliseconds of the last push per stage (CUDA events on the chain's stream) */
-int b200_chain_last_timing(b200_chain *c, float *ms_out, int n); /* [0]=total [1]=agc+fir [2]=costas [3]=m&m [4]=viterbi [5]=deframe+rs */
+int b200_chain_last_timing(b200_chain *c, float *ms_out, int n); /* n >= 9: [0]=sum of stages [1]=agc+fir [2]=costas(+rotate) [3]=m&m [4]=viterbi stage [5]=deframe+rs [6]=k_vit_main alone [7]=chunks it decoded [8]=whole push, event timed */
+/* forget the stream (loop state, lock, FIFOs) but keep every allocation: the next push starts a new stream */
+int b200_chain_reset(b200_chain *c);
 
 #ifdef __cplusplus
 }

@@ -25,7 +25,7 @@ SYMBOLS = [
     "b200_fec_create", "b200_fec_destroy", "b200_fec_push_soft", "b200_fec_push_soft_device", "b200_fec_pull_frames",
     "b200_fec_debug_bits", "b200_fec_get_stats", "b200_fec_cadu_bytes", "b200_fec_chunk_size",
     "b200_chain_create", "b200_chain_destroy", "b200_chain_push_iq", "b200_chain_push_iq_device", "b200_chain_pull_frames",
-    "b200_chain_frames_device", "b200_chain_get_stats", "b200_chain_last_timing",
+    "b200_chain_frames_device", "b200_chain_get_stats", "b200_chain_last_timing", "b200_chain_reset",
 ]
 
 
@@ -103,6 +103,7 @@ def lib():
         L.b200_chain_frames_device.argtypes = [vp, C.POINTER(vp), C.POINTER(cl)]
         L.b200_chain_get_stats.argtypes = [vp, C.POINTER(DemodStats), C.POINTER(FecStats)]
         L.b200_chain_last_timing.argtypes = [vp, vp, ci]
+        L.b200_chain_reset.argtypes = [vp]
         _lib = L
     return _lib
 
@@ -306,6 +307,10 @@ class Chain:
         return _struct_dict(d), _struct_dict(f)
 
     def timing(self):
-        ms = np.zeros(6, np.float32)
-        _chk(lib().b200_chain_last_timing(self.h, ms.ctypes.data, 6))
-        return dict(zip(["total", "agc_fir", "costas", "mm", "viterbi", "deframe_rs"], ms.tolist()))
+        ms = np.zeros(9, np.float32)
+        _chk(lib().b200_chain_last_timing(self.h, ms.ctypes.data, 9))
+        return dict(zip(["stages_sum", "agc_fir", "costas", "mm", "viterbi", "deframe_rs", "k_vit_main", "vit_chunks", "push_events"], ms.tolist()))
+
+    def reset(self):
+        _chk(lib().b200_chain_reset(self.h))
+        return self

@@ -44,6 +44,7 @@ static void chain_push(Chain &c, const void *iq, long n, bool on_device)
     c.f->process();
     B200_CUDA(cudaEventRecord(c.e1, c.f->stream));
     B200_CUDA(cudaEventSynchronize(c.e1));
+    cudaEventElapsedTime(&c.t_total, c.e0, c.e1);
 }
 
 extern "C" {
@@ -99,6 +100,14 @@ int b200_chain_frames_device(b200_chain *h, const uint8_t **dev_ptr, long *nbyte
         h->c.f->out_frames = 0;
     });
 }
+int b200_chain_reset(b200_chain *h)
+{
+    return guarded([&] {
+        B200_REQUIRE(h, B200_EINVAL, "NULL argument");
+        h->c.d->reset();
+        h->c.f->reset();
+    });
+}
 int b200_chain_get_stats(b200_chain *h, b200_demod_stats *ds, b200_fec_stats *fs)
 {
     return guarded([&] {
@@ -112,7 +121,7 @@ int b200_chain_get_stats(b200_chain *h, b200_demod_stats *ds, b200_fec_stats *fs
 int b200_chain_last_timing(b200_chain *h, float *ms, int n)
 {
     return guarded([&] {
-        B200_REQUIRE(h && ms && n >= 6, B200_EINVAL, "need room for 6 floats");
+        B200_REQUIRE(h && ms && n >= 9, B200_EINVAL, "need room for 9 floats");
         Chain &c = h->c;
         ms[1] = c.d->t_agcfir;
         ms[2] = c.d->t_costas;
@@ -120,6 +129,9 @@ int b200_chain_last_timing(b200_chain *h, float *ms, int n)
         ms[4] = c.f->t_vit;
         ms[5] = c.f->t_frames;
         ms[0] = ms[1] + ms[2] + ms[3] + ms[4] + ms[5];
+        ms[6] = c.f->t_vit_main;               // k_vit_main alone (sum over its launches in the last push)
+        ms[7] = (float)c.f->last_main_chunks;  // chunks those launches decoded
+        ms[8] = c.t_total;                     // CUDA-event time from the start of the push (before any H2D) to the last kernel
     });
 }
 }

@@ -141,7 +141,7 @@ Demod::Demod(const b200_demod_cfg &c) : cfg(c)
     quad.alloc(nseg_max);
     offs.alloc(nseg_max + 1);
     const double omin = sps * (1.0 - c.clock_omega_limit) - 0.01;
-    slots.alloc((size_t)(max_batch / omin) + nseg_max * 16 + 1024);
+    slots.alloc((size_t)(max_batch / omin) + nseg_max * 24 + 1024);
     sym_out.alloc((size_t)(max_batch / omin) + 1024);
     soft.alloc(((size_t)(max_batch / omin) + 1024) * bps);
     d_bank.alloc(128 * 8);
@@ -178,6 +178,22 @@ Demod::~Demod()
         cudaStreamDestroy(stream);
 }
 
+void Demod::reset()
+{
+    DeviceGuard g(cfg.device);
+    B200_CUDA(cudaStreamSynchronize(stream));
+    memset(h_state, 0, sizeof(DemodDevState));
+    h_state->gain[0] = h_state->gain[1] = 1.0f;
+    for (int i = 0; i < 2; i++) {
+        h_state->mm[i].mu = cfg.clock_mu;
+        h_state->mm[i].omega = sps;
+    }
+    B200_CUDA(cudaMemcpyAsync(st.p, h_state, sizeof(DemodDevState), cudaMemcpyHostToDevice, stream));
+    B200_CUDA(cudaStreamSynchronize(stream));
+    parity = 0;
+    last_n = last_syms = 0;
+}
+
 int Demod::choose_L(long n) const
 {
     // one segment per thread; aim at one full wave of resident threads, but keep segments within [1024, 16384] samples
@@ -189,7 +205,7 @@ int Demod::choose_L(long n) const
 int Demod::slot_cap_for(int L) const
 {
     const double omin = sps * (1.0 - cfg.clock_omega_limit) - 0.01;
-    return (int)(L / omin) + 8;
+    return (int)(L / omin) + 16;
 }
 
 template <int FMT> static void launch_front(Demod &d, const void *raw, long n, int ntiles, FirTaps taps, int cur, bool dump)
@@ -266,7 +282,7 @@ long Demod::process(const void *d_raw, long n, int8_t *soft_dst)
     const int cap = slot_cap_for(L);
     B200_REQUIRE((size_t)nseg * cap <= slots.n, B200_ENOMEM, "internal: symbol slot storage too small");
     k_mm<<<nblk, SEG_THREADS, MM_SMEM_BYTES, stream>>>(mmin, n, L, Wm, nseg, MP, &S->mm[cur], &S->mm[nxt], d_bank.p, slots.p, cap, mrec.p);
-    k_mm_scan<<<1, 1024, 0, stream>>>(mrec.p, nseg, 1e-3f, offs.p, &S->mm_unconv, cap, &S->flags);
+    k_mm_scan<<<1, 1024, 0, stream>>>(mrec.p, nseg, 0.02f, offs.p, &S->mm_unconv, cap, &S->flags);
     int8_t *sdst = soft_dst ? soft_dst : soft.p;
     k_mm_compact<<<std::min(nseg, 148 * 8), 256, 0, stream>>>(slots.p, cap, mrec.p, offs.p, nseg, bps == 1, sym_out.p, sdst);
     launches += 3;

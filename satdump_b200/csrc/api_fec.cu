@@ -98,6 +98,10 @@ Fec::Fec(const b200_fec_cfg &c) : cfg(c)
     B200_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     for (auto &e : ev)
         B200_CUDA(cudaEventCreate(&e));
+    for (auto &e : evm)
+        B200_CUDA(cudaEventCreate(&e));
+    for (auto &e : evf)
+        B200_CUDA(cudaEventCreate(&e));
     max_chunks = c.max_soft / geom.chunk + 2;
     softbuf.alloc((size_t)c.max_soft + 2 * geom.chunk);
     dec.alloc((size_t)max_chunks * geom.dec_stride);
@@ -144,6 +148,10 @@ Fec::~Fec()
     if (stream)
         cudaStreamSynchronize(stream);
     for (auto &e : ev)
+        cudaEventDestroy(e);
+    for (auto &e : evm)
+        cudaEventDestroy(e);
+    for (auto &e : evf)
         cudaEventDestroy(e);
     for (void *p : {(void *)h_rec, (void *)h_idle, (void *)h_counters, (void *)h_dstate, (void *)h_events, (void *)h_rs_err})
         if (p)
@@ -205,11 +213,19 @@ static void viterbi_segment(Fec &f, long c0, long nch, std::vector<OutChunk> &ou
             k_vit_spec<<<(n - 1 + wpb - 1) / wpb, 32 * wpb, 0, f.stream>>>(f.softbuf.p, c, n, f.geom, f.hyp, f.spec_steps, f.start_state.p);
             f.launches++;
         }
+        B200_CUDA(cudaEventRecord(f.evm[0], f.stream));
         k_vit_main<<<nb_main, 32 * wpb, 0, f.stream>>>(f.softbuf.p, c, n, f.geom, f.hyp, f.start_state.p, f.dec.p, f.chunk_bits.p, out_base, f.rec.p);
+        B200_CUDA(cudaEventRecord(f.evm[1], f.stream));
         k_vit_ber<<<nb_main, 32 * wpb, 0, f.stream>>>(f.softbuf.p, c, n, f.geom, f.hyp, f.chunk_bits.p, out_base, f.enc_state, f.rec.p);
         f.launches += 2;
         B200_CUDA(cudaMemcpyAsync(f.h_rec, f.rec.p, sizeof(VitRec) * n, cudaMemcpyDeviceToHost, f.stream));
         B200_CUDA(cudaStreamSynchronize(f.stream));
+        {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, f.evm[0], f.evm[1]);
+            f.t_vit_main += ms;
+            f.last_main_chunks += n;
+        }
         int accepted = 0;
         for (int i = 0; i < n; i++) {
             if (i > 0 && f.h_rec[i].start_used != f.h_rec[i - 1].next_start) {
@@ -242,6 +258,7 @@ static void viterbi_segment(Fec &f, long c0, long nch, std::vector<OutChunk> &ou
 void Fec::deframe_and_rs(long new_bits)
 {
     const long nbits = fifo_bits + new_bits;
+    B200_CUDA(cudaEventRecord(evf[0], stream));
     k_deframe<<<1, 32, 0, stream>>>(fifo.p, nbits, cfg.cadu_size, st_synced, cfg.asm_sync, dstate.p, frames.p, (int)max_frames_push,
                                    reinterpret_cast<DefrEventDev *>(devents.p), 4096, counters.p);
     launches++;
@@ -290,8 +307,38 @@ void Fec::deframe_and_rs(long new_bits)
         out_frames += kept;
         total_frames += kept;
     }
+    B200_CUDA(cudaEventRecord(evf[1], stream));
+    B200_CUDA(cudaEventSynchronize(evf[1]));
+    {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, evf[0], evf[1]);
+        t_frames += ms;
+    }
     fifo_bits = nbits;
     defr_state_now = h_dstate->state;
+}
+
+// back to the state of a freshly created decoder (new stream), keeping all allocations
+void Fec::reset()
+{
+    DeviceGuard g(cfg.device);
+    B200_CUDA(cudaStreamSynchronize(stream));
+    soft_have = 0;
+    fifo_bits = 32;
+    vit_state = 0; invalid = 0; main_next_start = -1; enc_state = 0; nrzm_last = 0; nosync_runs = 0;
+    hyp = VitHyp{0, 0, 0};
+    idle_st = VitIdleState{-1, 0};
+    last_ber = 10.f;
+    defr_state_now = 2;
+    out_frames = 0;
+    last_bits0 = last_nbits = 0;
+    B200_CUDA(cudaMemsetAsync(fifo.p, 0, 64, stream));
+    h_dstate[0].state = 2;
+    h_dstate[0].inversion = h_dstate[0].good = h_dstate[0].bad = 0;
+    h_dstate[0].pos = 32;
+    h_dstate[0].frame_pay = -1;
+    B200_CUDA(cudaMemcpyAsync(dstate.p, h_dstate, sizeof(DefrState), cudaMemcpyHostToDevice, stream));
+    B200_CUDA(cudaStreamSynchronize(stream));
 }
 
 void Fec::process()
@@ -320,6 +367,9 @@ void Fec::process()
     }
     last_bits0 = fifo_bits;
     last_nbits = 0;
+    t_frames = 0;
+    t_vit_main = 0;
+    last_main_chunks = 0;
     B200_CUDA(cudaEventRecord(ev[0], stream));
     float acc_frames_ms = 0;
     long c = 0;
@@ -420,6 +470,7 @@ void Fec::process()
     B200_CUDA(cudaStreamSynchronize(stream));
     B200_CUDA(cudaGetLastError());
     cudaEventElapsedTime(&t_vit, ev[0], ev[1]);
+    t_vit -= t_frames; // ev[0]..ev[1] spans both stages
     (void)acc_frames_ms;
 }
 

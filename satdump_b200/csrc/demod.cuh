@@ -586,7 +586,11 @@ struct MMState // carried between batches (exact for segment 0)
     int inc; // window start of the next symbol, relative to the batch start, in buffer coordinates
     int pad;
 };
-struct MMRec { int u_first, u_final, count, pad; float mu_first, mu_final, omega_first, omega_final; };
+// per-segment record: the thread also emits the symbols of a short candidate zone BEFORE its segment (u >= own0 - MM_ZONE) and
+// records the sampling instants of its first emitted symbols; k_mm_scan stitches neighbours by matching real-valued instants
+// u + mu (so a symbol whose window start falls within the loops' ~1e-4 disagreement of a segment boundary is neither lost nor doubled).
+constexpr int MM_ZONE = 6;
+struct MMRec { int u_final, count, skip, pad; float mu_final, omega_final; int head_u[4]; float head_mu[4]; };
 
 #ifdef B200_DEFINE_KERNELS
 __global__ void __launch_bounds__(SEG_THREADS) k_mm(const float2 *__restrict__ mmin /* 16-sample front pad */, long N, int L, int W, int nseg,
@@ -638,8 +642,11 @@ __global__ void __launch_bounds__(SEG_THREADS) k_mm(const float2 *__restrict__ m
     };
     issue(r);
     issue(r + 1);
-    int count = 0, u_first = -1;
-    float mu_first = 0.f, omega_first = 0.f;
+    int count = 0;
+    MMRec mr;
+#pragma unroll
+    for (int i = 0; i < 4; i++) { mr.head_u[i] = 0; mr.head_mu[i] = 0.f; }
+    const long emit0 = (s == 0) ? own0 : own0 - MM_ZONE;
     float2 *my = slots + (long)s * cap;
     // row loop: with rows <= rr+... loaded we may process every symbol whose newest sample u < 16*(rr+1)
     for (long rr = r + 1; rr < rend + 1; rr++) {
@@ -647,10 +654,11 @@ __global__ void __launch_bounds__(SEG_THREADS) k_mm(const float2 *__restrict__ m
         cp_async_wait<1>(); // rows <= rr complete
         const long lim = min((rr + 1) << 4, own1);
         while (u < lim) {
-            if (u >= own0 && u_first < 0) {
-                u_first = (int)u;
-                mu_first = mu;
-                omega_first = omega;
+            if (u >= emit0 && count < 4) {
+                if (count == 0) { mr.head_u[0] = (int)u; mr.head_mu[0] = mu; }
+                else if (count == 1) { mr.head_u[1] = (int)u; mr.head_mu[1] = mu; }
+                else if (count == 2) { mr.head_u[2] = (int)u; mr.head_mu[2] = mu; }
+                else { mr.head_u[3] = (int)u; mr.head_mu[3] = mu; }
             }
             p2 = p1; p1 = p0; c2 = c1; c1 = c0;
             int imu = (int)rintf(mu * 128.0f);
@@ -670,7 +678,7 @@ __global__ void __launch_bounds__(SEG_THREADS) k_mm(const float2 *__restrict__ m
             float yr = (c0.x - c2.x) * p1.x + (c0.y - c2.y) * p1.y;
             float pe = xr - yr;
             pe = fminf(1.0f, fmaxf(-1.0f, pe));
-            if (u >= own0) {
+            if (u >= emit0) {
                 if (count < cap)
                     my[count] = p0;
                 count++;
@@ -688,14 +696,11 @@ __global__ void __launch_bounds__(SEG_THREADS) k_mm(const float2 *__restrict__ m
             break;
     }
     cp_async_wait<0>();
-    MMRec mr;
-    mr.u_first = u_first < 0 ? (int)u : u_first; // segment without symbols: report where the next one lies
-    mr.mu_first = u_first < 0 ? mu : mu_first;
-    mr.omega_first = u_first < 0 ? omega : omega_first;
     mr.u_final = (int)u;
     mr.mu_final = mu;
     mr.omega_final = omega;
     mr.count = count;
+    mr.skip = 0;
     mr.pad = 0;
     rec[s] = mr;
     if (s == nseg - 1) {
@@ -708,7 +713,7 @@ __global__ void __launch_bounds__(SEG_THREADS) k_mm(const float2 *__restrict__ m
 }
 
 // ---------------------------------------------------------------- K3b: symbol offsets (exclusive scan) + junction check
-__global__ void __launch_bounds__(1024) k_mm_scan(const MMRec *__restrict__ rec, int nseg, float tol_mu, long *__restrict__ offs /*nseg+1*/,
+__global__ void __launch_bounds__(1024) k_mm_scan(MMRec *__restrict__ rec, int nseg, float tol_t, long *__restrict__ offs /*nseg+1*/,
                                                  int *__restrict__ unconv, int cap, int *__restrict__ flags)
 {
     __shared__ long wsum[32];
@@ -722,14 +727,25 @@ __global__ void __launch_bounds__(1024) k_mm_scan(const MMRec *__restrict__ rec,
         int s = base + t;
         long c = 0;
         if (s < nseg) {
-            c = rec[s].count;
+            MMRec b = rec[s];
+            c = b.count;
             if (c > cap)
                 over = 1;
+            int skip = 0;
             if (s > 0) {
-                MMRec a = rec[s - 1], b = rec[s];
-                if (a.u_final != b.u_first || fabsf(a.mu_final - b.mu_first) > tol_mu)
+                // instant of the symbol that follows segment s-1's last one, as seen by its own thread
+                const MMRec a = rec[s - 1];
+                const double tref = (double)a.u_final + (double)a.mu_final;
+                const int nh = (int)min(4L, c);
+                while (skip < nh && (double)b.head_u[skip] + (double)b.head_mu[skip] < tref - 0.5)
+                    skip++;
+                // the first kept symbol must be that very symbol
+                double tk = (skip < nh) ? (double)b.head_u[skip] + (double)b.head_mu[skip] : (double)b.u_final + (double)b.mu_final;
+                if (skip >= 4 || fabs(tk - tref) > tol_t)
                     bad++;
             }
+            rec[s].skip = skip;
+            c -= skip;
         }
         long v = c;
 #pragma unroll
@@ -786,9 +802,10 @@ __global__ void __launch_bounds__(256) k_mm_compact(const float2 *__restrict__ s
                                                    int8_t *__restrict__ soft_out)
 {
     for (int s = blockIdx.x; s < nseg; s += gridDim.x) {
-        const int c = min(rec[s].count, cap);
+        const int sk = rec[s].skip;
+        const int c = min(rec[s].count, cap) - sk;
         const long o = offs[s];
-        const float2 *src = slots + (long)s * cap;
+        const float2 *src = slots + (long)s * cap + sk;
         for (int i = threadIdx.x; i < c; i += blockDim.x) {
             float2 v = src[i];
             if (sym_out)

@@ -33,6 +33,7 @@ class Demod
     long process(const void *d_raw, long nsamples, int8_t *soft_dst);
     long push_host(const void *h_raw, long nsamples, int8_t *soft_dst);
     void stats(b200_demod_stats *out);
+    void reset(); // back to the state of a freshly created demodulator (new stream)
 
     b200_demod_cfg cfg;
     cudaStream_t stream = nullptr;

@@ -32,7 +32,10 @@ class Fec
     int cadu_bytes, nphases, ph0, ph1, nswap, st_synced, spec_steps;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[3];
-    float t_vit = 0, t_frames = 0;
+    float t_vit = 0, t_frames = 0, t_vit_main = 0; // ms of the last process(): whole Viterbi stage, deframe+RS, k_vit_main alone
+    cudaEvent_t evm[2], evf[2];
+    long last_main_chunks = 0;
+    void reset();
 
     // device storage
     DevBuf<int8_t> softbuf;

@@ -1,0 +1,111 @@
+"""CPU: the oracle itself. (1) our C restatement (oracle.c) == the reference's own code (oracle/_ref) bit for bit, stage by
+stage; (2) both reproduce the committed golden fixtures (made from the reference by tests/golden/make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+
+from tests.common import ROOT, oracle_demod, oracle_fec, signal
+from satdump_b200 import synth
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+CONFIGS = ["metop_ahrpt", "bpsk_half", "jpss_hrd", "dvbs2_front"]
+
+
+def _ref():
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    return ref
+
+
+def bitwise(a, b):
+    return a.shape == b.shape and np.array_equal(a.view(np.uint8), b.view(np.uint8))
+
+
+@pytest.mark.parametrize("name", CONFIGS)
+def test_port_matches_golden(built, name):
+    from oracle import port
+    g = np.load(os.path.join(GOLD, f"{name}.npz"))
+    cfg = synth.CONFIGS[name]
+    o = oracle_demod(port, cfg).run(g["raw"])
+    assert o["mm"].size == int(g["nsym"])
+    assert bitwise(o["agc"][:4096], g["agc_head"]) and bitwise(o["fir"][:4096], g["fir_head"]) and bitwise(o["mm"][:4096], g["mm_head"])
+    if "costas_head" in g:
+        assert bitwise(o["costas"][:4096], g["costas_head"])
+    assert np.array_equal(o["soft"], g["soft"])
+    if cfg.decoder != "none":
+        f = oracle_fec(port, cfg).run(o["soft"])
+        assert np.array_equal(f["cadu"], g["cadu"])
+        assert np.array_equal(np.packbits(f["bits"]), g["bits"]) and f["bits"].size == int(g["nbits"])
+        assert np.array_equal(f["vit_state"], g["vit_state"]) and np.array_equal(f["defr_state"], g["defr_state"])
+        assert np.array_equal(f["rs_err"], g["rs_err"])
+
+
+@pytest.mark.parametrize("name", CONFIGS)
+def test_ref_matches_golden(built, name):
+    ref = _ref()
+    g = np.load(os.path.join(GOLD, f"{name}.npz"))
+    cfg = synth.CONFIGS[name]
+    o = oracle_demod(ref, cfg).run(g["raw"])
+    assert np.array_equal(o["soft"], g["soft"]) and bitwise(o["mm"][:4096], g["mm_head"])
+    if cfg.decoder != "none":
+        assert np.array_equal(oracle_fec(ref, cfg).run(o["soft"])["cadu"], g["cadu"])
+
+
+@pytest.mark.parametrize("name", CONFIGS)
+def test_port_equals_reference_fresh_signal(built, name):
+    """A signal that is not in the fixtures, longer, different seed."""
+    ref = _ref()
+    from oracle import port
+    cfg, raw, _ = signal(name, 18, seed=11)
+    a, b = oracle_demod(ref, cfg).run(raw), oracle_demod(port, cfg).run(raw)
+    for k in ("agc", "fir", "costas", "mm", "soft"):
+        if a[k] is not None:
+            assert bitwise(a[k], b[k]), k
+    if cfg.decoder != "none":
+        fa, fb = oracle_fec(ref, cfg).run(a["soft"]), oracle_fec(port, cfg).run(a["soft"])
+        for k in ("cadu", "bits", "vit_state", "defr_state", "rs_err"):
+            assert np.array_equal(fa[k], fb[k]), k
+
+
+def test_port_low_snr_matches_reference(built):
+    """Es/N0 5.5 dB: Viterbi makes errors, RS corrects most of them; the restatement must follow the reference through it."""
+    ref = _ref()
+    from oracle import port
+    cfg, raw, _ = signal("metop_ahrpt", 19, seed=5, esn0=5.5)
+    a = oracle_demod(ref, cfg).run(raw, stages=False)
+    fa, fb = oracle_fec(ref, cfg).run(a["soft"]), oracle_fec(port, cfg).run(a["soft"])
+    assert fa["rs_err"].sum() > 0, "the stress case should exercise RS"
+    for k in ("cadu", "bits", "vit_state", "defr_state", "rs_err"):
+        assert np.array_equal(fa[k], fb[k]), k
+
+
+def test_rs_stress_golden(built):
+    """RS(255,223) I=4 with 0..20 byte errors per codeword: corrections, the 'parity bytes stay as received' rule and the
+    failure verdicts (libcorrect: locator degree != root count) all match the reference's output."""
+    from oracle import port
+    g = np.load(os.path.join(GOLD, "rs_stress.npz"))
+    nfail = 0
+    for f in range(g["noisy"].shape[0]):
+        d, e = port.rs_decode_interleaved(g["noisy"][f], True, 4)
+        assert np.array_equal(d, g["decoded"][f]) and np.array_equal(e, g["errors"][f])
+        nfail += int((e < 0).sum())
+    assert nfail > 10
+
+
+def test_primitives_vs_reference(built):
+    ref = _ref()
+    from oracle import port
+    rng = np.random.default_rng(3)
+    bits = rng.integers(0, 2, 5000, dtype=np.uint8)
+    assert np.array_equal(ref.cc_encode(bits), port.cc_encode(bits))
+    syms = rng.integers(0, 256, 3 * 2 * 1024 + 12, dtype=np.uint8)
+    assert np.array_equal(ref.cc_decode(syms, 1024, 3), port.cc_decode(syms, 1024, 3))
+    soft = rng.integers(-128, 128, 4096, dtype=np.int8)
+    for ph in range(4):
+        for sw in (0, 1):
+            assert np.array_equal(ref.rotate_soft(soft, ph, sw), port.rotate_soft(soft, ph, sw))
+    assert np.array_equal(ref.derand(np.zeros(1020, np.uint8)), port.derand(np.zeros(1020, np.uint8)))
+    assert np.array_equal(ref.rrc_design(1, 6e6, 2333333, 0.5, 31), port.rrc_design(1, 6e6, 2333333, 0.5, 31))
+    assert np.array_equal(ref.mm_taps(), port.mm_taps())
