@@ -84,9 +84,10 @@ typedef struct b200_demod_stats
 {
     long samples_in, symbols_out;
     float agc_gain, costas_phase, costas_freq, mm_mu, mm_omega;
-    long costas_unconverged;  /* segment junctions whose warm-up had not converged (expected 0)  */
-    long mm_unconverged;      /* M&M segment junctions that disagreed (expected 0)               */
+    long costas_unconverged;  /* junctions still inconsistent after the repair rounds of the last push (expected 0) */
+    long mm_unconverged;      /* same for the M&M loop                                            */
     int agc_clamped;          /* AGC hit max_gain: outside the parallel formulation              */
+    int repairs;              /* segments re-run as exact sequential continuations (junction check failed) */
     long kernel_launches;     /* CUDA kernels launched by this object so far                     */
 } b200_demod_stats;
 

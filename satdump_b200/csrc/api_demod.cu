@@ -89,6 +89,9 @@ void design_mm_bank(std::vector<float> &out)
 }
 
 static int round_up16(double v) { return ((int)std::ceil(v / 16.0)) * 16; }
+constexpr int REPAIR_ROUNDS = 3;   // a run of r consecutive unconverged junctions needs r rounds
+constexpr float MM_TOL = 0.05f;    // samples: junction disagreement of the sampling instant that triggers a repair
+__global__ void k_count_repairs(const int *count, int *total) { *total += min(*count, 1024); }
 
 Demod::Demod(const b200_demod_cfg &c) : cfg(c)
 {
@@ -114,7 +117,9 @@ Demod::Demod(const b200_demod_cfg &c) : cfg(c)
     design_rrc(1, final_fs, (double)(int)rs, c.rrc_alpha, c.rrc_taps, rrc);
     design_mm_bank(bank);
     Wc = round_up16(24.0 / c.pll_bw);
-    Wm = round_up16(70.0 / c.clock_gain_mu);
+    // M&M warm-up: the critically damped timing loop needs ~10 time constants to land on the sequential trajectory to ~1e-4
+    // sample (measured: QPSK 3200 symbols -> max 1e-3; BPSK's TED gain is lower -> slower)
+    Wm = round_up16((c.constellation == B200_BPSK ? 120.0 : 70.0) / c.clock_gain_mu);
     int dev_sms = 148;
     cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, c.device);
     seg_cap_threads = dev_sms * 3 * SEG_THREADS;
@@ -140,6 +145,7 @@ Demod::Demod(const b200_demod_cfg &c) : cfg(c)
     mrec.alloc(nseg_max);
     quad.alloc(nseg_max);
     offs.alloc(nseg_max + 1);
+    repair.alloc(1025);
     const double omin = sps * (1.0 - c.clock_omega_limit) - 0.01;
     slots.alloc((size_t)(max_batch / omin) + nseg_max * 24 + 1024);
     sym_out.alloc((size_t)(max_batch / omin) + 1024);
@@ -263,8 +269,14 @@ long Demod::process(const void *d_raw, long n, int8_t *soft_dst)
         }
         P.fmin = -cfg.costas_max_offset;
         P.fmax = cfg.costas_max_offset;
-        k_costas<<<nblk, SEG_THREADS, 0, stream>>>(fir_out, n, L, Wc, nseg, P, S->costas[cur], cos_out, crec.p);
-        k_costas_fix<<<1, 1024, 0, stream>>>(crec.p, nseg, order, 2e-3f, 1e-4f, quad.p, S->costas[nxt], &S->costas_unconv);
+        k_costas<<<nblk, SEG_THREADS, 0, stream>>>(fir_out, n, L, Wc, nseg, P, S->costas[cur], cos_out, crec.p, nullptr, nullptr);
+        k_costas_fix<<<1, 1024, 0, stream>>>(crec.p, nseg, order, 2e-3f, 1e-4f, quad.p, S->costas[nxt], &S->costas_unconv, repair.p + 1, repair.p);
+        for (int round = 0; round < REPAIR_ROUNDS; round++) { // no-ops (a few microseconds) when every junction had converged
+            k_count_repairs<<<1, 1, 0, stream>>>(repair.p, &S->repairs);
+            k_costas<<<8, SEG_THREADS, 0, stream>>>(fir_out, n, L, Wc, nseg, P, S->costas[cur], cos_out, crec.p, repair.p + 1, repair.p);
+            k_costas_fix<<<1, 1024, 0, stream>>>(crec.p, nseg, order, 2e-3f, 1e-4f, quad.p, S->costas[nxt], &S->costas_unconv, repair.p + 1, repair.p);
+            launches += 3;
+        }
         mmin = bufA.p; // FIR output is dead now: reuse its buffer (in place compatible: same index mapping)
         k_rotate<<<2048, 256, 0, stream>>>(cos_out, n, L, order, cfg.constellation == B200_OQPSK, quad.p, S->mm_hist[cur], S->mm_hist[nxt], mmin);
         launches += 3;
@@ -281,8 +293,14 @@ long Demod::process(const void *d_raw, long n, int8_t *soft_dst)
     MP.mu_gain = cfg.clock_gain_mu;
     const int cap = slot_cap_for(L);
     B200_REQUIRE((size_t)nseg * cap <= slots.n, B200_ENOMEM, "internal: symbol slot storage too small");
-    k_mm<<<nblk, SEG_THREADS, MM_SMEM_BYTES, stream>>>(mmin, n, L, Wm, nseg, MP, &S->mm[cur], &S->mm[nxt], d_bank.p, slots.p, cap, mrec.p);
-    k_mm_scan<<<1, 1024, 0, stream>>>(mrec.p, nseg, 0.02f, offs.p, &S->mm_unconv, cap, &S->flags);
+    k_mm<<<nblk, SEG_THREADS, MM_SMEM_BYTES, stream>>>(mmin, n, L, Wm, nseg, MP, &S->mm[cur], &S->mm[nxt], d_bank.p, slots.p, cap, mrec.p, nullptr, nullptr);
+    k_mm_scan<<<1, 1024, 0, stream>>>(mrec.p, nseg, MM_TOL, offs.p, &S->mm_unconv, cap, &S->flags, repair.p + 1, repair.p);
+    for (int round = 0; round < REPAIR_ROUNDS; round++) {
+        k_count_repairs<<<1, 1, 0, stream>>>(repair.p, &S->repairs);
+        k_mm<<<8, SEG_THREADS, MM_SMEM_BYTES, stream>>>(mmin, n, L, Wm, nseg, MP, &S->mm[cur], &S->mm[nxt], d_bank.p, slots.p, cap, mrec.p, repair.p + 1, repair.p);
+        k_mm_scan<<<1, 1024, 0, stream>>>(mrec.p, nseg, MM_TOL, offs.p, &S->mm_unconv, cap, &S->flags, repair.p + 1, repair.p);
+        launches += 3;
+    }
     int8_t *sdst = soft_dst ? soft_dst : soft.p;
     k_mm_compact<<<std::min(nseg, 148 * 8), 256, 0, stream>>>(slots.p, cap, mrec.p, offs.p, nseg, bps == 1, sym_out.p, sdst);
     launches += 3;
@@ -328,6 +346,7 @@ void Demod::stats(b200_demod_stats *o)
     o->costas_unconverged = h_state->costas_unconv;
     o->mm_unconverged = h_state->mm_unconv;
     o->agc_clamped = h_state->flags & 1;
+    o->repairs = h_state->repairs;
     o->kernel_launches = launches;
 }
 

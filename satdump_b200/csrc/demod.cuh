@@ -366,19 +366,32 @@ __device__ __forceinline__ float costas_error(float vr, float vi, int order)
 
 // in/out: N samples. Segment s owns samples [s*L, min((s+1)L, N)); thread warms up from max(0, s*L - W).
 // state_in = {phase, freq} carried from the previous batch (exact start of segment 0 and of any clipped warm-up).
+// Repair mode (repair_list != nullptr): thread i re-runs segment repair_list[i] with NO warm-up, starting from the recorded end
+// state of its predecessor, i.e. as the exact sequential continuation of that segment (used for junctions whose warm-up had
+// not converged; k_costas_fix re-checks afterwards).
 __global__ void __launch_bounds__(SEG_THREADS) k_costas(const float2 *__restrict__ in, long N, int L, int W, int nseg, CostasParams P,
-                                                         const float *__restrict__ state_in, float2 *__restrict__ out, LoopRec *__restrict__ rec)
+                                                         const float *__restrict__ state_in, float2 *__restrict__ out, LoopRec *__restrict__ rec,
+                                                         const int *__restrict__ repair_list, const int *__restrict__ repair_count)
 {
     __shared__ float2 ring[32][SEG_THREADS];
     const int t = threadIdx.x;
-    const int s = blockIdx.x * SEG_THREADS + t;
+    int s = blockIdx.x * SEG_THREADS + t;
+    if (repair_list) {
+        if (s >= min(*repair_count, 1024))
+            return;
+        s = repair_list[s];
+    }
     if (s >= nseg)
         return;
     const long own0 = (long)s * L;
     const long own1 = min(own0 + L, N);
     long start = own0 - W;
     float phase = 0.f, freq = state_in[1];
-    if (start <= 0) {
+    if (repair_list) {
+        start = own0;
+        phase = rec[s - 1].ph_end;
+        freq = rec[s - 1].fr_end;
+    } else if (start <= 0) {
         start = 0;
         phase = state_in[0];
     }
@@ -454,15 +467,19 @@ __global__ void __launch_bounds__(SEG_THREADS) k_costas(const float2 *__restrict
 // ---------------------------------------------------------------- K2b: resolve per-segment rotation (prefix sum mod order)
 // quad[s] = number of 2pi/order steps segment s's phase runs AHEAD of the sequential loop. Also publishes the true
 // carried loop state. unconv counts junctions whose residual exceeds tol.
+// repair_list / repair_count: junctions (segment indices) that failed the check in THIS call (count is reset here).
 __global__ void __launch_bounds__(1024) k_costas_fix(const LoopRec *__restrict__ rec, int nseg, int order, float tol_phase, float tol_freq,
-                                                    uint8_t *__restrict__ quad, float *__restrict__ state_out, int *__restrict__ unconv)
+                                                    uint8_t *__restrict__ quad, float *__restrict__ state_out, int *__restrict__ unconv,
+                                                    int *__restrict__ repair_list, int *__restrict__ repair_count)
 {
     __shared__ int wsum[32];
     __shared__ int run;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const float step = 6.283185307179586f / (float)order;
-    if (t == 0)
+    if (t == 0) {
         run = 0;
+        *repair_count = 0;
+    }
     __syncthreads();
     int bad = 0;
     for (int base = 0; base < nseg; base += 1024) {
@@ -472,8 +489,12 @@ __global__ void __launch_bounds__(1024) k_costas_fix(const LoopRec *__restrict__
             float q = rintf(d / step);
             float resid = fabsf(d - q * step);
             k = ((int)q % order + order) % order;
-            if (resid > tol_phase || fabsf(rec[s].fr_start - rec[s - 1].fr_end) > tol_freq)
+            if (resid > tol_phase || fabsf(rec[s].fr_start - rec[s - 1].fr_end) > tol_freq) {
                 bad++;
+                const int slot = atomicAdd(repair_count, 1);
+                if (slot < 1024)
+                    repair_list[slot] = s;
+            }
         }
         int v = k;
 #pragma unroll
@@ -507,9 +528,10 @@ __global__ void __launch_bounds__(1024) k_costas_fix(const LoopRec *__restrict__
     // reduce bad count
     for (int off = 16; off; off >>= 1)
         bad += __shfl_xor_sync(0xffffffffu, bad, off);
-    if (lane == 0 && bad)
-        atomicAdd(unconv, bad);
+    (void)bad;
+    __syncthreads();
     if (t == 0) {
+        *unconv = *repair_count; // junctions still failing after this pass
         int q = quad[nseg - 1];
         float ph = (float)((double)rec[nseg - 1].ph_end - (double)q * (6.283185307179586 / order));
         while (ph > 6.283185307179586)
@@ -590,13 +612,13 @@ struct MMState // carried between batches (exact for segment 0)
 // records the sampling instants of its first emitted symbols; k_mm_scan stitches neighbours by matching real-valued instants
 // u + mu (so a symbol whose window start falls within the loops' ~1e-4 disagreement of a segment boundary is neither lost nor doubled).
 constexpr int MM_ZONE = 6;
-struct MMRec { int u_final, count, skip, pad; float mu_final, omega_final; int head_u[4]; float head_mu[4]; };
+struct MMRec { int u_final, count, skip, pad; float mu_final, omega_final; int head_u[4]; float head_mu[4]; float2 p0, p1, p2, c0, c1, c2; };
 
 #ifdef B200_DEFINE_KERNELS
 __global__ void __launch_bounds__(SEG_THREADS) k_mm(const float2 *__restrict__ mmin /* 16-sample front pad */, long N, int L, int W, int nseg,
                                                      MMParams P, const MMState *__restrict__ st_in, MMState *__restrict__ st_out,
                                                      const float *__restrict__ bank /*128x8*/, float2 *__restrict__ slots, int cap,
-                                                     MMRec *__restrict__ rec)
+                                                     MMRec *__restrict__ rec, const int *__restrict__ repair_list, const int *__restrict__ repair_count)
 {
     extern __shared__ __align__(16) unsigned char mm_smem[];
     float2(*ring)[SEG_THREADS] = reinterpret_cast<float2(*)[SEG_THREADS]>(mm_smem);      // [64][SEG_THREADS]
@@ -605,7 +627,12 @@ __global__ void __launch_bounds__(SEG_THREADS) k_mm(const float2 *__restrict__ m
     for (int i = t; i < 128 * 8; i += SEG_THREADS)
         sbank[i] = bank[i];
     __syncthreads();
-    const int s = blockIdx.x * SEG_THREADS + t;
+    int s = blockIdx.x * SEG_THREADS + t;
+    if (repair_list) { // exact sequential continuation of segment s-1 (see k_costas)
+        if (s >= min(*repair_count, 1024))
+            return;
+        s = repair_list[s];
+    }
     if (s >= nseg)
         return;
     const long own0 = (long)s * L, own1 = min(own0 + L, N);
@@ -614,7 +641,11 @@ __global__ void __launch_bounds__(SEG_THREADS) k_mm(const float2 *__restrict__ m
     float mu, omega;
     float2 p0, p1, p2, c0, c1, c2;
     long ustart = own0 - W;
-    if (ustart <= 0) {
+    if (repair_list) {
+        const MMRec pr = rec[s - 1];
+        mu = pr.mu_final; omega = pr.omega_final; p0 = pr.p0; p1 = pr.p1; p2 = pr.p2; c0 = pr.c0; c1 = pr.c1; c2 = pr.c2;
+        u = pr.u_final;
+    } else if (ustart <= 0) {
         MMState st = *st_in;
         mu = st.mu; omega = st.omega; p0 = st.p0; p1 = st.p1; p2 = st.p2; c0 = st.c0; c1 = st.c1; c2 = st.c2;
         u = st.inc;
@@ -646,7 +677,7 @@ __global__ void __launch_bounds__(SEG_THREADS) k_mm(const float2 *__restrict__ m
     MMRec mr;
 #pragma unroll
     for (int i = 0; i < 4; i++) { mr.head_u[i] = 0; mr.head_mu[i] = 0.f; }
-    const long emit0 = (s == 0) ? own0 : own0 - MM_ZONE;
+    const long emit0 = (s == 0 || repair_list) ? min(own0, u) : own0 - MM_ZONE;
     float2 *my = slots + (long)s * cap;
     // row loop: with rows <= rr+... loaded we may process every symbol whose newest sample u < 16*(rr+1)
     for (long rr = r + 1; rr < rend + 1; rr++) {
@@ -702,6 +733,7 @@ __global__ void __launch_bounds__(SEG_THREADS) k_mm(const float2 *__restrict__ m
     mr.count = count;
     mr.skip = 0;
     mr.pad = 0;
+    mr.p0 = p0; mr.p1 = p1; mr.p2 = p2; mr.c0 = c0; mr.c1 = c1; mr.c2 = c2;
     rec[s] = mr;
     if (s == nseg - 1) {
         MMState st;
@@ -714,13 +746,16 @@ __global__ void __launch_bounds__(SEG_THREADS) k_mm(const float2 *__restrict__ m
 
 // ---------------------------------------------------------------- K3b: symbol offsets (exclusive scan) + junction check
 __global__ void __launch_bounds__(1024) k_mm_scan(MMRec *__restrict__ rec, int nseg, float tol_t, long *__restrict__ offs /*nseg+1*/,
-                                                 int *__restrict__ unconv, int cap, int *__restrict__ flags)
+                                                 int *__restrict__ unconv, int cap, int *__restrict__ flags, int *__restrict__ repair_list,
+                                                 int *__restrict__ repair_count)
 {
     __shared__ long wsum[32];
     __shared__ long run;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    if (t == 0)
+    if (t == 0) {
         run = 0;
+        *repair_count = 0;
+    }
     __syncthreads();
     int bad = 0, over = 0;
     for (int base = 0; base < nseg; base += 1024) {
@@ -741,8 +776,12 @@ __global__ void __launch_bounds__(1024) k_mm_scan(MMRec *__restrict__ rec, int n
                     skip++;
                 // the first kept symbol must be that very symbol
                 double tk = (skip < nh) ? (double)b.head_u[skip] + (double)b.head_mu[skip] : (double)b.u_final + (double)b.mu_final;
-                if (skip >= 4 || fabs(tk - tref) > tol_t)
+                if (skip >= 4 || fabs(tk - tref) > tol_t) {
                     bad++;
+                    const int slot = atomicAdd(repair_count, 1);
+                    if (slot < 1024)
+                        repair_list[slot] = s;
+                }
             }
             rec[s].skip = skip;
             c -= skip;
@@ -780,12 +819,14 @@ __global__ void __launch_bounds__(1024) k_mm_scan(MMRec *__restrict__ rec, int n
         bad += __shfl_xor_sync(0xffffffffu, bad, off);
         over |= __shfl_xor_sync(0xffffffffu, over, off);
     }
-    if (lane == 0 && bad)
-        atomicAdd(unconv, bad);
+    (void)bad;
     if (lane == 0 && over)
         atomicOr(flags, 2);
-    if (t == 0)
+    __syncthreads();
+    if (t == 0) {
         offs[nseg] = run;
+        *unconv = *repair_count; // junctions still failing after this pass
+    }
 }
 
 // module_demod_base.h:106-113 (clamp) applied to re*scale / im*scale

@@ -18,9 +18,9 @@ struct DemodDevState
     float2 agc_tail[2][32];
     float2 mm_hist[2][8];
     int flags;          // bit0 AGC clamp, bit1 M&M slot overflow
-    int costas_unconv;
+    int costas_unconv;  // junctions still unconverged after the repair rounds of the last batch
     int mm_unconv;
-    int pad;
+    int repairs;        // segments re-run as exact continuations so far (all batches)
 };
 
 class Demod
@@ -53,6 +53,7 @@ class Demod
     DevBuf<LoopRec> crec;
     DevBuf<MMRec> mrec;
     DevBuf<uint8_t> quad;
+    DevBuf<int> repair; // [0] count, [1..1024] junction list (shared by the Costas and M&M repair rounds)
     DevBuf<long> offs;
     DevBuf<float> d_bank;
     DevBuf<DemodDevState> st;
