@@ -1,0 +1,447 @@
+#include "stream_modules.hpp"
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <thread>
+
+namespace b200host
+{
+// ------------------------------------------------------------------------------------------------ Params
+std::string Params::str(const std::string &k) const
+{
+    auto it = kv.find(k);
+    if (it == kv.end())
+        throw ModuleError(k + " parameter must be present!");
+    return it->second;
+}
+double Params::num(const std::string &k) const
+{
+    const std::string s = str(k);
+    char *end = nullptr;
+    double v = strtod(s.c_str(), &end);
+    if (end == s.c_str())
+        throw ModuleError("parameter " + k + " is not a number: " + s);
+    return v;
+}
+bool Params::flag(const std::string &k, bool d) const
+{
+    if (!has(k))
+        return d;
+    const std::string s = kv.at(k);
+    return s == "true" || s == "1";
+}
+
+// ------------------------------------------------------------------------------------------------ ByteFifo
+int ByteFifo::write(const uint8_t *data, int len)
+{
+    int done = 0;
+    std::unique_lock<std::mutex> lk(m);
+    while (done < len) {
+        can_write.wait(lk, [&] { return fill < buf.size() || stop_w; });
+        if (stop_w)
+            return -1;
+        size_t n = std::min<size_t>(len - done, buf.size() - fill), tail = (head + fill) % buf.size();
+        size_t first = std::min(n, buf.size() - tail);
+        memcpy(&buf[tail], data + done, first);
+        memcpy(&buf[0], data + done + first, n - first);
+        fill += n;
+        done += (int)n;
+        can_read.notify_one();
+    }
+    return len;
+}
+int ByteFifo::read(uint8_t *data, int len)
+{
+    int done = 0;
+    std::unique_lock<std::mutex> lk(m);
+    while (done < len) {
+        can_read.wait(lk, [&] { return fill > 0 || stop_r; });
+        if (stop_r && fill == 0)
+            return -1;
+        size_t n = std::min<size_t>(len - done, fill), first = std::min(n, buf.size() - head);
+        memcpy(data + done, &buf[head], first);
+        memcpy(data + done + first, &buf[0], n - first);
+        head = (head + n) % buf.size();
+        fill -= n;
+        done += (int)n;
+        can_write.notify_one();
+    }
+    return len;
+}
+int ByteFifo::readable()
+{
+    std::lock_guard<std::mutex> lk(m);
+    return (int)fill;
+}
+void ByteFifo::stopReader()
+{
+    {
+        std::lock_guard<std::mutex> lk(m);
+        stop_r = true;
+    }
+    can_read.notify_all();
+}
+void ByteFifo::stopWriter()
+{
+    {
+        std::lock_guard<std::mutex> lk(m);
+        stop_w = true;
+    }
+    can_write.notify_all();
+}
+
+// ------------------------------------------------------------------------------------------------ parameter mapping
+static void reject(const Params &p, const char *key, const char *why)
+{
+    if (p.has(key) && p.str(key) != "false" && p.str(key) != "0")
+        throw ModuleError(std::string("parameter '") + key + "' is not supported by the B200 path (" + why + "); there is no CPU fallback");
+}
+
+b200_demod_cfg demod_cfg_from_params(const Params &p, bool &is_bpsk)
+{
+    b200_demod_cfg c{};
+    if (!p.has("samplerate"))
+        throw ModuleError("Samplerate parameter must be present!"); // module_demod_base.cpp:17-20
+    c.samplerate = (double)(long)p.num("samplerate");
+    if (!p.has("symbolrate"))
+        throw ModuleError("Symbolrate parameter must be present!");
+    c.symbolrate = (double)(long)p.num("symbolrate");
+    if (!p.has("constellation"))
+        throw ModuleError("Constellation type parameter must be present!"); // module_psk_demod.cpp:18-21
+    const std::string con = p.str("constellation");
+    if (con == "bpsk") c.constellation = B200_BPSK;
+    else if (con == "qpsk") c.constellation = B200_QPSK;
+    else if (con == "oqpsk") c.constellation = B200_OQPSK;
+    else if (con == "8psk") c.constellation = B200_8PSK;
+    else throw ModuleError("unknown constellation " + con);
+    is_bpsk = c.constellation == B200_BPSK;
+    if (!p.has("rrc_alpha"))
+        throw ModuleError("RRC Alpha parameter must be present!");
+    c.rrc_alpha = (float)p.num("rrc_alpha");
+    c.rrc_taps = (int)p.num("rrc_taps", 31);
+    if (!p.has("pll_bw"))
+        throw ModuleError("PLL BW parameter must be present!");
+    c.pll_bw = (float)p.num("pll_bw");
+    c.agc_rate = (float)p.num("agc_rate", 1e-2);
+    // module_psk_demod.h:36-39 / module_psk_demod.cpp:36-49
+    c.clock_gain_omega = (float)(pow(8.7e-3, 2) / 4.0);
+    c.clock_mu = 0.5f;
+    c.clock_gain_mu = 8.7e-3f;
+    c.clock_omega_limit = 0.005f;
+    if (p.has("clock_alpha")) {
+        float a = (float)p.num("clock_alpha");
+        c.clock_gain_omega = (float)(pow(a, 2) / 4.0);
+        c.clock_gain_mu = a;
+    }
+    c.clock_gain_omega = (float)p.num("clock_gain_omega", c.clock_gain_omega);
+    c.clock_mu = (float)p.num("clock_mu", c.clock_mu);
+    c.clock_gain_mu = (float)p.num("clock_gain_mu", c.clock_gain_mu);
+    c.clock_omega_limit = (float)p.num("clock_omega_relative_limit", c.clock_omega_limit);
+    c.costas_max_offset = 1.0f;
+    if (p.has("costas_max_offset")) // Hz -> rad/sample (module_psk_demod.cpp:116-118)
+        c.costas_max_offset = (float)(2.0 * M_PI * (p.num("costas_max_offset") / c.samplerate));
+    const std::string fmt = p.str("baseband_format", "cf32"); // common/dsp/io/baseband_type.cpp:103-127
+    if (fmt == "cf32" || fmt == "f32") c.format = B200_CF32;
+    else if (fmt == "cs16" || fmt == "s16") c.format = B200_CS16;
+    else if (fmt == "cs8" || fmt == "s8") c.format = B200_CS8;
+    else throw ModuleError("baseband_format " + fmt + " is not supported by the B200 path (cf32/cs16/cs8 only)");
+    reject(p, "dc_block", "CorrectIQ block");
+    reject(p, "freq_shift", "FreqShift block");
+    reject(p, "iq_swap", "IQ swap");
+    reject(p, "post_costas_dc", "CorrectIQ block");
+    reject(p, "has_carrier", "PLL carrier tracking");
+    reject(p, "enable_doppler", "Doppler correction");
+    reject(p, "custom_samplerate", "resampler");
+    reject(p, "dump_intermediate", "intermediate dump");
+    c.device = (int)p.num("b200_device", 0);
+    return c;
+}
+
+b200_fec_cfg fec_cfg_from_params(const std::string &id, const Params &p)
+{
+    b200_fec_cfg c{};
+    c.outsync_after = (int)p.num("viterbi_outsync_after");
+    c.ber_thresold = (float)p.num("viterbi_ber_thresold");
+    c.device = (int)p.num("b200_device", 0);
+    c.asm_sync = 0x1ACFFC1D;
+    if (id == "metop_ahrpt_decoder") {
+        c.kind = B200_FEC_METOP;
+        c.constellation = B200_QPSK;
+        c.cadu_size = 8192;
+        return c;
+    }
+    if (id != "ccsds_conv_concat_decoder")
+        throw ModuleError("unknown decoder module " + id);
+    c.kind = B200_FEC_CCSDS;
+    const std::string con = p.str("constellation"); // module_ccsds_conv_concat_decoder.cpp:38-56
+    if (con == "bpsk") c.constellation = B200_BPSK;
+    else if (con == "bpsk_90") c.constellation = B200_BPSK_90;
+    else if (con == "qpsk") c.constellation = B200_QPSK;
+    else if (con == "oqpsk") c.constellation = B200_OQPSK;
+    else throw ModuleError("CCSDS Concatenated 1/2 Decoder : invalid constellation type!");
+    c.cadu_size = (int)p.num("cadu_size");
+    c.nrzm = p.flag("nrzm", false);
+    c.derandomize = p.flag("derandomize", true);
+    c.derand_after_rs = p.flag("derand_after_rs", false);
+    c.derand_start = (int)p.num("derand_start", 4);
+    if (p.str("conv_rate", "1/2") != "1/2")
+        throw ModuleError("conv_rate " + p.str("conv_rate") + " (Viterbi_Depunc) is not supported by the B200 path");
+    c.rs_i = (int)p.num("rs_i");
+    c.rs_fill_bytes = (int)p.num("rs_fill_bytes", -1);
+    c.rs_dualbasis = p.flag("rs_dualbasis", true);
+    const std::string rst = p.str("rs_type", "none");
+    if (c.rs_i != 0) {
+        if (rst == "rs223") c.rs_type = 0;
+        else if (rst == "rs239") c.rs_type = 1;
+        else throw ModuleError("CCSDS Concatenated 1/2 Decoder : invalid Reed-Solomon type!");
+    }
+    c.rs_usecheck = p.flag("rs_usecheck", false);
+    c.iq_invert = p.flag("iq_invert", false);
+    if (c.iq_invert)
+        throw ModuleError("iq_invert is not supported by the B200 path");
+    if (p.has("asm"))
+        c.asm_sync = (unsigned)strtoul(p.str("asm").c_str(), nullptr, 16);
+    return c;
+}
+
+static uint64_t file_size(const std::string &path)
+{
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f)
+        return 0;
+    fseek(f, 0, SEEK_END);
+    uint64_t n = (uint64_t)ftell(f);
+    fclose(f);
+    return n;
+}
+static void check(int rc, const char *what)
+{
+    if (rc != B200_OK)
+        throw std::runtime_error(std::string(what) + ": " + b200_last_error());
+}
+
+// ------------------------------------------------------------------------------------------------ PskDemodStage
+PskDemodStage::PskDemodStage(std::string in, std::string hint, Params p) : StageBase(std::move(in), std::move(hint), std::move(p))
+{
+    cfg = demod_cfg_from_params(params, is_bpsk);
+    batch_samples = (long)params.num("b200_batch_samples", (double)batch_samples);
+    cfg.max_batch = batch_samples;
+}
+PskDemodStage::~PskDemodStage() { b200_demod_destroy(h); }
+void PskDemodStage::init()
+{
+    h = b200_demod_create(&cfg);
+    if (!h)
+        throw ModuleError(b200_last_error());
+}
+void PskDemodStage::process()
+{
+    if (!h)
+        init();
+    const int bpsamp = cfg.format == B200_CF32 ? 8 : (cfg.format == B200_CS16 ? 4 : 2);
+    std::vector<uint8_t> raw((size_t)batch_samples * bpsamp);
+    std::vector<int8_t> soft((size_t)batch_samples * 2 + 4096);
+    FILE *fin = nullptr, *fout = nullptr;
+    if (in_type == DataType::FILE) {
+        fin = fopen(input_file.c_str(), "rb");
+        if (!fin)
+            throw std::runtime_error("cannot open " + input_file);
+        filesize = file_size(input_file);
+    }
+    if (out_type == DataType::FILE) {
+        output_file = output_hint + ".soft"; // module_psk_demod.cpp:147-151
+        fout = fopen(output_file.c_str(), "wb");
+    }
+    uint64_t done = 0;
+    size_t have = 0; // bytes buffered (a batch must hold whole samples and at least 64 of them)
+    bool eof = false;
+    while (!should_stop && !eof) {
+        size_t got;
+        if (fin)
+            got = fread(raw.data() + have, 1, raw.size() - have, fin);
+        else {
+            // DATA_STREAM input of raw baseband bytes (the reference feeds a dsp::stream<complex_t> here; a byte FIFO of the
+            // configured baseband_format is the C-ABI friendly equivalent)
+            int want = (int)std::min<size_t>(raw.size() - have, 1 << 20);
+            int r = input_fifo->read(raw.data() + have, want);
+            got = r < 0 ? 0 : (size_t)r;
+        }
+        if (got == 0)
+            eof = true;
+        have += got;
+        long ns = (long)(have / bpsamp);
+        if (ns < 64 || (!eof && have < raw.size() && fin == nullptr && ns < 65536))
+            continue;
+        check(b200_demod_push_iq(h, raw.data(), ns), "b200_demod_push_iq");
+        long n = 0;
+        check(b200_demod_pull_soft(h, soft.data(), (long)soft.size(), &n), "b200_demod_pull_soft");
+        if (fout)
+            fwrite(soft.data(), 1, (size_t)n, fout);
+        else if (output_fifo->write((uint8_t *)soft.data(), (int)n) < 0)
+            break;
+        size_t used = (size_t)ns * bpsamp;
+        memmove(raw.data(), raw.data() + used, have - used);
+        have -= used;
+        done += used;
+        progress = filesize ? (double)done / (double)filesize : 0.0;
+        b200_demod_stats st;
+        if (b200_demod_get_stats(h, &st) == B200_OK)
+            freq = st.costas_freq * cfg.samplerate / (2.0 * M_PI); // rad_to_hz, module_psk_demod.cpp:196
+    }
+    if (fin)
+        fclose(fin);
+    if (fout)
+        fclose(fout);
+}
+
+// ------------------------------------------------------------------------------------------------ FecStage
+FecStage::FecStage(const std::string &module_id, std::string in, std::string hint, Params p)
+    : StageBase(std::move(in), std::move(hint), std::move(p)), id(module_id)
+{
+    cfg = fec_cfg_from_params(id, params);
+    batch_soft = (long)params.num("b200_batch_soft", (double)batch_soft);
+    cfg.max_soft = batch_soft + (1 << 16);
+}
+FecStage::~FecStage() { b200_fec_destroy(h); }
+void FecStage::init()
+{
+    h = b200_fec_create(&cfg);
+    if (!h)
+        throw ModuleError(b200_last_error());
+}
+void FecStage::process()
+{
+    if (!h)
+        init();
+    std::vector<int8_t> soft((size_t)batch_soft);
+    std::vector<uint8_t> out((size_t)batch_soft / 4 + (1 << 20));
+    FILE *fin = nullptr, *fout = nullptr;
+    if (in_type == DataType::FILE) {
+        fin = fopen(input_file.c_str(), "rb");
+        if (!fin)
+            throw std::runtime_error("cannot open " + input_file);
+    }
+    if (out_type == DataType::FILE) {
+        const bool ccsds = params.flag("ccsds", true);
+        output_file = output_hint + (ccsds ? ".cadu" : ".frm"); // filestream_to_filestream.cpp:27-36, ccsds decoder :131
+        fout = fopen(output_file.c_str(), "wb");
+    }
+    const int chunk = b200_fec_chunk_size(h);
+    while (!should_stop) {
+        size_t got;
+        if (fin)
+            got = fread(soft.data(), 1, soft.size(), fin);
+        else {
+            // read whole decoder chunks as the reference does (read_data(soft_buffer, BUFFER_SIZE)), several at a time when available
+            int avail = input_fifo->readable();
+            int want = std::max(chunk, std::min<int>((int)soft.size() / chunk * chunk, avail / chunk * chunk));
+            int r = input_fifo->read((uint8_t *)soft.data(), want);
+            got = r < 0 ? 0 : (size_t)r;
+        }
+        if (got == 0)
+            break;
+        check(b200_fec_push_soft(h, soft.data(), (long)got), "b200_fec_push_soft");
+        long nb = 0;
+        check(b200_fec_pull_frames(h, out.data(), (long)out.size(), &nb), "b200_fec_pull_frames");
+        if (nb > 0) {
+            if (fout)
+                fwrite(out.data(), 1, (size_t)nb, fout);
+            else if (output_fifo->write(out.data(), (int)nb) < 0)
+                break;
+        }
+        b200_fec_stats st;
+        if (b200_fec_get_stats(h, &st) == B200_OK) {
+            viterbi_lock = st.viterbi_state;
+            viterbi_ber = st.viterbi_ber;
+            deframer_state = st.deframer_state;
+            frames_written = st.frames_out;
+        }
+    }
+    if (fin)
+        fclose(fin);
+    if (fout)
+        fclose(fout);
+}
+
+// ------------------------------------------------------------------------------------------------ FusedStage
+FusedStage::FusedStage(const std::string &decoder_id, std::string in, std::string hint, Params dp, Params fp)
+    : StageBase(std::move(in), std::move(hint), std::move(fp)), dec_id(decoder_id), dparams(std::move(dp))
+{
+    bool bpsk;
+    dcfg = demod_cfg_from_params(dparams, bpsk);
+    fcfg = fec_cfg_from_params(dec_id, params);
+    batch_samples = (long)dparams.num("b200_batch_samples", (double)batch_samples);
+    dcfg.max_batch = batch_samples;
+    fcfg.max_soft = batch_samples + (1 << 20);
+    fcfg.device = dcfg.device;
+}
+FusedStage::~FusedStage() { b200_chain_destroy(h); }
+void FusedStage::init()
+{
+    h = b200_chain_create(&dcfg, &fcfg);
+    if (!h)
+        throw ModuleError(b200_last_error());
+}
+void FusedStage::process()
+{
+    if (!h)
+        init();
+    const int bpsamp = dcfg.format == B200_CF32 ? 8 : (dcfg.format == B200_CS16 ? 4 : 2);
+    std::vector<uint8_t> raw((size_t)batch_samples * bpsamp), out((size_t)batch_samples / 4 + (1 << 20));
+    FILE *fin = fopen(input_file.c_str(), "rb");
+    if (!fin)
+        throw std::runtime_error("cannot open " + input_file);
+    const uint64_t fsz = file_size(input_file);
+    output_file = output_hint + ".cadu";
+    FILE *fout = fopen(output_file.c_str(), "wb");
+    uint64_t done = 0;
+    size_t have = 0;
+    while (!should_stop) {
+        size_t got = fread(raw.data() + have, 1, raw.size() - have, fin);
+        have += got;
+        long ns = (long)(have / bpsamp);
+        if (ns < 64)
+            break;
+        check(b200_chain_push_iq(h, raw.data(), ns), "b200_chain_push_iq");
+        long nb = 0;
+        check(b200_chain_pull_frames(h, out.data(), (long)out.size(), &nb), "b200_chain_pull_frames");
+        if (nb > 0)
+            fwrite(out.data(), 1, (size_t)nb, fout);
+        frames_written += nb / ((fcfg.kind == B200_FEC_METOP) ? 1024 : (fcfg.cadu_size + 7) / 8);
+        size_t used = (size_t)ns * bpsamp;
+        memmove(raw.data(), raw.data() + used, have - used);
+        have -= used;
+        done += used;
+        progress = fsz ? (double)done / (double)fsz : 0.0;
+        if (got == 0)
+            break;
+    }
+    fclose(fin);
+    fclose(fout);
+}
+
+// ------------------------------------------------------------------------------------------------ two-module wiring
+void run_two_stage(StageBase &m1, StageBase &m2)
+{
+    auto fifo = std::make_shared<ByteFifo>(1000000); // pipeline_run.cpp:74
+    m1.setOutputType(DataType::STREAM);
+    m2.setInputType(DataType::STREAM);
+    m1.output_fifo = fifo;
+    m2.input_fifo = fifo;
+    m2.input_active = true;
+    m1.init();
+    m2.init();
+    std::exception_ptr e1, e2;
+    std::thread t1([&] { try { m1.process(); } catch (...) { e1 = std::current_exception(); } fifo->stopReader(); });
+    std::thread t2([&] { try { m2.process(); } catch (...) { e2 = std::current_exception(); fifo->stopWriter(); } });
+    t1.join();
+    m2.input_active = false; // the reader drains what is left, then read() returns -1
+    t2.join();
+    if (e1)
+        std::rethrow_exception(e1);
+    if (e2)
+        std::rethrow_exception(e2);
+}
+
+} // namespace b200host
