@@ -21,7 +21,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-ALG_BYTES_PER_CHUNK = 16384 + 12288 // 8  # k_vit_main: int8 soft in + packed decoded bits out
+ALG_BYTES_PER_CHUNK = 16384 + 12288 // 8  # Viterbi of one chunk: int8 soft in + packed decoded bits out
 
 
 def peaks():
@@ -155,13 +155,15 @@ def main():
         ch.frames_device()
         return ch.timing()["push_events"]  # ms, CUDA events on the chain's own streams (torch events cannot see them)
 
-    out_host = np.zeros(max_soft // 8 + (1 << 20), np.uint8)
+    out_host = torch.empty(max_soft // 8 + (1 << 20), dtype=torch.uint8, pin_memory=True)  # the caller-owned CADU buffer
 
-    def step_host():
+    def step_host(prefetch_next=False):
         ch.reset()
+        if prefetch_next:  # double buffering: the H2D copy of the NEXT step's batch overlaps this step's kernels
+            ch.prefetch_ptr(host.data_ptr(), n)
         ch.push_ptr(host.data_ptr(), n)
-        fr = ch.frames(cap=out_host.size)
-        return fr
+        nb = ch.pull_into(out_host.data_ptr(), out_host.numel())  # D2H of this step's CADUs
+        return out_host[:nb].numpy().reshape(-1, 1024)
 
     # warm-up (also the full-size correctness gate: every CADU must be one of the transmitted frames, in order)
     for _ in range(max(args.warmup, 3)):
@@ -188,8 +190,9 @@ def main():
     barrier()
     # ---- e2e: host buffers, H2D + D2H inside
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        fr = step_host()
+    ch.prefetch_ptr(host.data_ptr(), n)  # the first batch's copy is inside the timed region
+    for i in range(args.steps):
+        fr = step_host(prefetch_next=(i + 1 < args.steps))
     torch.cuda.synchronize()
     wall_e2e = time.perf_counter() - t0
     barrier()
@@ -207,7 +210,7 @@ def main():
         hbm, which = peaks()
         value = n * args.steps * world / wall_dev / 1e6
         e2e = n * args.steps * world / wall_e2e / 1e6
-        vit_ms = tim["k_vit_main"]
+        vit_ms = tim["k_vit_acs"]
         achieved = tim["vit_chunks"] * ALG_BYTES_PER_CHUNK / (vit_ms * 1e-3) / 1e9 if vit_ms > 0 else 0.0
         fir_ms = tim["agc_fir"]
         line = {"metric": "baseband MS/s end-to-end IQ->CADU (METOP AHRPT)", "value": value, "unit": "MS/s", "n_gpus": world, "steps": args.steps,
@@ -219,7 +222,7 @@ def main():
                 "e2e": {"value": e2e, "unit": "MS/s", "h2d_bytes_per_step": n * 4 * world, "d2h_bytes_per_step": int(nfr) * 1024 * world},
                 "gpu_launches": int(launches1 - launches0), "host_wall_ms_per_step": wall_dev_host / args.steps * 1e3,
                 "stage_ms_last_step": {k: round(v, 4) for k, v in tim.items() if k != "vit_chunks"},
-                "roofline": {"kernel": "k_vit_main (warp-per-chunk ACS + chainback)", "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
+                "roofline": {"kernel": "k_vit_acs (warp-per-chunk add-compare-select, the longest kernel of the step)", "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
                              "frac": achieved / hbm, "traffic": None, "peak_source": which},
                 "roofline_fir_stage": {"kernels": "k_agc_compose + k_agc_scan + k_agc_fir", "bound": "hbm",
                                        "achieved": n * 12 / (fir_ms * 1e-3) / 1e9 if fir_ms > 0 else 0.0, "peak": hbm, "unit": "GB/s",

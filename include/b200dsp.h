@@ -144,6 +144,9 @@ b200_chain *b200_chain_create(const b200_demod_cfg *dcfg, const b200_fec_cfg *fc
 void b200_chain_destroy(b200_chain *c);
 int b200_chain_push_iq(b200_chain *c, const void *host_iq, long nsamples);
 int b200_chain_push_iq_device(b200_chain *c, const void *dev_iq, long nsamples);
+/* Double buffering for host streams: start the H2D copy of a FUTURE batch (pinned memory) on a copy stream; the later
+ * b200_chain_push_iq() with the same (pointer, nsamples) only waits for it. At most two batches may be pending. */
+int b200_chain_prefetch_iq(b200_chain *c, const void *host_iq, long nsamples);
 int b200_chain_pull_frames(b200_chain *c, uint8_t *host_out, long cap, long *nbytes_out);
 /* device-resident result access (no D2H): pointer to the frames produced since the last pull/reset */
 int b200_chain_frames_device(b200_chain *c, const uint8_t **dev_ptr, long *nbytes);

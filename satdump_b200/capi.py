@@ -24,7 +24,7 @@ SYMBOLS = [
     "b200_demod_pull_symbols", "b200_demod_debug_stage", "b200_demod_get_stats", "b200_demod_get_taps",
     "b200_fec_create", "b200_fec_destroy", "b200_fec_push_soft", "b200_fec_push_soft_device", "b200_fec_pull_frames",
     "b200_fec_debug_bits", "b200_fec_get_stats", "b200_fec_cadu_bytes", "b200_fec_chunk_size",
-    "b200_chain_create", "b200_chain_destroy", "b200_chain_push_iq", "b200_chain_push_iq_device", "b200_chain_pull_frames",
+    "b200_chain_create", "b200_chain_destroy", "b200_chain_push_iq", "b200_chain_push_iq_device", "b200_chain_prefetch_iq", "b200_chain_pull_frames",
     "b200_chain_frames_device", "b200_chain_get_stats", "b200_chain_last_timing", "b200_chain_reset",
 ]
 
@@ -99,6 +99,7 @@ def lib():
         L.b200_chain_destroy.argtypes = [vp]
         L.b200_chain_push_iq.argtypes = [vp, vp, cl]
         L.b200_chain_push_iq_device.argtypes = [vp, vp, cl]
+        L.b200_chain_prefetch_iq.argtypes = [vp, vp, cl]
         L.b200_chain_pull_frames.argtypes = [vp, vp, cl, C.POINTER(cl)]
         L.b200_chain_frames_device.argtypes = [vp, C.POINTER(vp), C.POINTER(cl)]
         L.b200_chain_get_stats.argtypes = [vp, C.POINTER(DemodStats), C.POINTER(FecStats)]
@@ -288,12 +289,22 @@ class Chain:
         self._n = n
         return self
 
+    def prefetch_ptr(self, host_ptr, n):
+        _chk(lib().b200_chain_prefetch_iq(self.h, host_ptr, n))
+        return self
+
     def frames(self, cap=None):
         cap = cap or int(self._n) + 65536
         out = np.zeros(cap, np.uint8)
         n = C.c_long(0)
         _chk(lib().b200_chain_pull_frames(self.h, out.ctypes.data, cap, C.byref(n)))
         return out[:n.value].reshape(-1, self.cadu_bytes).copy()
+
+    def pull_into(self, host_ptr, cap):
+        """CADUs since the last pull straight into caller memory (no numpy temporaries); returns the byte count."""
+        n = C.c_long(0)
+        _chk(lib().b200_chain_pull_frames(self.h, host_ptr, cap, C.byref(n)))
+        return n.value
 
     def frames_device(self):
         p = C.c_void_p(0)
@@ -309,7 +320,7 @@ class Chain:
     def timing(self):
         ms = np.zeros(9, np.float32)
         _chk(lib().b200_chain_last_timing(self.h, ms.ctypes.data, 9))
-        return dict(zip(["stages_sum", "agc_fir", "costas", "mm", "viterbi", "deframe_rs", "k_vit_main", "vit_chunks", "push_events"], ms.tolist()))
+        return dict(zip(["stages_sum", "agc_fir", "costas", "mm", "viterbi", "deframe_rs", "k_vit_acs", "vit_chunks", "push_events"], ms.tolist()))
 
     def reset(self):
         _chk(lib().b200_chain_reset(self.h))

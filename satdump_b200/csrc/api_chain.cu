@@ -100,6 +100,13 @@ int b200_chain_frames_device(b200_chain *h, const uint8_t **dev_ptr, long *nbyte
         h->c.f->out_frames = 0;
     });
 }
+int b200_chain_prefetch_iq(b200_chain *h, const void *host_iq, long n)
+{
+    return guarded([&] {
+        B200_REQUIRE(h && host_iq, B200_EINVAL, "NULL argument");
+        h->c.d->prefetch_host(host_iq, n);
+    });
+}
 int b200_chain_reset(b200_chain *h)
 {
     return guarded([&] {

@@ -89,9 +89,9 @@ void design_mm_bank(std::vector<float> &out)
 }
 
 static int round_up16(double v) { return ((int)std::ceil(v / 16.0)) * 16; }
-constexpr int REPAIR_ROUNDS = 3;   // a run of r consecutive unconverged junctions needs r rounds
+constexpr int REPAIR_ROUNDS = 8;   // a run of r consecutive unconverged junctions needs r rounds; idle rounds cost two empty launches
 constexpr float MM_TOL = 0.05f;    // samples: junction disagreement of the sampling instant that triggers a repair
-__global__ void k_count_repairs(const int *count, int *total) { *total += min(*count, 1024); }
+
 
 Demod::Demod(const b200_demod_cfg &c) : cfg(c)
 {
@@ -129,6 +129,9 @@ Demod::Demod(const b200_demod_cfg &c) : cfg(c)
         B200_CUDA(cudaEventCreate(&e));
     const int fmt_bytes = c.format == B200_CF32 ? 8 : (c.format == B200_CS16 ? 4 : 2);
     raw.alloc((size_t)max_batch * fmt_bytes + 64);
+    B200_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+    for (auto &p : pf)
+        B200_CUDA(cudaEventCreateWithFlags(&p.done, cudaEventDisableTiming));
     bufA.alloc(max_batch + 64);
     bufB.alloc(max_batch + 64);
     if (c.keep_stages) {
@@ -166,6 +169,7 @@ Demod::Demod(const b200_demod_cfg &c) : cfg(c)
     bufA.zero(stream);
     bufB.zero(stream);
     B200_CUDA(cudaFuncSetAttribute(k_mm, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM_BYTES));
+    B200_CUDA(cudaFuncSetAttribute(k_costas, cudaFuncAttributeMaxDynamicSharedMemorySize, COSTAS_SMEM_BYTES));
     B200_CUDA(cudaStreamSynchronize(stream));
 }
 
@@ -176,6 +180,13 @@ Demod::~Demod()
         cudaStreamSynchronize(stream);
     for (auto &e : ev)
         cudaEventDestroy(e);
+    if (copy_stream) {
+        cudaStreamSynchronize(copy_stream);
+        cudaStreamDestroy(copy_stream);
+    }
+    for (auto &p : pf)
+        if (p.done)
+            cudaEventDestroy(p.done);
     if (h_total)
         cudaFreeHost(h_total);
     if (h_state)
@@ -269,13 +280,14 @@ long Demod::process(const void *d_raw, long n, int8_t *soft_dst)
         }
         P.fmin = -cfg.costas_max_offset;
         P.fmax = cfg.costas_max_offset;
-        k_costas<<<nblk, SEG_THREADS, 0, stream>>>(fir_out, n, L, Wc, nseg, P, S->costas[cur], cos_out, crec.p, nullptr, nullptr);
-        k_costas_fix<<<1, 1024, 0, stream>>>(crec.p, nseg, order, 2e-3f, 1e-4f, quad.p, S->costas[nxt], &S->costas_unconv, repair.p + 1, repair.p);
-        for (int round = 0; round < REPAIR_ROUNDS; round++) { // no-ops (a few microseconds) when every junction had converged
-            k_count_repairs<<<1, 1, 0, stream>>>(repair.p, &S->repairs);
-            k_costas<<<8, SEG_THREADS, 0, stream>>>(fir_out, n, L, Wc, nseg, P, S->costas[cur], cos_out, crec.p, repair.p + 1, repair.p);
-            k_costas_fix<<<1, 1024, 0, stream>>>(crec.p, nseg, order, 2e-3f, 1e-4f, quad.p, S->costas[nxt], &S->costas_unconv, repair.p + 1, repair.p);
-            launches += 3;
+        k_costas<<<nblk, SEG_THREADS, COSTAS_SMEM_BYTES, stream>>>(fir_out, n, L, Wc, nseg, P, S->costas[cur], cos_out, crec.p, nullptr, nullptr);
+        k_costas_fix<<<1, 1024, 0, stream>>>(crec.p, nseg, order, 2e-3f, 1e-4f, quad.p, S->costas[nxt], &S->costas_unconv, repair.p + 1, repair.p, 0,
+                                             &S->repairs);
+        for (int round = 1; round <= REPAIR_ROUNDS; round++) { // both kernels return at once when no junction is flagged
+            k_costas<<<8, SEG_THREADS, COSTAS_SMEM_BYTES, stream>>>(fir_out, n, L, Wc, nseg, P, S->costas[cur], cos_out, crec.p, repair.p + 1, repair.p);
+            k_costas_fix<<<1, 1024, 0, stream>>>(crec.p, nseg, order, 2e-3f, 1e-4f, quad.p, S->costas[nxt], &S->costas_unconv, repair.p + 1, repair.p,
+                                                 round, &S->repairs);
+            launches += 2;
         }
         mmin = bufA.p; // FIR output is dead now: reuse its buffer (in place compatible: same index mapping)
         k_rotate<<<2048, 256, 0, stream>>>(cos_out, n, L, order, cfg.constellation == B200_OQPSK, quad.p, S->mm_hist[cur], S->mm_hist[nxt], mmin);
@@ -294,12 +306,11 @@ long Demod::process(const void *d_raw, long n, int8_t *soft_dst)
     const int cap = slot_cap_for(L);
     B200_REQUIRE((size_t)nseg * cap <= slots.n, B200_ENOMEM, "internal: symbol slot storage too small");
     k_mm<<<nblk, SEG_THREADS, MM_SMEM_BYTES, stream>>>(mmin, n, L, Wm, nseg, MP, &S->mm[cur], &S->mm[nxt], d_bank.p, slots.p, cap, mrec.p, nullptr, nullptr);
-    k_mm_scan<<<1, 1024, 0, stream>>>(mrec.p, nseg, MM_TOL, offs.p, &S->mm_unconv, cap, &S->flags, repair.p + 1, repair.p);
-    for (int round = 0; round < REPAIR_ROUNDS; round++) {
-        k_count_repairs<<<1, 1, 0, stream>>>(repair.p, &S->repairs);
+    k_mm_scan<<<1, 1024, 0, stream>>>(mrec.p, nseg, MM_TOL, offs.p, &S->mm_unconv, cap, &S->flags, repair.p + 1, repair.p, 0, &S->repairs);
+    for (int round = 1; round <= REPAIR_ROUNDS; round++) {
         k_mm<<<8, SEG_THREADS, MM_SMEM_BYTES, stream>>>(mmin, n, L, Wm, nseg, MP, &S->mm[cur], &S->mm[nxt], d_bank.p, slots.p, cap, mrec.p, repair.p + 1, repair.p);
-        k_mm_scan<<<1, 1024, 0, stream>>>(mrec.p, nseg, MM_TOL, offs.p, &S->mm_unconv, cap, &S->flags, repair.p + 1, repair.p);
-        launches += 3;
+        k_mm_scan<<<1, 1024, 0, stream>>>(mrec.p, nseg, MM_TOL, offs.p, &S->mm_unconv, cap, &S->flags, repair.p + 1, repair.p, round, &S->repairs);
+        launches += 2;
     }
     int8_t *sdst = soft_dst ? soft_dst : soft.p;
     k_mm_compact<<<std::min(nseg, 148 * 8), 256, 0, stream>>>(slots.p, cap, mrec.p, offs.p, nseg, bps == 1, sym_out.p, sdst);
@@ -324,13 +335,50 @@ long Demod::process(const void *d_raw, long n, int8_t *soft_dst)
     return last_syms;
 }
 
+void Demod::prefetch_host(const void *h_raw, long n)
+{
+    B200_REQUIRE(n <= max_batch && n >= 64, B200_ESTATE, "prefetch of %ld samples outside [64, max_batch %ld]", n, max_batch);
+    DeviceGuard g(cfg.device);
+    const int fmt_bytes = cfg.format == B200_CF32 ? 8 : (cfg.format == B200_CS16 ? 4 : 2);
+    if (!raw2.p)
+        raw2.alloc((size_t)max_batch * fmt_bytes + 64);
+    Prefetch *slot = !pf[0].valid ? &pf[0] : (!pf[1].valid ? &pf[1] : nullptr);
+    B200_REQUIRE(slot != nullptr, B200_ESTATE, "two prefetched batches are already pending: push one first");
+    slot->buf = pf_next_buf;
+    pf_next_buf ^= 1;
+    B200_CUDA(cudaMemcpyAsync(slot->buf ? raw2.p : raw.p, h_raw, (size_t)n * fmt_bytes, cudaMemcpyHostToDevice, copy_stream));
+    B200_CUDA(cudaEventRecord(slot->done, copy_stream));
+    slot->ptr = h_raw;
+    slot->n = n;
+    slot->valid = true;
+    slot->seq = pf_seq++;
+}
+
 long Demod::push_host(const void *h_raw, long n, int8_t *soft_dst)
 {
     B200_REQUIRE(n <= max_batch, B200_ESTATE, "batch of %ld samples exceeds max_batch %ld", n, max_batch);
     DeviceGuard g(cfg.device);
+    // oldest matching prefetch, if any
+    Prefetch *hit = nullptr;
+    for (auto &p : pf)
+        if (p.valid && p.ptr == h_raw && p.n == n && (!hit || p.seq < hit->seq))
+            hit = &p;
+    if (hit) {
+        B200_CUDA(cudaStreamWaitEvent(stream, hit->done, 0));
+        hit->valid = false;
+        return process(hit->buf ? raw2.p : raw.p, n, soft_dst);
+    }
     const int fmt_bytes = cfg.format == B200_CF32 ? 8 : (cfg.format == B200_CS16 ? 4 : 2);
-    B200_CUDA(cudaMemcpyAsync(raw.p, h_raw, (size_t)n * fmt_bytes, cudaMemcpyHostToDevice, stream));
-    return process(raw.p, n, soft_dst);
+    // no pending prefetch may target the buffer we copy into
+    unsigned char *dst = (pf[0].valid && pf[0].buf == 0) || (pf[1].valid && pf[1].buf == 0) ? nullptr : raw.p;
+    if (!dst) {
+        if (!raw2.p)
+            raw2.alloc((size_t)max_batch * fmt_bytes + 64);
+        B200_REQUIRE(!((pf[0].valid && pf[0].buf == 1) || (pf[1].valid && pf[1].buf == 1)), B200_ESTATE, "both staging buffers hold prefetched batches");
+        dst = raw2.p;
+    }
+    B200_CUDA(cudaMemcpyAsync(dst, h_raw, (size_t)n * fmt_bytes, cudaMemcpyHostToDevice, stream));
+    return process(dst, n, soft_dst);
 }
 
 void Demod::stats(b200_demod_stats *o)

@@ -188,12 +188,14 @@ static void viterbi_segment(Fec &f, long c0, long nch, std::vector<OutChunk> &ou
     const float kber = f.geom.rate34 ? 5.0f : 2.5f;
     while (c < nch) {
         if (f.vit_state == 0) {
+            f.idle_st.enc_state = f.enc_state; // ONE chained CCEncoder serves the lock test and the SYNCED BER check (viterbi_3_4.cpp:126,157)
             k_vit_idle<<<1, 32, 0, f.stream>>>(f.softbuf.p, c, (int)(nch - c), f.geom, f.nswap, f.nphases, f.ph0, f.ph1, f.cfg.ber_thresold, f.idle_st,
                                               f.idle_dec.p, f.idle_out.p);
             f.launches++;
             B200_CUDA(cudaMemcpyAsync(f.h_idle, f.idle_out.p, sizeof(VitIdleOut), cudaMemcpyDeviceToHost, f.stream));
             B200_CUDA(cudaStreamSynchronize(f.stream));
             f.idle_st = f.h_idle->st;
+            f.enc_state = f.idle_st.enc_state;
             float bb = 10.f;
             for (int i = 0; i < 16; i++)
                 bb = std::min(bb, f.h_idle->bers[i]);
@@ -214,8 +216,10 @@ static void viterbi_segment(Fec &f, long c0, long nch, std::vector<OutChunk> &ou
             f.launches++;
         }
         B200_CUDA(cudaEventRecord(f.evm[0], f.stream));
-        k_vit_main<<<nb_main, 32 * wpb, 0, f.stream>>>(f.softbuf.p, c, n, f.geom, f.hyp, f.start_state.p, f.dec.p, f.chunk_bits.p, out_base, f.rec.p);
+        k_vit_acs<<<nb_main, 32 * wpb, 0, f.stream>>>(f.softbuf.p, c, n, f.geom, f.hyp, f.start_state.p, f.dec.p, f.rec.p);
         B200_CUDA(cudaEventRecord(f.evm[1], f.stream));
+        k_vit_tb<<<(n + 127) / 128, 128, 0, f.stream>>>(n, f.geom, f.dec.p, f.chunk_bits.p, out_base, f.rec.p);
+        f.launches++;
         k_vit_ber<<<nb_main, 32 * wpb, 0, f.stream>>>(f.softbuf.p, c, n, f.geom, f.hyp, f.chunk_bits.p, out_base, f.enc_state, f.rec.p);
         f.launches += 2;
         B200_CUDA(cudaMemcpyAsync(f.h_rec, f.rec.p, sizeof(VitRec) * n, cudaMemcpyDeviceToHost, f.stream));

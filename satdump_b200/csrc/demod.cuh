@@ -30,7 +30,8 @@ constexpr int FIR_TO = 2016;         // outputs per CTA
 constexpr int FIR_TL = 2048;         // samples loaded per CTA (32 halo + 2016)
 constexpr int FIR_THREADS = 256;
 constexpr int SEG_THREADS = 128;     // threads (= stream segments) per CTA in the loop kernels
-constexpr int MM_SMEM_BYTES = 64 * SEG_THREADS * 8 + 128 * 8 * 4;
+constexpr int MM_BANK_STRIDE = 9; // floats per arm row in smem: spreads the per-thread random arm reads over the banks
+constexpr int MM_SMEM_BYTES = 64 * SEG_THREADS * 8 + 128 * MM_BANK_STRIDE * 4;
 
 struct FirTaps { float h[32]; };
 
@@ -366,28 +367,68 @@ __device__ __forceinline__ float costas_error(float vr, float vi, int order)
 
 // in/out: N samples. Segment s owns samples [s*L, min((s+1)L, N)); thread warms up from max(0, s*L - W).
 // state_in = {phase, freq} carried from the previous batch (exact start of segment 0 and of any clipped warm-up).
+// Warp-cooperative staging shared by the two loop kernels. Every thread walks ITS OWN stretch of the stream, so a per-thread
+// load touches 32 different cache lines per instruction (measured: the L1 wavefront rate, not the math, bounded the first version).
+// Instead the warp moves whole 128-byte rows: in instruction i, lanes 8q..8q+7 copy the eight 16-byte chunks of the row of thread
+// 4i+q -> 4 lines per instruction. In shared memory chunk p of thread T sits at 16-byte slot p*32 + (T ^ (p & 7)): the XOR makes both
+// the copy-in (8 chunks of one thread) and the per-thread reads / transposed copy-out (one chunk of 8 consecutive threads) hit 8
+// distinct bank groups, i.e. conflict free.
+__device__ __forceinline__ int swz16(int p, int T) { return p * 32 + (T ^ (p & 7)); }
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
+{
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem_src));
+}
+
+// copies row `row` (16 samples from sample index 16*row; may be negative for the history pad) of every lane's thread into
+// dst (swizzled). `base` must be 16-byte aligned at sample 0 and readable from the first requested sample on.
+// pbase < 0: the destination is a per-thread RING addressed by the row number (chunk slot = 8*row mod (pmask+1)), which differs
+// between the threads of a warp; pbase >= 0: one fixed slot group for the whole warp.
+__device__ __forceinline__ void warp_load_rows(float4 *dst, int pbase, int pmask, const float2 *__restrict__ base, int row, bool row_valid, long limit,
+                                               int lane)
+{
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int T = 4 * i + (lane >> 3), c = lane & 7;
+        const int r = __shfl_sync(0xffffffffu, row, T);
+        const int ok = __shfl_sync(0xffffffffu, (int)row_valid, T);
+        const long n0 = (long)r * 16 + 2 * c;
+        const int pb = pbase < 0 ? (r << 3) + 64 : pbase; // the SOURCE thread's row decides the ring position
+        if (ok && n0 < limit)
+            cp_async16(&dst[swz16((pb + c) & pmask, T)], base + n0);
+    }
+}
+
 // Repair mode (repair_list != nullptr): thread i re-runs segment repair_list[i] with NO warm-up, starting from the recorded end
 // state of its predecessor, i.e. as the exact sequential continuation of that segment (used for junctions whose warm-up had
 // not converged; k_costas_fix re-checks afterwards).
+constexpr int COSTAS_SMEM_BYTES = (SEG_THREADS / 32) * (16 + 8) * 32 * 16; // per warp: 2 input rows + 1 output row of 8 chunks x 32 threads
 __global__ void __launch_bounds__(SEG_THREADS) k_costas(const float2 *__restrict__ in, long N, int L, int W, int nseg, CostasParams P,
                                                          const float *__restrict__ state_in, float2 *__restrict__ out, LoopRec *__restrict__ rec,
                                                          const int *__restrict__ repair_list, const int *__restrict__ repair_count)
 {
-    __shared__ float2 ring[32][SEG_THREADS];
-    const int t = threadIdx.x;
+    extern __shared__ __align__(16) unsigned char cs_smem[];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    float4 *ring = reinterpret_cast<float4 *>(cs_smem) + warp * (24 * 32); // [16 chunk slots][32] in, then [8][32] out
+    float4 *obuf = ring + 16 * 32;
     int s = blockIdx.x * SEG_THREADS + t;
+    bool active = true;
     if (repair_list) {
         if (s >= min(*repair_count, 1024))
-            return;
-        s = repair_list[s];
+            active = false;
+        else
+            s = repair_list[s];
     }
     if (s >= nseg)
-        return;
+        active = false;
+    if (!active)
+        s = 0;
     const long own0 = (long)s * L;
-    const long own1 = min(own0 + L, N);
+    const long own1 = active ? min(own0 + L, N) : own0;
     long start = own0 - W;
     float phase = 0.f, freq = state_in[1];
-    if (repair_list) {
+    if (repair_list && active) {
         start = own0;
         phase = rec[s - 1].ph_end;
         freq = rec[s - 1].fr_end;
@@ -395,73 +436,104 @@ __global__ void __launch_bounds__(SEG_THREADS) k_costas(const float2 *__restrict
         start = 0;
         phase = state_in[0];
     }
-    const long row0 = start >> 4, row1 = (own1 + 15) >> 4; // rows of 16 samples, [row0, row1)
-    auto issue = [&](long r) {
-        if (r < row1) {
-            const long b = r << 4;
-            const int slot0 = (int)(r & 1) << 4;
+    const int row0 = (int)(start >> 4), row1 = (int)((own1 + 15) >> 4); // rows of 16 samples, [row0, row1)
+    int nrows = active ? row1 - row0 : 0, maxrows = nrows;
 #pragma unroll
-            for (int j = 0; j < 16; j++)
-                if (b + j < N)
-                    cp_async8(&ring[slot0 + j][t], in + b + j);
-        }
-        cp_async_commit();
-    };
-    issue(row0);
+    for (int off = 16; off; off >>= 1)
+        maxrows = max(maxrows, __shfl_xor_sync(0xffffffffu, maxrows, off));
     LoopRec lr;
     lr.ph_start = phase;
     lr.fr_start = freq;
-    for (long r = row0; r < row1; r++) {
-        issue(r + 1);
+    float sn, cs;
+    sincosf(phase, &sn, &cs);
+    warp_load_rows(ring, 0, 15, in, row0, nrows > 0, N, lane);
+    cp_async_commit();
+    for (int it = 0; it < maxrows; it++) {
+        const int slot = (it & 1) * 8;
+        warp_load_rows(ring, ((it + 1) & 1) * 8, 15, in, row0 + it + 1, it + 1 < nrows, N, lane);
+        cp_async_commit();
         cp_async_wait<1>();
-        const long b = r << 4;
-        const int slot0 = (int)(r & 1) << 4;
-        float2 o[16];
+        __syncwarp();
+        const bool mine = it < nrows;
+        const long b = (long)(row0 + it) << 4;
 #pragma unroll
-        for (int j = 0; j < 16; j++) {
-            const long n = b + j;
-            float2 x = ring[slot0 + j][t];
-            if (n == own0) {
-                lr.ph_start = phase;
-                lr.fr_start = freq;
+        for (int p = 0; p < 8; p++) {
+            const float4 v = ring[swz16(slot + p, lane)];
+            float2 o[2];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int j = 2 * p + h;
+                const long n = b + j;
+                const float2 x = h ? make_float2(v.z, v.w) : make_float2(v.x, v.y);
+                if (mine && n == own0) {
+                    lr.ph_start = phase;
+                    lr.fr_start = freq;
+                }
+                if (mine && n >= start && n < own1) {
+                    // in * (cos(-phase) + j sin(-phase))  (costas_loop.cpp:26); (cs, sn) = cos/sin of the CURRENT float phase
+                    float vr = x.x * cs + x.y * sn;
+                    float vi = x.y * cs - x.x * sn;
+                    o[h] = make_float2(vr, vi);
+                    float err = costas_error(vr, vi, P.order);
+                    freq = freq + P.beta * err;
+                    const float prev = phase;
+                    phase = phase + (freq + P.alpha * err);
+                    const float d = phase - prev; // the increment the float phase really took (exact difference)
+                    bool refresh = (j & 7) == 7 || fabsf(d) > 0.05f;
+                    while (phase > 6.283185307179586) {
+                        phase = (float)((double)phase - 6.283185307179586);
+                        refresh = true;
+                    }
+                    while (phase < -6.283185307179586) {
+                        phase = (float)((double)phase + 6.283185307179586);
+                        refresh = true;
+                    }
+                    if (freq > P.fmax)
+                        freq = P.fmax;
+                    if (freq < P.fmin)
+                        freq = P.fmin;
+                    if (refresh)
+                        sincosf(phase, &sn, &cs); // exact re-anchor every 8 samples / on a wrap: bounds the rotation's rounding drift to < 1e-6
+                    else {
+                        // rotate (cs, sn) by the small increment d: Taylor sin/cos, |d| <= 0.05 -> truncation < 2e-10
+                        const float d2 = d * d;
+                        const float sd = d * fmaf(d2, fmaf(d2, 8.3333333e-3f, -0.16666667f), 1.0f);
+                        const float cd = fmaf(d2, fmaf(d2, 4.1666667e-2f, -0.5f), 1.0f);
+                        const float c2 = cs * cd - sn * sd;
+                        sn = sn * cd + cs * sd;
+                        cs = c2;
+                    }
+                } else
+                    o[h] = make_float2(0.f, 0.f);
             }
-            if (n >= start && n < own1) {
-                float sn, cs;
-                sincosf(phase, &sn, &cs);
-                // in * (cos(-phase) + j sin(-phase))  (costas_loop.cpp:26)
-                float vr = x.x * cs + x.y * sn;
-                float vi = x.y * cs - x.x * sn;
-                o[j] = make_float2(vr, vi);
-                float err = costas_error(vr, vi, P.order);
-                freq = freq + P.beta * err;
-                phase = phase + (freq + P.alpha * err);
-                while (phase > 6.283185307179586)
-                    phase = (float)((double)phase - 6.283185307179586);
-                while (phase < -6.283185307179586)
-                    phase = (float)((double)phase + 6.283185307179586);
-                if (freq > P.fmax)
-                    freq = P.fmax;
-                if (freq < P.fmin)
-                    freq = P.fmin;
-            } else
-                o[j] = make_float2(0.f, 0.f);
+            obuf[swz16(p, lane)] = make_float4(o[0].x, o[0].y, o[1].x, o[1].y);
         }
-        if (b >= own0 && b + 16 <= own1) {
-            float4 *p = reinterpret_cast<float4 *>(out + b);
+        __syncwarp();
+        // transposed copy-out: lanes 8q..8q+7 store the eight chunks of thread 4i+q's row (owned samples only)
+        const int wr0 = (int)min(own0, 0x7fffffffL), wr1 = (int)own1;
+        const int brow = mine ? (int)b : -1;
 #pragma unroll
-            for (int j = 0; j < 8; j++)
-                p[j] = make_float4(o[2 * j].x, o[2 * j].y, o[2 * j + 1].x, o[2 * j + 1].y);
-        } else if (b + 16 > own0 && b < own1) {
-#pragma unroll
-            for (int j = 0; j < 16; j++)
-                if (b + j >= own0 && b + j < own1)
-                    out[b + j] = o[j];
+        for (int i = 0; i < 8; i++) {
+            const int T = 4 * i + (lane >> 3), c = lane & 7;
+            const int bb = __shfl_sync(0xffffffffu, brow, T);
+            const int o0 = __shfl_sync(0xffffffffu, wr0, T), o1 = __shfl_sync(0xffffffffu, wr1, T);
+            const int n0 = bb + 2 * c;
+            if (bb >= 0 && n0 >= o0 && n0 < o1) {
+                const float4 v = obuf[swz16(c, T)];
+                if (n0 + 1 < o1)
+                    *reinterpret_cast<float4 *>(out + n0) = v;
+                else
+                    out[n0] = make_float2(v.x, v.y);
+            }
         }
+        __syncwarp();
     }
     cp_async_wait<0>();
-    lr.ph_end = phase;
-    lr.fr_end = freq;
-    rec[s] = lr;
+    if (active) {
+        lr.ph_end = phase;
+        lr.fr_end = freq;
+        rec[s] = lr;
+    }
 }
 
 // ---------------------------------------------------------------- K2b: resolve per-segment rotation (prefix sum mod order)
@@ -470,11 +542,19 @@ __global__ void __launch_bounds__(SEG_THREADS) k_costas(const float2 *__restrict
 // repair_list / repair_count: junctions (segment indices) that failed the check in THIS call (count is reset here).
 __global__ void __launch_bounds__(1024) k_costas_fix(const LoopRec *__restrict__ rec, int nseg, int order, float tol_phase, float tol_freq,
                                                     uint8_t *__restrict__ quad, float *__restrict__ state_out, int *__restrict__ unconv,
-                                                    int *__restrict__ repair_list, int *__restrict__ repair_count)
+                                                    int *__restrict__ repair_list, int *__restrict__ repair_count, int round, int *__restrict__ repairs_total)
 {
     __shared__ int wsum[32];
     __shared__ int run;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    if (round > 0) { // repair round: nothing was re-run since the last pass unless junctions had been flagged
+        const int pending = *repair_count;
+        if (pending == 0)
+            return;
+        __syncthreads(); // everyone has read the count before thread 0 resets it below
+        if (t == 0)
+            *repairs_total += min(pending, 1024);
+    }
     const float step = 6.283185307179586f / (float)order;
     if (t == 0) {
         run = 0;
@@ -621,27 +701,32 @@ __global__ void __launch_bounds__(SEG_THREADS) k_mm(const float2 *__restrict__ m
                                                      MMRec *__restrict__ rec, const int *__restrict__ repair_list, const int *__restrict__ repair_count)
 {
     extern __shared__ __align__(16) unsigned char mm_smem[];
-    float2(*ring)[SEG_THREADS] = reinterpret_cast<float2(*)[SEG_THREADS]>(mm_smem);      // [64][SEG_THREADS]
-    float *sbank = reinterpret_cast<float *>(mm_smem + 64 * SEG_THREADS * sizeof(float2)); // [128*8]
-    const int t = threadIdx.x;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    // per warp: ring of 64 samples = 32 chunk slots x 32 threads x 16 B (swizzled, see warp_load_rows); then the interpolator bank
+    float4 *ring = reinterpret_cast<float4 *>(mm_smem) + warp * (32 * 32);
+    float *sbank = reinterpret_cast<float *>(mm_smem + 64 * SEG_THREADS * sizeof(float2)); // [128][MM_BANK_STRIDE]
     for (int i = t; i < 128 * 8; i += SEG_THREADS)
-        sbank[i] = bank[i];
+        sbank[(i >> 3) * MM_BANK_STRIDE + (i & 7)] = bank[i];
     __syncthreads();
     int s = blockIdx.x * SEG_THREADS + t;
+    bool active = true;
     if (repair_list) { // exact sequential continuation of segment s-1 (see k_costas)
         if (s >= min(*repair_count, 1024))
-            return;
-        s = repair_list[s];
+            active = false;
+        else
+            s = repair_list[s];
     }
     if (s >= nseg)
-        return;
-    const long own0 = (long)s * L, own1 = min(own0 + L, N);
+        active = false;
+    if (!active)
+        s = 0;
+    const long own0 = (long)s * L, own1 = active ? min(own0 + L, N) : own0;
     // buffer coordinate u: window = input samples u-7 .. u
     long u;
     float mu, omega;
     float2 p0, p1, p2, c0, c1, c2;
     long ustart = own0 - W;
-    if (repair_list) {
+    if (repair_list && active) {
         const MMRec pr = rec[s - 1];
         mu = pr.mu_final; omega = pr.omega_final; p0 = pr.p0; p1 = pr.p1; p2 = pr.p2; c0 = pr.c0; c1 = pr.c1; c2 = pr.c2;
         u = pr.u_final;
@@ -654,79 +739,90 @@ __global__ void __launch_bounds__(SEG_THREADS) k_mm(const float2 *__restrict__ m
         p0 = p1 = p2 = c0 = c1 = c2 = make_float2(0.f, 0.f);
         u = ustart;
     }
-    // rows of 16 samples; sample n lives in ring[(n + 64) & 63]; rows cover n in [16r, 16r+16)
-    long r; // floor((u-7)/16): row holding the oldest sample of the first window
+    // rows of 16 samples; sample n lives in chunk slot ((n + 64) >> 1) & 31; the first window's oldest sample is u-7 (>= -8)
+    int r0;
     {
-        long a = u - 7;
-        r = (a >= 0) ? (a >> 4) : -((-a + 15) >> 4);
+        const long a = u - 7;
+        r0 = (int)((a >= 0) ? (a >> 4) : -((-a + 15) >> 4));
     }
-    const long rend = (own1 + 15) >> 4; // exclusive: samples < own1 <= N are ever needed
-    auto issue = [&](long row) {
-        if (row < rend) {
-            const long b = row << 4;
+    const int rend = (int)((own1 + 15) >> 4); // exclusive: samples < own1 <= N are ever needed
+    // iteration `it` makes row r0+it+1 the newest complete row; symbols with u < 16*(r0+it+2) can then be produced
+    int nit = active ? max(0, rend - r0) : 0, maxit = nit;
 #pragma unroll
-            for (int j = 0; j < 16; j++)
-                if (b + j < N)
-                    cp_async8(&ring[(int)((b + j + 64) & 63)][t], mmin + 16 + b + j);
-        }
-        cp_async_commit();
-    };
-    issue(r);
-    issue(r + 1);
+    for (int off = 16; off; off >>= 1)
+        maxit = max(maxit, __shfl_xor_sync(0xffffffffu, maxit, off));
+    const float2 *base = mmin + 16; // sample 0
+    auto load = [&](int row, bool ok) { warp_load_rows(ring, -1, 31, base, row, ok && row < rend, N, lane); cp_async_commit(); };
+    load(r0, active);
+    load(r0 + 1, active);
     int count = 0;
     MMRec mr;
 #pragma unroll
     for (int i = 0; i < 4; i++) { mr.head_u[i] = 0; mr.head_mu[i] = 0.f; }
     const long emit0 = (s == 0 || repair_list) ? min(own0, u) : own0 - MM_ZONE;
     float2 *my = slots + (long)s * cap;
-    // row loop: with rows <= rr+... loaded we may process every symbol whose newest sample u < 16*(rr+1)
-    for (long rr = r + 1; rr < rend + 1; rr++) {
-        issue(rr + 1);
+    const float2 *ringf = reinterpret_cast<const float2 *>(ring);
+    bool done = !active;
+    for (int it = 0; it < maxit; it++) {
+        const int rr = r0 + 1 + it;
+        load(rr + 1, active);
         cp_async_wait<1>(); // rows <= rr complete
-        const long lim = min((rr + 1) << 4, own1);
-        while (u < lim) {
-            if (u >= emit0 && count < 4) {
-                if (count == 0) { mr.head_u[0] = (int)u; mr.head_mu[0] = mu; }
-                else if (count == 1) { mr.head_u[1] = (int)u; mr.head_mu[1] = mu; }
-                else if (count == 2) { mr.head_u[2] = (int)u; mr.head_mu[2] = mu; }
-                else { mr.head_u[3] = (int)u; mr.head_mu[3] = mu; }
-            }
-            p2 = p1; p1 = p0; c2 = c1; c1 = c0;
-            int imu = (int)rintf(mu * 128.0f);
-            imu = max(0, min(127, imu));
-            const float *tp = &sbank[imu * 8];
-            float ar = 0.f, ai = 0.f;
+        __syncwarp();
+        if (!done) {
+            const long lim = min((long)(rr + 1) << 4, own1);
+            while (u < lim) {
+                if (u >= emit0 && count < 4) {
+                    if (count == 0) { mr.head_u[0] = (int)u; mr.head_mu[0] = mu; }
+                    else if (count == 1) { mr.head_u[1] = (int)u; mr.head_mu[1] = mu; }
+                    else if (count == 2) { mr.head_u[2] = (int)u; mr.head_mu[2] = mu; }
+                    else { mr.head_u[3] = (int)u; mr.head_mu[3] = mu; }
+                }
+                p2 = p1; p1 = p0; c2 = c1; c1 = c0;
+                int imu = (int)rintf(mu * 128.0f);
+                imu = max(0, min(127, imu));
+                const float *tp = &sbank[imu * MM_BANK_STRIDE];
+                const int n0 = (int)(u - 7) + 64; // >= 56
+                float ar = 0.f, ai = 0.f, br = 0.f, bi = 0.f; // two chains (taps 0-3 / 4-7) to halve the dependent-FMA depth
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                float2 x = ring[(int)((u - 7 + k + 64) & 63)][t];
-                ar = fmaf(x.x, tp[k], ar);
-                ai = fmaf(x.y, tp[k], ai);
+                for (int k = 0; k < 4; k++) {
+                    const int na = n0 + k, nb = n0 + k + 4;
+                    const float2 x = ringf[swz16((na >> 1) & 31, lane) * 2 + (na & 1)], y = ringf[swz16((nb >> 1) & 31, lane) * 2 + (nb & 1)];
+                    ar = fmaf(x.x, tp[k], ar);
+                    ai = fmaf(x.y, tp[k], ai);
+                    br = fmaf(y.x, tp[k + 4], br);
+                    bi = fmaf(y.y, tp[k + 4], bi);
+                }
+                ar += br;
+                ai += bi;
+                p0 = make_float2(ar, ai);
+                c0 = make_float2(ar > 0.0f ? 1.0f : 0.0f, ai > 0.0f ? 1.0f : 0.0f);
+                // Re[(p0-p2) conj(c1) - (c0-c2) conj(p1)]  (clock_recovery_mm.cpp:103)
+                float xr = (p0.x - p2.x) * c1.x + (p0.y - p2.y) * c1.y;
+                float yr = (c0.x - c2.x) * p1.x + (c0.y - c2.y) * p1.y;
+                float pe = xr - yr;
+                pe = fminf(1.0f, fmaxf(-1.0f, pe));
+                if (u >= emit0) {
+                    if (count < cap)
+                        my[count] = p0;
+                    count++;
+                }
+                omega = omega + P.omega_gain * pe;
+                float dev = omega - P.omega_mid;
+                dev = fminf(P.omega_limit, fmaxf(-P.omega_limit, dev));
+                omega = P.omega_mid + dev;
+                mu = (mu + omega) + P.mu_gain * pe;
+                float fl = floorf(mu);
+                u += (long)fl;
+                mu -= fl;
             }
-            p0 = make_float2(ar, ai);
-            c0 = make_float2(ar > 0.0f ? 1.0f : 0.0f, ai > 0.0f ? 1.0f : 0.0f);
-            // Re[(p0-p2) conj(c1) - (c0-c2) conj(p1)]  (clock_recovery_mm.cpp:103)
-            float xr = (p0.x - p2.x) * c1.x + (p0.y - p2.y) * c1.y;
-            float yr = (c0.x - c2.x) * p1.x + (c0.y - c2.y) * p1.y;
-            float pe = xr - yr;
-            pe = fminf(1.0f, fmaxf(-1.0f, pe));
-            if (u >= emit0) {
-                if (count < cap)
-                    my[count] = p0;
-                count++;
-            }
-            omega = omega + P.omega_gain * pe;
-            float dev = omega - P.omega_mid;
-            dev = fminf(P.omega_limit, fmaxf(-P.omega_limit, dev));
-            omega = P.omega_mid + dev;
-            mu = (mu + omega) + P.mu_gain * pe;
-            float fl = floorf(mu);
-            u += (long)fl;
-            mu -= fl;
+            if (u >= own1)
+                done = true;
         }
-        if (u >= own1)
-            break;
+        __syncwarp(); // the next iteration's copy overwrites the oldest row of the ring
     }
     cp_async_wait<0>();
+    if (!active)
+        return;
     mr.u_final = (int)u;
     mr.mu_final = mu;
     mr.omega_final = omega;
@@ -747,11 +843,19 @@ __global__ void __launch_bounds__(SEG_THREADS) k_mm(const float2 *__restrict__ m
 // ---------------------------------------------------------------- K3b: symbol offsets (exclusive scan) + junction check
 __global__ void __launch_bounds__(1024) k_mm_scan(MMRec *__restrict__ rec, int nseg, float tol_t, long *__restrict__ offs /*nseg+1*/,
                                                  int *__restrict__ unconv, int cap, int *__restrict__ flags, int *__restrict__ repair_list,
-                                                 int *__restrict__ repair_count)
+                                                 int *__restrict__ repair_count, int round, int *__restrict__ repairs_total)
 {
     __shared__ long wsum[32];
     __shared__ long run;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    if (round > 0) {
+        const int pending = *repair_count;
+        if (pending == 0)
+            return;
+        __syncthreads();
+        if (t == 0)
+            *repairs_total += min(pending, 1024);
+    }
     if (t == 0) {
         run = 0;
         *repair_count = 0;

@@ -32,6 +32,9 @@ class Demod
     // there (device pointer), otherwise into the object's own soft buffer. Returns the number of symbols produced.
     long process(const void *d_raw, long nsamples, int8_t *soft_dst);
     long push_host(const void *h_raw, long nsamples, int8_t *soft_dst);
+    // Starts the host->device copy of a FUTURE batch on a dedicated copy stream (double buffered); the matching push_host()
+    // then only waits for that copy. Lets the H2D of batch i+1 overlap the kernels of batch i. Pinned host memory required.
+    void prefetch_host(const void *h_raw, long nsamples);
     void stats(b200_demod_stats *out);
     void reset(); // back to the state of a freshly created demodulator (new stream)
 
@@ -45,7 +48,11 @@ class Demod
     long total_in = 0, total_syms = 0, launches = 0;
     int parity = 0;
     float t_agcfir = 0, t_costas = 0, t_mm = 0; // ms of the last batch
-    DevBuf<unsigned char> raw;
+    DevBuf<unsigned char> raw, raw2;
+    cudaStream_t copy_stream = nullptr;
+    struct Prefetch { const void *ptr = nullptr; long n = 0; int buf = 0; bool valid = false; cudaEvent_t done = nullptr; long seq = 0; } pf[2];
+    long pf_seq = 0;
+    int pf_next_buf = 0;
     DevBuf<float2> bufA, bufB, agc_dump, fir_dump, slots, sym_out;
     DevBuf<int8_t> soft;
     DevBuf<Affine> tile_map;

@@ -137,6 +137,58 @@ __device__ __forceinline__ int tb_step(int state, unsigned D0, unsigned D1, int 
     return (state >> 1) | (bit << 5);
 }
 
+// ---------------------------------------------------------------- packed ACS core (production path)
+// Same arithmetic as acs_step, two 16-bit fields per register: xl2 = X[i] | X[i]<<16, xh2 = X[i+32] | X[i+32]<<16.
+// The per-step branch metric comes from a 4-entry table word (one byte per (Branchtab0, Branchtab1) combination) that the lane
+// owning the step computed from the symbols and broadcast with one shuffle:
+//   Sl = (xl2 + (m | 63-m << 16)) & 0x00FF00FF = m0 | m2<<16        (uint8 wrap of volk_k7_r2_generic_fixed.h:108-111)
+//   Sh = (xh2 + (63-m | m << 16)) & 0x00FF00FF = m1 | m3<<16
+//   Y  = min.u16x2(Sl, Sh) = Y[2i] | Y[2i+1]<<16 ; decision = (field of Y == field of Sh)  <=>  m0 >= m1 (ties pick m1, :112-115)
+struct Acs2Lane { unsigned selA, selX; };
+__device__ __forceinline__ Acs2Lane acs2_lane_consts(int lane)
+{
+    const unsigned idx = (parity_u32((2u * lane) & 79u) ? 2u : 0u) + (parity_u32((2u * lane) & 109u) ? 1u : 0u);
+    Acs2Lane a;
+    a.selA = idx | (4u << 4) | (idx << 8) | (4u << 12); // byte idx of the table word into both 16-bit fields
+    a.selX = (lane & 1) ? 0x3232u : 0x1010u;            // after the shuffle: this lane's field of the source pair, duplicated
+    return a;
+}
+__device__ __forceinline__ unsigned metric_table(int sy)
+{
+    const int s0 = sy & 255, s1 = sy >> 8;
+    const unsigned m00 = (1 + s0 + s1) >> 3, m01 = (1 + s0 + (s1 ^ 255)) >> 3, m10 = (1 + (s0 ^ 255) + s1) >> 3,
+                   m11 = (1 + (s0 ^ 255) + (s1 ^ 255)) >> 3;
+    return m00 | (m01 << 8) | (m10 << 16) | (m11 << 24); // byte index = 2*[mask0 set] + [mask1 set]
+}
+__device__ __forceinline__ void acs2_step(unsigned w, const Acs2Lane L, int lane, unsigned &xl2, unsigned &xh2, unsigned &D0, unsigned &D1)
+{
+    const unsigned mm = __byte_perm(w, 0u, L.selA);
+    const unsigned Sl = (xl2 + (mm ^ 0x003F0000u)) & 0x00FF00FFu;
+    const unsigned Sh = (xh2 + (mm ^ 0x0000003Fu)) & 0x00FF00FFu;
+    unsigned Y = __vminu2(Sl, Sh);
+    const unsigned E = Y ^ Sh;
+    D0 = __ballot_sync(0xffffffffu, (E << 16) == 0u);
+    D1 = __ballot_sync(0xffffffffu, E < 0x10000u);
+    const unsigned mn = __reduce_min_sync(0xffffffffu, min(Y & 0xFFFFu, Y >> 16));
+    Y -= mn * 0x00010001u;
+    const unsigned a = __shfl_sync(0xffffffffu, Y, lane >> 1);
+    const unsigned b = __shfl_sync(0xffffffffu, Y, (lane >> 1) + 16);
+    xl2 = __byte_perm(a, 0u, L.selX);
+    xh2 = __byte_perm(b, 0u, L.selX);
+}
+__device__ __forceinline__ void acs2_init(int ss, int lane, unsigned &xl2, unsigned &xh2)
+{
+    // init_viterbi (63 everywhere, 0 at the start state) / init_viterbi_unbiased (31): cc_decoder.cpp:159-190
+    const unsigned l = ss < 0 ? 31u : (lane == ss ? 0u : 63u), h = ss < 0 ? 31u : (lane + 32 == ss ? 0u : 63u);
+    xl2 = l * 0x00010001u;
+    xh2 = h * 0x00010001u;
+}
+__device__ __forceinline__ int acs2_endstate(unsigned xl2, unsigned xh2, int lane)
+{
+    const unsigned k0 = ((xl2 & 0xFFFFu) << 6) | lane, k1 = ((xh2 & 0xFFFFu) << 6) | (lane + 32);
+    return (int)(__reduce_min_sync(0xffffffffu, min(k0, k1)) & 63);
+}
+
 // ---------------------------------------------------------------- start-state speculation
 // For chunk index q (q = 1 .. n-1 of this launch's range): predict the decoder state at the end of chunk q-1's F bits
 // by running the ACS over its last `spec` real steps + the 6 tail steps from all-equal metrics, then walking back 6.
@@ -146,86 +198,113 @@ __global__ void __launch_bounds__(128) k_vit_spec(const int8_t *__restrict__ sof
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (w >= nchunks - 1) return;
     const int8_t *c = soft + (chunk0 + w) * (long)g.chunk; // chunk w predicts the start of chunk w+1
-    const AcsLane L = acs_lane_consts(lane);
-    int xl = 0, xh = 0;
-    unsigned D0 = 0, D1 = 0;
-    unsigned d0h[6], d1h[6];
-    for (int t = g.F - spec; t < g.F; t++) {
-        const int sy = vit_symbols(c, t, g, h, g.chunk, 128);
-        acs_step(sy, L, lane, xl, xh, D0, D1);
+    const Acs2Lane L = acs2_lane_consts(lane);
+    unsigned xl2 = 0, xh2 = 0, D0 = 0, D1 = 0;
+    for (int t0 = g.F - spec; t0 < g.F; t0 += 32) { // spec is a multiple of 32
+        const unsigned mine = metric_table(vit_symbols(c, t0 + lane, g, h, g.chunk, 128));
+#pragma unroll 8
+        for (int j = 0; j < 32; j++)
+            acs2_step(__shfl_sync(0xffffffffu, mine, j), L, lane, xl2, xh2, D0, D1);
     }
+    unsigned d0h[6], d1h[6];
+    const unsigned wt = metric_table(128 | (128 << 8)); // the six flush steps read erasures (d_veclen = frame + k - 1)
 #pragma unroll
-    for (int k = 0; k < 6; k++) { // the six flush steps read erasures (cc_decoder.cpp d_veclen = frame + k - 1)
-        acs_step(128 | (128 << 8), L, lane, xl, xh, D0, D1);
+    for (int k = 0; k < 6; k++) {
+        acs2_step(wt, L, lane, xl2, xh2, D0, D1);
         d0h[k] = D0;
         d1h[k] = D1;
     }
-    int st = acs_endstate(xl, xh, lane), bit;
+    int st = acs2_endstate(xl2, xh2, lane), bit;
 #pragma unroll
     for (int k = 5; k >= 0; k--)
         st = tb_step(st, d0h[k], d1h[k], bit);
     if (lane == 0) start_state[w + 1] = st;
 }
 
-// ---------------------------------------------------------------- main decode: ACS + chainback + BER
+// ---------------------------------------------------------------- main decode, part 1: ACS (one warp per chunk)
 #endif // B200_DEFINE_KERNELS
-struct VitRec { int start_used, next_start, ber_errors, ber_total, enc_tail, pad0, pad1, pad2; };
+struct VitRec { int start_used, next_start, ber_errors, ber_total, enc_tail, end_state, pad1, pad2; };
+#ifdef B200_DEFINE_KERNELS
 
 // start_state[q]: >= 0 biased start (63 everywhere, 0 at that state), -1: unbiased all-31 (first call ever).
-// enc_state_in: the BER encoder's 6-bit register before the first chunk of this launch; chunk q>0 uses the bits
-// [TEST-6, TEST) of chunk q-1's output, like the chained CCEncoder (cc_encoder.cpp:92-104 via viterbi_3_4.cpp:157).
-#ifdef B200_DEFINE_KERNELS
-__global__ void __launch_bounds__(128) k_vit_main(const int8_t *__restrict__ soft, long chunk0, int nchunks, VitGeom g, VitHyp h,
-                                                   const int *__restrict__ start_state, uint2 *__restrict__ dec, uint32_t *__restrict__ bits,
-                                                   long out_chunk0, VitRec *__restrict__ rec)
+// Writes the survivor decisions (two ballot words per trellis step) and the first-minimum end state.
+__global__ void __launch_bounds__(128) k_vit_acs(const int8_t *__restrict__ soft, long chunk0, int nchunks, VitGeom g, VitHyp h,
+                                                  const int *__restrict__ start_state, uint2 *__restrict__ dec, VitRec *__restrict__ rec)
 {
     const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (q >= nchunks) return;
     const int8_t *c = soft + (chunk0 + q) * (long)g.chunk;
     uint2 *d = dec + (long)q * g.dec_stride;
-    uint32_t *ob = bits + (out_chunk0 + q) * (long)g.bit_words;
-    const AcsLane L = acs_lane_consts(lane);
+    const Acs2Lane L = acs2_lane_consts(lane);
     const int ss = start_state[q];
-    int xl, xh;
-    if (ss < 0) xl = xh = 31;
-    else { xl = (lane == ss) ? 0 : 63; xh = (lane + 32 == ss) ? 0 : 63; }
+    unsigned xl2, xh2, D0, D1;
+    acs2_init(ss, lane, xl2, xh2);
     const int steps = g.F + 6;
-    unsigned D0, D1;
-    // symbols are fetched 32 steps at a time (lane j computes step t0+j) and broadcast with a shuffle
     for (int t0 = 0; t0 < steps; t0 += 32) {
+        // lane j prepares step t0+j (symbol fetch incl. rotate / soft->u8 / depuncture, then the 4-entry metric table)
         const int tm = t0 + lane;
-        const int mine = tm < steps ? vit_symbols(c, tm, g, h, g.chunk, 128) : 0;
-        unsigned keep0 = 0, keep1 = 0;
-        const int nn = min(32, steps - t0);
-        for (int j = 0; j < nn; j++) {
-            const int sy = __shfl_sync(0xffffffffu, mine, j);
-            acs_step(sy, L, lane, xl, xh, D0, D1);
-            if (lane == j) { keep0 = D0; keep1 = D1; }
+        const unsigned mine = tm < steps ? metric_table(vit_symbols(c, tm, g, h, g.chunk, 128)) : 0u;
+        if (t0 + 32 <= steps) {
+#pragma unroll 8
+            for (int j = 0; j < 32; j++) {
+                acs2_step(__shfl_sync(0xffffffffu, mine, j), L, lane, xl2, xh2, D0, D1);
+                if (lane == 0) d[t0 + j] = make_uint2(D0, D1);
+            }
+        } else {
+            for (int j = 0; j < steps - t0; j++) {
+                acs2_step(__shfl_sync(0xffffffffu, mine, j), L, lane, xl2, xh2, D0, D1);
+                if (lane == 0) d[t0 + j] = make_uint2(D0, D1);
+            }
         }
-        if (lane < nn) d[t0 + lane] = make_uint2(keep0, keep1);
     }
-    __syncwarp();
-    // chainback over rows F+5 .. 6 (cc_decoder.cpp:228-276): output bit i comes from row i+6; the state after the first
-    // six steps is the next call's start state. Word wv holds bits 32wv .. 32wv+31, MSB first.
-    int st = acs_endstate(xl, xh, lane), bit, next_start = 0, walked = 0;
-    for (int wv = (g.F - 1) >> 5; wv >= 0; wv--) {
-        const int i0 = wv << 5, nb = min(32, g.F - i0);
-        uint2 r = lane < nb ? d[6 + i0 + lane] : make_uint2(0, 0);
-        unsigned word = 0;
-        for (int j = nb - 1; j >= 0; j--) {
-            const unsigned a = __shfl_sync(0xffffffffu, r.x, j), b = __shfl_sync(0xffffffffu, r.y, j);
-            st = tb_step(st, a, b, bit);
-            word |= (unsigned)bit << (31 - j);
-            if (++walked == 6) next_start = st;
-        }
-        if (lane == 0) ob[wv] = word;
-    }
+    const int st = acs2_endstate(xl2, xh2, lane);
     if (lane == 0) {
         VitRec r = rec[q];
         r.start_used = ss;
-        r.next_start = next_start;
+        r.end_state = st;
         rec[q] = r;
     }
+}
+
+// ---------------------------------------------------------------- main decode, part 2: chainback (one THREAD per chunk)
+// Rows F+5 .. 6 (cc_decoder.cpp:228-276): output bit i comes from row i+6; the state after the first six steps is the next
+// call's start state. The walk is inherently serial per chunk and every lane of a warp would do the same work, so it runs
+// thread-per-chunk: 6 ALU instructions + one 8-byte load per row instead of a warp's worth.
+__global__ void __launch_bounds__(128) k_vit_tb(int nchunks, VitGeom g, const uint2 *__restrict__ dec, uint32_t *__restrict__ bits, long out_chunk0,
+                                                 VitRec *__restrict__ rec)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nchunks) return;
+    const uint2 *d = dec + (long)q * g.dec_stride;
+    uint32_t *ob = bits + (out_chunk0 + q) * (long)g.bit_words;
+    int st = rec[q].end_state, bit, next_start = 0, walked = 0;
+    for (int wv = (g.F - 1) >> 5; wv >= 0; wv--) {
+        const int i0 = wv << 5, nb = min(32, g.F - i0);
+        unsigned word = 0;
+        if (nb == 32) {
+            // 32 independent 8-byte loads in flight (the addresses do not depend on the walk), then 32 dependent steps
+            const uint2 *row = d + 6 + i0;
+            uint2 r[32];
+#pragma unroll
+            for (int j = 0; j < 32; j++)
+                r[j] = __ldcs(row + j);
+#pragma unroll
+            for (int j = 31; j >= 0; j--) {
+                st = tb_step(st, r[j].x, r[j].y, bit);
+                word |= (unsigned)bit << (31 - j);
+                if (++walked == 6) next_start = st;
+            }
+        } else {
+            for (int j = nb - 1; j >= 0; j--) {
+                const uint2 r = d[6 + i0 + j];
+                st = tb_step(st, r.x, r.y, bit);
+                word |= (unsigned)bit << (31 - j);
+                if (++walked == 6) next_start = st;
+            }
+        }
+        ob[wv] = word;
+    }
+    rec[q].next_start = next_start;
 }
 
 // BER pass (separate launch so every chunk's bits are complete): one warp per chunk.

@@ -73,7 +73,9 @@ def test_noise_then_signal_then_noise(built):
     soft = oracle_demod(O, cfg).run(raw, stages=False)["soft"]
     rng = np.random.default_rng(4)
     noise = lambda n: np.clip(rng.normal(0, 40, n), -127, 127).astype(np.int8)
-    stream = np.concatenate([noise(16384 * 5 + 77), soft[:16384 * 40], noise(16384 * 30), soft[16384 * 40:16384 * 70]])
+    # (offsets are multiples of 4 soft bytes: an odd offset would split I/Q pairs and leave the lock test on a knife edge, where the
+    # reference itself is not reproducible — its BER scratch buffer has never-written bytes)
+    stream = np.concatenate([noise(16384 * 5 + 76), soft[:16384 * 40], noise(16384 * 30), soft[16384 * 40:16384 * 70]])
     want = oracle_fec(O, cfg).run(stream)
     assert 0 in want["vit_state"] and 1 in want["vit_state"]
     g = gpu_fec(cfg, stream.size).push(stream)
