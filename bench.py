@@ -115,7 +115,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--log2-samples", dest="log2_samples", type=int, default=27)
+    ap.add_argument("--log2-samples", dest="log2_samples", type=int, default=28)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -89,7 +89,17 @@ void design_mm_bank(std::vector<float> &out)
 }
 
 static int round_up16(double v) { return ((int)std::ceil(v / 16.0)) * 16; }
-constexpr int REPAIR_ROUNDS = 8;   // a run of r consecutive unconverged junctions needs r rounds; idle rounds cost two empty launches
+static int repair_rounds()
+{
+    // a run of r consecutive unconverged junctions needs r rounds; idle rounds cost two empty launches. B200_REPAIR_ROUNDS overrides (profiling).
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("B200_REPAIR_ROUNDS");
+        v = e ? atoi(e) : 8;
+    }
+    return v;
+}
+#define REPAIR_ROUNDS repair_rounds()
 constexpr float MM_TOL = 0.05f;    // samples: junction disagreement of the sampling instant that triggers a repair
 
 

@@ -111,6 +111,9 @@ Fec::Fec(const b200_fec_cfg &c) : cfg(c)
     fifo.alloc((size_t)((max_new_bits + 2L * cfg.cadu_size + 4096) / 32 + 8));
     start_state.alloc(max_chunks + 1);
     rec.alloc(max_chunks + 1);
+    tb_blocks = ((geom.F + 31) / 32 + TB_WORDS - 1) / TB_WORDS;
+    tb_edges.alloc((size_t)(max_chunks + 1) * tb_blocks);
+    tb_list.alloc(4097);
     idle_out.alloc(1);
     dstate.alloc(2);
     devents.alloc(4096);
@@ -218,12 +221,22 @@ static void viterbi_segment(Fec &f, long c0, long nch, std::vector<OutChunk> &ou
         B200_CUDA(cudaEventRecord(f.evm[0], f.stream));
         k_vit_acs<<<nb_main, 32 * wpb, 0, f.stream>>>(f.softbuf.p, c, n, f.geom, f.hyp, f.start_state.p, f.dec.p, f.rec.p);
         B200_CUDA(cudaEventRecord(f.evm[1], f.stream));
-        k_vit_tb<<<(n + 127) / 128, 128, 0, f.stream>>>(n, f.geom, f.dec.p, f.chunk_bits.p, out_base, f.rec.p);
-        f.launches++;
+        {
+            const long nthr = (long)n * f.tb_blocks;
+            B200_CUDA(cudaMemsetAsync(f.tb_list.p, 0, sizeof(int), f.stream));
+            k_vit_tb<<<(unsigned)((nthr + 127) / 128), 128, 0, f.stream>>>(n, f.tb_blocks, f.geom, f.dec.p, f.chunk_bits.p, out_base, f.rec.p, f.tb_edges.p);
+            k_vit_tb_check<<<(n + 255) / 256, 256, 0, f.stream>>>(n, f.tb_blocks, f.tb_edges.p, f.tb_list.p, 4096);
+            k_vit_tb_serial<<<32, 128, 0, f.stream>>>(f.tb_list.p, 4096, f.geom, f.dec.p, f.chunk_bits.p, out_base, f.rec.p);
+            f.launches += 3;
+        }
         k_vit_ber<<<nb_main, 32 * wpb, 0, f.stream>>>(f.softbuf.p, c, n, f.geom, f.hyp, f.chunk_bits.p, out_base, f.enc_state, f.rec.p);
         f.launches += 2;
         B200_CUDA(cudaMemcpyAsync(f.h_rec, f.rec.p, sizeof(VitRec) * n, cudaMemcpyDeviceToHost, f.stream));
+        int tb_redone = 0;
+        B200_CUDA(cudaMemcpyAsync(&tb_redone, f.tb_list.p, sizeof(int), cudaMemcpyDeviceToHost, f.stream));
         B200_CUDA(cudaStreamSynchronize(f.stream));
+        f.tb_serial_total += tb_redone;
+        B200_REQUIRE(tb_redone <= 4096, B200_EUNSUPPORTED, "more than 4096 chunks needed a serial chainback in one launch");
         {
             float ms = 0;
             cudaEventElapsedTime(&ms, f.evm[0], f.evm[1]);
@@ -503,7 +516,7 @@ void Fec::stats(b200_fec_stats *o)
     o->deframer_state = defr_state_now;
     o->rs_corrected = rs_corrected;
     o->rs_failed = rs_failed;
-    o->replays = replays;
+    o->replays = replays + tb_serial_total; // start-state mis-speculations + chunks whose parallel chainback had to be redone serially
     o->kernel_launches = launches;
 }
 

@@ -266,41 +266,107 @@ __global__ void __launch_bounds__(128) k_vit_acs(const int8_t *__restrict__ soft
     }
 }
 
-// ---------------------------------------------------------------- main decode, part 2: chainback (one THREAD per chunk)
+// ---------------------------------------------------------------- main decode, part 2: chainback, parallel blocks
 // Rows F+5 .. 6 (cc_decoder.cpp:228-276): output bit i comes from row i+6; the state after the first six steps is the next
-// call's start state. The walk is inherently serial per chunk and every lane of a warp would do the same work, so it runs
-// thread-per-chunk: 6 ALU instructions + one 8-byte load per row instead of a warp's worth.
-__global__ void __launch_bounds__(128) k_vit_tb(int nchunks, VitGeom g, const uint2 *__restrict__ dec, uint32_t *__restrict__ bits, long out_chunk0,
-                                                 VitRec *__restrict__ rec)
+// call's start state. The walk is serial in the state, but survivor paths merge: a walk started TB_OVERLAP rows higher from an
+// arbitrary state has joined the true path by the time it reaches its block. One thread per (chunk, block of TB_WORDS output
+// words): block 0 starts from the true end state, block k>0 warms up over TB_OVERLAP rows and records the state it assumed at
+// its top edge; k_vit_tb_check compares it with the state its upper neighbour really left there. If every edge agrees the
+// result IS the serial chainback; chunks with a disagreeing edge are redone serially by k_vit_tb_serial (rare; counted).
+constexpr int TB_WORDS = 16;     // 512 output bits per block
+constexpr int TB_OVERLAP = 256;  // warm-up rows
+#endif // B200_DEFINE_KERNELS
+struct TbEdge { unsigned char assumed, left; };
+#ifdef B200_DEFINE_KERNELS
+__device__ __forceinline__ int tb_walk_rows(const uint2 *__restrict__ rowbase, int nrows, int st)
+{
+    // walks rows rowbase[nrows-1] .. rowbase[0] without output (warm-up)
+    int bit;
+    for (int j = nrows - 1; j >= 0; j -= 8) {
+        uint2 r[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) r[k] = (j - k >= 0) ? __ldg(rowbase + j - k) : make_uint2(0, 0);
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            if (j - k >= 0) st = tb_step(st, r[k].x, r[k].y, bit);
+    }
+    return st;
+}
+
+__global__ void __launch_bounds__(128) k_vit_tb(int nchunks, int nblocks, VitGeom g, const uint2 *__restrict__ dec, uint32_t *__restrict__ bits,
+                                                 long out_chunk0, VitRec *__restrict__ rec, TbEdge *__restrict__ edges)
+{
+    const long gid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long)nchunks * nblocks) return;
+    const int q = (int)(gid / nblocks), k = (int)(gid - (long)q * nblocks);
+    const uint2 *d = dec + (long)q * g.dec_stride;
+    uint32_t *ob = bits + (out_chunk0 + q) * (long)g.bit_words;
+    const int nwords = (g.F + 31) >> 5;
+    const int w_hi = nwords - k * TB_WORDS;            // exclusive
+    const int w_lo = max(0, w_hi - TB_WORDS);          // inclusive
+    int st, bit, walked = 0, next_start = 0;
+    if (k == 0)
+        st = rec[q].end_state;
+    else {
+        // top edge of this block = row 6 + 32*w_hi (first row above it); warm up from TB_OVERLAP rows higher
+        const int top = min(g.F, 32 * w_hi + TB_OVERLAP); // output index (exclusive) where the warm-up starts
+        st = tb_walk_rows(d + 6 + 32 * w_hi, top - 32 * w_hi, 0);
+        edges[(long)q * nblocks + k].assumed = (unsigned char)st;
+    }
+    for (int wv = w_hi - 1; wv >= w_lo; wv--) {
+        const int i0 = wv << 5, nb = min(32, g.F - i0);
+        const uint2 *row = d + 6 + i0;
+        unsigned word = 0;
+        for (int jb = ((nb - 1) >> 3) << 3; jb >= 0; jb -= 8) {
+            uint2 r[8];
+#pragma unroll
+            for (int t = 0; t < 8; t++) r[t] = (jb + t < nb) ? __ldg(row + jb + t) : make_uint2(0, 0);
+#pragma unroll
+            for (int t = 7; t >= 0; t--)
+                if (jb + t < nb) {
+                    st = tb_step(st, r[t].x, r[t].y, bit);
+                    word |= (unsigned)bit << (31 - (jb + t));
+                    if (++walked == 6) next_start = st;
+                }
+        }
+        ob[wv] = word;
+    }
+    if (k == 0) rec[q].next_start = next_start;
+    edges[(long)q * nblocks + k].left = (unsigned char)st; // state handed to the block below (rows < 6 + 32*w_lo)
+}
+
+// flags chunks whose blocks disagree at an edge; list[0] = count, list[1..] = chunk indices
+__global__ void k_vit_tb_check(int nchunks, int nblocks, const TbEdge *__restrict__ edges, int *__restrict__ list, int cap)
 {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nchunks) return;
+    bool bad = false;
+    for (int k = 1; k < nblocks; k++)
+        if (edges[(long)q * nblocks + k].assumed != edges[(long)q * nblocks + k - 1].left) bad = true;
+    if (bad) {
+        const int slot = atomicAdd(list, 1);
+        if (slot < cap) list[1 + slot] = q;
+    }
+}
+
+// serial chainback of the flagged chunks (one thread per chunk)
+__global__ void __launch_bounds__(128) k_vit_tb_serial(const int *__restrict__ list, int cap, VitGeom g, const uint2 *__restrict__ dec,
+                                                        uint32_t *__restrict__ bits, long out_chunk0, VitRec *__restrict__ rec)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= min(list[0], cap)) return;
+    const int q = list[1 + i];
     const uint2 *d = dec + (long)q * g.dec_stride;
     uint32_t *ob = bits + (out_chunk0 + q) * (long)g.bit_words;
     int st = rec[q].end_state, bit, next_start = 0, walked = 0;
     for (int wv = (g.F - 1) >> 5; wv >= 0; wv--) {
         const int i0 = wv << 5, nb = min(32, g.F - i0);
         unsigned word = 0;
-        if (nb == 32) {
-            // 32 independent 8-byte loads in flight (the addresses do not depend on the walk), then 32 dependent steps
-            const uint2 *row = d + 6 + i0;
-            uint2 r[32];
-#pragma unroll
-            for (int j = 0; j < 32; j++)
-                r[j] = __ldcs(row + j);
-#pragma unroll
-            for (int j = 31; j >= 0; j--) {
-                st = tb_step(st, r[j].x, r[j].y, bit);
-                word |= (unsigned)bit << (31 - j);
-                if (++walked == 6) next_start = st;
-            }
-        } else {
-            for (int j = nb - 1; j >= 0; j--) {
-                const uint2 r = d[6 + i0 + j];
-                st = tb_step(st, r.x, r.y, bit);
-                word |= (unsigned)bit << (31 - j);
-                if (++walked == 6) next_start = st;
-            }
+        for (int j = nb - 1; j >= 0; j--) {
+            const uint2 r = d[6 + i0 + j];
+            st = tb_step(st, r.x, r.y, bit);
+            word |= (unsigned)bit << (31 - j);
+            if (++walked == 6) next_start = st;
         }
         ob[wv] = word;
     }

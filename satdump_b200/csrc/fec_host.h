@@ -44,6 +44,10 @@ class Fec
     DevBuf<uint32_t> chunk_bits, fifo;
     DevBuf<int> start_state, rs_err, counters;
     DevBuf<VitRec> rec;
+    DevBuf<TbEdge> tb_edges;
+    DevBuf<int> tb_list; // [0] count of chunks redone serially in the last launch, [1..] their indices
+    int tb_blocks = 1;
+    long tb_serial_total = 0;
     DevBuf<VitIdleOut> idle_out;
     DevBuf<DefrState> dstate;
     DevBuf<DefrEvent> devents;
