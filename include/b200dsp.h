@@ -122,6 +122,8 @@ int b200_demod_pull_soft(b200_demod *d, int8_t *host_out, long cap, long *n_out)
 int b200_demod_pull_symbols(b200_demod *d, float *host_out, long cap_symbols, long *n_out);
 /* stage outputs of the LAST push (needs keep_stages): nsamples complex values, interleaved re,im */
 int b200_demod_debug_stage(b200_demod *d, int stage, float *host_out, long cap_samples);
+/* test hook: only the sample conversion (BasebandReader::read_samples, baseband_interface.h:170-190) of `nsamples` host samples */
+int b200_demod_debug_convert(b200_demod *d, const void *host_iq, long nsamples, float *host_out);
 int b200_demod_get_stats(b200_demod *d, b200_demod_stats *out);
 /* RRC taps / M&M polyphase bank as designed on the host (for parity tests against firdes / PolyphaseBank) */
 int b200_demod_get_taps(b200_demod *d, float *rrc_out, int rrc_cap, float *bank_out /* 128*8 or NULL */);

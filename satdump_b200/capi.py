@@ -21,7 +21,7 @@ E_NAMES = {0: "OK", -1: "EINVAL", -2: "ENODEV", -3: "ECUDA", -4: "ENOMEM", -5: "
 SYMBOLS = [
     "b200_last_error", "b200_device_count",
     "b200_demod_create", "b200_demod_destroy", "b200_demod_push_iq", "b200_demod_push_iq_device", "b200_demod_pull_soft",
-    "b200_demod_pull_symbols", "b200_demod_debug_stage", "b200_demod_get_stats", "b200_demod_get_taps",
+    "b200_demod_pull_symbols", "b200_demod_debug_stage", "b200_demod_debug_convert", "b200_demod_get_stats", "b200_demod_get_taps",
     "b200_fec_create", "b200_fec_destroy", "b200_fec_push_soft", "b200_fec_push_soft_device", "b200_fec_pull_frames",
     "b200_fec_debug_bits", "b200_fec_get_stats", "b200_fec_cadu_bytes", "b200_fec_chunk_size",
     "b200_chain_create", "b200_chain_destroy", "b200_chain_push_iq", "b200_chain_push_iq_device", "b200_chain_prefetch_iq", "b200_chain_pull_frames",
@@ -82,6 +82,7 @@ def lib():
         L.b200_demod_pull_soft.argtypes = [vp, vp, cl, C.POINTER(cl)]
         L.b200_demod_pull_symbols.argtypes = [vp, vp, cl, C.POINTER(cl)]
         L.b200_demod_debug_stage.argtypes = [vp, ci, vp, cl]
+        L.b200_demod_debug_convert.argtypes = [vp, vp, cl, vp]
         L.b200_demod_get_stats.argtypes = [vp, C.POINTER(DemodStats)]
         L.b200_demod_get_taps.argtypes = [vp, vp, ci, vp]
         L.b200_fec_create.restype = vp
@@ -198,6 +199,12 @@ class Demod:
     def stage(self, which):
         out = np.zeros(self._n, np.complex64)
         _chk(lib().b200_demod_debug_stage(self.h, {"agc": 0, "fir": 1, "costas": 2}[which], out.ctypes.data, self._n))
+        return out
+
+    def convert(self, raw):
+        raw, n = _nsamples(raw, self.cfg.format)
+        out = np.zeros(n, np.complex64)
+        _chk(lib().b200_demod_debug_convert(self.h, raw.ctypes.data, n, out.ctypes.data))
         return out
 
     def stats(self):

@@ -502,6 +502,27 @@ int b200_demod_debug_stage(b200_demod *h, int stage, float *out, long cap_sample
         B200_CUDA(cudaStreamSynchronize(d.stream));
     });
 }
+int b200_demod_debug_convert(b200_demod *h, const void *host_iq, long n, float *host_out)
+{
+    return guarded([&] {
+        B200_REQUIRE(h && host_iq && host_out, B200_EINVAL, "NULL argument");
+        Demod &d = *h->d;
+        B200_REQUIRE(n > 0 && n <= d.max_batch, B200_ESTATE, "sample count outside (0, max_batch]");
+        DeviceGuard g(d.cfg.device);
+        const int fmt_bytes = d.cfg.format == B200_CF32 ? 8 : (d.cfg.format == B200_CS16 ? 4 : 2);
+        B200_CUDA(cudaMemcpyAsync(d.raw.p, host_iq, (size_t)n * fmt_bytes, cudaMemcpyHostToDevice, d.stream));
+        float2 *out = d.bufB.p + 16;
+        const unsigned blocks = (unsigned)((n + 8 * 256 - 1) / (8 * 256));
+        if (d.cfg.format == B200_CF32)
+            k_convert_only<0><<<blocks, 256, 0, d.stream>>>(d.raw.p, n, out);
+        else if (d.cfg.format == B200_CS16)
+            k_convert_only<1><<<blocks, 256, 0, d.stream>>>(d.raw.p, n, out);
+        else
+            k_convert_only<2><<<blocks, 256, 0, d.stream>>>(d.raw.p, n, out);
+        B200_CUDA(cudaMemcpyAsync(host_out, out, n * sizeof(float2), cudaMemcpyDeviceToHost, d.stream));
+        B200_CUDA(cudaStreamSynchronize(d.stream));
+    });
+}
 int b200_demod_get_stats(b200_demod *h, b200_demod_stats *out)
 {
     return guarded([&] {

@@ -115,6 +115,9 @@ Fec::Fec(const b200_fec_cfg &c) : cfg(c)
     tb_edges.alloc((size_t)(max_chunks + 1) * tb_blocks);
     tb_list.alloc(4097);
     idle_out.alloc(1);
+    idle2_out.alloc(1);
+    B200_CUDA(cudaMallocHost((void **)&h_idle2, sizeof(VitIdle2Out)));
+    B200_CUDA(cudaFuncSetAttribute(k_vit_idle2, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * VIT_IDLE_WARP_BYTES));
     dstate.alloc(2);
     devents.alloc(4096);
     max_frames_push = max_new_bits / cfg.cadu_size + 4;
@@ -156,7 +159,7 @@ Fec::~Fec()
         cudaEventDestroy(e);
     for (auto &e : evf)
         cudaEventDestroy(e);
-    for (void *p : {(void *)h_rec, (void *)h_idle, (void *)h_counters, (void *)h_dstate, (void *)h_events, (void *)h_rs_err})
+    for (void *p : {(void *)h_idle2, (void *)h_rec, (void *)h_idle, (void *)h_counters, (void *)h_dstate, (void *)h_events, (void *)h_rs_err})
         if (p)
             cudaFreeHost(p);
     if (stream)
@@ -192,11 +195,28 @@ static void viterbi_segment(Fec &f, long c0, long nch, std::vector<OutChunk> &ou
     while (c < nch) {
         if (f.vit_state == 0) {
             f.idle_st.enc_state = f.enc_state; // ONE chained CCEncoder serves the lock test and the SYNCED BER check (viterbi_3_4.cpp:126,157)
-            k_vit_idle<<<1, 32, 0, f.stream>>>(f.softbuf.p, c, (int)(nch - c), f.geom, f.nswap, f.nphases, f.ph0, f.ph1, f.cfg.ber_thresold, f.idle_st,
-                                              f.idle_dec.p, f.idle_out.p);
-            f.launches++;
-            B200_CUDA(cudaMemcpyAsync(f.h_idle, f.idle_out.p, sizeof(VitIdleOut), cudaMemcpyDeviceToHost, f.stream));
-            B200_CUDA(cudaStreamSynchronize(f.stream));
+            {
+                // parallel search first (one warp per hypothesis); it hands over to the serial kernel at the first chunk whose chained
+                // 6-bit states its two-pass guess did not reproduce
+                const int nh = f.nswap * f.nphases * 2;
+                k_vit_idle2<<<1, 32 * nh, nh * VIT_IDLE_WARP_BYTES, f.stream>>>(f.softbuf.p, c, (int)(nch - c), f.geom, f.nswap, f.nphases, f.ph0, f.ph1,
+                                                                               f.cfg.ber_thresold, f.idle_st, f.idle2_out.p);
+                f.launches++;
+                B200_CUDA(cudaMemcpyAsync(f.h_idle2, f.idle2_out.p, sizeof(VitIdle2Out), cudaMemcpyDeviceToHost, f.stream));
+                B200_CUDA(cudaStreamSynchronize(f.stream));
+                *f.h_idle = f.h_idle2->o;
+                if (f.h_idle2->fallback_chunk >= 0) {
+                    f.idle_fallbacks++;
+                    const long c2 = c + f.h_idle2->fallback_chunk;
+                    k_vit_idle<<<1, 32, 0, f.stream>>>(f.softbuf.p, c2, (int)(nch - c2), f.geom, f.nswap, f.nphases, f.ph0, f.ph1, f.cfg.ber_thresold,
+                                                      f.h_idle2->o.st, f.idle_dec.p, f.idle_out.p);
+                    f.launches++;
+                    B200_CUDA(cudaMemcpyAsync(f.h_idle, f.idle_out.p, sizeof(VitIdleOut), cudaMemcpyDeviceToHost, f.stream));
+                    B200_CUDA(cudaStreamSynchronize(f.stream));
+                    if (f.h_idle->lock_chunk >= 0)
+                        f.h_idle->lock_chunk += (int)(c2 - c);
+                }
+            }
             f.idle_st = f.h_idle->st;
             f.enc_state = f.idle_st.enc_state;
             float bb = 10.f;

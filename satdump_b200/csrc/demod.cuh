@@ -51,6 +51,16 @@ template <> struct RawBytes<0> { static constexpr int v = 8; };
 template <> struct RawBytes<1> { static constexpr int v = 4; };
 template <> struct RawBytes<2> { static constexpr int v = 2; };
 
+// x / d for a small integer-valued x, correctly rounded (= the generic VOLK converters' ((float)x) / scalar)
+// without the ~10-instruction IEEE division: q = x * (1/d) is within 1 ulp; one FMA residual step makes it the correctly rounded
+// quotient (tests/test_gpu_demod.py checks all 65 536 / 256 inputs bit for bit).
+__device__ __forceinline__ float div_exact(float x, float d, float rd)
+{
+    const float q = x * rd;
+    const float r = fmaf(-q, d, x);
+    return fmaf(r, rd, q);
+}
+
 // load 8 consecutive complex samples starting at sample index s0 (multiple of 8 relative to a 16-aligned base) and convert
 #ifdef B200_DEFINE_KERNELS
 template <int FMT>
@@ -63,8 +73,8 @@ __device__ __forceinline__ void load8(const void *__restrict__ raw, long s0, lon
             int w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
             for (int i = 0; i < 8; i++) {
-                x[i].x = __fdiv_rn((float)(short)(w[i] & 0xFFFF), 32767.0f);
-                x[i].y = __fdiv_rn((float)(short)(w[i] >> 16), 32767.0f);
+                x[i].x = div_exact((float)(short)(w[i] & 0xFFFF), 32767.0f, 1.0f / 32767.0f);
+                x[i].y = div_exact((float)(short)(w[i] >> 16), 32767.0f, 1.0f / 32767.0f);
             }
         } else if (FMT == 2) {
             const int4 *p = reinterpret_cast<const int4 *>(reinterpret_cast<const int8_t *>(raw) + 2 * s0);
@@ -72,10 +82,10 @@ __device__ __forceinline__ void load8(const void *__restrict__ raw, long s0, lon
             int w[4] = {v0.x, v0.y, v0.z, v0.w};
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                x[2 * i].x = __fdiv_rn((float)(signed char)(w[i] & 0xFF), 127.0f);
-                x[2 * i].y = __fdiv_rn((float)(signed char)((w[i] >> 8) & 0xFF), 127.0f);
-                x[2 * i + 1].x = __fdiv_rn((float)(signed char)((w[i] >> 16) & 0xFF), 127.0f);
-                x[2 * i + 1].y = __fdiv_rn((float)(signed char)((w[i] >> 24) & 0xFF), 127.0f);
+                x[2 * i].x = div_exact((float)(signed char)(w[i] & 0xFF), 127.0f, 1.0f / 127.0f);
+                x[2 * i].y = div_exact((float)(signed char)((w[i] >> 8) & 0xFF), 127.0f, 1.0f / 127.0f);
+                x[2 * i + 1].x = div_exact((float)(signed char)((w[i] >> 16) & 0xFF), 127.0f, 1.0f / 127.0f);
+                x[2 * i + 1].y = div_exact((float)(signed char)((w[i] >> 24) & 0xFF), 127.0f, 1.0f / 127.0f);
             }
         } else {
             const float4 *p = reinterpret_cast<const float4 *>(reinterpret_cast<const float2 *>(raw) + s0);
@@ -94,12 +104,12 @@ __device__ __forceinline__ void load8(const void *__restrict__ raw, long s0, lon
             if (s < n_valid) {
                 if (FMT == 1) {
                     const int16_t *p = reinterpret_cast<const int16_t *>(raw) + 2 * s;
-                    v.x = __fdiv_rn((float)p[0], 32767.0f);
-                    v.y = __fdiv_rn((float)p[1], 32767.0f);
+                    v.x = div_exact((float)p[0], 32767.0f, 1.0f / 32767.0f);
+                    v.y = div_exact((float)p[1], 32767.0f, 1.0f / 32767.0f);
                 } else if (FMT == 2) {
                     const int8_t *p = reinterpret_cast<const int8_t *>(raw) + 2 * s;
-                    v.x = __fdiv_rn((float)p[0], 127.0f);
-                    v.y = __fdiv_rn((float)p[1], 127.0f);
+                    v.x = div_exact((float)p[0], 127.0f, 1.0f / 127.0f);
+                    v.y = div_exact((float)p[1], 127.0f, 1.0f / 127.0f);
                 } else
                     v = reinterpret_cast<const float2 *>(raw)[s];
             }
@@ -108,10 +118,24 @@ __device__ __forceinline__ void load8(const void *__restrict__ raw, long s0, lon
     }
 }
 
+// test hook: the conversion alone (8 samples per thread)
+template <int FMT>
+__global__ void k_convert_only(const void *__restrict__ raw, long N, float2 *__restrict__ out)
+{
+    const long s0 = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+    if (s0 >= N) return;
+    float2 x[8];
+    load8<FMT>(raw, s0, N, x);
+    for (int i = 0; i < 8; i++)
+        if (s0 + i < N) out[s0 + i] = x[i];
+}
+
 // affine map of one AGC step for input sample x:  g' = g*(1 - rate*|x|) + rate*ref   (agc.cpp:30-33 rewritten)
+__device__ __forceinline__ float fast_mag(float s2) { return s2 > 0.f ? s2 * rsqrtf(s2) : 0.f; }
+
 __device__ __forceinline__ Affine agc_map(float2 x, float rate)
 {
-    float mag = sqrtf(x.x * x.x + x.y * x.y);
+    float mag = fast_mag(x.x * x.x + x.y * x.y);
     Affine m;
     m.a = 1.0 - (double)rate * (double)mag;
     m.b = (double)rate;
@@ -259,25 +283,36 @@ __global__ void __launch_bounds__(FIR_THREADS) k_agc_fir(const void *__restrict_
         // replay the reference's float recurrence over this thread's 8 samples from the scanned seed
         float g = (float)fma(excl.a, seeds[k], excl.b);
         bool clamped = false;
+        if (lstart + FIR_TL + 32 <= N && !DUMP) { // interior tile: every sample exists, none is in the stream tail
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            long s = lstart + l0 + i;
-            float2 o = make_float2(x[i].x * g, x[i].y * g);
-            if (s < N) {
-                float mag = sqrtf(__fadd_rn(__fmul_rn(o.x, o.x), __fmul_rn(o.y, o.y)));
+            for (int i = 0; i < 8; i++) {
+                const float2 o = make_float2(x[i].x * g, x[i].y * g);
+                const float mag = fast_mag(__fadd_rn(__fmul_rn(o.x, o.x), __fmul_rn(o.y, o.y)));
                 g = (float)((double)g + (double)rate * (1.0 - (double)mag));
-                if (g > 65536.0f) {
-                    g = 65536.0f;
-                    clamped = true;
-                }
-                if (DUMP)
-                    agc_dump[s] = o;
-                if (s >= N - 32)
-                    tail_out[s - (N - 32)] = o;
-                if (s == N - 1)
-                    *gain_out = g;
+                clamped |= g > 65536.0f;
+                x[i] = o;
             }
-            x[i] = o;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                long s = lstart + l0 + i;
+                float2 o = make_float2(x[i].x * g, x[i].y * g);
+                if (s < N) {
+                    float mag = fast_mag(__fadd_rn(__fmul_rn(o.x, o.x), __fmul_rn(o.y, o.y)));
+                    g = (float)((double)g + (double)rate * (1.0 - (double)mag));
+                    if (g > 65536.0f) {
+                        g = 65536.0f;
+                        clamped = true;
+                    }
+                    if (DUMP)
+                        agc_dump[s] = o;
+                    if (s >= N - 32)
+                        tail_out[s - (N - 32)] = o;
+                    if (s == N - 1)
+                        *gain_out = g;
+                }
+                x[i] = o;
+            }
         }
         if (clamped)
             atomicOr(flags, 1);
@@ -456,6 +491,12 @@ __global__ void __launch_bounds__(SEG_THREADS) k_costas(const float2 *__restrict
         __syncwarp();
         const bool mine = it < nrows;
         const long b = (long)(row0 + it) << 4;
+        // start / own0 are multiples of 16, so a row is entirely warm-up or entirely owned; only the batch's last row can be partial
+        if (mine && b == own0) {
+            lr.ph_start = phase;
+            lr.fr_start = freq;
+        }
+        const int nvalid = mine ? (int)min(16L, own1 - b) : 0;
 #pragma unroll
         for (int p = 0; p < 8; p++) {
             const float4 v = ring[swz16(slot + p, lane)];
@@ -463,37 +504,31 @@ __global__ void __launch_bounds__(SEG_THREADS) k_costas(const float2 *__restrict
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 const int j = 2 * p + h;
-                const long n = b + j;
                 const float2 x = h ? make_float2(v.z, v.w) : make_float2(v.x, v.y);
-                if (mine && n == own0) {
-                    lr.ph_start = phase;
-                    lr.fr_start = freq;
-                }
-                if (mine && n >= start && n < own1) {
+                o[h] = make_float2(0.f, 0.f);
+                if (j < nvalid) {
                     // in * (cos(-phase) + j sin(-phase))  (costas_loop.cpp:26); (cs, sn) = cos/sin of the CURRENT float phase
-                    float vr = x.x * cs + x.y * sn;
-                    float vi = x.y * cs - x.x * sn;
+                    const float vr = x.x * cs + x.y * sn;
+                    const float vi = x.y * cs - x.x * sn;
                     o[h] = make_float2(vr, vi);
-                    float err = costas_error(vr, vi, P.order);
+                    const float err = costas_error(vr, vi, P.order);
                     freq = freq + P.beta * err;
                     const float prev = phase;
                     phase = phase + (freq + P.alpha * err);
                     const float d = phase - prev; // the increment the float phase really took (exact difference)
-                    bool refresh = (j & 7) == 7 || fabsf(d) > 0.05f;
-                    while (phase > 6.283185307179586) {
+                    bool refresh = (j & 3) == 3 || fabsf(d) > 0.05f;
+                    // while (phase > 2*M_PI) in double == float compare against the largest float below 2*pi (0x40C90FDA)
+                    while (phase > 6.283185005f) {
                         phase = (float)((double)phase - 6.283185307179586);
                         refresh = true;
                     }
-                    while (phase < -6.283185307179586) {
+                    while (phase < -6.283185005f) {
                         phase = (float)((double)phase + 6.283185307179586);
                         refresh = true;
                     }
-                    if (freq > P.fmax)
-                        freq = P.fmax;
-                    if (freq < P.fmin)
-                        freq = P.fmin;
+                    freq = fminf(P.fmax, fmaxf(P.fmin, freq));
                     if (refresh)
-                        sincosf(phase, &sn, &cs); // exact re-anchor every 8 samples / on a wrap: bounds the rotation's rounding drift to < 1e-6
+                        sincosf(phase, &sn, &cs); // exact re-anchor every 4 samples / on a wrap: bounds the rotation's rounding drift to < 1e-6
                     else {
                         // rotate (cs, sn) by the small increment d: Taylor sin/cos, |d| <= 0.05 -> truncation < 2e-10
                         const float d2 = d * d;
@@ -503,8 +538,7 @@ __global__ void __launch_bounds__(SEG_THREADS) k_costas(const float2 *__restrict
                         sn = sn * cd + cs * sd;
                         cs = c2;
                     }
-                } else
-                    o[h] = make_float2(0.f, 0.f);
+                }
             }
             obuf[swz16(p, lane)] = make_float4(o[0].x, o[0].y, o[1].x, o[1].y);
         }

@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(128) k_vit_acs(const int8_t *__restrict__ soft
         const int tm = t0 + lane;
         const unsigned mine = tm < steps ? metric_table(vit_symbols(c, tm, g, h, g.chunk, 128)) : 0u;
         if (t0 + 32 <= steps) {
-#pragma unroll 8
+#pragma unroll
             for (int j = 0; j < 32; j++) {
                 acs2_step(__shfl_sync(0xffffffffu, mine, j), L, lane, xl2, xh2, D0, D1);
                 if (lane == 0) d[t0 + j] = make_uint2(D0, D1);
@@ -516,6 +516,148 @@ __global__ void __launch_bounds__(32) k_vit_idle(const int8_t *__restrict__ soft
         for (int i = 0; i < 16; i++) o.bers[i] = bers[i];
         o.st.dec_start = dec_start; o.st.enc_state = (int)enc; o.pad = 0;
         *out = o;
+    }
+}
+
+// ---------------------------------------------------------------- lock search, parallel form
+// The 4 (8 with the OQPSK I/Q-swap search) hypotheses of a chunk form a chain only through two 6-bit registers (the test decoder's
+// start state and the BER encoder's register). One warp per hypothesis: pass A runs every ACS with a guessed start (hypothesis 0's is
+// the exact carried one) to learn the chainback states; pass B re-runs hypotheses 1.. from their predecessor's pass-A state and does
+// the full chainback; if every predecessor's pass-B state equals its pass-A state the chain is the serial one. Otherwise the kernel
+// reports `fallback_chunk` and the host continues with the serial k_vit_idle from there.
+#endif // B200_DEFINE_KERNELS
+struct VitIdle2Out { VitIdleOut o; int fallback_chunk; int pad[3]; };
+constexpr int VIT_IDLE_ROWS = VIT_TESTLEN * 3 / 4 + 6 + 2;           // decision rows per hypothesis (r=3/4 is the larger: 1542)
+constexpr int VIT_IDLE_WARP_BYTES = VIT_IDLE_ROWS * 8 + 64 * 4;       // + 64 words of decoded bits
+#ifdef B200_DEFINE_KERNELS
+__global__ void __launch_bounds__(256) k_vit_idle2(const int8_t *__restrict__ soft, long chunk0, int nchunks, VitGeom g, int nswap, int nphases, int ph0,
+                                                    int ph1, float thr, VitIdleState st_in, VitIdle2Out *__restrict__ out)
+{
+    extern __shared__ __align__(16) unsigned char idle_smem[];
+    __shared__ int rA[8], rB[8], errs[8], tots[8], tails[8];
+    __shared__ int s_lock, s_dec, s_enc, s_fallback;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, nh = nswap * nphases * 2;
+    uint2 *dec = reinterpret_cast<uint2 *>(idle_smem + (size_t)w * VIT_IDLE_WARP_BYTES);
+    uint32_t *tb = reinterpret_cast<uint32_t *>(idle_smem + (size_t)w * VIT_IDLE_WARP_BYTES + VIT_IDLE_ROWS * 8);
+    const Acs2Lane L = acs2_lane_consts(lane);
+    VitGeom tg = g;
+    tg.F = g.rate34 ? VIT_TESTLEN * 3 / 4 : VIT_TESTLEN / 2;
+    const int steps = tg.F + 6, nsym = g.rate34 ? VIT_TESTLEN * 3 / 2 : VIT_TESTLEN;
+    // hypothesis w in the reference's loop order: swap-major, then phase, then shift
+    const int hs = w / (nphases * 2), hp = (w / 2) % nphases, hshift = w & 1;
+    const VitHyp h{hs, hp == 0 ? ph0 : ph1, hshift};
+    if (threadIdx.x == 0) { s_lock = -1; s_dec = st_in.dec_start; s_enc = st_in.enc_state; s_fallback = -1; }
+    __syncthreads();
+    float bers[16];
+    for (int i = 0; i < 16; i++) bers[i] = 10.f;
+    float best = 10.f;
+    int lswap = 0, lphase = 0, lshift = 0;
+    for (int q = 0; q < nchunks; q++) {
+        const int8_t *c = soft + (chunk0 + q) * (long)g.chunk;
+        auto run_acs = [&](int start, bool keep) {
+            unsigned xl2, xh2, D0, D1;
+            acs2_init(start, lane, xl2, xh2);
+            for (int t0 = 0; t0 < steps; t0 += 32) {
+                const int tm = t0 + lane;
+                const unsigned mine = tm < steps ? metric_table(vit_symbols(c, tm, tg, h, VIT_TESTLEN, 0)) : 0u;
+                const int nn = min(32, steps - t0);
+                for (int j = 0; j < nn; j++) {
+                    acs2_step(__shfl_sync(0xffffffffu, mine, j), L, lane, xl2, xh2, D0, D1);
+                    if (lane == 0 && (keep || t0 + j >= tg.F)) dec[t0 + j] = make_uint2(D0, D1);
+                }
+            }
+            __syncwarp();
+            return acs2_endstate(xl2, xh2, lane);
+        };
+        auto chain6 = [&](int st) { // state after the first six chainback steps = next call's start state
+            int bit;
+            for (int row = steps - 1; row >= steps - 6; row--) st = tb_step(st, dec[row].x, dec[row].y, bit);
+            return st;
+        };
+        // ---- pass A
+        if (w < nh) {
+            const int e = run_acs(w == 0 ? s_dec : -1, w == 0);
+            const int r = chain6(e);
+            if (lane == 0) { rA[w] = r; if (w == 0) rB[0] = r; tails[w] = e; }
+        }
+        __syncthreads();
+        // ---- pass B (hypothesis 0 already ran from its exact start)
+        int endst = tails[w < nh ? w : 0];
+        if (w > 0 && w < nh) {
+            endst = run_acs(rA[w - 1], true);
+            const int r = chain6(endst);
+            if (lane == 0) rB[w] = r;
+        }
+        __syncthreads();
+        bool ok = true;
+        for (int k = 1; k < nh - 1; k++) ok &= (rB[k] == rA[k]); // rA[k] was the start handed to hypothesis k+1
+        if (!ok) { // (uniform) the guesses did not reproduce the serial chain: hand this chunk to the serial kernel
+            if (threadIdx.x == 0) s_fallback = q;
+            break;
+        }
+        // ---- full chainback (lane 0 of each warp; rows in shared memory) + decoded bits, MSB first
+        if (w < nh) {
+            if (lane == 0) {
+                int st = endst, bit;
+                for (int i = 0; i < 64; i++) tb[i] = 0;
+                for (int row = steps - 1; row >= 6; row--) {
+                    st = tb_step(st, dec[row].x, dec[row].y, bit);
+                    const int i = row - 6;
+                    tb[i >> 5] |= (unsigned)bit << (31 - (i & 31));
+                }
+                unsigned tail = 0;
+                for (int k = tg.F - 6; k < tg.F; k++) tail = (tail << 1) | ((tb[k >> 5] >> (31 - (k & 31))) & 1u);
+                tails[w] = (int)tail;
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+        // ---- BER with the chained encoder register (previous hypothesis' last six decoded bits)
+        if (w < nh) {
+            const unsigned enc = (unsigned)(w == 0 ? s_enc : tails[w - 1]);
+            int errors = 0, total = 0;
+            for (int t = lane; t < tg.F; t += 32) {
+                unsigned reg = 0;
+                for (int k = 6; k >= 0; k--) {
+                    const int idx = t - k;
+                    const unsigned b = idx >= 0 ? ((tb[idx >> 5] >> (31 - (idx & 31))) & 1u) : ((enc >> (-idx - 1)) & 1u);
+                    reg = (reg << 1) | b;
+                }
+                const int e0 = parity_u32(reg & 79u), e1 = parity_u32(reg & 109u);
+                const int sy = vit_symbols(c, t, tg, h, VIT_TESTLEN, 0);
+                const int s0 = sy & 255, s1 = sy >> 8;
+                if (2 * t < nsym && s0 != 128) { errors += ((s0 > 127) != e0); total++; }
+                if (2 * t + 1 < nsym && s1 != 128) { errors += ((s1 > 127) != e1); total++; }
+            }
+            for (int off = 16; off; off >>= 1) {
+                errors += __shfl_xor_sync(0xffffffffu, errors, off);
+                total += __shfl_xor_sync(0xffffffffu, total, off);
+            }
+            if (lane == 0) { errs[w] = errors; tots[w] = total; }
+        }
+        __syncthreads();
+        // ---- the lock decision, in the reference's order (viterbi_3_4.cpp:130-141) — every thread evaluates it identically
+        best = 10.f;
+        int lock = -1;
+        for (int k = 0; k < nh; k++) {
+            const float b = ((float)errs[k] / (float)tots[k]) * (g.rate34 ? 5.0f : 2.5f);
+            const int ks = k / (nphases * 2), kp = ((k / 2) % nphases) == 0 ? ph0 : ph1, ksh = k & 1;
+            bers[(ks * 4 + kp) * 2 + ksh] = b;
+            if ((best == 10.f && b < thr) || (best < 10.f && b < best)) { best = b; lock = q; lswap = ks; lphase = kp; lshift = ksh; }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { s_dec = rB[nh - 1]; s_enc = tails[nh - 1]; s_lock = lock; }
+        __syncthreads();
+        if (lock >= 0) break;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        VitIdle2Out r;
+        r.o.lock_chunk = s_lock; r.o.swap = lswap; r.o.phase = lphase; r.o.shift = lshift; r.o.ber = best;
+        for (int i = 0; i < 16; i++) r.o.bers[i] = bers[i];
+        r.o.st.dec_start = s_dec; r.o.st.enc_state = s_enc; r.o.pad = 0;
+        r.fallback_chunk = s_fallback; r.pad[0] = r.pad[1] = r.pad[2] = 0;
+        *out = r;
     }
 }
 

@@ -49,6 +49,9 @@ class Fec
     int tb_blocks = 1;
     long tb_serial_total = 0;
     DevBuf<VitIdleOut> idle_out;
+    DevBuf<VitIdle2Out> idle2_out;
+    VitIdle2Out *h_idle2 = nullptr;
+    long idle_fallbacks = 0;
     DevBuf<DefrState> dstate;
     DevBuf<DefrEvent> devents;
     DevBuf<FrameRec> frames;

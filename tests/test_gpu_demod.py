@@ -40,6 +40,22 @@ def test_filter_taps_bitwise(built):
     assert np.array_equal(bank, O.mm_taps())
 
 
+def test_sample_conversion_is_bit_exact(built):
+    """Every possible cs16 / cs8 sample value: the reciprocal+FMA conversion equals ((float)x) / scale of the reference's generic
+    converters (baseband_interface.h:178-188) bit for bit."""
+    cfg, _, _ = signal("metop_ahrpt", 16)
+    v16 = np.arange(-32768, 32768, dtype=np.int16)
+    got = gpu_demod(cfg, 1 << 16).convert(np.stack([v16, v16[::-1]], axis=1).reshape(-1))
+    assert np.array_equal(got.real.view(np.uint32), (v16.astype(np.float32) / np.float32(32767)).view(np.uint32))
+    assert np.array_equal(got.imag.view(np.uint32), (v16[::-1].astype(np.float32) / np.float32(32767)).view(np.uint32))
+    import dataclasses
+    from satdump_b200 import capi
+    v8 = np.tile(np.arange(-128, 128, dtype=np.int8), 32)
+    g8 = capi.Demod(capi.demod_cfg(90e6, 45e6, "none", 0.25, fmt="cs8", max_batch=8192))
+    got8 = g8.convert(np.stack([v8, v8[::-1]], axis=1).reshape(-1))
+    assert np.array_equal(got8.real.view(np.uint32), (v8.astype(np.float32) / np.float32(127)).view(np.uint32))
+
+
 @pytest.mark.parametrize("name", CONFIGS)
 def test_stage_parity(built, name):
     O = oracle()
