@@ -227,7 +227,9 @@ def main():
                 "roofline_fir_stage": {"kernels": "k_agc_compose + k_agc_scan + k_agc_fir", "bound": "hbm",
                                        "achieved": n * 12 / (fir_ms * 1e-3) / 1e9 if fir_ms > 0 else 0.0, "peak": hbm, "unit": "GB/s",
                                        "frac": (n * 12 / (fir_ms * 1e-3) / 1e9 / hbm) if fir_ms > 0 else 0.0},
-                "clocks": sampler.summary()}
+                "clocks": sampler.summary(),
+                "stream_stats": {"demod": {k: v for k, v in ch.stats()[0].items() if k in ("costas_unconverged", "mm_unconverged", "repairs", "agc_clamped")},
+                                 "fec": {k: v for k, v in ch.stats()[1].items() if k in ("replays", "rs_failed", "rs_corrected", "viterbi_state", "deframer_state")}}}
         if world == 1 and not args.no_cpu_baseline:
             try:
                 from oracle import ref, port

@@ -332,34 +332,37 @@ __global__ void __launch_bounds__(FIR_THREADS) k_agc_fir(const void *__restrict_
 
     // FIR: thread t (< 252) -> outputs local 32+8t .. +7 ; y[i] = sum_j x[i-30+j] * h[30-j], oldest first (fir.cpp:74-83)
     if (t < FIR_TO / 8) {
-        float2 acc[8];
+        // packed FP32x2: one FFMA2 does the (re, im) pair of a complex sample x real tap MAC (two independent fma.rn, i.e. the same
+        // results as scalar fmaf); the tap is a scalar broadcast operand. 31 FFMA2 per output sample instead of 62 FFMA.
+        unsigned long long acc[8];
 #pragma unroll
         for (int o = 0; o < 8; o++)
-            acc[o] = make_float2(0.f, 0.f);
+            acc[o] = 0ull;
         const int first = 8 * t + 2; // local index of the oldest input of output 0
 #pragma unroll
         for (int mI = 0; mI < 38; mI++) {
-            float2 v = xs[pidx(first + mI)];
+            const unsigned long long v = *reinterpret_cast<const unsigned long long *>(&xs[pidx(first + mI)]);
 #pragma unroll
             for (int o = 0; o < 8; o++) {
                 const int j = mI - o; // tap position (0 = oldest)
                 if (j >= 0 && j < FIR_NT) {
-                    acc[o].x = fmaf(v.x, taps.h[FIR_NT - 1 - j], acc[o].x);
-                    acc[o].y = fmaf(v.y, taps.h[FIR_NT - 1 - j], acc[o].y);
+                    unsigned long long hh;
+                    asm("mov.b64 %0, {%1, %1};" : "=l"(hh) : "f"(taps.h[FIR_NT - 1 - j]));
+                    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[o]) : "l"(v), "l"(hh));
                 }
             }
         }
         const long s0 = (long)k * FIR_TO + 8 * t;
         if (s0 + 8 <= N) {
-            float4 *p = reinterpret_cast<float4 *>(fir_out + s0);
+            ulonglong2 *p = reinterpret_cast<ulonglong2 *>(fir_out + s0);
 #pragma unroll
             for (int o = 0; o < 4; o++)
-                p[o] = make_float4(acc[2 * o].x, acc[2 * o].y, acc[2 * o + 1].x, acc[2 * o + 1].y);
+                p[o] = make_ulonglong2(acc[2 * o], acc[2 * o + 1]);
         } else {
 #pragma unroll
             for (int o = 0; o < 8; o++)
                 if (s0 + o < N)
-                    fir_out[s0 + o] = acc[o];
+                    *reinterpret_cast<unsigned long long *>(fir_out + s0 + o) = acc[o];
         }
     }
 }
@@ -545,7 +548,8 @@ __global__ void __launch_bounds__(SEG_THREADS) k_costas(const float2 *__restrict
         __syncwarp();
         // transposed copy-out: lanes 8q..8q+7 store the eight chunks of thread 4i+q's row (owned samples only)
         const int wr0 = (int)min(own0, 0x7fffffffL), wr1 = (int)own1;
-        const int brow = mine ? (int)b : -1;
+        const int brow = (mine && b >= own0) ? (int)b : -1;
+        if (__any_sync(0xffffffffu, brow >= 0))
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             const int T = 4 * i + (lane >> 3), c = lane & 7;
