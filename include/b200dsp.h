@@ -89,6 +89,7 @@ typedef struct b200_demod_stats
     int agc_clamped;          /* AGC hit max_gain: outside the parallel formulation              */
     int repairs;              /* segments re-run as exact sequential continuations (junction check failed) */
     long kernel_launches;     /* CUDA kernels launched by this object so far                     */
+    long agc_exact_passes;    /* batches whose AGC seeds needed the scanned (exact) pass: weak signal */
 } b200_demod_stats;
 
 typedef struct b200_fec_stats

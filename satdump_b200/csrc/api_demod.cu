@@ -148,9 +148,30 @@ Demod::Demod(const b200_demod_cfg &c) : cfg(c)
         agc_dump.alloc(max_batch);
         fir_dump.alloc(max_batch);
     }
-    const int ntiles_max = (int)((max_batch + FIR_TO - 1) / FIR_TO);
+    const int ntiles_max = (int)((max_batch + FIR_TILE - 1) / FIR_TILE);
     tile_map.alloc(ntiles_max + 1);
     seeds.alloc(ntiles_max + 2);
+    agc_need.alloc(2);
+    agc_need.zero(stream);
+    {
+        // 5 CTAs x 41.7 KB of static smem per SM: ask for the large shared-memory carve-out
+        B200_CUDA(cudaFuncSetAttribute(k_agc_fir<0, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        B200_CUDA(cudaFuncSetAttribute(k_agc_fir<1, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        B200_CUDA(cudaFuncSetAttribute(k_agc_fir<2, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        B200_CUDA(cudaFuncSetAttribute(k_agc_fir<0, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        B200_CUDA(cudaFuncSetAttribute(k_agc_fir<1, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        B200_CUDA(cudaFuncSetAttribute(k_agc_fir<2, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        int per_sm = 0;
+        if (c.format == B200_CF32)
+            B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_agc_fir<0, false>, FIR_THREADS, 0));
+        else if (c.format == B200_CS16)
+            B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_agc_fir<1, false>, FIR_THREADS, 0));
+        else
+            B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_agc_fir<2, false>, FIR_THREADS, 0));
+        fir_ctas = std::max(1, per_sm) * dev_sms;
+        if (const char *e = getenv("B200_AGC_WARM_TILES")) // 0 forces the exact (scanned-seed) pass: test hook
+            agc_warm_max = std::max(0, atoi(e));
+    }
     // worst-case segment count / slot storage: L >= 1024
     const int lmin = 1024;
     const long nseg_max = (max_batch + lmin - 1) / lmin + 1;
@@ -239,15 +260,29 @@ template <int FMT> static void launch_front(Demod &d, const void *raw, long n, i
 {
     DemodDevState *S = d.st.p;
     float2 *fir_out = d.bufA.p + 16;
-    k_agc_compose<FMT><<<ntiles, FIR_THREADS, 0, d.stream>>>(raw, n, d.cfg.agc_rate, d.tile_map.p);
-    k_agc_scan<<<1, 1024, 0, d.stream>>>(d.tile_map.p, ntiles, &S->gain[cur], d.seeds.p);
-    if (dump)
-        k_agc_fir<FMT, true><<<ntiles, FIR_THREADS, 0, d.stream>>>(raw, n, d.cfg.agc_rate, d.seeds.p, taps, S->agc_tail[cur], S->agc_tail[cur ^ 1], fir_out,
-                                                                  d.agc_dump.p, &S->gain[cur ^ 1], &S->flags);
-    else
-        k_agc_fir<FMT, false><<<ntiles, FIR_THREADS, 0, d.stream>>>(raw, n, d.cfg.agc_rate, d.seeds.p, taps, S->agc_tail[cur], S->agc_tail[cur ^ 1], fir_out,
-                                                                   nullptr, &S->gain[cur ^ 1], &S->flags);
-    d.launches += 3;
+    // one wave of persistent CTAs, each running a range of R consecutive tiles
+    const int R = std::max(4, (ntiles + d.fir_ctas - 1) / d.fir_ctas);
+    const int nranges = (ntiles + R - 1) / R;
+    AgcCtl ctl;
+    ctl.seeds = d.seeds.p;
+    ctl.need = d.agc_need.p;
+    ctl.epoch = ++d.agc_epoch;
+    ctl.warm_max = d.agc_warm_max;
+    const int *need = d.agc_need.p + (ctl.epoch & 1);
+    for (int pass = 0; pass < 2; pass++) {
+        ctl.seeded = pass;
+        if (pass) { // exact pass: returns at once unless the fast pass asked for it
+            k_agc_compose<FMT><<<ntiles, FIR_THREADS, 0, d.stream>>>(raw, n, d.cfg.agc_rate, need, d.tile_map.p);
+            k_agc_scan<<<1, 1024, 0, d.stream>>>(d.tile_map.p, ntiles, &S->gain[cur], need, d.seeds.p, &S->agc_exact);
+        }
+        if (dump)
+            k_agc_fir<FMT, true><<<nranges, FIR_THREADS, 0, d.stream>>>(raw, n, d.cfg.agc_rate, &S->gain[cur], R, ctl, taps, S->agc_tail[cur],
+                                                                       S->agc_tail[cur ^ 1], fir_out, d.agc_dump.p, &S->gain[cur ^ 1], &S->flags);
+        else
+            k_agc_fir<FMT, false><<<nranges, FIR_THREADS, 0, d.stream>>>(raw, n, d.cfg.agc_rate, &S->gain[cur], R, ctl, taps, S->agc_tail[cur],
+                                                                        S->agc_tail[cur ^ 1], fir_out, nullptr, &S->gain[cur ^ 1], &S->flags);
+    }
+    d.launches += 4;
 }
 
 long Demod::process(const void *d_raw, long n, int8_t *soft_dst)
@@ -257,7 +292,7 @@ long Demod::process(const void *d_raw, long n, int8_t *soft_dst)
     DeviceGuard g(cfg.device);
     const int cur = parity, nxt = parity ^ 1;
     DemodDevState *S = st.p;
-    const int ntiles = (int)((n + FIR_TO - 1) / FIR_TO);
+    const int ntiles = (int)((n + FIR_TILE - 1) / FIR_TILE);
     FirTaps taps;
     memset(&taps, 0, sizeof(taps));
     for (int i = 0; i < FIR_NT; i++)
@@ -406,6 +441,7 @@ void Demod::stats(b200_demod_stats *o)
     o->agc_clamped = h_state->flags & 1;
     o->repairs = h_state->repairs;
     o->kernel_launches = launches;
+    o->agc_exact_passes = h_state->agc_exact;
 }
 
 } // namespace b200

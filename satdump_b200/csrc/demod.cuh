@@ -26,9 +26,10 @@ namespace b200
 {
 
 constexpr int FIR_NT = 31;           // taps
-constexpr int FIR_TO = 2016;         // outputs per CTA
-constexpr int FIR_TL = 2048;         // samples loaded per CTA (32 halo + 2016)
+constexpr int FIR_TILE = 2048;       // samples (= outputs) per tile: 256 threads x 8
 constexpr int FIR_THREADS = 256;
+constexpr int FIR_BUF = FIR_TILE + 32;                   // smem tile with the 32-sample history in front
+constexpr int FIR_BUF_F2 = FIR_BUF + 2 * (FIR_BUF / 8);  // padded (see xidx)
 constexpr int SEG_THREADS = 128;     // threads (= stream segments) per CTA in the loop kernels
 constexpr int MM_BANK_STRIDE = 9; // floats per arm row in smem: spreads the per-thread random arm reads over the banks
 constexpr int MM_SMEM_BYTES = 64 * SEG_THREADS * 8 + 128 * MM_BANK_STRIDE * 4;
@@ -36,30 +37,20 @@ constexpr int MM_SMEM_BYTES = 64 * SEG_THREADS * 8 + 128 * MM_BANK_STRIDE * 4;
 struct FirTaps { float h[32]; };
 
 struct Affine { double a, b; };     // g -> a*g + b
-#ifdef B200_DEFINE_KERNELS
-__device__ __forceinline__ Affine compose(const Affine &first, const Affine &second)
-{
-    Affine r;
-    r.a = second.a * first.a;
-    r.b = fma(second.a, first.b, second.b);
-    return r;
-}
 
-#endif // B200_DEFINE_KERNELS
 template <int FMT> struct RawBytes;
 template <> struct RawBytes<0> { static constexpr int v = 8; };
 template <> struct RawBytes<1> { static constexpr int v = 4; };
 template <> struct RawBytes<2> { static constexpr int v = 2; };
 
-// x / d for a small integer-valued x, correctly rounded (= the generic VOLK converters' ((float)x) / scalar)
-// without the ~10-instruction IEEE division: q = x * (1/d) is within 1 ulp; one FMA residual step makes it the correctly rounded
-// quotient (tests/test_gpu_demod.py checks all 65 536 / 256 inputs bit for bit).
-__device__ __forceinline__ float div_exact(float x, float d, float rd)
-{
-    const float q = x * rd;
-    const float r = fmaf(-q, d, x);
-    return fmaf(r, rd, q);
-}
+// x / (2^B - 1) for an integer x of at most B bits, correctly rounded (= the generic VOLK converters' ((float)x) / scalar,
+// SURVEY.md App. A.1) in two instructions. 1/(2^B-1) = 2^-B + 2^-2B + 2^-3B + ..., so with t = x*2^-B (exact) and
+// c = 2^-2B + ... + 2^-mB (exact in a float), fma(x, c, t) is the single rounding of the series cut after m terms. The cut-off
+// tail is below 2^-45 (cs16, m=3) / 2^-35 (cs8, m=5) of the quotient, and no rounding boundary can lie that close: a midpoint M
+// with |x/(2^B-1) - M| that small would force x*2^k == odd*(2^B-1) with x*2^k even. tests/test_gpu_demod.py checks all 65 536 /
+// 256 inputs bit for bit against the division.
+__device__ __forceinline__ float cvt_s16(float x) { return fmaf(x, 0x1p-30f + 0x1p-45f, x * 0x1p-15f); }
+__device__ __forceinline__ float cvt_s8(float x) { return fmaf(x, 0x1p-14f + 0x1p-21f + 0x1p-28f + 0x1p-35f, x * 0x1p-7f); }
 
 // load 8 consecutive complex samples starting at sample index s0 (multiple of 8 relative to a 16-aligned base) and convert
 #ifdef B200_DEFINE_KERNELS
@@ -73,8 +64,8 @@ __device__ __forceinline__ void load8(const void *__restrict__ raw, long s0, lon
             int w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
             for (int i = 0; i < 8; i++) {
-                x[i].x = div_exact((float)(short)(w[i] & 0xFFFF), 32767.0f, 1.0f / 32767.0f);
-                x[i].y = div_exact((float)(short)(w[i] >> 16), 32767.0f, 1.0f / 32767.0f);
+                x[i].x = cvt_s16((float)(short)(w[i] & 0xFFFF));
+                x[i].y = cvt_s16((float)(short)(w[i] >> 16));
             }
         } else if (FMT == 2) {
             const int4 *p = reinterpret_cast<const int4 *>(reinterpret_cast<const int8_t *>(raw) + 2 * s0);
@@ -82,10 +73,10 @@ __device__ __forceinline__ void load8(const void *__restrict__ raw, long s0, lon
             int w[4] = {v0.x, v0.y, v0.z, v0.w};
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                x[2 * i].x = div_exact((float)(signed char)(w[i] & 0xFF), 127.0f, 1.0f / 127.0f);
-                x[2 * i].y = div_exact((float)(signed char)((w[i] >> 8) & 0xFF), 127.0f, 1.0f / 127.0f);
-                x[2 * i + 1].x = div_exact((float)(signed char)((w[i] >> 16) & 0xFF), 127.0f, 1.0f / 127.0f);
-                x[2 * i + 1].y = div_exact((float)(signed char)((w[i] >> 24) & 0xFF), 127.0f, 1.0f / 127.0f);
+                x[2 * i].x = cvt_s8((float)(signed char)(w[i] & 0xFF));
+                x[2 * i].y = cvt_s8((float)(signed char)((w[i] >> 8) & 0xFF));
+                x[2 * i + 1].x = cvt_s8((float)(signed char)((w[i] >> 16) & 0xFF));
+                x[2 * i + 1].y = cvt_s8((float)(signed char)((w[i] >> 24) & 0xFF));
             }
         } else {
             const float4 *p = reinterpret_cast<const float4 *>(reinterpret_cast<const float2 *>(raw) + s0);
@@ -104,12 +95,12 @@ __device__ __forceinline__ void load8(const void *__restrict__ raw, long s0, lon
             if (s < n_valid) {
                 if (FMT == 1) {
                     const int16_t *p = reinterpret_cast<const int16_t *>(raw) + 2 * s;
-                    v.x = div_exact((float)p[0], 32767.0f, 1.0f / 32767.0f);
-                    v.y = div_exact((float)p[1], 32767.0f, 1.0f / 32767.0f);
+                    v.x = cvt_s16((float)p[0]);
+                    v.y = cvt_s16((float)p[1]);
                 } else if (FMT == 2) {
                     const int8_t *p = reinterpret_cast<const int8_t *>(raw) + 2 * s;
-                    v.x = div_exact((float)p[0], 127.0f, 1.0f / 127.0f);
-                    v.y = div_exact((float)p[1], 127.0f, 1.0f / 127.0f);
+                    v.x = cvt_s8((float)p[0]);
+                    v.y = cvt_s8((float)p[1]);
                 } else
                     v = reinterpret_cast<const float2 *>(raw)[s];
             }
@@ -130,16 +121,33 @@ __global__ void k_convert_only(const void *__restrict__ raw, long N, float2 *__r
         if (s0 + i < N) out[s0 + i] = x[i];
 }
 
-// affine map of one AGC step for input sample x:  g' = g*(1 - rate*|x|) + rate*ref   (agc.cpp:30-33 rewritten)
-__device__ __forceinline__ float fast_mag(float s2) { return s2 > 0.f ? s2 * rsqrtf(s2) : 0.f; }
-
-__device__ __forceinline__ Affine agc_map(float2 x, float rate)
+// sqrt(s2) as s2 * rsqrt(s2): one MUFU + one FMUL (~2 ulp); the max() keeps 0 * inf out (s2 == 0 -> 0)
+__device__ __forceinline__ float fast_mag(float s2)
 {
-    float mag = fast_mag(x.x * x.x + x.y * x.y);
-    Affine m;
-    m.a = 1.0 - (double)rate * (double)mag;
-    m.b = (double)rate;
-    return m;
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaxf(s2, 1e-36f)));
+    return s2 * r;
+}
+
+// One AGC step (agc.cpp:30-33) for input x is the affine map g' = g*(1 - e) + rate with e = rate*|x| (exact while the clamp is
+// not hit). Inside a tile a composed map is carried as the float pair (E, B): g -> g*(1 - E) + B. Keeping E = 1 - a rather than
+// a keeps the *relative* precision of the decay for weak signals (e ~ 1e-5), so float is enough here: the composition depth on
+// any path is ~20 and a seed error decays by (1 - e) per sample anyway. Across tiles the maps are composed in fp64.
+struct EB { float E, B; };
+__device__ __forceinline__ EB eb_compose(const EB first, const EB second)
+{
+    EB r;
+    r.B = fmaf(-second.E, first.B, first.B + second.B);
+    r.E = fmaf(-first.E, second.E, first.E + second.E);
+    return r;
+}
+
+__device__ __forceinline__ Affine compose(const Affine &first, const Affine &second)
+{
+    Affine r;
+    r.a = second.a * first.a;
+    r.b = fma(second.a, first.b, second.b);
+    return r;
 }
 
 __device__ __forceinline__ Affine warp_scan_inclusive(Affine v, int lane)
@@ -156,29 +164,298 @@ __device__ __forceinline__ Affine warp_scan_inclusive(Affine v, int lane)
     return v;
 }
 
-// Tile geometry shared by k_agc_compose and k_agc_fir: tile k holds local samples 0..2047 <-> stream samples
-// lstart+i with lstart = k*FIR_TO - 32. Its AGC seed is the gain before local sample (k==0 ? 32 : 0); tile 0's first
-// 32 local samples are the previous batch's AGC outputs (FIR history), not scanned.
-__device__ __forceinline__ long tile_lstart(int k) { return (long)k * FIR_TO - 32; }
+// smem index (float2 units): 8 samples + 16 B pad per group -> 16-byte aligned, conflict-free 128-bit accesses at a thread
+// stride of 8 samples
+__device__ __forceinline__ int xidx(int i) { return i + 2 * (i >> 3); }
 
-// ---------------------------------------------------------------- K0a: per-tile affine composition
-template <int FMT>
-__global__ void __launch_bounds__(FIR_THREADS) k_agc_compose(const void *__restrict__ raw, long N, float rate, Affine *__restrict__ tile_map)
+// composed AGC map of 8 samples (all valid)
+__device__ __forceinline__ EB agc_map8(const float2 (&x)[8], float rate)
 {
-    const int k = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const long lstart = tile_lstart(k);
-    __shared__ Affine wsum[FIR_THREADS / 32];
-    Affine m{1.0, 0.0};
-    // tile k's map covers stream samples [seed_pos(k), seed_pos(k+1)) = local [k?0:32, 2016)
-    const int l0 = 8 * t;
-    if (l0 < FIR_TO && (k > 0 || l0 >= 32)) {
-        float2 x[8];
-        load8<FMT>(raw, lstart + l0, N, x);
+    EB m{0.f, 0.f};
 #pragma unroll
-        for (int i = 0; i < 8; i++)
-            if (lstart + l0 + i < N)
-                m = compose(m, agc_map(x[i], rate));
+    for (int i = 0; i < 8; i++) {
+        const float e = rate * fast_mag(fmaf(x[i].x, x[i].x, x[i].y * x[i].y));
+        m.B = fmaf(-e, m.B, m.B + rate);
+        m.E = fmaf(-m.E, e, m.E + e);
     }
+    return m;
+}
+
+// Control block of the AGC seeding. need[epoch & 1] is raised by the fast pass when some range cannot prove its seed; the exact
+// pass (k_agc_compose, k_agc_scan, k_agc_fir with seeded = 1) then runs, otherwise those launches return at once.
+struct AgcCtl
+{
+    const double *seeds; // [ntiles + 1] gain before every tile (exact pass only)
+    int *need;           // [2], indexed by launch parity; the fast pass clears the other one for the next batch
+    unsigned epoch;
+    int seeded;
+    int warm_max;        // fast pass: how many tiles a range may walk back before giving up
+};
+
+// ---------------------------------------------------------------- K1: convert + AGC + 31-tap FIR
+// The AGC gain is a serial recurrence over the whole stream (agc.cpp:25-39). The stream is cut into `ranges` of R consecutive
+// 2048-sample tiles, one persistent CTA per range, so inside a range the gain simply chains from tile to tile (each tile: affine
+// maps of the 8-sample groups -> CTA scan -> every thread replays the reference's float recurrence over its 8 samples from its
+// scanned seed). What a range needs from the past is its start gain. Because the loop is a contraction that gain is a function
+// of the preceding samples only up to a weight A = prod(1 - rate|x|) on whatever came before: the CTA walks backwards tile by
+// tile composing the maps until A * max_gain is below float resolution of the seed (normally 2-8 tiles, each a cheap map-only
+// pass), which PROVES the seed to ~1e-9 without knowing anything older; if warm_max tiles do not suffice (very weak signal) it
+// raises `need` and the exact pass redoes the stage from scanned per-tile seeds. One more tile before the range is replayed
+// without output to provide the 30-sample FIR history.
+// gain_out: gain after the last sample; flags bit0 = AGC clamp hit
+template <int FMT, bool DUMP>
+__global__ void __launch_bounds__(FIR_THREADS, 5) k_agc_fir(const void *__restrict__ raw, long N, float rate, const float *__restrict__ gain_in, int R,
+                                                         const AgcCtl ctl, const FirTaps taps, const float2 *__restrict__ tail_in,
+                                                         float2 *__restrict__ tail_out, float2 *__restrict__ fir_out, float2 *__restrict__ agc_dump,
+                                                         float *__restrict__ gain_out, int *__restrict__ flags)
+{
+    __shared__ __align__(16) float2 xs[2][FIR_BUF_F2];
+    __shared__ EB wsum[2][FIR_THREADS / 32];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    int *need = ctl.need + (ctl.epoch & 1);
+    if (ctl.seeded) {
+        if (*need == 0)
+            return;
+    } else if (blockIdx.x == 0 && t == 0)
+        ctl.need[(ctl.epoch & 1) ^ 1] = 0;
+    const int ntiles = (int)((N + FIR_TILE - 1) / FIR_TILE);
+    const int first = blockIdx.x * R;
+    if (first >= ntiles)
+        return;
+    const int last = min(first + R, ntiles);
+    int par = 0, buf = 0, i0 = first;
+    double G; // gain before the next tile to run
+    if (first == 0) {
+        G = (double)*gain_in;
+        if (t < 4) { // FIR history: the previous batch's last 32 AGC outputs
+            float4 *dst = reinterpret_cast<float4 *>(&xs[0][xidx(8 * t)]);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const float2 u = tail_in[8 * t + 2 * i], v = tail_in[8 * t + 2 * i + 1];
+                dst[i] = make_float4(u.x, u.y, v.x, v.y);
+            }
+        }
+    } else {
+        i0 = first - 1;
+        if (ctl.seeded)
+            G = ctl.seeds[i0];
+        else {
+            double A = 1.0, Bc = 0.0; // composition of the tiles walked so far: g(i0 start) = A * g(older) + Bc
+            bool ok = false;
+            for (int j = i0 - 1, w = 0;; j--, w++) {
+                if (j < 0) { // reached the batch start: the carried gain is exact
+                    Bc = fma(A, (double)*gain_in, Bc);
+                    ok = true;
+                    break;
+                }
+                if (w >= ctl.warm_max)
+                    break;
+                float2 x[8];
+                load8<FMT>(raw, (long)j * FIR_TILE + 8 * t, N, x);
+                EB m = agc_map8(x, rate);
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) { // lane l <- groups [l, l + 2*off)
+                    EB o;
+                    o.E = __shfl_down_sync(0xffffffffu, m.E, off);
+                    o.B = __shfl_down_sync(0xffffffffu, m.B, off);
+                    if (lane + off < 32)
+                        m = eb_compose(m, o);
+                }
+                if (lane == 0)
+                    wsum[par][warp] = m;
+                __syncthreads();
+                EB tot = wsum[par][0];
+#pragma unroll
+                for (int w2 = 1; w2 < FIR_THREADS / 32; w2++)
+                    tot = eb_compose(tot, wsum[par][w2]);
+                par ^= 1;
+                Bc = fma(A, (double)tot.B, Bc);
+                A *= 1.0 - (double)tot.E;
+                // anything older enters as A * gain with gain <= 2^16: done once that is below float resolution of the seed
+                if (A * 65536.0 <= Bc * 0x1p-30) {
+                    ok = true;
+                    break;
+                }
+            }
+            if (!ok) {
+                if (t == 0)
+                    atomicOr(need, 1);
+                return;
+            }
+            G = Bc;
+        }
+    }
+
+    for (int i = i0; i < last; i++) {
+        const bool out = i >= first; // tile first-1 only provides the FIR history
+        const long s0 = (long)i * FIR_TILE + 8 * t;
+        const bool interior = (long)(i + 1) * FIR_TILE + 32 <= N && !DUMP; // every sample exists, none is in the stream tail
+        float2 x[8];
+        load8<FMT>(raw, s0, N, x);
+        EB inc{0.f, 0.f};
+        if (interior)
+            inc = agc_map8(x, rate);
+        else {
+#pragma unroll
+            for (int q = 0; q < 8; q++)
+                if (s0 + q < N) {
+                    const float e = rate * fast_mag(fmaf(x[q].x, x[q].x, x[q].y * x[q].y));
+                    inc.B = fmaf(-e, inc.B, inc.B + rate);
+                    inc.E = fmaf(-inc.E, e, inc.E + e);
+                }
+        }
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            EB p;
+            p.E = __shfl_up_sync(0xffffffffu, inc.E, off);
+            p.B = __shfl_up_sync(0xffffffffu, inc.B, off);
+            if (lane >= off)
+                inc = eb_compose(p, inc);
+        }
+        if (lane == 31)
+            wsum[par][warp] = inc;
+        __syncthreads();
+        // every warp scans the 8 warp aggregates (lanes 0-7 hold them, the rest mirror)
+        EB wv = wsum[par][lane & 7];
+        par ^= 1;
+#pragma unroll
+        for (int off = 1; off < 8; off <<= 1) {
+            EB p;
+            p.E = __shfl_up_sync(0xffffffffu, wv.E, off, 8);
+            p.B = __shfl_up_sync(0xffffffffu, wv.B, off, 8);
+            if ((lane & 7) >= off)
+                wv = eb_compose(p, wv);
+        }
+        EB tot, excl{0.f, 0.f};
+        tot.E = __shfl_sync(0xffffffffu, wv.E, 7);
+        tot.B = __shfl_sync(0xffffffffu, wv.B, 7);
+        {
+            EB p;
+            p.E = __shfl_sync(0xffffffffu, wv.E, (warp + 7) & 7);
+            p.B = __shfl_sync(0xffffffffu, wv.B, (warp + 7) & 7);
+            if (warp > 0)
+                excl = p;
+            p.E = __shfl_up_sync(0xffffffffu, inc.E, 1);
+            p.B = __shfl_up_sync(0xffffffffu, inc.B, 1);
+            if (lane > 0)
+                excl = eb_compose(excl, p);
+        }
+        // replay the reference's recurrence over this thread's 8 samples from the scanned seed. The reference evaluates
+        // gain + rate*(1 - sqrt(.)) in double and rounds to float; 1 - mag is exact in float for mag in [0.5, 2] and the FMA rounds
+        // once, so this differs from the double evaluation only through the ~1 ulp of mag.
+        const float Gf = (float)G;
+        float g = fmaf(-excl.E, Gf, Gf) + excl.B;
+        G = fma(1.0 - (double)tot.E, G, (double)tot.B);
+        float gmax = g;
+        if (interior) {
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const float2 o = make_float2(x[q].x * g, x[q].y * g);
+                const float mag = fast_mag(__fadd_rn(__fmul_rn(o.x, o.x), __fmul_rn(o.y, o.y)));
+                g = fmaf(rate, 1.0f - mag, g);
+                gmax = fmaxf(gmax, g);
+                x[q] = o;
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const long s = s0 + q;
+                float2 o = make_float2(x[q].x * g, x[q].y * g);
+                if (s < N) {
+                    const float mag = fast_mag(__fadd_rn(__fmul_rn(o.x, o.x), __fmul_rn(o.y, o.y)));
+                    g = fmaf(rate, 1.0f - mag, g);
+                    gmax = fmaxf(gmax, g);
+                    g = fminf(g, 65536.0f);
+                    if (out) {
+                        if (DUMP)
+                            agc_dump[s] = o;
+                        if (s >= N - 32)
+                            tail_out[s - (N - 32)] = o;
+                        if (s == N - 1)
+                            *gain_out = g;
+                    }
+                }
+                x[q] = o;
+            }
+        }
+        if (gmax > 65536.0f)
+            atomicOr(flags, 1);
+        {
+            float4 *dst = reinterpret_cast<float4 *>(&xs[buf][xidx(32 + 8 * t)]);
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                dst[q] = make_float4(x[2 * q].x, x[2 * q].y, x[2 * q + 1].x, x[2 * q + 1].y);
+            if (t >= FIR_THREADS - 4) { // the last 32 samples are the next tile's history
+                float4 *h = reinterpret_cast<float4 *>(&xs[buf ^ 1][xidx(8 * (t - (FIR_THREADS - 4)))]);
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    h[q] = make_float4(x[2 * q].x, x[2 * q].y, x[2 * q + 1].x, x[2 * q + 1].y);
+            }
+        }
+        __syncthreads();
+
+        // FIR: thread t -> outputs 8t .. 8t+7 of the tile; y[n] = sum_j x[n-30+j] * h[30-j], oldest first (fir.cpp:74-83)
+        if (out) {
+            // packed FP32x2: one FFMA2 does the (re, im) pair of a complex sample x real tap MAC (two independent fma.rn, i.e. the
+            // same results as scalar fmaf); the tap is a scalar broadcast operand. 31 FFMA2 per output sample instead of 62 FFMA.
+            unsigned long long acc[8];
+#pragma unroll
+            for (int o = 0; o < 8; o++)
+                acc[o] = 0ull;
+            const int fi = 8 * t + 2; // buffer index of the oldest input of output 0 (even: 16-byte aligned pairs)
+#pragma unroll
+            for (int pI = 0; pI < 19; pI++) {
+                const ulonglong2 vv = *reinterpret_cast<const ulonglong2 *>(&xs[buf][xidx(fi + 2 * pI)]);
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const unsigned long long v = h ? vv.y : vv.x;
+                    const int mI = 2 * pI + h;
+#pragma unroll
+                    for (int o = 0; o < 8; o++) {
+                        const int j = mI - o; // tap position (0 = oldest)
+                        if (j >= 0 && j < FIR_NT) {
+                            unsigned long long hh;
+                            asm("mov.b64 %0, {%1, %1};" : "=l"(hh) : "f"(taps.h[FIR_NT - 1 - j]));
+                            asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[o]) : "l"(v), "l"(hh));
+                        }
+                    }
+                }
+            }
+            if (s0 + 8 <= N) {
+                ulonglong2 *p = reinterpret_cast<ulonglong2 *>(fir_out + s0);
+#pragma unroll
+                for (int o = 0; o < 4; o++)
+                    p[o] = make_ulonglong2(acc[2 * o], acc[2 * o + 1]);
+            } else {
+#pragma unroll
+                for (int o = 0; o < 8; o++)
+                    if (s0 + o < N)
+                        *reinterpret_cast<unsigned long long *>(fir_out + s0 + o) = acc[o];
+            }
+        }
+        buf ^= 1;
+    }
+}
+
+// ---------------------------------------------------------------- exact pass (weak signals): per-tile maps -> scan -> seeds
+template <int FMT>
+__global__ void __launch_bounds__(FIR_THREADS) k_agc_compose(const void *__restrict__ raw, long N, float rate, const int *__restrict__ need,
+                                                             Affine *__restrict__ tile_map)
+{
+    if (*need == 0)
+        return;
+    const int k = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    __shared__ Affine wsum[FIR_THREADS / 32];
+    const long s0 = (long)k * FIR_TILE + 8 * t;
+    Affine m{1.0, 0.0};
+    float2 x[8];
+    load8<FMT>(raw, s0, N, x);
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+        if (s0 + i < N) {
+            const float mag = fast_mag(fmaf(x[i].x, x[i].x, x[i].y * x[i].y));
+            m = compose(m, Affine{1.0 - (double)rate * (double)mag, (double)rate});
+        }
     m = warp_scan_inclusive(m, lane);
     if (lane == 31)
         wsum[warp] = m;
@@ -191,10 +468,13 @@ __global__ void __launch_bounds__(FIR_THREADS) k_agc_compose(const void *__restr
     }
 }
 
-// ---------------------------------------------------------------- K0b: scan over tiles -> gain seed of every tile
 __global__ void __launch_bounds__(1024) k_agc_scan(const Affine *__restrict__ tile_map, int ntiles, const float *__restrict__ gain_in,
-                                                  double *__restrict__ seeds)
+                                                  const int *__restrict__ need, double *__restrict__ seeds, int *__restrict__ exact_count)
 {
+    if (*need == 0)
+        return;
+    if (threadIdx.x == 0)
+        *exact_count += 1;
     __shared__ Affine wsum[32];
     __shared__ double g_run;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -219,7 +499,6 @@ __global__ void __launch_bounds__(1024) k_agc_scan(const Affine *__restrict__ ti
         Affine pre{1.0, 0.0}; // composition of everything before this thread's tile in this round
         if (warp > 0)
             pre = wsum[warp - 1];
-        // exclusive = pre o (inclusive of previous lane)
         double ea = __shfl_up_sync(0xffffffffu, inc.a, 1), eb = __shfl_up_sync(0xffffffffu, inc.b, 1);
         Affine excl = pre;
         if (lane > 0)
@@ -236,135 +515,6 @@ __global__ void __launch_bounds__(1024) k_agc_scan(const Affine *__restrict__ ti
     }
     if (t == 0)
         seeds[ntiles] = g_run;
-}
-
-// padded smem index: conflict-free 64-bit accesses at a thread stride of 8 samples
-__device__ __forceinline__ int pidx(int i) { return i + (i >> 3); }
-
-// ---------------------------------------------------------------- K1: convert + AGC + 31-tap FIR
-// state_io[0] = carried gain (in: unused here, out: gain after the last sample), flags: bit0 = AGC clamp hit
-template <int FMT, bool DUMP>
-__global__ void __launch_bounds__(FIR_THREADS) k_agc_fir(const void *__restrict__ raw, long N, float rate, const double *__restrict__ seeds,
-                                                         const FirTaps taps, const float2 *__restrict__ tail_in, float2 *__restrict__ tail_out,
-                                                         float2 *__restrict__ fir_out, float2 *__restrict__ agc_dump, float *__restrict__ gain_out,
-                                                         int *__restrict__ flags)
-{
-    __shared__ float2 xs[FIR_TL + FIR_TL / 8 + 8];
-    __shared__ Affine wsum[FIR_THREADS / 32];
-    const int k = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const long lstart = tile_lstart(k);
-    const int l0 = 8 * t;
-    const bool hist = (k == 0 && l0 < 32); // previous batch's AGC outputs, passed through
-    float2 x[8];
-    Affine m{1.0, 0.0};
-    if (hist) {
-#pragma unroll
-        for (int i = 0; i < 8; i++)
-            x[i] = tail_in[l0 + i];
-    } else {
-        load8<FMT>(raw, lstart + l0, N, x);
-#pragma unroll
-        for (int i = 0; i < 8; i++)
-            if (lstart + l0 + i < N)
-                m = compose(m, agc_map(x[i], rate));
-    }
-    Affine inc = warp_scan_inclusive(m, lane);
-    if (lane == 31)
-        wsum[warp] = inc;
-    __syncthreads();
-    Affine pre{1.0, 0.0};
-    for (int w = 0; w < warp; w++)
-        pre = compose(pre, wsum[w]);
-    double ea = __shfl_up_sync(0xffffffffu, inc.a, 1), eb = __shfl_up_sync(0xffffffffu, inc.b, 1);
-    Affine excl = pre;
-    if (lane > 0)
-        excl = compose(pre, Affine{ea, eb});
-    if (!hist) {
-        // replay the reference's float recurrence over this thread's 8 samples from the scanned seed
-        float g = (float)fma(excl.a, seeds[k], excl.b);
-        bool clamped = false;
-        if (lstart + FIR_TL + 32 <= N && !DUMP) { // interior tile: every sample exists, none is in the stream tail
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const float2 o = make_float2(x[i].x * g, x[i].y * g);
-                const float mag = fast_mag(__fadd_rn(__fmul_rn(o.x, o.x), __fmul_rn(o.y, o.y)));
-                g = (float)((double)g + (double)rate * (1.0 - (double)mag));
-                clamped |= g > 65536.0f;
-                x[i] = o;
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                long s = lstart + l0 + i;
-                float2 o = make_float2(x[i].x * g, x[i].y * g);
-                if (s < N) {
-                    float mag = fast_mag(__fadd_rn(__fmul_rn(o.x, o.x), __fmul_rn(o.y, o.y)));
-                    g = (float)((double)g + (double)rate * (1.0 - (double)mag));
-                    if (g > 65536.0f) {
-                        g = 65536.0f;
-                        clamped = true;
-                    }
-                    if (DUMP)
-                        agc_dump[s] = o;
-                    if (s >= N - 32)
-                        tail_out[s - (N - 32)] = o;
-                    if (s == N - 1)
-                        *gain_out = g;
-                }
-                x[i] = o;
-            }
-        }
-        if (clamped)
-            atomicOr(flags, 1);
-    } else if (N < 32) {
-        // degenerate tiny batch: keep the still-needed part of the old history in the new tail
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-            long d = (long)(l0 + i) - N; // old tail index l0+i moves to position l0+i-N
-            if (d >= 0)
-                tail_out[d] = x[i];
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < 8; i++)
-        xs[pidx(l0 + i)] = x[i];
-    __syncthreads();
-
-    // FIR: thread t (< 252) -> outputs local 32+8t .. +7 ; y[i] = sum_j x[i-30+j] * h[30-j], oldest first (fir.cpp:74-83)
-    if (t < FIR_TO / 8) {
-        // packed FP32x2: one FFMA2 does the (re, im) pair of a complex sample x real tap MAC (two independent fma.rn, i.e. the same
-        // results as scalar fmaf); the tap is a scalar broadcast operand. 31 FFMA2 per output sample instead of 62 FFMA.
-        unsigned long long acc[8];
-#pragma unroll
-        for (int o = 0; o < 8; o++)
-            acc[o] = 0ull;
-        const int first = 8 * t + 2; // local index of the oldest input of output 0
-#pragma unroll
-        for (int mI = 0; mI < 38; mI++) {
-            const unsigned long long v = *reinterpret_cast<const unsigned long long *>(&xs[pidx(first + mI)]);
-#pragma unroll
-            for (int o = 0; o < 8; o++) {
-                const int j = mI - o; // tap position (0 = oldest)
-                if (j >= 0 && j < FIR_NT) {
-                    unsigned long long hh;
-                    asm("mov.b64 %0, {%1, %1};" : "=l"(hh) : "f"(taps.h[FIR_NT - 1 - j]));
-                    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[o]) : "l"(v), "l"(hh));
-                }
-            }
-        }
-        const long s0 = (long)k * FIR_TO + 8 * t;
-        if (s0 + 8 <= N) {
-            ulonglong2 *p = reinterpret_cast<ulonglong2 *>(fir_out + s0);
-#pragma unroll
-            for (int o = 0; o < 4; o++)
-                p[o] = make_ulonglong2(acc[2 * o], acc[2 * o + 1]);
-        } else {
-#pragma unroll
-            for (int o = 0; o < 8; o++)
-                if (s0 + o < N)
-                    *reinterpret_cast<unsigned long long *>(fir_out + s0 + o) = acc[o];
-        }
-    }
 }
 
 // ---------------------------------------------------------------- cp.async helpers (8-byte granules)

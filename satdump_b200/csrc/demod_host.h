@@ -21,6 +21,7 @@ struct DemodDevState
     int costas_unconv;  // junctions still unconverged after the repair rounds of the last batch
     int mm_unconv;
     int repairs;        // segments re-run as exact continuations so far (all batches)
+    int agc_exact;      // batches that needed the exact AGC pass so far
 };
 
 class Demod
@@ -55,8 +56,12 @@ class Demod
     int pf_next_buf = 0;
     DevBuf<float2> bufA, bufB, agc_dump, fir_dump, slots, sym_out;
     DevBuf<int8_t> soft;
-    DevBuf<Affine> tile_map;
-    DevBuf<double> seeds;
+    DevBuf<Affine> tile_map;       // exact AGC pass (weak signals): per-tile maps,
+    DevBuf<double> seeds;          // gain before every tile
+    DevBuf<int> agc_need;          // [2] raised by the fast pass when a range cannot prove its seed
+    unsigned agc_epoch = 0;
+    int fir_ctas = 0;              // resident k_agc_fir CTAs on the device (one wave of ranges)
+    int agc_warm_max = 24;
     DevBuf<LoopRec> crec;
     DevBuf<MMRec> mrec;
     DevBuf<uint8_t> quad;
