@@ -165,7 +165,16 @@ def main():
         ch.frames_device()
         return ch.timing()["push_events"]  # ms, CUDA events on the chain's own streams (torch events cannot see them)
 
-    out_host = torch.empty(max_soft // 8 + (1 << 20), dtype=torch.uint8, pin_memory=True)  # the caller-owned CADU buffer
+    out_host = torch.empty(2 * (max_soft // 8) + (1 << 20), dtype=torch.uint8, pin_memory=True)  # the caller-owned CADU buffer (two batches of CADUs)
+
+    def drain():
+        ch.sync()
+        total = 0
+        while True:
+            nb = ch.pull_into(out_host.data_ptr(), out_host.numel())
+            if nb == 0:
+                return total
+            total += nb
 
     def step_host(prefetch_next=False):
         ch.reset()
@@ -182,32 +191,61 @@ def main():
     nfr = fr.shape[0]
     first = next((i for i in range(min(64, clear.shape[0])) if np.array_equal(clear[i], fr[0])), None) if nfr else None
     frames_ok = first is not None and nfr > 0 and np.array_equal(fr, clear[first:first + nfr])
-    launches0 = sum(s["kernel_launches"] for s in ch.stats())
 
     sampler = ClockSampler(local)
     sampler.start()
-    # ---- value: inputs resident in HBM
+    # ---- per-kernel / per-stage times: one synchronous push (each kernel alone on the GPU), CUDA events on the chain's own streams
+    barrier()
+    sync_ms = 0.0
+    for _ in range(args.steps):
+        sync_ms += step_dev()
+    tim = ch.timing()
+    sync_ms /= args.steps
+    # ---- value: inputs resident in HBM, pipelined chain (decoder one batch behind the demodulator on its own stream / thread,
+    # the reference's one-thread-per-module model). Every step is a fresh stream (reset), K steps + drain inside the stopwatch.
+    ch.set_pipelined(True)
+    for _ in range(2):  # warm the pipelined path (staging buffers, worker thread)
+        ch.reset()
+        ch.push_device(raw.data_ptr(), n)
+        ch.pull_into(out_host.data_ptr(), out_host.numel())
+    drain()
+    launches0 = sum(s["kernel_launches"] for s in ch.stats())
     barrier()
     t0 = time.perf_counter()
-    ev_ms = 0.0
+    ch.span_begin()
+    nb_dev, checked = 0, False
     for _ in range(args.steps):
-        ev_ms += step_dev()
-    torch.cuda.synchronize()
+        ch.reset()
+        ch.push_device(raw.data_ptr(), n)
+        nb = ch.pull_into(out_host.data_ptr(), out_host.numel())  # CADUs of the batches decoded so far (keeps the output buffer drained)
+        if nb and not checked:
+            checked = True
+            frames_ok = frames_ok and np.array_equal(out_host[:nfr * 1024].numpy().reshape(-1, 1024), clear[first:first + nfr])
+        nb_dev += nb
+    wall_dev = ch.span_end() * 1e-3  # CUDA events: demodulator stream at the start -> decoder stream after the drain
     wall_dev_host = time.perf_counter() - t0
-    wall_dev = ev_ms * 1e-3  # device time of the K steps (sum of per-push event intervals)
-    tim = ch.timing()
+    nb_dev += drain()
+    frames_ok = frames_ok and nb_dev == args.steps * nfr * 1024
     launches1 = sum(s["kernel_launches"] for s in ch.stats())
     barrier()
-    # ---- e2e: host buffers, H2D + D2H inside
+    # ---- e2e: host buffers; H2D of step i+1, demodulation of step i and decoding of step i-1 overlap; D2H of the CADUs every step
     t0 = time.perf_counter()
     ch.prefetch_ptr(host.data_ptr(), n)  # the first batch's copy is inside the timed region
+    nb_e2e = 0
     for i in range(args.steps):
-        fr = step_host(prefetch_next=(i + 1 < args.steps))
+        ch.reset()
+        if i + 1 < args.steps:
+            ch.prefetch_ptr(host.data_ptr(), n)
+        ch.push_ptr(host.data_ptr(), n)
+        nb_e2e += ch.pull_into(out_host.data_ptr(), out_host.numel())  # CADUs decoded so far
+    nb_e2e += drain()
     torch.cuda.synchronize()
     wall_e2e = time.perf_counter() - t0
+    frames_ok = frames_ok and nb_e2e == args.steps * nfr * 1024
     barrier()
     sampler.stop_flag = True
     sampler.join(timeout=2)
+    ch.set_pipelined(False)
 
     t = torch.tensor([wall_dev, wall_e2e], dtype=torch.float64, device=dev)
     if world > 1:
@@ -231,15 +269,18 @@ def main():
                            "l2": "input batch (%.0f MiB) larger than L2" % (n * 4 / 2 ** 20), "esn0_db": cfg.esn0_db},
                 "e2e": {"value": e2e, "unit": "MS/s", "h2d_bytes_per_step": n * 4 * world, "d2h_bytes_per_step": int(nfr) * 1024 * world},
                 "gpu_launches": int(launches1 - launches0), "host_wall_ms_per_step": wall_dev_host / args.steps * 1e3,
-                "stage_ms_last_step": {k: round(v, 4) for k, v in tim.items() if k != "vit_chunks"},
+                "mode": "pipelined chain: decoder one batch behind the demodulator (own stream + worker thread); K fresh streams + drain inside the timed region",
+                "sync_mode": {"value": n * world / (sync_ms * 1e-3) / 1e6, "ms_per_step": sync_ms,
+                              "note": "same step with the decoder run after the demodulator on the calling thread (rank 0)"},
+                "stage_ms_sync_step": {k: round(v, 4) for k, v in tim.items() if k != "vit_chunks"},
                 "roofline": {"kernel": "k_vit_acs (warp-per-chunk add-compare-select, the longest kernel of the step)", "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
                              "frac": achieved / hbm, "traffic": measured_traffic("k_vit_acs", args.log2_samples), "peak_source": which,
-                             "note": "integer ACS kernel, issue/ALU bound (ncu: 85 % SM throughput, 2.7 % DRAM); its ncu DRAM traffic includes the 98 KB/chunk survivor decisions it hands to k_vit_tb"},
-                "roofline_fir_stage": {"kernels": "k_agc_compose + k_agc_scan + k_agc_fir", "bound": "hbm",
+                             "note": "timed alone (synchronous step); integer ACS kernel, issue/ALU bound (ncu: 85 % SM throughput, 2.7 % DRAM); its ncu DRAM traffic includes the 98 KB/chunk survivor decisions it hands to k_vit_tb"},
+                "roofline_fir_stage": {"kernels": "k_agc_fir (convert + AGC + 31-tap RRC in one pass; the exact-seed launches return at once)", "bound": "hbm",
                                        "achieved": n * 12 / (fir_ms * 1e-3) / 1e9 if fir_ms > 0 else 0.0, "peak": hbm, "unit": "GB/s",
                                        "frac": (n * 12 / (fir_ms * 1e-3) / 1e9 / hbm) if fir_ms > 0 else 0.0,
                                        "traffic_k_agc_fir": measured_traffic("k_agc_fir", args.log2_samples),
-                                       "note": "12 B/sample (cs16 in + cf32 out) over the event-timed sum of the three kernels; k_agc_fir alone: profiles/ncu_r1_final_summary.csv"},
+                                       "note": "12 B/sample (cs16 in + cf32 out) over the event-timed FIR stage of a synchronous step; FP32-pipe bound: 62 FMA + ~45 other lane-ops per sample put the stage above the fp32 ridge (DESIGN.md 6)"},
                 "clocks": sampler.summary(),
                 "stream_stats": {"demod": {k: v for k, v in ch.stats()[0].items() if k in ("costas_unconverged", "mm_unconverged", "repairs", "agc_clamped")},
                                  "fec": {k: v for k, v in ch.stats()[1].items() if k in ("replays", "rs_failed", "rs_corrected", "viterbi_state", "deframer_state")}}}

@@ -158,6 +158,17 @@ int b200_chain_get_stats(b200_chain *c, b200_demod_stats *ds, b200_fec_stats *fs
 int b200_chain_last_timing(b200_chain *c, float *ms_out, int n); /* n >= 9: [0]=sum of stages [1]=agc+fir [2]=costas(+rotate) [3]=m&m [4]=viterbi stage [5]=deframe+rs [6]=k_vit_main alone [7]=chunks it decoded [8]=whole push, event timed */
 /* forget the stream (loop state, lock, FIFOs) but keep every allocation: the next push starts a new stream */
 int b200_chain_reset(b200_chain *c);
+/* Pipelined mode: the decoder runs on a worker thread and its own CUDA stream one batch behind the demodulator, like the
+ * reference's one-thread-per-module pipeline (src-core/pipeline/pipeline_run.cpp:44-117) with a whole batch of soft symbols in HBM
+ * as the FIFO element. push(i) returns when batch i is demodulated and batch i-1 decoded; b200_chain_pull_frames() then returns
+ * the frames of the batches decoded so far without waiting for the one in flight; b200_chain_sync() waits for the decoder
+ * (after it, pull returns everything). Decoder errors surface at the next push / sync. Output is identical to the synchronous mode. */
+int b200_chain_set_pipelined(b200_chain *c, int on);
+int b200_chain_sync(b200_chain *c);
+/* CUDA-event stopwatch over several pushes (both streams): begin syncs the chain and stamps the demodulator's stream, end syncs
+ * and stamps the decoder's stream; *ms = elapsed device time */
+int b200_chain_span_begin(b200_chain *c);
+int b200_chain_span_end(b200_chain *c, float *ms);
 
 #ifdef __cplusplus
 }

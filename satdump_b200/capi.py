@@ -26,6 +26,7 @@ SYMBOLS = [
     "b200_fec_debug_bits", "b200_fec_get_stats", "b200_fec_cadu_bytes", "b200_fec_chunk_size",
     "b200_chain_create", "b200_chain_destroy", "b200_chain_push_iq", "b200_chain_push_iq_device", "b200_chain_prefetch_iq", "b200_chain_pull_frames",
     "b200_chain_frames_device", "b200_chain_get_stats", "b200_chain_last_timing", "b200_chain_reset",
+    "b200_chain_set_pipelined", "b200_chain_sync", "b200_chain_span_begin", "b200_chain_span_end",
 ]
 
 
@@ -107,6 +108,10 @@ def lib():
         L.b200_chain_get_stats.argtypes = [vp, C.POINTER(DemodStats), C.POINTER(FecStats)]
         L.b200_chain_last_timing.argtypes = [vp, vp, ci]
         L.b200_chain_reset.argtypes = [vp]
+        L.b200_chain_set_pipelined.argtypes = [vp, ci]
+        L.b200_chain_sync.argtypes = [vp]
+        L.b200_chain_span_begin.argtypes = [vp]
+        L.b200_chain_span_end.argtypes = [vp, C.POINTER(C.c_float)]
         _lib = L
     return _lib
 
@@ -329,6 +334,23 @@ class Chain:
         ms = np.zeros(9, np.float32)
         _chk(lib().b200_chain_last_timing(self.h, ms.ctypes.data, 9))
         return dict(zip(["stages_sum", "agc_fir", "costas", "mm", "viterbi", "deframe_rs", "k_vit_acs", "vit_chunks", "push_events"], ms.tolist()))
+
+    def set_pipelined(self, on=True):
+        """Decoder on a worker thread / own stream, one batch behind the demodulator; frames of a push appear after the next one
+        (or after sync())."""
+        _chk(lib().b200_chain_set_pipelined(self.h, 1 if on else 0))
+        return self
+
+    def sync(self):
+        _chk(lib().b200_chain_sync(self.h))
+
+    def span_begin(self):
+        _chk(lib().b200_chain_span_begin(self.h))
+
+    def span_end(self):
+        ms = C.c_float()
+        _chk(lib().b200_chain_span_end(self.h, C.byref(ms)))
+        return ms.value
 
     def reset(self):
         _chk(lib().b200_chain_reset(self.h))

@@ -52,61 +52,89 @@ template <> struct RawBytes<2> { static constexpr int v = 2; };
 __device__ __forceinline__ float cvt_s16(float x) { return fmaf(x, 0x1p-30f + 0x1p-45f, x * 0x1p-15f); }
 __device__ __forceinline__ float cvt_s8(float x) { return fmaf(x, 0x1p-14f + 0x1p-21f + 0x1p-28f + 0x1p-35f, x * 0x1p-7f); }
 
-// load 8 consecutive complex samples starting at sample index s0 (multiple of 8 relative to a 16-aligned base) and convert
+// 8 consecutive complex samples: raw registers (so a tile's loads can be issued one tile ahead) and their conversion
 #ifdef B200_DEFINE_KERNELS
+template <int FMT> struct RawRegs;
+template <> struct RawRegs<0> { float4 v[4]; };
+template <> struct RawRegs<1> { int4 a, b; };
+template <> struct RawRegs<2> { int4 a; };
+
+// requires s0 + 8 <= n_valid; s0 a multiple of 8 relative to a 16-aligned base
+template <int FMT> __device__ __forceinline__ void raw_fetch(const void *__restrict__ raw, long s0, RawRegs<FMT> &r)
+{
+    if constexpr (FMT == 1) {
+        const int4 *p = reinterpret_cast<const int4 *>(reinterpret_cast<const int16_t *>(raw) + 2 * s0);
+        r.a = __ldg(p);
+        r.b = __ldg(p + 1);
+    } else if constexpr (FMT == 2) {
+        r.a = __ldg(reinterpret_cast<const int4 *>(reinterpret_cast<const int8_t *>(raw) + 2 * s0));
+    } else {
+        const float4 *p = reinterpret_cast<const float4 *>(reinterpret_cast<const float2 *>(raw) + s0);
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            r.v[i] = __ldg(p + i);
+    }
+}
+
+template <int FMT> __device__ __forceinline__ void raw_convert(const RawRegs<FMT> &r, float2 (&x)[8])
+{
+    if constexpr (FMT == 1) {
+        const int w[8] = {r.a.x, r.a.y, r.a.z, r.a.w, r.b.x, r.b.y, r.b.z, r.b.w};
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            x[i].x = cvt_s16((float)(short)(w[i] & 0xFFFF));
+            x[i].y = cvt_s16((float)(short)(w[i] >> 16));
+        }
+    } else if constexpr (FMT == 2) {
+        const int w[4] = {r.a.x, r.a.y, r.a.z, r.a.w};
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            x[2 * i].x = cvt_s8((float)(signed char)(w[i] & 0xFF));
+            x[2 * i].y = cvt_s8((float)(signed char)((w[i] >> 8) & 0xFF));
+            x[2 * i + 1].x = cvt_s8((float)(signed char)((w[i] >> 16) & 0xFF));
+            x[2 * i + 1].y = cvt_s8((float)(signed char)((w[i] >> 24) & 0xFF));
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            x[2 * i] = make_float2(r.v[i].x, r.v[i].y);
+            x[2 * i + 1] = make_float2(r.v[i].z, r.v[i].w);
+        }
+    }
+}
+
+// samples beyond n_valid read as 0
+template <int FMT> __device__ __forceinline__ void load8_ragged(const void *__restrict__ raw, long s0, long n_valid, float2 (&x)[8])
+{
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        long s = s0 + i;
+        float2 v = make_float2(0.f, 0.f);
+        if (s < n_valid) {
+            if (FMT == 1) {
+                const int16_t *p = reinterpret_cast<const int16_t *>(raw) + 2 * s;
+                v.x = cvt_s16((float)p[0]);
+                v.y = cvt_s16((float)p[1]);
+            } else if (FMT == 2) {
+                const int8_t *p = reinterpret_cast<const int8_t *>(raw) + 2 * s;
+                v.x = cvt_s8((float)p[0]);
+                v.y = cvt_s8((float)p[1]);
+            } else
+                v = reinterpret_cast<const float2 *>(raw)[s];
+        }
+        x[i] = v;
+    }
+}
+
 template <int FMT>
 __device__ __forceinline__ void load8(const void *__restrict__ raw, long s0, long n_valid, float2 (&x)[8])
 {
     if (s0 + 8 <= n_valid) {
-        if (FMT == 1) {
-            const int4 *p = reinterpret_cast<const int4 *>(reinterpret_cast<const int16_t *>(raw) + 2 * s0);
-            int4 v0 = __ldg(p), v1 = __ldg(p + 1);
-            int w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                x[i].x = cvt_s16((float)(short)(w[i] & 0xFFFF));
-                x[i].y = cvt_s16((float)(short)(w[i] >> 16));
-            }
-        } else if (FMT == 2) {
-            const int4 *p = reinterpret_cast<const int4 *>(reinterpret_cast<const int8_t *>(raw) + 2 * s0);
-            int4 v0 = __ldg(p);
-            int w[4] = {v0.x, v0.y, v0.z, v0.w};
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                x[2 * i].x = cvt_s8((float)(signed char)(w[i] & 0xFF));
-                x[2 * i].y = cvt_s8((float)(signed char)((w[i] >> 8) & 0xFF));
-                x[2 * i + 1].x = cvt_s8((float)(signed char)((w[i] >> 16) & 0xFF));
-                x[2 * i + 1].y = cvt_s8((float)(signed char)((w[i] >> 24) & 0xFF));
-            }
-        } else {
-            const float4 *p = reinterpret_cast<const float4 *>(reinterpret_cast<const float2 *>(raw) + s0);
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                float4 v = __ldg(p + i);
-                x[2 * i] = make_float2(v.x, v.y);
-                x[2 * i + 1] = make_float2(v.z, v.w);
-            }
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-            long s = s0 + i;
-            float2 v = make_float2(0.f, 0.f);
-            if (s < n_valid) {
-                if (FMT == 1) {
-                    const int16_t *p = reinterpret_cast<const int16_t *>(raw) + 2 * s;
-                    v.x = cvt_s16((float)p[0]);
-                    v.y = cvt_s16((float)p[1]);
-                } else if (FMT == 2) {
-                    const int8_t *p = reinterpret_cast<const int8_t *>(raw) + 2 * s;
-                    v.x = cvt_s8((float)p[0]);
-                    v.y = cvt_s8((float)p[1]);
-                } else
-                    v = reinterpret_cast<const float2 *>(raw)[s];
-            }
-            x[i] = v;
-        }
-    }
+        RawRegs<FMT> r;
+        raw_fetch<FMT>(raw, s0, r);
+        raw_convert<FMT>(r, x);
+    } else
+        load8_ragged<FMT>(raw, s0, n_valid, x);
 }
 
 // test hook: the conversion alone (8 samples per thread)
@@ -141,6 +169,15 @@ __device__ __forceinline__ EB eb_compose(const EB first, const EB second)
     r.E = fmaf(-first.E, second.E, first.E + second.E);
     return r;
 }
+// second with first put in front when take is set (branch-free scan step)
+__device__ __forceinline__ EB eb_compose_if(bool take, const EB first, const EB second)
+{
+    const EB c = eb_compose(first, second);
+    EB r;
+    r.E = take ? c.E : second.E;
+    r.B = take ? c.B : second.B;
+    return r;
+}
 
 __device__ __forceinline__ Affine compose(const Affine &first, const Affine &second)
 {
@@ -169,14 +206,14 @@ __device__ __forceinline__ Affine warp_scan_inclusive(Affine v, int lane)
 __device__ __forceinline__ int xidx(int i) { return i + 2 * (i >> 3); }
 
 // composed AGC map of 8 samples (all valid)
-__device__ __forceinline__ EB agc_map8(const float2 (&x)[8], float rate)
+__device__ __forceinline__ EB agc_map8(const float2 (&x)[8], float rate, float (&e)[8])
 {
     EB m{0.f, 0.f};
 #pragma unroll
     for (int i = 0; i < 8; i++) {
-        const float e = rate * fast_mag(fmaf(x[i].x, x[i].x, x[i].y * x[i].y));
-        m.B = fmaf(-e, m.B, m.B + rate);
-        m.E = fmaf(-m.E, e, m.E + e);
+        e[i] = rate * fast_mag(fmaf(x[i].x, x[i].x, x[i].y * x[i].y));
+        m.B = fmaf(-e[i], m.B, m.B + rate);
+        m.E = fmaf(-m.E, e[i], m.E + e[i]);
     }
     return m;
 }
@@ -252,7 +289,8 @@ __global__ void __launch_bounds__(FIR_THREADS, 5) k_agc_fir(const void *__restri
                     break;
                 float2 x[8];
                 load8<FMT>(raw, (long)j * FIR_TILE + 8 * t, N, x);
-                EB m = agc_map8(x, rate);
+                float e[8];
+                EB m = agc_map8(x, rate, e);
 #pragma unroll
                 for (int off = 1; off < 32; off <<= 1) { // lane l <- groups [l, l + 2*off)
                     EB o;
@@ -286,31 +324,44 @@ __global__ void __launch_bounds__(FIR_THREADS, 5) k_agc_fir(const void *__restri
         }
     }
 
+    RawRegs<FMT> rr;
+    if (FMT != 0 && (long)i0 * FIR_TILE + 8 * t + 8 <= N)
+        raw_fetch<FMT>(raw, (long)i0 * FIR_TILE + 8 * t, rr);
+    const float2 *xrd0 = &xs[0][10 * t], *xrd1 = &xs[1][10 * t]; // xidx(8t + c) = 10t + xidx(c) for c < 8... see fir loop
     for (int i = i0; i < last; i++) {
         const bool out = i >= first; // tile first-1 only provides the FIR history
         const long s0 = (long)i * FIR_TILE + 8 * t;
         const bool interior = (long)(i + 1) * FIR_TILE + 32 <= N && !DUMP; // every sample exists, none is in the stream tail
         float2 x[8];
-        load8<FMT>(raw, s0, N, x);
+        if (s0 + 8 <= N) {
+            if (FMT == 0) // cf32: 16 registers of raw data are too many to hold across a tile
+                raw_fetch<FMT>(raw, s0, rr);
+            raw_convert<FMT>(rr, x);
+        } else
+            load8_ragged<FMT>(raw, s0, N, x);
+        if (FMT != 0 && i + 1 < last && s0 + FIR_TILE + 8 <= N) // next tile's loads fly under this tile's arithmetic
+            raw_fetch<FMT>(raw, s0 + FIR_TILE, rr);
         EB inc{0.f, 0.f};
+        float e[8]; // rate * |x|: the step map of sample q is g -> g * (1 - e[q]) + rate
         if (interior)
-            inc = agc_map8(x, rate);
+            inc = agc_map8(x, rate, e);
         else {
 #pragma unroll
-            for (int q = 0; q < 8; q++)
+            for (int q = 0; q < 8; q++) {
+                e[q] = 0.f;
                 if (s0 + q < N) {
-                    const float e = rate * fast_mag(fmaf(x[q].x, x[q].x, x[q].y * x[q].y));
-                    inc.B = fmaf(-e, inc.B, inc.B + rate);
-                    inc.E = fmaf(-inc.E, e, inc.E + e);
+                    e[q] = rate * fast_mag(fmaf(x[q].x, x[q].x, x[q].y * x[q].y));
+                    inc.B = fmaf(-e[q], inc.B, inc.B + rate);
+                    inc.E = fmaf(-inc.E, e[q], inc.E + e[q]);
                 }
+            }
         }
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
             EB p;
             p.E = __shfl_up_sync(0xffffffffu, inc.E, off);
             p.B = __shfl_up_sync(0xffffffffu, inc.B, off);
-            if (lane >= off)
-                inc = eb_compose(p, inc);
+            inc = eb_compose_if(lane >= off, p, inc);
         }
         if (lane == 31)
             wsum[par][warp] = inc;
@@ -323,8 +374,7 @@ __global__ void __launch_bounds__(FIR_THREADS, 5) k_agc_fir(const void *__restri
             EB p;
             p.E = __shfl_up_sync(0xffffffffu, wv.E, off, 8);
             p.B = __shfl_up_sync(0xffffffffu, wv.B, off, 8);
-            if ((lane & 7) >= off)
-                wv = eb_compose(p, wv);
+            wv = eb_compose_if((lane & 7) >= off, p, wv);
         }
         EB tot, excl{0.f, 0.f};
         tot.E = __shfl_sync(0xffffffffu, wv.E, 7);
@@ -333,16 +383,18 @@ __global__ void __launch_bounds__(FIR_THREADS, 5) k_agc_fir(const void *__restri
             EB p;
             p.E = __shfl_sync(0xffffffffu, wv.E, (warp + 7) & 7);
             p.B = __shfl_sync(0xffffffffu, wv.B, (warp + 7) & 7);
-            if (warp > 0)
-                excl = p;
+            excl.E = warp > 0 ? p.E : 0.f;
+            excl.B = warp > 0 ? p.B : 0.f;
             p.E = __shfl_up_sync(0xffffffffu, inc.E, 1);
             p.B = __shfl_up_sync(0xffffffffu, inc.B, 1);
-            if (lane > 0)
-                excl = eb_compose(excl, p);
+            p.E = lane > 0 ? p.E : 0.f; // identity map in lane 0
+            p.B = lane > 0 ? p.B : 0.f;
+            excl = eb_compose(excl, p);
         }
-        // replay the reference's recurrence over this thread's 8 samples from the scanned seed. The reference evaluates
-        // gain + rate*(1 - sqrt(.)) in double and rounds to float; 1 - mag is exact in float for mag in [0.5, 2] and the FMA rounds
-        // once, so this differs from the double evaluation only through the ~1 ulp of mag.
+        // per-sample gains from the scanned seed with the same step maps: g' = g*(1 - e) + rate is the reference's
+        // gain += rate*(1 - |x*gain|) (agc.cpp:30-33) up to the rounding of one step (~1e-9 relative), which is two orders below
+        // the reference's own accumulated float rounding noise in the gain (~1e-7 rms, time constant 100*gain samples) that no
+        // parallel evaluation reproduces anyway.
         const float Gf = (float)G;
         float g = fmaf(-excl.E, Gf, Gf) + excl.B;
         G = fma(1.0 - (double)tot.E, G, (double)tot.B);
@@ -350,20 +402,17 @@ __global__ void __launch_bounds__(FIR_THREADS, 5) k_agc_fir(const void *__restri
         if (interior) {
 #pragma unroll
             for (int q = 0; q < 8; q++) {
-                const float2 o = make_float2(x[q].x * g, x[q].y * g);
-                const float mag = fast_mag(__fadd_rn(__fmul_rn(o.x, o.x), __fmul_rn(o.y, o.y)));
-                g = fmaf(rate, 1.0f - mag, g);
+                x[q] = make_float2(x[q].x * g, x[q].y * g);
+                g = fmaf(-e[q], g, g + rate);
                 gmax = fmaxf(gmax, g);
-                x[q] = o;
             }
         } else {
 #pragma unroll
             for (int q = 0; q < 8; q++) {
                 const long s = s0 + q;
-                float2 o = make_float2(x[q].x * g, x[q].y * g);
+                const float2 o = make_float2(x[q].x * g, x[q].y * g);
                 if (s < N) {
-                    const float mag = fast_mag(__fadd_rn(__fmul_rn(o.x, o.x), __fmul_rn(o.y, o.y)));
-                    g = fmaf(rate, 1.0f - mag, g);
+                    g = fmaf(-e[q], g, g + rate);
                     gmax = fmaxf(gmax, g);
                     g = fminf(g, 65536.0f);
                     if (out) {
@@ -381,12 +430,12 @@ __global__ void __launch_bounds__(FIR_THREADS, 5) k_agc_fir(const void *__restri
         if (gmax > 65536.0f)
             atomicOr(flags, 1);
         {
-            float4 *dst = reinterpret_cast<float4 *>(&xs[buf][xidx(32 + 8 * t)]);
+            float4 *dst = reinterpret_cast<float4 *>(&xs[buf][10 * t + 40]);
 #pragma unroll
             for (int q = 0; q < 4; q++)
                 dst[q] = make_float4(x[2 * q].x, x[2 * q].y, x[2 * q + 1].x, x[2 * q + 1].y);
             if (t >= FIR_THREADS - 4) { // the last 32 samples are the next tile's history
-                float4 *h = reinterpret_cast<float4 *>(&xs[buf ^ 1][xidx(8 * (t - (FIR_THREADS - 4)))]);
+                float4 *h = reinterpret_cast<float4 *>(&xs[buf ^ 1][10 * (t - (FIR_THREADS - 4))]);
 #pragma unroll
                 for (int q = 0; q < 4; q++)
                     h[q] = make_float4(x[2 * q].x, x[2 * q].y, x[2 * q + 1].x, x[2 * q + 1].y);
@@ -402,10 +451,11 @@ __global__ void __launch_bounds__(FIR_THREADS, 5) k_agc_fir(const void *__restri
 #pragma unroll
             for (int o = 0; o < 8; o++)
                 acc[o] = 0ull;
-            const int fi = 8 * t + 2; // buffer index of the oldest input of output 0 (even: 16-byte aligned pairs)
+            // buffer index of the oldest input of output 0 is 8t + 2 (even: 16-byte aligned pairs); xidx(8t + c) = 10t + xidx(c)
+            const float2 *xrd = buf ? xrd1 : xrd0;
 #pragma unroll
             for (int pI = 0; pI < 19; pI++) {
-                const ulonglong2 vv = *reinterpret_cast<const ulonglong2 *>(&xs[buf][xidx(fi + 2 * pI)]);
+                const ulonglong2 vv = *reinterpret_cast<const ulonglong2 *>(xrd + xidx(2 + 2 * pI));
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
                     const unsigned long long v = h ? vv.y : vv.x;

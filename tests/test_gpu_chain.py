@@ -100,3 +100,46 @@ def test_prefetched_host_batches_equal_plain_pushes(built):
     b = ch.push_ptr(p1, n - half).frames()
     got = np.concatenate([a, b])
     assert got.shape == want.shape and np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("name", ["metop_ahrpt", "jpss_hrd"])
+def test_pipelined_mode_gives_the_same_frames(built, name):
+    """Decoder on its worker thread, one batch behind the demodulator: same CADUs, in order; frames of a push become pullable only
+    once that batch is decoded; sync() drains; switching back to the synchronous mode continues the same stream."""
+    O = oracle()
+    cfg, raw, _ = signal(name, 22)
+    n = nsamples(raw, cfg)
+    per = 1 if cfg.fmt == "cf32" else 2
+    soft = oracle_demod(O, cfg).run(raw, stages=False)["soft"]
+    want = oracle_fec(O, cfg).run(soft)["cadu"].reshape(-1, cfg.cadu_bytes)
+    ch = gpu_chain(cfg, n).set_pipelined(True)
+    cuts = [0, n // 7, n // 3 + 5, n // 2, (3 * n) // 4 + 77, n]
+    parts = []
+    for k, (a, b) in enumerate(zip(cuts[:-1], cuts[1:])):
+        if k == 3:  # mode switches drain the decoder and keep the stream
+            ch.set_pipelined(False)
+        if k == 4:
+            ch.set_pipelined(True)
+        ch.push(raw[a * per:b * per])
+        parts.append(ch.frames())
+    ch.sync()
+    parts.append(ch.frames())
+    got = np.concatenate(parts)
+    assert got.shape == want.shape and np.array_equal(got, want)
+    ds, fs = ch.stats()
+    assert fs["frames_out"] == want.shape[0] and ds["samples_in"] == n
+    ch.close()
+
+
+def test_pipelined_decoder_errors_surface(built):
+    """A decoder-side failure on the worker thread (soft FIFO too small for the batch) is reported by the next call, not lost."""
+    from satdump_b200 import capi
+    cfg, raw, _ = signal("metop_ahrpt", 20)
+    n = nsamples(raw, cfg)
+    ch = capi.Chain(capi.demod_cfg(cfg.samplerate, cfg.symbolrate, cfg.constellation, cfg.rrc_alpha, cfg.pll_bw, cfg.fmt, max_batch=n),
+                    capi.metop_cfg(cfg.ber_thresold, cfg.outsync_after, max_soft=65536)).set_pipelined(True)
+    ch.push(raw)
+    with pytest.raises(capi.B200Error) as e:
+        ch.sync()
+    assert e.value.code == -5
+    ch.close()
