@@ -43,7 +43,7 @@ enum { B200_CF32 = 0, B200_CS16 = 1, B200_CS8 = 2 };
 /* decoder kind */
 enum { B200_FEC_METOP = 0, B200_FEC_CCSDS = 1 };
 /* debug stage ids for b200_demod_debug_stage */
-enum { B200_STAGE_AGC = 0, B200_STAGE_FIR = 1, B200_STAGE_COSTAS = 2 };
+enum { B200_STAGE_AGC = 0, B200_STAGE_FIR = 1, B200_STAGE_COSTAS = 2, B200_STAGE_RESAMP = 3 };
 
 typedef struct b200_demod_cfg
 {
@@ -63,6 +63,10 @@ typedef struct b200_demod_cfg
     int device;               /* CUDA device ordinal                                             */
     long max_batch;           /* largest nsamples of one push (device buffers are sized for it)  */
     int keep_stages;          /* !=0: keep AGC/FIR/Costas stage outputs for b200_demod_debug_stage */
+    int iq_swap;              /* "iq_swap": re <-> im at the reader (dsp/io/file_source.cpp:31-33)    */
+    double final_samplerate;  /* 0 = samplerate. Otherwise the rate BaseDemodModule::initb resamples to when samplerate/symbolrate is
+                                 outside [min_sps, max_sps] (module_demod_base.cpp:59-87,203-204): use b200_demod_final_samplerate().
+                                 Only the rational part of SmartResamplerBlock is built: samplerate / final_samplerate must be < 2 */
 } b200_demod_cfg;
 
 typedef struct b200_fec_cfg
@@ -90,6 +94,7 @@ typedef struct b200_demod_stats
     int repairs;              /* segments re-run as exact sequential continuations (junction check failed) */
     long kernel_launches;     /* CUDA kernels launched by this object so far                     */
     long agc_exact_passes;    /* batches whose AGC seeds needed the scanned (exact) pass: weak signal */
+    long last_front_samples;  /* samples that entered the AGC in the last push (= nsamples unless the front-end resampler runs) */
 } b200_demod_stats;
 
 typedef struct b200_fec_stats
@@ -104,6 +109,11 @@ typedef struct b200_fec_stats
 } b200_fec_stats;
 
 typedef struct b200_demod b200_demod;
+
+/* BaseDemodModule::initb's choice of the working sample rate (module_demod_base.cpp:59-87): returns samplerate when
+ * samplerate/symbolrate lies inside [min_sps, max_sps] (psk_demod: 1.1..4.0, OQPSK 1.6..2.4; pass 0 for those defaults), else the
+ * rate the reference's front-end resampler converts to. custom_samplerate > 0 overrides ("custom_samplerate"). */
+double b200_demod_final_samplerate(double samplerate, double symbolrate, int constellation, float min_sps, float max_sps, double custom_samplerate);
 typedef struct b200_fec b200_fec;
 typedef struct b200_chain b200_chain;
 

@@ -69,6 +69,132 @@ void orc_mm_bank(float *out)
     }
 }
 
+/* ======================================================================= rational resampler (front end of BaseDemodModule)
+ * SmartResamplerBlock (resamp/smart_resampler.cpp:8-61) = optional power-of-two decimator + RationalResamplerBlock. The decimator's
+ * tap tables are data of the reference (resamp/power_decim/\*.h) and are not restated: ratios needing it (input rate >= 2 x output
+ * rate) are reported as unsupported here and in the CUDA path alike. */
+
+static double izero(double x) /* firdes.cpp:357-373 */
+{
+    double sum, u, halfx, temp;
+    int n;
+    sum = u = n = 1;
+    halfx = x / 2.0;
+    do {
+        temp = halfx / (double)n;
+        n += 1;
+        temp *= temp;
+        u *= temp;
+        sum += u;
+    } while (u >= 1E-21 * sum);
+    return sum;
+}
+
+/* firdes::design_resampler_filter_float (firdes.cpp:276-301) -> low_pass (:80-120) with window::kaiser (:453-478); returns ntaps */
+static int design_resampler(unsigned interpolation, unsigned decimation, float fractional_bw, float **out)
+{
+    float beta = 7.0, halfband = 0.5, rate = (float)interpolation / (float)decimation, trans_width, mid;
+    if (rate >= 1.0) { trans_width = halfband - fractional_bw; mid = halfband - trans_width / 2.0; }
+    else { trans_width = rate * (halfband - fractional_bw); mid = rate * halfband - trans_width / 2.0; }
+    double gain = interpolation, fs = interpolation, cutoff = mid, tw = trans_width, b = beta;
+    double a = b / 0.1102 + 8.7; /* window::max_attenuation(WIN_KAISER) */
+    int ntaps = (int)(a * fs / (22.0 * tw));
+    if ((ntaps & 1) == 0) ntaps++;
+    float *taps = malloc(sizeof(float) * ntaps), *w = malloc(sizeof(float) * ntaps);
+    {
+        double IBeta = 1.0 / izero(b), inm1 = 1.0 / ((double)(ntaps - 1)), temp;
+        w[0] = IBeta;
+        for (int i = 1; i < ntaps - 1; i++) { temp = 2 * i * inm1 - 1; w[i] = izero(b * sqrt(1.0 - temp * temp)) * IBeta; }
+        w[ntaps - 1] = IBeta;
+    }
+    int M = (ntaps - 1) / 2;
+    double fwT0 = 2 * M_PI * cutoff / fs;
+    for (int n = -M; n <= M; n++) {
+        if (n == 0) taps[n + M] = fwT0 / M_PI * w[n + M];
+        else taps[n + M] = sin(n * fwT0) / (n * M_PI) * w[n + M];
+    }
+    double fmax = taps[0 + M];
+    for (int n = 1; n <= M; n++) fmax += 2 * taps[n + M];
+    gain /= fmax;
+    for (int i = 0; i < ntaps; i++) taps[i] *= gain;
+    free(w);
+    *out = taps;
+    return ntaps;
+}
+
+static unsigned gcd_u(unsigned a, unsigned b) { while (b) { unsigned t = a % b; a = b; b = t; } return a; }
+
+typedef struct
+{
+    int active, interp, decim, ntaps, ctr, inc; /* RationalResamplerBlock: d_interpolation, d_decimation, pfb.ntaps, d_ctr, inc */
+    float *bank;                                /* [interp][ntaps] */
+    float *buffer;                              /* re,im pairs */
+} orc_resamp;
+
+/* SmartResamplerBlock ctor (smart_resampler.cpp:8-61) reduced to its rational branch; returns 0 if unsupported (needs the decimator) */
+static int resamp_init(orc_resamp *r, unsigned interpolation, unsigned decimation, int max_in)
+{
+    memset(r, 0, sizeof(*r));
+    if (decimation == interpolation) return 1;
+    double rsamp_in = decimation, fout = interpolation;
+    if (decimation > interpolation) {
+        int best_power = floor(log2(decimation / interpolation)); /* integer division, as in the reference */
+        if (best_power > 0) return 0;
+        double t;
+        while (modf(rsamp_in, &t) != 0 || modf(fout, &t) != 0) { rsamp_in *= 10; fout *= 10; }
+    }
+    unsigned I = (unsigned)fout, D = (unsigned)rsamp_in, g = gcd_u(I, D); /* rational_resampler.cpp:27-41 */
+    I /= g; D /= g;
+    float *rt;
+    int n = design_resampler(I, D, 0.4, &rt);
+    /* PolyphaseBank::init(rtaps, nfilt = I) — polyphase_bank.cpp:6-39 */
+    int nt = (n + I - 1) / I;
+    if (fmod((double)n / (double)I, 1.0) > 0.0) nt++;
+    r->bank = calloc((size_t)I * nt, sizeof(float));
+    for (int i = 0; i < (int)I * nt; i++) r->bank[((I - 1) - (i % I)) * nt + i / I] = i < n ? rt[i] : 0;
+    free(rt);
+    r->active = 1; r->interp = I; r->decim = D; r->ntaps = nt;
+    r->buffer = calloc((size_t)2 * (max_in + nt + 16), sizeof(float));
+    return 1;
+}
+
+/* RationalResamplerBlock::process (rational_resampler.cpp:43-65); generic volk_32fc_32f_dot_prod_32fc: left to right, mul then add */
+static int resamp_run(orc_resamp *r, const float *in, int nsamples, float *out)
+{
+    memcpy(&r->buffer[2 * (r->ntaps - 1)], in, nsamples * 2 * sizeof(float));
+    int outc = 0;
+    while (r->inc < nsamples) {
+        const float *x = &r->buffer[2 * r->inc], *t = &r->bank[(size_t)r->ctr * r->ntaps];
+        float re = 0, im = 0;
+        for (int k = 0; k < r->ntaps; k++) { re += x[2 * k] * t[k]; im += x[2 * k + 1] * t[k]; }
+        out[2 * outc] = re; out[2 * outc + 1] = im; outc++;
+        r->ctr += r->decim;
+        r->inc += r->ctr / r->interp;
+        r->ctr = r->ctr % r->interp;
+    }
+    r->inc -= nsamples;
+    memmove(&r->buffer[0], &r->buffer[2 * nsamples], r->ntaps * 2 * sizeof(float));
+    return outc;
+}
+
+int orc_resampler_taps(unsigned interpolation, unsigned decimation, float *out, int cap, int *nfilt)
+{
+    orc_resamp r;
+    /* RationalResamplerBlock(nullptr, interpolation, decimation) directly (no SmartResampler pre-scaling) */
+    unsigned g = gcd_u(interpolation, decimation), I = interpolation / g, D = decimation / g;
+    float *rt;
+    int n = design_resampler(I, D, 0.4, &rt);
+    int nt = (n + I - 1) / I;
+    if (fmod((double)n / (double)I, 1.0) > 0.0) nt++;
+    *nfilt = I;
+    if ((long)I * nt > cap) { free(rt); return -1; }
+    memset(out, 0, sizeof(float) * I * nt);
+    for (int i = 0; i < (int)I * nt; i++) out[((I - 1) - (i % I)) * nt + i / I] = i < n ? rt[i] : 0;
+    free(rt);
+    (void)r;
+    return nt;
+}
+
 /* ======================================================================= demodulator chain */
 
 typedef struct { float re, im; } cf_t;
@@ -94,6 +220,9 @@ typedef struct
     int inc;
     cf_t *mm_buf;
     cf_t *w0, *w1, *w2; /* per-buffer scratch */
+    orc_resamp rs;      /* front-end resampler (module_demod_base.cpp:203-204) */
+    long last_front;    /* samples that entered the AGC in the last orc_demod_run call */
+    cf_t *rs_in;
 } orc_demod;
 
 static float clip_branchless(float x, float c) { return 0.5 * (fabsf(x + c) - fabsf(x - c)); } /* block.cpp:5 */
@@ -108,8 +237,16 @@ void *orc_demod_create(const orc_demod_cfg *c)
     int def = fs / 200 > 8193 ? (int)(fs / 200) : 8193;
     if (def > STREAM_MAX) def = STREAM_MAX;
     d->buffer_size = c->buffer_size > 0 ? c->buffer_size : def;
-    float final_fs = fs;               /* float final_samplerate, module_demod_base.h:58 */
+    float final_fs = c->final_samplerate > 0 ? (float)c->final_samplerate : (float)fs; /* float final_samplerate, module_demod_base.h:58 */
     d->sps = final_fs / (float)rs;     /* module_demod_base.cpp:81 */
+    if (c->final_samplerate > 0 && (long)c->final_samplerate != fs) {
+        float decimation_factor = fs / final_fs; /* module_demod_base.cpp:84-87 */
+        d->buffer_size *= ceil(decimation_factor);
+        if (d->buffer_size > 8192 * 20) d->buffer_size = 8192 * 20;
+        /* SmartResamplerBlock(input, final_samplerate, d_samplerate): (unsigned interpolation, unsigned decimation) */
+        if (!resamp_init(&d->rs, (unsigned)final_fs, (unsigned)fs, d->buffer_size)) { free(d); return NULL; }
+        d->rs_in = malloc(sizeof(cf_t) * d->buffer_size);
+    }
     d->agc_rate = c->agc_rate; d->agc_ref = 1.0f; d->agc_gain = 1.0f; d->agc_max = 65536; /* module_demod_base.cpp:207 */
     d->ntaps = orc_rrc_taps(1, final_fs, (int)rs, c->rrc_alpha, c->rrc_taps, d->taps);      /* module_psk_demod.cpp:91 */
     d->fir_buf = calloc(2 * STREAM_MAX, sizeof(cf_t));
@@ -125,16 +262,19 @@ void *orc_demod_create(const orc_demod_cfg *c)
     d->mu = c->clock_mu; d->omega = d->sps; d->omega_gain = c->clock_gain_omega; d->mu_gain = c->clock_gain_mu;
     d->omega_mid = d->sps; d->omega_limit = c->clock_omega_limit * d->sps; /* clock_recovery_mm.cpp:14-15 */
     d->mm_buf = calloc(STREAM_MAX + 64, sizeof(cf_t));
-    d->w0 = malloc(sizeof(cf_t) * d->buffer_size);
-    d->w1 = malloc(sizeof(cf_t) * d->buffer_size);
-    d->w2 = malloc(sizeof(cf_t) * d->buffer_size);
+    /* the resampler may interpolate: up to ceil(n * I / D) + 1 outputs per input buffer */
+    size_t wn = d->rs.active ? (size_t)((double)d->buffer_size * d->rs.interp / d->rs.decim) + 16 : (size_t)d->buffer_size;
+    if (wn < (size_t)d->buffer_size) wn = d->buffer_size;
+    d->w0 = malloc(sizeof(cf_t) * wn);
+    d->w1 = malloc(sizeof(cf_t) * wn);
+    d->w2 = malloc(sizeof(cf_t) * wn);
     return d;
 }
 
 void orc_demod_destroy(void *h)
 {
     orc_demod *d = h;
-    free(d->fir_buf); free(d->mm_buf); free(d->w0); free(d->w1); free(d->w2); free(d);
+    free(d->fir_buf); free(d->mm_buf); free(d->w0); free(d->w1); free(d->w2); free(d->rs.bank); free(d->rs.buffer); free(d->rs_in); free(d);
 }
 float orc_demod_sps(void *h) { return ((orc_demod *)h)->sps; }
 
@@ -151,6 +291,8 @@ static void convert_in(const orc_demod_cfg *c, const void *raw, long off, int n,
     if (c->format == 0) memcpy(dst, (const cf_t *)raw + off, n * sizeof(cf_t));
     else if (c->format == 1) { const int16_t *s = (const int16_t *)raw + off * 2; for (int i = 0; i < 2 * n; i++) o[i] = ((float)s[i]) / 32767.0f; }
     else { const int8_t *s = (const int8_t *)raw + off * 2; for (int i = 0; i < 2 * n; i++) o[i] = ((float)s[i]) / 127.0f; }
+    if (c->iq_swap) /* file_source.cpp:31-33 */
+        for (int i = 0; i < n; i++) { float t = dst[i].re; dst[i].re = dst[i].im; dst[i].im = t; }
 }
 
 /* AGCBlock<complex_t>::work — agc.cpp:25-39. The magnitude goes through ::sqrt(double). */
@@ -269,21 +411,27 @@ long orc_demod_run(void *h, const void *raw, long nsamples, float *agc_out, floa
                    int8_t *soft_out, long sym_cap)
 {
     orc_demod *d = h;
-    long nsym = 0;
+    long nsym = 0, pos = 0; /* pos: samples after the (optional) resampler so far in this call */
     for (long off = 0; off < nsamples; off += d->buffer_size) {
         int n = (int)(nsamples - off < d->buffer_size ? nsamples - off : d->buffer_size);
-        convert_in(&d->cfg, raw, off, n, d->w0);
+        if (d->rs.active) {
+            convert_in(&d->cfg, raw, off, n, d->rs_in);
+            n = resamp_run(&d->rs, (const float *)d->rs_in, n, (float *)d->w0);
+            if (n <= 0) continue;
+        } else
+            convert_in(&d->cfg, raw, off, n, d->w0);
         agc_run(d, d->w0, d->w1, n);
-        if (agc_out) memcpy(agc_out + off * 2, d->w1, n * sizeof(cf_t));
+        if (agc_out) memcpy(agc_out + pos * 2, d->w1, n * sizeof(cf_t));
         fir_run(d, d->w1, d->w0, n);
-        if (fir_out) memcpy(fir_out + off * 2, d->w0, n * sizeof(cf_t));
+        if (fir_out) memcpy(fir_out + pos * 2, d->w0, n * sizeof(cf_t));
         cf_t *cur = d->w0;
         if (d->order) {
             costas_run(d, d->w0, d->w1, n);
             cur = d->w1;
             if (d->cfg.constellation == 2) delay_run(d, cur, n);
-            if (costas_out) memcpy(costas_out + off * 2, cur, n * sizeof(cf_t));
+            if (costas_out) memcpy(costas_out + pos * 2, cur, n * sizeof(cf_t));
         }
+        pos += n;
         int m = mm_run(d, cur, d->w2, n);
         if (nsym + m > sym_cap) m = (int)(sym_cap - nsym);
         if (mm_out) memcpy(mm_out + nsym * 2, d->w2, m * sizeof(cf_t));
@@ -298,7 +446,30 @@ long orc_demod_run(void *h, const void *raw, long nsamples, float *agc_out, floa
         }
         nsym += m;
     }
+    d->last_front = pos;
     return nsym;
+}
+long orc_demod_last_front(void *h) { return ((orc_demod *)h)->last_front; }
+
+long orc_resample(const orc_demod_cfg *c, const void *raw, long nsamples, float *out, long cap)
+{
+    orc_demod *d = orc_demod_create(c);
+    if (!d) return -1;
+    long pos = 0;
+    cf_t *in = malloc(sizeof(cf_t) * d->buffer_size);
+    for (long off = 0; off < nsamples; off += d->buffer_size) {
+        int n = (int)(nsamples - off < d->buffer_size ? nsamples - off : d->buffer_size);
+        convert_in(&d->cfg, raw, off, n, in);
+        int m = n;
+        const float *src = (const float *)in;
+        if (d->rs.active) { m = resamp_run(&d->rs, (const float *)in, n, (float *)d->w0); src = (const float *)d->w0; }
+        if (pos + m > cap) m = (int)(cap - pos);
+        memcpy(out + pos * 2, src, m * sizeof(cf_t));
+        pos += m;
+    }
+    free(in);
+    orc_demod_destroy(d);
+    return pos;
 }
 
 /* ======================================================================= convolutional code k=7 r=1/2 */

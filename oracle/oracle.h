@@ -26,6 +26,8 @@ typedef struct
     float costas_max_offset;
     int format; /* 0 cf32, 1 cs16, 2 cs8 */
     int buffer_size;
+    int iq_swap;             /* re <-> im at the reader (file_source.cpp:31-33) */
+    double final_samplerate; /* 0 = samplerate; else the rate BaseDemodModule::initb resamples to (module_demod_base.cpp:59-87) */
 } orc_demod_cfg;
 
 typedef struct
@@ -49,6 +51,11 @@ float orc_demod_sps(void *h);
 long orc_demod_run(void *h, const void *raw, long nsamples, float *agc_out, float *fir_out, float *costas_out, float *mm_out,
                    int8_t *soft_out, long sym_cap);
 void orc_demod_state(void *h, float *out8);
+long orc_demod_last_front(void *h);
+/* front end alone: conversion (+ iq_swap) + SmartResamplerBlock (rational part) on a fresh resampler; returns output samples */
+long orc_resample(const orc_demod_cfg *cfg, const void *raw, long nsamples, float *out, long cap);
+/* polyphase bank of RationalResamplerBlock(interpolation, decimation): returns taps per arm, *nfilt arms; out[arm*ntaps + k] */
+int orc_resampler_taps(unsigned interpolation, unsigned decimation, float *out, int cap, int *nfilt);
 
 void *orc_fec_create(const orc_fec_cfg *cfg);
 void orc_fec_destroy(void *h);

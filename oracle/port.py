@@ -29,6 +29,11 @@ def _lib():
         L.ref_demod_run.restype = C.c_long
         L.ref_demod_run.argtypes = [C.c_void_p, C.c_void_p, C.c_long] + [C.c_void_p] * 5 + [C.c_long]
         L.ref_demod_state.argtypes = [C.c_void_p, C.c_void_p]
+        L.ref_demod_last_front.restype = C.c_long
+        L.ref_demod_last_front.argtypes = [C.c_void_p]
+        L.ref_resample.restype = C.c_long
+        L.ref_resample.argtypes = [C.POINTER(_m.DemodCfg), C.c_void_p, C.c_long, C.c_void_p, C.c_long]
+        L.ref_resampler_taps.argtypes = [C.c_uint, C.c_uint, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
         L.ref_fec_create.restype = C.c_void_p
         L.ref_fec_create.argtypes = [C.POINTER(_m.FecCfg)]
         L.ref_fec_destroy.argtypes = [C.c_void_p]
@@ -60,6 +65,7 @@ def available():
 lib = _lib
 DemodCfg, FecCfg = _m.DemodCfg, _m.FecCfg
 demod_cfg, metop_cfg, ccsds_cfg = _m.demod_cfg, _m.metop_cfg, _m.ccsds_cfg
+final_samplerate_of, resample, resampler_taps = _m.final_samplerate_of, _m.resample, _m.resampler_taps
 Fec = _m.Fec
 rs_decode_interleaved, derand, cc_encode, cc_decode, rotate_soft, deframe = (
     _m.rs_decode_interleaved, _m.derand, _m.cc_encode, _m.cc_decode, _m.rotate_soft, _m.deframe)

@@ -18,7 +18,7 @@ class DemodCfg(C.Structure):
                 ("rrc_alpha", C.c_float), ("rrc_taps", C.c_int), ("pll_bw", C.c_float), ("agc_rate", C.c_float),
                 ("clock_gain_omega", C.c_float), ("clock_mu", C.c_float), ("clock_gain_mu", C.c_float),
                 ("clock_omega_limit", C.c_float), ("costas_max_offset", C.c_float), ("format", C.c_int),
-                ("buffer_size", C.c_int)]
+                ("buffer_size", C.c_int), ("iq_swap", C.c_int), ("final_samplerate", C.c_double)]
 
 
 class FecCfg(C.Structure):
@@ -68,6 +68,11 @@ def lib():
         L.ref_demod_run.restype = C.c_long
         L.ref_demod_run.argtypes = [C.c_void_p, C.c_void_p, C.c_long] + [C.c_void_p] * 5 + [C.c_long]
         L.ref_demod_state.argtypes = [C.c_void_p, C.c_void_p]
+        L.ref_demod_last_front.restype = C.c_long
+        L.ref_demod_last_front.argtypes = [C.c_void_p]
+        L.ref_resample.restype = C.c_long
+        L.ref_resample.argtypes = [C.POINTER(DemodCfg), C.c_void_p, C.c_long, C.c_void_p, C.c_long]
+        L.ref_resampler_taps.argtypes = [C.c_uint, C.c_uint, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
         L.ref_fec_create.restype = C.c_void_p
         L.ref_fec_create.argtypes = [C.POINTER(FecCfg)]
         L.ref_fec_destroy.argtypes = [C.c_void_p]
@@ -95,8 +100,13 @@ def _p(a):
 
 def demod_cfg(samplerate, symbolrate, constellation, rrc_alpha, pll_bw=0.003, fmt="cs16", rrc_taps=31, agc_rate=1e-2,
               clock_alpha=None, clock_gain_omega=None, clock_mu=0.5, clock_gain_mu=8.7e-3, clock_omega_limit=0.005,
-              costas_max_offset=1.0, buffer_size=0):
-    """Defaults follow module_psk_demod.h:31-39 and module_demod_base.h:54."""
+              costas_max_offset=1.0, buffer_size=0, iq_swap=False, final_samplerate=None, min_sps=None, max_sps=None):
+    """Defaults follow module_psk_demod.h:31-39 and module_demod_base.h:54. final_samplerate=None applies BaseDemodModule::initb's
+    rule (resample when samplerate/symbolrate is outside [min_sps, max_sps]); 0 = no resampler."""
+    if final_samplerate is None:
+        final_samplerate = final_samplerate_of(samplerate, symbolrate, constellation, min_sps, max_sps)
+        if final_samplerate == float(int(samplerate)):
+            final_samplerate = 0.0
     if clock_alpha is not None:  # module_psk_demod.cpp:36-41 ; DVB-S2 REC_ALPHA module_dvbs2_demod.h:49-53
         clock_gain_omega = np.float32(clock_alpha) ** 2 / 4.0
         clock_gain_mu = clock_alpha
@@ -104,7 +114,29 @@ def demod_cfg(samplerate, symbolrate, constellation, rrc_alpha, pll_bw=0.003, fm
         clock_gain_omega = float(np.float32(pow(8.7e-3, 2) / 4.0))
     return DemodCfg(float(samplerate), float(symbolrate), CONST[constellation], rrc_alpha, rrc_taps, pll_bw, agc_rate,
                     float(clock_gain_omega), clock_mu, float(clock_gain_mu), clock_omega_limit, costas_max_offset, FMT[fmt],
-                    buffer_size)
+                    buffer_size, int(iq_swap), float(final_samplerate))
+
+
+def final_samplerate_of(samplerate, symbolrate, constellation, min_sps=None, max_sps=None, custom=None):
+    """BaseDemodModule::initb (module_demod_base.cpp:59-80) with its types: long d_samplerate, int d_symbolrate, float MIN_SPS /
+    MAX_SPS / final_samplerate; psk_demod's OQPSK window module_psk_demod.cpp:65-70."""
+    f32 = np.float32
+    d_samplerate, d_symbolrate = int(samplerate), int(symbolrate)
+    MIN_SPS = f32(1.6 if constellation == "oqpsk" else 1.1) if not min_sps else f32(min_sps)
+    MAX_SPS = f32(2.4 if constellation == "oqpsk" else 4.0) if not max_sps else f32(max_sps)
+    input_sps = f32(d_samplerate) / f32(d_symbolrate)
+    resample = input_sps > MAX_SPS or input_sps < MIN_SPS
+    rng = int(pow(10, len(str(d_symbolrate)) - 1))
+    final = f32(d_samplerate)
+    if custom:
+        final = f32(int(custom))
+    elif MAX_SPS == MIN_SPS:
+        final = f32(d_symbolrate) * MAX_SPS
+    elif input_sps > MAX_SPS:
+        final = f32(float(round(d_symbolrate // rng) * rng) * float(MAX_SPS)) if resample else f32(d_samplerate)
+    elif input_sps < MIN_SPS:
+        final = f32(d_symbolrate) * MIN_SPS if resample else f32(d_samplerate)
+    return float(final)
 
 
 def metop_cfg(ber_thresold=0.28, outsync_after=10):
@@ -152,14 +184,18 @@ class Demod:
         raw = np.ascontiguousarray(raw)
         n = raw.size if self.cfg.format == 0 and np.iscomplexobj(raw) else raw.size // 2
         bps = 1 if self.cfg.constellation == 0 else 2
-        cap = int(n / max(1.0, self.sps) * 1.1) + 64
-        agc = np.zeros(n, np.complex64) if stages else None
-        fir = np.zeros(n, np.complex64) if stages else None
-        cos = np.zeros(n, np.complex64) if (stages and self.cfg.constellation != 4) else None
+        ratio = self.cfg.final_samplerate / self.cfg.samplerate if self.cfg.final_samplerate > 0 else 1.0
+        nf = int(n * ratio) + 64  # samples after the front-end resampler (upper bound)
+        cap = int(nf / max(1.0, self.sps) * 1.1) + 64
+        agc = np.zeros(nf, np.complex64) if stages else None
+        fir = np.zeros(nf, np.complex64) if stages else None
+        cos = np.zeros(nf, np.complex64) if (stages and self.cfg.constellation != 4) else None
         mm = np.zeros(cap, np.complex64)
         soft = np.zeros(cap * bps, np.int8)
         ns = lib().ref_demod_run(self.h, _p(raw), n, _p(agc), _p(fir), _p(cos), _p(mm), _p(soft), cap)
-        return dict(agc=agc, fir=fir, costas=cos, mm=mm[:ns].copy(), soft=soft[:ns * bps].copy())
+        front = lib().ref_demod_last_front(self.h)
+        cut = (lambda a: None if a is None else a[:front])
+        return dict(agc=cut(agc), fir=cut(fir), costas=cut(cos), mm=mm[:ns].copy(), soft=soft[:ns * bps].copy(), front=front)
 
 
 class Fec:
@@ -193,6 +229,26 @@ class Fec:
                               _p(rse), C.byref(nfr))
         return dict(cadu=cadu[:w].copy(), vit_state=vs, vit_ber=vb, defr_state=ds, bits=bits[:nbits.value].copy(),
                     rs_err=rse[:nfr.value * rs_i].reshape(-1, rs_i).copy(), nframes=nfr.value)
+
+
+def resample(cfg, raw):
+    """Conversion (+ iq_swap) and the front-end SmartResamplerBlock alone, on a fresh resampler."""
+    raw = np.ascontiguousarray(raw)
+    n = raw.size if cfg.format == 0 and np.iscomplexobj(raw) else raw.size // 2
+    ratio = cfg.final_samplerate / cfg.samplerate if cfg.final_samplerate > 0 else 1.0
+    out = np.zeros(int(n * ratio) + 64, np.complex64)
+    m = lib().ref_resample(C.byref(cfg), _p(raw), n, _p(out), out.size)
+    if m < 0:
+        raise RuntimeError("resampling ratio needs the power-of-two decimator (not restated)")
+    return out[:m].copy()
+
+
+def resampler_taps(interpolation, decimation):
+    """Polyphase bank of RationalResamplerBlock(interpolation, decimation): array [arms, taps per arm]."""
+    out = np.zeros(1 << 20, np.float32)
+    nf = C.c_int(0)
+    nt = lib().ref_resampler_taps(interpolation, decimation, _p(out), out.size, C.byref(nf))
+    return out[:nf.value * nt].reshape(nf.value, nt).copy()
 
 
 def rrc_design(gain, fs, rs, alpha, ntaps):

@@ -45,6 +45,8 @@
 #include "common/dsp/pll/costas_loop.h"
 #include "common/dsp/demod/delay_one_imag.h"
 #include "common/dsp/clock_recovery/clock_recovery_mm.h"
+#include "common/dsp/resamp/smart_resampler.h"
+#include "common/dsp/resamp/rational_resampler.h"
 #undef private
 #undef protected
 #include "common/dsp/resamp/polyphase_bank.h"
@@ -87,6 +89,8 @@ extern "C"
         float costas_max_offset; /* rad/sample, default 1.0 */
         int format;              /* 0 cf32, 1 cs16, 2 cs8 */
         int buffer_size;         /* 0 = reference default rule */
+        int iq_swap;             /* FileSourceBlock(.., iq_swap): re <-> im at the reader (file_source.cpp:31-33) */
+        double final_samplerate; /* 0 = samplerate (sps inside [MIN_SPS, MAX_SPS]); else BaseDemodModule::initb's resampled rate */
     } ref_demod_cfg;
 
     typedef struct
@@ -111,12 +115,15 @@ namespace
         int buffer_size;
         float final_samplerate, final_sps;
         std::shared_ptr<dsp::stream<complex_t>> in;
+        std::shared_ptr<dsp::SmartResamplerBlock<complex_t>> resampler; /* module_demod_base.cpp:203-204 */
+        std::vector<complex_t> rs_in;
         std::shared_ptr<dsp::AGCBlock<complex_t>> agc;
         std::shared_ptr<dsp::FIRBlock<complex_t>> rrc;
         std::shared_ptr<dsp::CostasLoopBlock> pll;
         std::shared_ptr<dsp::DelayOneImagBlock> delay;
         std::shared_ptr<dsp::MMClockRecoveryBlock<complex_t>> rec;
         std::vector<float> rrc_taps;
+        long last_front = 0; /* samples that entered the AGC in the last ref_demod_run call */
     };
 
     int8_t soft_clamp(float x) /* module_demod_base.h:106-113 semantics */
@@ -137,6 +144,9 @@ namespace
             volk_16i_s32f_convert_32f_u((float *)dst, (const int16_t *)raw + off * 2, 32767, n * 2);
         else
             volk_8i_s32f_convert_32f_u((float *)dst, (const int8_t *)raw + off * 2, 127, n * 2);
+        if (cfg.iq_swap) /* file_source.cpp:31-33 */
+            for (int i = 0; i < n; i++)
+                dst[i] = complex_t(dst[i].imag, dst[i].real);
     }
 
     struct RefFec
@@ -163,9 +173,19 @@ extern "C"
         d->cfg = *c;
         long samplerate = (long)c->samplerate, symbolrate = (long)c->symbolrate;
         d->buffer_size = c->buffer_size > 0 ? c->buffer_size : std::min<int>(dsp::STREAM_BUFFER_SIZE, std::max<int>(8192 + 1, samplerate / 200));
-        d->final_samplerate = samplerate; /* sps inside the window: no resampler */
+        d->final_samplerate = c->final_samplerate > 0 ? (float)c->final_samplerate : (float)samplerate;
         d->final_sps = d->final_samplerate / (float)symbolrate;
         d->in = std::make_shared<dsp::stream<complex_t>>();
+        if (c->final_samplerate > 0 && (long)c->final_samplerate != samplerate)
+        {
+            /* module_demod_base.cpp:84-87,203-204: buffer scaled by ceil(decimation factor), resampler (final, input) */
+            float decimation_factor = samplerate / d->final_samplerate;
+            d->buffer_size *= ceil(decimation_factor);
+            if (d->buffer_size > 8192 * 20)
+                d->buffer_size = 8192 * 20;
+            d->resampler = std::make_shared<dsp::SmartResamplerBlock<complex_t>>(nullptr, d->final_samplerate, samplerate);
+            d->rs_in.resize(d->buffer_size);
+        }
         d->agc = std::make_shared<dsp::AGCBlock<complex_t>>(d->in, c->agc_rate, 1.0f, 1.0f, 65536);
         d->rrc_taps = dsp::firdes::root_raised_cosine(1, d->final_samplerate, (int)symbolrate, c->rrc_alpha, c->rrc_taps);
         d->rrc = std::make_shared<dsp::FIRBlock<complex_t>>(d->agc->output_stream, d->rrc_taps);
@@ -224,26 +244,35 @@ extern "C"
                        long sym_cap)
     {
         RefDemod *d = (RefDemod *)h;
-        long nsym = 0;
+        long nsym = 0, pos = 0; /* pos: samples after the (optional) resampler so far in this call */
         for (long off = 0; off < nsamples; off += d->buffer_size)
         {
             int n = (int)std::min<long>(d->buffer_size, nsamples - off);
-            convert_block(d->cfg, raw, off, n, d->in->writeBuf);
+            if (d->resampler)
+            {
+                convert_block(d->cfg, raw, off, n, d->rs_in.data());
+                n = d->resampler->process(d->rs_in.data(), n, d->in->writeBuf);
+                if (n <= 0)
+                    continue;
+            }
+            else
+                convert_block(d->cfg, raw, off, n, d->in->writeBuf);
             d->in->swap(n);
             d->agc->work();
             if (agc_out)
-                memcpy(agc_out + off * 2, d->agc->output_stream->readBuf, n * sizeof(complex_t));
+                memcpy(agc_out + pos * 2, d->agc->output_stream->readBuf, n * sizeof(complex_t));
             d->rrc->work();
             if (fir_out)
-                memcpy(fir_out + off * 2, d->rrc->output_stream->readBuf, n * sizeof(complex_t));
+                memcpy(fir_out + pos * 2, d->rrc->output_stream->readBuf, n * sizeof(complex_t));
             if (d->pll)
             {
                 d->pll->work();
                 if (d->delay)
                     d->delay->work();
                 if (costas_out)
-                    memcpy(costas_out + off * 2, (d->delay ? d->delay->output_stream : d->pll->output_stream)->readBuf, n * sizeof(complex_t));
+                    memcpy(costas_out + pos * 2, (d->delay ? d->delay->output_stream : d->pll->output_stream)->readBuf, n * sizeof(complex_t));
             }
+            pos += n;
             d->rec->work();
             int m = d->rec->output_stream->getDataSize();
             complex_t *sym = d->rec->output_stream->readBuf;
@@ -266,7 +295,49 @@ extern "C"
             d->rec->output_stream->flush();
             nsym += m;
         }
+        d->last_front = pos;
         return nsym;
+    }
+    long ref_demod_last_front(void *h) { return ((RefDemod *)h)->last_front; }
+
+    /* The front end alone: conversion (+ iq_swap) and SmartResamplerBlock, in reference-sized buffers on a fresh resampler.
+       Returns the number of output samples (<= cap). */
+    long ref_resample(const ref_demod_cfg *c, const void *raw, long nsamples, float *out, long cap)
+    {
+        RefDemod *d = (RefDemod *)ref_demod_create(c);
+        std::vector<complex_t> tmp(d->buffer_size * 2 + 16);
+        std::vector<complex_t> in(d->buffer_size);
+        long pos = 0;
+        for (long off = 0; off < nsamples; off += d->buffer_size)
+        {
+            int n = (int)std::min<long>(d->buffer_size, nsamples - off);
+            convert_block(d->cfg, raw, off, n, in.data());
+            int m = n;
+            if (d->resampler)
+                m = d->resampler->process(in.data(), n, tmp.data());
+            else
+                memcpy(tmp.data(), in.data(), n * sizeof(complex_t));
+            if (pos + m > cap)
+                m = (int)(cap - pos);
+            memcpy(out + pos * 2, tmp.data(), m * sizeof(complex_t));
+            pos += m;
+        }
+        delete d;
+        return pos;
+    }
+
+    /* Polyphase bank of the rational resampler for (interpolation, decimation) as RationalResamplerBlock::set_ratio builds it
+       (rational_resampler.cpp:27-41): returns ntaps per arm, *nfilt = arms after the gcd reduction; out[arm*ntaps + k] */
+    int ref_resampler_taps(unsigned interpolation, unsigned decimation, float *out, int cap, int *nfilt)
+    {
+        dsp::RationalResamplerBlock<complex_t> r(nullptr, interpolation, decimation);
+        *nfilt = r.pfb.nfilt;
+        if (r.pfb.nfilt * r.pfb.ntaps > cap)
+            return -1;
+        for (int a = 0; a < r.pfb.nfilt; a++)
+            for (int k = 0; k < r.pfb.ntaps; k++)
+                out[a * r.pfb.ntaps + k] = r.pfb.taps[a][k];
+        return r.pfb.ntaps;
     }
 
     /* Carried loop state, for stage-isolated tests */

@@ -19,7 +19,7 @@ E_NAMES = {0: "OK", -1: "EINVAL", -2: "ENODEV", -3: "ECUDA", -4: "ENOMEM", -5: "
 
 # every symbol include/b200dsp.h declares (tests check the built library exports all of them)
 SYMBOLS = [
-    "b200_last_error", "b200_device_count",
+    "b200_last_error", "b200_device_count", "b200_demod_final_samplerate",
     "b200_demod_create", "b200_demod_destroy", "b200_demod_push_iq", "b200_demod_push_iq_device", "b200_demod_pull_soft",
     "b200_demod_pull_symbols", "b200_demod_debug_stage", "b200_demod_debug_convert", "b200_demod_get_stats", "b200_demod_get_taps",
     "b200_fec_create", "b200_fec_destroy", "b200_fec_push_soft", "b200_fec_push_soft_device", "b200_fec_pull_frames",
@@ -35,7 +35,7 @@ class DemodCfg(C.Structure):
                 ("rrc_taps", C.c_int), ("pll_bw", C.c_float), ("agc_rate", C.c_float), ("clock_gain_omega", C.c_float),
                 ("clock_mu", C.c_float), ("clock_gain_mu", C.c_float), ("clock_omega_limit", C.c_float),
                 ("costas_max_offset", C.c_float), ("format", C.c_int), ("device", C.c_int), ("max_batch", C.c_long),
-                ("keep_stages", C.c_int)]
+                ("keep_stages", C.c_int), ("iq_swap", C.c_int), ("final_samplerate", C.c_double)]
 
 
 class FecCfg(C.Structure):
@@ -50,7 +50,7 @@ class DemodStats(C.Structure):
     _fields_ = [("samples_in", C.c_long), ("symbols_out", C.c_long), ("agc_gain", C.c_float), ("costas_phase", C.c_float),
                 ("costas_freq", C.c_float), ("mm_mu", C.c_float), ("mm_omega", C.c_float), ("costas_unconverged", C.c_long),
                 ("mm_unconverged", C.c_long), ("agc_clamped", C.c_int), ("repairs", C.c_int), ("kernel_launches", C.c_long),
-                ("agc_exact_passes", C.c_long)]
+                ("agc_exact_passes", C.c_long), ("last_front_samples", C.c_long)]
 
 
 class FecStats(C.Structure):
@@ -77,6 +77,8 @@ def lib():
         vp, ci, cl = C.c_void_p, C.c_int, C.c_long
         L.b200_last_error.restype = C.c_char_p
         L.b200_demod_create.restype = vp
+        L.b200_demod_final_samplerate.restype = C.c_double
+        L.b200_demod_final_samplerate.argtypes = [C.c_double, C.c_double, ci, C.c_float, C.c_float, C.c_double]
         L.b200_demod_create.argtypes = [C.POINTER(DemodCfg)]
         L.b200_demod_destroy.argtypes = [vp]
         L.b200_demod_push_iq.argtypes = [vp, vp, cl]
@@ -127,15 +129,26 @@ def _chk(rc):
 
 def demod_cfg(samplerate, symbolrate, constellation, rrc_alpha, pll_bw=0.003, fmt="cs16", rrc_taps=31, agc_rate=1e-2, clock_alpha=None,
               clock_gain_omega=None, clock_mu=0.5, clock_gain_mu=8.7e-3, clock_omega_limit=0.005, costas_max_offset=1.0, device=0,
-              max_batch=1 << 24, keep_stages=False):
-    """Parameter defaults = module_psk_demod.h:31-39, module_demod_base.h:54."""
+              max_batch=1 << 24, keep_stages=False, iq_swap=False, final_samplerate=None, min_sps=0.0, max_sps=0.0):
+    """Parameter defaults = module_psk_demod.h:31-39, module_demod_base.h:54. final_samplerate=None applies BaseDemodModule::initb's
+    rule (resample when samplerate/symbolrate is outside [min_sps, max_sps]); 0 forces "no resampler"."""
+    if final_samplerate is None:
+        final_samplerate = final_samplerate_of(samplerate, symbolrate, constellation, min_sps, max_sps)
+        if final_samplerate == float(int(samplerate)):
+            final_samplerate = 0.0
     if clock_alpha is not None:
         clock_gain_omega = float(np.float32(clock_alpha) ** 2 / 4.0)
         clock_gain_mu = clock_alpha
     if clock_gain_omega is None:
         clock_gain_omega = float(np.float32(pow(8.7e-3, 2) / 4.0))
     return DemodCfg(float(samplerate), float(symbolrate), CONST[constellation], rrc_alpha, rrc_taps, pll_bw, agc_rate, clock_gain_omega,
-                    clock_mu, clock_gain_mu, clock_omega_limit, costas_max_offset, FMT[fmt], device, max_batch, int(keep_stages))
+                    clock_mu, clock_gain_mu, clock_omega_limit, costas_max_offset, FMT[fmt], device, max_batch, int(keep_stages), int(iq_swap),
+                    float(final_samplerate))
+
+
+def final_samplerate_of(samplerate, symbolrate, constellation, min_sps=0.0, max_sps=0.0, custom=0.0):
+    """BaseDemodModule::initb's working sample rate (module_demod_base.cpp:59-87)."""
+    return lib().b200_demod_final_samplerate(float(samplerate), float(symbolrate), CONST[constellation], min_sps, max_sps, custom)
 
 
 def metop_cfg(ber_thresold=0.28, outsync_after=10, device=0, max_soft=1 << 24):
@@ -203,8 +216,10 @@ class Demod:
         return out[:n.value].copy()
 
     def stage(self, which):
-        out = np.zeros(self._n, np.complex64)
-        _chk(lib().b200_demod_debug_stage(self.h, {"agc": 0, "fir": 1, "costas": 2}[which], out.ctypes.data, self._n))
+        """agc / fir / costas stage outputs, or resamp = what entered the AGC when the front-end resampler / iq_swap runs."""
+        n = self.stats()["last_front_samples"]
+        out = np.zeros(n, np.complex64)
+        _chk(lib().b200_demod_debug_stage(self.h, {"agc": 0, "fir": 1, "costas": 2, "resamp": 3}[which], out.ctypes.data, n))
         return out
 
     def convert(self, raw):

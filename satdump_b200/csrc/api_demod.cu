@@ -1,6 +1,7 @@
 // C ABI + host driver of the demodulator (see include/b200dsp.h, demod_host.h).
 #define B200_DEFINE_KERNELS
 #include "demod_host.h"
+#include <string>
 #include <algorithm>
 #include <cmath>
 #include <mutex>
@@ -88,6 +89,80 @@ void design_mm_bank(std::vector<float> &out)
     }
 }
 
+// Kaiser-windowed low-pass of the rational resampler, evaluated like firdes::design_resampler_filter_float -> firdes::low_pass ->
+// window::kaiser (src-core/common/dsp/filter/firdes.cpp:276-301, 80-120, 453-478, Izero 357-373) so the float taps come out
+// identical, then folded into arms like PolyphaseBank::init (resamp/polyphase_bank.cpp:6-39).
+static double izero(double x)
+{
+    double sum = 1, u = 1;
+    int n = 1;
+    const double halfx = x / 2.0;
+    do {
+        double temp = halfx / (double)n;
+        n += 1;
+        temp *= temp;
+        u *= temp;
+        sum += u;
+    } while (u >= 1E-21 * sum);
+    return sum;
+}
+
+int design_resampler_bank(unsigned I, unsigned D, std::vector<float> &bank)
+{
+    const float beta = 7.0f, halfband = 0.5f, fractional_bw = 0.4f, rate = (float)I / (float)D;
+    float trans_width, mid;
+    if (rate >= 1.0f) {
+        trans_width = halfband - fractional_bw;
+        mid = (float)(halfband - trans_width / 2.0);
+    } else {
+        trans_width = rate * (halfband - fractional_bw);
+        mid = (float)(rate * halfband - trans_width / 2.0);
+    }
+    double gain = I;
+    const double fs = I, cutoff = mid, tw = trans_width, b = beta;
+    const double a = b / 0.1102 + 8.7;
+    int ntaps = (int)(a * fs / (22.0 * tw));
+    if ((ntaps & 1) == 0)
+        ntaps++;
+    std::vector<float> taps(ntaps), w(ntaps);
+    {
+        const double IBeta = 1.0 / izero(b), inm1 = 1.0 / ((double)(ntaps - 1));
+        w[0] = (float)IBeta;
+        for (int i = 1; i < ntaps - 1; i++) {
+            const double temp = 2 * i * inm1 - 1;
+            w[i] = (float)(izero(b * sqrt(1.0 - temp * temp)) * IBeta);
+        }
+        w[ntaps - 1] = (float)IBeta;
+    }
+    const int M = (ntaps - 1) / 2;
+    const double fwT0 = 2 * M_PI * cutoff / fs;
+    for (int n = -M; n <= M; n++)
+        taps[n + M] = n == 0 ? (float)(fwT0 / M_PI * w[n + M]) : (float)(sin(n * fwT0) / (n * M_PI) * w[n + M]);
+    double fmax = taps[M];
+    for (int n = 1; n <= M; n++)
+        fmax += 2 * taps[n + M];
+    gain /= fmax;
+    for (int i = 0; i < ntaps; i++)
+        taps[i] = (float)(taps[i] * gain);
+    int nt = (ntaps + (int)I - 1) / (int)I;
+    if (fmod((double)ntaps / (double)I, 1.0) > 0.0)
+        nt++;
+    bank.assign((size_t)I * nt, 0.f);
+    for (int i = 0; i < (int)I * nt; i++)
+        bank[(size_t)((I - 1) - (i % I)) * nt + i / I] = i < ntaps ? taps[i] : 0.f;
+    return nt;
+}
+
+static unsigned gcd_u(unsigned a, unsigned b)
+{
+    while (b) {
+        unsigned t = a % b;
+        a = b;
+        b = t;
+    }
+    return a;
+}
+
 static int round_up16(double v) { return ((int)std::ceil(v / 16.0)) * 16; }
 static int repair_rounds()
 {
@@ -113,23 +188,58 @@ Demod::Demod(const b200_demod_cfg &c) : cfg(c)
     B200_REQUIRE(c.agc_rate > 0 && c.agc_rate < 0.5f, B200_EINVAL, "agc_rate out of range");
     B200_REQUIRE(c.clock_gain_mu > 0 && c.pll_bw > 0, B200_EINVAL, "loop gains must be positive");
     const long fs = (long)c.samplerate, rs = (long)c.symbolrate;
-    const float final_fs = (float)fs;
+    const float final_fs = c.final_samplerate > 0 ? (float)c.final_samplerate : (float)fs; // float final_samplerate (module_demod_base.h:67)
     sps = final_fs / (float)rs;
-    // the reference resamples outside [MIN_SPS, MAX_SPS] (module_demod_base.cpp:66-80, module_psk_demod.cpp:65-70): not built here
+    // the loops are built for the reference's working window (module_demod_base.h:71-72, module_psk_demod.cpp:65-70); outside it
+    // the reference resamples first: pass final_samplerate = b200_demod_final_samplerate(...)
     const float lo = c.constellation == B200_OQPSK ? 1.6f : 1.1f, hi = c.constellation == B200_OQPSK ? 2.4f : 4.0f;
-    B200_REQUIRE(sps >= lo && sps <= hi, B200_EINVAL, "samples per symbol %.4f outside [%.1f, %.1f]: the resampler front-end is not part of this build", sps,
-                 lo, hi);
+    B200_REQUIRE(sps >= lo * 0.999f && sps <= hi * 1.001f, B200_EINVAL,
+                 "samples per symbol %.4f outside [%.1f, %.1f]: set final_samplerate (b200_demod_final_samplerate) so that the front-end resampler runs", sps, lo,
+                 hi);
+    if (c.final_samplerate > 0 && (long)c.final_samplerate != fs) {
+        // SmartResamplerBlock(input, final_samplerate, d_samplerate) -> (unsigned interpolation, unsigned decimation), smart_resampler.cpp:8-61
+        const unsigned interpolation = (unsigned)final_fs, decimation = (unsigned)fs;
+        B200_REQUIRE(interpolation > 0, B200_EINVAL, "final_samplerate too small");
+        double rsamp_in = decimation, fout = interpolation;
+        if (decimation > interpolation) {
+            const int best_power = (int)floor(log2((double)(decimation / interpolation)));
+            B200_REQUIRE(best_power <= 0, B200_EUNSUPPORTED,
+                         "samplerate / final_samplerate >= 2 needs SmartResamplerBlock's power-of-two decimator, whose tap tables are not part of this build");
+        }
+        unsigned I = (unsigned)fout, D = (unsigned)rsamp_in;
+        const unsigned g = gcd_u(I, D);
+        I /= g;
+        D /= g;
+        rs_I = (int)I;
+        rs_D = (int)D;
+        rs_nt = design_resampler_bank(I, D, rs_bank);
+        B200_REQUIRE(rs_nt <= RS_MAX_TAPS, B200_EUNSUPPORTED, "resampler arm of %d taps exceeds the built maximum %d", rs_nt, RS_MAX_TAPS);
+        resamp = true;
+    } else if (c.iq_swap) { // the plain swap runs as the identity resampler
+        rs_bank.assign(1, 1.0f);
+        resamp = true;
+    }
     check_device(c.device);
     DeviceGuard g(c.device);
     bps = c.constellation == B200_BPSK ? 1 : 2;
     order = c.constellation == B200_BPSK ? 2 : (c.constellation == B200_8PSK ? 8 : (c.constellation == B200_NONE ? 0 : 4));
     max_batch = c.max_batch;
+    max_work = resamp ? std::max<long>(max_batch, (long)((double)max_batch * rs_I / rs_D) + 64) : max_batch;
     design_rrc(1, final_fs, (double)(int)rs, c.rrc_alpha, c.rrc_taps, rrc);
     design_mm_bank(bank);
     Wc = round_up16(24.0 / c.pll_bw);
-    // M&M warm-up: the critically damped timing loop needs ~10 time constants to land on the sequential trajectory to ~1e-4
-    // sample (measured: QPSK 3200 symbols -> max 1e-3; BPSK's TED gain is lower -> slower)
-    Wm = round_up16((c.constellation == B200_BPSK ? 120.0 : 70.0) / c.clock_gain_mu);
+    // M&M warm-up: the timing loop has to land on the sequential trajectory to ~1e-4 sample. Its time constant is 1/(gain_mu * K)
+    // symbols with a TED gain K that falls with the samples per symbol (the pulse slope per sample) and is about half as large for
+    // BPSK (one rail), i.e. ~ sps^2 in samples. Measured on 2^21-sample signals: QPSK sps 2.57 with 70/gain_mu samples sits at the
+    // reference's own chaos floor (1.1-1.6 % of the symbols off by an interpolator arm); BPSK needs 240/gain_mu at sps 2.5 and
+    // 4x that... i.e. (sps/2.5)^2 more at sps 3.6 (0.5 % = floor; with half of it 3 %, with a quarter 49 %).
+    {
+        const double ref_sps = c.constellation == B200_BPSK ? 2.5 : 2.5714;
+        const double scale = std::max(1.0, (double)sps * sps / (ref_sps * ref_sps));
+        Wm = round_up16((c.constellation == B200_BPSK ? 240.0 : 70.0) * scale / c.clock_gain_mu);
+    }
+    if (const char *e = getenv("B200_MM_WARMUP_SCALE")) // tuning hook
+        Wm = round_up16(Wm * atof(e));
     int dev_sms = 148;
     cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, c.device);
     seg_cap_threads = dev_sms * 3 * SEG_THREADS;
@@ -142,13 +252,13 @@ Demod::Demod(const b200_demod_cfg &c) : cfg(c)
     B200_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
     for (auto &p : pf)
         B200_CUDA(cudaEventCreateWithFlags(&p.done, cudaEventDisableTiming));
-    bufA.alloc(max_batch + 64);
-    bufB.alloc(max_batch + 64);
+    bufA.alloc(max_work + 64);
+    bufB.alloc(max_work + 64);
     if (c.keep_stages) {
-        agc_dump.alloc(max_batch);
-        fir_dump.alloc(max_batch);
+        agc_dump.alloc(max_work);
+        fir_dump.alloc(max_work);
     }
-    const int ntiles_max = (int)((max_batch + FIR_TILE - 1) / FIR_TILE);
+    const int ntiles_max = (int)((max_work + FIR_TILE - 1) / FIR_TILE);
     tile_map.alloc(ntiles_max + 1);
     seeds.alloc(ntiles_max + 2);
     agc_need.alloc(2);
@@ -162,7 +272,7 @@ Demod::Demod(const b200_demod_cfg &c) : cfg(c)
         B200_CUDA(cudaFuncSetAttribute(k_agc_fir<1, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         B200_CUDA(cudaFuncSetAttribute(k_agc_fir<2, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         int per_sm = 0;
-        if (c.format == B200_CF32)
+        if (c.format == B200_CF32 || resamp)
             B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_agc_fir<0, false>, FIR_THREADS, 0));
         else if (c.format == B200_CS16)
             B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_agc_fir<1, false>, FIR_THREADS, 0));
@@ -174,17 +284,22 @@ Demod::Demod(const b200_demod_cfg &c) : cfg(c)
     }
     // worst-case segment count / slot storage: L >= 1024
     const int lmin = 1024;
-    const long nseg_max = (max_batch + lmin - 1) / lmin + 1;
+    const long nseg_max = (max_work + lmin - 1) / lmin + 1;
     crec.alloc(nseg_max);
     mrec.alloc(nseg_max);
     quad.alloc(nseg_max);
     offs.alloc(nseg_max + 1);
     repair.alloc(1025);
     const double omin = sps * (1.0 - c.clock_omega_limit) - 0.01;
-    slots.alloc((size_t)(max_batch / omin) + nseg_max * 24 + 1024);
-    sym_out.alloc((size_t)(max_batch / omin) + 1024);
-    soft.alloc(((size_t)(max_batch / omin) + 1024) * bps);
+    slots.alloc((size_t)(max_work / omin) + nseg_max * 24 + 1024);
+    sym_out.alloc((size_t)(max_work / omin) + 1024);
+    soft.alloc(((size_t)(max_work / omin) + 1024) * bps);
     d_bank.alloc(128 * 8);
+    if (resamp) {
+        d_rs_bank.alloc(rs_bank.size());
+        rs_out.alloc(max_work + 64);
+        B200_CUDA(cudaMemcpyAsync(d_rs_bank.p, rs_bank.data(), rs_bank.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
+    }
     st.alloc(1);
     B200_CUDA(cudaMemcpyAsync(d_bank.p, bank.data(), 128 * 8 * sizeof(float), cudaMemcpyHostToDevice, stream));
     B200_CUDA(cudaMallocHost((void **)&h_total, sizeof(long)));
@@ -240,6 +355,7 @@ void Demod::reset()
     B200_CUDA(cudaStreamSynchronize(stream));
     parity = 0;
     last_n = last_syms = 0;
+    rs_inc = rs_ctr = 0;
 }
 
 int Demod::choose_L(long n) const
@@ -292,16 +408,41 @@ long Demod::process(const void *d_raw, long n, int8_t *soft_dst)
     DeviceGuard g(cfg.device);
     const int cur = parity, nxt = parity ^ 1;
     DemodDevState *S = st.p;
+    const long n_in = n;
+    int front_fmt = cfg.format;
+    B200_CUDA(cudaEventRecord(ev[0], stream));
+    if (resamp) {
+        // outputs of this batch: all j >= 0 with rs_inc + (rs_ctr + j*D) / I < n  (the while loop of rational_resampler.cpp:48-57)
+        const long I = rs_I, D = rs_D;
+        long J = 0;
+        if (n > rs_inc)
+            J = ((n - rs_inc) * I - rs_ctr + D - 1) / D;
+        B200_REQUIRE(J >= 64 && J <= max_work, B200_ESTATE, "batch of %ld samples resamples to %ld: outside [64, %ld]", n, J, max_work);
+        const unsigned grid = (unsigned)((J + RS_THREADS - 1) / RS_THREADS);
+        if (cfg.format == B200_CF32)
+            k_resample<0><<<grid, RS_THREADS, 0, stream>>>(d_raw, n, cfg.iq_swap, S->rs_tail[cur], S->rs_tail[nxt], d_rs_bank.p, rs_I, rs_D, rs_nt, rs_inc, rs_ctr, J, rs_out.p);
+        else if (cfg.format == B200_CS16)
+            k_resample<1><<<grid, RS_THREADS, 0, stream>>>(d_raw, n, cfg.iq_swap, S->rs_tail[cur], S->rs_tail[nxt], d_rs_bank.p, rs_I, rs_D, rs_nt, rs_inc, rs_ctr, J, rs_out.p);
+        else
+            k_resample<2><<<grid, RS_THREADS, 0, stream>>>(d_raw, n, cfg.iq_swap, S->rs_tail[cur], S->rs_tail[nxt], d_rs_bank.p, rs_I, rs_D, rs_nt, rs_inc, rs_ctr, J, rs_out.p);
+        launches++;
+        const long c_end = rs_ctr + J * D;
+        rs_inc = rs_inc + c_end / I - n;
+        rs_ctr = c_end % I;
+        d_raw = rs_out.p;
+        n = J;
+        front_fmt = B200_CF32;
+    }
+    last_front = n;
     const int ntiles = (int)((n + FIR_TILE - 1) / FIR_TILE);
     FirTaps taps;
     memset(&taps, 0, sizeof(taps));
     for (int i = 0; i < FIR_NT; i++)
         taps.h[i] = rrc[i];
-    B200_CUDA(cudaEventRecord(ev[0], stream));
     const bool dump = cfg.keep_stages != 0;
-    if (cfg.format == B200_CF32)
+    if (front_fmt == B200_CF32)
         launch_front<0>(*this, d_raw, n, ntiles, taps, cur, dump);
-    else if (cfg.format == B200_CS16)
+    else if (front_fmt == B200_CS16)
         launch_front<1>(*this, d_raw, n, ntiles, taps, cur, dump);
     else
         launch_front<2>(*this, d_raw, n, ntiles, taps, cur, dump);
@@ -371,7 +512,7 @@ long Demod::process(const void *d_raw, long n, int8_t *soft_dst)
     parity = nxt;
     last_n = n;
     last_syms = *h_total;
-    total_in += n;
+    total_in += n_in;
     total_syms += last_syms;
     if (h_state->flags & 1)
         throw ApiError(B200_EUNSUPPORTED, "AGC gain reached max_gain (65536): input is (near) silent; the scan formulation does not cover the clamp");
@@ -442,6 +583,7 @@ void Demod::stats(b200_demod_stats *o)
     o->repairs = h_state->repairs;
     o->kernel_launches = launches;
     o->agc_exact_passes = h_state->agc_exact;
+    o->last_front_samples = last_front;
 }
 
 } // namespace b200
@@ -518,6 +660,32 @@ int b200_demod_pull_symbols(b200_demod *h, float *out, long cap_symbols, long *n
         *n_out = d.last_syms;
     });
 }
+double b200_demod_final_samplerate(double samplerate, double symbolrate, int constellation, float min_sps, float max_sps, double custom_samplerate)
+{
+    // module_demod_base.cpp:59-80 with its types: long d_samplerate, int d_symbolrate, float MIN_SPS / MAX_SPS / final_samplerate
+    const long d_samplerate = (long)samplerate;
+    const int d_symbolrate = (int)symbolrate;
+    float MIN_SPS = constellation == B200_OQPSK ? 1.6f : 1.1f, MAX_SPS = constellation == B200_OQPSK ? 2.4f : 4.0f; // module_psk_demod.cpp:65-70
+    if (min_sps > 0)
+        MIN_SPS = min_sps;
+    if (max_sps > 0)
+        MAX_SPS = max_sps;
+    if (d_symbolrate <= 0 || d_samplerate <= 0)
+        return samplerate;
+    const float input_sps = (float)d_samplerate / (float)d_symbolrate;
+    const bool resample = input_sps > MAX_SPS || input_sps < MIN_SPS;
+    const int range = (int)pow(10, (std::to_string(int(d_symbolrate)).size() - 1));
+    float final_samplerate = (float)d_samplerate;
+    if (custom_samplerate > 0)
+        final_samplerate = (float)(long)custom_samplerate;
+    else if (MAX_SPS == MIN_SPS)
+        final_samplerate = d_symbolrate * MAX_SPS;
+    else if (input_sps > MAX_SPS)
+        final_samplerate = resample ? (round(d_symbolrate / range) * range) * MAX_SPS : d_samplerate;
+    else if (input_sps < MIN_SPS)
+        final_samplerate = resample ? d_symbolrate * MIN_SPS : d_samplerate;
+    return (double)final_samplerate;
+}
 int b200_demod_debug_stage(b200_demod *h, int stage, float *out, long cap_samples)
 {
     return guarded([&] {
@@ -532,6 +700,8 @@ int b200_demod_debug_stage(b200_demod *h, int stage, float *out, long cap_sample
             src = d.fir_dump.p;
         else if (stage == B200_STAGE_COSTAS)
             src = (d.order ? d.bufA.p : d.bufB.p) + 16; // M&M input = Costas output after rotation fix-up (+ OQPSK delay)
+        else if (stage == B200_STAGE_RESAMP && d.resamp)
+            src = d.rs_out.p; // what entered the AGC: front-end resampler / iq_swap output
         B200_REQUIRE(src, B200_EINVAL, "unknown stage %d", stage);
         DeviceGuard g(d.cfg.device);
         B200_CUDA(cudaMemcpyAsync(out, src, d.last_n * sizeof(float2), cudaMemcpyDeviceToHost, d.stream));

@@ -30,6 +30,9 @@ constexpr int FIR_TILE = 2048;       // samples (= outputs) per tile: 256 thread
 constexpr int FIR_THREADS = 256;
 constexpr int FIR_BUF = FIR_TILE + 32;                   // smem tile with the 32-sample history in front
 constexpr int FIR_BUF_F2 = FIR_BUF + 2 * (FIR_BUF / 8);  // padded (see xidx)
+constexpr int RS_THREADS = 256;      // front-end resampler: outputs per CTA
+constexpr int RS_MAX_TAPS = 160;     // taps per polyphase arm
+constexpr int RS_SPAN = 2 * RS_THREADS + RS_MAX_TAPS + 8; // decimation < 2: at most 2 input samples per output
 constexpr int SEG_THREADS = 128;     // threads (= stream segments) per CTA in the loop kernels
 constexpr int MM_BANK_STRIDE = 9; // floats per arm row in smem: spreads the per-thread random arm reads over the banks
 constexpr int MM_SMEM_BYTES = 64 * SEG_THREADS * 8 + 128 * MM_BANK_STRIDE * 4;
@@ -147,6 +150,75 @@ __global__ void k_convert_only(const void *__restrict__ raw, long N, float2 *__r
     load8<FMT>(raw, s0, N, x);
     for (int i = 0; i < 8; i++)
         if (s0 + i < N) out[s0 + i] = x[i];
+}
+
+// ---------------------------------------------------------------- K0: front-end rational resampler (+ iq_swap)
+// RationalResamplerBlock::process (resamp/rational_resampler.cpp:43-65) in closed form: with the carried counters (inc0, ctr0) of the
+// batch, output j reads the ntaps-long window starting at buffer index inc0 + (ctr0 + j*D) / I with arm (ctr0 + j*D) % I of the
+// polyphase bank, where buffer index b < ntaps-1 is the previous batch's tail and b >= ntaps-1 is input sample b - (ntaps-1).
+// No feedback, so every output is independent: one thread per output, the CTA's input span staged (converted, optionally re<->im
+// swapped: file_source.cpp:31-33) in shared memory. I = D = 1 with the one-tap bank {1} is the plain iq_swap pass.
+
+template <int FMT> __device__ __forceinline__ float2 load1(const void *__restrict__ raw, long s)
+{
+    if (FMT == 1) {
+        const short2 v = reinterpret_cast<const short2 *>(raw)[s];
+        return make_float2(cvt_s16((float)v.x), cvt_s16((float)v.y));
+    } else if (FMT == 2) {
+        const char2 v = reinterpret_cast<const char2 *>(raw)[s];
+        return make_float2(cvt_s8((float)v.x), cvt_s8((float)v.y));
+    } else
+        return reinterpret_cast<const float2 *>(raw)[s];
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(RS_THREADS) k_resample(const void *__restrict__ raw, long n_in, int iq_swap, const float2 *__restrict__ tail_in,
+                                                         float2 *__restrict__ tail_out, const float *__restrict__ bank, int I, int D, int nt, long inc0,
+                                                         long ctr0, long J, float2 *__restrict__ out)
+{
+    __shared__ float2 xs[RS_SPAN];
+    const int t = threadIdx.x;
+    const long j0 = (long)blockIdx.x * RS_THREADS;
+    if (blockIdx.x == 0 && t < nt) { // new tail = buffer[n_in .. n_in + nt - 1) (memmove of rational_resampler.cpp:62)
+        const long b = n_in + t;
+        if (t < nt - 1) {
+            float2 v = b < nt - 1 ? tail_in[b] : load1<FMT>(raw, b - (nt - 1));
+            if (b >= nt - 1 && iq_swap)
+                v = make_float2(v.y, v.x);
+            tail_out[t] = v;
+        }
+    }
+    if (j0 >= J)
+        return;
+    const long jl = min(j0 + RS_THREADS, J) - 1; // last output of this CTA
+    const long b_first = inc0 + (ctr0 + j0 * D) / I, b_last = inc0 + (ctr0 + jl * D) / I + nt - 1;
+    const int span = (int)(b_last - b_first + 1);
+    for (int q = t; q < span; q += RS_THREADS) {
+        const long b = b_first + q;
+        float2 v;
+        if (b < nt - 1)
+            v = tail_in[b];
+        else {
+            v = load1<FMT>(raw, b - (nt - 1));
+            if (iq_swap)
+                v = make_float2(v.y, v.x);
+        }
+        xs[q] = v;
+    }
+    __syncthreads();
+    const long j = j0 + t;
+    if (j < J) {
+        const long c = ctr0 + j * D;
+        const int off = (int)(inc0 + c / I - b_first);
+        const float *tp = bank + (long)(c % I) * nt;
+        float re = 0.f, im = 0.f;
+        for (int k = 0; k < nt; k++) {
+            const float h = __ldg(tp + k);
+            re = fmaf(xs[off + k].x, h, re);
+            im = fmaf(xs[off + k].y, h, im);
+        }
+        out[j] = make_float2(re, im);
+    }
 }
 
 // sqrt(s2) as s2 * rsqrt(s2): one MUFU + one FMUL (~2 ulp); the max() keeps 0 * inf out (s2 == 0 -> 0)

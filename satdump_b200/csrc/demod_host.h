@@ -16,6 +16,7 @@ struct DemodDevState
     float costas[2][2]; // phase, freq
     MMState mm[2];
     float2 agc_tail[2][32];
+    float2 rs_tail[2][RS_MAX_TAPS]; // resampler history (ntaps-1 converted input samples)
     float2 mm_hist[2][8];
     int flags;          // bit0 AGC clamp, bit1 M&M slot overflow
     int costas_unconv;  // junctions still unconverged after the repair rounds of the last batch
@@ -61,6 +62,15 @@ class Demod
     DevBuf<int> agc_need;          // [2] raised by the fast pass when a range cannot prove its seed
     unsigned agc_epoch = 0;
     int fir_ctas = 0;              // resident k_agc_fir CTAs on the device (one wave of ranges)
+    // front-end resampler (RationalResamplerBlock) / iq_swap pass
+    bool resamp = false;
+    int rs_I = 1, rs_D = 1, rs_nt = 1;
+    long rs_inc = 0, rs_ctr = 0;   // carried counters (rational_resampler.h: inc, d_ctr)
+    std::vector<float> rs_bank;
+    DevBuf<float> d_rs_bank;
+    DevBuf<float2> rs_out;
+    long max_work = 0;             // largest sample count after the front end
+    long last_front = 0;           // samples that entered the AGC in the last batch
     int agc_warm_max = 24;
     DevBuf<LoopRec> crec;
     DevBuf<MMRec> mrec;
@@ -80,5 +90,7 @@ class Demod
 
 void design_rrc(double gain, double fs, double rs, double alpha, int ntaps, std::vector<float> &out);
 void design_mm_bank(std::vector<float> &out);
+// RationalResamplerBlock::set_ratio's bank for the reduced (I, D): returns taps per arm, bank[arm * ntaps + k]
+int design_resampler_bank(unsigned I, unsigned D, std::vector<float> &bank);
 
 } // namespace b200

@@ -139,8 +139,6 @@ b200_demod_cfg demod_cfg_from_params(const Params &p, bool &is_bpsk)
     c.clock_gain_mu = (float)p.num("clock_gain_mu", c.clock_gain_mu);
     c.clock_omega_limit = (float)p.num("clock_omega_relative_limit", c.clock_omega_limit);
     c.costas_max_offset = 1.0f;
-    if (p.has("costas_max_offset")) // Hz -> rad/sample (module_psk_demod.cpp:116-118)
-        c.costas_max_offset = (float)(2.0 * M_PI * (p.num("costas_max_offset") / c.samplerate));
     const std::string fmt = p.str("baseband_format", "cf32"); // common/dsp/io/baseband_type.cpp:103-127
     if (fmt == "cf32" || fmt == "f32") c.format = B200_CF32;
     else if (fmt == "cs16" || fmt == "s16") c.format = B200_CS16;
@@ -148,11 +146,20 @@ b200_demod_cfg demod_cfg_from_params(const Params &p, bool &is_bpsk)
     else throw ModuleError("baseband_format " + fmt + " is not supported by the B200 path (cf32/cs16/cs8 only)");
     reject(p, "dc_block", "CorrectIQ block");
     reject(p, "freq_shift", "FreqShift block");
-    reject(p, "iq_swap", "IQ swap");
+    c.iq_swap = p.flag("iq_swap", false); // module_demod_base.cpp:41-42 -> FileSourceBlock
     reject(p, "post_costas_dc", "CorrectIQ block");
     reject(p, "has_carrier", "PLL carrier tracking");
     reject(p, "enable_doppler", "Doppler correction");
-    reject(p, "custom_samplerate", "resampler");
+    // BaseDemodModule::initb (module_demod_base.cpp:59-87): outside [min_sps, max_sps] the front-end resampler converts to this rate
+    c.final_samplerate = b200_demod_final_samplerate(c.samplerate, c.symbolrate, c.constellation, (float)p.num("min_sps", 0), (float)p.num("max_sps", 0),
+                                                     p.has("custom_samplerate") ? (double)(long)p.num("custom_samplerate") : 0.0);
+    if (c.final_samplerate == c.samplerate)
+        c.final_samplerate = 0;
+    if ((float)c.samplerate / (float)c.symbolrate < 1.0f) // module_demod_base.cpp:96-105
+        throw ModuleError("Your sampling rate is too low! Minimum: " +
+                          (c.symbolrate > 1e6 ? std::to_string(c.symbolrate / 1e6) + " Msps" : std::to_string(c.symbolrate / 1e3) + " ksps"));
+    if (p.has("costas_max_offset")) // Hz -> rad/sample at the working rate (module_psk_demod.cpp:116-118)
+        c.costas_max_offset = (float)(2.0 * M_PI * (p.num("costas_max_offset") / (c.final_samplerate > 0 ? c.final_samplerate : c.samplerate)));
     reject(p, "dump_intermediate", "intermediate dump");
     c.device = (int)p.num("b200_device", 0);
     return c;

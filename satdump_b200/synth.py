@@ -201,6 +201,14 @@ CONFIGS = {
     "jpss_hrd": SignalCfg(name="jpss_hrd", samplerate=30e6, symbolrate=15000000, constellation="oqpsk", conv="1/2", interleave=5,
                           nrzm=True, pll_bw=0.002, fmt="cs16", decoder="ccsds", ber_thresold=0.3, outsync_after=20, rs_usecheck=True,
                           esn0_db=7.0),
+    # C2 at the real NOAA HRPT rate: 665.4 kbaud @ 3 MS/s = 4.51 samples/symbol > MAX_SPS, so BaseDemodModule's front-end resampler
+    # runs first (module_demod_base.cpp:66-80,203-204): 3 MS/s -> 2.4 MS/s (4/5), 3.607 samples/symbol
+    "hrpt_bpsk": SignalCfg(name="hrpt_bpsk", samplerate=3e6, symbolrate=665400, constellation="bpsk", conv="1/2", interleave=4,
+                           fmt="cf32", decoder="ccsds", ber_thresold=0.3, outsync_after=20, esn0_db=7.0),
+    # a narrow-roll-off QPSK stream recorded too slowly: 2.4 Msym/s @ 2.6 MS/s = 1.083 samples/symbol < MIN_SPS -> interpolated to
+    # 2.64 MS/s (66/65). Exercises the interpolating branch of the resampler; too close to aliasing to be a decoding test
+    "qpsk_undersampled": SignalCfg(name="qpsk_undersampled", samplerate=2.6e6, symbolrate=2400000, constellation="qpsk", conv="1/2",
+                                   interleave=4, rrc_alpha=0.1, fmt="cs16", decoder="none", esn0_db=14.0),
     # C5: DVB-S2 front half AGC->RRC->M&M, cs8, 45 Msym/s @ 90 MS/s (sps 2.0), alpha 0.25 (DVB_Test.json:132-137), REC_ALPHA 1.7e-3
     "dvbs2_front": SignalCfg(name="dvbs2_front", samplerate=90e6, symbolrate=45000000, constellation="qpsk", conv="none", interleave=4,
                              rrc_alpha=0.25, fmt="cs8", decoder="none", clock_alpha=1.7e-3, carrier_rad=0.0, phase0=0.0, esn0_db=12.0),

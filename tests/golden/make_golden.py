@@ -20,7 +20,10 @@ OUT = os.path.dirname(os.path.abspath(__file__))
 
 def main():
     assert ref.available(), "build oracle/_ref first (python -c 'import __graft_entry__ as g; g.build()')"
-    for name, lg in [("metop_ahrpt", 17), ("bpsk_half", 16), ("jpss_hrd", 17), ("dvbs2_front", 16)]:
+    only = sys.argv[1:]
+    for name, lg in [("metop_ahrpt", 17), ("bpsk_half", 16), ("jpss_hrd", 17), ("dvbs2_front", 16), ("hrpt_bpsk", 18), ("qpsk_undersampled", 16)]:
+        if only and name not in only:
+            continue
         cfg = synth.CONFIGS[name]
         raw, clear = synth.make_signal(cfg, 1 << lg, seed=0x600D, device="cpu")
         raw = raw.numpy()
@@ -28,12 +31,18 @@ def main():
         d = dict(raw=raw, soft=o["soft"], mm_head=o["mm"][:4096], fir_head=o["fir"][:4096], agc_head=o["agc"][:4096], nsym=np.int64(o["mm"].size))
         if o["costas"] is not None:
             d["costas_head"] = o["costas"][:4096]
+        dc = oracle_demod(ref, cfg).cfg
+        if dc.final_samplerate > 0:  # the front-end resampler ran: pin its output and its bank too
+            I, D = int(dc.final_samplerate), int(dc.samplerate)
+            d.update(resamp_head=ref.resample(dc, raw)[:4096], front=np.int64(o["front"]), resamp_bank=ref.resampler_taps(I, D))
         if cfg.decoder != "none":
             f = oracle_fec(ref, cfg).run(o["soft"])
             d.update(cadu=f["cadu"], bits=np.packbits(f["bits"]), nbits=np.int64(f["bits"].size), vit_state=f["vit_state"], defr_state=f["defr_state"],
                      rs_err=f["rs_err"])
         np.savez_compressed(os.path.join(OUT, f"{name}.npz"), **d)
         print(name, {k: (v.shape if hasattr(v, "shape") else v) for k, v in d.items()})
+    if only:
+        return
     # FEC stress vectors: RS decoder on codewords with 0..20 byte errors (beyond-capacity ones must fail the same way)
     rng = np.random.default_rng(0xFEC)
     pay = rng.integers(0, 256, size=(64, 4 * 223), dtype=np.uint8)

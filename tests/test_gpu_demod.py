@@ -18,7 +18,7 @@ import pytest
 from tests.common import gpu_demod, nsamples, oracle, oracle_demod, signal
 
 pytestmark = pytest.mark.gpu
-CONFIGS = ["metop_ahrpt", "bpsk_half", "jpss_hrd", "dvbs2_front"]
+CONFIGS = ["metop_ahrpt", "bpsk_half", "jpss_hrd", "dvbs2_front", "hrpt_bpsk"]
 
 
 def check_mm(gs, om, gsoft=None, osoft=None, big_soft=1e-4):
@@ -66,6 +66,9 @@ def test_stage_parity(built, name):
     n = nsamples(raw, cfg)
     o = oracle_demod(O, cfg).run(raw)
     g = gpu_demod(cfg, n, keep_stages=True).push(raw)
+    if g.cfg.final_samplerate > 0:  # front-end resampler (hrpt_bpsk): same length, same samples
+        rs = O.resample(oracle_demod(O, cfg).cfg, raw)
+        assert g.stage("resamp").size == rs.size == o["front"] and np.abs(g.stage("resamp") - rs).max() <= 2e-6
     for st in ("agc", "fir") + (("costas",) if o["costas"] is not None else ()):
         d = np.abs(g.stage(st) - o[st])
         if st == "costas" and cfg.constellation == "oqpsk":
@@ -77,7 +80,7 @@ def test_stage_parity(built, name):
     check_mm(g.symbols(), o["mm"], g.soft(), o["soft"], big_soft=3e-4 if cfg.constellation == "oqpsk" else 1e-4)
     s = g.stats()
     assert s["costas_unconverged"] == 0 and s["mm_unconverged"] == 0 and s["agc_clamped"] == 0, s
-    assert s["symbols_out"] == o["mm"].size and s["samples_in"] == n
+    assert s["symbols_out"] == o["mm"].size and s["samples_in"] == n and s["last_front_samples"] == o["agc"].size
     # carried loop state ends where the oracle's ends
     ost = oracle_demod(O, cfg)
     ost.run(raw, stages=False)
@@ -153,6 +156,44 @@ def test_weak_signal_takes_the_exact_agc_pass(built):
     assert 50 < g.stats()["agc_gain"] < 100 and g.stats()["agc_exact_passes"] == 1
     assert np.abs(g.stage("agc") - o["agc"]).max() <= 3e-5 and np.abs(g.stage("fir") - o["fir"]).max() <= 3e-5
     assert g.symbols().size == o["mm"].size
+
+
+def test_interpolating_resampler_and_streaming(built):
+    """2.4 Msym/s recorded at 2.6 MS/s (1.083 samples/symbol < MIN_SPS): the reference interpolates by 66/65 first. Stage parity of
+    the front end, and ragged pushes (the resampler's carried counters and history) give the very same resampled stream."""
+    O = oracle()
+    cfg, raw, _ = signal("qpsk_undersampled", 20)
+    n = nsamples(raw, cfg)
+    o = oracle_demod(O, cfg).run(raw)
+    g = gpu_demod(cfg, n, keep_stages=True).push(raw)
+    assert g.cfg.final_samplerate == 2640000.0
+    one = g.stage("resamp")
+    assert one.size == o["front"] and np.abs(one - O.resample(oracle_demod(O, cfg).cfg, raw)).max() <= 2e-6
+    assert np.abs(g.stage("agc") - o["agc"]).max() <= 1e-5 and np.abs(g.stage("fir") - o["fir"]).max() <= 1e-5
+    g2 = gpu_demod(cfg, n, keep_stages=True)
+    parts, prev = [], 0
+    for c in [4099, 300001, 300001 + 70000, n]:
+        g2.push(raw[2 * prev:2 * c])
+        parts.append(g2.stage("resamp"))
+        prev = c
+    assert np.array_equal(np.concatenate(parts).view(np.uint32), one.view(np.uint32))
+    assert abs(g2.stats()["agc_gain"] - g.stats()["agc_gain"]) <= 1e-5 * g.stats()["agc_gain"]
+
+
+def test_iq_swap(built):
+    """iq_swap (FileSourceBlock, file_source.cpp:31-33) = feeding the swapped samples: identical stream, bit for bit; and parity."""
+    O = oracle()
+    cfg, raw, _ = signal("metop_ahrpt", 20)
+    n = nsamples(raw, cfg)
+    from satdump_b200 import capi
+    from tests.common import demod_kwargs
+    swapped = raw.reshape(-1, 2)[:, ::-1].reshape(-1).copy()
+    a = capi.Demod(capi.demod_cfg(max_batch=n, keep_stages=True, iq_swap=True, **demod_kwargs(cfg))).push(swapped)
+    b = gpu_demod(cfg, n, keep_stages=True).push(raw)
+    assert np.array_equal(a.stage("fir").view(np.uint32), b.stage("fir").view(np.uint32))
+    assert np.array_equal(a.soft(), b.soft())
+    o = O.Demod(O.demod_cfg(iq_swap=True, **demod_kwargs(cfg))).run(swapped)
+    assert np.abs(a.stage("fir") - o["fir"]).max() <= 1e-5
 
 
 def test_errors_are_loud(built):

@@ -9,7 +9,7 @@ from tests.common import ROOT, oracle_demod, oracle_fec, signal
 from satdump_b200 import synth
 
 GOLD = os.path.join(ROOT, "tests", "golden")
-CONFIGS = ["metop_ahrpt", "bpsk_half", "jpss_hrd", "dvbs2_front"]
+CONFIGS = ["metop_ahrpt", "bpsk_half", "jpss_hrd", "dvbs2_front", "hrpt_bpsk", "qpsk_undersampled"]
 
 
 def _ref():
@@ -33,6 +33,10 @@ def test_port_matches_golden(built, name):
     assert bitwise(o["agc"][:4096], g["agc_head"]) and bitwise(o["fir"][:4096], g["fir_head"]) and bitwise(o["mm"][:4096], g["mm_head"])
     if "costas_head" in g:
         assert bitwise(o["costas"][:4096], g["costas_head"])
+    if "resamp_head" in g:  # front-end resampler: output, length and polyphase bank
+        dc = oracle_demod(port, cfg).cfg
+        assert bitwise(port.resample(dc, g["raw"])[:4096], g["resamp_head"]) and o["front"] == int(g["front"])
+        assert bitwise(port.resampler_taps(int(dc.final_samplerate), int(dc.samplerate)), g["resamp_bank"])
     assert np.array_equal(o["soft"], g["soft"])
     if cfg.decoder != "none":
         f = oracle_fec(port, cfg).run(o["soft"])
@@ -67,6 +71,34 @@ def test_port_equals_reference_fresh_signal(built, name):
         fa, fb = oracle_fec(ref, cfg).run(a["soft"]), oracle_fec(port, cfg).run(a["soft"])
         for k in ("cadu", "bits", "vit_state", "defr_state", "rs_err"):
             assert np.array_equal(fa[k], fb[k]), k
+
+
+def test_final_samplerate_rule():
+    """BaseDemodModule::initb's choice of the working rate (module_demod_base.cpp:59-80), Python restatement vs the C ABI helper."""
+    from oracle import port
+    from satdump_b200 import capi
+    cases = [(3e6, 665400, "bpsk", 2400000.0), (6e6, 2333333, "qpsk", 6e6), (30e6, 15e6, "oqpsk", 30e6), (2.6e6, 2.4e6, "qpsk", 2640000.0),
+             (50e6, 15e6, "oqpsk", None), (1e6, 72000, "bpsk", None), (12.5e6, 3.5e6, "qpsk", 12.5e6)]
+    for fs, rs, con, want in cases:
+        a, b = port.final_samplerate_of(fs, rs, con), capi.final_samplerate_of(fs, rs, con)
+        assert a == b, (fs, rs, con, a, b)
+        if want is not None:
+            assert a == want, (fs, rs, con, a)
+    assert port.final_samplerate_of(6e6, 2e6, "qpsk", min_sps=2.0, max_sps=2.0) == capi.final_samplerate_of(6e6, 2e6, "qpsk", 2.0, 2.0) == 4e6
+    assert capi.final_samplerate_of(6e6, 2e6, "qpsk", custom=5e6) == 5e6
+
+
+def test_resampler_streaming_equals_one_shot(built):
+    """The rational resampler's carried counters / history: any chunking gives the same stream (reference and restatement)."""
+    ref = _ref()
+    from oracle import port
+    cfg, raw, _ = signal("hrpt_bpsk", 17, seed=3)
+    for O in (ref, port):
+        one = oracle_demod(O, cfg).run(raw)
+        d = oracle_demod(O, cfg)
+        parts = [d.run(raw[a:b]) for a, b in [(0, 33333), (33333, 33334), (33334, 100001), (100001, raw.size)]]
+        assert bitwise(np.concatenate([p["agc"] for p in parts]), one["agc"])
+        assert np.array_equal(np.concatenate([p["soft"] for p in parts]), one["soft"])
 
 
 def test_port_low_snr_matches_reference(built):
