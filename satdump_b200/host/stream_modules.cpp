@@ -278,7 +278,8 @@ void PskDemodStage::process()
             eof = true;
         have += got;
         long ns = (long)(have / bpsamp);
-        if (ns < 64 || (!eof && have < raw.size() && fin == nullptr && ns < 65536))
+        const long min_batch = cfg.final_samplerate > 0 ? 256 : 64; // the front-end resampler must still yield 64 samples
+        if (ns < min_batch || (!eof && have < raw.size() && fin == nullptr && ns < 65536))
             continue;
         check(b200_demod_push_iq(h, raw.data(), ns), "b200_demod_push_iq");
         long n = 0;
@@ -294,7 +295,7 @@ void PskDemodStage::process()
         progress = filesize ? (double)done / (double)filesize : 0.0;
         b200_demod_stats st;
         if (b200_demod_get_stats(h, &st) == B200_OK)
-            freq = st.costas_freq * cfg.samplerate / (2.0 * M_PI); // rad_to_hz, module_psk_demod.cpp:196
+            freq = st.costas_freq * (cfg.final_samplerate > 0 ? cfg.final_samplerate : cfg.samplerate) / (2.0 * M_PI); // rad_to_hz(freq, final_samplerate), module_psk_demod.cpp:196
     }
     if (fin)
         fclose(fin);
@@ -404,18 +405,28 @@ void FusedStage::process()
     FILE *fout = fopen(output_file.c_str(), "wb");
     uint64_t done = 0;
     size_t have = 0;
+    const long min_batch = dcfg.final_samplerate > 0 ? 256 : 64;
+    const int cadu_bytes = (fcfg.kind == B200_FEC_METOP) ? 1024 : (fcfg.cadu_size + 7) / 8;
+    auto drain = [&]() { // frames of the batches decoded so far (never waits for the one in flight)
+        for (;;) {
+            long nb = 0;
+            check(b200_chain_pull_frames(h, out.data(), (long)out.size(), &nb), "b200_chain_pull_frames");
+            if (nb <= 0)
+                return;
+            fwrite(out.data(), 1, (size_t)nb, fout);
+            frames_written += nb / cadu_bytes;
+        }
+    };
+    // decoder one batch behind the demodulator on its own thread / stream, like the reference's two module threads
+    check(b200_chain_set_pipelined(h, 1), "b200_chain_set_pipelined");
     while (!should_stop) {
         size_t got = fread(raw.data() + have, 1, raw.size() - have, fin);
         have += got;
         long ns = (long)(have / bpsamp);
-        if (ns < 64)
+        if (ns < min_batch)
             break;
         check(b200_chain_push_iq(h, raw.data(), ns), "b200_chain_push_iq");
-        long nb = 0;
-        check(b200_chain_pull_frames(h, out.data(), (long)out.size(), &nb), "b200_chain_pull_frames");
-        if (nb > 0)
-            fwrite(out.data(), 1, (size_t)nb, fout);
-        frames_written += nb / ((fcfg.kind == B200_FEC_METOP) ? 1024 : (fcfg.cadu_size + 7) / 8);
+        drain();
         size_t used = (size_t)ns * bpsamp;
         memmove(raw.data(), raw.data() + used, have - used);
         have -= used;
@@ -424,6 +435,8 @@ void FusedStage::process()
         if (got == 0)
             break;
     }
+    check(b200_chain_sync(h), "b200_chain_sync");
+    drain();
     fclose(fin);
     fclose(fout);
 }

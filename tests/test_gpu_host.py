@@ -36,3 +36,27 @@ def test_cli_rejects_unsupported_options_loudly(built, tmp_path):
         base = ["--samplerate", "6e6", "--baseband_format", "cs16"]
         r = subprocess.run([TOOL, "metop_ahrpt", "baseband", str(inp), str(tmp_path / "o")] + base + extra, capture_output=True, text=True, timeout=120)
         assert r.returncode == 1 and "error" in r.stderr.lower(), (extra, r.stderr)
+
+
+def test_metop_recorded_at_12msps_goes_through_the_front_end_resampler(built, tmp_path):
+    """`--samplerate 12e6`: 5.14 samples/symbol > MAX_SPS, so BaseDemodModule::initb resamples to 8 MS/s (2/3) first
+    (module_demod_base.cpp:66-80,203-204). Same CLI, same .cadu bytes as the reference's code."""
+    import dataclasses
+    import torch
+    from satdump_b200 import synth
+    O = oracle()
+    cfg = dataclasses.replace(synth.CONFIGS["metop_ahrpt"], samplerate=12e6)
+    raw, _ = synth.make_signal(cfg, 1 << 22, seed=2, device="cuda" if torch.cuda.is_available() else "cpu")
+    raw = raw.cpu().numpy()
+    od = oracle_demod(O, cfg)
+    assert od.cfg.final_samplerate == 8e6
+    want = oracle_fec(O, cfg).run(od.run(raw, stages=False)["soft"])["cadu"]
+    assert want.size >= 20 * 1024
+    inp = tmp_path / "metop12.cs16"
+    raw.tofile(inp)
+    hint = str(tmp_path / "out12")
+    r = subprocess.run([TOOL, "metop_ahrpt", "baseband", str(inp), hint, "--samplerate", "12e6", "--baseband_format", "cs16"], capture_output=True, text=True,
+                       timeout=300)
+    assert r.returncode == 0, r.stderr
+    got = np.fromfile(hint + ".cadu", np.uint8)
+    assert got.size == want.size and np.array_equal(got, want)
