@@ -192,6 +192,19 @@ def main():
     first = next((i for i in range(min(64, clear.shape[0])) if np.array_equal(clear[i], fr[0])), None) if nfr else None
     frames_ok = first is not None and nfr > 0 and np.array_equal(fr, clear[first:first + nfr])
 
+    # PCIe ceiling of the e2e number: the same pinned batch copied host -> device alone (torch copy engine, CUDA events)
+    dst = torch.empty_like(raw)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dst.copy_(host, non_blocking=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(3):
+        dst.copy_(host, non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize()
+    h2d_gbps = 3 * host.numel() * host.element_size() / (e0.elapsed_time(e1) * 1e-3) / 1e9
+    del dst
+
     sampler = ClockSampler(local)
     sampler.start()
     # ---- per-kernel / per-stage times: one synchronous push (each kernel alone on the GPU), CUDA events on the chain's own streams
@@ -267,7 +280,9 @@ def main():
                 "config": {"workload": "METOP AHRPT QPSK + Viterbi r=3/4 + RS(255,223) I=4, cs16 @6 MS/s signal (BASELINE configs[2]), one stream per GPU",
                            "samples_per_step_per_gpu": n, "cadus_per_step_per_gpu": int(nfr), "cadus_bit_exact_vs_transmitted": bool(int(okt[0])),
                            "l2": "input batch (%.0f MiB) larger than L2" % (n * 4 / 2 ** 20), "esn0_db": cfg.esn0_db},
-                "e2e": {"value": e2e, "unit": "MS/s", "h2d_bytes_per_step": n * 4 * world, "d2h_bytes_per_step": int(nfr) * 1024 * world},
+                "e2e": {"value": e2e, "unit": "MS/s", "h2d_bytes_per_step": n * 4 * world, "d2h_bytes_per_step": int(nfr) * 1024 * world,
+                        "pcie_h2d_GBps_alone": round(h2d_gbps, 2), "pcie_bound_MSps_per_gpu": round(h2d_gbps * 1e9 / 4 / 1e6, 1),
+                        "note": "cs16 is 4 B/sample: the H2D copy of a step alone takes %.1f ms; e2e cannot exceed pcie_bound" % (n * 4 / h2d_gbps / 1e6)},
                 "gpu_launches": int(launches1 - launches0), "host_wall_ms_per_step": wall_dev_host / args.steps * 1e3,
                 "mode": "pipelined chain: decoder one batch behind the demodulator (own stream + worker thread); K fresh streams + drain inside the timed region",
                 "sync_mode": {"value": n * world / (sync_ms * 1e-3) / 1e6, "ms_per_step": sync_ms,
