@@ -131,6 +131,7 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries exactly one JSON line
     import torch
     import torch.distributed as dist
     from satdump_b200 import capi
