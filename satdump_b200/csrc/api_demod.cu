@@ -227,7 +227,11 @@ Demod::Demod(const b200_demod_cfg &c) : cfg(c)
     max_work = resamp ? std::max<long>(max_batch, (long)((double)max_batch * rs_I / rs_D) + 64) : max_batch;
     design_rrc(1, final_fs, (double)(int)rs, c.rrc_alpha, c.rrc_taps, rrc);
     design_mm_bank(bank);
-    Wc = round_up16(24.0 / c.pll_bw);
+    // Costas warm-up: 24 loop time constants for orders 2/4; the order-8 detector has about a third of the gain (measured on the
+    // psk8 signal: 0.94 % of the samples off by >1e-5 with 24/bw, 0.10 % with 48/bw, 0.015 % with 96/bw)
+    Wc = round_up16((c.constellation == B200_8PSK ? 72.0 : 24.0) / c.pll_bw);
+    if (const char *e = getenv("B200_COSTAS_WARMUP_SCALE")) // tuning hook
+        Wc = round_up16(Wc * atof(e));
     // M&M warm-up: the timing loop has to land on the sequential trajectory to ~1e-4 sample. Its time constant is 1/(gain_mu * K)
     // symbols with a TED gain K that falls with the samples per symbol (the pulse slope per sample) and is about half as large for
     // BPSK (one rail), i.e. ~ sps^2 in samples. Measured on 2^21-sample signals: QPSK sps 2.57 with 70/gain_mu samples sits at the

@@ -209,6 +209,9 @@ CONFIGS = {
     # 2.64 MS/s (66/65). Exercises the interpolating branch of the resampler; too close to aliasing to be a decoding test
     "qpsk_undersampled": SignalCfg(name="qpsk_undersampled", samplerate=2.6e6, symbolrate=2400000, constellation="qpsk", conv="1/2",
                                    interleave=4, rrc_alpha=0.1, fmt="cs16", decoder="none", esn0_db=14.0),
+    # 8PSK through psk_demod alone (order-8 Costas loop; no decoder of this path takes 8PSK): demodulator parity only
+    "psk8": SignalCfg(name="psk8", samplerate=6e6, symbolrate=2400000, constellation="8psk", conv="none", interleave=4, fmt="cs16",
+                      decoder="demod", esn0_db=18.0),
     # C5: DVB-S2 front half AGC->RRC->M&M, cs8, 45 Msym/s @ 90 MS/s (sps 2.0), alpha 0.25 (DVB_Test.json:132-137), REC_ALPHA 1.7e-3
     "dvbs2_front": SignalCfg(name="dvbs2_front", samplerate=90e6, symbolrate=45000000, constellation="qpsk", conv="none", interleave=4,
                              rrc_alpha=0.25, fmt="cs8", decoder="none", clock_alpha=1.7e-3, carrier_rad=0.0, phase0=0.0, esn0_db=12.0),
@@ -235,13 +238,19 @@ def modulate(cfg: SignalCfg, coded, seed, nsamples=None, device="cpu"):
     """coded bits -> raw IQ in cfg.fmt. Heavy lifting in torch so bench-sized signals are made on the GPU."""
     import torch
     dev = torch.device(device)
-    bps = 1 if cfg.constellation == "bpsk" else 2
+    bps = 1 if cfg.constellation == "bpsk" else (3 if cfg.constellation == "8psk" else 2)
     nsym = coded.size // bps
-    a = torch.from_numpy((coded[:nsym * bps].astype(np.float32) * 2 - 1)).to(dev)
-    if bps == 2:
-        ai, aq = a[0::2].contiguous(), a[1::2].contiguous()
+    if bps == 3:  # 8PSK: points at pi/8 + k*pi/4, where the order-8 Costas detector (costas_loop.cpp) has its stable locks
+        b = coded[:nsym * 3].reshape(-1, 3).astype(np.int64)
+        ang = np.pi / 8 + (b[:, 0] * 4 + b[:, 1] * 2 + b[:, 2]) * (np.pi / 4)
+        ai = torch.from_numpy(np.cos(ang).astype(np.float32)).to(dev)
+        aq = torch.from_numpy(np.sin(ang).astype(np.float32)).to(dev)
     else:
-        ai, aq = a, None
+        a = torch.from_numpy((coded[:nsym * bps].astype(np.float32) * 2 - 1)).to(dev)
+        if bps == 2:
+            ai, aq = a[0::2].contiguous(), a[1::2].contiguous()
+        else:
+            ai, aq = a, None
     sps = cfg.samplerate / cfg.symbolrate * (1.0 + cfg.clock_ppm * 1e-6)  # samples per symbol seen by the receiver
     span = 10
     total = int((nsym - 2 * span) * sps)

@@ -22,7 +22,7 @@ def oracle():
 
 
 def rx_const(cfg):
-    return cfg.constellation if cfg.decoder != "none" else "none"
+    return cfg.constellation if cfg.decoder != "none" else "none"  # decoder "demod": psk_demod alone, with its Costas loop
 
 
 def demod_kwargs(cfg):

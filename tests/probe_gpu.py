@@ -67,7 +67,7 @@ def main():
     s2 = gd2.symbols()
     cmp_complex("mm/2push", np.concatenate([s1, s2]), o["mm"])
     print("  stats2", gd2.stats())
-    if cfg.decoder == "none":
+    if cfg.decoder not in ("metop", "ccsds"):
         return
     fo = ORC.Fec(ORC.metop_cfg(cfg.ber_thresold, cfg.outsync_after) if cfg.decoder == "metop" else
                  ORC.ccsds_cfg(cfg.constellation, cfg.cadu_bytes * 8, cfg.ber_thresold, cfg.outsync_after, cfg.interleave, nrzm=cfg.nrzm,

@@ -6,7 +6,7 @@ Gates (measured values are recorded in DESIGN.md):
                                      1.01e-5 BPSK: the AGC's own float rounding noise, which no exact-arithmetic scan can
                                      reproduce, is ~0.4e-5 at signal peaks and the loop adds its own); for OQPSK (a QPSK Costas
                                      loop tracking an offset signal converges more slowly / noisily) <= 1e-5 on >= 99 % and
-                                     <= 2e-2 on all
+                                     <= 2e-2 on all; 8PSK (order-8 detector, a third of the gain; measured 99.90 %, max 7.6e-3) >= 99.8 % and <= 2e-2
   M&M symbols                      : identical count; <= 1e-5 on >= 97 % of the symbols and <= 5e-2 (a few arms of the
                                      128-arm interpolator) on all — the loop's rint(mu*128) arm choice makes any run that is
                                      not bit-identical upstream differ by one arm on ~1-2 % of the symbols (A.14)
@@ -18,7 +18,7 @@ import pytest
 from tests.common import gpu_demod, nsamples, oracle, oracle_demod, signal
 
 pytestmark = pytest.mark.gpu
-CONFIGS = ["metop_ahrpt", "bpsk_half", "jpss_hrd", "dvbs2_front", "hrpt_bpsk"]
+CONFIGS = ["metop_ahrpt", "bpsk_half", "jpss_hrd", "dvbs2_front", "hrpt_bpsk", "psk8"]
 
 
 def check_mm(gs, om, gsoft=None, osoft=None, big_soft=1e-4):
@@ -73,6 +73,8 @@ def test_stage_parity(built, name):
         d = np.abs(g.stage(st) - o[st])
         if st == "costas" and cfg.constellation == "oqpsk":
             assert (d <= 1e-5).mean() >= 0.99 and d.max() <= 2e-2, (st, float((d <= 1e-5).mean()), float(d.max()))
+        elif st == "costas" and cfg.constellation == "8psk":  # order-8 loop: low detector gain, rare near-slips at 18 dB
+            assert (d <= 1e-5).mean() >= 0.998 and d.max() <= 2e-2, (st, float((d <= 1e-5).mean()), float(d.max()))
         elif st == "costas":
             assert (d <= 1e-5).mean() >= 0.99999 and d.max() <= 2e-5, (st, float((d <= 1e-5).mean()), float(d.max()), int(np.argmax(d)))
         else:
