@@ -41,7 +41,7 @@ enum { B200_BPSK = 0, B200_QPSK = 1, B200_OQPSK = 2, B200_8PSK = 3, B200_NONE = 
 /* baseband_format (common/dsp/io/baseband_type.h:7-21) */
 enum { B200_CF32 = 0, B200_CS16 = 1, B200_CS8 = 2 };
 /* decoder kind */
-enum { B200_FEC_METOP = 0, B200_FEC_CCSDS = 1 };
+enum { B200_FEC_METOP = 0, B200_FEC_CCSDS = 1, B200_FEC_SIMPLE = 2 };
 /* debug stage ids for b200_demod_debug_stage */
 enum { B200_STAGE_AGC = 0, B200_STAGE_FIR = 1, B200_STAGE_COSTAS = 2, B200_STAGE_RESAMP = 3 };
 
@@ -71,8 +71,10 @@ typedef struct b200_demod_cfg
 
 typedef struct b200_fec_cfg
 {
-    int kind;                 /* B200_FEC_METOP | B200_FEC_CCSDS                                 */
-    int constellation;        /* ccsds: B200_BPSK / BPSK_90 / QPSK / OQPSK                       */
+    int kind;                 /* B200_FEC_METOP (metop_ahrpt_decoder) | B200_FEC_CCSDS (ccsds_conv_concat_decoder) |
+                                 B200_FEC_SIMPLE (ccsds_simple_psk_decoder: no convolutional code,
+                                 src-core/pipeline/modules/ccsds/module_ccsds_simple_psk_decoder.cpp)                */
+    int constellation;        /* ccsds: B200_BPSK / BPSK_90 / QPSK / OQPSK; simple: B200_BPSK / QPSK */
     int cadu_size;            /* bits ("cadu_size"); METOP: 8192                                 */
     int outsync_after;        /* "viterbi_outsync_after"                                         */
     float ber_thresold;       /* "viterbi_ber_thresold"                                          */
@@ -82,6 +84,9 @@ typedef struct b200_fec_cfg
     unsigned int asm_sync;    /* "asm", default 0x1ACFFC1D                                       */
     int device;
     long max_soft;            /* largest number of soft bytes of one push                        */
+    int qpsk_swap_iq;         /* simple: "qpsk_swap_iq"   (module_ccsds_simple_psk_decoder.cpp:27)    */
+    int qpsk_swap_diff;       /* simple: "qpsk_swap_diff", default true (:28); used with nrzm on QPSK  */
+    int oqpsk_delay;          /* simple: "oqpsk_delay" (:29)                                          */
 } b200_fec_cfg;
 
 typedef struct b200_demod_stats

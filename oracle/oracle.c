@@ -908,10 +908,14 @@ typedef struct
     orc_fec_cfg cfg;
     int chunk, cadu_bytes, nosync_runs, errors[16];
     orc_vit vit;
-    orc_deframer defr;
+    orc_deframer defr, defr_qpsk; /* defr_qpsk: the second deframer of ccsds_simple_psk_decoder (QPSK without NRZ-M) */
     uint8_t nrzm_last;
     uint8_t *vout, *frames;
     int8_t *soft;
+    /* ccsds_simple_psk_decoder: oqpsk_delay register, QPSKDiff state (differential/qpsk_diff.h: buffer[2], inBuf) */
+    int8_t last_q_oqpsk;
+    uint8_t qd_buf[2];
+    int qd_in;
 } orc_fec;
 
 void *orc_fec_create(const orc_fec_cfg *c)
@@ -924,6 +928,14 @@ void *orc_fec_create(const orc_fec_cfg *c)
         vit_init(&f->vit, 1, c->ber_thresold, c->outsync_after, f->chunk, ph, 2, 0);
         defr_init(&f->defr, 8192, 0x1ACFFC1D);
         f->defr.st_synced = 18;
+    } else if (c->kind == 2) { /* module_ccsds_simple_psk_decoder.cpp:19-98 */
+        f->chunk = c->cadu_size;
+        f->cadu_bytes = (c->cadu_size + 7) / 8;
+        defr_init(&f->defr, c->cadu_size, c->asm_sync);
+        defr_init(&f->defr_qpsk, c->cadu_size, c->asm_sync);
+        f->defr.pad = f->defr_qpsk.pad = c->cadu_size % 8;
+        f->vout = calloc(1, f->chunk * 8); f->frames = malloc(f->chunk * 8 + 10240); f->soft = malloc(f->chunk);
+        return f;
     } else { /* module_ccsds_conv_concat_decoder.cpp:16-131 */
         int ph[2] = {0, 1}, n = 2;
         if (c->constellation == 0) { ph[0] = 0; n = 1; }
@@ -937,7 +949,61 @@ void *orc_fec_create(const orc_fec_cfg *c)
     f->vout = malloc(f->chunk * 8); f->frames = malloc(f->chunk * 8 + 10240); f->soft = malloc(f->chunk);
     return f;
 }
-void orc_fec_destroy(void *h) { orc_fec *f = h; vit_free(&f->vit); free(f->defr.frame); free(f->vout); free(f->frames); free(f->soft); free(f); }
+void orc_fec_destroy(void *h)
+{
+    orc_fec *f = h;
+    if (f->cfg.kind != 2) vit_free(&f->vit);
+    free(f->defr.frame); free(f->defr_qpsk.frame); free(f->vout); free(f->frames); free(f->soft); free(f);
+}
+
+/* QPSKDiff::work — differential/qpsk_diff.cpp:5-53 (2 output bits per decoded symbol; the first two symbols only fill the buffer) */
+static int qpsk_diff_work(orc_fec *f, const uint8_t *in, int len, uint8_t *out, int swap)
+{
+    int oo = 0;
+    for (int ii = 0; ii < len; ii++) {
+        f->qd_buf[0] = f->qd_buf[1];
+        f->qd_buf[1] = in[ii];
+        if (f->qd_in < 2) { f->qd_in++; continue; }
+        uint8_t Xin_1 = f->qd_buf[0] & 0x02, Yin_1 = f->qd_buf[0] & 0x01, Xin = f->qd_buf[1] & 0x02, Yin = f->qd_buf[1] & 0x01, Xout, Yout, ou;
+        if (((Xin >> 1) ^ Yin) == 1) { Xout = (Yin_1 ^ Yin); Yout = (Xin_1 ^ Xin); ou = (Xout << 1) + (Yout >> 1); }
+        else { Xout = (Xin_1 ^ Xin); Yout = (Yin_1 ^ Yin); ou = (Xout + Yout); }
+        if (swap) { out[oo * 2 + 0] = ou & 1; out[oo * 2 + 1] = ou >> 1; }
+        else { out[oo * 2 + 0] = ou >> 1; out[oo * 2 + 1] = ou & 1; }
+        oo++;
+    }
+    return oo;
+}
+
+/* one iteration of CCSDSSimplePSKDecoderModule::process — module_ccsds_simple_psk_decoder.cpp:144-262 (oqpsk_method2/3 not restated);
+ * leaves the bits for the main deframer in f->vout, returns the frames the second deframer already put into f->frames */
+static int simple_bits(orc_fec *f)
+{
+    const orc_fec_cfg *k = &f->cfg;
+    const int n = f->chunk;
+    int8_t *sb = f->soft;
+    uint8_t *bits = f->vout;
+    int frames = 0;
+    if (k->constellation == 0) {
+        for (int i = 0; i < n; i++) bits[i] = sb[i] > 0;
+        if (k->nrzm)
+            for (int i = 0; i < n; i++) { uint8_t cur = bits[i]; bits[i] = cur ^ f->nrzm_last; f->nrzm_last = cur; }
+        return 0;
+    }
+    if (k->oqpsk_delay)
+        for (int i = 0; i < n / 2; i++) { int8_t back = sb[i * 2]; sb[i * 2] = f->last_q_oqpsk; f->last_q_oqpsk = back; }
+    if (k->qpsk_swap_iq) orc_rotate_soft(sb, n, 0, 1);
+    if (k->nrzm) {
+        uint8_t *syms = f->frames + f->chunk * 4; /* scratch behind the frame area */
+        for (int i = 0; i < n / 2; i++) syms[i] = 2 * (sb[i * 2 + 1] > 0) + (sb[i * 2] > 0); /* constellation_t::soft_demod, QPSK */
+        qpsk_diff_work(f, syms, n / 2, bits, k->qpsk_swap_diff);
+    } else {
+        for (int i = 0; i < n / 2; i++) { bits[i * 2] = sb[i * 2 + 1] > 0; bits[i * 2 + 1] = sb[i * 2] > 0; }
+        frames += defr_work(&f->defr_qpsk, bits, n, f->frames);
+        orc_rotate_soft(sb, n, 1, 0);
+        for (int i = 0; i < n / 2; i++) { bits[i * 2] = sb[i * 2 + 1] > 0; bits[i * 2 + 1] = sb[i * 2] > 0; }
+    }
+    return frames;
+}
 int orc_fec_chunk_size(void *h) { return ((orc_fec *)h)->chunk; }
 int orc_fec_cadu_bytes(void *h) { return ((orc_fec *)h)->cadu_bytes; }
 
@@ -951,6 +1017,26 @@ long orc_fec_run(void *h, const int8_t *soft, long nsoft, uint8_t *cadu_out, lon
     long outp = 0, bitp = 0, seen = 0;
     for (long c = 0; c < nsoft / f->chunk; c++) {
         memcpy(f->soft, soft + c * f->chunk, f->chunk);
+        if (k->kind == 2) {
+            int nf = simple_bits(f);
+            if (bits_out) memcpy(bits_out + bitp, f->vout, f->chunk);
+            bitp += f->chunk;
+            nf += defr_work(&f->defr, f->vout, f->chunk, f->frames + nf * f->cadu_bytes);
+            for (int i = 0; i < nf; i++) {
+                uint8_t *cadu = f->frames + i * f->cadu_bytes;
+                if (k->derandomize && !k->derand_after_rs) orc_derand(cadu + k->derand_start, f->cadu_bytes - k->derand_start);
+                if (k->rs_i) orc_rs_decode_interleaved(cadu + 4, k->rs_dualbasis, k->rs_i, k->rs_type, k->rs_fill_bytes, f->errors);
+                int valid = 1;
+                for (int j = 0; j < k->rs_i; j++) if (f->errors[j] == -1) valid = 0;
+                if (k->derandomize && k->derand_after_rs) orc_derand(cadu + k->derand_start, f->cadu_bytes - k->derand_start);
+                if (rs_err) memcpy(rs_err + seen * k->rs_i, f->errors, sizeof(int) * k->rs_i);
+                seen++;
+                if ((!k->rs_usecheck || valid) && outp + f->cadu_bytes <= cadu_cap) { memcpy(cadu_out + outp, cadu, f->cadu_bytes); outp += f->cadu_bytes; }
+            }
+            if (vit_state) vit_state[c] = f->defr_qpsk.state;
+            if (defr_state) defr_state[c] = f->defr.state;
+            continue;
+        }
         if (k->kind == 1 && (k->constellation == 5 || k->iq_invert)) orc_rotate_soft(f->soft, f->chunk, 0, 1);
         int vout = vit_work(&f->vit, f->soft, f->vout);
         if (vit_state) vit_state[c] = f->vit.state;

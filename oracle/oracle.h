@@ -40,6 +40,7 @@ typedef struct
     int rs_i, rs_dualbasis, rs_fill_bytes, rs_usecheck, rs_type;
     int iq_invert;
     unsigned int asm_sync;
+    int qpsk_swap_iq, qpsk_swap_diff, oqpsk_delay; /* kind 2 = ccsds_simple_psk_decoder */
 } orc_fec_cfg;
 
 int orc_rrc_taps(double gain, double fs, double rs, double alpha, int ntaps, float *out);

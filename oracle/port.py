@@ -64,7 +64,7 @@ def available():
 
 lib = _lib
 DemodCfg, FecCfg = _m.DemodCfg, _m.FecCfg
-demod_cfg, metop_cfg, ccsds_cfg = _m.demod_cfg, _m.metop_cfg, _m.ccsds_cfg
+demod_cfg, metop_cfg, ccsds_cfg, simple_cfg = _m.demod_cfg, _m.metop_cfg, _m.ccsds_cfg, _m.simple_cfg
 final_samplerate_of, resample, resampler_taps = _m.final_samplerate_of, _m.resample, _m.resampler_taps
 Fec = _m.Fec
 rs_decode_interleaved, derand, cc_encode, cc_decode, rotate_soft, deframe = (

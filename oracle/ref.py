@@ -25,7 +25,8 @@ class FecCfg(C.Structure):
     _fields_ = [("kind", C.c_int), ("constellation", C.c_int), ("cadu_size", C.c_int), ("outsync_after", C.c_int),
                 ("ber_thresold", C.c_float), ("nrzm", C.c_int), ("derandomize", C.c_int), ("derand_after_rs", C.c_int),
                 ("derand_start", C.c_int), ("rs_i", C.c_int), ("rs_dualbasis", C.c_int), ("rs_fill_bytes", C.c_int),
-                ("rs_usecheck", C.c_int), ("rs_type", C.c_int), ("iq_invert", C.c_int), ("asm_sync", C.c_uint)]
+                ("rs_usecheck", C.c_int), ("rs_type", C.c_int), ("iq_invert", C.c_int), ("asm_sync", C.c_uint),
+                ("qpsk_swap_iq", C.c_int), ("qpsk_swap_diff", C.c_int), ("oqpsk_delay", C.c_int)]
 
 
 class _Prefixed:
@@ -140,7 +141,14 @@ def final_samplerate_of(samplerate, symbolrate, constellation, min_sps=None, max
 
 
 def metop_cfg(ber_thresold=0.28, outsync_after=10):
-    return FecCfg(0, 1, 8192, outsync_after, ber_thresold, 0, 1, 0, 4, 4, 1, -1, 0, 0, 0, 0x1ACFFC1D)
+    return FecCfg(0, 1, 8192, outsync_after, ber_thresold, 0, 1, 0, 4, 4, 1, -1, 0, 0, 0, 0x1ACFFC1D, 0, 0, 0)
+
+
+def simple_cfg(constellation, cadu_size, rs_i, nrzm=False, derandomize=True, rs_usecheck=False, rs_dualbasis=True, rs_fill_bytes=-1,
+               derand_after_rs=False, derand_start=4, rs_type=0, asm_sync=0x1ACFFC1D, qpsk_swap_iq=False, qpsk_swap_diff=True, oqpsk_delay=False):
+    """ccsds_simple_psk_decoder (module_ccsds_simple_psk_decoder.cpp:19-44 defaults): no convolutional code."""
+    return FecCfg(2, CONST[constellation], cadu_size, 0, 0.0, int(nrzm), int(derandomize), int(derand_after_rs), derand_start, rs_i,
+                  int(rs_dualbasis), rs_fill_bytes, int(rs_usecheck), rs_type, 0, asm_sync, int(qpsk_swap_iq), int(qpsk_swap_diff), int(oqpsk_delay))
 
 
 def ccsds_cfg(constellation, cadu_size, ber_thresold, outsync_after, rs_i, nrzm=False, derandomize=True, rs_usecheck=False,
@@ -148,7 +156,7 @@ def ccsds_cfg(constellation, cadu_size, ber_thresold, outsync_after, rs_i, nrzm=
               asm_sync=0x1ACFFC1D):
     return FecCfg(1, CONST[constellation], cadu_size, outsync_after, ber_thresold, int(nrzm), int(derandomize),
                   int(derand_after_rs), derand_start, rs_i, int(rs_dualbasis), rs_fill_bytes, int(rs_usecheck), rs_type,
-                  int(iq_invert), asm_sync)
+                  int(iq_invert), asm_sync, 0, 0, 0)
 
 
 class Demod:
@@ -214,7 +222,7 @@ class Fec:
     def run(self, soft):
         soft = np.ascontiguousarray(soft, np.int8)
         nch = soft.size // self.chunk
-        bits_per_chunk = self.chunk * 3 // 4 if self.cfg.kind == 0 else self.chunk // 2
+        bits_per_chunk = self.chunk * 3 // 4 if self.cfg.kind == 0 else (self.chunk if self.cfg.kind == 2 else self.chunk // 2)
         cap = (nch * bits_per_chunk // max(1, self.cfg.cadu_size) + 2) * self.cadu_bytes
         cadu = np.zeros(cap, np.uint8)
         vs = np.zeros(nch, np.int32)

@@ -59,6 +59,8 @@
 #include "common/codings/randomization.h"
 #include "common/codings/reedsolomon/reedsolomon.h"
 #include "common/codings/differential/nrzm.h"
+#include "common/codings/differential/qpsk_diff.h"
+#include "common/dsp/demod/constellation.h"
 #include "common/codings/rotation.h"
 
 #include <atomic>
@@ -95,7 +97,7 @@ extern "C"
 
     typedef struct
     {
-        int kind;           /* 0 = metop_ahrpt_decoder, 1 = ccsds_conv_concat_decoder (r=1/2) */
+        int kind;           /* 0 = metop_ahrpt_decoder, 1 = ccsds_conv_concat_decoder (r=1/2), 2 = ccsds_simple_psk_decoder */
         int constellation;  /* ccsds: 0 bpsk, 1 qpsk, 2 oqpsk, 5 bpsk_90 */
         int cadu_size;      /* bits */
         int outsync_after;
@@ -104,6 +106,8 @@ extern "C"
         int rs_i, rs_dualbasis, rs_fill_bytes, rs_usecheck, rs_type; /* rs_type 0 rs223 1 rs239 */
         int iq_invert;
         unsigned int asm_sync;
+        /* kind 2 = ccsds_simple_psk_decoder (module_ccsds_simple_psk_decoder.cpp): no convolutional code */
+        int qpsk_swap_iq, qpsk_swap_diff, oqpsk_delay;
     } ref_fec_cfg;
 }
 
@@ -155,9 +159,12 @@ namespace
         int buffer_size, cadu_bytes;
         std::shared_ptr<viterbi::Viterbi3_4> v34;
         std::shared_ptr<viterbi::Viterbi1_2> v12;
-        std::shared_ptr<deframing::BPSK_CCSDS_Deframer> deframer;
+        std::shared_ptr<deframing::BPSK_CCSDS_Deframer> deframer, deframer_qpsk;
         std::shared_ptr<reedsolomon::ReedSolomon> rs;
         diff::NRZMDiff diff;
+        diff::QPSKDiff qpsk_diff;
+        int8_t last_q_oqpsk = 0;
+        std::vector<uint8_t> bits_buf, qpsk_diff_buffer;
         int errors[16];
         int noSyncsRuns = 0;
         std::vector<uint8_t> viterbi_out, frame_buffer;
@@ -369,6 +376,24 @@ extern "C"
             f->deframer->STATE_SYNCED = 18;
             f->rs = std::make_shared<reedsolomon::ReedSolomon>(reedsolomon::RS223);
         }
+        else if (c->kind == 2)
+        {
+            /* CCSDSSimplePSKDecoderModule ctor, module_ccsds_simple_psk_decoder.cpp:19-98 */
+            f->buffer_size = c->cadu_size;
+            f->cadu_bytes = (int)ceil(c->cadu_size / 8.0);
+            f->deframer = std::make_shared<deframing::BPSK_CCSDS_Deframer>(c->cadu_size, c->asm_sync);
+            f->deframer_qpsk = std::make_shared<deframing::BPSK_CCSDS_Deframer>(c->cadu_size, c->asm_sync);
+            if (c->rs_i != 0)
+                f->rs = std::make_shared<reedsolomon::ReedSolomon>(c->rs_type == 1 ? reedsolomon::RS239 : reedsolomon::RS223, c->rs_fill_bytes);
+            if (c->cadu_size % 8 != 0)
+            {
+                f->deframer->CADU_PADDING = c->cadu_size % 8;
+                f->deframer_qpsk->CADU_PADDING = c->cadu_size % 8;
+            }
+            f->qpsk_diff.swap = c->qpsk_swap_diff;
+            f->bits_buf.resize(c->cadu_size * 2);
+            f->qpsk_diff_buffer.resize(c->cadu_size * 2);
+        }
         else
         {
             f->buffer_size = std::max<int>(c->cadu_size, 8192);
@@ -453,6 +478,88 @@ extern "C"
                         }
                     }
                 }
+            }
+            else if (f->cfg.kind == 2)
+            {
+                /* one iteration of CCSDSSimplePSKDecoderModule::process, module_ccsds_simple_psk_decoder.cpp:144-296
+                   (oqpsk_method2/3 not wired: the CUDA path rejects them) */
+                const ref_fec_cfg &k = f->cfg;
+                const int n = f->buffer_size;
+                int8_t *sb = f->soft.data();
+                uint8_t *bits = f->bits_buf.data();
+                dsp::constellation_t qpsk_const(dsp::QPSK);
+                int frames = 0;
+                if (k.constellation == 0)
+                {
+                    for (int i = 0; i < n; i++)
+                        bits[i] = sb[i] > 0;
+                    if (k.nrzm)
+                        f->diff.decode_bits(bits, n);
+                }
+                else
+                {
+                    if (k.oqpsk_delay)
+                        for (int i = 0; i < n / 2; i++)
+                        {
+                            int8_t back = sb[i * 2 + 0];
+                            sb[i * 2 + 0] = f->last_q_oqpsk;
+                            f->last_q_oqpsk = back;
+                        }
+                    if (k.qpsk_swap_iq)
+                        rotate_soft(sb, n, PHASE_0, true);
+                    if (k.nrzm)
+                    {
+                        for (int i = 0; i < n / 2; i++)
+                            f->qpsk_diff_buffer[i] = qpsk_const.soft_demod(&sb[i * 2]);
+                        f->qpsk_diff.work(f->qpsk_diff_buffer.data(), n / 2, bits);
+                    }
+                    else
+                    {
+                        for (int i = 0; i < n / 2; i++)
+                        {
+                            uint8_t sym = qpsk_const.soft_demod(&sb[i * 2]);
+                            bits[i * 2 + 0] = sym >> 1;
+                            bits[i * 2 + 1] = sym & 1;
+                        }
+                        frames += f->deframer_qpsk->work(bits, n, &f->frame_buffer[frames * f->cadu_bytes]);
+                        rotate_soft(sb, n, PHASE_90, false);
+                        for (int i = 0; i < n / 2; i++)
+                        {
+                            uint8_t sym = qpsk_const.soft_demod(&sb[i * 2]);
+                            bits[i * 2 + 0] = sym >> 1;
+                            bits[i * 2 + 1] = sym & 1;
+                        }
+                    }
+                }
+                if (bits_out)
+                    memcpy(bits_out + bitp, bits, n);
+                bitp += n;
+                frames += f->deframer->work(bits, n, &f->frame_buffer[frames * f->cadu_bytes]);
+                for (int i = 0; i < frames; i++)
+                {
+                    uint8_t *cadu = &f->frame_buffer[i * f->cadu_bytes];
+                    if (k.derandomize && !k.derand_after_rs)
+                        derand_ccsds(&cadu[k.derand_start], f->cadu_bytes - k.derand_start);
+                    if (k.rs_i != 0)
+                        f->rs->decode_interlaved(&cadu[4], k.rs_dualbasis, k.rs_i, f->errors);
+                    bool valid = true;
+                    for (int j = 0; j < k.rs_i; j++)
+                        if (f->errors[j] == -1)
+                            valid = false;
+                    if (k.derandomize && k.derand_after_rs)
+                        derand_ccsds(&cadu[k.derand_start], f->cadu_bytes - k.derand_start);
+                    if (rs_err)
+                        memcpy(rs_err + frames_seen * k.rs_i, f->errors, k.rs_i * sizeof(int));
+                    frames_seen++;
+                    if (!k.rs_usecheck || valid)
+                        if (outp + f->cadu_bytes <= cadu_cap)
+                        {
+                            memcpy(cadu_out + outp, cadu, f->cadu_bytes);
+                            outp += f->cadu_bytes;
+                        }
+                }
+                if (vit_state)
+                    vit_state[c] = f->deframer_qpsk->getState(); /* second deframer's state (QPSK without NRZ-M) */
             }
             else
             {

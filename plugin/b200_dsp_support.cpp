@@ -6,7 +6,7 @@
 //
 //   loader()                          the one symbol SatDump dlsym()s (core/plugin.cpp:15-33)
 //   B200DSPSupport::init()            on SatDumpStartedEvent (fired after every plugin registered its modules, init.cpp:163) the
-//                                     entries "psk_demod", "metop_ahrpt_decoder" and "ccsds_conv_concat_decoder" of
+//                                     entries "psk_demod", "metop_ahrpt_decoder", "ccsds_conv_concat_decoder" and "ccsds_simple_psk_decoder" of
 //                                     satdump::pipeline::modules_registry (module.h:210, looked up first-match by id, module.cpp:129-135)
 //                                     get their factory replaced, so existing pipelines instantiate the CUDA modules.
 //                                     Set B200_DSP_REGISTER_ONLY=1 to register "<id>_b200" ids instead and leave the originals alone.
@@ -203,14 +203,14 @@ public:
 
     static void registerHandler(const satdump::pipeline::RegisterModulesEvent &evt)
     {
-        for (const char *id : {"psk_demod", "metop_ahrpt_decoder", "ccsds_conv_concat_decoder"})
+        for (const char *id : {"psk_demod", "metop_ahrpt_decoder", "ccsds_conv_concat_decoder", "ccsds_simple_psk_decoder"})
             evt.modules_registry.push_back({std::string(id) + "_b200", nlohmann::json(), factory(id)});
     }
 
     static void patchHandler(const satdump::SatDumpStartedEvent &)
     {
         for (auto &e : satdump::pipeline::modules_registry)
-            if (e.id == "psk_demod" || e.id == "metop_ahrpt_decoder" || e.id == "ccsds_conv_concat_decoder")
+            if (e.id == "psk_demod" || e.id == "metop_ahrpt_decoder" || e.id == "ccsds_conv_concat_decoder" || e.id == "ccsds_simple_psk_decoder")
             {
                 e.inst = factory(e.id);
                 logger->info("b200_dsp_support: module " + e.id + " now runs on the B200 path");

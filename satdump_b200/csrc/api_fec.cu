@@ -48,7 +48,7 @@ void build_rs_tables(RsTables &T)
 
 Fec::Fec(const b200_fec_cfg &c) : cfg(c)
 {
-    B200_REQUIRE(c.kind == B200_FEC_METOP || c.kind == B200_FEC_CCSDS, B200_EINVAL, "unknown decoder kind %d", c.kind);
+    B200_REQUIRE(c.kind == B200_FEC_METOP || c.kind == B200_FEC_CCSDS || c.kind == B200_FEC_SIMPLE, B200_EINVAL, "unknown decoder kind %d", c.kind);
     B200_REQUIRE(c.max_soft >= 65536, B200_EINVAL, "max_soft must be >= 65536");
     memset(&geom, 0, sizeof(geom));
     if (c.kind == B200_FEC_METOP) {
@@ -69,6 +69,22 @@ Fec::Fec(const b200_fec_cfg &c) : cfg(c)
         nphases = 2; ph0 = 0; ph1 = 1; nswap = 1;
         st_synced = 18;
         spec_steps = VIT_SPEC_STEPS_34;
+    } else if (c.kind == B200_FEC_SIMPLE) {
+        // module_ccsds_simple_psk_decoder.cpp:19-98: one loop iteration = cadu_size soft bytes -> cadu_size bits
+        B200_REQUIRE(c.cadu_size >= 64 && c.cadu_size <= 65536, B200_EINVAL, "cadu_size out of range");
+        B200_REQUIRE(c.cadu_size % 8 == 0, B200_EINVAL, "cadu_size must be a multiple of 8 (frame padding is not built)");
+        B200_REQUIRE(c.rs_i >= 0 && c.rs_i <= RS_MAX_I, B200_EINVAL, "rs_i out of range (0..%d)", RS_MAX_I);
+        B200_REQUIRE(c.rs_i == 0 || c.cadu_size / 8 >= 4 + 255 * c.rs_i, B200_EINVAL, "cadu_size too small for rs_i interleaved codewords");
+        B200_REQUIRE(c.rs_fill_bytes <= 0, B200_EINVAL, "rs_fill_bytes (shortened codes) is not built");
+        B200_REQUIRE(c.constellation == B200_BPSK || c.constellation == B200_QPSK, B200_EINVAL, "CCSDS Simple PSK Decoder : invalid constellation type!");
+        geom.rate34 = 0;
+        geom.chunk = c.cadu_size;
+        geom.F = c.cadu_size;
+        nphases = 1; ph0 = ph1 = 0; nswap = 1;
+        st_synced = 12;
+        spec_steps = 0;
+        if (cfg.asm_sync == 0)
+            cfg.asm_sync = 0x1ACFFC1D;
     } else {
         // module_ccsds_conv_concat_decoder.cpp:16-131 (conv_rate 1/2 only; the Viterbi_Depunc rates are not built)
         B200_REQUIRE(c.cadu_size >= 64 && c.cadu_size <= 65536, B200_EINVAL, "cadu_size out of range");
@@ -104,7 +120,8 @@ Fec::Fec(const b200_fec_cfg &c) : cfg(c)
         B200_CUDA(cudaEventCreate(&e));
     max_chunks = c.max_soft / geom.chunk + 2;
     softbuf.alloc((size_t)c.max_soft + 2 * geom.chunk);
-    dec.alloc((size_t)max_chunks * geom.dec_stride);
+    const bool simple = cfg.kind == B200_FEC_SIMPLE;
+    dec.alloc(simple ? (size_t)(c.max_soft / 8 + geom.chunk) : (size_t)max_chunks * geom.dec_stride); // simple: only scratch for the tail move
     idle_dec.alloc(VIT_TESTLEN + 64);
     chunk_bits.alloc((size_t)max_chunks * geom.bit_words + 4);
     const long max_new_bits = max_chunks * (long)geom.F;
@@ -112,7 +129,7 @@ Fec::Fec(const b200_fec_cfg &c) : cfg(c)
     start_state.alloc(max_chunks + 1);
     rec.alloc(max_chunks + 1);
     tb_blocks = ((geom.F + 31) / 32 + TB_WORDS - 1) / TB_WORDS;
-    tb_edges.alloc((size_t)(max_chunks + 1) * tb_blocks);
+    tb_edges.alloc(simple ? 1 : (size_t)(max_chunks + 1) * tb_blocks);
     tb_list.alloc(4097);
     idle_out.alloc(1);
     idle2_out.alloc(1);
@@ -120,6 +137,12 @@ Fec::Fec(const b200_fec_cfg &c) : cfg(c)
     B200_CUDA(cudaFuncSetAttribute(k_vit_idle2, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * VIT_IDLE_WARP_BYTES));
     dstate.alloc(2);
     devents.alloc(4096);
+    if (simple) {
+        chunk_bits2.alloc((size_t)max_chunks * geom.bit_words + 4);
+        fifo2.alloc(fifo.n);
+        dstate2.alloc(2);
+        slice_carry.alloc(4);
+    }
     max_frames_push = max_new_bits / cfg.cadu_size + 4;
     frames.alloc(max_frames_push);
     frames_out.alloc((size_t)(2 * max_frames_push + 4) * cadu_bytes);
@@ -143,6 +166,12 @@ Fec::Fec(const b200_fec_cfg &c) : cfg(c)
     h_dstate[0].pos = 32; // the FIFO starts with 32 zero bits = the deframer's empty shifter
     h_dstate[0].frame_pay = -1;
     B200_CUDA(cudaMemcpyAsync(dstate.p, h_dstate, sizeof(DefrState), cudaMemcpyHostToDevice, stream));
+    if (simple) {
+        h_dstate2 = h_dstate[0];
+        fifo2.zero(stream);
+        slice_carry.zero(stream);
+        B200_CUDA(cudaMemcpyAsync(dstate2.p, h_dstate, sizeof(DefrState), cudaMemcpyHostToDevice, stream));
+    }
     const int fr_smem = (int)sizeof(RsTables) + ((cadu_bytes + 15) & ~15) + RS_MAX_I * 704;
     B200_CUDA(cudaFuncSetAttribute(k_frames, cudaFuncAttributeMaxDynamicSharedMemorySize, fr_smem));
     B200_CUDA(cudaStreamSynchronize(stream));
@@ -304,6 +333,7 @@ void Fec::deframe_and_rs(long new_bits)
     B200_CUDA(cudaMemcpyAsync(h_events, devents.p, sizeof(DefrEvent) * 4096, cudaMemcpyDeviceToHost, stream));
     B200_CUDA(cudaStreamSynchronize(stream));
     const int nf = h_counters[0];
+    last_nf = nf;
     B200_REQUIRE(nf <= max_frames_push, B200_ESTATE, "internal: frame list overflow");
     B200_REQUIRE(h_counters[1] <= 4096, B200_EUNSUPPORTED, "deframer changed state more than 4096 times in one push (noise input?): push smaller batches");
     if (nf > 0) {
@@ -375,11 +405,167 @@ void Fec::reset()
     h_dstate[0].pos = 32;
     h_dstate[0].frame_pay = -1;
     B200_CUDA(cudaMemcpyAsync(dstate.p, h_dstate, sizeof(DefrState), cudaMemcpyHostToDevice, stream));
+    if (cfg.kind == B200_FEC_SIMPLE) {
+        h_dstate2 = h_dstate[0];
+        fifo_bits2 = 32;
+        defr_state2 = 2;
+        slice_par = 0;
+        total_chunks = 0; // the hard-decision stage knows the stream's very first chunk by this count
+        B200_CUDA(cudaMemsetAsync(fifo2.p, 0, 64, stream));
+        B200_CUDA(cudaMemsetAsync(slice_carry.p, 0, sizeof(int) * 4, stream));
+        B200_CUDA(cudaMemcpyAsync(dstate2.p, h_dstate, sizeof(DefrState), cudaMemcpyHostToDevice, stream));
+    }
     B200_CUDA(cudaStreamSynchronize(stream));
+}
+
+void Fec::swap_unit()
+{
+    std::swap(fifo.p, fifo2.p);
+    std::swap(fifo.n, fifo2.n);
+    std::swap(dstate.p, dstate2.p);
+    std::swap(fifo_bits, fifo_bits2);
+    std::swap(h_dstate[0], h_dstate2);
+    std::swap(defr_state_now, defr_state2);
+}
+
+// keep from the open frame's payload, or the 31 bits of shifter history
+void Fec::compact_fifo()
+{
+    DefrState S = *h_dstate;
+    long keep = S.frame_pay >= 0 ? S.frame_pay : S.pos - 31;
+    keep = std::max<long>(0, std::min<long>(keep, fifo_bits));
+    const long keep_al = keep & ~31L;
+    if (keep_al > 0) {
+        const long nwords = ((fifo_bits - keep_al) + 31) / 32 + 1;
+        k_words_move<<<1, 1024, 0, stream>>>(fifo.p, fifo.p + keep_al / 32, nwords);
+        launches++;
+        S.pos -= keep_al;
+        if (S.frame_pay >= 0)
+            S.frame_pay -= keep_al;
+        fifo_bits -= keep_al;
+        *h_dstate = S;
+        B200_CUDA(cudaMemcpyAsync(dstate.p, h_dstate, sizeof(DefrState), cudaMemcpyHostToDevice, stream));
+        B200_CUDA(cudaStreamSynchronize(stream)); // swap_unit() reuses the pinned mirror right away
+    }
+}
+
+// ccsds_simple_psk_decoder: module_ccsds_simple_psk_decoder.cpp:144-296 over every complete cadu_size-byte chunk of the soft FIFO
+void Fec::process_simple()
+{
+    DeviceGuard g(cfg.device);
+    const int n = geom.chunk;
+    const long nch = soft_have / n;
+    B200_REQUIRE(nch <= max_chunks, B200_ESTATE, "internal: too many chunks");
+    const bool qpsk = cfg.constellation == B200_QPSK, two = qpsk && !cfg.nrzm;
+    compact_fifo();
+    if (two) {
+        swap_unit();
+        compact_fifo();
+        swap_unit();
+    }
+    last_bits0 = fifo_bits;
+    last_nbits = 0;
+    t_frames = 0;
+    t_vit_main = 0;
+    last_main_chunks = 0;
+    B200_CUDA(cudaEventRecord(ev[0], stream));
+    if (nch > 0) {
+        B200_REQUIRE(((fifo_bits + nch * (long)n + 64) >> 5) + 2 < (long)fifo.n, B200_ESTATE, "internal: bit FIFO too small");
+        SliceCfg P;
+        P.n = n;
+        P.bit_words = geom.bit_words;
+        P.qpsk = qpsk;
+        P.nrzm = cfg.nrzm;
+        P.swap_iq = cfg.qpsk_swap_iq;
+        P.swap_diff = cfg.qpsk_swap_diff;
+        P.delay = cfg.oqpsk_delay;
+        const long words = nch * ((n + 31) / 32);
+        k_slice<<<(unsigned)std::min<long>((words + 255) / 256, 148 * 16), 256, 0, stream>>>(softbuf.p, nch, P, total_chunks, slice_carry.p + 2 * slice_par,
+                                                                                         slice_carry.p + 2 * (slice_par ^ 1), two ? chunk_bits2.p : nullptr,
+                                                                                         chunk_bits.p);
+        slice_par ^= 1;
+        launches++;
+        const bool bpsk_nrzm = !qpsk && cfg.nrzm;
+        // one pass over chunks [c0, c0 + m): second deframer first, then the main one (the order of one reference iteration)
+        auto run = [&](long c0, long m) {
+            int nfa = 0;
+            if (two) {
+                swap_unit();
+                k_bits_append<<<1024, 256, 0, stream>>>(chunk_bits2.p + c0 * geom.bit_words, m, n, geom.bit_words, 0, 0, fifo.p, fifo_bits);
+                launches++;
+                deframe_and_rs(m * (long)n);
+                nfa = last_nf;
+                swap_unit();
+            }
+            int last_raw = 0;
+            if (bpsk_nrzm) {
+                uint32_t w;
+                const int k = n - 1;
+                B200_CUDA(cudaMemcpyAsync(&w, chunk_bits.p + (c0 + m - 1) * geom.bit_words + (k >> 5), 4, cudaMemcpyDeviceToHost, stream));
+                B200_CUDA(cudaStreamSynchronize(stream));
+                last_raw = (w >> (31 - (k & 31))) & 1;
+            }
+            k_bits_append<<<1024, 256, 0, stream>>>(chunk_bits.p + c0 * geom.bit_words, m, n, geom.bit_words, bpsk_nrzm, nrzm_last, fifo.p, fifo_bits);
+            launches++;
+            deframe_and_rs(m * (long)n);
+            if (bpsk_nrzm)
+                nrzm_last = last_raw;
+            return std::make_pair(nfa, last_nf);
+        };
+        if (!two || nch == 1)
+            run(0, nch);
+        else {
+            // both deframers finding frames in the same call is all but impossible for a real signal; if it happens the
+            // reference's output order is per iteration, so redo this call one chunk at a time
+            B200_CUDA(cudaMemcpyAsync(dstate.p + 1, dstate.p, sizeof(DefrState), cudaMemcpyDeviceToDevice, stream));
+            B200_CUDA(cudaMemcpyAsync(dstate2.p + 1, dstate2.p, sizeof(DefrState), cudaMemcpyDeviceToDevice, stream));
+            const DefrState h0 = h_dstate[0], h1 = h_dstate2;
+            const long fb0 = fifo_bits, fb1 = fifo_bits2, of0 = out_frames, tf0 = total_frames, rc0 = rs_corrected, rf0 = rs_failed;
+            const int ds0 = defr_state_now, ds1 = defr_state2;
+            const auto r = run(0, nch);
+            if (r.first > 0 && r.second > 0) {
+                replays++;
+                B200_CUDA(cudaMemcpyAsync(dstate.p, dstate.p + 1, sizeof(DefrState), cudaMemcpyDeviceToDevice, stream));
+                B200_CUDA(cudaMemcpyAsync(dstate2.p, dstate2.p + 1, sizeof(DefrState), cudaMemcpyDeviceToDevice, stream));
+                h_dstate[0] = h0;
+                h_dstate2 = h1;
+                fifo_bits = fb0;
+                fifo_bits2 = fb1;
+                out_frames = of0;
+                total_frames = tf0;
+                rs_corrected = rc0;
+                rs_failed = rf0;
+                defr_state_now = ds0;
+                defr_state2 = ds1;
+                for (long c = 0; c < nch; c++)
+                    run(c, 1);
+            }
+        }
+        total_bits += nch * (long)n;
+        last_nbits += nch * (long)n;
+    }
+    total_chunks += nch;
+    const long used = nch * (long)n, left = soft_have - used;
+    if (used > 0 && left > 0) {
+        if (left <= used)
+            B200_CUDA(cudaMemcpyAsync(softbuf.p, softbuf.p + used, left, cudaMemcpyDeviceToDevice, stream));
+        else {
+            B200_CUDA(cudaMemcpyAsync(dec.p, softbuf.p + used, left, cudaMemcpyDeviceToDevice, stream));
+            B200_CUDA(cudaMemcpyAsync(softbuf.p, dec.p, left, cudaMemcpyDeviceToDevice, stream));
+        }
+    }
+    soft_have = left;
+    B200_CUDA(cudaEventRecord(ev[1], stream));
+    B200_CUDA(cudaStreamSynchronize(stream));
+    B200_CUDA(cudaGetLastError());
+    cudaEventElapsedTime(&t_vit, ev[0], ev[1]);
+    t_vit -= t_frames;
 }
 
 void Fec::process()
 {
+    if (cfg.kind == B200_FEC_SIMPLE)
+        return process_simple();
     DeviceGuard g(cfg.device);
     const long nch = soft_have / geom.chunk;
     B200_REQUIRE(nch <= max_chunks, B200_ESTATE, "internal: too many chunks");

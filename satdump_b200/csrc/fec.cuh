@@ -729,6 +729,101 @@ __device__ __forceinline__ uint32_t fifo_window(const uint32_t *__restrict__ fif
     return (a << o) | (fifo[w + 1] >> (32 - o));
 }
 
+// ---------------------------------------------------------------- hard decisions of ccsds_simple_psk_decoder (no convolutional code)
+// One loop iteration of CCSDSSimplePSKDecoderModule::process (module_ccsds_simple_psk_decoder.cpp:144-262) takes `n` = cadu_size soft
+// bytes and makes n bits out of them; here every thread makes one 32-bit word of one chunk's bit store (the chunk_bits layout
+// k_bits_append reads). carry_in / carry_out: [0] = original I of the last symbol (the oqpsk_delay register), [1] = hard symbol of
+// the last symbol (QPSKDiff's buffer) of the previous / this call.
+//   BPSK              bitsB[k] = soft[k] > 0                                  (:151-158; NRZ-M is applied by k_bits_append)
+//   QPSK, no NRZ-M    bitsA = (Q>0),(I>0) of the symbols as they are -> second deframer (:190-199); bitsB = the same after
+//                     rotate_soft(PHASE_90): (I',Q') = (Q,-I)                 -> main deframer (:201-210)
+//   QPSK, NRZ-M       QPSKDiff (differential/qpsk_diff.cpp:5-53) over the hard symbols 2*(Q>0)+(I>0): output i of the stream's very
+//                     first chunk comes from symbols (i+1, i+2) and its last four bits are never written (left 0 here); afterwards
+//                     output g comes from symbols (g-1, g)
+struct SliceCfg { int n, bit_words, qpsk, nrzm, swap_iq, swap_diff, delay; };
+__global__ void k_slice(const int8_t *__restrict__ soft, long nchunks, SliceCfg P, long first_global_chunk, const int *__restrict__ carry_in,
+                        int *__restrict__ carry_out, uint32_t *__restrict__ bitsA, uint32_t *__restrict__ bitsB)
+{
+    const int wpc = (P.n + 31) >> 5; // words per chunk
+    const long nw = nchunks * wpc;
+    const long nsym_total = nchunks * (long)(P.n >> 1);
+    auto sym_iq = [&](long g, int &I, int &Q) { // symbol g of this call after oqpsk_delay and qpsk_swap_iq
+        int i0 = soft[2 * g], q0 = soft[2 * g + 1];
+        if (P.delay)
+            i0 = g > 0 ? soft[2 * (g - 1)] : carry_in[0];
+        if (P.swap_iq) {
+            const int t = i0;
+            i0 = q0;
+            q0 = t;
+        }
+        I = i0;
+        Q = q0;
+    };
+    auto hard_sym = [&](long g) -> int { // constellation_t::soft_demod for QPSK: 2*(Q>0) + (I>0); g = -1: previous call's last
+        if (g < 0)
+            return carry_in[1];
+        int I, Q;
+        sym_iq(g, I, Q);
+        return 2 * (Q > 0) + (I > 0);
+    };
+    for (long w = (long)blockIdx.x * blockDim.x + threadIdx.x; w < nw; w += (long)gridDim.x * blockDim.x) {
+        const long c = w / wpc;
+        const int k0 = (int)(w - c * wpc) << 5;
+        uint32_t a = 0, b = 0;
+        for (int j = 0; j < 32 && k0 + j < P.n; j++) {
+            const int k = k0 + j;
+            unsigned ba = 0, bb = 0;
+            if (!P.qpsk)
+                bb = soft[c * P.n + k] > 0;
+            else {
+                const long g = c * (long)(P.n >> 1) + (k >> 1); // symbol of this call
+                if (!P.nrzm) {
+                    int I, Q;
+                    sym_iq(g, I, Q);
+                    ba = (k & 1) ? (I > 0) : (Q > 0);
+                    bb = (k & 1) ? (Q > 0) : (I < 0);
+                } else {
+                    const bool first = first_global_chunk + c == 0;
+                    long g0, g1; // the pair (older, newer)
+                    if (first) {
+                        g0 = g + 1;
+                        g1 = g + 2;
+                    } else {
+                        g0 = g - 1;
+                        g1 = g;
+                    }
+                    if (first && (k >> 1) >= (P.n >> 1) - 2)
+                        bb = 0; // never written by the reference's first call
+                    else {
+                        const int s0 = hard_sym(g0), s1 = hard_sym(g1);
+                        const int Xin_1 = s0 & 2, Yin_1 = s0 & 1, Xin = s1 & 2, Yin = s1 & 1;
+                        int ou;
+                        if (((Xin >> 1) ^ Yin) == 1) {
+                            const int Xout = Yin_1 ^ Yin, Yout = Xin_1 ^ Xin;
+                            ou = (Xout << 1) + (Yout >> 1);
+                        } else {
+                            const int Xout = Xin_1 ^ Xin, Yout = Yin_1 ^ Yin;
+                            ou = Xout + Yout;
+                        }
+                        const int b0 = P.swap_diff ? (ou & 1) : (ou >> 1), b1 = P.swap_diff ? (ou >> 1) : (ou & 1);
+                        bb = (k & 1) ? b1 : b0;
+                    }
+                }
+            }
+            a |= ba << (31 - j);
+            b |= bb << (31 - j);
+        }
+        const long o = c * P.bit_words + (k0 >> 5);
+        if (bitsA)
+            bitsA[o] = a;
+        bitsB[o] = b;
+        if (w == nw - 1 && P.qpsk) {
+            carry_out[0] = soft[2 * (nsym_total - 1)];
+            carry_out[1] = hard_sym(nsym_total - 1);
+        }
+    }
+}
+
 // ---------------------------------------------------------------- deframer walk (one warp), frame level replay of the bit-serial machine
 #endif // B200_DEFINE_KERNELS
 struct DefrState

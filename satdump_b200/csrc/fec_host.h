@@ -24,6 +24,7 @@ class Fec
     void push_host(const int8_t *h, long n);
     void push_device(const int8_t *d, long n);
     void process(); // decode every complete chunk in the FIFO
+    void process_simple(); // kind B200_FEC_SIMPLE: hard decisions -> deframer(s) -> RS
     long pull(uint8_t *host_out, long cap);
     void stats(b200_fec_stats *o);
 
@@ -57,6 +58,16 @@ class Fec
     DevBuf<FrameRec> frames;
     DevBuf<uint8_t> frames_out, frames_tmp;
     DevBuf<RsTables> tables;
+    // ccsds_simple_psk_decoder: second deframer (QPSK without NRZ-M runs one on the symbols as they are, one on the 90-degree
+    // rotated ones) and the carried registers of the hard-decision stage
+    DevBuf<uint32_t> chunk_bits2, fifo2;
+    DevBuf<DefrState> dstate2;
+    DevBuf<int> slice_carry; // [2][2]: oqpsk_delay register, QPSKDiff's previous symbol (ping-pong by call)
+    DefrState h_dstate2{};
+    long fifo_bits2 = 32;
+    int defr_state2 = 2, slice_par = 0, last_nf = 0;
+    void swap_unit();
+    void compact_fifo();
     // pinned host mirrors
     VitRec *h_rec = nullptr;
     VitIdleOut *h_idle = nullptr;

@@ -25,6 +25,13 @@ int main(int argc, char **argv)
         fp = Params{{"constellation", "oqpsk"}, {"cadu_size", "10232"}, {"viterbi_ber_thresold", "0.3"}, {"viterbi_outsync_after", "20"},
                     {"derandomize", "true"}, {"nrzm", "true"}, {"rs_i", "5"}, {"rs_type", "rs223"}, {"rs_usecheck", "true"}};
         dec = "ccsds_conv_concat_decoder";
+    } else if (pipe == "simple_bpsk" || pipe == "simple_qpsk") { // psk_demod -> ccsds_simple_psk_decoder (no convolutional code), the shape of
+        // 50 shipped pipelines (e.g. resources/pipelines/FengYun-3.json:630-639); symbolrate etc. come from the command line
+        const char *con = pipe == "simple_bpsk" ? "bpsk" : "qpsk";
+        dp = Params{{"constellation", con}, {"symbolrate", "1200000"}, {"rrc_alpha", "0.5"}, {"pll_bw", "0.003"}};
+        fp = Params{{"constellation", con}, {"cadu_size", "8192"}, {"nrzm", pipe == "simple_bpsk" ? "true" : "false"}, {"derandomize", "true"}, {"rs_i", "4"},
+                    {"rs_type", "rs223"}};
+        dec = "ccsds_simple_psk_decoder";
     } else {
         fprintf(stderr, "unknown pipeline %s\n", pipe.c_str());
         return 2;

@@ -168,14 +168,52 @@ b200_demod_cfg demod_cfg_from_params(const Params &p, bool &is_bpsk)
 b200_fec_cfg fec_cfg_from_params(const std::string &id, const Params &p)
 {
     b200_fec_cfg c{};
-    c.outsync_after = (int)p.num("viterbi_outsync_after");
-    c.ber_thresold = (float)p.num("viterbi_ber_thresold");
+    if (id != "ccsds_simple_psk_decoder") {
+        c.outsync_after = (int)p.num("viterbi_outsync_after");
+        c.ber_thresold = (float)p.num("viterbi_ber_thresold");
+    }
     c.device = (int)p.num("b200_device", 0);
     c.asm_sync = 0x1ACFFC1D;
     if (id == "metop_ahrpt_decoder") {
         c.kind = B200_FEC_METOP;
         c.constellation = B200_QPSK;
         c.cadu_size = 8192;
+        return c;
+    }
+    if (id == "ccsds_simple_psk_decoder") { // module_ccsds_simple_psk_decoder.cpp:19-98
+        c.kind = B200_FEC_SIMPLE;
+        c.outsync_after = 0;
+        c.ber_thresold = 0;
+        const std::string con = p.str("constellation");
+        if (con == "bpsk") c.constellation = B200_BPSK;
+        else if (con == "qpsk") c.constellation = B200_QPSK;
+        else throw ModuleError("CCSDS Simple PSK Decoder : invalid constellation type!");
+        c.cadu_size = (int)p.num("cadu_size");
+        c.qpsk_swap_iq = p.flag("qpsk_swap_iq", false);
+        c.qpsk_swap_diff = p.flag("qpsk_swap_diff", true);
+        c.oqpsk_delay = p.flag("oqpsk_delay", false);
+        if (p.flag("oqpsk_method2", false) || p.flag("oqpsk_method3", false))
+            throw ModuleError("oqpsk_method2 / oqpsk_method3 are not supported by the B200 path");
+        if (p.flag("hard_symbols", false))
+            throw ModuleError("hard_symbols input is not supported by the B200 path");
+        c.nrzm = p.flag("nrzm", false);
+        c.derandomize = p.flag("derandomize", true);
+        c.derand_after_rs = p.flag("derand_after_rs", false);
+        c.derand_start = (int)p.num("derand_start", 4);
+        c.rs_i = (int)p.num("rs_i");
+        c.rs_fill_bytes = (int)p.num("rs_fill_bytes", -1);
+        c.rs_dualbasis = p.flag("rs_dualbasis", true);
+        const std::string rst = p.str("rs_type", "none");
+        if (c.rs_i != 0) {
+            if (rst == "rs223") c.rs_type = 0;
+            else if (rst == "rs239") c.rs_type = 1;
+            else throw ModuleError("CCSDS Simple PSK Decoder : invalid Reed-Solomon type!");
+        }
+        c.rs_usecheck = p.flag("rs_usecheck", false);
+        if (p.has("asm"))
+            c.asm_sync = (unsigned)std::stoul(p.str("asm"), nullptr, 16);
+        if (p.has("ccsds") && !p.flag("ccsds", true))
+            throw ModuleError("ccsds=false (.frm output naming) is not supported by the B200 path");
         return c;
     }
     if (id != "ccsds_conv_concat_decoder")

@@ -218,6 +218,30 @@ CONFIGS = {
 }
 
 
+def qpsk_diff_encode(dibits, swap=True):
+    """Transmit side of the reference's QPSKDiff decoder (src-core/common/codings/differential/qpsk_diff.cpp:5-53): hard symbols
+    s = 2*X + Y (X on the Q rail, Y on the I rail, as constellation_t::soft_demod reads them) such that decoding the pair
+    (s[i-1], s[i]) gives dibits[i]. Two leading symbols fill the decoder's buffer."""
+    def dec(prev, cur):
+        xin_1, yin_1, xin, yin = prev & 2, prev & 1, cur & 2, cur & 1
+        if ((xin >> 1) ^ yin) == 1:
+            ou = ((yin_1 ^ yin) << 1) + ((xin_1 ^ xin) >> 1)
+        else:
+            ou = (xin_1 ^ xin) + (yin_1 ^ yin)
+        return ((ou & 1) << 1 | (ou >> 1)) if swap else ou  # value of the two output bits, first bit = MSB
+    nxt = np.zeros((4, 4), np.int64)
+    for prev in range(4):
+        for cur in range(4):
+            nxt[prev, dec(prev, cur)] = cur
+    d = np.asarray(dibits, np.int64)
+    out = np.zeros(d.size + 2, np.int64)
+    cur = 0
+    for i, v in enumerate(d.tolist()):
+        cur = int(nxt[cur, v])
+        out[i + 2] = cur
+    return out
+
+
 def make_bitstream(cfg: SignalCfg, nframes, seed):
     rng = np.random.default_rng(seed)
     payload = rng.integers(0, 256, size=(nframes, cfg.interleave * 223), dtype=np.uint8)

@@ -41,6 +41,16 @@ def main():
                      rs_err=f["rs_err"])
         np.savez_compressed(os.path.join(OUT, f"{name}.npz"), **d)
         print(name, {k: (v.shape if hasattr(v, "shape") else v) for k, v in d.items()})
+    if not only or "simple_psk" in only:
+        from tests.common import simple_soft_cases
+        cases, _ = simple_soft_cases()
+        d = {}
+        for name, kw, soft in cases:
+            f = ref.Fec(ref.simple_cfg(cadu_size=8192, rs_i=4, **kw))
+            r = f.run(soft[:soft.size // f.chunk * f.chunk])
+            d[f"{name}_soft"], d[f"{name}_cadu"], d[f"{name}_bits"] = soft, r["cadu"], np.packbits(r["bits"])
+        np.savez_compressed(os.path.join(OUT, "simple_psk.npz"), **d)
+        print("simple_psk", {k: v.shape for k, v in d.items() if k.endswith("_cadu")})
     if only:
         return
     # FEC stress vectors: RS decoder on codewords with 0..20 byte errors (beyond-capacity ones must fail the same way)
