@@ -209,6 +209,12 @@ CONFIGS = {
     # 2.64 MS/s (66/65). Exercises the interpolating branch of the resampler; too close to aliasing to be a decoding test
     "qpsk_undersampled": SignalCfg(name="qpsk_undersampled", samplerate=2.6e6, symbolrate=2400000, constellation="qpsk", conv="1/2",
                                    interleave=4, rrc_alpha=0.1, fmt="cs16", decoder="none", esn0_db=14.0),
+    # psk_demod -> ccsds_simple_psk_decoder (no convolutional code; 50 shipped pipelines have this shape, e.g. FengYun-3.json:630-639):
+    # BPSK + NRZ-M + RS I=4, and QPSK (I rail first on air, so the receiver runs with qpsk_swap_iq) + RS I=4
+    "bpsk_simple": SignalCfg(name="bpsk_simple", samplerate=3e6, symbolrate=1200000, constellation="bpsk", conv="none", interleave=4, nrzm=True,
+                             fmt="cs16", decoder="simple", esn0_db=9.0),
+    "qpsk_simple": SignalCfg(name="qpsk_simple", samplerate=6e6, symbolrate=2400000, constellation="qpsk", conv="none", interleave=4, fmt="cs16",
+                             decoder="simple", esn0_db=12.0),
     # 8PSK through psk_demod alone (order-8 Costas loop; no decoder of this path takes 8PSK): demodulator parity only
     "psk8": SignalCfg(name="psk8", samplerate=6e6, symbolrate=2400000, constellation="8psk", conv="none", interleave=4, fmt="cs16",
                       decoder="demod", esn0_db=18.0),

@@ -39,7 +39,7 @@ def oracle_demod(O, cfg):
 
 def oracle_fec(O, cfg):
     if cfg.decoder == "simple":
-        return O.Fec(O.simple_cfg(cfg.constellation, cfg.cadu_bytes * 8, cfg.interleave, nrzm=cfg.nrzm))
+        return O.Fec(O.simple_cfg(cfg.constellation, cfg.cadu_bytes * 8, cfg.interleave, nrzm=cfg.nrzm, qpsk_swap_iq=cfg.constellation == "qpsk"))
     if cfg.decoder == "metop":
         return O.Fec(O.metop_cfg(cfg.ber_thresold, cfg.outsync_after))
     return O.Fec(O.ccsds_cfg(cfg.constellation, cfg.cadu_bytes * 8, cfg.ber_thresold, cfg.outsync_after, cfg.interleave, nrzm=cfg.nrzm,
@@ -54,7 +54,8 @@ def gpu_demod(cfg, n, keep_stages=False):
 def gpu_fec_cfg(cfg, max_soft):
     from satdump_b200 import capi
     if cfg.decoder == "simple":
-        return capi.simple_cfg(cfg.constellation, cfg.cadu_bytes * 8, cfg.interleave, nrzm=cfg.nrzm, max_soft=max(max_soft, 65536))
+        return capi.simple_cfg(cfg.constellation, cfg.cadu_bytes * 8, cfg.interleave, nrzm=cfg.nrzm, qpsk_swap_iq=cfg.constellation == "qpsk",
+                               max_soft=max(max_soft, 65536))
     if cfg.decoder == "metop":
         return capi.metop_cfg(cfg.ber_thresold, cfg.outsync_after, max_soft=max(max_soft, 65536))
     return capi.ccsds_cfg(cfg.constellation, cfg.cadu_bytes * 8, cfg.ber_thresold, cfg.outsync_after, cfg.interleave, nrzm=cfg.nrzm,

@@ -21,7 +21,7 @@ OUT = os.path.dirname(os.path.abspath(__file__))
 def main():
     assert ref.available(), "build oracle/_ref first (python -c 'import __graft_entry__ as g; g.build()')"
     only = sys.argv[1:]
-    for name, lg in [("metop_ahrpt", 17), ("bpsk_half", 16), ("jpss_hrd", 17), ("dvbs2_front", 16), ("hrpt_bpsk", 18), ("qpsk_undersampled", 16), ("psk8", 17)]:
+    for name, lg in [("metop_ahrpt", 17), ("bpsk_half", 16), ("jpss_hrd", 17), ("dvbs2_front", 16), ("hrpt_bpsk", 18), ("qpsk_undersampled", 16), ("psk8", 17), ("bpsk_simple", 17), ("qpsk_simple", 17)]:
         if only and name not in only:
             continue
         cfg = synth.CONFIGS[name]
@@ -35,7 +35,7 @@ def main():
         if dc.final_samplerate > 0:  # the front-end resampler ran: pin its output and its bank too
             I, D = int(dc.final_samplerate), int(dc.samplerate)
             d.update(resamp_head=ref.resample(dc, raw)[:4096], front=np.int64(o["front"]), resamp_bank=ref.resampler_taps(I, D))
-        if cfg.decoder in ("metop", "ccsds"):
+        if cfg.decoder in ("metop", "ccsds", "simple"):
             f = oracle_fec(ref, cfg).run(o["soft"])
             d.update(cadu=f["cadu"], bits=np.packbits(f["bits"]), nbits=np.int64(f["bits"].size), vit_state=f["vit_state"], defr_state=f["defr_state"],
                      rs_err=f["rs_err"])

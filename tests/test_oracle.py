@@ -9,7 +9,7 @@ from tests.common import ROOT, oracle_demod, oracle_fec, signal, simple_soft_cas
 from satdump_b200 import synth
 
 GOLD = os.path.join(ROOT, "tests", "golden")
-CONFIGS = ["metop_ahrpt", "bpsk_half", "jpss_hrd", "dvbs2_front", "hrpt_bpsk", "qpsk_undersampled", "psk8"]
+CONFIGS = ["metop_ahrpt", "bpsk_half", "jpss_hrd", "dvbs2_front", "hrpt_bpsk", "qpsk_undersampled", "psk8", "bpsk_simple", "qpsk_simple"]
 
 
 def _ref():
@@ -38,7 +38,7 @@ def test_port_matches_golden(built, name):
         assert bitwise(port.resample(dc, g["raw"])[:4096], g["resamp_head"]) and o["front"] == int(g["front"])
         assert bitwise(port.resampler_taps(int(dc.final_samplerate), int(dc.samplerate)), g["resamp_bank"])
     assert np.array_equal(o["soft"], g["soft"])
-    if cfg.decoder in ("metop", "ccsds"):
+    if cfg.decoder in ("metop", "ccsds", "simple"):
         f = oracle_fec(port, cfg).run(o["soft"])
         assert np.array_equal(f["cadu"], g["cadu"])
         assert np.array_equal(np.packbits(f["bits"]), g["bits"]) and f["bits"].size == int(g["nbits"])
@@ -53,7 +53,7 @@ def test_ref_matches_golden(built, name):
     cfg = synth.CONFIGS[name]
     o = oracle_demod(ref, cfg).run(g["raw"])
     assert np.array_equal(o["soft"], g["soft"]) and bitwise(o["mm"][:4096], g["mm_head"])
-    if cfg.decoder in ("metop", "ccsds"):
+    if cfg.decoder in ("metop", "ccsds", "simple"):
         assert np.array_equal(oracle_fec(ref, cfg).run(o["soft"])["cadu"], g["cadu"])
 
 
@@ -67,7 +67,7 @@ def test_port_equals_reference_fresh_signal(built, name):
     for k in ("agc", "fir", "costas", "mm", "soft"):
         if a[k] is not None:
             assert bitwise(a[k], b[k]), k
-    if cfg.decoder in ("metop", "ccsds"):
+    if cfg.decoder in ("metop", "ccsds", "simple"):
         fa, fb = oracle_fec(ref, cfg).run(a["soft"]), oracle_fec(port, cfg).run(a["soft"])
         for k in ("cadu", "bits", "vit_state", "defr_state", "rs_err"):
             assert np.array_equal(fa[k], fb[k]), k
