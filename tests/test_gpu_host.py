@@ -60,3 +60,21 @@ def test_metop_recorded_at_12msps_goes_through_the_front_end_resampler(built, tm
     assert r.returncode == 0, r.stderr
     got = np.fromfile(hint + ".cadu", np.uint8)
     assert got.size == want.size and np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("mode", ["two_stage", "fused"])
+def test_simple_psk_decoder_cli(built, tmp_path, mode):
+    """psk_demod -> ccsds_simple_psk_decoder (uncoded BPSK + NRZ-M + RS I=4) through the C++ module layer: same .cadu bytes as the
+    reference's code."""
+    O = oracle()
+    cfg, raw, _ = signal("bpsk_simple", 22)
+    inp = tmp_path / "b.cs16"
+    raw.tofile(inp)
+    want = oracle_fec(O, cfg).run(oracle_demod(O, cfg).run(raw, stages=False)["soft"])["cadu"]
+    assert want.size >= 100 * 1024
+    hint = str(tmp_path / f"simple_{mode}")
+    cmd = [TOOL, "simple_bpsk", "baseband", str(inp), hint, "--samplerate", "3e6", "--baseband_format", "cs16"] + (["--fused"] if mode == "fused" else [])
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    got = np.fromfile(hint + ".cadu", np.uint8)
+    assert got.size == want.size and np.array_equal(got, want)
