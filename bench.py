@@ -44,30 +44,50 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons DURING the timed regions. In-process NVML (nvidia_ml_py) every 25 ms; spawning nvidia-smi
+    (the fallback) costs ~0.5 s of driver-lock time per call and visibly slows a 200 ms timed region."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.sm, self.max_sm, self.mask, self.stop_flag, self.how = index, [], None, 0, False, "nvml"
 
     def run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_sm = int(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            while not self.stop_flag:
+                self.sm.append(int(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                self.mask |= int(reasons(h))
+                time.sleep(0.025)
+            return
+        except Exception:
+            self.how = "nvidia-smi"
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         while not self.stop_flag:
             try:
                 out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                r = [x.strip() for x in out.split(",")]
+                if r and r[0].isdigit():
+                    self.sm.append(int(r[0]))
+                    self.max_sm = int(r[1]) if r[1].isdigit() else self.max_sm
+                    for i, bit in enumerate((0x8, 0x40, 0x20, 0x4)):
+                        if len(r) > 2 + i and r[2 + i].lower().startswith("active"):
+                            self.mask |= bit
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.5)
 
     def summary(self):
-        if not self.rows:
+        if not self.sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
-                "reasons": reasons, "samples": len(self.rows)}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_sm, "reasons": [n for b, n in self.REASONS.items() if self.mask & b],
+                "samples": len(sm), "source": self.how}
 
 
 def make_workload(log2n, rank, device):

@@ -248,7 +248,14 @@ Demod::Demod(const b200_demod_cfg &c) : cfg(c)
     cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, c.device);
     seg_cap_threads = dev_sms * 3 * SEG_THREADS;
 
-    B200_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    {
+        // in a pipelined chain the demodulator of batch i runs next to the decoder of batch i-1 and is the longer of the two: its
+        // kernels take freed SM slots first (B200_STREAM_PRIORITY=0 disables, for A/B measurements)
+        int lo = 0, hi = 0;
+        B200_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        const char *e = getenv("B200_STREAM_PRIORITY");
+        B200_CUDA(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, (e && atoi(e) == 0) ? lo : hi));
+    }
     for (auto &e : ev)
         B200_CUDA(cudaEventCreate(&e));
     const int fmt_bytes = c.format == B200_CF32 ? 8 : (c.format == B200_CS16 ? 4 : 2);
@@ -392,7 +399,7 @@ template <int FMT> static void launch_front(Demod &d, const void *raw, long n, i
     for (int pass = 0; pass < 2; pass++) {
         ctl.seeded = pass;
         if (pass) { // exact pass: returns at once unless the fast pass asked for it
-            k_agc_compose<FMT><<<ntiles, FIR_THREADS, 0, d.stream>>>(raw, n, d.cfg.agc_rate, need, d.tile_map.p);
+            k_agc_compose<FMT><<<std::min(ntiles, d.fir_ctas * 2), FIR_THREADS, 0, d.stream>>>(raw, n, d.cfg.agc_rate, need, ntiles, d.tile_map.p);
             k_agc_scan<<<1, 1024, 0, d.stream>>>(d.tile_map.p, ntiles, &S->gain[cur], need, d.seeds.p, &S->agc_exact);
         }
         if (dump)

@@ -561,32 +561,35 @@ __global__ void __launch_bounds__(FIR_THREADS, 5) k_agc_fir(const void *__restri
 
 // ---------------------------------------------------------------- exact pass (weak signals): per-tile maps -> scan -> seeds
 template <int FMT>
-__global__ void __launch_bounds__(FIR_THREADS) k_agc_compose(const void *__restrict__ raw, long N, float rate, const int *__restrict__ need,
+__global__ void __launch_bounds__(FIR_THREADS) k_agc_compose(const void *__restrict__ raw, long N, float rate, const int *__restrict__ need, int ntiles,
                                                              Affine *__restrict__ tile_map)
 {
-    if (*need == 0)
+    if (*need == 0) // the usual case: a small grid that returns at once
         return;
-    const int k = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     __shared__ Affine wsum[FIR_THREADS / 32];
-    const long s0 = (long)k * FIR_TILE + 8 * t;
-    Affine m{1.0, 0.0};
-    float2 x[8];
-    load8<FMT>(raw, s0, N, x);
+    for (int k = blockIdx.x; k < ntiles; k += gridDim.x) {
+        const long s0 = (long)k * FIR_TILE + 8 * t;
+        Affine m{1.0, 0.0};
+        float2 x[8];
+        load8<FMT>(raw, s0, N, x);
 #pragma unroll
-    for (int i = 0; i < 8; i++)
-        if (s0 + i < N) {
-            const float mag = fast_mag(fmaf(x[i].x, x[i].x, x[i].y * x[i].y));
-            m = compose(m, Affine{1.0 - (double)rate * (double)mag, (double)rate});
+        for (int i = 0; i < 8; i++)
+            if (s0 + i < N) {
+                const float mag = fast_mag(fmaf(x[i].x, x[i].x, x[i].y * x[i].y));
+                m = compose(m, Affine{1.0 - (double)rate * (double)mag, (double)rate});
+            }
+        m = warp_scan_inclusive(m, lane);
+        if (lane == 31)
+            wsum[warp] = m;
+        __syncthreads();
+        if (t == 0) {
+            Affine tot = wsum[0];
+            for (int w = 1; w < FIR_THREADS / 32; w++)
+                tot = compose(tot, wsum[w]);
+            tile_map[k] = tot;
         }
-    m = warp_scan_inclusive(m, lane);
-    if (lane == 31)
-        wsum[warp] = m;
-    __syncthreads();
-    if (t == 0) {
-        Affine tot = wsum[0];
-        for (int w = 1; w < FIR_THREADS / 32; w++)
-            tot = compose(tot, wsum[w]);
-        tile_map[k] = tot;
+        __syncthreads();
     }
 }
 
