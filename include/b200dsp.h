@@ -43,7 +43,7 @@ enum { B200_CF32 = 0, B200_CS16 = 1, B200_CS8 = 2 };
 /* decoder kind */
 enum { B200_FEC_METOP = 0, B200_FEC_CCSDS = 1, B200_FEC_SIMPLE = 2 };
 /* debug stage ids for b200_demod_debug_stage */
-enum { B200_STAGE_AGC = 0, B200_STAGE_FIR = 1, B200_STAGE_COSTAS = 2, B200_STAGE_RESAMP = 3 };
+enum { B200_STAGE_AGC = 0, B200_STAGE_FIR = 1, B200_STAGE_COSTAS = 2, B200_STAGE_RESAMP = 3, B200_STAGE_DC = 4 };
 
 typedef struct b200_demod_cfg
 {
@@ -67,6 +67,7 @@ typedef struct b200_demod_cfg
     double final_samplerate;  /* 0 = samplerate. Otherwise the rate BaseDemodModule::initb resamples to when samplerate/symbolrate is
                                  outside [min_sps, max_sps] (module_demod_base.cpp:59-87,203-204): use b200_demod_final_samplerate().
                                  Only the rational part of SmartResamplerBlock is built: samplerate / final_samplerate must be < 2 */
+    int dc_block;             /* "dc_block": CorrectIQBlock in front (utils/correct_iq.cpp:18-35, module_demod_base.cpp:113-114) */
 } b200_demod_cfg;
 
 typedef struct b200_fec_cfg

@@ -222,6 +222,7 @@ typedef struct
     cf_t *w0, *w1, *w2; /* per-buffer scratch */
     orc_resamp rs;      /* front-end resampler (module_demod_base.cpp:203-204) */
     long last_front;    /* samples that entered the AGC in the last orc_demod_run call */
+    cf_t dc_acc;        /* CorrectIQBlock::acc */
     cf_t *rs_in;
 } orc_demod;
 
@@ -293,6 +294,20 @@ static void convert_in(const orc_demod_cfg *c, const void *raw, long off, int n,
     else { const int8_t *s = (const int8_t *)raw + off * 2; for (int i = 0; i < 2 * n; i++) o[i] = ((float)s[i]) / 127.0f; }
     if (c->iq_swap) /* file_source.cpp:31-33 */
         for (int i = 0; i < n; i++) { float t = dst[i].re; dst[i].re = dst[i].im; dst[i].im = t; }
+}
+
+/* reader + optional CorrectIQBlock<complex_t>::work (utils/correct_iq.cpp:18-35; alpha = 1e-4 member default, beta = 1 - alpha) */
+static void front_in(orc_demod *d, const void *raw, long off, int n, cf_t *dst)
+{
+    convert_in(&d->cfg, raw, off, n, dst);
+    if (!d->cfg.dc_block) return;
+    const float alpha = 0.0001, beta = 1.0f - alpha;
+    for (int i = 0; i < n; i++) {
+        d->dc_acc.re = d->dc_acc.re * beta + dst[i].re * alpha;
+        d->dc_acc.im = d->dc_acc.im * beta + dst[i].im * alpha;
+        dst[i].re = dst[i].re - d->dc_acc.re;
+        dst[i].im = dst[i].im - d->dc_acc.im;
+    }
 }
 
 /* AGCBlock<complex_t>::work — agc.cpp:25-39. The magnitude goes through ::sqrt(double). */
@@ -415,11 +430,11 @@ long orc_demod_run(void *h, const void *raw, long nsamples, float *agc_out, floa
     for (long off = 0; off < nsamples; off += d->buffer_size) {
         int n = (int)(nsamples - off < d->buffer_size ? nsamples - off : d->buffer_size);
         if (d->rs.active) {
-            convert_in(&d->cfg, raw, off, n, d->rs_in);
+            front_in(d, raw, off, n, d->rs_in);
             n = resamp_run(&d->rs, (const float *)d->rs_in, n, (float *)d->w0);
             if (n <= 0) continue;
         } else
-            convert_in(&d->cfg, raw, off, n, d->w0);
+            front_in(d, raw, off, n, d->w0);
         agc_run(d, d->w0, d->w1, n);
         if (agc_out) memcpy(agc_out + pos * 2, d->w1, n * sizeof(cf_t));
         fir_run(d, d->w1, d->w0, n);
@@ -459,7 +474,7 @@ long orc_resample(const orc_demod_cfg *c, const void *raw, long nsamples, float 
     cf_t *in = malloc(sizeof(cf_t) * d->buffer_size);
     for (long off = 0; off < nsamples; off += d->buffer_size) {
         int n = (int)(nsamples - off < d->buffer_size ? nsamples - off : d->buffer_size);
-        convert_in(&d->cfg, raw, off, n, in);
+        front_in(d, raw, off, n, in);
         int m = n;
         const float *src = (const float *)in;
         if (d->rs.active) { m = resamp_run(&d->rs, (const float *)in, n, (float *)d->w0); src = (const float *)d->w0; }

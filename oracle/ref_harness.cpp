@@ -40,6 +40,7 @@
 #define private public
 #include "common/dsp/block.h"
 #include "common/dsp/utils/agc.h"
+#include "common/dsp/utils/correct_iq.h"
 #include "common/dsp/filter/fir.h"
 #include "common/dsp/filter/firdes.h"
 #include "common/dsp/pll/costas_loop.h"
@@ -93,6 +94,7 @@ extern "C"
         int buffer_size;         /* 0 = reference default rule */
         int iq_swap;             /* FileSourceBlock(.., iq_swap): re <-> im at the reader (file_source.cpp:31-33) */
         double final_samplerate; /* 0 = samplerate (sps inside [MIN_SPS, MAX_SPS]); else BaseDemodModule::initb's resampled rate */
+        int dc_block;            /* CorrectIQBlock behind the reader (module_demod_base.cpp:113-114) */
     } ref_demod_cfg;
 
     typedef struct
@@ -120,6 +122,8 @@ namespace
         float final_samplerate, final_sps;
         std::shared_ptr<dsp::stream<complex_t>> in;
         std::shared_ptr<dsp::SmartResamplerBlock<complex_t>> resampler; /* module_demod_base.cpp:203-204 */
+        std::shared_ptr<dsp::stream<complex_t>> dc_in;
+        std::shared_ptr<dsp::CorrectIQBlock<complex_t>> dc; /* module_demod_base.cpp:113-114 */
         std::vector<complex_t> rs_in;
         std::shared_ptr<dsp::AGCBlock<complex_t>> agc;
         std::shared_ptr<dsp::FIRBlock<complex_t>> rrc;
@@ -153,6 +157,21 @@ namespace
                 dst[i] = complex_t(dst[i].imag, dst[i].real);
     }
 
+    /* reader (+ iq_swap) and the optional DC blocker: n samples into dst */
+    void front_block(RefDemod *d, const void *raw, long off, int n, complex_t *dst)
+    {
+        if (!d->dc)
+        {
+            convert_block(d->cfg, raw, off, n, dst);
+            return;
+        }
+        convert_block(d->cfg, raw, off, n, d->dc_in->writeBuf);
+        d->dc_in->swap(n);
+        d->dc->work();
+        memcpy(dst, d->dc->output_stream->readBuf, n * sizeof(complex_t));
+        d->dc->output_stream->flush();
+    }
+
     struct RefFec
     {
         ref_fec_cfg cfg;
@@ -183,6 +202,11 @@ extern "C"
         d->final_samplerate = c->final_samplerate > 0 ? (float)c->final_samplerate : (float)samplerate;
         d->final_sps = d->final_samplerate / (float)symbolrate;
         d->in = std::make_shared<dsp::stream<complex_t>>();
+        if (c->dc_block)
+        {
+            d->dc_in = std::make_shared<dsp::stream<complex_t>>();
+            d->dc = std::make_shared<dsp::CorrectIQBlock<complex_t>>(d->dc_in);
+        }
         if (c->final_samplerate > 0 && (long)c->final_samplerate != samplerate)
         {
             /* module_demod_base.cpp:84-87,203-204: buffer scaled by ceil(decimation factor), resampler (final, input) */
@@ -257,13 +281,13 @@ extern "C"
             int n = (int)std::min<long>(d->buffer_size, nsamples - off);
             if (d->resampler)
             {
-                convert_block(d->cfg, raw, off, n, d->rs_in.data());
+                front_block(d, raw, off, n, d->rs_in.data());
                 n = d->resampler->process(d->rs_in.data(), n, d->in->writeBuf);
                 if (n <= 0)
                     continue;
             }
             else
-                convert_block(d->cfg, raw, off, n, d->in->writeBuf);
+                front_block(d, raw, off, n, d->in->writeBuf);
             d->in->swap(n);
             d->agc->work();
             if (agc_out)
@@ -318,7 +342,7 @@ extern "C"
         for (long off = 0; off < nsamples; off += d->buffer_size)
         {
             int n = (int)std::min<long>(d->buffer_size, nsamples - off);
-            convert_block(d->cfg, raw, off, n, in.data());
+            front_block(d, raw, off, n, in.data());
             int m = n;
             if (d->resampler)
                 m = d->resampler->process(in.data(), n, tmp.data());

@@ -283,7 +283,7 @@ Demod::Demod(const b200_demod_cfg &c) : cfg(c)
         B200_CUDA(cudaFuncSetAttribute(k_agc_fir<1, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         B200_CUDA(cudaFuncSetAttribute(k_agc_fir<2, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         int per_sm = 0;
-        if (c.format == B200_CF32 || resamp)
+        if (c.format == B200_CF32 || resamp || c.dc_block)
             B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_agc_fir<0, false>, FIR_THREADS, 0));
         else if (c.format == B200_CS16)
             B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_agc_fir<1, false>, FIR_THREADS, 0));
@@ -306,6 +306,12 @@ Demod::Demod(const b200_demod_cfg &c) : cfg(c)
     sym_out.alloc((size_t)(max_work / omin) + 1024);
     soft.alloc(((size_t)(max_work / omin) + 1024) * bps);
     d_bank.alloc(128 * 8);
+    if (cfg.dc_block) {
+        const int nt = (int)((max_batch + FIR_TILE - 1) / FIR_TILE);
+        dc_map.alloc(nt + 1);
+        dc_seeds.alloc(nt + 2);
+        dc_out.alloc(max_batch + 64);
+    }
     if (resamp) {
         d_rs_bank.alloc(rs_bank.size());
         rs_out.alloc(max_work + 64);
@@ -420,9 +426,33 @@ long Demod::process(const void *d_raw, long n, int8_t *soft_dst)
     const int cur = parity, nxt = parity ^ 1;
     DemodDevState *S = st.p;
     const long n_in = n;
+    last_in = n;
     int front_fmt = cfg.format;
     B200_CUDA(cudaEventRecord(ev[0], stream));
-    if (resamp) {
+    int rs_swap = cfg.iq_swap;
+    if (cfg.dc_block) {
+        // CorrectIQBlock sits right behind the reader (module_demod_base.cpp:113-120): (iq_swap ->) dc block -> (resampler ->) AGC
+        const int nt = (int)((n + FIR_TILE - 1) / FIR_TILE);
+        const float alpha = 0.0001f, beta = 1.0f - alpha; // correct_iq.h:24, correct_iq.cpp:9
+#define B200_DC(F)                                                                                                                          \
+    do {                                                                                                                                    \
+        k_dc_tile<F><<<nt, FIR_THREADS, 0, stream>>>(d_raw, n, cfg.iq_swap, alpha, beta, dc_map.p);                                         \
+        k_dc_scan<<<1, 1024, 0, stream>>>(dc_map.p, nt, &S->dc_acc[cur], dc_seeds.p);                                                        \
+        k_dc_apply<F><<<nt, FIR_THREADS, 0, stream>>>(d_raw, n, cfg.iq_swap, alpha, beta, dc_seeds.p, dc_out.p, &S->dc_acc[nxt]);            \
+    } while (0)
+        if (cfg.format == B200_CF32)
+            B200_DC(0);
+        else if (cfg.format == B200_CS16)
+            B200_DC(1);
+        else
+            B200_DC(2);
+#undef B200_DC
+        launches += 3;
+        d_raw = dc_out.p;
+        front_fmt = B200_CF32;
+        rs_swap = 0; // already applied
+    }
+    if (resamp && !(cfg.dc_block && rs_I == 1 && rs_D == 1 && rs_nt == 1)) {
         // outputs of this batch: all j >= 0 with rs_inc + (rs_ctr + j*D) / I < n  (the while loop of rational_resampler.cpp:48-57)
         const long I = rs_I, D = rs_D;
         long J = 0;
@@ -430,12 +460,12 @@ long Demod::process(const void *d_raw, long n, int8_t *soft_dst)
             J = ((n - rs_inc) * I - rs_ctr + D - 1) / D;
         B200_REQUIRE(J >= 64 && J <= max_work, B200_ESTATE, "batch of %ld samples resamples to %ld: outside [64, %ld]", n, J, max_work);
         const unsigned grid = (unsigned)((J + RS_THREADS - 1) / RS_THREADS);
-        if (cfg.format == B200_CF32)
-            k_resample<0><<<grid, RS_THREADS, 0, stream>>>(d_raw, n, cfg.iq_swap, S->rs_tail[cur], S->rs_tail[nxt], d_rs_bank.p, rs_I, rs_D, rs_nt, rs_inc, rs_ctr, J, rs_out.p);
-        else if (cfg.format == B200_CS16)
-            k_resample<1><<<grid, RS_THREADS, 0, stream>>>(d_raw, n, cfg.iq_swap, S->rs_tail[cur], S->rs_tail[nxt], d_rs_bank.p, rs_I, rs_D, rs_nt, rs_inc, rs_ctr, J, rs_out.p);
+        if (front_fmt == B200_CF32)
+            k_resample<0><<<grid, RS_THREADS, 0, stream>>>(d_raw, n, rs_swap, S->rs_tail[cur], S->rs_tail[nxt], d_rs_bank.p, rs_I, rs_D, rs_nt, rs_inc, rs_ctr, J, rs_out.p);
+        else if (front_fmt == B200_CS16)
+            k_resample<1><<<grid, RS_THREADS, 0, stream>>>(d_raw, n, rs_swap, S->rs_tail[cur], S->rs_tail[nxt], d_rs_bank.p, rs_I, rs_D, rs_nt, rs_inc, rs_ctr, J, rs_out.p);
         else
-            k_resample<2><<<grid, RS_THREADS, 0, stream>>>(d_raw, n, cfg.iq_swap, S->rs_tail[cur], S->rs_tail[nxt], d_rs_bank.p, rs_I, rs_D, rs_nt, rs_inc, rs_ctr, J, rs_out.p);
+            k_resample<2><<<grid, RS_THREADS, 0, stream>>>(d_raw, n, rs_swap, S->rs_tail[cur], S->rs_tail[nxt], d_rs_bank.p, rs_I, rs_D, rs_nt, rs_inc, rs_ctr, J, rs_out.p);
         launches++;
         const long c_end = rs_ctr + J * D;
         rs_inc = rs_inc + c_end / I - n;
@@ -703,7 +733,8 @@ int b200_demod_debug_stage(b200_demod *h, int stage, float *out, long cap_sample
         B200_REQUIRE(h && out, B200_EINVAL, "NULL argument");
         Demod &d = *h->d;
         B200_REQUIRE(d.cfg.keep_stages, B200_ESTATE, "create the demodulator with keep_stages=1 to read stage outputs");
-        B200_REQUIRE(d.last_n <= cap_samples, B200_ESTATE, "output buffer too small");
+        const long count = stage == B200_STAGE_DC ? d.last_in : d.last_n;
+        B200_REQUIRE(count <= cap_samples, B200_ESTATE, "output buffer too small");
         const float2 *src = nullptr;
         if (stage == B200_STAGE_AGC)
             src = d.agc_dump.p;
@@ -713,9 +744,11 @@ int b200_demod_debug_stage(b200_demod *h, int stage, float *out, long cap_sample
             src = (d.order ? d.bufA.p : d.bufB.p) + 16; // M&M input = Costas output after rotation fix-up (+ OQPSK delay)
         else if (stage == B200_STAGE_RESAMP && d.resamp)
             src = d.rs_out.p; // what entered the AGC: front-end resampler / iq_swap output
+        else if (stage == B200_STAGE_DC && d.cfg.dc_block)
+            src = d.dc_out.p; // DC blocker output (as many samples as were pushed)
         B200_REQUIRE(src, B200_EINVAL, "unknown stage %d", stage);
         DeviceGuard g(d.cfg.device);
-        B200_CUDA(cudaMemcpyAsync(out, src, d.last_n * sizeof(float2), cudaMemcpyDeviceToHost, d.stream));
+        B200_CUDA(cudaMemcpyAsync(out, src, count * sizeof(float2), cudaMemcpyDeviceToHost, d.stream));
         B200_CUDA(cudaStreamSynchronize(d.stream));
     });
 }

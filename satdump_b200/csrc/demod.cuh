@@ -40,6 +40,7 @@ constexpr int MM_SMEM_BYTES = 64 * SEG_THREADS * 8 + 128 * MM_BANK_STRIDE * 4;
 struct FirTaps { float h[32]; };
 
 struct Affine { double a, b; };     // g -> a*g + b
+struct DcAff { double a, br, bi; };  // DC blocker: acc -> a*acc + (br, bi)
 
 template <int FMT> struct RawBytes;
 template <> struct RawBytes<0> { static constexpr int v = 8; };
@@ -219,6 +220,139 @@ __global__ void __launch_bounds__(RS_THREADS) k_resample(const void *__restrict_
         }
         out[j] = make_float2(re, im);
     }
+}
+
+// ---------------------------------------------------------------- K0': front-end DC blocker ("dc_block")
+// CorrectIQBlock<complex_t>::work (utils/correct_iq.cpp:18-35): acc = acc*beta + x*alpha; y = x - acc, alpha = 1e-4, beta = 1 - alpha.
+// A constant-coefficient linear recurrence: tiles of 2048 samples, each thread runs the reference's float recurrence over its 8
+// samples from 0, the (beta^8, partial) maps are composed in fp64 (k_dc_tile -> k_dc_scan over tiles -> k_dc_apply), and every thread
+// replays its 8 samples from its scanned accumulator. Output cf32 (what the reference hands to the resampler / AGC).
+__device__ __forceinline__ DcAff dc_compose(const DcAff f, const DcAff s) { return DcAff{s.a * f.a, fma(s.a, f.br, s.br), fma(s.a, f.bi, s.bi)}; }
+__device__ __forceinline__ DcAff dc_warp_scan(DcAff v, int lane)
+{
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        DcAff p;
+        p.a = __shfl_up_sync(0xffffffffu, v.a, off);
+        p.br = __shfl_up_sync(0xffffffffu, v.br, off);
+        p.bi = __shfl_up_sync(0xffffffffu, v.bi, off);
+        if (lane >= off)
+            v = dc_compose(p, v);
+    }
+    return v;
+}
+template <int FMT>
+__device__ __forceinline__ DcAff dc_local(const void *__restrict__ raw, long s0, long N, int iq_swap, float alpha, float beta, float2 (&x)[8])
+{
+    load8<FMT>(raw, s0, N, x);
+    float2 acc = make_float2(0.f, 0.f);
+    double a = 1.0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        if (iq_swap)
+            x[i] = make_float2(x[i].y, x[i].x);
+        if (s0 + i < N) {
+            acc.x = __fadd_rn(__fmul_rn(acc.x, beta), __fmul_rn(x[i].x, alpha));
+            acc.y = __fadd_rn(__fmul_rn(acc.y, beta), __fmul_rn(x[i].y, alpha));
+            a *= (double)beta;
+        }
+    }
+    return DcAff{a, (double)acc.x, (double)acc.y};
+}
+template <int FMT>
+__global__ void __launch_bounds__(FIR_THREADS) k_dc_tile(const void *__restrict__ raw, long N, int iq_swap, float alpha, float beta, DcAff *__restrict__ tile_map)
+{
+    __shared__ DcAff wsum[FIR_THREADS / 32];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    float2 x[8];
+    DcAff m = dc_local<FMT>(raw, (long)blockIdx.x * FIR_TILE + 8 * t, N, iq_swap, alpha, beta, x);
+    m = dc_warp_scan(m, lane);
+    if (lane == 31)
+        wsum[warp] = m;
+    __syncthreads();
+    if (t == 0) {
+        DcAff tot = wsum[0];
+        for (int w = 1; w < FIR_THREADS / 32; w++)
+            tot = dc_compose(tot, wsum[w]);
+        tile_map[blockIdx.x] = tot;
+    }
+}
+// seeds[k] = accumulator before tile k; seeds[ntiles] = after the batch (carried to the next one through acc_io)
+__global__ void __launch_bounds__(1024) k_dc_scan(const DcAff *__restrict__ tile_map, int ntiles, const float2 *__restrict__ acc_in, double2 *__restrict__ seeds)
+{
+    __shared__ DcAff wsum[32];
+    __shared__ double2 run;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    if (t == 0)
+        run = make_double2((double)acc_in->x, (double)acc_in->y);
+    __syncthreads();
+    for (int base = 0; base < ntiles; base += 1024) {
+        const int k = base + t;
+        DcAff m{1.0, 0.0, 0.0};
+        if (k < ntiles)
+            m = tile_map[k];
+        const DcAff inc = dc_warp_scan(m, lane);
+        if (lane == 31)
+            wsum[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            DcAff w = dc_warp_scan(wsum[lane], lane);
+            wsum[lane] = w;
+        }
+        __syncthreads();
+        DcAff pre{1.0, 0.0, 0.0};
+        if (warp > 0)
+            pre = wsum[warp - 1];
+        DcAff e;
+        e.a = __shfl_up_sync(0xffffffffu, inc.a, 1);
+        e.br = __shfl_up_sync(0xffffffffu, inc.br, 1);
+        e.bi = __shfl_up_sync(0xffffffffu, inc.bi, 1);
+        const DcAff excl = lane > 0 ? dc_compose(pre, e) : pre;
+        const double2 g0 = run;
+        if (k < ntiles)
+            seeds[k] = make_double2(fma(excl.a, g0.x, excl.br), fma(excl.a, g0.y, excl.bi));
+        __syncthreads();
+        if (t == 1023) {
+            const DcAff tot = dc_compose(pre, inc);
+            run = make_double2(fma(tot.a, g0.x, tot.br), fma(tot.a, g0.y, tot.bi));
+        }
+        __syncthreads();
+    }
+    if (t == 0)
+        seeds[ntiles] = run;
+}
+template <int FMT>
+__global__ void __launch_bounds__(FIR_THREADS) k_dc_apply(const void *__restrict__ raw, long N, int iq_swap, float alpha, float beta,
+                                                          const double2 *__restrict__ seeds, float2 *__restrict__ out, float2 *__restrict__ acc_out)
+{
+    __shared__ DcAff wsum[FIR_THREADS / 32];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const long s0 = (long)blockIdx.x * FIR_TILE + 8 * t;
+    float2 x[8];
+    const DcAff m = dc_local<FMT>(raw, s0, N, iq_swap, alpha, beta, x);
+    const DcAff inc = dc_warp_scan(m, lane);
+    if (lane == 31)
+        wsum[warp] = inc;
+    __syncthreads();
+    DcAff pre{1.0, 0.0, 0.0};
+    for (int w = 0; w < warp; w++)
+        pre = dc_compose(pre, wsum[w]);
+    DcAff e;
+    e.a = __shfl_up_sync(0xffffffffu, inc.a, 1);
+    e.br = __shfl_up_sync(0xffffffffu, inc.br, 1);
+    e.bi = __shfl_up_sync(0xffffffffu, inc.bi, 1);
+    const DcAff excl = lane > 0 ? dc_compose(pre, e) : pre;
+    const double2 g0 = seeds[blockIdx.x];
+    float2 acc = make_float2((float)fma(excl.a, g0.x, excl.br), (float)fma(excl.a, g0.y, excl.bi));
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+        if (s0 + i < N) {
+            acc.x = __fadd_rn(__fmul_rn(acc.x, beta), __fmul_rn(x[i].x, alpha));
+            acc.y = __fadd_rn(__fmul_rn(acc.y, beta), __fmul_rn(x[i].y, alpha));
+            out[s0 + i] = make_float2(x[i].x - acc.x, x[i].y - acc.y);
+            if (s0 + i == N - 1)
+                *acc_out = acc;
+        }
 }
 
 // sqrt(s2) as s2 * rsqrt(s2): one MUFU + one FMUL (~2 ulp); the max() keeps 0 * inf out (s2 == 0 -> 0)

@@ -17,6 +17,7 @@ struct DemodDevState
     MMState mm[2];
     float2 agc_tail[2][32];
     float2 rs_tail[2][RS_MAX_TAPS]; // resampler history (ntaps-1 converted input samples)
+    float2 dc_acc[2];               // DC blocker accumulator (correct_iq.h: acc)
     float2 mm_hist[2][8];
     int flags;          // bit0 AGC clamp, bit1 M&M slot overflow
     int costas_unconv;  // junctions still unconverged after the repair rounds of the last batch
@@ -70,7 +71,11 @@ class Demod
     DevBuf<float> d_rs_bank;
     DevBuf<float2> rs_out;
     long max_work = 0;             // largest sample count after the front end
+    DevBuf<DcAff> dc_map;          // DC blocker: per-tile maps, per-tile accumulators, output (cf32)
+    DevBuf<double2> dc_seeds;
+    DevBuf<float2> dc_out;
     long last_front = 0;           // samples that entered the AGC in the last batch
+    long last_in = 0;              // samples pushed in the last batch
     int agc_warm_max = 24;
     DevBuf<LoopRec> crec;
     DevBuf<MMRec> mrec;

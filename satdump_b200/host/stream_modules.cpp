@@ -144,7 +144,7 @@ b200_demod_cfg demod_cfg_from_params(const Params &p, bool &is_bpsk)
     else if (fmt == "cs16" || fmt == "s16") c.format = B200_CS16;
     else if (fmt == "cs8" || fmt == "s8") c.format = B200_CS8;
     else throw ModuleError("baseband_format " + fmt + " is not supported by the B200 path (cf32/cs16/cs8 only)");
-    reject(p, "dc_block", "CorrectIQ block");
+    c.dc_block = p.flag("dc_block", false); // module_demod_base.cpp:33-34,113-114
     reject(p, "freq_shift", "FreqShift block");
     c.iq_swap = p.flag("iq_swap", false); // module_demod_base.cpp:41-42 -> FileSourceBlock
     reject(p, "post_costas_dc", "CorrectIQ block");

@@ -198,6 +198,44 @@ def test_iq_swap(built):
     assert np.abs(a.stage("fir") - o["fir"]).max() <= 1e-5
 
 
+@pytest.mark.parametrize("name", ["metop_ahrpt", "hrpt_bpsk"])
+def test_dc_block(built, name):
+    """dc_block: CorrectIQBlock behind the reader (utils/correct_iq.cpp:18-35), before the resampler / AGC. A constant-coefficient
+    recurrence with a 10^4-sample memory, evaluated as a scan: output parity, carried accumulator across ragged pushes, and the rest
+    of the chain on top of it."""
+    from satdump_b200 import capi
+    from tests.common import demod_kwargs
+    O = oracle()
+    cfg, raw, _ = signal(name, 20)
+    raw = raw.copy()
+    if cfg.fmt == "cf32":
+        raw += np.complex64(0.03 - 0.011j)
+    else:
+        raw[0::2] += 900
+        raw[1::2] -= 400
+    n = nsamples(raw, cfg)
+    per = 1 if cfg.fmt == "cf32" else 2
+    oc = O.demod_cfg(dc_block=True, **demod_kwargs(cfg))
+    o = O.Demod(oc).run(raw)
+    g = capi.Demod(capi.demod_cfg(max_batch=n, keep_stages=True, dc_block=True, **demod_kwargs(cfg))).push(raw)
+    front = O.resample(oc, raw)  # the oracle's front end: reader -> dc block (-> resampler)
+    if g.cfg.final_samplerate > 0:
+        assert np.abs(g.stage("resamp") - front).max() <= 2e-6
+    else:
+        assert np.abs(g.stage("dc") - front).max() <= 1e-6
+    assert abs(g.stage("dc")[-100000:].mean()) < 2e-3  # the offset is gone
+    assert np.abs(g.stage("agc") - o["agc"]).max() <= 1e-5 and np.abs(g.stage("fir") - o["fir"]).max() <= 1e-5
+    assert g.symbols().size == o["mm"].size
+    one = g.stage("dc")
+    g2 = capi.Demod(capi.demod_cfg(max_batch=n, keep_stages=True, dc_block=True, **demod_kwargs(cfg)))
+    parts, prev = [], 0
+    for c in [4099, 300001, n]:
+        g2.push(raw[per * prev:per * c])
+        parts.append(g2.stage("dc"))
+        prev = c
+    assert np.abs(np.concatenate(parts) - one).max() <= 1e-6
+
+
 def test_errors_are_loud(built):
     from satdump_b200 import capi
     cfg, raw, _ = signal("metop_ahrpt", 16)

@@ -96,6 +96,20 @@ def test_simple_psk_decoder_port_equals_reference_and_golden(built):
         assert fr.shape[0] >= 20 and sum(any(np.array_equal(x, c) for c in sent) for x in fr) >= fr.shape[0] - 2, name
 
 
+def test_dc_block_port_equals_reference(built):
+    """CorrectIQBlock in front (dc_block), alone and with iq_swap and the resampler behind it."""
+    ref = _ref()
+    from oracle import port
+    from tests.common import demod_kwargs
+    for name, kw in [("metop_ahrpt", dict(dc_block=True)), ("metop_ahrpt", dict(dc_block=True, iq_swap=True)), ("hrpt_bpsk", dict(dc_block=True))]:
+        cfg, raw, _ = signal(name, 17, seed=4)
+        raw = raw + np.complex64(0.02 + 0.01j) if cfg.fmt == "cf32" else raw + np.int16(300)
+        a = ref.Demod(ref.demod_cfg(**kw, **demod_kwargs(cfg))).run(raw)
+        b = port.Demod(port.demod_cfg(**kw, **demod_kwargs(cfg))).run(raw)
+        for k in ("agc", "fir", "costas", "mm", "soft"):
+            assert bitwise(a[k], b[k]), (name, kw, k)
+
+
 def test_final_samplerate_rule():
     """BaseDemodModule::initb's choice of the working rate (module_demod_base.cpp:59-80), Python restatement vs the C ABI helper."""
     from oracle import port
