@@ -909,7 +909,9 @@ __global__ void __launch_bounds__(SEG_THREADS) k_costas(const float2 *__restrict
             lr.fr_start = freq;
         }
         const int nvalid = mine ? (int)min(16L, own1 - b) : 0;
-#pragma unroll
+        // 4 samples per loop body (the sincosf re-anchor pattern has period 4): a full 16-sample unroll is 59 KB of code and
+        // stalls on instruction fetch (ncu: no_instruction 0.8 cycles per issue)
+#pragma unroll 2
         for (int p = 0; p < 8; p++) {
             const float4 v = ring[swz16(slot + p, lane)];
             float2 o[2];
