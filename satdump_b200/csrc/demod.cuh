@@ -930,15 +930,18 @@ __global__ void __launch_bounds__(SEG_THREADS) k_costas(const float2 *__restrict
                     const float prev = phase;
                     phase = phase + (freq + P.alpha * err);
                     const float d = phase - prev; // the increment the float phase really took (exact difference)
-                    bool refresh = (j & 3) == 3 || fabsf(d) > 0.05f;
-                    // while (phase > 2*M_PI) in double == float compare against the largest float below 2*pi (0x40C90FDA)
-                    while (phase > 6.283185005f) {
-                        phase = (float)((double)phase - 6.283185307179586);
-                        refresh = true;
-                    }
-                    while (phase < -6.283185005f) {
-                        phase = (float)((double)phase + 6.283185307179586);
-                        refresh = true;
+                    bool refresh = (j & 3) == 3;
+                    if (fmaxf(fabsf(phase), fabsf(d) * 125.0f) > 6.25f) { // rare: a wrap is due or the step is too large to rotate by
+                        refresh = refresh || fabsf(d) > 0.05f;
+                        // while (phase > 2*M_PI) in double == float compare against the largest float below 2*pi (0x40C90FDA)
+                        while (phase > 6.283185005f) {
+                            phase = (float)((double)phase - 6.283185307179586);
+                            refresh = true;
+                        }
+                        while (phase < -6.283185005f) {
+                            phase = (float)((double)phase + 6.283185307179586);
+                            refresh = true;
+                        }
                     }
                     freq = fminf(P.fmax, fmaxf(P.fmin, freq));
                     if (refresh)
@@ -1098,6 +1101,39 @@ __global__ void k_rotate(const float2 *__restrict__ src, long N, int L, int orde
                          float2 *__restrict__ mmin)
 {
     const long stride = (long)gridDim.x * blockDim.x;
+    if (!oqpsk) {
+        // two samples per thread, 16-byte accesses (src and mmin + 16 are 128-byte aligned; L is a multiple of 16, so a pair never
+        // straddles two Costas segments)
+        const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+        if (tid < 8) {
+            const float2 h = hist_in[tid];
+            mmin[8 + tid] = h;
+        }
+        for (long p = tid; 2 * p < N; p += stride) {
+            const long n = 2 * p;
+            if (n + 1 < N) {
+                float4 v = *reinterpret_cast<const float4 *>(src + n);
+                float2 a = make_float2(v.x, v.y), b = make_float2(v.z, v.w);
+                if (order) {
+                    const int q = quad[n / L];
+                    a = rot_steps(a, q, order);
+                    b = rot_steps(b, q, order);
+                }
+                *reinterpret_cast<float4 *>(mmin + 16 + n) = make_float4(a.x, a.y, b.x, b.y);
+                if (n >= N - 8)
+                    hist_out[n - (N - 8)] = a;
+                if (n + 1 >= N - 8)
+                    hist_out[n + 1 - (N - 8)] = b;
+            } else {
+                float2 a = src[n];
+                if (order)
+                    a = rot_steps(a, quad[n / L], order);
+                mmin[16 + n] = a;
+                hist_out[n - (N - 8)] = a;
+            }
+        }
+        return;
+    }
     for (long n = (long)blockIdx.x * blockDim.x + threadIdx.x - 8; n < N; n += stride) {
         float2 cur, prev;
         if (n >= 0) {
@@ -1109,17 +1145,15 @@ __global__ void k_rotate(const float2 *__restrict__ src, long N, int L, int orde
         if (n >= N - 8 && n >= 0) // (the host rejects batches below 64 samples)
             hist_out[n - (N - 8)] = cur;
         float2 v = cur;
-        if (oqpsk) {
-            if (n - 1 >= 0) {
-                prev = src[n - 1];
-                if (order)
-                    prev = rot_steps(prev, quad[(n - 1) / L], order);
-            } else if (n - 1 >= -8)
-                prev = hist_in[8 + n - 1];
-            else
-                prev = make_float2(0.f, 0.f);
-            v.y = prev.y;
-        }
+        if (n - 1 >= 0) {
+            prev = src[n - 1];
+            if (order)
+                prev = rot_steps(prev, quad[(n - 1) / L], order);
+        } else if (n - 1 >= -8)
+            prev = hist_in[8 + n - 1];
+        else
+            prev = make_float2(0.f, 0.f);
+        v.y = prev.y;
         mmin[16 + n] = v;
     }
 }
