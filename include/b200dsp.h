@@ -68,6 +68,8 @@ typedef struct b200_demod_cfg
                                  outside [min_sps, max_sps] (module_demod_base.cpp:59-87,203-204): use b200_demod_final_samplerate().
                                  Only the rational part of SmartResamplerBlock is built: samplerate / final_samplerate must be < 2 */
     int dc_block;             /* "dc_block": CorrectIQBlock in front (utils/correct_iq.cpp:18-35, module_demod_base.cpp:113-114) */
+    int post_costas_dc;       /* "post_costas_dc": CorrectIQBlock between the Costas loop and the clock recovery
+                                 (module_psk_demod.cpp:127-134); not with OQPSK                                         */
 } b200_demod_cfg;
 
 typedef struct b200_fec_cfg

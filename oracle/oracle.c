@@ -222,7 +222,8 @@ typedef struct
     cf_t *w0, *w1, *w2; /* per-buffer scratch */
     orc_resamp rs;      /* front-end resampler (module_demod_base.cpp:203-204) */
     long last_front;    /* samples that entered the AGC in the last orc_demod_run call */
-    cf_t dc_acc;        /* CorrectIQBlock::acc */
+    cf_t dc_acc;        /* CorrectIQBlock::acc (front) */
+    cf_t dc_acc2;       /* CorrectIQBlock::acc (behind the Costas loop) */
     cf_t *rs_in;
 } orc_demod;
 
@@ -443,6 +444,15 @@ long orc_demod_run(void *h, const void *raw, long nsamples, float *agc_out, floa
         if (d->order) {
             costas_run(d, d->w0, d->w1, n);
             cur = d->w1;
+            if (d->cfg.post_costas_dc) { /* module_psk_demod.cpp:127-128, correct_iq.cpp:18-35 */
+                const float alpha = 0.0001, beta = 1.0f - alpha;
+                for (int i = 0; i < n; i++) {
+                    d->dc_acc2.re = d->dc_acc2.re * beta + cur[i].re * alpha;
+                    d->dc_acc2.im = d->dc_acc2.im * beta + cur[i].im * alpha;
+                    cur[i].re = cur[i].re - d->dc_acc2.re;
+                    cur[i].im = cur[i].im - d->dc_acc2.im;
+                }
+            }
             if (d->cfg.constellation == 2) delay_run(d, cur, n);
             if (costas_out) memcpy(costas_out + pos * 2, cur, n * sizeof(cf_t));
         }

@@ -29,6 +29,7 @@ typedef struct
     int iq_swap;             /* re <-> im at the reader (file_source.cpp:31-33) */
     double final_samplerate; /* 0 = samplerate; else the rate BaseDemodModule::initb resamples to (module_demod_base.cpp:59-87) */
     int dc_block;            /* CorrectIQBlock behind the reader (module_demod_base.cpp:113-114) */
+    int post_costas_dc;      /* CorrectIQBlock behind the Costas loop (module_psk_demod.cpp:127-134) */
 } orc_demod_cfg;
 
 typedef struct

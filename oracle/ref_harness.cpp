@@ -95,6 +95,7 @@ extern "C"
         int iq_swap;             /* FileSourceBlock(.., iq_swap): re <-> im at the reader (file_source.cpp:31-33) */
         double final_samplerate; /* 0 = samplerate (sps inside [MIN_SPS, MAX_SPS]); else BaseDemodModule::initb's resampled rate */
         int dc_block;            /* CorrectIQBlock behind the reader (module_demod_base.cpp:113-114) */
+        int post_costas_dc;      /* CorrectIQBlock behind the Costas loop (module_psk_demod.cpp:127-134) */
     } ref_demod_cfg;
 
     typedef struct
@@ -128,6 +129,7 @@ namespace
         std::shared_ptr<dsp::AGCBlock<complex_t>> agc;
         std::shared_ptr<dsp::FIRBlock<complex_t>> rrc;
         std::shared_ptr<dsp::CostasLoopBlock> pll;
+        std::shared_ptr<dsp::CorrectIQBlock<complex_t>> post_pll_dc;
         std::shared_ptr<dsp::DelayOneImagBlock> delay;
         std::shared_ptr<dsp::MMClockRecoveryBlock<complex_t>> rec;
         std::vector<float> rrc_taps;
@@ -226,6 +228,11 @@ extern "C"
             int order = c->constellation == 0 ? 2 : (c->constellation == 3 ? 8 : 4);
             d->pll = std::make_shared<dsp::CostasLoopBlock>(last, c->pll_bw, order, c->costas_max_offset);
             last = d->pll->output_stream;
+            if (c->post_costas_dc)
+            {
+                d->post_pll_dc = std::make_shared<dsp::CorrectIQBlock<complex_t>>(last);
+                last = d->post_pll_dc->output_stream;
+            }
             if (c->constellation == 2)
             {
                 d->delay = std::make_shared<dsp::DelayOneImagBlock>(last);
@@ -298,10 +305,14 @@ extern "C"
             if (d->pll)
             {
                 d->pll->work();
+                if (d->post_pll_dc)
+                    d->post_pll_dc->work();
                 if (d->delay)
                     d->delay->work();
-                if (costas_out)
-                    memcpy(costas_out + pos * 2, (d->delay ? d->delay->output_stream : d->pll->output_stream)->readBuf, n * sizeof(complex_t));
+                if (costas_out) /* what the clock recovery reads */
+                    memcpy(costas_out + pos * 2,
+                           (d->delay ? d->delay->output_stream : (d->post_pll_dc ? d->post_pll_dc->output_stream : d->pll->output_stream))->readBuf,
+                           n * sizeof(complex_t));
             }
             pos += n;
             d->rec->work();
@@ -699,6 +710,8 @@ extern "C"
         d->rrc->start();
         if (d->pll)
             d->pll->start();
+        if (d->post_pll_dc)
+            d->post_pll_dc->start();
         if (d->delay)
             d->delay->start();
         d->rec->start();
@@ -777,6 +790,8 @@ extern "C"
         d->rrc->stop();
         if (d->pll)
             d->pll->stop();
+        if (d->post_pll_dc)
+            d->post_pll_dc->stop();
         if (d->delay)
             d->delay->stop();
         d->rec->stop();

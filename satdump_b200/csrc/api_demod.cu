@@ -306,11 +306,17 @@ Demod::Demod(const b200_demod_cfg &c) : cfg(c)
     sym_out.alloc((size_t)(max_work / omin) + 1024);
     soft.alloc(((size_t)(max_work / omin) + 1024) * bps);
     d_bank.alloc(128 * 8);
-    if (cfg.dc_block) {
-        const int nt = (int)((max_batch + FIR_TILE - 1) / FIR_TILE);
+    if (cfg.dc_block || cfg.post_costas_dc) {
+        const int nt = (int)((std::max(max_batch, max_work) + FIR_TILE - 1) / FIR_TILE);
         dc_map.alloc(nt + 1);
         dc_seeds.alloc(nt + 2);
+    }
+    if (cfg.dc_block)
         dc_out.alloc(max_batch + 64);
+    if (cfg.post_costas_dc) {
+        B200_REQUIRE(order != 0 && c.constellation != B200_OQPSK, B200_EINVAL, "post_costas_dc needs a Costas loop and is not built for OQPSK");
+        pdc_out.alloc(max_work + 64);
+        pdc_out.zero(stream);
     }
     if (resamp) {
         d_rs_bank.alloc(rs_bank.size());
@@ -519,6 +525,18 @@ long Demod::process(const void *d_raw, long n, int8_t *soft_dst)
         mmin = bufA.p; // FIR output is dead now: reuse its buffer (in place compatible: same index mapping)
         k_rotate<<<2048, 256, 0, stream>>>(cos_out, n, L, order, cfg.constellation == B200_OQPSK, quad.p, S->mm_hist[cur], S->mm_hist[nxt], mmin);
         launches += 3;
+        if (cfg.post_costas_dc) {
+            // CorrectIQBlock on the loop's output (module_psk_demod.cpp:127-134); the clock recovery's 8-sample history are ITS outputs
+            const int nt = (int)((n + FIR_TILE - 1) / FIR_TILE);
+            const float alpha = 0.0001f, beta = 1.0f - alpha;
+            k_dc_tile<0><<<nt, FIR_THREADS, 0, stream>>>(mmin + 16, n, 0, alpha, beta, dc_map.p);
+            k_dc_scan<<<1, 1024, 0, stream>>>(dc_map.p, nt, &S->dc_acc2[cur], dc_seeds.p);
+            k_dc_apply<0><<<nt, FIR_THREADS, 0, stream>>>(mmin + 16, n, 0, alpha, beta, dc_seeds.p, pdc_out.p + 16, &S->dc_acc2[nxt]);
+            B200_CUDA(cudaMemcpyAsync(pdc_out.p + 8, S->pdc_hist[cur], 8 * sizeof(float2), cudaMemcpyDeviceToDevice, stream));
+            B200_CUDA(cudaMemcpyAsync(S->pdc_hist[nxt], pdc_out.p + 16 + n - 8, 8 * sizeof(float2), cudaMemcpyDeviceToDevice, stream));
+            launches += 3;
+            mmin = pdc_out.p;
+        }
     } else {
         mmin = bufB.p;
         k_rotate<<<2048, 256, 0, stream>>>(fir_out, n, L, 0, 0, quad.p, S->mm_hist[cur], S->mm_hist[nxt], mmin);
@@ -741,7 +759,7 @@ int b200_demod_debug_stage(b200_demod *h, int stage, float *out, long cap_sample
         else if (stage == B200_STAGE_FIR)
             src = d.fir_dump.p;
         else if (stage == B200_STAGE_COSTAS)
-            src = (d.order ? d.bufA.p : d.bufB.p) + 16; // M&M input = Costas output after rotation fix-up (+ OQPSK delay)
+            src = (d.cfg.post_costas_dc ? d.pdc_out.p : (d.order ? d.bufA.p : d.bufB.p)) + 16; // M&M input = Costas output after rotation fix-up (+ post-Costas DC blocker / OQPSK delay)
         else if (stage == B200_STAGE_RESAMP && d.resamp)
             src = d.rs_out.p; // what entered the AGC: front-end resampler / iq_swap output
         else if (stage == B200_STAGE_DC && d.cfg.dc_block)

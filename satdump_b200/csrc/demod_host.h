@@ -18,6 +18,8 @@ struct DemodDevState
     float2 agc_tail[2][32];
     float2 rs_tail[2][RS_MAX_TAPS]; // resampler history (ntaps-1 converted input samples)
     float2 dc_acc[2];               // DC blocker accumulator (correct_iq.h: acc)
+    float2 dc_acc2[2];              // accumulator of the post-Costas DC blocker
+    float2 pdc_hist[2][8];          // its last 8 outputs: the clock recovery's history across batches
     float2 mm_hist[2][8];
     int flags;          // bit0 AGC clamp, bit1 M&M slot overflow
     int costas_unconv;  // junctions still unconverged after the repair rounds of the last batch
@@ -74,6 +76,7 @@ class Demod
     DevBuf<DcAff> dc_map;          // DC blocker: per-tile maps, per-tile accumulators, output (cf32)
     DevBuf<double2> dc_seeds;
     DevBuf<float2> dc_out;
+    DevBuf<float2> pdc_out;        // post-Costas DC blocker output (16-sample front pad like bufA / bufB)
     long last_front = 0;           // samples that entered the AGC in the last batch
     long last_in = 0;              // samples pushed in the last batch
     int agc_warm_max = 24;

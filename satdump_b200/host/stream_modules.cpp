@@ -147,7 +147,7 @@ b200_demod_cfg demod_cfg_from_params(const Params &p, bool &is_bpsk)
     c.dc_block = p.flag("dc_block", false); // module_demod_base.cpp:33-34,113-114
     reject(p, "freq_shift", "FreqShift block");
     c.iq_swap = p.flag("iq_swap", false); // module_demod_base.cpp:41-42 -> FileSourceBlock
-    reject(p, "post_costas_dc", "CorrectIQ block");
+    c.post_costas_dc = p.flag("post_costas_dc", false); // module_psk_demod.cpp:36-37,127-134
     reject(p, "has_carrier", "PLL carrier tracking");
     reject(p, "enable_doppler", "Doppler correction");
     // BaseDemodModule::initb (module_demod_base.cpp:59-87): outside [min_sps, max_sps] the front-end resampler converts to this rate

@@ -21,12 +21,12 @@ pytestmark = pytest.mark.gpu
 CONFIGS = ["metop_ahrpt", "bpsk_half", "jpss_hrd", "dvbs2_front", "hrpt_bpsk", "psk8"]
 
 
-def check_mm(gs, om, gsoft=None, osoft=None, big_soft=1e-4):
+def check_mm(gs, om, gsoft=None, osoft=None, big_soft=1e-4, dmax=5e-2):
     assert gs.size == om.size, (gs.size, om.size)
     d = np.abs(gs - om)
     frac = float((d <= 1e-5).mean())
     assert frac >= 0.97, frac
-    assert d.max() <= 5e-2, d.max()
+    assert d.max() <= dmax, d.max()
     if gsoft is not None:
         assert gsoft.size == osoft.size
         ds = np.abs(gsoft.astype(np.int16) - osoft.astype(np.int16))
@@ -234,6 +234,31 @@ def test_dc_block(built, name):
         parts.append(g2.stage("dc"))
         prev = c
     assert np.abs(np.concatenate(parts) - one).max() <= 1e-6
+
+
+def test_post_costas_dc(built):
+    """post_costas_dc: CorrectIQBlock between the Costas loop and the clock recovery (module_psk_demod.cpp:127-134; three shipped BPSK
+    pipelines). The clock recovery's input (stage "costas") and the symbols follow the reference, one shot and in ragged pushes."""
+    from satdump_b200 import capi
+    from tests.common import demod_kwargs
+    O = oracle()
+    cfg, raw, _ = signal("bpsk_half", 20)
+    n = nsamples(raw, cfg)
+    o = O.Demod(O.demod_cfg(post_costas_dc=True, **demod_kwargs(cfg))).run(raw)
+    g = capi.Demod(capi.demod_cfg(max_batch=n, keep_stages=True, post_costas_dc=True, **demod_kwargs(cfg))).push(raw)
+    d = np.abs(g.stage("costas") - o["costas"])
+    assert (d <= 1e-5).mean() >= 0.99999 and d.max() <= 2e-5, (float((d <= 1e-5).mean()), float(d.max()))
+    # measured: 0.92 % of the symbols off by >1e-5 (0.51 % without the block), max 6.7e-2 (4-5 interpolator arms), 1.6e-4 of the soft bytes off by >1
+    check_mm(g.symbols(), o["mm"], g.soft(), o["soft"], big_soft=3e-4, dmax=0.1)
+    g2 = capi.Demod(capi.demod_cfg(max_batch=n, keep_stages=True, post_costas_dc=True, **demod_kwargs(cfg)))
+    syms, prev = [], 0
+    for c in [100003, 600000, n]:
+        g2.push(raw[prev:c])
+        syms.append(g2.symbols())
+        prev = c
+    check_mm(np.concatenate(syms), o["mm"], dmax=0.1)
+    with pytest.raises(capi.B200Error):
+        capi.Demod(capi.demod_cfg(30e6, 15e6, "oqpsk", 0.5, post_costas_dc=True, max_batch=65536))
 
 
 def test_errors_are_loud(built):

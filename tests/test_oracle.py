@@ -101,7 +101,8 @@ def test_dc_block_port_equals_reference(built):
     ref = _ref()
     from oracle import port
     from tests.common import demod_kwargs
-    for name, kw in [("metop_ahrpt", dict(dc_block=True)), ("metop_ahrpt", dict(dc_block=True, iq_swap=True)), ("hrpt_bpsk", dict(dc_block=True))]:
+    for name, kw in [("metop_ahrpt", dict(dc_block=True)), ("metop_ahrpt", dict(dc_block=True, iq_swap=True)), ("hrpt_bpsk", dict(dc_block=True)),
+                     ("bpsk_half", dict(post_costas_dc=True)), ("metop_ahrpt", dict(dc_block=True, post_costas_dc=True))]:
         cfg, raw, _ = signal(name, 17, seed=4)
         raw = raw + np.complex64(0.02 + 0.01j) if cfg.fmt == "cf32" else raw + np.int16(300)
         a = ref.Demod(ref.demod_cfg(**kw, **demod_kwargs(cfg))).run(raw)
