@@ -25,11 +25,12 @@ ALG_BYTES_PER_CHUNK = 16384 + 12288 // 8  # Viterbi of one chunk: int8 soft in +
 
 
 def measured_traffic(kernel, log2n):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu --set full capture (same batch size only)."""
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu --set full capture (taken at 2^28 samples per
+    launch; these kernels' traffic is linear in the batch, so other batch sizes are scaled from it)."""
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_r1_traffic.json")) as f:
             t = json.load(f)
-        return t["dram_bytes_per_launch"][kernel] if t["batch_log2_samples"] == log2n else None
+        return int(t["dram_bytes_per_launch"][kernel] * 2.0 ** (log2n - t["batch_log2_samples"]))
     except Exception:
         return None
 
@@ -145,7 +146,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--log2-samples", dest="log2_samples", type=int, default=28)
+    ap.add_argument("--log2-samples", dest="log2_samples", type=int, default=29)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -311,7 +312,7 @@ def main():
                 "stage_ms_sync_step": {k: round(v, 4) for k, v in tim.items() if k != "vit_chunks"},
                 "roofline": {"kernel": "k_vit_acs (warp-per-chunk add-compare-select, the longest kernel of the step)", "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
                              "frac": achieved / hbm, "traffic": measured_traffic("k_vit_acs", args.log2_samples), "peak_source": which,
-                             "note": "timed alone (synchronous step); integer ACS kernel, issue/ALU bound (ncu: 85 % SM throughput, 2.7 % DRAM); its ncu DRAM traffic includes the 98 KB/chunk survivor decisions it hands to k_vit_tb"},
+                             "note": "timed alone (synchronous step); integer ACS kernel, issue/ALU bound (ncu: 85 % SM throughput, 2.7 % DRAM); its ncu DRAM traffic (captured at 2^28 samples, scaled to this batch) includes the 98 KB/chunk survivor decisions it hands to k_vit_tb"},
                 "roofline_fir_stage": {"kernels": "k_agc_fir (convert + AGC + 31-tap RRC in one pass; the exact-seed launches return at once)", "bound": "hbm",
                                        "achieved": n * 12 / (fir_ms * 1e-3) / 1e9 if fir_ms > 0 else 0.0, "peak": hbm, "unit": "GB/s",
                                        "frac": (n * 12 / (fir_ms * 1e-3) / 1e9 / hbm) if fir_ms > 0 else 0.0,
