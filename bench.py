@@ -137,10 +137,28 @@ def run_reference(args):
             "cpu_baseline": {"value": val, "unit": "MS/s", "cores": threads, "kind": "reference" if use_ref else "port",
                              "sample": f"2^{log2n} samples of the bench signal per step; reference threading model ({threads} threads, generic non-SIMD VOLK shim; host has {os.cpu_count()} cores)"},
             "e2e": {"value": val, "unit": "MS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """stdout carries exactly one JSON line: whatever libraries print at C level (NCCL's version banner, ...) goes to stderr."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + "\n").encode())
 
 
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -339,7 +357,7 @@ def main():
                                         "sample": f"first 2^25 samples of the bench signal, reference threading model ({threads} threads, generic VOLK shim); host has {os.cpu_count()} cores"}
             except Exception as ex:  # the oracle is test infrastructure: its absence must not break the product bench
                 line["cpu_baseline"] = {"value": None, "unit": "MS/s", "cores": 0, "kind": "unavailable", "sample": str(ex)[:200]}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
