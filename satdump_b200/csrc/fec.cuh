@@ -894,22 +894,46 @@ __global__ void __launch_bounds__(32) k_deframe(const uint32_t *__restrict__ fif
             continue;
         }
         if (S.state != 6) {
-            // SYNCED: 32 frames of lookahead, lane l tests the ASM expected l frames ahead
-            const long e = S.pos + (long)lane * cadu_size;
-            bool pass = false;
-            if (e < nbits) {
-                const uint32_t wv = fifo_window(fifo, e - 31);
-                pass = __popc(wv ^ (S.inversion ? ~sync : sync)) < st_synced;
+            // SYNCED: 128 frames of lookahead per iteration (4 independent loads per lane, so their latencies overlap); lane l tests
+            // the ASMs expected l, l+32, l+64, l+96 frames ahead. n = leading passes, m = how many of those are complete.
+            constexpr int G = 4;
+            unsigned pm[G], cm[G];
+            const uint32_t want = S.inversion ? ~sync : sync;
+#pragma unroll
+            for (int gq = 0; gq < G; gq++) {
+                const long e = S.pos + (long)(lane + 32 * gq) * cadu_size;
+                bool pass = false;
+                if (e < nbits)
+                    pass = __popc(fifo_window(fifo, e - 31) ^ want) < st_synced;
+                pm[gq] = __ballot_sync(0xffffffffu, pass);
+                cm[gq] = __ballot_sync(0xffffffffu, pass && (e + 1 + pay_bits <= nbits));
             }
-            const unsigned pm = __ballot_sync(0xffffffffu, pass);
-            const int n = (pm == 0xffffffffu) ? 32 : (__ffs(~pm) - 1);                 // leading passes
-            const unsigned cm = __ballot_sync(0xffffffffu, pass && (e + 1 + pay_bits <= nbits));
-            const int m = min(n, (cm == 0xffffffffu) ? 32 : (__ffs(~cm) - 1));          // of which complete
-            if (lane < m && nf + lane < max_frames) frames[nf + lane] = FrameRec{e + 1, S.inversion, 0};
+            int n = 0, m = 0;
+            bool nrun = true, mrun = true;
+#pragma unroll
+            for (int gq = 0; gq < G; gq++) {
+                if (nrun) {
+                    const int k = (pm[gq] == 0xffffffffu) ? 32 : (__ffs(~pm[gq]) - 1);
+                    n += k;
+                    nrun = k == 32;
+                }
+                if (mrun) {
+                    const int k = (cm[gq] == 0xffffffffu) ? 32 : (__ffs(~cm[gq]) - 1);
+                    m += k;
+                    mrun = k == 32;
+                }
+            }
+            m = min(m, n);
+#pragma unroll
+            for (int gq = 0; gq < G; gq++) {
+                const int f = lane + 32 * gq;
+                if (f < m && nf + f < max_frames)
+                    frames[nf + f] = FrameRec{S.pos + (long)f * cadu_size + 1, S.inversion, 0};
+            }
             nf += m;
             const long e_m = S.pos + (long)m * cadu_size;
             if (m < n) { S.frame_pay = e_m + 1; S.pos = e_m; break; }                   // accepted, payload still arriving
-            if (n == 32) { S.pos = e_m; continue; }
+            if (n == 32 * G) { S.pos = e_m; continue; }
             if (e_m >= nbits) { S.pos = e_m; break; }                                    // next ASM not here yet
             S.good = S.bad = 0; S.state = 2; S.pos = e_m + 1;                            // hard NOSYNC (bpsk_ccsds_deframer.cpp:98-102)
             note(e_m, 2);
