@@ -1,0 +1,44 @@
+"""CPU: the C++ host module layer's parameter handling (satdump_b200/host/stream_modules.cpp), through the b200_pipeline CLI. Parameters
+are validated before any device is touched, so the messages can be checked without a GPU; with valid parameters and no GPU the tool
+must stop with the library's ENODEV text — never decode on the host."""
+import os
+import subprocess
+
+import pytest
+
+from tests.common import ROOT
+
+TOOL = os.path.join(ROOT, "satdump_b200", "host", "b200_pipeline")
+BASE = ["--samplerate", "6e6", "--baseband_format", "cs16"]
+
+
+def run(pipe, extra, tmp_path):
+    inp = tmp_path / "in.cs16"
+    inp.write_bytes(b"\0" * 4096)
+    return subprocess.run([TOOL, pipe, "baseband", str(inp), str(tmp_path / "out")] + BASE + extra, capture_output=True, text=True, timeout=60)
+
+
+@pytest.mark.parametrize("pipe,extra,needle", [
+    ("metop_ahrpt", ["--freq_shift", "100"], "freq_shift"),                      # VOLK rotator: not reproducible in parallel
+    ("metop_ahrpt", ["--enable_doppler", "true"], "enable_doppler"),
+    ("metop_ahrpt", ["--has_carrier", "true"], "has_carrier"),
+    ("metop_ahrpt", ["--baseband_format", "cu8"], "baseband_format"),
+    ("metop_ahrpt", ["--samplerate", "1e6"], "sampling rate is too low"),         # module_demod_base.cpp:96-105
+    ("simple_qpsk", ["--symbolrate", "2400000", "--oqpsk_method2", "true"], "oqpsk_method2"),
+    ("simple_bpsk", ["--samplerate", "3e6", "--hard_symbols", "true"], "hard_symbols"),
+    ("simple_bpsk", ["--samplerate", "3e6", "--constellation", "8psk"], "invalid constellation"),
+    ("jpss_hrd", ["--samplerate", "50e6", "--conv_rate", "3/4"], "conv_rate"),
+])
+def test_unsupported_parameters_are_named(built, tmp_path, pipe, extra, needle):
+    r = run(pipe, extra, tmp_path)
+    assert r.returncode == 1 and needle.lower() in r.stderr.lower(), r.stderr
+
+
+def test_valid_parameters_reach_the_device_check(built, tmp_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    for pipe, extra in [("metop_ahrpt", []), ("metop_ahrpt", ["--samplerate", "12e6"]), ("metop_ahrpt", ["--dc_block", "true", "--iq_swap", "true"]),
+                        ("simple_bpsk", ["--samplerate", "3e6", "--post_costas_dc", "true"])]:
+        r = run(pipe, extra, tmp_path)
+        assert r.returncode == 1 and "no cpu fallback" in r.stderr.lower() and "cuda" in r.stderr.lower(), (pipe, extra, r.stderr)
