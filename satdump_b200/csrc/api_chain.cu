@@ -129,7 +129,7 @@ struct Chain
         }
         DeviceGuard g(d->cfg.device);
         const double omin = d->sps * (1.0 - d->cfg.clock_omega_limit) - 0.01;
-        const size_t cap = (size_t)(d->max_batch / omin + 1024) * d->bps;
+        const size_t cap = (size_t)(d->max_work / omin + 1024) * d->bps; // max_work: after an interpolating front-end resampler
         for (auto &s : stage)
             if (!s.p)
                 s.alloc(cap);
@@ -179,7 +179,8 @@ static void chain_push(Chain &c, const void *iq, long n, bool on_device)
     B200_CUDA(cudaEventRecord(c.e0, c.d->stream));
     // upper bound of the soft bytes this batch can produce
     const double omin = c.d->sps * (1.0 - c.d->cfg.clock_omega_limit) - 0.01;
-    const long bound = (long)(n / omin + 64) * c.d->bps;
+    const double front = c.d->resamp ? (double)n * c.d->rs_I / c.d->rs_D + 64 : (double)n; // samples after the front-end resampler
+    const long bound = (long)(front / omin + 64) * c.d->bps;
     if (c.pipelined) {
         B200_REQUIRE((size_t)bound <= c.stage[c.cur].n, B200_ESTATE, "internal: soft staging buffer too small");
         const long syms = on_device ? c.d->process(iq, n, c.stage[c.cur].p) : c.d->push_host(iq, n, c.stage[c.cur].p);
