@@ -21,6 +21,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+WORKLOAD = "METOP AHRPT QPSK + Viterbi r=3/4 + RS(255,223) I=4, cs16 @6 MS/s signal (BASELINE configs[2]), one stream per GPU"
 ALG_BYTES_PER_CHUNK = 16384 + 12288 // 8  # Viterbi of one chunk: int8 soft in + packed decoded bits out
 
 
@@ -132,8 +133,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "baseband MS/s end-to-end IQ->CADU (METOP AHRPT)", "value": val, "unit": "MS/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot / len(times) * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32+u8", "data": "synthetic",
-            "config": {"workload": "METOP AHRPT QPSK + Viterbi r=3/4 + RS(255,223) I=4, cs16 @6 MS/s signal, single stream",
-                       "samples_per_step": n, "cadus_per_step": frames},
+            "config": {"workload": WORKLOAD, "samples_per_step_per_gpu": n, "cadus_per_step_per_gpu": frames,
+                       "note": "bounded sample of the b200 arm's workload (same signal generator, stream of rank 0), one CPU stream"},
             "cpu_baseline": {"value": val, "unit": "MS/s", "cores": threads, "kind": "reference" if use_ref else "port",
                              "sample": f"2^{log2n} samples of the bench signal per step; reference threading model ({threads} threads, generic non-SIMD VOLK shim; host has {os.cpu_count()} cores)"},
             "e2e": {"value": val, "unit": "MS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -317,7 +318,7 @@ def main():
         line = {"metric": "baseband MS/s end-to-end IQ->CADU (METOP AHRPT)", "value": value, "unit": "MS/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": wall_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32+u8", "data": "synthetic",
-                "config": {"workload": "METOP AHRPT QPSK + Viterbi r=3/4 + RS(255,223) I=4, cs16 @6 MS/s signal (BASELINE configs[2]), one stream per GPU",
+                "config": {"workload": WORKLOAD,
                            "samples_per_step_per_gpu": n, "cadus_per_step_per_gpu": int(nfr), "cadus_bit_exact_vs_transmitted": bool(int(okt[0])),
                            "l2": "input batch (%.0f MiB) larger than L2" % (n * 4 / 2 ** 20), "esn0_db": cfg.esn0_db},
                 "e2e": {"value": e2e, "unit": "MS/s", "h2d_bytes_per_step": n * 4 * world, "d2h_bytes_per_step": int(nfr) * 1024 * world,

@@ -78,3 +78,25 @@ def test_product_never_touches_the_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp")) or fn == "Makefile":
                 txt = open(os.path.join(dp, fn), errors="ignore").read()
                 assert "liboracle" not in txt and "libsatref" not in txt and "from oracle" not in txt and "import oracle" not in txt, fn
+
+
+def test_bench_reference_arm_contract(built):
+    """`bench.py --impl reference` (the reference's own threaded CPU pipeline from oracle/_ref, or the port where the reference is
+    absent): exactly one JSON line on stdout with the contract's keys, same metric / unit / workload as the B200 arm."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--log2-samples", "22"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [x for x in r.stdout.splitlines() if x.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
+              "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["impl"] == "reference" and d["unit"] == "MS/s" and d["config"]["workload"] == bench.WORKLOAD and d["value"] > 0
+    assert d["e2e"] == {"value": d["value"], "unit": "MS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1 and d["config"]["cadus_per_step_per_gpu"] > 100
