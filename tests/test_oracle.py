@@ -179,3 +179,26 @@ def test_primitives_vs_reference(built):
     assert np.array_equal(ref.derand(np.zeros(1020, np.uint8)), port.derand(np.zeros(1020, np.uint8)))
     assert np.array_equal(ref.rrc_design(1, 6e6, 2333333, 0.5, 31), port.rrc_design(1, 6e6, 2333333, 0.5, 31))
     assert np.array_equal(ref.mm_taps(), port.mm_taps())
+
+
+def test_simple_psk_decoder_options_port_equals_reference(built):
+    """rs_i = 0, RS(255,239), derandomiser off / after RS, rs_usecheck, another ASM, 10232-bit CADUs with I = 5 — restatement vs reference."""
+    ref = _ref()
+    from oracle import port
+    rng = np.random.default_rng(9)
+    for kw in [dict(rs_i=0, derandomize=False), dict(rs_i=4, rs_type=1), dict(rs_i=4, derand_after_rs=True), dict(rs_i=4, rs_usecheck=True),
+               dict(rs_i=4, asm_sync=0xFAF3200D), dict(rs_i=5, cadu_size=10232), dict(rs_i=1, cadu_size=2072)]:
+        kw = dict(kw)
+        cadu_size = kw.pop("cadu_size", 8192)
+        body = rng.integers(0, 256, size=(12, cadu_size // 8 - 4), dtype=np.uint8)
+        asm = np.frombuffer(int(kw.get("asm_sync", 0x1ACFFC1D)).to_bytes(4, "big"), np.uint8)
+        bits = np.unpackbits(np.concatenate([np.tile(asm, (12, 1)), body], axis=1).reshape(-1))
+        soft = np.clip(np.round((bits * 2.0 - 1) * 60 + rng.normal(0, 15, bits.size)), -127, 127).astype(np.int8)
+        for con in ("bpsk", "qpsk"):
+            cfg = ref.simple_cfg(con, cadu_size, **kw)
+            fa, fb = ref.Fec(cfg), port.Fec(cfg)
+            n = soft.size // fa.chunk * fa.chunk
+            a, b = fa.run(soft[:n]), fb.run(soft[:n])
+            for k in ("cadu", "bits", "defr_state", "vit_state", "rs_err"):
+                assert np.array_equal(a[k], b[k]), (kw, con, k)
+        assert a["bits"].size == n
