@@ -202,3 +202,28 @@ def test_simple_psk_decoder_options_port_equals_reference(built):
             for k in ("cadu", "bits", "defr_state", "vit_state", "rs_err"):
                 assert np.array_equal(a[k], b[k]), (kw, con, k)
         assert a["bits"].size == n
+
+
+def test_resampler_port_equals_reference_over_rates_and_formats(built):
+    """The front-end resampler restatement vs the reference over decimating and interpolating ratios, every sample format, with and
+    without iq_swap / dc_block; ratios that need the power-of-two decimator are refused by the restatement (returns no handle)."""
+    ref = _ref()
+    from oracle import port
+    rng = np.random.default_rng(5)
+    cases = [(3e6, 665400, "bpsk"), (12e6, 2333333, "qpsk"), (2.6e6, 2.4e6, "qpsk"), (1.05e6, 1e6, "bpsk"), (7e6, 1.5e6, "qpsk"), (40e6, 15e6, "oqpsk"),
+             (10.5e6, 2.5e6, "qpsk")]
+    for fs, rs, con in cases:
+        for fmt in ("cs16", "cs8", "cf32"):
+            n = 40000
+            if fmt == "cf32":
+                raw = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64) * 0.3
+            else:
+                raw = (rng.standard_normal(2 * n) * (3000 if fmt == "cs16" else 30)).astype(np.int16 if fmt == "cs16" else np.int8)
+            for extra in (dict(), dict(iq_swap=True, dc_block=True)):
+                cfg = ref.demod_cfg(fs, rs, con, 0.5, fmt=fmt, **extra)
+                assert cfg.final_samplerate > 0 and cfg.samplerate / cfg.final_samplerate < 2, (fs, rs)
+                a, b = ref.resample(cfg, raw), port.resample(cfg, raw)
+                assert a.size == b.size and bitwise(a, b), (fs, rs, con, fmt, extra)
+    cfg = ref.demod_cfg(6e6, 233333, "qpsk", 0.5)  # 6 MS/s -> 0.8 MS/s: needs the decimator
+    assert cfg.samplerate / cfg.final_samplerate >= 2
+    assert not port.lib().ref_demod_create(cfg)
