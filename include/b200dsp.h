@@ -122,6 +122,10 @@ typedef struct b200_demod b200_demod;
  * samplerate/symbolrate lies inside [min_sps, max_sps] (psk_demod: 1.1..4.0, OQPSK 1.6..2.4; pass 0 for those defaults), else the
  * rate the reference's front-end resampler converts to. custom_samplerate > 0 overrides ("custom_samplerate"). */
 double b200_demod_final_samplerate(double samplerate, double symbolrate, int constellation, float min_sps, float max_sps, double custom_samplerate);
+/* The polyphase bank the front-end resampler uses for (samplerate -> final_samplerate): RationalResamplerBlock::set_ratio
+ * (resamp/rational_resampler.cpp:27-41) = firdes::design_resampler_filter_float + PolyphaseBank::init. Host-only (no device):
+ * out[arm * *ntaps + k], *interp arms, reduced ratio *interp / *decim. */
+int b200_demod_resampler_bank(double samplerate, double final_samplerate, float *out, long cap, int *ntaps, int *interp, int *decim);
 typedef struct b200_fec b200_fec;
 typedef struct b200_chain b200_chain;
 

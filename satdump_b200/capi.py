@@ -19,7 +19,7 @@ E_NAMES = {0: "OK", -1: "EINVAL", -2: "ENODEV", -3: "ECUDA", -4: "ENOMEM", -5: "
 
 # every symbol include/b200dsp.h declares (tests check the built library exports all of them)
 SYMBOLS = [
-    "b200_last_error", "b200_device_count", "b200_demod_final_samplerate",
+    "b200_last_error", "b200_device_count", "b200_demod_final_samplerate", "b200_demod_resampler_bank",
     "b200_demod_create", "b200_demod_destroy", "b200_demod_push_iq", "b200_demod_push_iq_device", "b200_demod_pull_soft",
     "b200_demod_pull_symbols", "b200_demod_debug_stage", "b200_demod_debug_convert", "b200_demod_get_stats", "b200_demod_get_taps",
     "b200_fec_create", "b200_fec_destroy", "b200_fec_push_soft", "b200_fec_push_soft_device", "b200_fec_pull_frames",
@@ -79,6 +79,7 @@ def lib():
         L.b200_demod_create.restype = vp
         L.b200_demod_final_samplerate.restype = C.c_double
         L.b200_demod_final_samplerate.argtypes = [C.c_double, C.c_double, ci, C.c_float, C.c_float, C.c_double]
+        L.b200_demod_resampler_bank.argtypes = [C.c_double, C.c_double, vp, cl, C.POINTER(ci), C.POINTER(ci), C.POINTER(ci)]
         L.b200_demod_create.argtypes = [C.POINTER(DemodCfg)]
         L.b200_demod_destroy.argtypes = [vp]
         L.b200_demod_push_iq.argtypes = [vp, vp, cl]
@@ -144,6 +145,14 @@ def demod_cfg(samplerate, symbolrate, constellation, rrc_alpha, pll_bw=0.003, fm
     return DemodCfg(float(samplerate), float(symbolrate), CONST[constellation], rrc_alpha, rrc_taps, pll_bw, agc_rate, clock_gain_omega,
                     clock_mu, clock_gain_mu, clock_omega_limit, costas_max_offset, FMT[fmt], device, max_batch, int(keep_stages), int(iq_swap),
                     float(final_samplerate), int(dc_block), int(post_costas_dc))
+
+
+def resampler_bank(samplerate, final_samplerate):
+    """Polyphase bank of the front-end resampler for (samplerate -> final_samplerate): array [arms, taps per arm], reduced (I, D)."""
+    out = np.zeros(1 << 20, np.float32)
+    nt, i, d = C.c_int(0), C.c_int(0), C.c_int(0)
+    _chk(lib().b200_demod_resampler_bank(float(samplerate), float(final_samplerate), out.ctypes.data, out.size, C.byref(nt), C.byref(i), C.byref(d)))
+    return out[:i.value * nt.value].reshape(i.value, nt.value).copy(), i.value, d.value
 
 
 def final_samplerate_of(samplerate, symbolrate, constellation, min_sps=0.0, max_sps=0.0, custom=0.0):

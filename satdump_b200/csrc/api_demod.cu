@@ -745,6 +745,25 @@ double b200_demod_final_samplerate(double samplerate, double symbolrate, int con
         final_samplerate = resample ? d_symbolrate * MIN_SPS : d_samplerate;
     return (double)final_samplerate;
 }
+int b200_demod_resampler_bank(double samplerate, double final_samplerate, float *out, long cap, int *ntaps, int *interp, int *decim)
+{
+    return guarded([&] {
+        B200_REQUIRE(out && ntaps && interp && decim, B200_EINVAL, "NULL argument");
+        // the same reduction as the constructor: SmartResamplerBlock(final, input) -> RationalResamplerBlock::set_ratio
+        const unsigned interpolation = (unsigned)(float)final_samplerate, decimation = (unsigned)(long)samplerate;
+        B200_REQUIRE(interpolation > 0 && decimation > 0, B200_EINVAL, "rates must be positive");
+        if (decimation > interpolation)
+            B200_REQUIRE((int)floor(log2((double)(decimation / interpolation))) <= 0, B200_EUNSUPPORTED, "ratio needs the power-of-two decimator");
+        const unsigned g = gcd_u(interpolation, decimation);
+        std::vector<float> bank;
+        const int nt = design_resampler_bank(interpolation / g, decimation / g, bank);
+        B200_REQUIRE((long)bank.size() <= cap, B200_ESTATE, "output buffer too small: need %zu floats", bank.size());
+        memcpy(out, bank.data(), bank.size() * sizeof(float));
+        *ntaps = nt;
+        *interp = (int)(interpolation / g);
+        *decim = (int)(decimation / g);
+    });
+}
 int b200_demod_debug_stage(b200_demod *h, int stage, float *out, long cap_samples)
 {
     return guarded([&] {

@@ -224,6 +224,13 @@ def test_resampler_port_equals_reference_over_rates_and_formats(built):
                 assert cfg.final_samplerate > 0 and cfg.samplerate / cfg.final_samplerate < 2, (fs, rs)
                 a, b = ref.resample(cfg, raw), port.resample(cfg, raw)
                 assert a.size == b.size and bitwise(a, b), (fs, rs, con, fmt, extra)
+    # the product's host-side design of the same banks (b200_demod_resampler_bank needs no device): bitwise
+    from satdump_b200 import capi
+    for fs, rs, con in cases:
+        fin = port.final_samplerate_of(fs, rs, con)
+        bank, i, d = capi.resampler_bank(fs, fin)
+        want = ref.resampler_taps(int(fin), int(fs))
+        assert bank.shape == want.shape and bitwise(bank, want), (fs, rs, i, d)
     cfg = ref.demod_cfg(6e6, 233333, "qpsk", 0.5)  # 6 MS/s -> 0.8 MS/s: needs the decimator
     assert cfg.samplerate / cfg.final_samplerate >= 2
     assert not port.lib().ref_demod_create(cfg)
