@@ -43,7 +43,10 @@ enum { B200_CF32 = 0, B200_CS16 = 1, B200_CS8 = 2 };
 /* decoder kind */
 enum { B200_FEC_METOP = 0, B200_FEC_CCSDS = 1, B200_FEC_SIMPLE = 2 };
 /* debug stage ids for b200_demod_debug_stage */
-enum { B200_STAGE_AGC = 0, B200_STAGE_FIR = 1, B200_STAGE_COSTAS = 2, B200_STAGE_RESAMP = 3, B200_STAGE_DC = 4 };
+enum { B200_STAGE_AGC = 0, B200_STAGE_FIR = 1, B200_STAGE_COSTAS = 2, B200_STAGE_RESAMP = 3, B200_STAGE_DC = 4, B200_STAGE_MM = 5 };
+/* mode bits of b200_demod_debug_run_stage */
+#define B200_DEBUG_STRICT 1     /* the reference's operation order: separate multiply and add, left to right (generic VOLK, no FMA) */
+#define B200_DEBUG_SEQUENTIAL 2 /* one segment: the feedback loop runs as ONE sequential thread from the initial state */
 
 typedef struct b200_demod_cfg
 {
@@ -145,6 +148,18 @@ int b200_demod_pull_soft(b200_demod *d, int8_t *host_out, long cap, long *n_out)
 int b200_demod_pull_symbols(b200_demod *d, float *host_out, long cap_symbols, long *n_out);
 /* stage outputs of the LAST push (needs keep_stages): nsamples complex values, interleaved re,im */
 int b200_demod_debug_stage(b200_demod *d, int stage, float *host_out, long cap_samples);
+/* Stage-isolated parity hook: runs ONE stage of a freshly reset demodulator on a caller-supplied stage input
+ * (nsamples complex values, interleaved re,im: normally the ORACLE's output of the stage before) and returns the stage output.
+ *   B200_STAGE_FIR     in = AGC output.  mode STRICT: fir.cpp:74-83 in the generic VOLK order -> bitwise the oracle's FIR output;
+ *                      mode 0: the production kernel (k_agc_fir with the AGC switched off), one fma per tap
+ *   B200_STAGE_COSTAS  in = FIR output; out = what the clock recovery reads (rotation fix-up, OQPSK delay, post_costas_dc applied)
+ *   B200_STAGE_MM      in = the clock recovery's input; out = symbols (*n_out of them). STRICT | SEQUENTIAL -> bitwise the oracle's
+ * SEQUENTIAL runs the loop as one segment (no warm-up, no stitching). The demodulator is reset before and after. */
+int b200_demod_debug_run_stage(b200_demod *d, int stage, const float *host_in, long nsamples, int mode, float *host_out, long cap_complex, long *n_out);
+/* Junction residuals of the LAST push / debug run: per segment s > 0 the Costas phase (mod 2pi/order) and frequency difference
+ * between segment s's warmed-up state at its first owned sample and segment s-1's end state (costas_out[2s], [2s+1]), and the M&M
+ * sampling-instant difference (mm_out[s], samples). Either pointer may be NULL. */
+int b200_demod_debug_junctions(b200_demod *d, double *costas_out, double *mm_out, long cap_segments, long *nseg_out, long *seg_len);
 /* test hook: only the sample conversion (BasebandReader::read_samples, baseband_interface.h:170-190) of `nsamples` host samples */
 int b200_demod_debug_convert(b200_demod *d, const void *host_iq, long nsamples, float *host_out);
 int b200_demod_get_stats(b200_demod *d, b200_demod_stats *out);

@@ -475,6 +475,42 @@ long orc_demod_run(void *h, const void *raw, long nsamples, float *agc_out, floa
     return nsym;
 }
 long orc_demod_last_front(void *h) { return ((orc_demod *)h)->last_front; }
+/* ONE stage of the chain on a caller-supplied cf32 input, in reference-sized buffers (stage-isolated parity tests): 1 = FIR,
+   2 = Costas loop (+ post-Costas DC blocker / OQPSK delay: what the clock recovery reads), 5 = M&M. Returns the output count. */
+long orc_demod_run_stage(void *h, int stage, const float *in, long nsamples, float *out, long cap)
+{
+    orc_demod *d = h;
+    long pos = 0;
+    if (stage == 2 && !d->order) return -1;
+    for (long off = 0; off < nsamples; off += d->buffer_size) {
+        int n = (int)(nsamples - off < d->buffer_size ? nsamples - off : d->buffer_size), m = n;
+        memcpy(d->w0, in + off * 2, n * sizeof(cf_t));
+        cf_t *res = d->w1;
+        if (stage == 1)
+            fir_run(d, d->w0, d->w1, n);
+        else if (stage == 2) {
+            costas_run(d, d->w0, d->w1, n);
+            if (d->cfg.post_costas_dc) {
+                const float alpha = 0.0001, beta = 1.0f - alpha;
+                for (int i = 0; i < n; i++) {
+                    d->dc_acc2.re = d->dc_acc2.re * beta + d->w1[i].re * alpha;
+                    d->dc_acc2.im = d->dc_acc2.im * beta + d->w1[i].im * alpha;
+                    d->w1[i].re = d->w1[i].re - d->dc_acc2.re;
+                    d->w1[i].im = d->w1[i].im - d->dc_acc2.im;
+                }
+            }
+            if (d->cfg.constellation == 2) delay_run(d, d->w1, n);
+        } else {
+            m = mm_run(d, d->w0, d->w2, n);
+            res = d->w2;
+        }
+        if (pos + m > cap) m = (int)(cap - pos);
+        memcpy(out + pos * 2, res, m * sizeof(cf_t));
+        pos += m;
+    }
+    return pos;
+}
+
 
 long orc_resample(const orc_demod_cfg *c, const void *raw, long nsamples, float *out, long cap)
 {

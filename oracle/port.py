@@ -29,6 +29,8 @@ def _lib():
         L.ref_demod_run.restype = C.c_long
         L.ref_demod_run.argtypes = [C.c_void_p, C.c_void_p, C.c_long] + [C.c_void_p] * 5 + [C.c_long]
         L.ref_demod_state.argtypes = [C.c_void_p, C.c_void_p]
+        L.ref_demod_run_stage.restype = C.c_long
+        L.ref_demod_run_stage.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_long, C.c_void_p, C.c_long]
         L.ref_demod_last_front.restype = C.c_long
         L.ref_demod_last_front.argtypes = [C.c_void_p]
         L.ref_resample.restype = C.c_long
@@ -67,6 +69,7 @@ DemodCfg, FecCfg = _m.DemodCfg, _m.FecCfg
 demod_cfg, metop_cfg, ccsds_cfg, simple_cfg = _m.demod_cfg, _m.metop_cfg, _m.ccsds_cfg, _m.simple_cfg
 final_samplerate_of, resample, resampler_taps = _m.final_samplerate_of, _m.resample, _m.resampler_taps
 Fec = _m.Fec
+run_stage = _m.run_stage
 rs_decode_interleaved, derand, cc_encode, cc_decode, rotate_soft, deframe = (
     _m.rs_decode_interleaved, _m.derand, _m.cc_encode, _m.cc_decode, _m.rotate_soft, _m.deframe)
 

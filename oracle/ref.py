@@ -69,6 +69,8 @@ def lib():
         L.ref_demod_run.restype = C.c_long
         L.ref_demod_run.argtypes = [C.c_void_p, C.c_void_p, C.c_long] + [C.c_void_p] * 5 + [C.c_long]
         L.ref_demod_state.argtypes = [C.c_void_p, C.c_void_p]
+        L.ref_demod_run_stage.restype = C.c_long
+        L.ref_demod_run_stage.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_long, C.c_void_p, C.c_long]
         L.ref_demod_last_front.restype = C.c_long
         L.ref_demod_last_front.argtypes = [C.c_void_p]
         L.ref_resample.restype = C.c_long
@@ -204,6 +206,17 @@ class Demod:
         front = lib().ref_demod_last_front(self.h)
         cut = (lambda a: None if a is None else a[:front])
         return dict(agc=cut(agc), fir=cut(fir), costas=cut(cos), mm=mm[:ns].copy(), soft=soft[:ns * bps].copy(), front=front)
+
+
+def run_stage(cfg, which, x):
+    """ONE block ("fir" / "costas" incl. post-Costas DC blocker and OQPSK delay / "mm") of a FRESH chain on the cf32 stage input x."""
+    x = np.ascontiguousarray(x, np.complex64)
+    d = Demod(cfg)
+    out = np.zeros(x.size + 64, np.complex64)
+    n = lib().ref_demod_run_stage(d.h, {"fir": 1, "costas": 2, "mm": 5}[which], _p(x), x.size, _p(out), out.size)
+    if n < 0:
+        raise RuntimeError("this configuration has no such stage")
+    return out[:n].copy()
 
 
 class Fec:

@@ -382,6 +382,57 @@ extern "C"
         return r.pfb.ntaps;
     }
 
+    /* ONE block of a fresh chain on a caller-supplied cf32 input, in reference-sized buffers: stage 1 = FIRBlock, 2 = CostasLoopBlock
+       (+ post-Costas CorrectIQBlock / DelayOneImagBlock: what the clock recovery reads), 5 = MMClockRecoveryBlock. The input is written
+       straight into the stream the block reads. Returns the number of complex outputs (<= cap). */
+    long ref_demod_run_stage(void *h, int stage, const float *in, long nsamples, float *out, long cap)
+    {
+        RefDemod *d = (RefDemod *)h;
+        long pos = 0;
+        for (long off = 0; off < nsamples; off += d->buffer_size)
+        {
+            int n = (int)std::min<long>(d->buffer_size, nsamples - off);
+            std::shared_ptr<dsp::stream<complex_t>> src = stage == 1 ? d->agc->output_stream : (stage == 2 ? d->rrc->output_stream : d->rec->input_stream);
+            memcpy(src->writeBuf, in + off * 2, n * sizeof(complex_t));
+            src->swap(n);
+            std::shared_ptr<dsp::stream<complex_t>> dst;
+            if (stage == 1)
+            {
+                d->rrc->work();
+                dst = d->rrc->output_stream;
+            }
+            else if (stage == 2)
+            {
+                if (!d->pll)
+                    return -1;
+                d->pll->work();
+                dst = d->pll->output_stream;
+                if (d->post_pll_dc)
+                {
+                    d->post_pll_dc->work();
+                    dst = d->post_pll_dc->output_stream;
+                }
+                if (d->delay)
+                {
+                    d->delay->work();
+                    dst = d->delay->output_stream;
+                }
+            }
+            else
+            {
+                d->rec->work();
+                dst = d->rec->output_stream;
+            }
+            int m = dst->getDataSize();
+            if (pos + m > cap)
+                m = (int)(cap - pos);
+            memcpy(out + pos * 2, dst->readBuf, m * sizeof(complex_t));
+            dst->flush();
+            pos += m;
+        }
+        return pos;
+    }
+
     /* Carried loop state, for stage-isolated tests */
     void ref_demod_state(void *h, float *out8)
     {

@@ -21,7 +21,7 @@ E_NAMES = {0: "OK", -1: "EINVAL", -2: "ENODEV", -3: "ECUDA", -4: "ENOMEM", -5: "
 SYMBOLS = [
     "b200_last_error", "b200_device_count", "b200_demod_final_samplerate", "b200_demod_resampler_bank",
     "b200_demod_create", "b200_demod_destroy", "b200_demod_push_iq", "b200_demod_push_iq_device", "b200_demod_pull_soft",
-    "b200_demod_pull_symbols", "b200_demod_debug_stage", "b200_demod_debug_convert", "b200_demod_get_stats", "b200_demod_get_taps",
+    "b200_demod_pull_symbols", "b200_demod_debug_stage", "b200_demod_debug_convert", "b200_demod_debug_run_stage", "b200_demod_debug_junctions", "b200_demod_get_stats", "b200_demod_get_taps",
     "b200_fec_create", "b200_fec_destroy", "b200_fec_push_soft", "b200_fec_push_soft_device", "b200_fec_pull_frames",
     "b200_fec_debug_bits", "b200_fec_get_stats", "b200_fec_cadu_bytes", "b200_fec_chunk_size",
     "b200_chain_create", "b200_chain_destroy", "b200_chain_push_iq", "b200_chain_push_iq_device", "b200_chain_prefetch_iq", "b200_chain_pull_frames",
@@ -88,6 +88,8 @@ def lib():
         L.b200_demod_pull_symbols.argtypes = [vp, vp, cl, C.POINTER(cl)]
         L.b200_demod_debug_stage.argtypes = [vp, ci, vp, cl]
         L.b200_demod_debug_convert.argtypes = [vp, vp, cl, vp]
+        L.b200_demod_debug_run_stage.argtypes = [vp, ci, vp, cl, ci, vp, cl, C.POINTER(cl)]
+        L.b200_demod_debug_junctions.argtypes = [vp, vp, vp, cl, C.POINTER(cl), C.POINTER(cl)]
         L.b200_demod_get_stats.argtypes = [vp, C.POINTER(DemodStats)]
         L.b200_demod_get_taps.argtypes = [vp, vp, ci, vp]
         L.b200_fec_create.restype = vp
@@ -240,6 +242,23 @@ class Demod:
         out = np.zeros(n, np.complex64)
         _chk(lib().b200_demod_debug_stage(self.h, {"agc": 0, "fir": 1, "costas": 2, "resamp": 3, "dc": 4}[which], out.ctypes.data, n))
         return out
+
+    def run_stage(self, which, x, strict=False, sequential=False):
+        """Stage-isolated parity hook: ONE stage ("fir" / "costas" / "mm") of a freshly reset demodulator on the cf32 stage input x."""
+        x = np.ascontiguousarray(x, np.complex64)
+        out = np.zeros(x.size + 1024, np.complex64)
+        n = C.c_long(0)
+        _chk(lib().b200_demod_debug_run_stage(self.h, {"fir": 1, "costas": 2, "mm": 5}[which], x.ctypes.data, x.size,
+                                              (1 if strict else 0) | (2 if sequential else 0), out.ctypes.data, out.size, C.byref(n)))
+        return out[:n.value].copy()
+
+    def junctions(self):
+        """Junction residuals of the last push / run_stage: (costas [nseg, 2] phase / frequency, mm [nseg] sampling instant, segment length)."""
+        cap = 1 << 22
+        c, m = np.zeros(2 * cap), np.zeros(cap)
+        ns, L = C.c_long(0), C.c_long(0)
+        _chk(lib().b200_demod_debug_junctions(self.h, c.ctypes.data, m.ctypes.data, cap, C.byref(ns), C.byref(L)))
+        return c[:2 * ns.value].reshape(-1, 2).copy(), m[:ns.value].copy(), L.value
 
     def convert(self, raw):
         raw, n = _nsamples(raw, self.cfg.format)

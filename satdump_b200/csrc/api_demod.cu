@@ -175,7 +175,6 @@ static int repair_rounds()
     return v;
 }
 #define REPAIR_ROUNDS repair_rounds()
-constexpr float MM_TOL = 0.05f;    // samples: junction disagreement of the sampling instant that triggers a repair
 
 
 Demod::Demod(const b200_demod_cfg &c) : cfg(c)
@@ -244,6 +243,13 @@ Demod::Demod(const b200_demod_cfg &c) : cfg(c)
     }
     if (const char *e = getenv("B200_MM_WARMUP_SCALE")) // tuning hook
         Wm = round_up16(Wm * atof(e));
+    // junction tolerances (a junction outside them is repaired = re-run as the exact sequential continuation); tuning hooks
+    if (const char *e = getenv("B200_COSTAS_TOL"))
+        tol_cphase = (float)atof(e);
+    if (const char *e = getenv("B200_COSTAS_FTOL"))
+        tol_cfreq = (float)atof(e);
+    if (const char *e = getenv("B200_MM_TOL"))
+        tol_mm = (float)atof(e);
     int dev_sms = 148;
     cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, c.device);
     seg_cap_threads = dev_sms * 3 * SEG_THREADS;
@@ -337,7 +343,8 @@ Demod::Demod(const b200_demod_cfg &c) : cfg(c)
     B200_CUDA(cudaMemcpyAsync(st.p, h_state, sizeof(DemodDevState), cudaMemcpyHostToDevice, stream));
     bufA.zero(stream);
     bufB.zero(stream);
-    B200_CUDA(cudaFuncSetAttribute(k_mm, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM_BYTES));
+    B200_CUDA(cudaFuncSetAttribute(k_mm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM_BYTES));
+    B200_CUDA(cudaFuncSetAttribute(k_mm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM_BYTES));
     B200_CUDA(cudaFuncSetAttribute(k_costas, cudaFuncAttributeMaxDynamicSharedMemorySize, COSTAS_SMEM_BYTES));
     B200_CUDA(cudaStreamSynchronize(stream));
 }
@@ -424,6 +431,90 @@ template <int FMT> static void launch_front(Demod &d, const void *raw, long n, i
     d.launches += 4;
 }
 
+// Costas loop (+ junction fix-up and repair rounds) over the FIR output in bufA, exact rotation / OQPSK delay / optional DC blocker
+// into the clock recovery's input buffer (16-sample front pad: [8, 16) = the previous batch's last 8 inputs). Returns that buffer.
+float2 *Demod::stage_costas(long n, int L, int nseg, int cur, int nxt)
+{
+    DemodDevState *S = st.p;
+    float2 *fir_out = bufA.p + 16, *cos_out = bufB.p + 16;
+    const int nblk = (nseg + SEG_THREADS - 1) / SEG_THREADS;
+    last_L = L;
+    last_nseg = nseg;
+    float2 *mmin;
+    if (order) {
+        CostasParams P;
+        P.order = order;
+        { // costas_loop.cpp:5-12
+            float damping = sqrtf(2.0f) / 2.0f;
+            float denom = (float)(1.0 + 2.0 * damping * cfg.pll_bw + cfg.pll_bw * cfg.pll_bw);
+            P.alpha = (4 * damping * cfg.pll_bw) / denom;
+            P.beta = (4 * cfg.pll_bw * cfg.pll_bw) / denom;
+        }
+        P.fmin = -cfg.costas_max_offset;
+        P.fmax = cfg.costas_max_offset;
+        k_costas<<<nblk, SEG_THREADS, COSTAS_SMEM_BYTES, stream>>>(fir_out, n, L, Wc, nseg, P, S->costas[cur], cos_out, crec.p, nullptr, nullptr);
+        k_costas_fix<<<1, 1024, 0, stream>>>(crec.p, nseg, order, tol_cphase, tol_cfreq, quad.p, S->costas[nxt], &S->costas_unconv, repair.p + 1, repair.p, 0,
+                                             &S->repairs);
+        for (int round = 1; round <= REPAIR_ROUNDS; round++) { // both kernels return at once when no junction is flagged
+            k_costas<<<8, SEG_THREADS, COSTAS_SMEM_BYTES, stream>>>(fir_out, n, L, Wc, nseg, P, S->costas[cur], cos_out, crec.p, repair.p + 1, repair.p);
+            k_costas_fix<<<1, 1024, 0, stream>>>(crec.p, nseg, order, tol_cphase, tol_cfreq, quad.p, S->costas[nxt], &S->costas_unconv, repair.p + 1, repair.p,
+                                                 round, &S->repairs);
+            launches += 2;
+        }
+        mmin = bufA.p; // FIR output is dead now: reuse its buffer (in place compatible: same index mapping)
+        k_rotate<<<2048, 256, 0, stream>>>(cos_out, n, L, order, cfg.constellation == B200_OQPSK, quad.p, S->mm_hist[cur], S->mm_hist[nxt], mmin);
+        launches += 3;
+        if (cfg.post_costas_dc) {
+            // CorrectIQBlock on the loop's output (module_psk_demod.cpp:127-134); the clock recovery's 8-sample history are ITS outputs
+            const int nt = (int)((n + FIR_TILE - 1) / FIR_TILE);
+            const float alpha = 0.0001f, beta = 1.0f - alpha;
+            k_dc_tile<0><<<nt, FIR_THREADS, 0, stream>>>(mmin + 16, n, 0, alpha, beta, dc_map.p);
+            k_dc_scan<<<1, 1024, 0, stream>>>(dc_map.p, nt, &S->dc_acc2[cur], dc_seeds.p);
+            k_dc_apply<0><<<nt, FIR_THREADS, 0, stream>>>(mmin + 16, n, 0, alpha, beta, dc_seeds.p, pdc_out.p + 16, &S->dc_acc2[nxt]);
+            B200_CUDA(cudaMemcpyAsync(pdc_out.p + 8, S->pdc_hist[cur], 8 * sizeof(float2), cudaMemcpyDeviceToDevice, stream));
+            B200_CUDA(cudaMemcpyAsync(S->pdc_hist[nxt], pdc_out.p + 16 + n - 8, 8 * sizeof(float2), cudaMemcpyDeviceToDevice, stream));
+            launches += 3;
+            mmin = pdc_out.p;
+        }
+    } else {
+        mmin = bufB.p;
+        k_rotate<<<2048, 256, 0, stream>>>(fir_out, n, L, 0, 0, quad.p, S->mm_hist[cur], S->mm_hist[nxt], mmin);
+        launches += 1;
+    }
+    return mmin;
+}
+
+// M&M clock recovery over mmin (+ stitching, repair rounds, compaction and the int8 quantiser). `strict`: test hook, see k_mm.
+void Demod::stage_mm(float2 *mmin, long n, int L, int nseg, int cur, int nxt, int8_t *sdst, bool strict)
+{
+    DemodDevState *S = st.p;
+    const int nblk = (nseg + SEG_THREADS - 1) / SEG_THREADS;
+#define B200_MM_LAUNCH(grid, ...)                                                                                                           \
+    do {                                                                                                                                    \
+        if (strict)                                                                                                                         \
+            k_mm<true><<<grid, SEG_THREADS, MM_SMEM_BYTES, stream>>>(__VA_ARGS__);                                                           \
+        else                                                                                                                                \
+            k_mm<false><<<grid, SEG_THREADS, MM_SMEM_BYTES, stream>>>(__VA_ARGS__);                                                          \
+    } while (0)
+    MMParams MP;
+    MP.omega_mid = sps;
+    MP.omega_limit = cfg.clock_omega_limit * sps;
+    MP.omega_gain = cfg.clock_gain_omega;
+    MP.mu_gain = cfg.clock_gain_mu;
+    const int cap = slot_cap_for(L);
+    B200_REQUIRE((size_t)nseg * cap <= slots.n, B200_ENOMEM, "internal: symbol slot storage too small");
+    B200_MM_LAUNCH(nblk, mmin, n, L, Wm, nseg, MP, &S->mm[cur], &S->mm[nxt], d_bank.p, slots.p, cap, mrec.p, nullptr, nullptr);
+    k_mm_scan<<<1, 1024, 0, stream>>>(mrec.p, nseg, tol_mm, offs.p, &S->mm_unconv, cap, &S->flags, repair.p + 1, repair.p, 0, &S->repairs);
+    for (int round = 1; round <= REPAIR_ROUNDS; round++) {
+        B200_MM_LAUNCH(8, mmin, n, L, Wm, nseg, MP, &S->mm[cur], &S->mm[nxt], d_bank.p, slots.p, cap, mrec.p, repair.p + 1, repair.p);
+        k_mm_scan<<<1, 1024, 0, stream>>>(mrec.p, nseg, tol_mm, offs.p, &S->mm_unconv, cap, &S->flags, repair.p + 1, repair.p, round, &S->repairs);
+        launches += 2;
+    }
+    k_mm_compact<<<std::min(nseg, 148 * 8), 256, 0, stream>>>(slots.p, cap, mrec.p, offs.p, nseg, bps == 1, sym_out.p, sdst);
+    launches += 3;
+#undef B200_MM_LAUNCH
+}
+
 long Demod::process(const void *d_raw, long n, int8_t *soft_dst)
 {
     B200_REQUIRE(n >= 64, B200_ESTATE, "a batch needs at least 64 samples (got %ld)", n);
@@ -500,66 +591,9 @@ long Demod::process(const void *d_raw, long n, int8_t *soft_dst)
 
     const int L = choose_L(n);
     const int nseg = (int)((n + L - 1) / L);
-    const int nblk = (nseg + SEG_THREADS - 1) / SEG_THREADS;
-    float2 *mmin;
-    if (order) {
-        CostasParams P;
-        P.order = order;
-        { // costas_loop.cpp:5-12
-            float damping = sqrtf(2.0f) / 2.0f;
-            float denom = (float)(1.0 + 2.0 * damping * cfg.pll_bw + cfg.pll_bw * cfg.pll_bw);
-            P.alpha = (4 * damping * cfg.pll_bw) / denom;
-            P.beta = (4 * cfg.pll_bw * cfg.pll_bw) / denom;
-        }
-        P.fmin = -cfg.costas_max_offset;
-        P.fmax = cfg.costas_max_offset;
-        k_costas<<<nblk, SEG_THREADS, COSTAS_SMEM_BYTES, stream>>>(fir_out, n, L, Wc, nseg, P, S->costas[cur], cos_out, crec.p, nullptr, nullptr);
-        k_costas_fix<<<1, 1024, 0, stream>>>(crec.p, nseg, order, 2e-3f, 1e-4f, quad.p, S->costas[nxt], &S->costas_unconv, repair.p + 1, repair.p, 0,
-                                             &S->repairs);
-        for (int round = 1; round <= REPAIR_ROUNDS; round++) { // both kernels return at once when no junction is flagged
-            k_costas<<<8, SEG_THREADS, COSTAS_SMEM_BYTES, stream>>>(fir_out, n, L, Wc, nseg, P, S->costas[cur], cos_out, crec.p, repair.p + 1, repair.p);
-            k_costas_fix<<<1, 1024, 0, stream>>>(crec.p, nseg, order, 2e-3f, 1e-4f, quad.p, S->costas[nxt], &S->costas_unconv, repair.p + 1, repair.p,
-                                                 round, &S->repairs);
-            launches += 2;
-        }
-        mmin = bufA.p; // FIR output is dead now: reuse its buffer (in place compatible: same index mapping)
-        k_rotate<<<2048, 256, 0, stream>>>(cos_out, n, L, order, cfg.constellation == B200_OQPSK, quad.p, S->mm_hist[cur], S->mm_hist[nxt], mmin);
-        launches += 3;
-        if (cfg.post_costas_dc) {
-            // CorrectIQBlock on the loop's output (module_psk_demod.cpp:127-134); the clock recovery's 8-sample history are ITS outputs
-            const int nt = (int)((n + FIR_TILE - 1) / FIR_TILE);
-            const float alpha = 0.0001f, beta = 1.0f - alpha;
-            k_dc_tile<0><<<nt, FIR_THREADS, 0, stream>>>(mmin + 16, n, 0, alpha, beta, dc_map.p);
-            k_dc_scan<<<1, 1024, 0, stream>>>(dc_map.p, nt, &S->dc_acc2[cur], dc_seeds.p);
-            k_dc_apply<0><<<nt, FIR_THREADS, 0, stream>>>(mmin + 16, n, 0, alpha, beta, dc_seeds.p, pdc_out.p + 16, &S->dc_acc2[nxt]);
-            B200_CUDA(cudaMemcpyAsync(pdc_out.p + 8, S->pdc_hist[cur], 8 * sizeof(float2), cudaMemcpyDeviceToDevice, stream));
-            B200_CUDA(cudaMemcpyAsync(S->pdc_hist[nxt], pdc_out.p + 16 + n - 8, 8 * sizeof(float2), cudaMemcpyDeviceToDevice, stream));
-            launches += 3;
-            mmin = pdc_out.p;
-        }
-    } else {
-        mmin = bufB.p;
-        k_rotate<<<2048, 256, 0, stream>>>(fir_out, n, L, 0, 0, quad.p, S->mm_hist[cur], S->mm_hist[nxt], mmin);
-        launches += 1;
-    }
+    float2 *mmin = stage_costas(n, L, nseg, cur, nxt);
     B200_CUDA(cudaEventRecord(ev[2], stream));
-    MMParams MP;
-    MP.omega_mid = sps;
-    MP.omega_limit = cfg.clock_omega_limit * sps;
-    MP.omega_gain = cfg.clock_gain_omega;
-    MP.mu_gain = cfg.clock_gain_mu;
-    const int cap = slot_cap_for(L);
-    B200_REQUIRE((size_t)nseg * cap <= slots.n, B200_ENOMEM, "internal: symbol slot storage too small");
-    k_mm<<<nblk, SEG_THREADS, MM_SMEM_BYTES, stream>>>(mmin, n, L, Wm, nseg, MP, &S->mm[cur], &S->mm[nxt], d_bank.p, slots.p, cap, mrec.p, nullptr, nullptr);
-    k_mm_scan<<<1, 1024, 0, stream>>>(mrec.p, nseg, MM_TOL, offs.p, &S->mm_unconv, cap, &S->flags, repair.p + 1, repair.p, 0, &S->repairs);
-    for (int round = 1; round <= REPAIR_ROUNDS; round++) {
-        k_mm<<<8, SEG_THREADS, MM_SMEM_BYTES, stream>>>(mmin, n, L, Wm, nseg, MP, &S->mm[cur], &S->mm[nxt], d_bank.p, slots.p, cap, mrec.p, repair.p + 1, repair.p);
-        k_mm_scan<<<1, 1024, 0, stream>>>(mrec.p, nseg, MM_TOL, offs.p, &S->mm_unconv, cap, &S->flags, repair.p + 1, repair.p, round, &S->repairs);
-        launches += 2;
-    }
-    int8_t *sdst = soft_dst ? soft_dst : soft.p;
-    k_mm_compact<<<std::min(nseg, 148 * 8), 256, 0, stream>>>(slots.p, cap, mrec.p, offs.p, nseg, bps == 1, sym_out.p, sdst);
-    launches += 3;
+    stage_mm(mmin, n, L, nseg, cur, nxt, soft_dst ? soft_dst : soft.p, false);
     B200_CUDA(cudaEventRecord(ev[3], stream));
     B200_CUDA(cudaMemcpyAsync(h_total, offs.p + nseg, sizeof(long), cudaMemcpyDeviceToHost, stream));
     B200_CUDA(cudaMemcpyAsync(h_state, st.p, sizeof(DemodDevState), cudaMemcpyDeviceToHost, stream));
@@ -578,6 +612,65 @@ long Demod::process(const void *d_raw, long n, int8_t *soft_dst)
     if (h_state->flags & 2)
         throw ApiError(B200_EUNSUPPORTED, "M&M produced more symbols per segment than the omega limit allows (slot overflow)");
     return last_syms;
+}
+
+// Test hook behind b200_demod_debug_run_stage: ONE stage of a freshly reset demodulator on a caller-supplied cf32 stage input.
+long Demod::debug_run_stage(int stage, const float *h_in, long n, int mode, float *h_out, long cap)
+{
+    B200_REQUIRE(n >= 64 && n <= max_work, B200_ESTATE, "stage input of %ld samples outside [64, %ld]", n, max_work);
+    B200_REQUIRE(stage == B200_STAGE_FIR || stage == B200_STAGE_COSTAS || stage == B200_STAGE_MM, B200_EINVAL, "stage %d cannot be run alone", stage);
+    DeviceGuard g(cfg.device);
+    reset();
+    const bool strict = mode & B200_DEBUG_STRICT, seq = mode & B200_DEBUG_SEQUENTIAL;
+    const int L = seq ? (int)((n + 15) / 16 * 16) : choose_L(n);
+    const int nseg = (int)((n + L - 1) / L);
+    DemodDevState *S = st.p;
+    long count = n;
+    const float2 *src = nullptr;
+    if (stage == B200_STAGE_FIR) {
+        FirTaps taps;
+        memset(&taps, 0, sizeof(taps));
+        for (int i = 0; i < FIR_NT; i++)
+            taps.h[i] = rrc[i];
+        B200_CUDA(cudaMemcpyAsync(bufB.p + 16, h_in, n * sizeof(float2), cudaMemcpyHostToDevice, stream));
+        if (strict)
+            k_fir_only<true><<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(bufB.p + 16, n, taps, bufA.p + 16);
+        else {
+            // the production kernel with the AGC switched off: rate 0 makes every step map the identity and the gain stay 1, so
+            // k_agc_fir's output is the FFMA2 FIR of its input (the ranges take the scanned-seed pass: nothing proves a seed at rate 0)
+            const float rate = cfg.agc_rate;
+            cfg.agc_rate = 0.f;
+            launch_front<0>(*this, bufB.p + 16, n, (int)((n + FIR_TILE - 1) / FIR_TILE), taps, 0, false);
+            cfg.agc_rate = rate;
+        }
+        src = bufA.p + 16;
+    } else if (stage == B200_STAGE_COSTAS) {
+        B200_REQUIRE(order != 0, B200_EINVAL, "this configuration has no Costas loop");
+        B200_CUDA(cudaMemcpyAsync(bufA.p + 16, h_in, n * sizeof(float2), cudaMemcpyHostToDevice, stream));
+        src = stage_costas(n, L, nseg, 0, 1) + 16;
+    } else {
+        float2 *mmin = order ? bufA.p : bufB.p;
+        B200_CUDA(cudaMemsetAsync(mmin, 0, 16 * sizeof(float2), stream)); // history of a new stream
+        B200_CUDA(cudaMemcpyAsync(mmin + 16, h_in, n * sizeof(float2), cudaMemcpyHostToDevice, stream));
+        last_L = L;
+        last_nseg = nseg;
+        stage_mm(mmin, n, L, nseg, 0, 1, soft.p, strict);
+        B200_CUDA(cudaMemcpyAsync(h_total, offs.p + nseg, sizeof(long), cudaMemcpyDeviceToHost, stream));
+        B200_CUDA(cudaStreamSynchronize(stream));
+        count = *h_total;
+        src = sym_out.p;
+    }
+    B200_REQUIRE(count <= cap, B200_ESTATE, "output buffer too small: need %ld complex values", count);
+    B200_CUDA(cudaMemcpyAsync(h_out, src, count * sizeof(float2), cudaMemcpyDeviceToHost, stream));
+    B200_CUDA(cudaMemcpyAsync(h_state, S, sizeof(DemodDevState), cudaMemcpyDeviceToHost, stream));
+    B200_CUDA(cudaStreamSynchronize(stream));
+    B200_CUDA(cudaGetLastError());
+    dbg_costas_unconv = h_state->costas_unconv;
+    dbg_mm_unconv = h_state->mm_unconv;
+    dbg_repairs = h_state->repairs;
+    last_syms = stage == B200_STAGE_MM ? count : 0;
+    reset();
+    return count;
 }
 
 void Demod::prefetch_host(const void *h_raw, long n)
@@ -808,6 +901,48 @@ int b200_demod_debug_convert(b200_demod *h, const void *host_iq, long n, float *
             k_convert_only<2><<<blocks, 256, 0, d.stream>>>(d.raw.p, n, out);
         B200_CUDA(cudaMemcpyAsync(host_out, out, n * sizeof(float2), cudaMemcpyDeviceToHost, d.stream));
         B200_CUDA(cudaStreamSynchronize(d.stream));
+    });
+}
+int b200_demod_debug_run_stage(b200_demod *h, int stage, const float *host_in, long n, int mode, float *host_out, long cap, long *n_out)
+{
+    return guarded([&] {
+        B200_REQUIRE(h && host_in && host_out && n_out, B200_EINVAL, "NULL argument");
+        *n_out = h->d->debug_run_stage(stage, host_in, n, mode, host_out, cap);
+    });
+}
+int b200_demod_debug_junctions(b200_demod *h, double *costas_out, double *mm_out, long cap_segments, long *nseg_out, long *seg_len)
+{
+    return guarded([&] {
+        B200_REQUIRE(h && nseg_out && seg_len, B200_EINVAL, "NULL argument");
+        Demod &d = *h->d;
+        const long ns = d.last_nseg;
+        B200_REQUIRE(ns <= cap_segments, B200_ESTATE, "output buffers too small: %ld segments", ns);
+        DeviceGuard g(d.cfg.device);
+        std::vector<LoopRec> cr(ns);
+        std::vector<MMRec> mr(ns);
+        B200_CUDA(cudaMemcpyAsync(cr.data(), d.crec.p, ns * sizeof(LoopRec), cudaMemcpyDeviceToHost, d.stream));
+        B200_CUDA(cudaMemcpyAsync(mr.data(), d.mrec.p, ns * sizeof(MMRec), cudaMemcpyDeviceToHost, d.stream));
+        B200_CUDA(cudaStreamSynchronize(d.stream));
+        for (long s = 0; s < ns; s++) {
+            if (costas_out) {
+                costas_out[2 * s] = costas_out[2 * s + 1] = 0;
+                if (s > 0 && d.order) {
+                    const double step = 6.283185307179586 / d.order, dp = (double)cr[s].ph_start - (double)cr[s - 1].ph_end;
+                    costas_out[2 * s] = dp - std::nearbyint(dp / step) * step;
+                    costas_out[2 * s + 1] = (double)cr[s].fr_start - (double)cr[s - 1].fr_end;
+                }
+            }
+            if (mm_out) {
+                mm_out[s] = 0;
+                if (s > 0) {
+                    const double tref = (double)mr[s - 1].u_final + (double)mr[s - 1].mu_final;
+                    const int sk = std::min(std::max(mr[s].skip, 0), 3);
+                    mm_out[s] = ((double)mr[s].head_u[sk] + (double)mr[s].head_mu[sk]) - tref;
+                }
+            }
+        }
+        *nseg_out = ns;
+        *seg_len = d.last_L;
     });
 }
 int b200_demod_get_stats(b200_demod *h, b200_demod_stats *out)

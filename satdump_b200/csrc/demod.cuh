@@ -776,6 +776,33 @@ __global__ void __launch_bounds__(1024) k_agc_scan(const Affine *__restrict__ ti
         seeds[ntiles] = g_run;
 }
 
+// ---------------------------------------------------------------- test hook: the FIR alone (b200_demod_debug_run_stage)
+// y[i] = sum_j x[i-30+j] * h[30-j] over a cf32 stream with zero history, oldest sample first (fir.cpp:74-83). STRICT evaluates it
+// the way the generic VOLK dot product the oracle is built with does (separate multiply and add, left to right), so that fed the
+// oracle's own AGC output the result must be BITWISE the oracle's FIR output; !STRICT uses one fma per tap in the same order, i.e.
+// the arithmetic of k_agc_fir's FFMA2 loop.
+template <bool STRICT> __global__ void __launch_bounds__(256) k_fir_only(const float2 *__restrict__ in, long N, const FirTaps taps, float2 *__restrict__ out)
+{
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N)
+        return;
+    float ar = 0.f, ai = 0.f;
+#pragma unroll
+    for (int j = 0; j < FIR_NT; j++) {
+        const long s = i - (FIR_NT - 1) + j;
+        const float2 x = s >= 0 ? in[s] : make_float2(0.f, 0.f);
+        const float h = taps.h[FIR_NT - 1 - j];
+        if (STRICT) {
+            ar = __fadd_rn(ar, __fmul_rn(x.x, h));
+            ai = __fadd_rn(ai, __fmul_rn(x.y, h));
+        } else {
+            ar = fmaf(x.x, h, ar);
+            ai = fmaf(x.y, h, ai);
+        }
+    }
+    out[i] = make_float2(ar, ai);
+}
+
 // ---------------------------------------------------------------- cp.async helpers (8-byte granules)
 __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src)
 {
@@ -1178,6 +1205,11 @@ constexpr int MM_ZONE = 6;
 struct MMRec { int u_final, count, skip, pad; float mu_final, omega_final; int head_u[4]; float head_mu[4]; float2 p0, p1, p2, c0, c1, c2; };
 
 #ifdef B200_DEFINE_KERNELS
+// STRICT (test hook, b200_demod_debug_run_stage): the reference's operation order, separate multiplies and adds, left to right
+// (volk_32fc_32f_dot_prod_32fc generic; clock_recovery_mm.cpp:103-114 compiled without FMA contraction) -> run as ONE sequential
+// segment on the oracle's own M&M input the symbols must come out BITWISE the oracle's. The production instantiation keeps the
+// two-chain FMA interpolator.
+template <bool STRICT>
 __global__ void __launch_bounds__(SEG_THREADS) k_mm(const float2 *__restrict__ mmin /* 16-sample front pad */, long N, int L, int W, int nseg,
                                                      MMParams P, const MMState *__restrict__ st_in, MMState *__restrict__ st_out,
                                                      const float *__restrict__ bank /*128x8*/, float2 *__restrict__ slots, int cap,
@@ -1265,18 +1297,29 @@ __global__ void __launch_bounds__(SEG_THREADS) k_mm(const float2 *__restrict__ m
                 imu = max(0, min(127, imu));
                 const float *tp = &sbank[imu * MM_BANK_STRIDE];
                 const int n0 = (int)(u - 7) + 64; // >= 56
-                float ar = 0.f, ai = 0.f, br = 0.f, bi = 0.f; // two chains (taps 0-3 / 4-7) to halve the dependent-FMA depth
+                float ar = 0.f, ai = 0.f;
+                if (STRICT) {
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const int na = n0 + k, nb = n0 + k + 4;
-                    const float2 x = ringf[swz16((na >> 1) & 31, lane) * 2 + (na & 1)], y = ringf[swz16((nb >> 1) & 31, lane) * 2 + (nb & 1)];
-                    ar = fmaf(x.x, tp[k], ar);
-                    ai = fmaf(x.y, tp[k], ai);
-                    br = fmaf(y.x, tp[k + 4], br);
-                    bi = fmaf(y.y, tp[k + 4], bi);
+                    for (int k = 0; k < 8; k++) {
+                        const int na = n0 + k;
+                        const float2 x = ringf[swz16((na >> 1) & 31, lane) * 2 + (na & 1)];
+                        ar = __fadd_rn(ar, __fmul_rn(x.x, tp[k]));
+                        ai = __fadd_rn(ai, __fmul_rn(x.y, tp[k]));
+                    }
+                } else {
+                    float br = 0.f, bi = 0.f; // two chains (taps 0-3 / 4-7) to halve the dependent-FMA depth
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const int na = n0 + k, nb = n0 + k + 4;
+                        const float2 x = ringf[swz16((na >> 1) & 31, lane) * 2 + (na & 1)], y = ringf[swz16((nb >> 1) & 31, lane) * 2 + (nb & 1)];
+                        ar = fmaf(x.x, tp[k], ar);
+                        ai = fmaf(x.y, tp[k], ai);
+                        br = fmaf(y.x, tp[k + 4], br);
+                        bi = fmaf(y.y, tp[k + 4], bi);
+                    }
+                    ar += br;
+                    ai += bi;
                 }
-                ar += br;
-                ai += bi;
                 p0 = make_float2(ar, ai);
                 c0 = make_float2(ar > 0.0f ? 1.0f : 0.0f, ai > 0.0f ? 1.0f : 0.0f);
                 // Re[(p0-p2) conj(c1) - (c0-c2) conj(p1)]  (clock_recovery_mm.cpp:103)
@@ -1289,11 +1332,11 @@ __global__ void __launch_bounds__(SEG_THREADS) k_mm(const float2 *__restrict__ m
                         my[count] = p0;
                     count++;
                 }
-                omega = omega + P.omega_gain * pe;
+                omega = STRICT ? __fadd_rn(omega, __fmul_rn(P.omega_gain, pe)) : omega + P.omega_gain * pe;
                 float dev = omega - P.omega_mid;
                 dev = fminf(P.omega_limit, fmaxf(-P.omega_limit, dev));
                 omega = P.omega_mid + dev;
-                mu = (mu + omega) + P.mu_gain * pe;
+                mu = STRICT ? __fadd_rn(__fadd_rn(mu, omega), __fmul_rn(P.mu_gain, pe)) : (mu + omega) + P.mu_gain * pe;
                 float fl = floorf(mu);
                 u += (long)fl;
                 mu -= fl;

@@ -42,6 +42,14 @@ class Demod
     void prefetch_host(const void *h_raw, long nsamples);
     void stats(b200_demod_stats *out);
     void reset(); // back to the state of a freshly created demodulator (new stream)
+    // stages of process(), also run alone by the stage-isolated parity hook
+    float2 *stage_costas(long n, int L, int nseg, int cur, int nxt);
+    void stage_mm(float2 *mmin, long n, int L, int nseg, int cur, int nxt, int8_t *sdst, bool strict);
+    long debug_run_stage(int stage, const float *h_in, long n, int mode, float *h_out, long cap);
+    int last_L = 0, last_nseg = 0;          // segmentation of the last batch (b200_demod_debug_junctions)
+    int dbg_costas_unconv = 0, dbg_mm_unconv = 0, dbg_repairs = 0; // of the last debug_run_stage
+    // junction tolerances: Costas phase (rad) / frequency (rad/sample) residual, M&M sampling instant (samples)
+    float tol_cphase = 2e-3f, tol_cfreq = 1e-4f, tol_mm = 0.05f;
 
     b200_demod_cfg cfg;
     cudaStream_t stream = nullptr;

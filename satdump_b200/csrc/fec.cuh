@@ -266,6 +266,100 @@ __global__ void __launch_bounds__(128) k_vit_acs(const int8_t *__restrict__ soft
     }
 }
 
+// ---------------------------------------------------------------- ACS, DPX form (production kernel)
+// Same arithmetic as acs2_step with the metrics held as X << 8 in each 16-bit field (low byte 0): VIADD.16x2 adds per field modulo 2^16,
+// which IS the reference's uint8 wrap (volk_k7_r2_generic_fixed.h:108-111), so no mask is needed; VIMNMX.U16x2 with predicate outputs
+// returns the minima and both decisions in one instruction (min(Sh, Sl) prefers Sh on ties = the reference's "m0 >= m1 picks m1",
+// :112-115); the per-step renormalisation is min over the two fields (PRMT + VIMNMX), one warp reduction and one subtraction. The
+// branch-metric words come from the broadcast table byte by two IMADs on the FMA pipe: with mb = m << 8,
+//   Ml = mb * (1 - 2^16) + (63 << 24) = m << 8 | (63 - m) << 24        (added to X[i]:    m0 | m2 << 16)
+//   Mh = mb * (2^16 - 1) + (63 << 8)  = (63 - m) << 8 | m << 24        (added to X[i+32]: m1 | m3 << 16)
+struct Acs3Lane { unsigned selM, selX; };
+__device__ __forceinline__ Acs3Lane acs3_lane_consts(int lane)
+{
+    const unsigned idx = (parity_u32((2u * lane) & 79u) ? 2u : 0u) + (parity_u32((2u * lane) & 109u) ? 1u : 0u);
+    Acs3Lane a;
+    a.selM = 0x4404u | (idx << 4);                     // byte idx of the table word into byte 1, zeros elsewhere
+    a.selX = (lane & 1) ? 0x3232u : 0x1010u;           // this lane's field of the shuffled pair, duplicated
+    return a;
+}
+__device__ __forceinline__ void acs3_step(unsigned w, const Acs3Lane L, int lane, unsigned &xl2, unsigned &xh2, unsigned &D0, unsigned &D1)
+{
+    const unsigned mb = __byte_perm(w, 0u, L.selM);
+    const unsigned Ml = mb * 0xFFFF0001u + 0x3F000000u;
+    const unsigned Mh = mb * 0x0000FFFFu + 0x00003F00u;
+    const unsigned Sl = __vadd2(xl2, Ml), Sh = __vadd2(xh2, Mh);
+    bool p_hi, p_lo;
+    unsigned Y = __vibmin_u16x2(Sh, Sl, &p_hi, &p_lo); // predicate = "the first operand (Sh) is the minimum" (ties included)
+    D0 = __ballot_sync(0xffffffffu, p_lo);
+    D1 = __ballot_sync(0xffffffffu, p_hi);
+    const unsigned mn2 = __reduce_min_sync(0xffffffffu, __vminu2(Y, __byte_perm(Y, 0u, 0x1032u))); // min field, in both halves
+    Y -= mn2;
+    const unsigned a = __shfl_sync(0xffffffffu, Y, lane >> 1);
+    const unsigned b = __shfl_sync(0xffffffffu, Y, (lane >> 1) + 16);
+    xl2 = __byte_perm(a, 0u, L.selX);
+    xh2 = __byte_perm(b, 0u, L.selX);
+}
+__device__ __forceinline__ void acs3_init(int ss, int lane, unsigned &xl2, unsigned &xh2)
+{
+    const unsigned l = ss < 0 ? 31u : (lane == ss ? 0u : 63u), h = ss < 0 ? 31u : (lane + 32 == ss ? 0u : 63u);
+    xl2 = l * 0x01000100u;
+    xh2 = h * 0x01000100u;
+}
+__device__ __forceinline__ int acs3_endstate(unsigned xl2, unsigned xh2, int lane)
+{
+    const unsigned k0 = ((xl2 & 0xFF00u) >> 2) | lane, k1 = ((xh2 & 0xFF00u) >> 2) | (lane + 32);
+    return (int)(__reduce_min_sync(0xffffffffu, min(k0, k1)) & 63);
+}
+
+// One warp per chunk like k_vit_acs; the two decision words of a step go to a per-warp shared-memory row buffer (one STS by lane 0)
+// and leave as one coalesced 256-byte store per 32 steps.
+__global__ void __launch_bounds__(128) k_vit_acs3(const int8_t *__restrict__ soft, long chunk0, int nchunks, VitGeom g, VitHyp h,
+                                                   const int *__restrict__ start_state, uint2 *__restrict__ dec, VitRec *__restrict__ rec)
+{
+    __shared__ uint2 srow[4][2][32];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = blockIdx.x * 4 + wib;
+    if (q >= nchunks) return;
+    const int8_t *c = soft + (chunk0 + q) * (long)g.chunk;
+    uint2 *d = dec + (long)q * g.dec_stride;
+    const Acs3Lane L = acs3_lane_consts(lane);
+    const int ss = start_state[q];
+    unsigned xl2, xh2, D0, D1;
+    acs3_init(ss, lane, xl2, xh2);
+    const int steps = g.F + 6;
+    int par = 0;
+    for (int t0 = 0; t0 < steps; t0 += 32, par ^= 1) {
+        const int tm = t0 + lane;
+        const unsigned mine = tm < steps ? metric_table(vit_symbols(c, tm, g, h, g.chunk, 128)) : 0u;
+        uint2 *row = srow[wib][par];
+        if (t0 + 32 <= steps) {
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                acs3_step(__shfl_sync(0xffffffffu, mine, j), L, lane, xl2, xh2, D0, D1);
+                if (lane == 0) row[j] = make_uint2(D0, D1);
+            }
+            __syncwarp();
+            d[t0 + lane] = row[lane];
+        } else {
+            const int nn = steps - t0;
+            for (int j = 0; j < nn; j++) {
+                acs3_step(__shfl_sync(0xffffffffu, mine, j), L, lane, xl2, xh2, D0, D1);
+                if (lane == 0) row[j] = make_uint2(D0, D1);
+            }
+            __syncwarp();
+            if (lane < nn) d[t0 + lane] = row[lane];
+        }
+    }
+    const int st = acs3_endstate(xl2, xh2, lane);
+    if (lane == 0) {
+        VitRec r = rec[q];
+        r.start_used = ss;
+        r.end_state = st;
+        rec[q] = r;
+    }
+}
+
 // ---------------------------------------------------------------- main decode, part 2: chainback, parallel blocks
 // Rows F+5 .. 6 (cc_decoder.cpp:228-276): output bit i comes from row i+6; the state after the first six steps is the next
 // call's start state. The walk is serial in the state, but survivor paths merge: a walk started TB_OVERLAP rows higher from an
