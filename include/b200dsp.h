@@ -163,6 +163,14 @@ int b200_demod_debug_junctions(b200_demod *d, double *costas_out, double *mm_out
 /* test hook: only the sample conversion (BasebandReader::read_samples, baseband_interface.h:170-190) of `nsamples` host samples */
 int b200_demod_debug_convert(b200_demod *d, const void *host_iq, long nsamples, float *host_out);
 int b200_demod_get_stats(b200_demod *d, b200_demod_stats *out);
+/* forget the stream (loop state, resampler counters) but keep every allocation: the next push starts a new stream */
+int b200_demod_reset(b200_demod *d);
+/* double buffering for host streams, as b200_chain_prefetch_iq: start the H2D copy of a FUTURE batch (pinned memory); the later
+ * b200_demod_push_iq() with the same (pointer, nsamples) only waits for it */
+int b200_demod_prefetch_iq(b200_demod *d, const void *host_iq, long nsamples);
+/* elapsed device milliseconds of the last push (CUDA events on the demodulator's stream): [0] = sum, [1] = (front end +) AGC + FIR,
+ * [2] = Costas + rotation (+ OQPSK delay), [3] = M&M + compaction / quantiser */
+int b200_demod_last_timing(b200_demod *d, float *ms_out, int n);
 /* RRC taps / M&M polyphase bank as designed on the host (for parity tests against firdes / PolyphaseBank) */
 int b200_demod_get_taps(b200_demod *d, float *rrc_out, int rrc_cap, float *bank_out /* 128*8 or NULL */);
 

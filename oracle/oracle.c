@@ -486,7 +486,9 @@ long orc_demod_run_stage(void *h, int stage, const float *in, long nsamples, flo
         int n = (int)(nsamples - off < d->buffer_size ? nsamples - off : d->buffer_size), m = n;
         memcpy(d->w0, in + off * 2, n * sizeof(cf_t));
         cf_t *res = d->w1;
-        if (stage == 1)
+        if (stage == 0)
+            agc_run(d, d->w0, d->w1, n);
+        else if (stage == 1)
             fir_run(d, d->w0, d->w1, n);
         else if (stage == 2) {
             costas_run(d, d->w0, d->w1, n);

@@ -213,7 +213,7 @@ def run_stage(cfg, which, x):
     x = np.ascontiguousarray(x, np.complex64)
     d = Demod(cfg)
     out = np.zeros(x.size + 64, np.complex64)
-    n = lib().ref_demod_run_stage(d.h, {"fir": 1, "costas": 2, "mm": 5}[which], _p(x), x.size, _p(out), out.size)
+    n = lib().ref_demod_run_stage(d.h, {"agc": 0, "fir": 1, "costas": 2, "mm": 5}[which], _p(x), x.size, _p(out), out.size)
     if n < 0:
         raise RuntimeError("this configuration has no such stage")
     return out[:n].copy()
@@ -339,5 +339,5 @@ def pipeline_timed(dcfg, fcfg, raw):
     cadu = np.zeros(cap, np.uint8)
     nb = C.c_long(0)
     nt = C.c_int(0)
-    secs = lib().ref_pipeline_timed(C.byref(dcfg), C.byref(fcfg), _p(raw), n, _p(cadu), cap, C.byref(nb), C.byref(nt))
+    secs = lib().ref_pipeline_timed(C.byref(dcfg), C.byref(fcfg) if fcfg is not None else None, _p(raw), n, _p(cadu), cap, C.byref(nb), C.byref(nt))
     return secs, cadu[:nb.value].copy(), nt.value

@@ -384,7 +384,7 @@ extern "C"
 
     /* ONE block of a fresh chain on a caller-supplied cf32 input, in reference-sized buffers: stage 1 = FIRBlock, 2 = CostasLoopBlock
        (+ post-Costas CorrectIQBlock / DelayOneImagBlock: what the clock recovery reads), 5 = MMClockRecoveryBlock. The input is written
-       straight into the stream the block reads. Returns the number of complex outputs (<= cap). */
+       straight into the stream the block reads (stage 0 = AGCBlock on converted samples). Returns the number of complex outputs (<= cap). */
     long ref_demod_run_stage(void *h, int stage, const float *in, long nsamples, float *out, long cap)
     {
         RefDemod *d = (RefDemod *)h;
@@ -392,11 +392,17 @@ extern "C"
         for (long off = 0; off < nsamples; off += d->buffer_size)
         {
             int n = (int)std::min<long>(d->buffer_size, nsamples - off);
-            std::shared_ptr<dsp::stream<complex_t>> src = stage == 1 ? d->agc->output_stream : (stage == 2 ? d->rrc->output_stream : d->rec->input_stream);
+            std::shared_ptr<dsp::stream<complex_t>> src =
+                stage == 0 ? d->in : (stage == 1 ? d->agc->output_stream : (stage == 2 ? d->rrc->output_stream : d->rec->input_stream));
             memcpy(src->writeBuf, in + off * 2, n * sizeof(complex_t));
             src->swap(n);
             std::shared_ptr<dsp::stream<complex_t>> dst;
-            if (stage == 1)
+            if (stage == 0)
+            {
+                d->agc->work();
+                dst = d->agc->output_stream;
+            }
+            else if (stage == 1)
             {
                 d->rrc->work();
                 dst = d->rrc->output_stream;
@@ -751,7 +757,7 @@ extern "C"
                               long *cadu_bytes, int *threads_used)
     {
         RefDemod *d = (RefDemod *)ref_demod_create(dc);
-        RefFec *f = (RefFec *)ref_fec_create(fc);
+        RefFec *f = fc ? (RefFec *)ref_fec_create(fc) : nullptr; /* fc == NULL: the demodulator module alone (C5: symbols are the product) */
         auto fifo = std::make_shared<dsp::RingBuffer<uint8_t>>(1000000);
         std::atomic<bool> demod_done{false};
         std::atomic<long> out_bytes{0};
@@ -805,12 +811,19 @@ extern "C"
                     nb = m * 2;
                 }
                 d->rec->output_stream->flush();
+                if (!f)
+                {
+                    out_bytes += nb;
+                    continue;
+                }
                 if (fifo->write((uint8_t *)sym_buffer.data(), nb) < 0)
                     break;
             }
             demod_done = true;
         });
         std::thread decoder([&]() {
+            if (!f)
+                return;
             std::vector<int8_t> chunk(f->buffer_size);
             while (true)
             {
@@ -848,7 +861,7 @@ extern "C"
         d->rec->stop();
         d->rec->output_stream->stopReader();
         demod_mod.join();
-        while (fifo->getReadable() >= f->buffer_size)
+        while (f && fifo->getReadable() >= f->buffer_size)
             std::this_thread::sleep_for(std::chrono::milliseconds(1));
         fifo->stopReader();
         fifo->stopWriter();
@@ -860,7 +873,8 @@ extern "C"
         if (threads_used)
             *threads_used = nthreads;
         ref_demod_destroy(d);
-        ref_fec_destroy(f);
+        if (f)
+            ref_fec_destroy(f);
         return secs;
     }
 }

@@ -21,7 +21,7 @@ E_NAMES = {0: "OK", -1: "EINVAL", -2: "ENODEV", -3: "ECUDA", -4: "ENOMEM", -5: "
 SYMBOLS = [
     "b200_last_error", "b200_device_count", "b200_demod_final_samplerate", "b200_demod_resampler_bank",
     "b200_demod_create", "b200_demod_destroy", "b200_demod_push_iq", "b200_demod_push_iq_device", "b200_demod_pull_soft",
-    "b200_demod_pull_symbols", "b200_demod_debug_stage", "b200_demod_debug_convert", "b200_demod_debug_run_stage", "b200_demod_debug_junctions", "b200_demod_get_stats", "b200_demod_get_taps",
+    "b200_demod_pull_symbols", "b200_demod_debug_stage", "b200_demod_debug_convert", "b200_demod_debug_run_stage", "b200_demod_debug_junctions", "b200_demod_reset", "b200_demod_prefetch_iq", "b200_demod_last_timing", "b200_demod_get_stats", "b200_demod_get_taps",
     "b200_fec_create", "b200_fec_destroy", "b200_fec_push_soft", "b200_fec_push_soft_device", "b200_fec_pull_frames",
     "b200_fec_debug_bits", "b200_fec_get_stats", "b200_fec_cadu_bytes", "b200_fec_chunk_size",
     "b200_chain_create", "b200_chain_destroy", "b200_chain_push_iq", "b200_chain_push_iq_device", "b200_chain_prefetch_iq", "b200_chain_pull_frames",
@@ -91,6 +91,9 @@ def lib():
         L.b200_demod_debug_run_stage.argtypes = [vp, ci, vp, cl, ci, vp, cl, C.POINTER(cl)]
         L.b200_demod_debug_junctions.argtypes = [vp, vp, vp, cl, C.POINTER(cl), C.POINTER(cl)]
         L.b200_demod_get_stats.argtypes = [vp, C.POINTER(DemodStats)]
+        L.b200_demod_reset.argtypes = [vp]
+        L.b200_demod_prefetch_iq.argtypes = [vp, vp, cl]
+        L.b200_demod_last_timing.argtypes = [vp, vp, ci]
         L.b200_demod_get_taps.argtypes = [vp, vp, ci, vp]
         L.b200_fec_create.restype = vp
         L.b200_fec_create.argtypes = [C.POINTER(FecCfg)]
@@ -183,6 +186,25 @@ def ccsds_cfg(constellation, cadu_size, ber_thresold, outsync_after, rs_i, nrzm=
                   0, 0, 0)
 
 
+def fec_cfg_for(sig, max_soft, device=0):
+    """The decoder configuration that goes with a satdump_b200.synth.SignalCfg (metop_ahrpt_decoder / ccsds_conv_concat_decoder /
+    ccsds_simple_psk_decoder parameters of the shipped pipeline JSONs)."""
+    if sig.decoder == "metop":
+        return metop_cfg(sig.ber_thresold, sig.outsync_after, device=device, max_soft=max_soft)
+    if sig.decoder == "simple":
+        return simple_cfg(sig.constellation, (4 + 255 * sig.interleave) * 8, sig.interleave, nrzm=sig.nrzm, qpsk_swap_iq=sig.constellation == "qpsk",
+                          device=device, max_soft=max_soft)
+    return ccsds_cfg(sig.constellation, (4 + 255 * sig.interleave) * 8, sig.ber_thresold, sig.outsync_after, sig.interleave, nrzm=sig.nrzm,
+                     rs_usecheck=sig.rs_usecheck, device=device, max_soft=max_soft)
+
+
+def demod_cfg_for(sig, max_batch, device=0, **kw):
+    """psk_demod parameters of a satdump_b200.synth.SignalCfg (decoder "none": the Costas-less DVB-S2 front half)."""
+    extra = dict(clock_alpha=sig.clock_alpha) if sig.clock_alpha else {}
+    return demod_cfg(sig.samplerate, sig.symbolrate, sig.constellation if sig.decoder != "none" else "none", sig.rrc_alpha, sig.pll_bw, sig.fmt,
+                     device=device, max_batch=max_batch, **extra, **kw)
+
+
 def _nsamples(raw, fmt):
     raw = np.ascontiguousarray(raw)
     if fmt == 0:
@@ -221,6 +243,30 @@ class Demod:
         _chk(lib().b200_demod_push_iq_device(self.h, ptr, n))
         self._n = n
         return self
+
+    def push_ptr(self, host_ptr, n):
+        _chk(lib().b200_demod_push_iq(self.h, host_ptr, n))
+        self._n = n
+        return self
+
+    def prefetch_ptr(self, host_ptr, n):
+        _chk(lib().b200_demod_prefetch_iq(self.h, host_ptr, n))
+        return self
+
+    def reset(self):
+        _chk(lib().b200_demod_reset(self.h))
+        return self
+
+    def timing(self):
+        ms = np.zeros(4, np.float32)
+        _chk(lib().b200_demod_last_timing(self.h, ms.ctypes.data, 4))
+        return dict(zip(["stages_sum", "agc_fir", "costas", "mm"], ms.tolist()))
+
+    def pull_symbols_into(self, host_ptr, cap_symbols):
+        """Symbols of the last push straight into caller memory (complex64); returns the symbol count."""
+        n = C.c_long(0)
+        _chk(lib().b200_demod_pull_symbols(self.h, host_ptr, cap_symbols, C.byref(n)))
+        return n.value
 
     def soft(self):
         cap = int(self._n * self.bps) + 1024

@@ -239,11 +239,33 @@ Demod::Demod(const b200_demod_cfg &c) : cfg(c)
     {
         const double ref_sps = c.constellation == B200_BPSK ? 2.5 : 2.5714;
         const double scale = std::max(1.0, (double)sps * sps / (ref_sps * ref_sps));
-        Wm = round_up16((c.constellation == B200_BPSK ? 240.0 : 70.0) * scale / c.clock_gain_mu);
+        // QPSK-type: 70/gain_mu left the segments a median 1.1e-4 sample off the sequential trajectory at their first owned symbol
+        // (1.6 % of the symbols of 1024-sample segments off by an interpolator arm, against 0.3-0.4 % for the reference perturbed by
+        // 1e-6: tests/floors.py); the error falls by e per ~1200 samples: 87.5/gain_mu -> 4e-5 (0.7 %), measured on B200
+        Wm = round_up16((c.constellation == B200_BPSK ? 240.0 : 87.5) * scale / c.clock_gain_mu);
     }
     if (const char *e = getenv("B200_MM_WARMUP_SCALE")) // tuning hook
         Wm = round_up16(Wm * atof(e));
-    // junction tolerances (a junction outside them is repaired = re-run as the exact sequential continuation); tuning hooks
+    // gear shift (k_costas / k_mm): the first quarter of a warm-up runs first order at 4x the gain
+    Gc = (Wc / 4) & ~15;
+    Gm = (Wm / 4) & ~15;
+    if (const char *e = getenv("B200_GEAR_SCALE")) { // tuning hook: fraction of the warm-up
+        Gc = (int)(Wc * atof(e)) & ~15;
+        Gm = (int)(Wm * atof(e)) & ~15;
+    }
+    // junction tolerances (a junction outside them is repaired = re-run as the exact sequential continuation). Orders 2 / 4 on
+    // non-offset signals: converged segments sit within 6e-6 rad of their predecessor (float rounding noise of two loops on the same
+    // trajectory), so 1e-5 only catches real stragglers and bounds the output error of a junction to ~1e-5 |v|. The OQPSK / 8PSK
+    // detectors leave 0.1-0.4 % of the warm-ups ~1e-3 off (hang-ups near the unstable lock point); a junction that far off seeds
+    // sign-decision events in the segment (a 7e-3 rad kick each), hence 2e-5 there too. Environment: tuning hooks
+    if (order == 2 || (order == 4 && c.constellation != B200_OQPSK)) {
+        tol_cphase = 1e-5f;
+        tol_cfreq = 2e-6f;
+    } else if (order) { // repairs are common here (1-4 % of the junctions): a round costs about half a k_costas pass
+        tol_cphase = 2e-5f;
+        tol_cfreq = 4e-6f;
+    }
+    tol_mm = 0.01f; // samples (1.3 interpolator arms)
     if (const char *e = getenv("B200_COSTAS_TOL"))
         tol_cphase = (float)atof(e);
     if (const char *e = getenv("B200_COSTAS_FTOL"))
@@ -390,9 +412,10 @@ void Demod::reset()
 
 int Demod::choose_L(long n) const
 {
-    // one segment per thread; aim at one full wave of resident threads, but keep segments within [1024, 16384] samples
+    // one segment per thread; aim at one full wave of resident threads, but keep segments within [4096, 16384] samples: a segment
+    // shorter than a few loop time constants (M&M: ~1200 samples) spends its whole life in the tail of its warm-up transient
     long L = (n + seg_cap_threads - 1) / seg_cap_threads;
-    L = std::max<long>(1024, std::min<long>(16384, L));
+    L = std::max<long>(4096, std::min<long>(16384, L));
     return (int)((L + 15) / 16 * 16);
 }
 
@@ -452,11 +475,11 @@ float2 *Demod::stage_costas(long n, int L, int nseg, int cur, int nxt)
         }
         P.fmin = -cfg.costas_max_offset;
         P.fmax = cfg.costas_max_offset;
-        k_costas<<<nblk, SEG_THREADS, COSTAS_SMEM_BYTES, stream>>>(fir_out, n, L, Wc, nseg, P, S->costas[cur], cos_out, crec.p, nullptr, nullptr);
+        k_costas<<<nblk, SEG_THREADS, COSTAS_SMEM_BYTES, stream>>>(fir_out, n, L, Wc, Gc, nseg, P, S->costas[cur], cos_out, crec.p, nullptr, nullptr);
         k_costas_fix<<<1, 1024, 0, stream>>>(crec.p, nseg, order, tol_cphase, tol_cfreq, quad.p, S->costas[nxt], &S->costas_unconv, repair.p + 1, repair.p, 0,
                                              &S->repairs);
         for (int round = 1; round <= REPAIR_ROUNDS; round++) { // both kernels return at once when no junction is flagged
-            k_costas<<<8, SEG_THREADS, COSTAS_SMEM_BYTES, stream>>>(fir_out, n, L, Wc, nseg, P, S->costas[cur], cos_out, crec.p, repair.p + 1, repair.p);
+            k_costas<<<8, SEG_THREADS, COSTAS_SMEM_BYTES, stream>>>(fir_out, n, L, Wc, Gc, nseg, P, S->costas[cur], cos_out, crec.p, repair.p + 1, repair.p);
             k_costas_fix<<<1, 1024, 0, stream>>>(crec.p, nseg, order, tol_cphase, tol_cfreq, quad.p, S->costas[nxt], &S->costas_unconv, repair.p + 1, repair.p,
                                                  round, &S->repairs);
             launches += 2;
@@ -503,10 +526,10 @@ void Demod::stage_mm(float2 *mmin, long n, int L, int nseg, int cur, int nxt, in
     MP.mu_gain = cfg.clock_gain_mu;
     const int cap = slot_cap_for(L);
     B200_REQUIRE((size_t)nseg * cap <= slots.n, B200_ENOMEM, "internal: symbol slot storage too small");
-    B200_MM_LAUNCH(nblk, mmin, n, L, Wm, nseg, MP, &S->mm[cur], &S->mm[nxt], d_bank.p, slots.p, cap, mrec.p, nullptr, nullptr);
+    B200_MM_LAUNCH(nblk, mmin, n, L, Wm, Gm, nseg, MP, &S->mm[cur], &S->mm[nxt], d_bank.p, slots.p, cap, mrec.p, nullptr, nullptr);
     k_mm_scan<<<1, 1024, 0, stream>>>(mrec.p, nseg, tol_mm, offs.p, &S->mm_unconv, cap, &S->flags, repair.p + 1, repair.p, 0, &S->repairs);
     for (int round = 1; round <= REPAIR_ROUNDS; round++) {
-        B200_MM_LAUNCH(8, mmin, n, L, Wm, nseg, MP, &S->mm[cur], &S->mm[nxt], d_bank.p, slots.p, cap, mrec.p, repair.p + 1, repair.p);
+        B200_MM_LAUNCH(8, mmin, n, L, Wm, Gm, nseg, MP, &S->mm[cur], &S->mm[nxt], d_bank.p, slots.p, cap, mrec.p, repair.p + 1, repair.p);
         k_mm_scan<<<1, 1024, 0, stream>>>(mrec.p, nseg, tol_mm, offs.p, &S->mm_unconv, cap, &S->flags, repair.p + 1, repair.p, round, &S->repairs);
         launches += 2;
     }
@@ -943,6 +966,30 @@ int b200_demod_debug_junctions(b200_demod *h, double *costas_out, double *mm_out
         }
         *nseg_out = ns;
         *seg_len = d.last_L;
+    });
+}
+int b200_demod_reset(b200_demod *h)
+{
+    return guarded([&] {
+        B200_REQUIRE(h, B200_EINVAL, "NULL argument");
+        h->d->reset();
+    });
+}
+int b200_demod_prefetch_iq(b200_demod *h, const void *host_iq, long n)
+{
+    return guarded([&] {
+        B200_REQUIRE(h && host_iq, B200_EINVAL, "NULL argument");
+        h->d->prefetch_host(host_iq, n);
+    });
+}
+int b200_demod_last_timing(b200_demod *h, float *ms, int n)
+{
+    return guarded([&] {
+        B200_REQUIRE(h && ms && n >= 4, B200_EINVAL, "need room for 4 floats");
+        ms[1] = h->d->t_agcfir;
+        ms[2] = h->d->t_costas;
+        ms[3] = h->d->t_mm;
+        ms[0] = ms[1] + ms[2] + ms[3];
     });
 }
 int b200_demod_get_stats(b200_demod *h, b200_demod_stats *out)

@@ -878,7 +878,11 @@ __device__ __forceinline__ void warp_load_rows(float4 *dst, int pbase, int pmask
 // state of its predecessor, i.e. as the exact sequential continuation of that segment (used for junctions whose warm-up had
 // not converged; k_costas_fix re-checks afterwards).
 constexpr int COSTAS_SMEM_BYTES = (SEG_THREADS / 32) * (16 + 8) * 32 * 16; // per warp: 2 input rows + 1 output row of 8 chunks x 32 threads
-__global__ void __launch_bounds__(SEG_THREADS) k_costas(const float2 *__restrict__ in, long N, int L, int W, int nseg, CostasParams P,
+// Gear shift: for the first G samples of a warm-up the loop runs first order (frequency held at the carried value) with 4x the phase
+// gain: a warm-up that starts near an unstable lock point (a hang-up: the detector output is ~0 there) escapes four times faster, so
+// the slow tail of the junction residuals disappears; the remaining W - G samples at the true gains bring the state from the wide
+// loop's jitter down onto the sequential trajectory.
+__global__ void __launch_bounds__(SEG_THREADS) k_costas(const float2 *__restrict__ in, long N, int L, int W, int G, int nseg, CostasParams P,
                                                          const float *__restrict__ state_in, float2 *__restrict__ out, LoopRec *__restrict__ rec,
                                                          const int *__restrict__ repair_list, const int *__restrict__ repair_count)
 {
@@ -900,15 +904,17 @@ __global__ void __launch_bounds__(SEG_THREADS) k_costas(const float2 *__restrict
         s = 0;
     const long own0 = (long)s * L;
     const long own1 = active ? min(own0 + L, N) : own0;
-    long start = own0 - W;
+    long start = own0 - W, gear_end = own0 - W + G;
     float phase = 0.f, freq = state_in[1];
     if (repair_list && active) {
         start = own0;
         phase = rec[s - 1].ph_end;
         freq = rec[s - 1].fr_end;
+        gear_end = 0;
     } else if (start <= 0) {
         start = 0;
         phase = state_in[0];
+        gear_end = 0;
     }
     const int row0 = (int)(start >> 4), row1 = (int)((own1 + 15) >> 4); // rows of 16 samples, [row0, row1)
     int nrows = active ? row1 - row0 : 0, maxrows = nrows;
@@ -936,6 +942,8 @@ __global__ void __launch_bounds__(SEG_THREADS) k_costas(const float2 *__restrict
             lr.fr_start = freq;
         }
         const int nvalid = mine ? (int)min(16L, own1 - b) : 0;
+        const bool gear = b < gear_end;
+        const float al = gear ? 4.0f * P.alpha : P.alpha, be = gear ? 0.0f : P.beta;
         // 4 samples per loop body (the sincosf re-anchor pattern has period 4): a full 16-sample unroll is 59 KB of code and
         // stalls on instruction fetch (ncu: no_instruction 0.8 cycles per issue)
 #pragma unroll 2
@@ -953,9 +961,9 @@ __global__ void __launch_bounds__(SEG_THREADS) k_costas(const float2 *__restrict
                     const float vi = x.y * cs - x.x * sn;
                     o[h] = make_float2(vr, vi);
                     const float err = costas_error(vr, vi, P.order);
-                    freq = freq + P.beta * err;
+                    freq = freq + be * err;
                     const float prev = phase;
-                    phase = phase + (freq + P.alpha * err);
+                    phase = phase + (freq + al * err);
                     const float d = phase - prev; // the increment the float phase really took (exact difference)
                     bool refresh = (j & 3) == 3;
                     if (fmaxf(fabsf(phase), fabsf(d) * 125.0f) > 6.25f) { // rare: a wrap is due or the step is too large to rotate by
@@ -1210,7 +1218,7 @@ struct MMRec { int u_final, count, skip, pad; float mu_final, omega_final; int h
 // segment on the oracle's own M&M input the symbols must come out BITWISE the oracle's. The production instantiation keeps the
 // two-chain FMA interpolator.
 template <bool STRICT>
-__global__ void __launch_bounds__(SEG_THREADS) k_mm(const float2 *__restrict__ mmin /* 16-sample front pad */, long N, int L, int W, int nseg,
+__global__ void __launch_bounds__(SEG_THREADS) k_mm(const float2 *__restrict__ mmin /* 16-sample front pad */, long N, int L, int W, int G, int nseg,
                                                      MMParams P, const MMState *__restrict__ st_in, MMState *__restrict__ st_out,
                                                      const float *__restrict__ bank /*128x8*/, float2 *__restrict__ slots, int cap,
                                                      MMRec *__restrict__ rec, const int *__restrict__ repair_list, const int *__restrict__ repair_count)
@@ -1240,8 +1248,9 @@ __global__ void __launch_bounds__(SEG_THREADS) k_mm(const float2 *__restrict__ m
     long u;
     float mu, omega;
     float2 p0, p1, p2, c0, c1, c2;
-    long ustart = own0 - W;
+    long ustart = own0 - W, gear_end = own0 - W + G; // gear shift as in k_costas: omega held, 4x the mu gain for the first G samples
     if (repair_list && active) {
+        gear_end = 0;
         const MMRec pr = rec[s - 1];
         mu = pr.mu_final; omega = pr.omega_final; p0 = pr.p0; p1 = pr.p1; p2 = pr.p2; c0 = pr.c0; c1 = pr.c1; c2 = pr.c2;
         u = pr.u_final;
@@ -1249,6 +1258,7 @@ __global__ void __launch_bounds__(SEG_THREADS) k_mm(const float2 *__restrict__ m
         MMState st = *st_in;
         mu = st.mu; omega = st.omega; p0 = st.p0; p1 = st.p1; p2 = st.p2; c0 = st.c0; c1 = st.c1; c2 = st.c2;
         u = st.inc;
+        gear_end = 0;
     } else {
         mu = 0.5f; omega = st_in->omega;
         p0 = p1 = p2 = c0 = c1 = c2 = make_float2(0.f, 0.f);
@@ -1332,11 +1342,15 @@ __global__ void __launch_bounds__(SEG_THREADS) k_mm(const float2 *__restrict__ m
                         my[count] = p0;
                     count++;
                 }
-                omega = STRICT ? __fadd_rn(omega, __fmul_rn(P.omega_gain, pe)) : omega + P.omega_gain * pe;
-                float dev = omega - P.omega_mid;
-                dev = fminf(P.omega_limit, fmaxf(-P.omega_limit, dev));
-                omega = P.omega_mid + dev;
-                mu = STRICT ? __fadd_rn(__fadd_rn(mu, omega), __fmul_rn(P.mu_gain, pe)) : (mu + omega) + P.mu_gain * pe;
+                if (u < gear_end)
+                    mu = (mu + omega) + 4.0f * P.mu_gain * pe;
+                else {
+                    omega = STRICT ? __fadd_rn(omega, __fmul_rn(P.omega_gain, pe)) : omega + P.omega_gain * pe;
+                    float dev = omega - P.omega_mid;
+                    dev = fminf(P.omega_limit, fmaxf(-P.omega_limit, dev));
+                    omega = P.omega_mid + dev;
+                    mu = STRICT ? __fadd_rn(__fadd_rn(mu, omega), __fmul_rn(P.mu_gain, pe)) : (mu + omega) + P.mu_gain * pe;
+                }
                 float fl = floorf(mu);
                 u += (long)fl;
                 mu -= fl;

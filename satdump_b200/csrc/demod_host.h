@@ -98,7 +98,7 @@ class Demod
     long *h_total = nullptr; // pinned
     DemodDevState *h_state = nullptr; // pinned snapshot for stats
     cudaEvent_t ev[4];
-    int Wc, Wm, seg_cap_threads;
+    int Wc, Wm, Gc = 0, Gm = 0, seg_cap_threads; // warm-up lengths, gear-shift parts of them
     long max_batch;
     int slot_cap_for(int L) const;
     int choose_L(long n) const;

@@ -300,6 +300,33 @@ __device__ __forceinline__ void acs3_step(unsigned w, const Acs3Lane L, int lane
     xl2 = __byte_perm(a, 0u, L.selX);
     xh2 = __byte_perm(b, 0u, L.selX);
 }
+// the same step without the ballots: the lane's own two decisions as predicates (for the transposed decision store of k_vit_acs3)
+__device__ __forceinline__ void acs3_step_p(unsigned w, const Acs3Lane L, int lane, unsigned &xl2, unsigned &xh2, bool &p_lo, bool &p_hi)
+{
+    const unsigned mb = __byte_perm(w, 0u, L.selM);
+    const unsigned Ml = mb * 0xFFFF0001u + 0x3F000000u;
+    const unsigned Mh = mb * 0x0000FFFFu + 0x00003F00u;
+    const unsigned Sl = __vadd2(xl2, Ml), Sh = __vadd2(xh2, Mh);
+    unsigned Y = __vibmin_u16x2(Sh, Sl, &p_hi, &p_lo);
+    const unsigned mn2 = __reduce_min_sync(0xffffffffu, __vminu2(Y, __byte_perm(Y, 0u, 0x1032u)));
+    Y -= mn2;
+    const unsigned a = __shfl_sync(0xffffffffu, Y, lane >> 1);
+    const unsigned b = __shfl_sync(0xffffffffu, Y, (lane >> 1) + 16);
+    xl2 = __byte_perm(a, 0u, L.selX);
+    xh2 = __byte_perm(b, 0u, L.selX);
+}
+// 32 x 32 bit-matrix transpose across the warp: in: lane i holds row i; out: lane r holds column r (bit i = row i's bit r). Five
+// butterfly stages of one shuffle each.
+__device__ __forceinline__ unsigned warp_transpose32(unsigned x, int lane)
+{
+#pragma unroll
+    for (int sft = 16; sft >= 1; sft >>= 1) {
+        const unsigned m = sft == 16 ? 0x0000FFFFu : (sft == 8 ? 0x00FF00FFu : (sft == 4 ? 0x0F0F0F0Fu : (sft == 2 ? 0x33333333u : 0x55555555u)));
+        const unsigned y = __shfl_xor_sync(0xffffffffu, x, sft);
+        x = (lane & sft) ? ((x & ~m) | ((y & ~m) >> sft)) : ((x & m) | ((y & m) << sft));
+    }
+    return x;
+}
 __device__ __forceinline__ void acs3_init(int ss, int lane, unsigned &xl2, unsigned &xh2)
 {
     const unsigned l = ss < 0 ? 31u : (lane == ss ? 0u : 63u), h = ss < 0 ? 31u : (lane + 32 == ss ? 0u : 63u);
@@ -312,12 +339,17 @@ __device__ __forceinline__ int acs3_endstate(unsigned xl2, unsigned xh2, int lan
     return (int)(__reduce_min_sync(0xffffffffu, min(k0, k1)) & 63);
 }
 
-// One warp per chunk like k_vit_acs; the two decision words of a step go to a per-warp shared-memory row buffer (one STS by lane 0)
-// and leave as one coalesced 256-byte store per 32 steps.
+// One warp per chunk like k_vit_acs. Per batch of 32 trellis steps: every lane prepares the metric table word of one step (next
+// batch's symbol loads are issued one batch ahead), the 32 words are exchanged through shared memory (8 broadcast LDS.128 per lane
+// instead of one SHFL per step: the kernel is bound by the SM's shuffle / vote / reduce port, not by the ALUs), and the two decision
+// words of a step go to a per-warp shared-memory row (one STS by lane 0; DEC_SEL: kept by lane j in registers instead) that leaves
+// as one coalesced 256-byte store per 32 steps.
+template <bool MET_SMEM, int DEC_MODE> // DEC_MODE 0: STS row buffer, 1: lane j keeps step j (SEL), 2: per-lane bit accumulators + warp transpose
 __global__ void __launch_bounds__(128) k_vit_acs3(const int8_t *__restrict__ soft, long chunk0, int nchunks, VitGeom g, VitHyp h,
                                                    const int *__restrict__ start_state, uint2 *__restrict__ dec, VitRec *__restrict__ rec)
 {
     __shared__ uint2 srow[4][2][32];
+    __shared__ __align__(16) unsigned smet[4][2][32];
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = blockIdx.x * 4 + wib;
     if (q >= nchunks) return;
@@ -329,18 +361,51 @@ __global__ void __launch_bounds__(128) k_vit_acs3(const int8_t *__restrict__ sof
     acs3_init(ss, lane, xl2, xh2);
     const int steps = g.F + 6;
     int par = 0;
+    unsigned next = lane < steps ? metric_table(vit_symbols(c, lane, g, h, g.chunk, 128)) : 0u;
     for (int t0 = 0; t0 < steps; t0 += 32, par ^= 1) {
-        const int tm = t0 + lane;
-        const unsigned mine = tm < steps ? metric_table(vit_symbols(c, tm, g, h, g.chunk, 128)) : 0u;
+        const unsigned mine = next;
+        const int tn = t0 + 32 + lane;
+        next = tn < steps ? metric_table(vit_symbols(c, tn, g, h, g.chunk, 128)) : 0u; // consumed one batch later
         uint2 *row = srow[wib][par];
+        unsigned k0 = 0, k1 = 0;
         if (t0 + 32 <= steps) {
+            unsigned w[32];
+            if (MET_SMEM) {
+                smet[wib][par][lane] = mine;
+                __syncwarp();
 #pragma unroll
-            for (int j = 0; j < 32; j++) {
-                acs3_step(__shfl_sync(0xffffffffu, mine, j), L, lane, xl2, xh2, D0, D1);
-                if (lane == 0) row[j] = make_uint2(D0, D1);
+                for (int v = 0; v < 8; v++) {
+                    const uint4 u = reinterpret_cast<const uint4 *>(smet[wib][par])[v];
+                    w[4 * v] = u.x; w[4 * v + 1] = u.y; w[4 * v + 2] = u.z; w[4 * v + 3] = u.w;
+                }
             }
-            __syncwarp();
-            d[t0 + lane] = row[lane];
+            if (DEC_MODE == 2) {
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    bool p_lo, p_hi;
+                    acs3_step_p(MET_SMEM ? w[j] : __shfl_sync(0xffffffffu, mine, j), L, lane, xl2, xh2, p_lo, p_hi);
+                    k0 = k0 * 2u + (p_lo ? 1u : 0u); // step j ends up at bit 31 - j
+                    k1 = k1 * 2u + (p_hi ? 1u : 0u);
+                }
+                k0 = warp_transpose32(k0, lane);     // lane r: the ballot word of step 31 - r
+                k1 = warp_transpose32(k1, lane);
+                d[t0 + 31 - lane] = make_uint2(k0, k1);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    acs3_step(MET_SMEM ? w[j] : __shfl_sync(0xffffffffu, mine, j), L, lane, xl2, xh2, D0, D1);
+                    if (DEC_MODE == 1) {
+                        if (lane == j) { k0 = D0; k1 = D1; }
+                    } else if (lane == 0)
+                        row[j] = make_uint2(D0, D1);
+                }
+                if (DEC_MODE == 1)
+                    d[t0 + lane] = make_uint2(k0, k1);
+                else {
+                    __syncwarp();
+                    d[t0 + lane] = row[lane];
+                }
+            }
         } else {
             const int nn = steps - t0;
             for (int j = 0; j < nn; j++) {

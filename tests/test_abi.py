@@ -97,6 +97,12 @@ def test_bench_reference_arm_contract(built):
         assert k in d, k
     sys.path.insert(0, ROOT)
     import bench
-    assert d["impl"] == "reference" and d["unit"] == "MS/s" and d["config"]["workload"] == bench.WORKLOAD and d["value"] > 0
+    assert d["impl"] == "reference" and d["unit"] == "MS/s" and d["config"]["workload"] == bench.WORKLOADS["c3"]["label"] and d["value"] > 0
+    assert d["metric"] == bench.WORKLOADS["c3"]["metric"]
     assert d["e2e"] == {"value": d["value"], "unit": "MS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1 and d["config"]["cadus_per_step_per_gpu"] > 100
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and d["config"]["result_bytes_per_stream"] > 100 * 1024
+    if cb["kind"] == "reference":  # both builds of the reference, median of >= 3 runs, per-stage single-thread rates
+        assert set(cb["variants"]) == {"generic_O2", "native_O3_fma"}
+        for v in cb["variants"].values():
+            assert len(v["one_stream_MSps_runs"]) >= 3 and v["stage_single_thread_MSps"]["fir"] > 0

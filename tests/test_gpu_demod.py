@@ -1,37 +1,48 @@
-"""GPU: demodulator parity against the oracle, stage by stage, through the C ABI.
+"""GPU: demodulator parity against the oracle from raw IQ, stage by stage, through the C ABI.
 
-Gates (measured values are recorded in DESIGN.md):
-  AGC, FIR outputs                 : |gpu - oracle| <= 1e-5 on EVERY sample
-  Costas(+delay) output            : BPSK/QPSK: <= 1e-5 on >= 99.999 % of the samples and <= 2e-5 on all (measured max 0.75e-5 QPSK,
-                                     1.01e-5 BPSK: the AGC's own float rounding noise, which no exact-arithmetic scan can
-                                     reproduce, is ~0.4e-5 at signal peaks and the loop adds its own); for OQPSK (a QPSK Costas
-                                     loop tracking an offset signal converges more slowly / noisily) <= 1e-5 on >= 99 % and
-                                     <= 2e-2 on all; 8PSK (order-8 detector, a third of the gain; measured 99.90 %, max 7.6e-3) >= 99.8 % and <= 2e-2
-  M&M symbols                      : identical count; <= 1e-5 on >= 97 % of the symbols and <= 5e-2 (a few arms of the
-                                     128-arm interpolator) on all — the loop's rint(mu*128) arm choice makes any run that is
-                                     not bit-identical upstream differ by one arm on ~1-2 % of the symbols (A.14)
-  int8 soft                        : differing on <= 1 % of the bytes, by more than 1 LSB on <= 0.01 % (OQPSK 0.03 %), never by more than 4
+Gates = max(SURVEY.md 8c gate, 1.2 x the reference's own floor) with the floor measured on the reference itself (tests/floors.py:
+its output after a 1e-6 perturbation of the AGC output / with its release build flags). SURVEY 8c:
+  AGC, FIR outputs                 : |gpu - oracle| <= 1e-5 on EVERY sample (no feedback with sign / arm decisions: no floor needed)
+  Costas(+delay) output            : <= 1e-5 everywhere ... unless the reference itself, fed an input 1e-6 off, leaves 1e-5 (every
+                                     detector multiplies by sgn(v.re), sgn(v.im): a sample within the input difference of zero kicks
+                                     the phase by ~alpha for ~1000 samples; costas_loop.cpp:31-52)
+  M&M symbols                      : identical count; <= 1e-5 on >= 99 % of the symbols and <= 1.5e-2 on all
+  int8 soft                        : differing on <= 0.5 % of the bytes, by one LSB
+The same stages fed the oracle's exact stage input (bitwise rows) are in tests/test_gpu_stage_isolated.py.
 """
 import numpy as np
 import pytest
 
 from tests.common import gpu_demod, nsamples, oracle, oracle_demod, signal
+from tests.floors import SURVEY, chain_floor, gate
 
 pytestmark = pytest.mark.gpu
 CONFIGS = ["metop_ahrpt", "bpsk_half", "jpss_hrd", "dvbs2_front", "hrpt_bpsk", "psk8"]
 
 
-def check_mm(gs, om, gsoft=None, osoft=None, big_soft=1e-4, dmax=5e-2):
+def check_mm(gs, om, gsoft=None, osoft=None, floor=None):
+    """M&M symbols / int8 soft bytes against the oracle's: SURVEY 8c gates, or 1.2 x the reference's own floor where that is larger."""
+    fl = floor or {}
     assert gs.size == om.size, (gs.size, om.size)
     d = np.abs(gs - om)
-    frac = float((d <= 1e-5).mean())
-    assert frac >= 0.97, frac
-    assert d.max() <= dmax, d.max()
+    bad = float((d > 1e-5).mean())
+    assert bad <= gate(SURVEY["mm_frac"], fl.get("mm_frac", 0.0)), (bad, fl)
+    assert d.max() <= gate(SURVEY["mm_max"], fl.get("mm_max", 0.0)), (float(d.max()), fl)
     if gsoft is not None:
         assert gsoft.size == osoft.size
         ds = np.abs(gsoft.astype(np.int16) - osoft.astype(np.int16))
-        assert ds.max() <= 4 and (ds > 1).mean() <= big_soft and (ds > 0).mean() <= 0.01, (ds.max(), (ds > 1).mean(), (ds > 0).mean())
-    return frac
+        assert (ds > 0).mean() <= gate(SURVEY["soft_diff"], fl.get("soft_diff", 0.0)), (float((ds > 0).mean()), fl)
+        assert (ds > 1).mean() <= gate(SURVEY["soft_gt1"], fl.get("soft_gt1", 0.0)) + 2e-5 and ds.max() <= max(1, fl.get("soft_max", 0)) + 1, \
+            (float((ds > 1).mean()), int(ds.max()), fl)
+    return 1.0 - bad
+
+
+def check_costas(g, o, floor):
+    d = np.abs(g - o)
+    assert d.mean() <= 2e-6, float(d.mean())
+    # the 1e-5 of the survey with the margin the AGC's own deviation needs (measured max 1.3e-5 on BPSK), or the reference's event floor
+    assert (d > 1e-5).mean() <= gate(1e-5, floor.get("costas_frac", 0.0)), (float((d > 1e-5).mean()), floor)
+    assert d.max() <= gate(2e-5, floor.get("costas_max", 0.0)), (float(d.max()), floor)
 
 
 def test_filter_taps_bitwise(built):
@@ -69,17 +80,13 @@ def test_stage_parity(built, name):
     if g.cfg.final_samplerate > 0:  # front-end resampler (hrpt_bpsk): same length, same samples
         rs = O.resample(oracle_demod(O, cfg).cfg, raw)
         assert g.stage("resamp").size == rs.size == o["front"] and np.abs(g.stage("resamp") - rs).max() <= 2e-6
-    for st in ("agc", "fir") + (("costas",) if o["costas"] is not None else ()):
+    fl = chain_floor(name, 21)
+    for st in ("agc", "fir"):
         d = np.abs(g.stage(st) - o[st])
-        if st == "costas" and cfg.constellation == "oqpsk":
-            assert (d <= 1e-5).mean() >= 0.99 and d.max() <= 2e-2, (st, float((d <= 1e-5).mean()), float(d.max()))
-        elif st == "costas" and cfg.constellation == "8psk":  # order-8 loop: low detector gain, rare near-slips at 18 dB
-            assert (d <= 1e-5).mean() >= 0.998 and d.max() <= 2e-2, (st, float((d <= 1e-5).mean()), float(d.max()))
-        elif st == "costas":
-            assert (d <= 1e-5).mean() >= 0.99999 and d.max() <= 2e-5, (st, float((d <= 1e-5).mean()), float(d.max()), int(np.argmax(d)))
-        else:
-            assert d.max() <= 1e-5, (st, float(d.max()), int(np.argmax(d)))
-    check_mm(g.symbols(), o["mm"], g.soft(), o["soft"], big_soft=3e-4 if cfg.constellation == "oqpsk" else 1e-4)
+        assert d.max() <= 1e-5, (st, float(d.max()), int(np.argmax(d)))
+    if o["costas"] is not None:
+        check_costas(g.stage("costas"), o["costas"], fl)
+    check_mm(g.symbols(), o["mm"], g.soft(), o["soft"], floor=fl)
     s = g.stats()
     assert s["costas_unconverged"] == 0 and s["mm_unconverged"] == 0 and s["agc_clamped"] == 0, s
     assert s["symbols_out"] == o["mm"].size and s["samples_in"] == n and s["last_front_samples"] == o["agc"].size
@@ -106,7 +113,7 @@ def test_streaming_pushes_continue_the_same_stream(built, name, cuts):
         syms.append(g.symbols())
         soft.append(g.soft())
         prev = c
-    check_mm(np.concatenate(syms), o["mm"], np.concatenate(soft), o["soft"], big_soft=3e-4 if cfg.constellation == "oqpsk" else 1e-4)
+    check_mm(np.concatenate(syms), o["mm"], np.concatenate(soft), o["soft"], floor=chain_floor(name, 21))
     s = g.stats()
     assert s["costas_unconverged"] == 0 and s["mm_unconverged"] == 0
 
@@ -246,17 +253,16 @@ def test_post_costas_dc(built):
     n = nsamples(raw, cfg)
     o = O.Demod(O.demod_cfg(post_costas_dc=True, **demod_kwargs(cfg))).run(raw)
     g = capi.Demod(capi.demod_cfg(max_batch=n, keep_stages=True, post_costas_dc=True, **demod_kwargs(cfg))).push(raw)
-    d = np.abs(g.stage("costas") - o["costas"])
-    assert (d <= 1e-5).mean() >= 0.99999 and d.max() <= 2e-5, (float((d <= 1e-5).mean()), float(d.max()))
-    # measured: 0.92 % of the symbols off by >1e-5 (0.51 % without the block), max 6.7e-2 (4-5 interpolator arms), 1.6e-4 of the soft bytes off by >1
-    check_mm(g.symbols(), o["mm"], g.soft(), o["soft"], big_soft=3e-4, dmax=0.1)
+    fl = chain_floor("bpsk_half", 20)  # (the floor of the chain without the block: the block is linear)
+    check_costas(g.stage("costas"), o["costas"], fl)
+    check_mm(g.symbols(), o["mm"], g.soft(), o["soft"], floor=fl)
     g2 = capi.Demod(capi.demod_cfg(max_batch=n, keep_stages=True, post_costas_dc=True, **demod_kwargs(cfg)))
     syms, prev = [], 0
     for c in [100003, 600000, n]:
         g2.push(raw[prev:c])
         syms.append(g2.symbols())
         prev = c
-    check_mm(np.concatenate(syms), o["mm"], dmax=0.1)
+    check_mm(np.concatenate(syms), o["mm"], floor=fl)
     with pytest.raises(capi.B200Error):
         capi.Demod(capi.demod_cfg(30e6, 15e6, "oqpsk", 0.5, post_costas_dc=True, max_batch=65536))
 
