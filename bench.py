@@ -444,10 +444,11 @@ def main():
     frames_ok, first = True, None
     if w["kind"] == "chain":
         fr = res0.reshape(-1, unit)
-        first = next((i for i in range(min(64, clear.shape[0])) if np.array_equal(clear[i], fr[0])), None) if nres else None
-        # (at the stress SNR frames RS could not repair differ from the transmitted ones: compare only when RS reports no failure)
+        first = next((i for i in range(min(256, clear.shape[0])) if np.array_equal(clear[i], fr[0])), None) if nres else None
+        # every CADU must be one of the transmitted frames, in order and without a gap. (At the stress SNR frames RS could not repair
+        # differ from the transmitted ones, and rs_usecheck drops them: then only the repaired ones are compared.)
         strict = pipe.stats()["fec"]["rs_failed"] == 0
-        frames_ok = nres > 0 and (not strict or (first is not None and np.array_equal(fr, clear[first:first + nres])))
+        frames_ok = nres > 0 and (not strict or (first is not None and first + nres <= clear.shape[0] and np.array_equal(fr, clear[first:first + nres])))
 
     # PCIe ceiling of the e2e number: the same pinned batch copied host -> device alone (torch copy engine, CUDA events)
     dst = torch.empty_like(raw)
@@ -543,7 +544,7 @@ def main():
                 "warmup": max(args.warmup, 3), "ms_per_step": wall_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32+u8" if w["kind"] == "chain" else "f32", "data": "synthetic",
                 "config": {"workload": w["label"], "samples_per_step_per_gpu": n, "result_units_per_step_per_gpu": int(nres),
-                           "result_unit_bytes": unit, "cadus_bit_exact_vs_transmitted": bool(all_ok) if w["kind"] == "chain" else None,
+                           "result_unit_bytes": unit, "cadus_bit_exact_vs_transmitted": bool(all_ok) if w["kind"] == "chain" else None, "first_cadu_is_transmitted_frame": first,
                            "l2": "input batch (%.0f MiB) larger than L2" % (n * bps / 2 ** 20), "esn0_db": cfg.esn0_db},
                 "e2e": {"value": e2e, "unit": "MS/s", "h2d_bytes_per_step": n * bps * world, "d2h_bytes_per_step": int(nres) * unit * world,
                         "pcie_h2d_GBps_alone": round(h2d_gbps, 2), "pcie_bound_MSps_per_gpu": round(h2d_gbps * 1e9 / bps / 1e6, 1),

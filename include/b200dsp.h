@@ -34,7 +34,7 @@ extern "C" {
 #define B200_ECUDA -3      /* CUDA runtime failure */
 #define B200_ENOMEM -4
 #define B200_ESTATE -5     /* e.g. pull before push, batch larger than max_batch */
-#define B200_EUNSUPPORTED -6 /* signal condition the parallel formulation does not cover (AGC gain clamp hit, ...) */
+#define B200_EUNSUPPORTED -6 /* option / signal condition this build does not cover (the text says which) */
 
 /* constellation (module param "constellation", module_psk_demod.cpp:17-21; NONE = no Costas loop) */
 enum { B200_BPSK = 0, B200_QPSK = 1, B200_OQPSK = 2, B200_8PSK = 3, B200_NONE = 4, B200_BPSK_90 = 5 };
@@ -73,6 +73,10 @@ typedef struct b200_demod_cfg
     int dc_block;             /* "dc_block": CorrectIQBlock in front (utils/correct_iq.cpp:18-35, module_demod_base.cpp:113-114) */
     int post_costas_dc;       /* "post_costas_dc": CorrectIQBlock between the Costas loop and the clock recovery
                                  (module_psk_demod.cpp:127-134); not with OQPSK                                         */
+    int front_resample;       /* 0: the resampler runs iff final_samplerate differs from samplerate. 2: never - BaseDemodModule::initb's
+                                 `resample` is false (samplerate / symbolrate inside [min_sps, max_sps]) although "custom_samplerate" set
+                                 another final_samplerate: the reference then only designs the RRC and the clock recovery for that rate
+                                 (module_demod_base.cpp:66,73-74,203-204); b200_demod_resample_decision() tells                        */
 } b200_demod_cfg;
 
 typedef struct b200_fec_cfg
@@ -101,7 +105,7 @@ typedef struct b200_demod_stats
     float agc_gain, costas_phase, costas_freq, mm_mu, mm_omega;
     long costas_unconverged;  /* junctions still inconsistent after the repair rounds of the last push (expected 0) */
     long mm_unconverged;      /* same for the M&M loop                                            */
-    int agc_clamped;          /* AGC hit max_gain: outside the parallel formulation              */
+    int agc_clamped;          /* batches so far in which the AGC hit max_gain (silent input): handled by the clamp pass */
     int repairs;              /* segments re-run as exact sequential continuations (junction check failed) */
     long kernel_launches;     /* CUDA kernels launched by this object so far                     */
     long agc_exact_passes;    /* batches whose AGC seeds needed the scanned (exact) pass: weak signal */
@@ -125,6 +129,8 @@ typedef struct b200_demod b200_demod;
  * samplerate/symbolrate lies inside [min_sps, max_sps] (psk_demod: 1.1..4.0, OQPSK 1.6..2.4; pass 0 for those defaults), else the
  * rate the reference's front-end resampler converts to. custom_samplerate > 0 overrides ("custom_samplerate"). */
 double b200_demod_final_samplerate(double samplerate, double symbolrate, int constellation, float min_sps, float max_sps, double custom_samplerate);
+/* BaseDemodModule::initb's `resample` (module_demod_base.cpp:66): 1 when samplerate / symbolrate lies outside [min_sps, max_sps] */
+int b200_demod_resample_decision(double samplerate, double symbolrate, int constellation, float min_sps, float max_sps);
 /* The polyphase bank the front-end resampler uses for (samplerate -> final_samplerate): RationalResamplerBlock::set_ratio
  * (resamp/rational_resampler.cpp:27-41) = firdes::design_resampler_filter_float + PolyphaseBank::init. Host-only (no device):
  * out[arm * *ntaps + k], *interp arms, reduced ratio *interp / *decim. */

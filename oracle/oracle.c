@@ -69,10 +69,11 @@ void orc_mm_bank(float *out)
     }
 }
 
-/* ======================================================================= rational resampler (front end of BaseDemodModule)
- * SmartResamplerBlock (resamp/smart_resampler.cpp:8-61) = optional power-of-two decimator + RationalResamplerBlock. The decimator's
- * tap tables are data of the reference (resamp/power_decim/\*.h) and are not restated: ratios needing it (input rate >= 2 x output
- * rate) are reported as unsupported here and in the CUDA path alike. */
+/* ======================================================================= front-end resampler of BaseDemodModule
+ * SmartResamplerBlock (resamp/smart_resampler.cpp:8-61) = optional power-of-two decimator (PowerDecimatorBlock, resamp/power_decim.cpp: a
+ * cascade of DecimatingFIRBlocks, filter/decimating_fir.cpp) + RationalResamplerBlock. The decimator's tap tables are numeric data of the
+ * reference (resamp/power_decim/\*.h), shared with the CUDA path through satdump_b200/csrc/power_decim_taps.inc (generated). */
+#include "../satdump_b200/csrc/power_decim_taps.inc"
 
 static double izero(double x) /* firdes.cpp:357-373 */
 {
@@ -124,14 +125,40 @@ static int design_resampler(unsigned interpolation, unsigned decimation, float f
 
 static unsigned gcd_u(unsigned a, unsigned b) { while (b) { unsigned t = a % b; a = b; b = t; } return a; }
 
+typedef struct /* DecimatingFIRBlock<complex_t> (filter/decimating_fir.cpp:12-87) */
+{
+    int D, nt, inc;
+    const float *taps; /* as designed; applied reversed (decimating_fir.cpp:30) */
+    float *buffer;     /* re,im pairs: nt history + the call's input */
+} orc_decim;
+
 typedef struct
 {
     int active, interp, decim, ntaps, ctr, inc; /* RationalResamplerBlock: d_interpolation, d_decimation, pfb.ntaps, d_ctr, inc */
     float *bank;                                /* [interp][ntaps] */
     float *buffer;                              /* re,im pairs */
+    int nstages;                                /* PowerDecimatorBlock in front (0 = none), smart_resampler.cpp:22-29 */
+    orc_decim st[4];
+    float *tmp;
 } orc_resamp;
 
-/* SmartResamplerBlock ctor (smart_resampler.cpp:8-61) reduced to its rational branch; returns 0 if unsupported (needs the decimator) */
+/* DecimatingFIRBlock::process: out[k] = sum_j buffer[inc + 1 + j] * taps[nt - 1 - j], inc += D; generic dot product, left to right */
+static int decim_run(orc_decim *d, const float *in, int nsamples, float *out)
+{
+    memcpy(&d->buffer[2 * d->nt], in, (size_t)nsamples * 2 * sizeof(float));
+    int outc = 0;
+    for (; d->inc < nsamples; d->inc += d->D) {
+        const float *x = &d->buffer[2 * (d->inc + 1)];
+        float re = 0, im = 0;
+        for (int j = 0; j < d->nt; j++) { float h = d->taps[d->nt - 1 - j]; re += x[2 * j] * h; im += x[2 * j + 1] * h; }
+        out[2 * outc] = re; out[2 * outc + 1] = im; outc++;
+    }
+    d->inc -= nsamples;
+    memmove(&d->buffer[0], &d->buffer[2 * nsamples], (size_t)d->nt * 2 * sizeof(float));
+    return outc;
+}
+
+/* SmartResamplerBlock ctor (smart_resampler.cpp:8-61) */
 static int resamp_init(orc_resamp *r, unsigned interpolation, unsigned decimation, int max_in)
 {
     memset(r, 0, sizeof(*r));
@@ -139,7 +166,20 @@ static int resamp_init(orc_resamp *r, unsigned interpolation, unsigned decimatio
     double rsamp_in = decimation, fout = interpolation;
     if (decimation > interpolation) {
         int best_power = floor(log2(decimation / interpolation)); /* integer division, as in the reference */
-        if (best_power > 0) return 0;
+        if (best_power > 0) {
+            int best_decim = 1 << best_power;
+            if (best_decim > (1 << PD_NPLANS)) best_decim = 1 << PD_NPLANS;
+            rsamp_in = (double)decimation / (double)best_decim;
+            const PdPlan *plan = &PD_PLANS[(int)log2(best_decim) - 1]; /* power_decim.cpp:15-29 */
+            r->nstages = plan->nstages;
+            for (int i = 0; i < plan->nstages; i++) {
+                r->st[i].D = plan->stages[i].decimation; r->st[i].nt = plan->stages[i].ntaps; r->st[i].taps = PD_TAPS + plan->stages[i].offset;
+                r->st[i].buffer = calloc((size_t)2 * (max_in + r->st[i].nt + 16), sizeof(float));
+            }
+            r->tmp = calloc((size_t)2 * (max_in + 16), sizeof(float));
+            r->active = 1; r->interp = r->decim = 1; /* (the rational part below may replace these) */
+        }
+        if (rsamp_in == fout) { r->ntaps = 0; return 1; }
         double t;
         while (modf(rsamp_in, &t) != 0 || modf(fout, &t) != 0) { rsamp_in *= 10; fout *= 10; }
     }
@@ -161,6 +201,14 @@ static int resamp_init(orc_resamp *r, unsigned interpolation, unsigned decimatio
 /* RationalResamplerBlock::process (rational_resampler.cpp:43-65); generic volk_32fc_32f_dot_prod_32fc: left to right, mul then add */
 static int resamp_run(orc_resamp *r, const float *in, int nsamples, float *out)
 {
+    if (r->nstages) { /* SmartResamplerBlock::process: decimator, then (in place) the rational resampler */
+        float *cur = r->tmp;
+        for (int i = 0; i < r->nstages; i++) {
+            nsamples = decim_run(&r->st[i], in, nsamples, r->ntaps == 0 && i == r->nstages - 1 ? out : cur);
+            in = cur;
+        }
+        if (r->ntaps == 0) return nsamples;
+    }
     memcpy(&r->buffer[2 * (r->ntaps - 1)], in, nsamples * 2 * sizeof(float));
     int outc = 0;
     while (r->inc < nsamples) {
@@ -276,7 +324,9 @@ void *orc_demod_create(const orc_demod_cfg *c)
 void orc_demod_destroy(void *h)
 {
     orc_demod *d = h;
-    free(d->fir_buf); free(d->mm_buf); free(d->w0); free(d->w1); free(d->w2); free(d->rs.bank); free(d->rs.buffer); free(d->rs_in); free(d);
+    free(d->fir_buf); free(d->mm_buf); free(d->w0); free(d->w1); free(d->w2); free(d->rs.bank); free(d->rs.buffer); free(d->rs_in);
+    for (int i = 0; i < d->rs.nstages; i++) free(d->rs.st[i].buffer);
+    free(d->rs.tmp); free(d);
 }
 float orc_demod_sps(void *h) { return ((orc_demod *)h)->sps; }
 

@@ -35,7 +35,7 @@ namespace b200plugin
             else if (it.value().is_boolean())
                 p.set(it.key(), it.value().get<bool>() ? "true" : "false");
             else if (it.value().is_number())
-                p.set(it.key(), std::to_string(it.value().get<double>()));
+                p.set(it.key(), it.value().dump()); // the JSON text of the number: std::to_string(double) would print 1.89e-5 as 0.000019
         }
         return p;
     }
@@ -100,9 +100,10 @@ namespace b200plugin
                     for (;;)
                     {
                         int n = std::max(1, std::min<int>((int)b.size(), stage->output_fifo->readable()));
-                        if (stage->output_fifo->read(b.data(), n) < 0)
+                        const int r = stage->output_fifo->read(b.data(), n); // (a short count = the stage stopped writing)
+                        if (r < 0)
                             break;
-                        if (output_fifo->write(b.data(), n) < 0)
+                        if (output_fifo->write(b.data(), r) < 0)
                             break;
                     }
                 });
@@ -114,6 +115,14 @@ namespace b200plugin
             catch (const std::exception &e)
             {
                 logger->error("b200_dsp_support: %s", e.what()); // process() is void in the reference: runtime problems are logged
+                // the stage is gone: release the pump threads (they may sit in a blocking write / read on either FIFO)
+                if (stage->input_fifo)
+                {
+                    stage->input_fifo->stopWriter();
+                    stage->input_fifo->stopReader();
+                }
+                if (input_data_type == DATA_STREAM && input_fifo)
+                    input_fifo->stopReader();
             }
             d_output_file = stage->getOutput();
             if (stage->output_fifo)

@@ -19,7 +19,7 @@ E_NAMES = {0: "OK", -1: "EINVAL", -2: "ENODEV", -3: "ECUDA", -4: "ENOMEM", -5: "
 
 # every symbol include/b200dsp.h declares (tests check the built library exports all of them)
 SYMBOLS = [
-    "b200_last_error", "b200_device_count", "b200_demod_final_samplerate", "b200_demod_resampler_bank",
+    "b200_last_error", "b200_device_count", "b200_demod_final_samplerate", "b200_demod_resample_decision", "b200_demod_resampler_bank",
     "b200_demod_create", "b200_demod_destroy", "b200_demod_push_iq", "b200_demod_push_iq_device", "b200_demod_pull_soft",
     "b200_demod_pull_symbols", "b200_demod_debug_stage", "b200_demod_debug_convert", "b200_demod_debug_run_stage", "b200_demod_debug_junctions", "b200_demod_reset", "b200_demod_prefetch_iq", "b200_demod_last_timing", "b200_demod_get_stats", "b200_demod_get_taps",
     "b200_fec_create", "b200_fec_destroy", "b200_fec_push_soft", "b200_fec_push_soft_device", "b200_fec_pull_frames",
@@ -35,7 +35,8 @@ class DemodCfg(C.Structure):
                 ("rrc_taps", C.c_int), ("pll_bw", C.c_float), ("agc_rate", C.c_float), ("clock_gain_omega", C.c_float),
                 ("clock_mu", C.c_float), ("clock_gain_mu", C.c_float), ("clock_omega_limit", C.c_float),
                 ("costas_max_offset", C.c_float), ("format", C.c_int), ("device", C.c_int), ("max_batch", C.c_long),
-                ("keep_stages", C.c_int), ("iq_swap", C.c_int), ("final_samplerate", C.c_double), ("dc_block", C.c_int), ("post_costas_dc", C.c_int)]
+                ("keep_stages", C.c_int), ("iq_swap", C.c_int), ("final_samplerate", C.c_double), ("dc_block", C.c_int), ("post_costas_dc", C.c_int),
+                ("front_resample", C.c_int)]
 
 
 class FecCfg(C.Structure):
@@ -79,6 +80,7 @@ def lib():
         L.b200_demod_create.restype = vp
         L.b200_demod_final_samplerate.restype = C.c_double
         L.b200_demod_final_samplerate.argtypes = [C.c_double, C.c_double, ci, C.c_float, C.c_float, C.c_double]
+        L.b200_demod_resample_decision.argtypes = [C.c_double, C.c_double, ci, C.c_float, C.c_float]
         L.b200_demod_resampler_bank.argtypes = [C.c_double, C.c_double, vp, cl, C.POINTER(ci), C.POINTER(ci), C.POINTER(ci)]
         L.b200_demod_create.argtypes = [C.POINTER(DemodCfg)]
         L.b200_demod_destroy.argtypes = [vp]
@@ -135,7 +137,8 @@ def _chk(rc):
 
 def demod_cfg(samplerate, symbolrate, constellation, rrc_alpha, pll_bw=0.003, fmt="cs16", rrc_taps=31, agc_rate=1e-2, clock_alpha=None,
               clock_gain_omega=None, clock_mu=0.5, clock_gain_mu=8.7e-3, clock_omega_limit=0.005, costas_max_offset=1.0, device=0,
-              max_batch=1 << 24, keep_stages=False, iq_swap=False, final_samplerate=None, min_sps=0.0, max_sps=0.0, dc_block=False, post_costas_dc=False):
+              max_batch=1 << 24, keep_stages=False, iq_swap=False, final_samplerate=None, min_sps=0.0, max_sps=0.0, dc_block=False, post_costas_dc=False,
+              front_resample=0):
     """Parameter defaults = module_psk_demod.h:31-39, module_demod_base.h:54. final_samplerate=None applies BaseDemodModule::initb's
     rule (resample when samplerate/symbolrate is outside [min_sps, max_sps]); 0 forces "no resampler"."""
     if final_samplerate is None:
@@ -149,7 +152,7 @@ def demod_cfg(samplerate, symbolrate, constellation, rrc_alpha, pll_bw=0.003, fm
         clock_gain_omega = float(np.float32(pow(8.7e-3, 2) / 4.0))
     return DemodCfg(float(samplerate), float(symbolrate), CONST[constellation], rrc_alpha, rrc_taps, pll_bw, agc_rate, clock_gain_omega,
                     clock_mu, clock_gain_mu, clock_omega_limit, costas_max_offset, FMT[fmt], device, max_batch, int(keep_stages), int(iq_swap),
-                    float(final_samplerate), int(dc_block), int(post_costas_dc))
+                    float(final_samplerate), int(dc_block), int(post_costas_dc), int(front_resample))
 
 
 def resampler_bank(samplerate, final_samplerate):

@@ -239,7 +239,15 @@ b200_chain *b200_chain_create(const b200_demod_cfg *dcfg, const b200_fec_cfg *fc
         h = new b200_chain();
         try {
             h->c.d = new Demod(*dcfg);
-            h->c.f = new Fec(*fcfg);
+            // the decoder's soft FIFO must take the soft bytes of a whole demodulated batch whatever the caller guessed: at the
+            // lowest samples-per-symbol the clock recovery may settle at (and after an interpolating front-end resampler) that is
+            // max_work / omin symbols (e.g. 1.25 soft bytes per sample for QPSK at 1.6 samples per symbol)
+            b200_fec_cfg fc = *fcfg;
+            const double omin = h->c.d->sps * (1.0 - dcfg->clock_omega_limit) - 0.01;
+            const long need = (long)(h->c.d->max_work / omin + 1024) * h->c.d->bps + (1 << 16);
+            if (fc.max_soft < need)
+                fc.max_soft = need;
+            h->c.f = new Fec(fc);
             DeviceGuard g(dcfg->device);
             B200_CUDA(cudaEventCreate(&h->c.e0));
             B200_CUDA(cudaEventCreate(&h->c.e1));

@@ -1,6 +1,7 @@
 // C ABI + host driver of the demodulator (see include/b200dsp.h, demod_host.h).
 #define B200_DEFINE_KERNELS
 #include "demod_host.h"
+#include "power_decim_taps.inc"
 #include <string>
 #include <algorithm>
 #include <cmath>
@@ -195,25 +196,52 @@ Demod::Demod(const b200_demod_cfg &c) : cfg(c)
     B200_REQUIRE(sps >= lo * 0.999f && sps <= hi * 1.001f, B200_EINVAL,
                  "samples per symbol %.4f outside [%.1f, %.1f]: set final_samplerate (b200_demod_final_samplerate) so that the front-end resampler runs", sps, lo,
                  hi);
-    if (c.final_samplerate > 0 && (long)c.final_samplerate != fs) {
+    if (c.final_samplerate > 0 && (long)c.final_samplerate != fs && c.front_resample != 2) {
         // SmartResamplerBlock(input, final_samplerate, d_samplerate) -> (unsigned interpolation, unsigned decimation), smart_resampler.cpp:8-61
         const unsigned interpolation = (unsigned)final_fs, decimation = (unsigned)fs;
         B200_REQUIRE(interpolation > 0, B200_EINVAL, "final_samplerate too small");
         double rsamp_in = decimation, fout = interpolation;
+        bool rational = true;
         if (decimation > interpolation) {
-            const int best_power = (int)floor(log2((double)(decimation / interpolation)));
-            B200_REQUIRE(best_power <= 0, B200_EUNSUPPORTED,
-                         "samplerate / final_samplerate >= 2 needs SmartResamplerBlock's power-of-two decimator, whose tap tables are not part of this build");
+            const int best_power = (int)floor(log2((double)(decimation / interpolation))); // (unsigned division, as the reference)
+            if (best_power > 0) { // power-of-two decimator first: smart_resampler.cpp:22-29, power_decim.cpp:13-29
+                const int best_decim = std::min<int>(1 << best_power, 1 << PD_NPLANS);
+                rsamp_in = (double)decimation / (double)best_decim;
+                const PdPlan &plan = PD_PLANS[(int)log2((double)best_decim) - 1];
+                for (int i = 0; i < plan.nstages; i++) {
+                    DecimStage st;
+                    st.D = plan.stages[i].decimation;
+                    st.nt = plan.stages[i].ntaps;
+                    st.taps_rev.resize(st.nt);
+                    for (int k = 0; k < st.nt; k++)
+                        st.taps_rev[k] = PD_TAPS[plan.stages[i].offset + st.nt - 1 - k]; // decimating_fir.cpp:30: reversed
+                    decim.push_back(std::move(st));
+                }
+                decim_total = best_decim;
+            }
+            rational = rsamp_in != fout;
+            if (rational) {
+                double t; // "ensure it's all integer" (smart_resampler.cpp:35-40)
+                while (modf(rsamp_in, &t) != 0 || modf(fout, &t) != 0) {
+                    rsamp_in *= 10;
+                    fout *= 10;
+                }
+            }
         }
-        unsigned I = (unsigned)fout, D = (unsigned)rsamp_in;
-        const unsigned g = gcd_u(I, D);
-        I /= g;
-        D /= g;
-        rs_I = (int)I;
-        rs_D = (int)D;
-        rs_nt = design_resampler_bank(I, D, rs_bank);
-        B200_REQUIRE(rs_nt <= RS_MAX_TAPS, B200_EUNSUPPORTED, "resampler arm of %d taps exceeds the built maximum %d", rs_nt, RS_MAX_TAPS);
-        resamp = true;
+        if (rational) {
+            unsigned I = (unsigned)fout, D = (unsigned)rsamp_in;
+            const unsigned g = gcd_u(I, D);
+            I /= g;
+            D /= g;
+            rs_I = (int)I;
+            rs_D = (int)D;
+            rs_nt = design_resampler_bank(I, D, rs_bank);
+            B200_REQUIRE(rs_nt <= RS_MAX_TAPS, B200_EUNSUPPORTED, "resampler arm of %d taps exceeds the built maximum %d", rs_nt, RS_MAX_TAPS);
+            resamp = true;
+        } else if (c.iq_swap && decim.empty()) {
+            rs_bank.assign(1, 1.0f);
+            resamp = true;
+        }
     } else if (c.iq_swap) { // the plain swap runs as the identity resampler
         rs_bank.assign(1, 1.0f);
         resamp = true;
@@ -223,7 +251,7 @@ Demod::Demod(const b200_demod_cfg &c) : cfg(c)
     bps = c.constellation == B200_BPSK ? 1 : 2;
     order = c.constellation == B200_BPSK ? 2 : (c.constellation == B200_8PSK ? 8 : (c.constellation == B200_NONE ? 0 : 4));
     max_batch = c.max_batch;
-    max_work = resamp ? std::max<long>(max_batch, (long)((double)max_batch * rs_I / rs_D) + 64) : max_batch;
+    max_work = resamp ? std::max<long>(max_batch, (long)((double)max_batch * rs_I / rs_D) + 64) : max_batch; // (a decimator in front only shrinks it)
     design_rrc(1, final_fs, (double)(int)rs, c.rrc_alpha, c.rrc_taps, rrc);
     design_mm_bank(bank);
     // Costas warm-up: 24 loop time constants for orders 2/4; the order-8 detector has about a third of the gain (measured on the
@@ -299,30 +327,31 @@ Demod::Demod(const b200_demod_cfg &c) : cfg(c)
     }
     const int ntiles_max = (int)((max_work + FIR_TILE - 1) / FIR_TILE);
     tile_map.alloc(ntiles_max + 1);
+    tile_map3.alloc(ntiles_max + 1);
     seeds.alloc(ntiles_max + 2);
     agc_need.alloc(2);
     agc_need.zero(stream);
     {
         // 5 CTAs x 41.7 KB of static smem per SM: ask for the large shared-memory carve-out
-        B200_CUDA(cudaFuncSetAttribute(k_agc_fir<0, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        B200_CUDA(cudaFuncSetAttribute(k_agc_fir<1, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        B200_CUDA(cudaFuncSetAttribute(k_agc_fir<2, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        B200_CUDA(cudaFuncSetAttribute(k_agc_fir<0, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        B200_CUDA(cudaFuncSetAttribute(k_agc_fir<1, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        B200_CUDA(cudaFuncSetAttribute(k_agc_fir<2, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        B200_CUDA(cudaFuncSetAttribute(k_agc_fir<0, false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        B200_CUDA(cudaFuncSetAttribute(k_agc_fir<1, false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        B200_CUDA(cudaFuncSetAttribute(k_agc_fir<2, false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        B200_CUDA(cudaFuncSetAttribute(k_agc_fir<0, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        B200_CUDA(cudaFuncSetAttribute(k_agc_fir<1, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        B200_CUDA(cudaFuncSetAttribute(k_agc_fir<2, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         int per_sm = 0;
         if (c.format == B200_CF32 || resamp || c.dc_block)
-            B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_agc_fir<0, false>, FIR_THREADS, 0));
+            B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_agc_fir<0, false, false>, FIR_THREADS, 0));
         else if (c.format == B200_CS16)
-            B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_agc_fir<1, false>, FIR_THREADS, 0));
+            B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_agc_fir<1, false, false>, FIR_THREADS, 0));
         else
-            B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_agc_fir<2, false>, FIR_THREADS, 0));
+            B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_agc_fir<2, false, false>, FIR_THREADS, 0));
         fir_ctas = std::max(1, per_sm) * dev_sms;
         if (const char *e = getenv("B200_AGC_WARM_TILES")) // 0 forces the exact (scanned-seed) pass: test hook
             agc_warm_max = std::max(0, atoi(e));
     }
-    // worst-case segment count / slot storage: L >= 1024
-    const int lmin = 1024;
+    // worst-case segment count / slot storage: 4096 <= L <= 16384 (choose_L), nseg * cap(L) <= n/omin + L/omin + 16 (nseg + 1)
+    const int lmin = 4096;
     const long nseg_max = (max_work + lmin - 1) / lmin + 1;
     crec.alloc(nseg_max);
     mrec.alloc(nseg_max);
@@ -330,7 +359,7 @@ Demod::Demod(const b200_demod_cfg &c) : cfg(c)
     offs.alloc(nseg_max + 1);
     repair.alloc(1025);
     const double omin = sps * (1.0 - c.clock_omega_limit) - 0.01;
-    slots.alloc((size_t)(max_work / omin) + nseg_max * 24 + 1024);
+    slots.alloc((size_t)(max_work / omin) + (size_t)(16384 / omin) + nseg_max * 24 + 1024);
     sym_out.alloc((size_t)(max_work / omin) + 1024);
     soft.alloc(((size_t)(max_work / omin) + 1024) * bps);
     d_bank.alloc(128 * 8);
@@ -345,6 +374,19 @@ Demod::Demod(const b200_demod_cfg &c) : cfg(c)
         B200_REQUIRE(order != 0 && c.constellation != B200_OQPSK, B200_EINVAL, "post_costas_dc needs a Costas loop and is not built for OQPSK");
         pdc_out.alloc(max_work + 64);
         pdc_out.zero(stream);
+    }
+    {
+        long cap = max_batch;
+        for (auto &stg : decim) {
+            cap = cap / stg.D + 2;
+            stg.d_taps.alloc(stg.nt);
+            stg.tail[0].alloc(stg.nt);
+            stg.tail[1].alloc(stg.nt);
+            stg.tail[0].zero(stream);
+            stg.tail[1].zero(stream);
+            stg.out.alloc(cap + 64);
+            B200_CUDA(cudaMemcpyAsync(stg.d_taps.p, stg.taps_rev.data(), stg.nt * sizeof(float), cudaMemcpyHostToDevice, stream));
+        }
     }
     if (resamp) {
         d_rs_bank.alloc(rs_bank.size());
@@ -408,6 +450,12 @@ void Demod::reset()
     parity = 0;
     last_n = last_syms = 0;
     rs_inc = rs_ctr = 0;
+    for (auto &stg : decim) {
+        stg.inc = 0;
+        stg.tail[0].zero(stream);
+        stg.tail[1].zero(stream);
+    }
+    B200_CUDA(cudaStreamSynchronize(stream));
 }
 
 int Demod::choose_L(long n) const
@@ -445,20 +493,33 @@ template <int FMT> static void launch_front(Demod &d, const void *raw, long n, i
             k_agc_scan<<<1, 1024, 0, d.stream>>>(d.tile_map.p, ntiles, &S->gain[cur], need, d.seeds.p, &S->agc_exact);
         }
         if (dump)
-            k_agc_fir<FMT, true><<<nranges, FIR_THREADS, 0, d.stream>>>(raw, n, d.cfg.agc_rate, &S->gain[cur], R, ctl, taps, S->agc_tail[cur],
-                                                                       S->agc_tail[cur ^ 1], fir_out, d.agc_dump.p, &S->gain[cur ^ 1], &S->flags);
+            k_agc_fir<FMT, true, false><<<nranges, FIR_THREADS, 0, d.stream>>>(raw, n, d.cfg.agc_rate, &S->gain[cur], R, ctl, taps, S->agc_tail[cur],
+                                                                              S->agc_tail[cur ^ 1], fir_out, d.agc_dump.p, &S->gain[cur ^ 1], &S->flags);
         else
-            k_agc_fir<FMT, false><<<nranges, FIR_THREADS, 0, d.stream>>>(raw, n, d.cfg.agc_rate, &S->gain[cur], R, ctl, taps, S->agc_tail[cur],
-                                                                        S->agc_tail[cur ^ 1], fir_out, nullptr, &S->gain[cur ^ 1], &S->flags);
+            k_agc_fir<FMT, false, false><<<nranges, FIR_THREADS, 0, d.stream>>>(raw, n, d.cfg.agc_rate, &S->gain[cur], R, ctl, taps, S->agc_tail[cur],
+                                                                               S->agc_tail[cur ^ 1], fir_out, nullptr, &S->gain[cur ^ 1], &S->flags);
     }
-    d.launches += 4;
+    // clamp pass: the gain reached max_gain somewhere in this batch (silent input), so the unclamped maps above do not describe
+    // the reference's loop; redo the stage with the clamped ones. All three launches return at once otherwise.
+    ctl.seeded = 1;
+    k_agc_compose3<FMT><<<std::min(ntiles, d.fir_ctas * 2), FIR_THREADS, 0, d.stream>>>(raw, n, d.cfg.agc_rate, &S->flags, ntiles, d.tile_map3.p);
+    k_agc_scan3<<<1, 1024, 0, d.stream>>>(d.tile_map3.p, ntiles, &S->gain[cur], &S->flags, d.seeds.p);
+    if (dump)
+        k_agc_fir<FMT, true, true><<<nranges, FIR_THREADS, 0, d.stream>>>(raw, n, d.cfg.agc_rate, &S->gain[cur], R, ctl, taps, S->agc_tail[cur],
+                                                                         S->agc_tail[cur ^ 1], fir_out, d.agc_dump.p, &S->gain[cur ^ 1], &S->flags);
+    else
+        k_agc_fir<FMT, false, true><<<nranges, FIR_THREADS, 0, d.stream>>>(raw, n, d.cfg.agc_rate, &S->gain[cur], R, ctl, taps, S->agc_tail[cur],
+                                                                          S->agc_tail[cur ^ 1], fir_out, nullptr, &S->gain[cur ^ 1], &S->flags);
+    d.launches += 7;
 }
 
 // Costas loop (+ junction fix-up and repair rounds) over the FIR output in bufA, exact rotation / OQPSK delay / optional DC blocker
 // into the clock recovery's input buffer (16-sample front pad: [8, 16) = the previous batch's last 8 inputs). Returns that buffer.
-float2 *Demod::stage_costas(long n, int L, int nseg, int cur, int nxt)
+float2 *Demod::stage_costas(long n, int L, int nseg, int cur, int nxt, bool materialise)
 {
     DemodDevState *S = st.p;
+    mm_quad = nullptr;
+    mm_rot = mm_oqpsk = 0;
     float2 *fir_out = bufA.p + 16, *cos_out = bufB.p + 16;
     const int nblk = (nseg + SEG_THREADS - 1) / SEG_THREADS;
     last_L = L;
@@ -484,6 +545,15 @@ float2 *Demod::stage_costas(long n, int L, int nseg, int cur, int nxt)
                                                  round, &S->repairs);
             launches += 2;
         }
+        if (!materialise && !cfg.post_costas_dc) {
+            // fused: the clock recovery rotates (and, for OQPSK, delays) its input rows itself
+            k_mm_prep<<<1, 32, 0, stream>>>(bufB.p, n, L, order, quad.p, S->mm_hist[cur], S->mm_hist[nxt]);
+            launches += 3;
+            mm_quad = quad.p;
+            mm_rot = order;
+            mm_oqpsk = cfg.constellation == B200_OQPSK;
+            return bufB.p;
+        }
         mmin = bufA.p; // FIR output is dead now: reuse its buffer (in place compatible: same index mapping)
         k_rotate<<<2048, 256, 0, stream>>>(cos_out, n, L, order, cfg.constellation == B200_OQPSK, quad.p, S->mm_hist[cur], S->mm_hist[nxt], mmin);
         launches += 3;
@@ -499,6 +569,10 @@ float2 *Demod::stage_costas(long n, int L, int nseg, int cur, int nxt)
             launches += 3;
             mmin = pdc_out.p;
         }
+    } else if (!materialise) {
+        k_mm_prep<<<1, 32, 0, stream>>>(bufA.p, n, L, 0, quad.p, S->mm_hist[cur], S->mm_hist[nxt]);
+        launches += 1;
+        return bufA.p; // the clock recovery reads the FIR output in place
     } else {
         mmin = bufB.p;
         k_rotate<<<2048, 256, 0, stream>>>(fir_out, n, L, 0, 0, quad.p, S->mm_hist[cur], S->mm_hist[nxt], mmin);
@@ -526,10 +600,10 @@ void Demod::stage_mm(float2 *mmin, long n, int L, int nseg, int cur, int nxt, in
     MP.mu_gain = cfg.clock_gain_mu;
     const int cap = slot_cap_for(L);
     B200_REQUIRE((size_t)nseg * cap <= slots.n, B200_ENOMEM, "internal: symbol slot storage too small");
-    B200_MM_LAUNCH(nblk, mmin, n, L, Wm, Gm, nseg, MP, &S->mm[cur], &S->mm[nxt], d_bank.p, slots.p, cap, mrec.p, nullptr, nullptr);
+    B200_MM_LAUNCH(nblk, mmin, n, L, Wm, Gm, nseg, MP, &S->mm[cur], &S->mm[nxt], d_bank.p, slots.p, cap, mrec.p, nullptr, nullptr, mm_quad, mm_rot, mm_oqpsk);
     k_mm_scan<<<1, 1024, 0, stream>>>(mrec.p, nseg, tol_mm, offs.p, &S->mm_unconv, cap, &S->flags, repair.p + 1, repair.p, 0, &S->repairs);
     for (int round = 1; round <= REPAIR_ROUNDS; round++) {
-        B200_MM_LAUNCH(8, mmin, n, L, Wm, Gm, nseg, MP, &S->mm[cur], &S->mm[nxt], d_bank.p, slots.p, cap, mrec.p, repair.p + 1, repair.p);
+        B200_MM_LAUNCH(8, mmin, n, L, Wm, Gm, nseg, MP, &S->mm[cur], &S->mm[nxt], d_bank.p, slots.p, cap, mrec.p, repair.p + 1, repair.p, mm_quad, mm_rot, mm_oqpsk);
         k_mm_scan<<<1, 1024, 0, stream>>>(mrec.p, nseg, tol_mm, offs.p, &S->mm_unconv, cap, &S->flags, repair.p + 1, repair.p, round, &S->repairs);
         launches += 2;
     }
@@ -548,6 +622,7 @@ long Demod::process(const void *d_raw, long n, int8_t *soft_dst)
     const long n_in = n;
     last_in = n;
     int front_fmt = cfg.format;
+    B200_CUDA(cudaMemsetAsync(&S->flags, 0, sizeof(int), stream)); // per-batch conditions (AGC clamp seen, slot overflow)
     B200_CUDA(cudaEventRecord(ev[0], stream));
     int rs_swap = cfg.iq_swap;
     if (cfg.dc_block) {
@@ -572,7 +647,27 @@ long Demod::process(const void *d_raw, long n, int8_t *soft_dst)
         front_fmt = B200_CF32;
         rs_swap = 0; // already applied
     }
-    if (resamp && !(cfg.dc_block && rs_I == 1 && rs_D == 1 && rs_nt == 1)) {
+    for (auto &stg : decim) {
+        // outputs of this batch: all j >= 0 with inc + j * D < n (the for loop of decimating_fir.cpp:66-76)
+        long J = 0;
+        if (n > stg.inc)
+            J = (n - stg.inc + stg.D - 1) / stg.D;
+        B200_REQUIRE(J >= 64, B200_ESTATE, "batch of %ld samples decimates to %ld: push at least %d samples", n_in, J, 64 * decim_total + 4096);
+        const unsigned grid = (unsigned)((std::max<long>(J, stg.nt) + 255) / 256);
+        if (front_fmt == B200_CF32)
+            k_decim_fir<0><<<grid, 256, 0, stream>>>(d_raw, n, rs_swap, stg.tail[cur].p, stg.tail[nxt].p, stg.d_taps.p, stg.nt, stg.D, stg.inc, J, stg.out.p);
+        else if (front_fmt == B200_CS16)
+            k_decim_fir<1><<<grid, 256, 0, stream>>>(d_raw, n, rs_swap, stg.tail[cur].p, stg.tail[nxt].p, stg.d_taps.p, stg.nt, stg.D, stg.inc, J, stg.out.p);
+        else
+            k_decim_fir<2><<<grid, 256, 0, stream>>>(d_raw, n, rs_swap, stg.tail[cur].p, stg.tail[nxt].p, stg.d_taps.p, stg.nt, stg.D, stg.inc, J, stg.out.p);
+        launches++;
+        stg.inc = stg.inc + J * stg.D - n;
+        d_raw = stg.out.p;
+        n = J;
+        front_fmt = B200_CF32;
+        rs_swap = 0;
+    }
+    if (resamp && !((cfg.dc_block || !decim.empty()) && rs_I == 1 && rs_D == 1 && rs_nt == 1)) {
         // outputs of this batch: all j >= 0 with rs_inc + (rs_ctr + j*D) / I < n  (the while loop of rational_resampler.cpp:48-57)
         const long I = rs_I, D = rs_D;
         long J = 0;
@@ -614,7 +709,7 @@ long Demod::process(const void *d_raw, long n, int8_t *soft_dst)
 
     const int L = choose_L(n);
     const int nseg = (int)((n + L - 1) / L);
-    float2 *mmin = stage_costas(n, L, nseg, cur, nxt);
+    float2 *mmin = stage_costas(n, L, nseg, cur, nxt, cfg.keep_stages != 0);
     B200_CUDA(cudaEventRecord(ev[2], stream));
     stage_mm(mmin, n, L, nseg, cur, nxt, soft_dst ? soft_dst : soft.p, false);
     B200_CUDA(cudaEventRecord(ev[3], stream));
@@ -631,7 +726,7 @@ long Demod::process(const void *d_raw, long n, int8_t *soft_dst)
     total_in += n_in;
     total_syms += last_syms;
     if (h_state->flags & 1)
-        throw ApiError(B200_EUNSUPPORTED, "AGC gain reached max_gain (65536): input is (near) silent; the scan formulation does not cover the clamp");
+        agc_clamped_batches++; // the clamp pass produced this batch's front stage (silent input): information, not an error
     if (h_state->flags & 2)
         throw ApiError(B200_EUNSUPPORTED, "M&M produced more symbols per segment than the omega limit allows (slot overflow)");
     return last_syms;
@@ -670,9 +765,11 @@ long Demod::debug_run_stage(int stage, const float *h_in, long n, int mode, floa
     } else if (stage == B200_STAGE_COSTAS) {
         B200_REQUIRE(order != 0, B200_EINVAL, "this configuration has no Costas loop");
         B200_CUDA(cudaMemcpyAsync(bufA.p + 16, h_in, n * sizeof(float2), cudaMemcpyHostToDevice, stream));
-        src = stage_costas(n, L, nseg, 0, 1) + 16;
+        src = stage_costas(n, L, nseg, 0, 1, true) + 16;
     } else {
         float2 *mmin = order ? bufA.p : bufB.p;
+        mm_quad = nullptr; // the stage input is the clock recovery's input as it is: no rotation, no delay
+        mm_rot = mm_oqpsk = 0;
         B200_CUDA(cudaMemsetAsync(mmin, 0, 16 * sizeof(float2), stream)); // history of a new stream
         B200_CUDA(cudaMemcpyAsync(mmin + 16, h_in, n * sizeof(float2), cudaMemcpyHostToDevice, stream));
         last_L = L;
@@ -705,8 +802,9 @@ void Demod::prefetch_host(const void *h_raw, long n)
         raw2.alloc((size_t)max_batch * fmt_bytes + 64);
     Prefetch *slot = !pf[0].valid ? &pf[0] : (!pf[1].valid ? &pf[1] : nullptr);
     B200_REQUIRE(slot != nullptr, B200_ESTATE, "two prefetched batches are already pending: push one first");
-    slot->buf = pf_next_buf;
-    pf_next_buf ^= 1;
+    // the staging buffer no pending prefetch occupies (pushes may come in any order, so a blind alternation could overwrite one)
+    const Prefetch *other = slot == &pf[0] ? &pf[1] : &pf[0];
+    slot->buf = (other->valid && other->buf == 0) ? 1 : 0;
     B200_CUDA(cudaMemcpyAsync(slot->buf ? raw2.p : raw.p, h_raw, (size_t)n * fmt_bytes, cudaMemcpyHostToDevice, copy_stream));
     B200_CUDA(cudaEventRecord(slot->done, copy_stream));
     slot->ptr = h_raw;
@@ -754,7 +852,7 @@ void Demod::stats(b200_demod_stats *o)
     o->mm_omega = h_state->mm[parity].omega;
     o->costas_unconverged = h_state->costas_unconv;
     o->mm_unconverged = h_state->mm_unconv;
-    o->agc_clamped = h_state->flags & 1;
+    o->agc_clamped = (int)std::min<long>(agc_clamped_batches, 0x7fffffff); // batches in which the gain hit max_gain so far
     o->repairs = h_state->repairs;
     o->kernel_launches = launches;
     o->agc_exact_passes = h_state->agc_exact;
@@ -861,15 +959,39 @@ double b200_demod_final_samplerate(double samplerate, double symbolrate, int con
         final_samplerate = resample ? d_symbolrate * MIN_SPS : d_samplerate;
     return (double)final_samplerate;
 }
+int b200_demod_resample_decision(double samplerate, double symbolrate, int constellation, float min_sps, float max_sps)
+{
+    const long d_samplerate = (long)samplerate;
+    const int d_symbolrate = (int)symbolrate;
+    float MIN_SPS = constellation == B200_OQPSK ? 1.6f : 1.1f, MAX_SPS = constellation == B200_OQPSK ? 2.4f : 4.0f;
+    if (min_sps > 0)
+        MIN_SPS = min_sps;
+    if (max_sps > 0)
+        MAX_SPS = max_sps;
+    if (d_symbolrate <= 0 || d_samplerate <= 0)
+        return 0;
+    const float input_sps = (float)d_samplerate / (float)d_symbolrate;
+    return (input_sps > MAX_SPS || input_sps < MIN_SPS) ? 1 : 0;
+}
 int b200_demod_resampler_bank(double samplerate, double final_samplerate, float *out, long cap, int *ntaps, int *interp, int *decim)
 {
     return guarded([&] {
         B200_REQUIRE(out && ntaps && interp && decim, B200_EINVAL, "NULL argument");
         // the same reduction as the constructor: SmartResamplerBlock(final, input) -> RationalResamplerBlock::set_ratio
-        const unsigned interpolation = (unsigned)(float)final_samplerate, decimation = (unsigned)(long)samplerate;
+        unsigned interpolation = (unsigned)(float)final_samplerate, decimation = (unsigned)(long)samplerate;
         B200_REQUIRE(interpolation > 0 && decimation > 0, B200_EINVAL, "rates must be positive");
-        if (decimation > interpolation)
-            B200_REQUIRE((int)floor(log2((double)(decimation / interpolation))) <= 0, B200_EUNSUPPORTED, "ratio needs the power-of-two decimator");
+        if (decimation > interpolation) { // the rational part behind the power-of-two decimator (smart_resampler.cpp:17-44)
+            const int best_power = (int)floor(log2((double)(decimation / interpolation)));
+            double rsamp_in = decimation, fout = interpolation, t;
+            if (best_power > 0)
+                rsamp_in = (double)decimation / (double)std::min<int>(1 << best_power, 1 << PD_NPLANS);
+            while (modf(rsamp_in, &t) != 0 || modf(fout, &t) != 0) {
+                rsamp_in *= 10;
+                fout *= 10;
+            }
+            interpolation = (unsigned)fout;
+            decimation = (unsigned)rsamp_in;
+        }
         const unsigned g = gcd_u(interpolation, decimation);
         std::vector<float> bank;
         const int nt = design_resampler_bank(interpolation / g, decimation / g, bank);
@@ -895,8 +1017,8 @@ int b200_demod_debug_stage(b200_demod *h, int stage, float *out, long cap_sample
             src = d.fir_dump.p;
         else if (stage == B200_STAGE_COSTAS)
             src = (d.cfg.post_costas_dc ? d.pdc_out.p : (d.order ? d.bufA.p : d.bufB.p)) + 16; // M&M input = Costas output after rotation fix-up (+ post-Costas DC blocker / OQPSK delay)
-        else if (stage == B200_STAGE_RESAMP && d.resamp)
-            src = d.rs_out.p; // what entered the AGC: front-end resampler / iq_swap output
+        else if (stage == B200_STAGE_RESAMP && (d.resamp || !d.decim.empty()))
+            src = d.resamp ? d.rs_out.p : d.decim.back().out.p; // what entered the AGC: front-end decimator / resampler / iq_swap output
         else if (stage == B200_STAGE_DC && d.cfg.dc_block)
             src = d.dc_out.p; // DC blocker output (as many samples as were pushed)
         B200_REQUIRE(src, B200_EINVAL, "unknown stage %d", stage);

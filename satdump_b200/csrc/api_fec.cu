@@ -148,6 +148,7 @@ Fec::Fec(const b200_fec_cfg &c) : cfg(c)
     frames_out.alloc((size_t)(2 * max_frames_push + 4) * cadu_bytes);
     frames_tmp.alloc((size_t)(max_frames_push + 4) * cadu_bytes);
     rs_err.alloc((size_t)(max_frames_push + 4) * std::max(1, cfg.rs_i));
+    frame_dst.alloc((size_t)max_frames_push + 4);
     counters.alloc(8);
     tables.alloc(1);
     B200_CUDA(cudaMallocHost((void **)&h_rec, sizeof(VitRec) * (max_chunks + 1)));
@@ -212,6 +213,8 @@ void Fec::push_device(const int8_t *d, long n)
     process();
 }
 
+constexpr int ACS_DEC_MODE = 0; // decision store of k_vit_acs3: lane 0 writes each step's two ballot words to a shared-memory row (measured fastest: tests/tools/bench_acs.cu)
+
 struct OutChunk { long soft_chunk; int next_start, enc_tail, invalid_after, state_after; VitIdleState idle_st; };
 
 // Viterbi over soft chunks [c0, nch): lock search while IDLE, optimistic parallel decode while SYNCED. Decoded chunks land in
@@ -268,7 +271,7 @@ static void viterbi_segment(Fec &f, long c0, long nch, std::vector<OutChunk> &ou
             f.launches++;
         }
         B200_CUDA(cudaEventRecord(f.evm[0], f.stream));
-        k_vit_acs<<<nb_main, 32 * wpb, 0, f.stream>>>(f.softbuf.p, c, n, f.geom, f.hyp, f.start_state.p, f.dec.p, f.rec.p);
+        k_vit_acs3<true, ACS_DEC_MODE><<<nb_main, 32 * wpb, 0, f.stream>>>(f.softbuf.p, c, n, f.geom, f.hyp, f.start_state.p, f.dec.p, f.rec.p);
         B200_CUDA(cudaEventRecord(f.evm[1], f.stream));
         {
             const long nthr = (long)n * f.tb_blocks;
@@ -356,8 +359,9 @@ void Fec::deframe_and_rs(long new_bits)
         launches++;
         int kept = nf;
         if (filter) {
-            k_frames_filter<<<1, 1024, 0, stream>>>(frames_tmp.p, rs_err.p, nf, cfg.rs_i, cadu_bytes, frames_out.p + out_frames * cadu_bytes, counters.p + 2);
-            launches++;
+            k_frames_filter<<<1, 1024, 0, stream>>>(rs_err.p, nf, cfg.rs_i, frame_dst.p, counters.p + 2);
+            k_frames_gather<<<std::min(nf, 148 * 16), 256, 0, stream>>>(frames_tmp.p, frame_dst.p, nf, cadu_bytes, frames_out.p + out_frames * cadu_bytes);
+            launches += 2;
             B200_CUDA(cudaMemcpyAsync(h_counters + 2, counters.p + 2, sizeof(int), cudaMemcpyDeviceToHost, stream));
         }
         if (cfg.rs_i > 0)

@@ -40,6 +40,7 @@ constexpr int MM_SMEM_BYTES = 64 * SEG_THREADS * 8 + 128 * MM_BANK_STRIDE * 4;
 struct FirTaps { float h[32]; };
 
 struct Affine { double a, b; };     // g -> a*g + b
+struct Affine3 { double a, b, c; }; // g -> min(a*g + b, c): an AGC step with its max_gain clamp (agc.cpp:34-35); closed under composition
 struct DcAff { double a, br, bi; };  // DC blocker: acc -> a*acc + (br, bi)
 
 template <int FMT> struct RawBytes;
@@ -222,6 +223,39 @@ __global__ void __launch_bounds__(RS_THREADS) k_resample(const void *__restrict_
     }
 }
 
+// ---------------------------------------------------------------- K0'': power-of-two decimator stage (SmartResamplerBlock, ratio >= 2)
+// One stage of PowerDecimatorBlock (resamp/power_decim.cpp:37-56) = DecimatingFIRBlock::process (filter/decimating_fir.cpp:46-87): output j
+// is the ntaps-long dot product over the window ending at input sample inc0 + j * D, taps reversed so that taps_rev[0] meets the oldest
+// sample; carried state = inc (phase of the decimation) and the last ntaps - 1 inputs. Buffer index b < nt - 1 is the previous batch's tail,
+// b >= nt - 1 input sample b - (nt - 1), exactly the convention of k_resample (this IS the I = 1 case; a separate kernel because the
+// windows of one CTA span D * 256 + nt samples, too many to stage for D up to 128). One thread per output, inputs through L1 / L2.
+template <int FMT>
+__global__ void __launch_bounds__(256) k_decim_fir(const void *__restrict__ raw, long n_in, int iq_swap, const float2 *__restrict__ tail_in,
+                                                   float2 *__restrict__ tail_out, const float *__restrict__ taps_rev, int nt, int D, long inc0, long J,
+                                                   float2 *__restrict__ out)
+{
+    const long j = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    auto at = [&](long b) {
+        if (b < nt - 1)
+            return tail_in[b];
+        float2 v = load1<FMT>(raw, b - (nt - 1));
+        return iq_swap ? make_float2(v.y, v.x) : v;
+    };
+    if (j < nt - 1) // new tail = buffer[n_in .. n_in + nt - 1)
+        tail_out[j] = at(n_in + j);
+    if (j >= J)
+        return;
+    const long b0 = inc0 + j * D;
+    float re = 0.f, im = 0.f;
+    for (int k = 0; k < nt; k++) {
+        const float2 x = at(b0 + k);
+        const float h = __ldg(taps_rev + k);
+        re = fmaf(x.x, h, re);
+        im = fmaf(x.y, h, im);
+    }
+    out[j] = make_float2(re, im);
+}
+
 // ---------------------------------------------------------------- K0': front-end DC blocker ("dc_block")
 // CorrectIQBlock<complex_t>::work (utils/correct_iq.cpp:18-35): acc = acc*beta + x*alpha; y = x - acc, alpha = 1e-4, beta = 1 - alpha.
 // A constant-coefficient linear recurrence: tiles of 2048 samples, each thread runs the reference's float recurrence over its 8
@@ -393,6 +427,40 @@ __device__ __forceinline__ Affine compose(const Affine &first, const Affine &sec
     return r;
 }
 
+// (second o first)(g) = min(a2 min(a1 g + b1, c1) + b2, c2) = min(a2 a1 g + a2 b1 + b2, min(a2 c1 + b2, c2))   for a2 >= 0
+__device__ __forceinline__ Affine3 compose3(const Affine3 &first, const Affine3 &second)
+{
+    Affine3 r;
+    r.a = second.a * first.a;
+    r.b = fma(second.a, first.b, second.b);
+    r.c = fmin(fma(second.a, first.c, second.b), second.c);
+    return r;
+}
+__device__ __forceinline__ Affine3 warp_scan_inclusive3(Affine3 v, int lane)
+{
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        Affine3 p;
+        p.a = __shfl_up_sync(0xffffffffu, v.a, off);
+        p.b = __shfl_up_sync(0xffffffffu, v.b, off);
+        p.c = __shfl_up_sync(0xffffffffu, v.c, off);
+        if (lane >= off)
+            v = compose3(p, v);
+    }
+    return v;
+}
+constexpr double AGC_MAX_GAIN = 65536.0;  // AGCBlock(..., max_gain = 65536) (module_demod_base.cpp:207)
+constexpr double AGC_NO_CLAMP = 1e30;     // "c" of a map without a clamp (finite, so that a * c + b stays a number)
+struct EBC { float E, B, C; };            // g -> min(g*(1 - E) + B, C), the float form used inside a tile
+__device__ __forceinline__ EBC ebc_compose(const EBC first, const EBC second)
+{
+    EBC r;
+    r.B = fmaf(-second.E, first.B, first.B + second.B);
+    r.E = fmaf(-first.E, second.E, first.E + second.E);
+    r.C = fminf(fmaf(-second.E, first.C, first.C) + second.B, second.C);
+    return r;
+}
+
 __device__ __forceinline__ Affine warp_scan_inclusive(Affine v, int lane)
 {
 #pragma unroll
@@ -446,7 +514,10 @@ struct AgcCtl
 // raises `need` and the exact pass redoes the stage from scanned per-tile seeds. One more tile before the range is replayed
 // without output to provide the 30-sample FIR history.
 // gain_out: gain after the last sample; flags bit0 = AGC clamp hit
-template <int FMT, bool DUMP>
+// CLAMP (third pass, only when an earlier pass saw the gain exceed max_gain, i.e. on (near) silent input): the same kernel with the
+// clamped step maps g -> min(g(1-e) + rate, 65536) composed as (E, B, C) triples and the clamp applied after every replayed step, seeded
+// from the clamp-aware per-tile scan. Exact in the same sense as the unclamped passes.
+template <int FMT, bool DUMP, bool CLAMP>
 __global__ void __launch_bounds__(FIR_THREADS, 5) k_agc_fir(const void *__restrict__ raw, long N, float rate, const float *__restrict__ gain_in, int R,
                                                          const AgcCtl ctl, const FirTaps taps, const float2 *__restrict__ tail_in,
                                                          float2 *__restrict__ tail_out, float2 *__restrict__ fir_out, float2 *__restrict__ agc_dump,
@@ -454,9 +525,13 @@ __global__ void __launch_bounds__(FIR_THREADS, 5) k_agc_fir(const void *__restri
 {
     __shared__ __align__(16) float2 xs[2][FIR_BUF_F2];
     __shared__ EB wsum[2][FIR_THREADS / 32];
+    __shared__ float wsumC[2][FIR_THREADS / 32];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     int *need = ctl.need + (ctl.epoch & 1);
-    if (ctl.seeded) {
+    if (CLAMP) {
+        if ((*flags & 1) == 0)
+            return;
+    } else if (ctl.seeded) {
         if (*need == 0)
             return;
     } else if (blockIdx.x == 0 && t == 0)
@@ -537,7 +612,7 @@ __global__ void __launch_bounds__(FIR_THREADS, 5) k_agc_fir(const void *__restri
     for (int i = i0; i < last; i++) {
         const bool out = i >= first; // tile first-1 only provides the FIR history
         const long s0 = (long)i * FIR_TILE + 8 * t;
-        const bool interior = (long)(i + 1) * FIR_TILE + 32 <= N && !DUMP; // every sample exists, none is in the stream tail
+        const bool interior = (long)(i + 1) * FIR_TILE + 32 <= N && !DUMP && !CLAMP; // every sample exists, none is in the stream tail
         float2 x[8];
         if (s0 + 8 <= N) {
             if (FMT == 0) // cf32: 16 registers of raw data are too many to hold across a tile
@@ -548,6 +623,7 @@ __global__ void __launch_bounds__(FIR_THREADS, 5) k_agc_fir(const void *__restri
         if (FMT != 0 && i + 1 < last && s0 + FIR_TILE + 8 <= N) // next tile's loads fly under this tile's arithmetic
             raw_fetch<FMT>(raw, s0 + FIR_TILE, rr);
         EB inc{0.f, 0.f};
+        float incC = (float)AGC_NO_CLAMP; // CLAMP: third component of the composed map
         float e[8]; // rate * |x|: the step map of sample q is g -> g * (1 - e[q]) + rate
         if (interior)
             inc = agc_map8(x, rate, e);
@@ -559,6 +635,8 @@ __global__ void __launch_bounds__(FIR_THREADS, 5) k_agc_fir(const void *__restri
                     e[q] = rate * fast_mag(fmaf(x[q].x, x[q].x, x[q].y * x[q].y));
                     inc.B = fmaf(-e[q], inc.B, inc.B + rate);
                     inc.E = fmaf(-inc.E, e[q], inc.E + e[q]);
+                    if (CLAMP)
+                        incC = fminf(fmaf(-e[q], incC, incC) + rate, (float)AGC_MAX_GAIN);
                 }
             }
         }
@@ -567,34 +645,60 @@ __global__ void __launch_bounds__(FIR_THREADS, 5) k_agc_fir(const void *__restri
             EB p;
             p.E = __shfl_up_sync(0xffffffffu, inc.E, off);
             p.B = __shfl_up_sync(0xffffffffu, inc.B, off);
+            if (CLAMP) {
+                const float pC = __shfl_up_sync(0xffffffffu, incC, off);
+                if (lane >= off)
+                    incC = fminf(fmaf(-inc.E, pC, pC) + inc.B, incC); // (p then inc), with inc's E, B before they are updated below
+            }
             inc = eb_compose_if(lane >= off, p, inc);
         }
-        if (lane == 31)
+        if (lane == 31) {
             wsum[par][warp] = inc;
+            if (CLAMP)
+                wsumC[par][warp] = incC;
+        }
         __syncthreads();
         // every warp scans the 8 warp aggregates (lanes 0-7 hold them, the rest mirror)
         EB wv = wsum[par][lane & 7];
+        float wvC = CLAMP ? wsumC[par][lane & 7] : 0.f;
         par ^= 1;
 #pragma unroll
         for (int off = 1; off < 8; off <<= 1) {
             EB p;
             p.E = __shfl_up_sync(0xffffffffu, wv.E, off, 8);
             p.B = __shfl_up_sync(0xffffffffu, wv.B, off, 8);
+            if (CLAMP) {
+                const float pC = __shfl_up_sync(0xffffffffu, wvC, off, 8);
+                if ((lane & 7) >= off)
+                    wvC = fminf(fmaf(-wv.E, pC, pC) + wv.B, wvC);
+            }
             wv = eb_compose_if((lane & 7) >= off, p, wv);
         }
         EB tot, excl{0.f, 0.f};
+        float totC = 0.f, exclC = (float)AGC_NO_CLAMP;
         tot.E = __shfl_sync(0xffffffffu, wv.E, 7);
         tot.B = __shfl_sync(0xffffffffu, wv.B, 7);
+        if (CLAMP)
+            totC = __shfl_sync(0xffffffffu, wvC, 7);
         {
             EB p;
             p.E = __shfl_sync(0xffffffffu, wv.E, (warp + 7) & 7);
             p.B = __shfl_sync(0xffffffffu, wv.B, (warp + 7) & 7);
             excl.E = warp > 0 ? p.E : 0.f;
             excl.B = warp > 0 ? p.B : 0.f;
+            float pC = (float)AGC_NO_CLAMP, qC = (float)AGC_NO_CLAMP;
+            if (CLAMP) {
+                pC = __shfl_sync(0xffffffffu, wvC, (warp + 7) & 7);
+                pC = warp > 0 ? pC : (float)AGC_NO_CLAMP;
+                qC = __shfl_up_sync(0xffffffffu, incC, 1);
+                qC = lane > 0 ? qC : (float)AGC_NO_CLAMP;
+            }
             p.E = __shfl_up_sync(0xffffffffu, inc.E, 1);
             p.B = __shfl_up_sync(0xffffffffu, inc.B, 1);
             p.E = lane > 0 ? p.E : 0.f; // identity map in lane 0
             p.B = lane > 0 ? p.B : 0.f;
+            if (CLAMP)
+                exclC = fminf(fmaf(-p.E, pC, pC) + p.B, qC); // (warps before) then (lanes before)
             excl = eb_compose(excl, p);
         }
         // per-sample gains from the scanned seed with the same step maps: g' = g*(1 - e) + rate is the reference's
@@ -604,6 +708,10 @@ __global__ void __launch_bounds__(FIR_THREADS, 5) k_agc_fir(const void *__restri
         const float Gf = (float)G;
         float g = fmaf(-excl.E, Gf, Gf) + excl.B;
         G = fma(1.0 - (double)tot.E, G, (double)tot.B);
+        if (CLAMP) {
+            g = fminf(g, exclC);
+            G = fmin(G, (double)totC);
+        }
         float gmax = g;
         if (interior) {
 #pragma unroll
@@ -633,7 +741,7 @@ __global__ void __launch_bounds__(FIR_THREADS, 5) k_agc_fir(const void *__restri
                 x[q] = o;
             }
         }
-        if (gmax > 65536.0f)
+        if (!CLAMP && gmax > 65536.0f)
             atomicOr(flags, 1);
         {
             float4 *dst = reinterpret_cast<float4 *>(&xs[buf][10 * t + 40]);
@@ -725,6 +833,86 @@ __global__ void __launch_bounds__(FIR_THREADS) k_agc_compose(const void *__restr
         }
         __syncthreads();
     }
+}
+
+// clamp-aware versions of the two kernels above (run only when the flag says the gain hit max_gain in this batch)
+template <int FMT>
+__global__ void __launch_bounds__(FIR_THREADS) k_agc_compose3(const void *__restrict__ raw, long N, float rate, const int *__restrict__ flags, int ntiles,
+                                                              Affine3 *__restrict__ tile_map)
+{
+    if ((*flags & 1) == 0)
+        return;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    __shared__ Affine3 wsum[FIR_THREADS / 32];
+    for (int k = blockIdx.x; k < ntiles; k += gridDim.x) {
+        const long s0 = (long)k * FIR_TILE + 8 * t;
+        Affine3 m{1.0, 0.0, AGC_NO_CLAMP};
+        float2 x[8];
+        load8<FMT>(raw, s0, N, x);
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            if (s0 + i < N) {
+                const float mag = fast_mag(fmaf(x[i].x, x[i].x, x[i].y * x[i].y));
+                m = compose3(m, Affine3{1.0 - (double)rate * (double)mag, (double)rate, AGC_MAX_GAIN});
+            }
+        m = warp_scan_inclusive3(m, lane);
+        if (lane == 31)
+            wsum[warp] = m;
+        __syncthreads();
+        if (t == 0) {
+            Affine3 tot = wsum[0];
+            for (int w = 1; w < FIR_THREADS / 32; w++)
+                tot = compose3(tot, wsum[w]);
+            tile_map[k] = tot;
+        }
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(1024) k_agc_scan3(const Affine3 *__restrict__ tile_map, int ntiles, const float *__restrict__ gain_in,
+                                                   const int *__restrict__ flags, double *__restrict__ seeds)
+{
+    if ((*flags & 1) == 0)
+        return;
+    __shared__ Affine3 wsum[32];
+    __shared__ double g_run;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    if (t == 0)
+        g_run = (double)*gain_in;
+    __syncthreads();
+    for (int base = 0; base < ntiles; base += 1024) {
+        const int k = base + t;
+        Affine3 m{1.0, 0.0, AGC_NO_CLAMP};
+        if (k < ntiles)
+            m = tile_map[k];
+        const Affine3 inc = warp_scan_inclusive3(m, lane);
+        if (lane == 31)
+            wsum[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            Affine3 w = warp_scan_inclusive3(wsum[lane], lane);
+            wsum[lane] = w;
+        }
+        __syncthreads();
+        Affine3 pre{1.0, 0.0, AGC_NO_CLAMP};
+        if (warp > 0)
+            pre = wsum[warp - 1];
+        Affine3 e;
+        e.a = __shfl_up_sync(0xffffffffu, inc.a, 1);
+        e.b = __shfl_up_sync(0xffffffffu, inc.b, 1);
+        e.c = __shfl_up_sync(0xffffffffu, inc.c, 1);
+        const Affine3 excl = lane > 0 ? compose3(pre, e) : pre;
+        const double g0 = g_run;
+        if (k < ntiles)
+            seeds[k] = fmin(fma(excl.a, g0, excl.b), excl.c);
+        __syncthreads();
+        if (t == 1023) {
+            const Affine3 tot = compose3(pre, inc);
+            g_run = fmin(fma(tot.a, g0, tot.b), tot.c);
+        }
+        __syncthreads();
+    }
+    if (t == 0)
+        seeds[ntiles] = g_run;
 }
 
 __global__ void __launch_bounds__(1024) k_agc_scan(const Affine *__restrict__ tile_map, int ntiles, const float *__restrict__ gain_in,
@@ -1193,6 +1381,21 @@ __global__ void k_rotate(const float2 *__restrict__ src, long N, int L, int orde
     }
 }
 
+// Fused path (k_mm applies the rotation itself): only the 8-sample history moves. src has a 16-sample front pad: src[16 + n].
+__global__ void k_mm_prep(float2 *__restrict__ src, long N, int L, int order, const uint8_t *__restrict__ quad, const float2 *__restrict__ hist_in,
+                          float2 *__restrict__ hist_out)
+{
+    const int t = threadIdx.x;
+    if (t >= 8)
+        return;
+    src[8 + t] = hist_in[t]; // the previous batch's last 8 inputs, already in their final orientation (segment 0 never rotates)
+    const long n = N - 8 + t;
+    float2 v = src[16 + n];
+    if (order)
+        v = rot_steps(v, quad[n / L], order);
+    hist_out[t] = v;
+}
+
 // ---------------------------------------------------------------- K3: Mueller & Mueller clock recovery, one thread per segment
 #endif // B200_DEFINE_KERNELS
 struct MMParams
@@ -1218,10 +1421,14 @@ struct MMRec { int u_final, count, skip, pad; float mu_final, omega_final; int h
 // segment on the oracle's own M&M input the symbols must come out BITWISE the oracle's. The production instantiation keeps the
 // two-chain FMA interpolator.
 template <bool STRICT>
+// Fused input fix-up (rot_order != 0 or oqpsk): mmin is then the Costas loop's raw output, and every thread applies the exact
+// rotation by its row's quad[] entry (and the OQPSK one-sample delay of the imaginary rail, delay_one_imag.cpp:18-25) to each 16-sample
+// row of its ring right after the row has landed, instead of a separate pass over the whole stream (k_rotate).
 __global__ void __launch_bounds__(SEG_THREADS) k_mm(const float2 *__restrict__ mmin /* 16-sample front pad */, long N, int L, int W, int G, int nseg,
                                                      MMParams P, const MMState *__restrict__ st_in, MMState *__restrict__ st_out,
                                                      const float *__restrict__ bank /*128x8*/, float2 *__restrict__ slots, int cap,
-                                                     MMRec *__restrict__ rec, const int *__restrict__ repair_list, const int *__restrict__ repair_count)
+                                                     MMRec *__restrict__ rec, const int *__restrict__ repair_list, const int *__restrict__ repair_count,
+                                                     const uint8_t *__restrict__ quad, int rot_order, int oqpsk)
 {
     extern __shared__ __align__(16) unsigned char mm_smem[];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -1270,6 +1477,8 @@ __global__ void __launch_bounds__(SEG_THREADS) k_mm(const float2 *__restrict__ m
         const long a = u - 7;
         r0 = (int)((a >= 0) ? (a >> 4) : -((-a + 15) >> 4));
     }
+    if (oqpsk)
+        r0 -= 1; // one more row in front: its last sample's imaginary part is the delay register of the first row that is used
     const int rend = (int)((own1 + 15) >> 4); // exclusive: samples < own1 <= N are ever needed
     // iteration `it` makes row r0+it+1 the newest complete row; symbols with u < 16*(r0+it+2) can then be produced
     int nit = active ? max(0, rend - r0) : 0, maxit = nit;
@@ -1280,6 +1489,34 @@ __global__ void __launch_bounds__(SEG_THREADS) k_mm(const float2 *__restrict__ m
     auto load = [&](int row, bool ok) { warp_load_rows(ring, -1, 31, base, row, ok && row < rend, N, lane); cp_async_commit(); };
     load(r0, active);
     load(r0 + 1, active);
+    float carry_im = 0.f; // OQPSK: imaginary part (after rotation) of the sample in front of the next row
+    auto fixrow = [&](int row) {
+        if (!active || row >= rend || (!rot_order && !oqpsk))
+            return;
+        int q = 0;
+        if (rot_order && row >= 0)
+            q = quad[(16 * row) / L];
+        if (q == 0 && !oqpsk)
+            return;
+        const int sb = (row << 3) + 64;
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            const int idx = swz16((sb + c) & 31, lane);
+            float4 v = ring[idx];
+            float2 a = make_float2(v.x, v.y), b = make_float2(v.z, v.w);
+            if (q) {
+                a = rot_steps(a, q, rot_order);
+                b = rot_steps(b, q, rot_order);
+            }
+            if (oqpsk) {
+                const float ta = a.y, tb = b.y;
+                a.y = carry_im;
+                b.y = ta;
+                carry_im = tb;
+            }
+            ring[idx] = make_float4(a.x, a.y, b.x, b.y);
+        }
+    };
     int count = 0;
     MMRec mr;
 #pragma unroll
@@ -1293,6 +1530,9 @@ __global__ void __launch_bounds__(SEG_THREADS) k_mm(const float2 *__restrict__ m
         load(rr + 1, active);
         cp_async_wait<1>(); // rows <= rr complete
         __syncwarp();
+        if (it == 0)
+            fixrow(r0);
+        fixrow(rr);
         if (!done) {
             const long lim = min((long)(rr + 1) << 4, own1);
             while (u < lim) {

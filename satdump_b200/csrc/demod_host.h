@@ -43,7 +43,9 @@ class Demod
     void stats(b200_demod_stats *out);
     void reset(); // back to the state of a freshly created demodulator (new stream)
     // stages of process(), also run alone by the stage-isolated parity hook
-    float2 *stage_costas(long n, int L, int nseg, int cur, int nxt);
+    float2 *stage_costas(long n, int L, int nseg, int cur, int nxt, bool materialise);
+    const uint8_t *mm_quad = nullptr; // set by stage_costas when the clock recovery applies the rotation (/ OQPSK delay) itself
+    int mm_rot = 0, mm_oqpsk = 0;
     void stage_mm(float2 *mmin, long n, int L, int nseg, int cur, int nxt, int8_t *sdst, bool strict);
     long debug_run_stage(int stage, const float *h_in, long n, int mode, float *h_out, long cap);
     int last_L = 0, last_nseg = 0;          // segmentation of the last batch (b200_demod_debug_junctions)
@@ -68,6 +70,8 @@ class Demod
     int pf_next_buf = 0;
     DevBuf<float2> bufA, bufB, agc_dump, fir_dump, slots, sym_out;
     DevBuf<int8_t> soft;
+    DevBuf<Affine3> tile_map3;     // clamp pass (silent input): per-tile maps with the max_gain clamp
+    long agc_clamped_batches = 0;
     DevBuf<Affine> tile_map;       // exact AGC pass (weak signals): per-tile maps,
     DevBuf<double> seeds;          // gain before every tile
     DevBuf<int> agc_need;          // [2] raised by the fast pass when a range cannot prove its seed
@@ -80,6 +84,19 @@ class Demod
     std::vector<float> rs_bank;
     DevBuf<float> d_rs_bank;
     DevBuf<float2> rs_out;
+    // power-of-two decimator in front of the rational resampler (SmartResamplerBlock with samplerate / final_samplerate >= 2)
+    struct DecimStage
+    {
+        int D = 1, nt = 0;
+        long inc = 0;                  // carried decimation phase (decimating_fir.h: inc)
+        std::vector<float> taps_rev;
+        DevBuf<float> d_taps;
+        DevBuf<float2> tail[2], out;   // last nt - 1 inputs by batch parity; stage output (cf32)
+        DecimStage() = default;
+        DecimStage(DecimStage &&o) noexcept : D(o.D), nt(o.nt), inc(o.inc), taps_rev(std::move(o.taps_rev)) {}
+    };
+    std::vector<DecimStage> decim;
+    int decim_total = 1;
     long max_work = 0;             // largest sample count after the front end
     DevBuf<DcAff> dc_map;          // DC blocker: per-tile maps, per-tile accumulators, output (cf32)
     DevBuf<double2> dc_seeds;

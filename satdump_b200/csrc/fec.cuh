@@ -1303,9 +1303,10 @@ __global__ void __launch_bounds__(256) k_frames(const uint32_t *__restrict__ fif
     }
 }
 
-// rs_usecheck: keep only frames whose interleaves all decoded (module_ccsds_conv_concat_decoder.cpp:183-195); single CTA
-__global__ void __launch_bounds__(1024) k_frames_filter(const uint8_t *__restrict__ in, const int *__restrict__ rs_err, int nframes, int rs_i, int cadu_bytes,
-                                                       uint8_t *__restrict__ out, int *__restrict__ nkept)
+// rs_usecheck: keep only frames whose interleaves all decoded (module_ccsds_conv_concat_decoder.cpp:183-195). k_frames_filter: single CTA,
+// exclusive scan of the keep flags -> destination index of every frame (-1: dropped) and the number kept; k_frames_gather: one CTA per
+// frame copies it (coalesced) to its place.
+__global__ void __launch_bounds__(1024) k_frames_filter(const int *__restrict__ rs_err, int nframes, int rs_i, int *__restrict__ dst_index, int *__restrict__ nkept)
 {
     __shared__ int wsum[32];
     __shared__ int run;
@@ -1331,16 +1332,23 @@ __global__ void __launch_bounds__(1024) k_frames_filter(const uint8_t *__restric
         }
         __syncthreads();
         const int incl = run + v + (warp > 0 ? wsum[warp - 1] : 0);
-        if (ok) {
-            const uint8_t *s = in + (long)f * cadu_bytes;
-            uint8_t *d = out + (long)(incl - 1) * cadu_bytes;
-            for (int i = 0; i < cadu_bytes; i++) d[i] = s[i];
-        }
+        if (f < nframes) dst_index[f] = ok ? incl - 1 : -1;
         __syncthreads();
         if (t == 1023) run = incl;
         __syncthreads();
     }
     if (t == 0) *nkept = run;
+}
+__global__ void __launch_bounds__(256) k_frames_gather(const uint8_t *__restrict__ in, const int *__restrict__ dst_index, int nframes, int cadu_bytes,
+                                                       uint8_t *__restrict__ out)
+{
+    for (int f = blockIdx.x; f < nframes; f += gridDim.x) {
+        const int d = dst_index[f];
+        if (d < 0) continue;
+        const uint8_t *s = in + (long)f * cadu_bytes;
+        uint8_t *o = out + (long)d * cadu_bytes;
+        for (int i = threadIdx.x; i < cadu_bytes; i += blockDim.x) o[i] = s[i];
+    }
 }
 
 #endif // B200_DEFINE_KERNELS

@@ -43,7 +43,7 @@ class Fec
     DevBuf<uint2> dec;
     DevBuf<uint2> idle_dec;
     DevBuf<uint32_t> chunk_bits, fifo;
-    DevBuf<int> start_state, rs_err, counters;
+    DevBuf<int> start_state, rs_err, counters, frame_dst; // frame_dst: destination index of every frame under rs_usecheck
     DevBuf<VitRec> rec;
     DevBuf<TbEdge> tb_edges;
     DevBuf<int> tb_list; // [0] count of chunks redone serially in the last launch, [1..] their indices

@@ -58,7 +58,7 @@ int ByteFifo::read(uint8_t *data, int len)
     while (done < len) {
         can_read.wait(lk, [&] { return fill > 0 || stop_r; });
         if (stop_r && fill == 0)
-            return -1;
+            return done > 0 ? done : -1; // end of stream in the middle of a read: hand over what arrived (the caller sees -1 next time)
         size_t n = std::min<size_t>(len - done, fill), first = std::min(n, buf.size() - head);
         memcpy(data + done, &buf[head], first);
         memcpy(data + done + first, &buf[0], n - first);
@@ -89,6 +89,16 @@ void ByteFifo::stopWriter()
         stop_w = true;
     }
     can_write.notify_all();
+}
+
+// A junction of the segment-parallel loops that is still inconsistent after the repair rounds means this batch's output may differ
+// from the sequential reference around that junction (expected never; b200_demod_stats counts them). The reference's process() has
+// no error channel, so this goes where its logger->warn would.
+static void warn_unconverged(const b200_demod_stats &st)
+{
+    if (st.costas_unconverged > 0 || st.mm_unconverged > 0)
+        fprintf(stderr, "[b200] warning: %ld Costas / %ld clock-recovery segment junction(s) did not converge in the last batch (after %d repairs so far); "
+                        "output around them may deviate from the sequential loop\n", st.costas_unconverged, st.mm_unconverged, st.repairs);
 }
 
 // ------------------------------------------------------------------------------------------------ parameter mapping
@@ -155,6 +165,8 @@ b200_demod_cfg demod_cfg_from_params(const Params &p, bool &is_bpsk)
                                                      p.has("custom_samplerate") ? (double)(long)p.num("custom_samplerate") : 0.0);
     if (c.final_samplerate == c.samplerate)
         c.final_samplerate = 0;
+    else if (!b200_demod_resample_decision(c.samplerate, c.symbolrate, c.constellation, (float)p.num("min_sps", 0), (float)p.num("max_sps", 0)))
+        c.front_resample = 2; // custom_samplerate with an in-window sps: the reference designs its filters for it but does not resample
     if ((float)c.samplerate / (float)c.symbolrate < 1.0f) // module_demod_base.cpp:96-105
         throw ModuleError("Your sampling rate is too low! Minimum: " +
                           (c.symbolrate > 1e6 ? std::to_string(c.symbolrate / 1e6) + " Msps" : std::to_string(c.symbolrate / 1e3) + " ksps"));
@@ -309,7 +321,7 @@ void PskDemodStage::process()
             // DATA_STREAM input of raw baseband bytes (the reference feeds a dsp::stream<complex_t> here; a byte FIFO of the
             // configured baseband_format is the C-ABI friendly equivalent)
             int want = (int)std::min<size_t>(raw.size() - have, 1 << 20);
-            int r = input_fifo->read(raw.data() + have, want);
+            int r = input_fifo->read(raw.data() + have, want); // a short count = the writer stopped: the stream's last bytes
             got = r < 0 ? 0 : (size_t)r;
         }
         if (got == 0)
@@ -332,6 +344,8 @@ void PskDemodStage::process()
         done += used;
         progress = filesize ? (double)done / (double)filesize : 0.0;
         b200_demod_stats st;
+        if (b200_demod_get_stats(h, &st) == B200_OK)
+            warn_unconverged(st);
         if (b200_demod_get_stats(h, &st) == B200_OK)
             freq = st.costas_freq * (cfg.final_samplerate > 0 ? cfg.final_samplerate : cfg.samplerate) / (2.0 * M_PI); // rad_to_hz(freq, final_samplerate), module_psk_demod.cpp:196
     }
@@ -464,6 +478,12 @@ void FusedStage::process()
         if (ns < min_batch)
             break;
         check(b200_chain_push_iq(h, raw.data(), ns), "b200_chain_push_iq");
+        {
+            b200_demod_stats dst;
+            b200_fec_stats fst;
+            if (b200_chain_get_stats(h, &dst, &fst) == B200_OK)
+                warn_unconverged(dst);
+        }
         drain();
         size_t used = (size_t)ns * bpsamp;
         memmove(raw.data(), raw.data() + used, have - used);

@@ -218,6 +218,12 @@ CONFIGS = {
     # 8PSK through psk_demod alone (order-8 Costas loop; no decoder of this path takes 8PSK): demodulator parity only
     "psk8": SignalCfg(name="psk8", samplerate=6e6, symbolrate=2400000, constellation="8psk", conv="none", interleave=4, fmt="cs16",
                       decoder="demod", esn0_db=18.0),
+    # MetOp AHRPT recorded at 24 MS/s: 10.3 samples/symbol -> BaseDemodModule resamples to 8 MS/s (round(2333333 / 1e6) * 1e6 * MAX_SPS), a
+    # ratio of 3, so SmartResamplerBlock runs its power-of-two decimator (x2: one 69-tap stage) and then the rational resampler 2/3
+    "metop_oversampled": SignalCfg(name="metop_oversampled", samplerate=24e6),
+    # BPSK r=1/2 at 1 Msym/s recorded at 32 MS/s in cs8: ratio 8 -> power-of-two decimator alone (stages /4 and /2), no rational part
+    "bpsk_decim8": SignalCfg(name="bpsk_decim8", samplerate=32e6, symbolrate=1000000, constellation="bpsk", conv="1/2", interleave=4,
+                             fmt="cs8", decoder="ccsds", ber_thresold=0.3, outsync_after=20, esn0_db=9.0),
     # C5: DVB-S2 front half AGC->RRC->M&M, cs8, 45 Msym/s @ 90 MS/s (sps 2.0), alpha 0.25 (DVB_Test.json:132-137), REC_ALPHA 1.7e-3
     "dvbs2_front": SignalCfg(name="dvbs2_front", samplerate=90e6, symbolrate=45000000, constellation="qpsk", conv="none", interleave=4,
                              rrc_alpha=0.25, fmt="cs8", decoder="none", clock_alpha=1.7e-3, carrier_rad=0.0, phase0=0.0, esn0_db=12.0),

@@ -48,7 +48,7 @@ def ulp_perturb(x, seed):
 def diff_stats(a, b):
     assert a.size == b.size, (a.size, b.size)
     d = np.abs(a - b)
-    return dict(frac=float((d > 1e-5).mean()), max=float(d.max()), mean=float(d.mean()))
+    return dict(frac=float((d > 1e-5).mean()), max=float(d.max()), mean=float(d.mean()), median=float(np.median(d)))
 
 
 def soft_stats(a, b):
@@ -66,10 +66,11 @@ def quantise(sym, bpsk):
 
 
 @functools.lru_cache(maxsize=64)
-def reference_run(name, log2n):
+def reference_run(name, log2n, extra=()):
+    """`extra`: further demodulator options as a tuple of (key, value) pairs, e.g. (("post_costas_dc", True),)"""
     O = _O()
     cfg, raw, _ = signal(name, log2n)
-    oc = O.demod_cfg(**demod_kwargs(cfg))
+    oc = O.demod_cfg(**demod_kwargs(cfg), **dict(extra))
     return cfg, raw, oc, O.Demod(oc).run(raw)
 
 
@@ -78,10 +79,10 @@ def _worst(stats):
 
 
 @functools.lru_cache(maxsize=128)
-def stage_floor(name, log2n, stage, eps=1e-6, seeds=(1, 2, 3, 4, 5, 6, 7, 8)):
+def stage_floor(name, log2n, stage, eps=1e-6, seeds=(1, 2, 3, 4, 5, 6, 7, 8), extra=()):
     """Worst deviation of the reference's `stage` output ("costas" / "mm") from itself when its stage input is perturbed."""
     O = _O()
-    cfg, raw, oc, o = reference_run(name, log2n)
+    cfg, raw, oc, o = reference_run(name, log2n, extra)
     src = o["fir"] if (stage == "costas" or o["costas"] is None) else o["costas"]
     want = o[stage]
     out = []
@@ -95,11 +96,11 @@ def stage_floor(name, log2n, stage, eps=1e-6, seeds=(1, 2, 3, 4, 5, 6, 7, 8)):
 
 
 @functools.lru_cache(maxsize=64)
-def chain_floor(name, log2n, eps=1e-6, seeds=(1, 2, 3)):
+def chain_floor(name, log2n, eps=1e-6, seeds=(1, 2, 3), extra=()):
     """Worst deviation of the reference's Costas / M&M / soft outputs from themselves when the AGC output is perturbed by eps, and
     when the reference is built with its release flags (FMA contraction)."""
     O = _O()
-    cfg, raw, oc, o = reference_run(name, log2n)
+    cfg, raw, oc, o = reference_run(name, log2n, extra)
     bpsk = o["soft"].size == o["mm"].size
     runs = []
     for sd in seeds:
@@ -125,13 +126,13 @@ def chain_floor(name, log2n, eps=1e-6, seeds=(1, 2, 3)):
     w = _worst(runs)
     # the chain cannot be better than its stages fed a perturbed input directly (the loops' rare events are a matter of which
     # samples the perturbation happens to hit: take the worst of both injection points)
-    m = stage_floor(name, log2n, "mm", eps)
+    m = stage_floor(name, log2n, "mm", eps, extra=extra)
     for k in ("frac", "max"):
         w["mm_" + k] = max(w["mm_" + k], m[k])
     for k in ("diff", "gt1", "max"):
         w["soft_" + k] = max(w["soft_" + k], m["soft_" + k])
     if o["costas"] is not None:
-        c = stage_floor(name, log2n, "costas", eps)
+        c = stage_floor(name, log2n, "costas", eps, extra=extra)
         for k in ("frac", "max", "mean"):
             w["costas_" + k] = max(w["costas_" + k], c[k])
     return w

@@ -36,8 +36,6 @@ def test_struct_layouts_match_header(built):
 def test_parameter_validation_mirrors_reference_modules(built):
     from satdump_b200 import capi
     bad = [
-        # sps 25.7 -> the reference decimates 6 MS/s to 0.8 MS/s: needs SmartResamplerBlock's power-of-two decimator (tap tables not built)
-        (dict(samplerate=6e6, symbolrate=233333, constellation="qpsk", rrc_alpha=0.5), "decimator"),
         (dict(samplerate=6e6, symbolrate=233333, constellation="qpsk", rrc_alpha=0.5, final_samplerate=0), -1),  # resampler forced off
         (dict(samplerate=6e6, symbolrate=2333333, constellation="qpsk", rrc_alpha=0.5, rrc_taps=63), -1),
         (dict(samplerate=0, symbolrate=2333333, constellation="qpsk", rrc_alpha=0.5), -1),

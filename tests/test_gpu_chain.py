@@ -6,7 +6,7 @@ import pytest
 from tests.common import gpu_chain, match_frames, nsamples, oracle, oracle_demod, oracle_fec, signal
 
 pytestmark = pytest.mark.gpu
-DECODED = ["metop_ahrpt", "bpsk_half", "jpss_hrd", "hrpt_bpsk", "bpsk_simple", "qpsk_simple"]
+DECODED = ["metop_ahrpt", "bpsk_half", "jpss_hrd", "hrpt_bpsk", "metop_oversampled", "bpsk_decim8", "bpsk_simple", "qpsk_simple"]
 
 
 @pytest.mark.parametrize("name", DECODED)

@@ -17,7 +17,7 @@ from tests.common import gpu_demod, nsamples, oracle, oracle_demod, signal
 from tests.floors import SURVEY, chain_floor, gate
 
 pytestmark = pytest.mark.gpu
-CONFIGS = ["metop_ahrpt", "bpsk_half", "jpss_hrd", "dvbs2_front", "hrpt_bpsk", "psk8"]
+CONFIGS = ["metop_ahrpt", "bpsk_half", "jpss_hrd", "dvbs2_front", "hrpt_bpsk", "psk8", "metop_oversampled", "bpsk_decim8"]
 
 
 def check_mm(gs, om, gsoft=None, osoft=None, floor=None):
@@ -39,7 +39,7 @@ def check_mm(gs, om, gsoft=None, osoft=None, floor=None):
 
 def check_costas(g, o, floor):
     d = np.abs(g - o)
-    assert d.mean() <= 2e-6, float(d.mean())
+    assert np.median(d) <= 1e-6, float(np.median(d))  # nothing systematic (the mean would count the rare sign-decision events)
     # the 1e-5 of the survey with the margin the AGC's own deviation needs (measured max 1.3e-5 on BPSK), or the reference's event floor
     assert (d > 1e-5).mean() <= gate(1e-5, floor.get("costas_frac", 0.0)), (float((d > 1e-5).mean()), floor)
     assert d.max() <= gate(2e-5, floor.get("costas_max", 0.0)), (float(d.max()), floor)
@@ -253,7 +253,7 @@ def test_post_costas_dc(built):
     n = nsamples(raw, cfg)
     o = O.Demod(O.demod_cfg(post_costas_dc=True, **demod_kwargs(cfg))).run(raw)
     g = capi.Demod(capi.demod_cfg(max_batch=n, keep_stages=True, post_costas_dc=True, **demod_kwargs(cfg))).push(raw)
-    fl = chain_floor("bpsk_half", 20)  # (the floor of the chain without the block: the block is linear)
+    fl = chain_floor("bpsk_half", 20, extra=(("post_costas_dc", True),))
     check_costas(g.stage("costas"), o["costas"], fl)
     check_mm(g.symbols(), o["mm"], g.soft(), o["soft"], floor=fl)
     g2 = capi.Demod(capi.demod_cfg(max_batch=n, keep_stages=True, post_costas_dc=True, **demod_kwargs(cfg)))
@@ -278,12 +278,31 @@ def test_errors_are_loud(built):
         g.push(raw[:40])  # below the minimum batch
 
 
-def test_silent_input_is_reported_not_guessed(built):
-    """All-zero baseband drives the AGC into its max_gain clamp (agc.cpp:34-35), which the scan formulation does not model."""
-    from satdump_b200 import capi
-    cfg, _, _ = signal("metop_ahrpt", 16)
-    n = 1 << 23
-    g = gpu_demod(cfg, n)
-    with pytest.raises(capi.B200Error) as e:
-        g.push(np.zeros(2 * n, np.int16))
-    assert e.value.code == -6
+def test_silent_input_runs_into_the_agc_clamp_like_the_reference(built):
+    """All-zero baseband drives the AGC into its max_gain clamp after 6.55 M samples (agc.cpp:34-35); when the signal comes back the
+    gain falls from exactly 65536. The clamp pass (step maps g -> min(g(1-e) + rate, 65536) composed as triples) follows the
+    reference through the silence, the clamp and the recovery, also across a batch boundary inside the silence."""
+    O = oracle()
+    cfg, sig, _ = signal("metop_ahrpt", 21)
+    raw = np.concatenate([np.zeros(2 * (1 << 23), np.int16), sig])
+    n = raw.size // 2
+    o = oracle_demod(O, cfg).run(raw)
+    for cuts in ([n], [5000000, (1 << 23) + 4099, n]):
+        g = gpu_demod(cfg, n, keep_stages=True)
+        agc, fir, prev = [], [], 0
+        for c in cuts:
+            g.push(raw[2 * prev:2 * c])
+            agc.append(g.stage("agc"))
+            fir.append(g.stage("fir"))
+            prev = c
+        agc, fir = np.concatenate(agc), np.concatenate(fir)
+        scale = np.maximum(1.0, np.abs(o["agc"]))
+        assert (np.abs(agc - o["agc"]) / scale).max() <= 1e-5, float((np.abs(agc - o["agc"]) / scale).max())
+        fscale = np.maximum(1.0, np.abs(o["fir"]))
+        assert (np.abs(fir - o["fir"]) / fscale).max() <= 2e-5
+        assert np.abs(o["agc"]).max() > 1000  # the recovery really starts from a huge gain
+        s = g.stats()
+        assert s["agc_clamped"] >= 1
+        ost = oracle_demod(O, cfg)
+        ost.run(raw, stages=False)
+        assert abs(s["agc_gain"] - ost.state()["gain"]) <= 1e-4 * ost.state()["gain"]

@@ -55,7 +55,7 @@ def test_costas_fed_the_oracles_fir_output(built, name):
     assert d["max"] <= SURVEY["float_all"], d
     fl = stage_floor(name, LG, "costas")
     d = diff_stats(g.run_stage("costas", o["fir"]), o["costas"])
-    assert d["mean"] <= 2e-6, d  # nothing systematic
+    assert d["median"] <= 1e-6, d  # nothing systematic (the mean would count the rare sign-decision events)
     assert d["frac"] <= gate(0.0, fl["frac"]) + 1e-5 and d["max"] <= gate(SURVEY["float_all"], fl["max"]) * (2 if fl["frac"] == 0 else 1), (d, fl)
 
 

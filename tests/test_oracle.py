@@ -9,7 +9,7 @@ from tests.common import ROOT, oracle_demod, oracle_fec, signal, simple_soft_cas
 from satdump_b200 import synth
 
 GOLD = os.path.join(ROOT, "tests", "golden")
-CONFIGS = ["metop_ahrpt", "bpsk_half", "jpss_hrd", "dvbs2_front", "hrpt_bpsk", "qpsk_undersampled", "psk8", "bpsk_simple", "qpsk_simple"]
+CONFIGS = ["metop_ahrpt", "bpsk_half", "jpss_hrd", "dvbs2_front", "hrpt_bpsk", "metop_oversampled", "bpsk_decim8", "qpsk_undersampled", "psk8", "bpsk_simple", "qpsk_simple"]
 
 
 def _ref():
@@ -206,7 +206,7 @@ def test_simple_psk_decoder_options_port_equals_reference(built):
 
 def test_resampler_port_equals_reference_over_rates_and_formats(built):
     """The front-end resampler restatement vs the reference over decimating and interpolating ratios, every sample format, with and
-    without iq_swap / dc_block; ratios that need the power-of-two decimator are refused by the restatement (returns no handle)."""
+    without iq_swap / dc_block, and over ratios that put the power-of-two decimator in front."""
     ref = _ref()
     from oracle import port
     rng = np.random.default_rng(5)
@@ -231,6 +231,14 @@ def test_resampler_port_equals_reference_over_rates_and_formats(built):
         bank, i, d = capi.resampler_bank(fs, fin)
         want = ref.resampler_taps(int(fin), int(fs))
         assert bank.shape == want.shape and bitwise(bank, want), (fs, rs, i, d)
-    cfg = ref.demod_cfg(6e6, 233333, "qpsk", 0.5)  # 6 MS/s -> 0.8 MS/s: needs the decimator
-    assert cfg.samplerate / cfg.final_samplerate >= 2
-    assert not port.lib().ref_demod_create(cfg)
+    # ratios >= 2: SmartResamplerBlock's power-of-two decimator in front (one to three DecimatingFIR stages), with and without a
+    # rational part behind it
+    for fs, rs, con in [(6e6, 233333, "qpsk"), (24e6, 2333333, "qpsk"), (32e6, 1e6, "bpsk"), (100e6, 1.2e6, "bpsk"), (90e6, 2e6, "qpsk")]:
+        for fmt in ("cs16", "cf32"):
+            n = 300000
+            raw = ((rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64) * 0.3 if fmt == "cf32"
+                   else (rng.standard_normal(2 * n) * 3000).astype(np.int16))
+            cfg = ref.demod_cfg(fs, rs, con, 0.5, fmt=fmt)
+            assert cfg.samplerate / cfg.final_samplerate >= 2
+            a, b = ref.resample(cfg, raw), port.resample(cfg, raw)
+            assert a.size == b.size > 1000 and bitwise(a, b), (fs, rs, con, fmt)
