@@ -77,6 +77,9 @@ typedef struct b200_demod_cfg
                                  `resample` is false (samplerate / symbolrate inside [min_sps, max_sps]) although "custom_samplerate" set
                                  another final_samplerate: the reference then only designs the RRC and the clock recovery for that rate
                                  (module_demod_base.cpp:66,73-74,203-204); b200_demod_resample_decision() tells                        */
+    int clock_recovery;       /* 0: MMClockRecoveryBlock<complex_t> (what psk_demod builds, module_psk_demod.cpp:134-135);
+                                 1: dsp::GardnerClockRecoveryBlock<complex_t> with the same arguments
+                                 (common/dsp/clock_recovery/clock_recovery_gardner.cpp:33-131)                          */
 } b200_demod_cfg;
 
 typedef struct b200_fec_cfg

@@ -311,7 +311,7 @@ void *orc_demod_create(const orc_demod_cfg *c)
     orc_mm_bank(d->bank);
     d->mu = c->clock_mu; d->omega = d->sps; d->omega_gain = c->clock_gain_omega; d->mu_gain = c->clock_gain_mu;
     d->omega_mid = d->sps; d->omega_limit = c->clock_omega_limit * d->sps; /* clock_recovery_mm.cpp:14-15 */
-    d->mm_buf = calloc(STREAM_MAX + 64, sizeof(cf_t));
+    d->mm_buf = calloc(STREAM_MAX + 64, sizeof(cf_t)); /* (+ 8 / 28 samples of history in front: M&M / Gardner) */
     /* the resampler may interpolate: up to ceil(n * I / D) + 1 outputs per input buffer */
     size_t wn = d->rs.active ? (size_t)((double)d->buffer_size * d->rs.interp / d->rs.decim) + 16 : (size_t)d->buffer_size;
     if (wn < (size_t)d->buffer_size) wn = d->buffer_size;
@@ -465,6 +465,51 @@ static int mm_run(orc_demod *d, const cf_t *in, cf_t *out, int n)
     return ouc;
 }
 
+/* GardnerClockRecoveryBlock<complex_t>::work — clock_recovery_gardner.cpp:33-131. Same interpolator bank, omega / mu updates as M&M;
+   the error is zc * (last - sample) with a second interpolation half a symbol back. History: ntaps - 1 + bufs (= 27) samples.
+   BRANCHLESS_CLIP (block.h:10) is 0.5 * (abs(x + c) - abs(x - c)): with the double constant 1.0 the error clip is evaluated in double
+   (exact), the omega clip in float for the two sums, double for the rest. */
+static int gardner_run(orc_demod *d, const cf_t *in, cf_t *out, int n)
+{
+    const int bufs = 20;
+    cf_t *buf = d->mm_buf;
+    memcpy(&buf[7 + bufs], in, n * sizeof(cf_t));
+    int ouc = 0, inc = d->inc;
+    float mu = d->mu, omega = d->omega;
+    for (; inc < n && ouc < STREAM_MAX;) {
+        float muz = mu - (omega / 2.0);
+        int offzc = floor(omega / 2.0);
+        float mupos = fmod(muz + offzc, 1.0);
+        if (mupos < 0) { mupos = 1 + mupos; offzc += 1; }
+        int imuz = (int)rint(mupos * 128);
+        if (imuz < 0) imuz = 0;
+        if (imuz >= 128) imuz = 127;
+        int imu = (int)rint(mu * 128);
+        if (imu < 0) imu = 0;
+        if (imu >= 128) imu = 127;
+        const float *tz = &d->bank[imuz * 8], *tp = &d->bank[imu * 8];
+        const cf_t *xz = &buf[inc - offzc + bufs], *xs = &buf[inc + bufs];
+        float zr = 0.0f, zi = 0.0f, sr = 0.0f, si = 0.0f;
+        for (int k = 0; k < 8; k++) { zr += xz[k].re * tz[k]; zi += xz[k].im * tz[k]; }
+        for (int k = 0; k < 8; k++) { sr += xs[k].re * tp[k]; si += xs[k].im * tp[k]; }
+        float pe = zr * (d->p0.re - sr) + zi * (d->p0.im - si); /* p0 = last_sample */
+        pe = 0.5 * (fabs(pe + 1.0) - fabs(pe - 1.0));
+        d->p0.re = sr; d->p0.im = si;
+        out[ouc].re = sr; out[ouc].im = si; ouc++;
+        omega = omega + d->omega_gain * pe;
+        { float x = omega - d->omega_mid; omega = d->omega_mid + 0.5 * (fabsf(x + d->omega_limit) - fabsf(x - d->omega_limit)); }
+        mu = mu + omega + d->mu_gain * pe;
+        inc += (int)floor(mu);
+        mu -= floor(mu);
+        if (inc < 0) inc = 0;
+    }
+    inc -= n;
+    if (inc < 0) inc = 0;
+    memmove(&buf[0], &buf[n], (8 + bufs) * sizeof(cf_t));
+    d->inc = inc; d->mu = mu; d->omega = omega;
+    return ouc;
+}
+
 /* module_demod_base.h:106-113 */
 static int8_t soft_clamp(float x)
 {
@@ -507,7 +552,7 @@ long orc_demod_run(void *h, const void *raw, long nsamples, float *agc_out, floa
             if (costas_out) memcpy(costas_out + pos * 2, cur, n * sizeof(cf_t));
         }
         pos += n;
-        int m = mm_run(d, cur, d->w2, n);
+        int m = d->cfg.clock_recovery == 1 ? gardner_run(d, cur, d->w2, n) : mm_run(d, cur, d->w2, n);
         if (nsym + m > sym_cap) m = (int)(sym_cap - nsym);
         if (mm_out) memcpy(mm_out + nsym * 2, d->w2, m * sizeof(cf_t));
         if (soft_out) { /* module_psk_demod.cpp:199-213 */
@@ -553,7 +598,7 @@ long orc_demod_run_stage(void *h, int stage, const float *in, long nsamples, flo
             }
             if (d->cfg.constellation == 2) delay_run(d, d->w1, n);
         } else {
-            m = mm_run(d, d->w0, d->w2, n);
+            m = d->cfg.clock_recovery == 1 ? gardner_run(d, d->w0, d->w2, n) : mm_run(d, d->w0, d->w2, n);
             res = d->w2;
         }
         if (pos + m > cap) m = (int)(cap - pos);
@@ -791,6 +836,122 @@ static int vit_work(orc_vit *v, int8_t *in, uint8_t *out)
     return out_n;
 }
 
+/* ======================================================================= Viterbi_Depunc (rates 2/3, 3/4, 5/6, 7/8)
+ * viterbi_punc.cpp:53-145 + depunc.h. One table per rate: for every input position of the puncturing period, how many symbols it
+ * makes (1 or 2) and where the data symbol sits among them (the other one is the erasure 128). */
+typedef struct { int period, numstates; float berscale; uint8_t nout[8], datapos[8]; } orc_punc;
+static const orc_punc PUNC_23 = {3, 3, 3.5f, {1, 2, 1}, {0, 0, 0}};
+static const orc_punc PUNC_34 = {4, 4, 5.0f, {1, 2, 1, 2}, {0, 0, 0, 0}};
+static const orc_punc PUNC_56 = {6, 6, 8.0f, {1, 2, 1, 2, 2, 2}, {0, 0, 0, 0, 1, 0}};
+static const orc_punc PUNC_78 = {8, 8, 10.0f, {1, 2, 2, 2, 1, 2, 2, 2}, {0, 0, 0, 0, 0, 0, 1, 0}};
+
+static int punc_emit(const orc_punc *p, int phase, uint8_t v, uint8_t *out, int oo)
+{
+    if (p->nout[phase] == 1) out[oo++] = v;
+    else if (p->datapos[phase] == 0) { out[oo++] = v; out[oo++] = 128; }
+    else { out[oo++] = 128; out[oo++] = v; }
+    return oo;
+}
+/* DepuncXX::depunc_static */
+static int punc_static(const orc_punc *p, const uint8_t *in, uint8_t *out, int size, int shift)
+{
+    int oo = 0, a = shift % p->period;
+    if (shift > p->period - 1) out[oo++] = 128;
+    for (int i = 0; i < size; i++) oo = punc_emit(p, (i + a) % p->period, in[i], out, oo);
+    return oo;
+}
+typedef struct
+{
+    const orc_punc *p;
+    int is_first, changing_shift, got_extra; /* DepuncXX members */
+    uint8_t buf;
+    int size, vit_bufsize, in_buffer, state, phase, shift, swap, invalid, outsync, check_swap, nphases, phases[4], test_bit_len;
+    float thr, ber;
+    orc_ccdec dec_ber, dec_main;
+    orc_ccenc enc_ber;
+    int8_t test[TESTLEN];
+    uint8_t bsoft[TESTLEN], bdepunc[TESTLEN * 4], bdecoded[TESTLEN * 4], bencoded[TESTLEN * 4]; /* (zeroed: the oracle's pin of reads before writes) */
+    uint8_t *soft, *depunc, *vitbuf;
+} orc_vitp;
+
+static void vitp_init(orc_vitp *v, int conv_rate, float thr, int outsync, int size, const int *phases, int nphases, int check_swap)
+{
+    memset(v, 0, sizeof(*v));
+    v->p = conv_rate == 2 ? &PUNC_23 : (conv_rate == 3 ? &PUNC_34 : (conv_rate == 5 ? &PUNC_56 : &PUNC_78));
+    v->buf = 128;
+    v->thr = thr; v->outsync = outsync; v->size = size; v->vit_bufsize = size; v->check_swap = check_swap;
+    v->nphases = nphases; memcpy(v->phases, phases, sizeof(int) * nphases);
+    ccdec_init(&v->dec_ber, TESTLEN);
+    ccdec_init(&v->dec_main, size / 2);
+    v->soft = malloc((size_t)size * 8); v->depunc = malloc((size_t)size * 8); v->vitbuf = calloc((size_t)size * 4, 1);
+}
+static void vitp_free(orc_vitp *v) { free(v->dec_ber.dec); free(v->dec_main.dec); free(v->soft); free(v->depunc); free(v->vitbuf); }
+
+/* DepuncXX::depunc_cont */
+static int punc_cont(orc_vitp *v, const uint8_t *in, uint8_t *out, int size)
+{
+    int oo = 0;
+    if (v->is_first || v->got_extra) { out[oo++] = v->buf; v->is_first = 0; v->got_extra = 0; }
+    v->changing_shift %= v->p->period;
+    for (int i = 0; i < size; i++) { oo = punc_emit(v->p, v->changing_shift % v->p->period, in[i], out, oo); v->changing_shift++; }
+    if (oo % 2 == 1) { v->buf = out[oo - 1]; oo -= 1; v->got_extra = 1; }
+    return oo;
+}
+
+/* Viterbi_Depunc::work. `in` is modified in place. The deprecated CCDecoder::work(in, out, size) the lock search calls ignores its
+ * size (cc_decoder.cpp:304-314): it decodes the full TEST_BITS_LENGTH frame from 2 * 2054 symbols of the test buffer. */
+static int vitp_work(orc_vitp *v, int8_t *in, uint8_t *out)
+{
+    int size = v->size;
+    if (!v->state) {
+        v->ber = 10;
+        for (int s = 0; s < (v->check_swap ? 2 : 1); s++)
+            for (int pi = 0; pi < v->nphases; pi++) {
+                int ph = v->phases[pi];
+                memcpy(v->test, in, TESTLEN);
+                orc_rotate_soft(v->test, TESTLEN, 0, s);
+                orc_rotate_soft(v->test, TESTLEN, ph, 0);
+                soft_to_u8(v->test, v->bsoft, TESTLEN);
+                for (int shift = 0; shift < v->p->numstates * 2; shift++) {
+                    int lenp = punc_static(v->p, v->bsoft, v->bdepunc, TESTLEN, shift);
+                    if (lenp % 2) lenp--;
+                    ccdec_work(&v->dec_ber, v->bdepunc, v->bdecoded);
+                    ccenc_work(&v->enc_ber, v->bdecoded, lenp / 2, v->bencoded);
+                    v->test_bit_len = lenp;
+                    float b = ber_of(v->bdepunc, v->bencoded, lenp, v->p->berscale);
+                    if (b < v->thr && b < v->ber) {
+                        v->ber = b; v->swap = s; v->state = 1; v->phase = ph; v->shift = shift; v->invalid = 0;
+                        v->changing_shift = shift; v->is_first = shift > v->p->period - 1; /* set_shift */
+                        memset(v->soft, 128, (size_t)size * 4);
+                        memset(v->depunc, 128, (size_t)size * 4);
+                    }
+                }
+            }
+    }
+    int out_n = 0;
+    if (v->state) {
+        orc_rotate_soft(in, size, 0, v->swap);
+        orc_rotate_soft(in, size, v->phase, 0);
+        soft_to_u8(in, v->soft, size);
+        int sz = punc_cont(v, v->soft, v->depunc, size);
+        memcpy(&v->vitbuf[v->in_buffer], v->depunc, sz); /* ViterbiSlidingBuffer::add */
+        v->in_buffer += sz;
+        while (v->in_buffer > v->vit_bufsize) {
+            ccdec_work(&v->dec_main, v->vitbuf, out + out_n);
+            ccenc_work(&v->enc_ber, out + out_n, TESTLEN, v->bencoded);
+            v->ber = ber_of(v->vitbuf, v->bencoded, v->test_bit_len, 5);
+            out_n += v->vit_bufsize / 2;
+            int len = v->vit_bufsize; /* ViterbiSlidingBuffer::del */
+            memmove(v->vitbuf, v->vitbuf + len, v->in_buffer - len);
+            v->in_buffer -= len;
+            memset(v->vitbuf + v->in_buffer, 128, len > 100 ? 100 : len);
+        }
+        if (v->ber > v->thr) { v->invalid++; if (v->invalid > v->outsync) v->state = 0; }
+        else v->invalid = 0;
+    }
+    return out_n;
+}
+
 /* ======================================================================= deframer */
 
 typedef struct
@@ -1021,6 +1182,7 @@ typedef struct
     orc_fec_cfg cfg;
     int chunk, cadu_bytes, nosync_runs, errors[16];
     orc_vit vit;
+    orc_vitp vitp; /* conv_rate != 0: Viterbi_Depunc instead of Viterbi1_2 */
     orc_deframer defr, defr_qpsk; /* defr_qpsk: the second deframer of ccsds_simple_psk_decoder (QPSK without NRZ-M) */
     uint8_t nrzm_last;
     uint8_t *vout, *frames;
@@ -1055,7 +1217,8 @@ void *orc_fec_create(const orc_fec_cfg *c)
         else if (c->constellation == 5) { ph[0] = 1; n = 1; }
         f->chunk = c->cadu_size > 8192 ? c->cadu_size : 8192;
         f->cadu_bytes = (c->cadu_size + 7) / 8;
-        vit_init(&f->vit, 0, c->ber_thresold, c->outsync_after, f->chunk, ph, n, c->constellation == 2);
+        if (c->conv_rate) vitp_init(&f->vitp, c->conv_rate, c->ber_thresold, c->outsync_after, f->chunk, ph, n, c->constellation == 2);
+        else vit_init(&f->vit, 0, c->ber_thresold, c->outsync_after, f->chunk, ph, n, c->constellation == 2);
         defr_init(&f->defr, c->cadu_size, c->asm_sync);
         f->defr.pad = c->cadu_size % 8;
     }
@@ -1065,7 +1228,8 @@ void *orc_fec_create(const orc_fec_cfg *c)
 void orc_fec_destroy(void *h)
 {
     orc_fec *f = h;
-    if (f->cfg.kind != 2) vit_free(&f->vit);
+    if (f->cfg.kind == 1 && f->cfg.conv_rate) vitp_free(&f->vitp);
+    else if (f->cfg.kind != 2) vit_free(&f->vit);
     free(f->defr.frame); free(f->defr_qpsk.frame); free(f->vout); free(f->frames); free(f->soft); free(f);
 }
 
@@ -1151,9 +1315,10 @@ long orc_fec_run(void *h, const int8_t *soft, long nsoft, uint8_t *cadu_out, lon
             continue;
         }
         if (k->kind == 1 && (k->constellation == 5 || k->iq_invert)) orc_rotate_soft(f->soft, f->chunk, 0, 1);
-        int vout = vit_work(&f->vit, f->soft, f->vout);
-        if (vit_state) vit_state[c] = f->vit.state;
-        if (vit_b) vit_b[c] = vit_ber(&f->vit);
+        const int punc = k->kind == 1 && k->conv_rate;
+        int vout = punc ? vitp_work(&f->vitp, f->soft, f->vout) : vit_work(&f->vit, f->soft, f->vout);
+        if (vit_state) vit_state[c] = punc ? f->vitp.state : f->vit.state;
+        if (vit_b) vit_b[c] = punc ? f->vitp.ber : vit_ber(&f->vit);
         if (k->kind == 0) {
             if (vout > 0) {
                 if (bits_out) memcpy(bits_out + bitp, f->vout, vout);

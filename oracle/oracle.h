@@ -30,6 +30,7 @@ typedef struct
     double final_samplerate; /* 0 = samplerate; else the rate BaseDemodModule::initb resamples to (module_demod_base.cpp:59-87) */
     int dc_block;            /* CorrectIQBlock behind the reader (module_demod_base.cpp:113-114) */
     int post_costas_dc;      /* CorrectIQBlock behind the Costas loop (module_psk_demod.cpp:127-134) */
+    int clock_recovery;      /* 0 MMClockRecoveryBlock, 1 GardnerClockRecoveryBlock<complex_t> (clock_recovery_gardner.cpp) */
 } orc_demod_cfg;
 
 typedef struct
@@ -43,6 +44,7 @@ typedef struct
     int iq_invert;
     unsigned int asm_sync;
     int qpsk_swap_iq, qpsk_swap_diff, oqpsk_delay; /* kind 2 = ccsds_simple_psk_decoder */
+    int conv_rate;                                 /* kind 1: 0 = 1/2, 2 / 3 / 5 / 7 = Viterbi_Depunc rates 2/3, 3/4, 5/6, 7/8 */
 } orc_fec_cfg;
 
 int orc_rrc_taps(double gain, double fs, double rs, double alpha, int ntaps, float *out);

@@ -11,6 +11,7 @@ _PFX = "ref_"
 
 CONST = {"bpsk": 0, "qpsk": 1, "oqpsk": 2, "8psk": 3, "none": 4, "bpsk_90": 5}
 FMT = {"cf32": 0, "cs16": 1, "cs8": 2}
+CONV_RATE = {"1/2": 0, "2/3": 2, "3/4": 3, "5/6": 5, "7/8": 7}
 
 
 class DemodCfg(C.Structure):
@@ -18,7 +19,8 @@ class DemodCfg(C.Structure):
                 ("rrc_alpha", C.c_float), ("rrc_taps", C.c_int), ("pll_bw", C.c_float), ("agc_rate", C.c_float),
                 ("clock_gain_omega", C.c_float), ("clock_mu", C.c_float), ("clock_gain_mu", C.c_float),
                 ("clock_omega_limit", C.c_float), ("costas_max_offset", C.c_float), ("format", C.c_int),
-                ("buffer_size", C.c_int), ("iq_swap", C.c_int), ("final_samplerate", C.c_double), ("dc_block", C.c_int), ("post_costas_dc", C.c_int)]
+                ("buffer_size", C.c_int), ("iq_swap", C.c_int), ("final_samplerate", C.c_double), ("dc_block", C.c_int), ("post_costas_dc", C.c_int),
+                ("clock_recovery", C.c_int)]
 
 
 class FecCfg(C.Structure):
@@ -26,7 +28,7 @@ class FecCfg(C.Structure):
                 ("ber_thresold", C.c_float), ("nrzm", C.c_int), ("derandomize", C.c_int), ("derand_after_rs", C.c_int),
                 ("derand_start", C.c_int), ("rs_i", C.c_int), ("rs_dualbasis", C.c_int), ("rs_fill_bytes", C.c_int),
                 ("rs_usecheck", C.c_int), ("rs_type", C.c_int), ("iq_invert", C.c_int), ("asm_sync", C.c_uint),
-                ("qpsk_swap_iq", C.c_int), ("qpsk_swap_diff", C.c_int), ("oqpsk_delay", C.c_int)]
+                ("qpsk_swap_iq", C.c_int), ("qpsk_swap_diff", C.c_int), ("oqpsk_delay", C.c_int), ("conv_rate", C.c_int)]
 
 
 class _Prefixed:
@@ -103,7 +105,8 @@ def _p(a):
 
 def demod_cfg(samplerate, symbolrate, constellation, rrc_alpha, pll_bw=0.003, fmt="cs16", rrc_taps=31, agc_rate=1e-2,
               clock_alpha=None, clock_gain_omega=None, clock_mu=0.5, clock_gain_mu=8.7e-3, clock_omega_limit=0.005,
-              costas_max_offset=1.0, buffer_size=0, iq_swap=False, final_samplerate=None, min_sps=None, max_sps=None, dc_block=False, post_costas_dc=False):
+              costas_max_offset=1.0, buffer_size=0, iq_swap=False, final_samplerate=None, min_sps=None, max_sps=None, dc_block=False, post_costas_dc=False,
+              clock_recovery="mm"):
     """Defaults follow module_psk_demod.h:31-39 and module_demod_base.h:54. final_samplerate=None applies BaseDemodModule::initb's
     rule (resample when samplerate/symbolrate is outside [min_sps, max_sps]); 0 = no resampler."""
     if final_samplerate is None:
@@ -117,7 +120,7 @@ def demod_cfg(samplerate, symbolrate, constellation, rrc_alpha, pll_bw=0.003, fm
         clock_gain_omega = float(np.float32(pow(8.7e-3, 2) / 4.0))
     return DemodCfg(float(samplerate), float(symbolrate), CONST[constellation], rrc_alpha, rrc_taps, pll_bw, agc_rate,
                     float(clock_gain_omega), clock_mu, float(clock_gain_mu), clock_omega_limit, costas_max_offset, FMT[fmt],
-                    buffer_size, int(iq_swap), float(final_samplerate), int(dc_block), int(post_costas_dc))
+                    buffer_size, int(iq_swap), float(final_samplerate), int(dc_block), int(post_costas_dc), {"mm": 0, "gardner": 1}[clock_recovery])
 
 
 def final_samplerate_of(samplerate, symbolrate, constellation, min_sps=None, max_sps=None, custom=None):
@@ -143,22 +146,22 @@ def final_samplerate_of(samplerate, symbolrate, constellation, min_sps=None, max
 
 
 def metop_cfg(ber_thresold=0.28, outsync_after=10):
-    return FecCfg(0, 1, 8192, outsync_after, ber_thresold, 0, 1, 0, 4, 4, 1, -1, 0, 0, 0, 0x1ACFFC1D, 0, 0, 0)
+    return FecCfg(0, 1, 8192, outsync_after, ber_thresold, 0, 1, 0, 4, 4, 1, -1, 0, 0, 0, 0x1ACFFC1D, 0, 0, 0, 0)
 
 
 def simple_cfg(constellation, cadu_size, rs_i, nrzm=False, derandomize=True, rs_usecheck=False, rs_dualbasis=True, rs_fill_bytes=-1,
                derand_after_rs=False, derand_start=4, rs_type=0, asm_sync=0x1ACFFC1D, qpsk_swap_iq=False, qpsk_swap_diff=True, oqpsk_delay=False):
     """ccsds_simple_psk_decoder (module_ccsds_simple_psk_decoder.cpp:19-44 defaults): no convolutional code."""
     return FecCfg(2, CONST[constellation], cadu_size, 0, 0.0, int(nrzm), int(derandomize), int(derand_after_rs), derand_start, rs_i,
-                  int(rs_dualbasis), rs_fill_bytes, int(rs_usecheck), rs_type, 0, asm_sync, int(qpsk_swap_iq), int(qpsk_swap_diff), int(oqpsk_delay))
+                  int(rs_dualbasis), rs_fill_bytes, int(rs_usecheck), rs_type, 0, asm_sync, int(qpsk_swap_iq), int(qpsk_swap_diff), int(oqpsk_delay), 0)
 
 
 def ccsds_cfg(constellation, cadu_size, ber_thresold, outsync_after, rs_i, nrzm=False, derandomize=True, rs_usecheck=False,
               rs_dualbasis=True, rs_fill_bytes=-1, derand_after_rs=False, derand_start=4, iq_invert=False, rs_type=0,
-              asm_sync=0x1ACFFC1D):
+              asm_sync=0x1ACFFC1D, conv_rate="1/2"):
     return FecCfg(1, CONST[constellation], cadu_size, outsync_after, ber_thresold, int(nrzm), int(derandomize),
                   int(derand_after_rs), derand_start, rs_i, int(rs_dualbasis), rs_fill_bytes, int(rs_usecheck), rs_type,
-                  int(iq_invert), asm_sync, 0, 0, 0)
+                  int(iq_invert), asm_sync, 0, 0, 0, CONV_RATE[conv_rate])
 
 
 class Demod:
@@ -235,7 +238,7 @@ class Fec:
     def run(self, soft):
         soft = np.ascontiguousarray(soft, np.int8)
         nch = soft.size // self.chunk
-        bits_per_chunk = self.chunk * 3 // 4 if self.cfg.kind == 0 else (self.chunk if self.cfg.kind == 2 else self.chunk // 2)
+        bits_per_chunk = self.chunk * 3 // 4 if self.cfg.kind == 0 else (self.chunk if (self.cfg.kind == 2 or self.cfg.conv_rate) else self.chunk // 2)
         cap = (nch * bits_per_chunk // max(1, self.cfg.cadu_size) + 2) * self.cadu_bytes
         cadu = np.zeros(cap, np.uint8)
         vs = np.zeros(nch, np.int32)

@@ -46,6 +46,7 @@
 #include "common/dsp/pll/costas_loop.h"
 #include "common/dsp/demod/delay_one_imag.h"
 #include "common/dsp/clock_recovery/clock_recovery_mm.h"
+#include "common/dsp/clock_recovery/clock_recovery_gardner.h"
 #include "common/dsp/resamp/smart_resampler.h"
 #include "common/dsp/resamp/rational_resampler.h"
 #undef private
@@ -54,6 +55,9 @@
 #include "common/dsp/window/window.h"
 #include "common/codings/viterbi/viterbi_3_4.h"
 #include "common/codings/viterbi/viterbi_1_2.h"
+#define private public /* Viterbi_Depunc reads member buffers it never initialises (viterbi_punc.h:52-56): the harness zeroes them */
+#include "common/codings/viterbi/viterbi_punc.h"
+#undef private
 #include "common/codings/viterbi/cc_encoder.h"
 #include "common/codings/viterbi/cc_decoder.h"
 #include "common/codings/deframing/bpsk_ccsds_deframer.h"
@@ -96,6 +100,8 @@ extern "C"
         double final_samplerate; /* 0 = samplerate (sps inside [MIN_SPS, MAX_SPS]); else BaseDemodModule::initb's resampled rate */
         int dc_block;            /* CorrectIQBlock behind the reader (module_demod_base.cpp:113-114) */
         int post_costas_dc;      /* CorrectIQBlock behind the Costas loop (module_psk_demod.cpp:127-134) */
+        int clock_recovery;      /* 0: MMClockRecoveryBlock (psk_demod); 1: dsp::GardnerClockRecoveryBlock<complex_t> with the same arguments
+                                    (common/dsp/clock_recovery/clock_recovery_gardner.cpp) */
     } ref_demod_cfg;
 
     typedef struct
@@ -111,6 +117,7 @@ extern "C"
         unsigned int asm_sync;
         /* kind 2 = ccsds_simple_psk_decoder (module_ccsds_simple_psk_decoder.cpp): no convolutional code */
         int qpsk_swap_iq, qpsk_swap_diff, oqpsk_delay;
+        int conv_rate; /* kind 1: 0 = "1/2" (Viterbi1_2); 2 / 3 / 5 / 7 = "2/3" / "3/4" / "5/6" / "7/8" (Viterbi_Depunc, module_ccsds_conv_concat_decoder.cpp:99-117) */
     } ref_fec_cfg;
 }
 
@@ -131,7 +138,9 @@ namespace
         std::shared_ptr<dsp::CostasLoopBlock> pll;
         std::shared_ptr<dsp::CorrectIQBlock<complex_t>> post_pll_dc;
         std::shared_ptr<dsp::DelayOneImagBlock> delay;
-        std::shared_ptr<dsp::MMClockRecoveryBlock<complex_t>> rec;
+        std::shared_ptr<dsp::Block<complex_t, complex_t>> rec; /* the clock recovery in use: one of the two below */
+        std::shared_ptr<dsp::MMClockRecoveryBlock<complex_t>> rec_mm;
+        std::shared_ptr<dsp::GardnerClockRecoveryBlock<complex_t>> rec_g;
         std::vector<float> rrc_taps;
         long last_front = 0; /* samples that entered the AGC in the last ref_demod_run call */
     };
@@ -180,6 +189,7 @@ namespace
         int buffer_size, cadu_bytes;
         std::shared_ptr<viterbi::Viterbi3_4> v34;
         std::shared_ptr<viterbi::Viterbi1_2> v12;
+        std::shared_ptr<viterbi::Viterbi_Depunc> vp;
         std::shared_ptr<deframing::BPSK_CCSDS_Deframer> deframer, deframer_qpsk;
         std::shared_ptr<reedsolomon::ReedSolomon> rs;
         diff::NRZMDiff diff;
@@ -239,7 +249,16 @@ extern "C"
                 last = d->delay->output_stream;
             }
         }
-        d->rec = std::make_shared<dsp::MMClockRecoveryBlock<complex_t>>(last, d->final_sps, c->clock_gain_omega, c->clock_mu, c->clock_gain_mu, c->clock_omega_limit);
+        if (c->clock_recovery == 1)
+        {
+            d->rec_g = std::make_shared<dsp::GardnerClockRecoveryBlock<complex_t>>(last, d->final_sps, c->clock_gain_omega, c->clock_mu, c->clock_gain_mu, c->clock_omega_limit);
+            d->rec = d->rec_g;
+        }
+        else
+        {
+            d->rec_mm = std::make_shared<dsp::MMClockRecoveryBlock<complex_t>>(last, d->final_sps, c->clock_gain_omega, c->clock_mu, c->clock_gain_mu, c->clock_omega_limit);
+            d->rec = d->rec_mm;
+        }
         return d;
     }
 
@@ -446,9 +465,9 @@ extern "C"
         out8[0] = d->agc->gain;
         out8[1] = d->pll ? d->pll->phase : 0;
         out8[2] = d->pll ? d->pll->freq : 0;
-        out8[3] = d->rec->mu;
-        out8[4] = d->rec->omega;
-        out8[5] = (float)d->rec->inc;
+        out8[3] = d->rec_g ? d->rec_g->mu : d->rec_mm->mu;
+        out8[4] = d->rec_g ? d->rec_g->omega : d->rec_mm->omega;
+        out8[5] = (float)(d->rec_g ? d->rec_g->inc : d->rec_mm->inc);
         out8[6] = d->pll ? d->pll->alpha : 0;
         out8[7] = d->pll ? d->pll->beta : 0;
     }
@@ -498,7 +517,29 @@ extern "C"
                 phases = {PHASE_90};
             else
                 phases = {PHASE_0, PHASE_90};
-            f->v12 = std::make_shared<viterbi::Viterbi1_2>(c->ber_thresold, c->outsync_after, f->buffer_size, phases, oqpsk);
+            if (c->conv_rate == 0)
+                f->v12 = std::make_shared<viterbi::Viterbi1_2>(c->ber_thresold, c->outsync_after, f->buffer_size, phases, oqpsk);
+            else
+            {
+                std::shared_ptr<viterbi::puncturing::GenericDepunc> dp;
+                if (c->conv_rate == 2)
+                    dp = std::make_shared<viterbi::puncturing::Depunc23>();
+                else if (c->conv_rate == 3)
+                    dp = std::make_shared<viterbi::puncturing::Depunc34>();
+                else if (c->conv_rate == 5)
+                    dp = std::make_shared<viterbi::puncturing::Depunc56>();
+                else
+                    dp = std::make_shared<viterbi::puncturing::Depunc78>();
+                f->vp = std::make_shared<viterbi::Viterbi_Depunc>(dp, c->ber_thresold, c->outsync_after, f->buffer_size, phases, oqpsk);
+                /* members / heap blocks the reference reads before writing them (the tail of the 2054-step test decode beyond the
+                   depunctured test symbols, the sliding buffer): pinned to zero here so that the oracle is deterministic */
+                memset(f->vp->ber_test_buffer, 0, sizeof(f->vp->ber_test_buffer));
+                memset(f->vp->ber_soft_buffer, 0, sizeof(f->vp->ber_soft_buffer));
+                memset(f->vp->ber_depunc_buffer, 0, sizeof(f->vp->ber_depunc_buffer));
+                memset(f->vp->ber_decoded_buffer, 0, sizeof(f->vp->ber_decoded_buffer));
+                memset(f->vp->ber_encoded_buffer, 0, sizeof(f->vp->ber_encoded_buffer));
+                memset(f->vp->vit_buffer.buffer_ptr, 0, (size_t)f->buffer_size * 4);
+            }
             f->deframer = std::make_shared<deframing::BPSK_CCSDS_Deframer>(c->cadu_size, c->asm_sync);
             if (c->cadu_size % 8 != 0)
                 f->deframer->CADU_PADDING = c->cadu_size % 8;
@@ -658,11 +699,14 @@ extern "C"
                 const ref_fec_cfg &k = f->cfg;
                 if (k.constellation == 5 || k.iq_invert)
                     rotate_soft(f->soft.data(), f->buffer_size, PHASE_0, true);
-                vout = f->v12->work(f->soft.data(), f->buffer_size, f->viterbi_out.data());
+                if (f->vp)
+                    vout = f->vp->work(f->soft.data(), f->buffer_size, f->viterbi_out.data());
+                else
+                    vout = f->v12->work(f->soft.data(), f->buffer_size, f->viterbi_out.data());
                 if (vit_state)
-                    vit_state[c] = f->v12->getState();
+                    vit_state[c] = f->vp ? f->vp->getState() : f->v12->getState();
                 if (vit_ber)
-                    vit_ber[c] = f->v12->ber();
+                    vit_ber[c] = f->vp ? f->vp->d_ber : f->v12->ber();
                 if (k.nrzm)
                     f->diff.decode_bits(f->viterbi_out.data(), vout);
                 if (bits_out && vout > 0)

@@ -36,7 +36,7 @@ class DemodCfg(C.Structure):
                 ("clock_mu", C.c_float), ("clock_gain_mu", C.c_float), ("clock_omega_limit", C.c_float),
                 ("costas_max_offset", C.c_float), ("format", C.c_int), ("device", C.c_int), ("max_batch", C.c_long),
                 ("keep_stages", C.c_int), ("iq_swap", C.c_int), ("final_samplerate", C.c_double), ("dc_block", C.c_int), ("post_costas_dc", C.c_int),
-                ("front_resample", C.c_int)]
+                ("front_resample", C.c_int), ("clock_recovery", C.c_int)]
 
 
 class FecCfg(C.Structure):
@@ -138,7 +138,7 @@ def _chk(rc):
 def demod_cfg(samplerate, symbolrate, constellation, rrc_alpha, pll_bw=0.003, fmt="cs16", rrc_taps=31, agc_rate=1e-2, clock_alpha=None,
               clock_gain_omega=None, clock_mu=0.5, clock_gain_mu=8.7e-3, clock_omega_limit=0.005, costas_max_offset=1.0, device=0,
               max_batch=1 << 24, keep_stages=False, iq_swap=False, final_samplerate=None, min_sps=0.0, max_sps=0.0, dc_block=False, post_costas_dc=False,
-              front_resample=0):
+              front_resample=0, clock_recovery="mm"):
     """Parameter defaults = module_psk_demod.h:31-39, module_demod_base.h:54. final_samplerate=None applies BaseDemodModule::initb's
     rule (resample when samplerate/symbolrate is outside [min_sps, max_sps]); 0 forces "no resampler"."""
     if final_samplerate is None:
@@ -152,7 +152,7 @@ def demod_cfg(samplerate, symbolrate, constellation, rrc_alpha, pll_bw=0.003, fm
         clock_gain_omega = float(np.float32(pow(8.7e-3, 2) / 4.0))
     return DemodCfg(float(samplerate), float(symbolrate), CONST[constellation], rrc_alpha, rrc_taps, pll_bw, agc_rate, clock_gain_omega,
                     clock_mu, clock_gain_mu, clock_omega_limit, costas_max_offset, FMT[fmt], device, max_batch, int(keep_stages), int(iq_swap),
-                    float(final_samplerate), int(dc_block), int(post_costas_dc), int(front_resample))
+                    float(final_samplerate), int(dc_block), int(post_costas_dc), int(front_resample), {"mm": 0, "gardner": 1}[clock_recovery])
 
 
 def resampler_bank(samplerate, final_samplerate):

@@ -187,6 +187,7 @@ Demod::Demod(const b200_demod_cfg &c) : cfg(c)
     B200_REQUIRE(c.max_batch >= 4096, B200_EINVAL, "max_batch must be >= 4096 samples");
     B200_REQUIRE(c.agc_rate > 0 && c.agc_rate < 0.5f, B200_EINVAL, "agc_rate out of range");
     B200_REQUIRE(c.clock_gain_mu > 0 && c.pll_bw > 0, B200_EINVAL, "loop gains must be positive");
+    B200_REQUIRE(c.clock_recovery == 0 || c.clock_recovery == 1, B200_EINVAL, "clock_recovery must be 0 (M&M) or 1 (Gardner)");
     const long fs = (long)c.samplerate, rs = (long)c.symbolrate;
     const float final_fs = c.final_samplerate > 0 ? (float)c.final_samplerate : (float)fs; // float final_samplerate (module_demod_base.h:67)
     sps = final_fs / (float)rs;
@@ -407,8 +408,10 @@ Demod::Demod(const b200_demod_cfg &c) : cfg(c)
     B200_CUDA(cudaMemcpyAsync(st.p, h_state, sizeof(DemodDevState), cudaMemcpyHostToDevice, stream));
     bufA.zero(stream);
     bufB.zero(stream);
-    B200_CUDA(cudaFuncSetAttribute(k_mm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM_BYTES));
-    B200_CUDA(cudaFuncSetAttribute(k_mm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM_BYTES));
+    B200_CUDA(cudaFuncSetAttribute(k_mm<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM_BYTES));
+    B200_CUDA(cudaFuncSetAttribute(k_mm<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM_BYTES));
+    B200_CUDA(cudaFuncSetAttribute(k_mm<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM_BYTES));
+    B200_CUDA(cudaFuncSetAttribute(k_mm<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM_BYTES));
     B200_CUDA(cudaFuncSetAttribute(k_costas, cudaFuncAttributeMaxDynamicSharedMemorySize, COSTAS_SMEM_BYTES));
     B200_CUDA(cudaStreamSynchronize(stream));
 }
@@ -564,8 +567,8 @@ float2 *Demod::stage_costas(long n, int L, int nseg, int cur, int nxt, bool mate
             k_dc_tile<0><<<nt, FIR_THREADS, 0, stream>>>(mmin + 16, n, 0, alpha, beta, dc_map.p);
             k_dc_scan<<<1, 1024, 0, stream>>>(dc_map.p, nt, &S->dc_acc2[cur], dc_seeds.p);
             k_dc_apply<0><<<nt, FIR_THREADS, 0, stream>>>(mmin + 16, n, 0, alpha, beta, dc_seeds.p, pdc_out.p + 16, &S->dc_acc2[nxt]);
-            B200_CUDA(cudaMemcpyAsync(pdc_out.p + 8, S->pdc_hist[cur], 8 * sizeof(float2), cudaMemcpyDeviceToDevice, stream));
-            B200_CUDA(cudaMemcpyAsync(S->pdc_hist[nxt], pdc_out.p + 16 + n - 8, 8 * sizeof(float2), cudaMemcpyDeviceToDevice, stream));
+            B200_CUDA(cudaMemcpyAsync(pdc_out.p + 16 - MM_HIST, S->pdc_hist[cur], MM_HIST * sizeof(float2), cudaMemcpyDeviceToDevice, stream));
+            B200_CUDA(cudaMemcpyAsync(S->pdc_hist[nxt], pdc_out.p + 16 + n - MM_HIST, MM_HIST * sizeof(float2), cudaMemcpyDeviceToDevice, stream));
             launches += 3;
             mmin = pdc_out.p;
         }
@@ -588,10 +591,15 @@ void Demod::stage_mm(float2 *mmin, long n, int L, int nseg, int cur, int nxt, in
     const int nblk = (nseg + SEG_THREADS - 1) / SEG_THREADS;
 #define B200_MM_LAUNCH(grid, ...)                                                                                                           \
     do {                                                                                                                                    \
-        if (strict)                                                                                                                         \
-            k_mm<true><<<grid, SEG_THREADS, MM_SMEM_BYTES, stream>>>(__VA_ARGS__);                                                           \
+        if (cfg.clock_recovery == 1) {                                                                                                      \
+            if (strict)                                                                                                                     \
+                k_mm<true, true><<<grid, SEG_THREADS, MM_SMEM_BYTES, stream>>>(__VA_ARGS__);                                                 \
+            else                                                                                                                            \
+                k_mm<false, true><<<grid, SEG_THREADS, MM_SMEM_BYTES, stream>>>(__VA_ARGS__);                                                \
+        } else if (strict)                                                                                                                  \
+            k_mm<true, false><<<grid, SEG_THREADS, MM_SMEM_BYTES, stream>>>(__VA_ARGS__);                                                    \
         else                                                                                                                                \
-            k_mm<false><<<grid, SEG_THREADS, MM_SMEM_BYTES, stream>>>(__VA_ARGS__);                                                          \
+            k_mm<false, false><<<grid, SEG_THREADS, MM_SMEM_BYTES, stream>>>(__VA_ARGS__);                                                   \
     } while (0)
     MMParams MP;
     MP.omega_mid = sps;

@@ -34,6 +34,7 @@ constexpr int RS_THREADS = 256;      // front-end resampler: outputs per CTA
 constexpr int RS_MAX_TAPS = 160;     // taps per polyphase arm
 constexpr int RS_SPAN = 2 * RS_THREADS + RS_MAX_TAPS + 8; // decimation < 2: at most 2 input samples per output
 constexpr int SEG_THREADS = 128;     // threads (= stream segments) per CTA in the loop kernels
+constexpr int MM_HIST = 16;       // inputs of the previous batch kept in the front pad (M&M reaches 7 back, Gardner up to 11)
 constexpr int MM_BANK_STRIDE = 9; // floats per arm row in smem: spreads the per-thread random arm reads over the banks
 constexpr int MM_SMEM_BYTES = 64 * SEG_THREADS * 8 + 128 * MM_BANK_STRIDE * 4;
 
@@ -1317,10 +1318,10 @@ __device__ __forceinline__ float2 rot_steps(float2 v, int q, int order)
 }
 
 // ---------------------------------------------------------------- K2c: apply rotation (+ OQPSK delay) -> M&M input
-// mmin has a 16-sample front pad: mmin[16 + n]; mmin[8..15] = last 8 inputs of the previous batch (hist_in).
+// mmin has a 16-sample front pad: mmin[16 + n]; mmin[0..15] = last MM_HIST inputs of the previous batch (hist_in).
 // `src` is the Costas output (or, with order == 0, the FIR output passed straight through).
 __global__ void k_rotate(const float2 *__restrict__ src, long N, int L, int order, int oqpsk, const uint8_t *__restrict__ quad,
-                         const float2 *__restrict__ hist_in /*8: true pre-delay values*/, float2 *__restrict__ hist_out,
+                         const float2 *__restrict__ hist_in /*MM_HIST: true pre-delay values*/, float2 *__restrict__ hist_out,
                          float2 *__restrict__ mmin)
 {
     const long stride = (long)gridDim.x * blockDim.x;
@@ -1328,9 +1329,9 @@ __global__ void k_rotate(const float2 *__restrict__ src, long N, int L, int orde
         // two samples per thread, 16-byte accesses (src and mmin + 16 are 128-byte aligned; L is a multiple of 16, so a pair never
         // straddles two Costas segments)
         const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
-        if (tid < 8) {
+        if (tid < MM_HIST) {
             const float2 h = hist_in[tid];
-            mmin[8 + tid] = h;
+            mmin[16 - MM_HIST + tid] = h;
         }
         for (long p = tid; 2 * p < N; p += stride) {
             const long n = 2 * p;
@@ -1343,37 +1344,37 @@ __global__ void k_rotate(const float2 *__restrict__ src, long N, int L, int orde
                     b = rot_steps(b, q, order);
                 }
                 *reinterpret_cast<float4 *>(mmin + 16 + n) = make_float4(a.x, a.y, b.x, b.y);
-                if (n >= N - 8)
-                    hist_out[n - (N - 8)] = a;
-                if (n + 1 >= N - 8)
-                    hist_out[n + 1 - (N - 8)] = b;
+                if (n >= N - MM_HIST)
+                    hist_out[n - (N - MM_HIST)] = a;
+                if (n + 1 >= N - MM_HIST)
+                    hist_out[n + 1 - (N - MM_HIST)] = b;
             } else {
                 float2 a = src[n];
                 if (order)
                     a = rot_steps(a, quad[n / L], order);
                 mmin[16 + n] = a;
-                hist_out[n - (N - 8)] = a;
+                hist_out[n - (N - MM_HIST)] = a;
             }
         }
         return;
     }
-    for (long n = (long)blockIdx.x * blockDim.x + threadIdx.x - 8; n < N; n += stride) {
+    for (long n = (long)blockIdx.x * blockDim.x + threadIdx.x - MM_HIST; n < N; n += stride) {
         float2 cur, prev;
         if (n >= 0) {
             cur = src[n];
             if (order)
                 cur = rot_steps(cur, quad[n / L], order);
         } else
-            cur = hist_in[8 + n];
-        if (n >= N - 8 && n >= 0) // (the host rejects batches below 64 samples)
-            hist_out[n - (N - 8)] = cur;
+            cur = hist_in[MM_HIST + n];
+        if (n >= N - MM_HIST && n >= 0) // (the host rejects batches below 64 samples)
+            hist_out[n - (N - MM_HIST)] = cur;
         float2 v = cur;
         if (n - 1 >= 0) {
             prev = src[n - 1];
             if (order)
                 prev = rot_steps(prev, quad[(n - 1) / L], order);
-        } else if (n - 1 >= -8)
-            prev = hist_in[8 + n - 1];
+        } else if (n - 1 >= -MM_HIST)
+            prev = hist_in[MM_HIST + n - 1];
         else
             prev = make_float2(0.f, 0.f);
         v.y = prev.y;
@@ -1386,10 +1387,10 @@ __global__ void k_mm_prep(float2 *__restrict__ src, long N, int L, int order, co
                           float2 *__restrict__ hist_out)
 {
     const int t = threadIdx.x;
-    if (t >= 8)
+    if (t >= MM_HIST)
         return;
-    src[8 + t] = hist_in[t]; // the previous batch's last 8 inputs, already in their final orientation (segment 0 never rotates)
-    const long n = N - 8 + t;
+    src[16 - MM_HIST + t] = hist_in[t]; // the previous batch's last inputs, already in their final orientation (segment 0 never rotates)
+    const long n = N - MM_HIST + t;
     float2 v = src[16 + n];
     if (order)
         v = rot_steps(v, quad[n / L], order);
@@ -1420,10 +1421,13 @@ struct MMRec { int u_final, count, skip, pad; float mu_final, omega_final; int h
 // (volk_32fc_32f_dot_prod_32fc generic; clock_recovery_mm.cpp:103-114 compiled without FMA contraction) -> run as ONE sequential
 // segment on the oracle's own M&M input the symbols must come out BITWISE the oracle's. The production instantiation keeps the
 // two-chain FMA interpolator.
-template <bool STRICT>
+// GARDNER: dsp::GardnerClockRecoveryBlock<complex_t>::work (clock_recovery_gardner.cpp:33-131) instead of the M&M
+// detector: same interpolator bank, omega / mu updates, history and segmentation; the error is zc * (last - sample) with a second
+// interpolation half a symbol back (window u - offzc - 7 .. u - offzc); `p1` after the delay-line shift is last_sample.
 // Fused input fix-up (rot_order != 0 or oqpsk): mmin is then the Costas loop's raw output, and every thread applies the exact
 // rotation by its row's quad[] entry (and the OQPSK one-sample delay of the imaginary rail, delay_one_imag.cpp:18-25) to each 16-sample
 // row of its ring right after the row has landed, instead of a separate pass over the whole stream (k_rotate).
+template <bool STRICT, bool GARDNER>
 __global__ void __launch_bounds__(SEG_THREADS) k_mm(const float2 *__restrict__ mmin /* 16-sample front pad */, long N, int L, int W, int G, int nseg,
                                                      MMParams P, const MMState *__restrict__ st_in, MMState *__restrict__ st_out,
                                                      const float *__restrict__ bank /*128x8*/, float2 *__restrict__ slots, int cap,
@@ -1474,11 +1478,12 @@ __global__ void __launch_bounds__(SEG_THREADS) k_mm(const float2 *__restrict__ m
     // rows of 16 samples; sample n lives in chunk slot ((n + 64) >> 1) & 31; the first window's oldest sample is u-7 (>= -8)
     int r0;
     {
-        const long a = u - 7;
+        const long a = u - 7 - (GARDNER ? 4 : 0); // (the zero-crossing window reaches floor(omega / 2) + 1 <= 3 samples further back)
         r0 = (int)((a >= 0) ? (a >> 4) : -((-a + 15) >> 4));
     }
-    if (oqpsk)
+    if (oqpsk && r0 > -1)
         r0 -= 1; // one more row in front: its last sample's imaginary part is the delay register of the first row that is used
+                 // (row -1 is the front pad: nothing lies in front of it, and its first samples are never read)
     const int rend = (int)((own1 + 15) >> 4); // exclusive: samples < own1 <= N are ever needed
     // iteration `it` makes row r0+it+1 the newest complete row; symbols with u < 16*(r0+it+2) can then be produced
     int nit = active ? max(0, rend - r0) : 0, maxit = nit;
@@ -1546,6 +1551,32 @@ __global__ void __launch_bounds__(SEG_THREADS) k_mm(const float2 *__restrict__ m
                 int imu = (int)rintf(mu * 128.0f);
                 imu = max(0, min(127, imu));
                 const float *tp = &sbank[imu * MM_BANK_STRIDE];
+                float zr = 0.f, zi = 0.f;
+                if (GARDNER) { // zero-crossing sample (clock_recovery_gardner.cpp:49-63,88)
+                    const float muz = (float)((double)mu - (double)omega / 2.0);
+                    int offzc = (int)floor((double)omega / 2.0);
+                    float mupos = (float)fmod((double)__fadd_rn(muz, (float)offzc), 1.0);
+                    if (mupos < 0.f) {
+                        mupos = __fadd_rn(1.0f, mupos);
+                        offzc += 1;
+                    }
+                    int imuz = (int)rintf(__fmul_rn(mupos, 128.0f));
+                    imuz = max(0, min(127, imuz));
+                    const float *tz = &sbank[imuz * MM_BANK_STRIDE];
+                    const int z0 = (int)(u - offzc - 7) + 64;
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        const int na = z0 + k;
+                        const float2 x = ringf[swz16((na >> 1) & 31, lane) * 2 + (na & 1)];
+                        if (STRICT) {
+                            zr = __fadd_rn(zr, __fmul_rn(x.x, tz[k]));
+                            zi = __fadd_rn(zi, __fmul_rn(x.y, tz[k]));
+                        } else {
+                            zr = fmaf(x.x, tz[k], zr);
+                            zi = fmaf(x.y, tz[k], zi);
+                        }
+                    }
+                }
                 const int n0 = (int)(u - 7) + 64; // >= 56
                 float ar = 0.f, ai = 0.f;
                 if (STRICT) {
@@ -1571,11 +1602,16 @@ __global__ void __launch_bounds__(SEG_THREADS) k_mm(const float2 *__restrict__ m
                     ai += bi;
                 }
                 p0 = make_float2(ar, ai);
-                c0 = make_float2(ar > 0.0f ? 1.0f : 0.0f, ai > 0.0f ? 1.0f : 0.0f);
-                // Re[(p0-p2) conj(c1) - (c0-c2) conj(p1)]  (clock_recovery_mm.cpp:103)
-                float xr = (p0.x - p2.x) * c1.x + (p0.y - p2.y) * c1.y;
-                float yr = (c0.x - c2.x) * p1.x + (c0.y - c2.y) * p1.y;
-                float pe = xr - yr;
+                float pe;
+                if (GARDNER) { // zc * (last - sample), last = the previous output (p1 after the shift above); exact clip (:98-100)
+                    pe = STRICT ? __fadd_rn(__fmul_rn(zr, __fsub_rn(p1.x, ar)), __fmul_rn(zi, __fsub_rn(p1.y, ai))) : zr * (p1.x - ar) + zi * (p1.y - ai);
+                } else {
+                    c0 = make_float2(ar > 0.0f ? 1.0f : 0.0f, ai > 0.0f ? 1.0f : 0.0f);
+                    // Re[(p0-p2) conj(c1) - (c0-c2) conj(p1)]  (clock_recovery_mm.cpp:103)
+                    float xr = (p0.x - p2.x) * c1.x + (p0.y - p2.y) * c1.y;
+                    float yr = (c0.x - c2.x) * p1.x + (c0.y - c2.y) * p1.y;
+                    pe = xr - yr;
+                }
                 pe = fminf(1.0f, fmaxf(-1.0f, pe));
                 if (u >= emit0) {
                     if (count < cap)
@@ -1587,8 +1623,12 @@ __global__ void __launch_bounds__(SEG_THREADS) k_mm(const float2 *__restrict__ m
                 else {
                     omega = STRICT ? __fadd_rn(omega, __fmul_rn(P.omega_gain, pe)) : omega + P.omega_gain * pe;
                     float dev = omega - P.omega_mid;
-                    dev = fminf(P.omega_limit, fmaxf(-P.omega_limit, dev));
-                    omega = P.omega_mid + dev;
+                    if (GARDNER) // BRANCHLESS_CLIP with float operands (block.h:10): the two sums in float, the rest in double (:109)
+                        omega = (float)((double)P.omega_mid + 0.5 * (double)__fsub_rn(fabsf(__fadd_rn(dev, P.omega_limit)), fabsf(__fsub_rn(dev, P.omega_limit))));
+                    else {
+                        dev = fminf(P.omega_limit, fmaxf(-P.omega_limit, dev));
+                        omega = P.omega_mid + dev;
+                    }
                     mu = STRICT ? __fadd_rn(__fadd_rn(mu, omega), __fmul_rn(P.mu_gain, pe)) : (mu + omega) + P.mu_gain * pe;
                 }
                 float fl = floorf(mu);

@@ -19,8 +19,8 @@ struct DemodDevState
     float2 rs_tail[2][RS_MAX_TAPS]; // resampler history (ntaps-1 converted input samples)
     float2 dc_acc[2];               // DC blocker accumulator (correct_iq.h: acc)
     float2 dc_acc2[2];              // accumulator of the post-Costas DC blocker
-    float2 pdc_hist[2][8];          // its last 8 outputs: the clock recovery's history across batches
-    float2 mm_hist[2][8];
+    float2 pdc_hist[2][MM_HIST];    // its last outputs: the clock recovery's history across batches
+    float2 mm_hist[2][MM_HIST];
     int flags;          // bit0 AGC clamp, bit1 M&M slot overflow
     int costas_unconv;  // junctions still unconverged after the repair rounds of the last batch
     int mm_unconv;

@@ -161,6 +161,13 @@ b200_demod_cfg demod_cfg_from_params(const Params &p, bool &is_bpsk)
     reject(p, "has_carrier", "PLL carrier tracking");
     reject(p, "enable_doppler", "Doppler correction");
     // BaseDemodModule::initb (module_demod_base.cpp:59-87): outside [min_sps, max_sps] the front-end resampler converts to this rate
+    if (p.has("clock_recovery")) { // B200 extension (no reference module parameter): "gardner" swaps the clock recovery block
+        const std::string cr = p.str("clock_recovery");
+        if (cr == "gardner")
+            c.clock_recovery = 1;
+        else if (cr != "mm")
+            throw ModuleError("clock_recovery must be \"mm\" or \"gardner\"");
+    }
     c.final_samplerate = b200_demod_final_samplerate(c.samplerate, c.symbolrate, c.constellation, (float)p.num("min_sps", 0), (float)p.num("max_sps", 0),
                                                      p.has("custom_samplerate") ? (double)(long)p.num("custom_samplerate") : 0.0);
     if (c.final_samplerate == c.samplerate)

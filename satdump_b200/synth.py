@@ -137,6 +137,17 @@ def puncture_34_metop(coded):
     return e[:, [0, 1, 4, 3]].reshape(-1)
 
 
+# Puncturing patterns that Viterbi_Depunc undoes (src-core/common/codings/viterbi/depunc.h): which of the mother code's symbols of one
+# period (C1, C2 of consecutive bits) are transmitted = the positions where its depuncturers place data rather than an erasure.
+PUNCTURE_KEEP = {"p2/3": (4, [0, 1, 3]), "p3/4": (6, [0, 1, 3, 4]), "p5/6": (10, [0, 1, 3, 4, 7, 8]), "p7/8": (14, [0, 1, 3, 5, 7, 8, 11, 12])}
+
+
+def puncture_dvb(coded, conv):
+    period, keep = PUNCTURE_KEEP[conv]
+    n = coded.size // period * period
+    return coded[:n].reshape(-1, period)[:, keep].reshape(-1)
+
+
 def nrzm_encode(bits):
     return (np.cumsum(bits.astype(np.int64)) & 1).astype(np.uint8)
 
@@ -164,7 +175,7 @@ class SignalCfg:
     samplerate: float = 6e6
     symbolrate: float = 2333333
     constellation: str = "qpsk"     # bpsk | qpsk | oqpsk
-    conv: str = "3/4"               # "1/2" | "3/4" (MetOp order) | "none"
+    conv: str = "3/4"               # "1/2" | "3/4" (MetOp order) | "none" | "p2/3" "p3/4" "p5/6" "p7/8" (Viterbi_Depunc's patterns)
     interleave: int = 4             # RS interleaving depth I
     nrzm: bool = False
     rrc_alpha: float = 0.5
@@ -224,6 +235,11 @@ CONFIGS = {
     # BPSK r=1/2 at 1 Msym/s recorded at 32 MS/s in cs8: ratio 8 -> power-of-two decimator alone (stages /4 and /2), no rational part
     "bpsk_decim8": SignalCfg(name="bpsk_decim8", samplerate=32e6, symbolrate=1000000, constellation="bpsk", conv="1/2", interleave=4,
                              fmt="cs8", decoder="ccsds", ber_thresold=0.3, outsync_after=20, esn0_db=9.0),
+    # ccsds_conv_concat_decoder with conv_rate 2/3 ... 7/8 (Viterbi_Depunc, viterbi_punc.cpp): QPSK + punctured k=7 code + RS I=4
+    "qpsk_p23": SignalCfg(name="qpsk_p23", symbolrate=2400000, conv="p2/3", decoder="ccsds", ber_thresold=0.3, outsync_after=20, esn0_db=9.0),
+    "qpsk_p34": SignalCfg(name="qpsk_p34", symbolrate=2400000, conv="p3/4", decoder="ccsds", ber_thresold=0.3, outsync_after=20, esn0_db=10.0),
+    "qpsk_p56": SignalCfg(name="qpsk_p56", symbolrate=2400000, conv="p5/6", decoder="ccsds", ber_thresold=0.3, outsync_after=20, esn0_db=11.5),
+    "qpsk_p78": SignalCfg(name="qpsk_p78", symbolrate=2400000, conv="p7/8", decoder="ccsds", ber_thresold=0.3, outsync_after=20, esn0_db=12.5),
     # C5: DVB-S2 front half AGC->RRC->M&M, cs8, 45 Msym/s @ 90 MS/s (sps 2.0), alpha 0.25 (DVB_Test.json:132-137), REC_ALPHA 1.7e-3
     "dvbs2_front": SignalCfg(name="dvbs2_front", samplerate=90e6, symbolrate=45000000, constellation="qpsk", conv="none", interleave=4,
                              rrc_alpha=0.25, fmt="cs8", decoder="none", clock_alpha=1.7e-3, carrier_rad=0.0, phase0=0.0, esn0_db=12.0),
@@ -267,6 +283,8 @@ def make_bitstream(cfg: SignalCfg, nframes, seed):
         coded = conv_encode(bits)
         if cfg.conv == "3/4":
             coded = puncture_34_metop(coded)
+        elif cfg.conv in PUNCTURE_KEEP:
+            coded = puncture_dvb(coded, cfg.conv)
     return coded, clear
 
 
@@ -351,7 +369,7 @@ def modulate(cfg: SignalCfg, coded, seed, nsamples=None, device="cpu"):
 
 def frames_for_samples(cfg: SignalCfg, nsamples):
     bps = 1 if cfg.constellation == "bpsk" else 2
-    rate = {"1/2": 0.5, "3/4": 0.75, "none": 1.0}[cfg.conv]
+    rate = {"1/2": 0.5, "3/4": 0.75, "none": 1.0, "p2/3": 2 / 3, "p3/4": 0.75, "p5/6": 5 / 6, "p7/8": 7 / 8}[cfg.conv]
     bits_per_sample = bps * rate / (cfg.samplerate / cfg.symbolrate)
     return int(nsamples * bits_per_sample / (cfg.cadu_bytes * 8)) + 4
 

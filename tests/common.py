@@ -37,13 +37,17 @@ def oracle_demod(O, cfg):
     return O.Demod(O.demod_cfg(**demod_kwargs(cfg)))
 
 
+def conv_rate_of(cfg):
+    return cfg.conv[1:] if cfg.conv.startswith("p") else "1/2"
+
+
 def oracle_fec(O, cfg):
     if cfg.decoder == "simple":
         return O.Fec(O.simple_cfg(cfg.constellation, cfg.cadu_bytes * 8, cfg.interleave, nrzm=cfg.nrzm, qpsk_swap_iq=cfg.constellation == "qpsk"))
     if cfg.decoder == "metop":
         return O.Fec(O.metop_cfg(cfg.ber_thresold, cfg.outsync_after))
     return O.Fec(O.ccsds_cfg(cfg.constellation, cfg.cadu_bytes * 8, cfg.ber_thresold, cfg.outsync_after, cfg.interleave, nrzm=cfg.nrzm,
-                             rs_usecheck=cfg.rs_usecheck))
+                             rs_usecheck=cfg.rs_usecheck, conv_rate=conv_rate_of(cfg)))
 
 
 def gpu_demod(cfg, n, keep_stages=False):

@@ -16,6 +16,8 @@ with the floor measured here, per configuration and stage, as the worst of
 The maxima are extreme-value statistics of a chaotic process (one more interpolator arm, one more sign event), hence eight seeds per
 stage. Everything is deterministic (fixed seeds), so a gate is the same number on every run."""
 import functools
+import json
+import os
 
 import numpy as np
 
@@ -92,7 +94,20 @@ def stage_floor(name, log2n, stage, eps=1e-6, seeds=(1, 2, 3, 4, 5, 6, 7, 8), ex
         if stage == "mm":
             s |= {"soft_" + k: v for k, v in soft_stats(quantise(got, cfg.constellation == "bpsk" and cfg.decoder != "none"), o["soft"]).items()}
         out.append(s)
-    return _worst(out)
+    w = _worst(out)
+    if stage == "mm" and eps > 0:
+        # The largest deviations are excursions at a few fragile spots of the signal (one or two interpolator arms for a few hundred
+        # symbols); which of them a run triggers depends on the perturbation. They are sampled with more seeds and at 1e-5, the
+        # deviation SURVEY 8c itself allows the stages in front (AGC / FIR / Costas <= 1e-5): bpsk_half shows 1.8e-2 in 24 of 24 runs at
+        # 1e-6 and 2.1e-2 ... 3.2e-2 at 1e-5. Only the extreme-value statistics (max, more-than-1-LSB soft bytes) take these runs.
+        for sd in range(1, 17):
+            got = O.run_stage(oc, stage, perturb(src, 1e-5, sd))
+            d = diff_stats(got, want)
+            q = soft_stats(quantise(got, cfg.constellation == "bpsk" and cfg.decoder != "none"), o["soft"])
+            w["max"] = max(w["max"], d["max"])
+            w["soft_gt1"] = max(w["soft_gt1"], q["gt1"])
+            w["soft_max"] = max(w["soft_max"], q["max"])
+    return w
 
 
 @functools.lru_cache(maxsize=64)
@@ -136,6 +151,32 @@ def chain_floor(name, log2n, eps=1e-6, seeds=(1, 2, 3), extra=()):
         for k in ("frac", "max", "mean"):
             w["costas_" + k] = max(w["costas_" + k], c[k])
     return w
+
+
+# ---- committed cache: the floors are deterministic functions of the committed synthetic signals and the compiled reference, and cost
+# 10-20 s of CPU each; tests/golden/floors.json holds them (tests/golden/make_floors.py regenerates it, tests/test_floors.py re-measures
+# a sample of the entries against it), so the GPU box does not spend its minutes on them.
+_CACHE_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "floors.json")
+_cache = None
+
+
+def _key(kind, name, log2n, stage, eps, extra):
+    return "|".join([kind, name, str(log2n), str(stage), repr(float(eps)), repr(tuple(extra))])
+
+
+def cached(kind, name, log2n, stage=None, eps=1e-6, extra=()):
+    """stage_floor / chain_floor through the committed cache (computed and remembered in memory when the entry is missing)."""
+    global _cache
+    if _cache is None:
+        try:
+            with open(_CACHE_PATH) as f:
+                _cache = json.load(f)
+        except Exception:
+            _cache = {}
+    k = _key(kind, name, log2n, stage, eps, extra)
+    if k not in _cache:
+        _cache[k] = stage_floor(name, log2n, stage, eps, extra=tuple(extra)) if kind == "stage" else chain_floor(name, log2n, eps, extra=tuple(extra))
+    return _cache[k]
 
 
 def gate(survey, floor):

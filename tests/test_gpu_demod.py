@@ -14,7 +14,7 @@ import numpy as np
 import pytest
 
 from tests.common import gpu_demod, nsamples, oracle, oracle_demod, signal
-from tests.floors import SURVEY, chain_floor, gate
+from tests.floors import SURVEY, cached, gate
 
 pytestmark = pytest.mark.gpu
 CONFIGS = ["metop_ahrpt", "bpsk_half", "jpss_hrd", "dvbs2_front", "hrpt_bpsk", "psk8", "metop_oversampled", "bpsk_decim8"]
@@ -80,7 +80,7 @@ def test_stage_parity(built, name):
     if g.cfg.final_samplerate > 0:  # front-end resampler (hrpt_bpsk): same length, same samples
         rs = O.resample(oracle_demod(O, cfg).cfg, raw)
         assert g.stage("resamp").size == rs.size == o["front"] and np.abs(g.stage("resamp") - rs).max() <= 2e-6
-    fl = chain_floor(name, 21)
+    fl = cached("chain", name, 21)
     for st in ("agc", "fir"):
         d = np.abs(g.stage(st) - o[st])
         assert d.max() <= 1e-5, (st, float(d.max()), int(np.argmax(d)))
@@ -113,7 +113,7 @@ def test_streaming_pushes_continue_the_same_stream(built, name, cuts):
         syms.append(g.symbols())
         soft.append(g.soft())
         prev = c
-    check_mm(np.concatenate(syms), o["mm"], np.concatenate(soft), o["soft"], floor=chain_floor(name, 21))
+    check_mm(np.concatenate(syms), o["mm"], np.concatenate(soft), o["soft"], floor=cached("chain", name, 21))
     s = g.stats()
     assert s["costas_unconverged"] == 0 and s["mm_unconverged"] == 0
 
@@ -253,7 +253,7 @@ def test_post_costas_dc(built):
     n = nsamples(raw, cfg)
     o = O.Demod(O.demod_cfg(post_costas_dc=True, **demod_kwargs(cfg))).run(raw)
     g = capi.Demod(capi.demod_cfg(max_batch=n, keep_stages=True, post_costas_dc=True, **demod_kwargs(cfg))).push(raw)
-    fl = chain_floor("bpsk_half", 20, extra=(("post_costas_dc", True),))
+    fl = cached("chain", "bpsk_half", 20, extra=(("post_costas_dc", True),))
     check_costas(g.stage("costas"), o["costas"], fl)
     check_mm(g.symbols(), o["mm"], g.soft(), o["soft"], floor=fl)
     g2 = capi.Demod(capi.demod_cfg(max_batch=n, keep_stages=True, post_costas_dc=True, **demod_kwargs(cfg)))

@@ -15,10 +15,10 @@ import pytest
 
 from tests import floors
 from tests.common import gpu_demod, nsamples, oracle
-from tests.floors import SURVEY, diff_stats, gate, reference_run, stage_floor
+from tests.floors import SURVEY, cached, diff_stats, gate, reference_run
 
 pytestmark = pytest.mark.gpu
-CONFIGS = ["metop_ahrpt", "bpsk_half", "jpss_hrd", "dvbs2_front", "hrpt_bpsk", "psk8"]
+CONFIGS = ["metop_ahrpt", "bpsk_half", "jpss_hrd", "dvbs2_front", "hrpt_bpsk", "psk8", "metop_oversampled", "bpsk_decim8"]
 LG = 21
 
 
@@ -41,7 +41,7 @@ def test_mm_fed_the_oracles_input(built, name):
     g = gpu_demod(cfg, nsamples(raw, cfg))
     mm_in = o["fir"] if o["costas"] is None else o["costas"]
     assert bitwise(g.run_stage("mm", mm_in, strict=True, sequential=True), o["mm"])
-    fl = stage_floor(name, LG, "mm")
+    fl = cached("stage", name, LG, "mm")
     for sequential in (True, False):  # production arithmetic: one segment / the production segmentation
         d = diff_stats(g.run_stage("mm", mm_in, sequential=sequential), o["mm"])
         assert d["frac"] <= gate(SURVEY["mm_frac"], fl["frac"]) and d["max"] <= gate(SURVEY["mm_max"], fl["max"]), (sequential, d, fl)
@@ -53,7 +53,7 @@ def test_costas_fed_the_oracles_fir_output(built, name):
     g = gpu_demod(cfg, nsamples(raw, cfg))
     d = diff_stats(g.run_stage("costas", o["fir"], sequential=True), o["costas"])
     assert d["max"] <= SURVEY["float_all"], d
-    fl = stage_floor(name, LG, "costas")
+    fl = cached("stage", name, LG, "costas")
     d = diff_stats(g.run_stage("costas", o["fir"]), o["costas"])
     assert d["median"] <= 1e-6, d  # nothing systematic (the mean would count the rare sign-decision events)
     assert d["frac"] <= gate(0.0, fl["frac"]) + 1e-5 and d["max"] <= gate(SURVEY["float_all"], fl["max"]) * (2 if fl["frac"] == 0 else 1), (d, fl)
@@ -70,3 +70,32 @@ def test_junction_residuals_are_small(built):
     assert np.median(np.abs(mj[1:])) <= 1e-4 and np.abs(mj[1:]).max() <= 0.01, (float(np.median(np.abs(mj[1:]))), float(np.abs(mj[1:]).max()))
     s = g.stats()
     assert s["costas_unconverged"] == 0 and s["mm_unconverged"] == 0
+
+
+@pytest.mark.parametrize("name", ["metop_ahrpt", "bpsk_half"])
+def test_gardner_clock_recovery(built, name):
+    """SURVEY row G: dsp::GardnerClockRecoveryBlock<complex_t> (clock_recovery_gardner.cpp:33-131) as a variant of the clock recovery
+    kernel. Strict sequential: BITWISE the reference block on the reference's own input; production arithmetic / segmentation and the
+    whole chain within the floor gates; CADUs of the chain bit-exact against the reference chain built with the same block."""
+    from satdump_b200 import capi
+    from tests.common import demod_kwargs, gpu_fec_cfg, oracle_fec
+    from tests.test_gpu_demod import check_mm
+    O = oracle()
+    gx = (("clock_recovery", "gardner"),)
+    cfg, raw, oc, o = reference_run(name, LG, gx)
+    n = nsamples(raw, cfg)
+    g = capi.Demod(capi.demod_cfg(max_batch=n, clock_recovery="gardner", **demod_kwargs(cfg)))
+    mm_in = o["costas"]
+    assert bitwise(g.run_stage("mm", mm_in, strict=True, sequential=True), o["mm"])
+    fl = cached("stage", name, LG, "mm", extra=gx)
+    for sequential in (True, False):
+        d = diff_stats(g.run_stage("mm", mm_in, sequential=sequential), o["mm"])
+        assert d["frac"] <= gate(SURVEY["mm_frac"], fl["frac"]) and d["max"] <= gate(SURVEY["mm_max"], fl["max"]), (sequential, d, fl)
+    g.push(raw)
+    check_mm(g.symbols(), o["mm"], g.soft(), o["soft"], floor=cached("chain", name, LG, extra=gx))
+    s = g.stats()
+    assert s["costas_unconverged"] == 0 and s["mm_unconverged"] == 0
+    want = oracle_fec(O, cfg).run(o["soft"])["cadu"].reshape(-1, cfg.cadu_bytes)
+    ch = capi.Chain(capi.demod_cfg(max_batch=n, clock_recovery="gardner", **demod_kwargs(cfg)), gpu_fec_cfg(cfg, 2 * n)).push(raw)
+    got = ch.frames()
+    assert want.shape[0] >= 50 and got.shape == want.shape and np.array_equal(got, want)
