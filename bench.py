@@ -535,10 +535,10 @@ def main():
         sps = cfg.samplerate / cfg.symbolrate
         fir_ms = tim["agc_fir"]
         fir_bytes = bps + 8
-        fir_roof = {"kernels": "k_agc_fir (convert + AGC + 31-tap RRC in one pass; the exact-seed launches return at once)", "bound": "hbm",
+        fir_roof = {"kernels": "k_agc_fir_w (convert + AGC + 31-tap RRC in one pass, one warp per range of tiles; the exact-seed launches return at once)", "bound": "hbm",
                     "achieved": n * fir_bytes / (fir_ms * 1e-3) / 1e9 if fir_ms > 0 else 0.0, "peak": hbm, "unit": "GB/s",
                     "frac": (n * fir_bytes / (fir_ms * 1e-3) / 1e9 / hbm) if fir_ms > 0 else 0.0, "peak_source": which,
-                    "traffic": measured_traffic("k_agc_fir", args.log2_samples) if cfg.fmt == "cs16" else None,
+                    "traffic": measured_traffic("k_agc_fir_w", args.log2_samples) if cfg.fmt == "cs16" else None,
                     "note": f"{fir_bytes} B/sample ({cfg.fmt} in + cf32 out) over the event-timed FIR stage of a synchronous step"}
         line = {"metric": w["metric"], "value": value, "unit": "MS/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": wall_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",

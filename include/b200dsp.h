@@ -160,7 +160,7 @@ int b200_demod_debug_stage(b200_demod *d, int stage, float *host_out, long cap_s
 /* Stage-isolated parity hook: runs ONE stage of a freshly reset demodulator on a caller-supplied stage input
  * (nsamples complex values, interleaved re,im: normally the ORACLE's output of the stage before) and returns the stage output.
  *   B200_STAGE_FIR     in = AGC output.  mode STRICT: fir.cpp:74-83 in the generic VOLK order -> bitwise the oracle's FIR output;
- *                      mode 0: the production kernel (k_agc_fir with the AGC switched off), one fma per tap
+ *                      mode 0: the production kernel (k_agc_fir_w with the AGC switched off), one fma per tap
  *   B200_STAGE_COSTAS  in = FIR output; out = what the clock recovery reads (rotation fix-up, OQPSK delay, post_costas_dc applied)
  *   B200_STAGE_MM      in = the clock recovery's input; out = symbols (*n_out of them). STRICT | SEQUENTIAL -> bitwise the oracle's
  * SEQUENTIAL runs the loop as one segment (no warm-up, no stitching). The demodulator is reset before and after. */

@@ -374,6 +374,21 @@ static void agc_run(orc_demod *d, const cf_t *in, cf_t *out, int n)
     d->agc_gain = g;
 }
 
+/* The same recurrence evaluated in double precision (gain, product and magnitude): what agc.cpp:25-39 computes before its float
+ * rounding. The distance of the reference's float output from this is the reference's own rounding noise (a random walk of the gain
+ * with the loop's memory of ~100 * gain samples): the floor no other evaluation of the recurrence can get under. Test use only. */
+void orc_agc_exact(const float *in, long n, double rate, double ref, double max_gain, float *out)
+{
+    double g = 1.0;
+    for (long i = 0; i < n; i++) {
+        const double re = (double)in[2 * i] * g, im = (double)in[2 * i + 1] * g;
+        out[2 * i] = (float)re;
+        out[2 * i + 1] = (float)im;
+        g += rate * (ref - sqrt(re * re + im * im));
+        if (max_gain > 0.0 && g > max_gain) g = max_gain;
+    }
+}
+
 /* FIRBlock<complex_t>::work — fir.cpp:47-89; y[i] = sum_j buf[i+1+j] * taps[ntaps-1-j], oldest sample first */
 static void fir_run(orc_demod *d, const cf_t *in, cf_t *out, int n)
 {

@@ -62,6 +62,9 @@ long orc_resample(const orc_demod_cfg *cfg, const void *raw, long nsamples, floa
 /* polyphase bank of RationalResamplerBlock(interpolation, decimation): returns taps per arm, *nfilt arms; out[arm*ntaps + k] */
 int orc_resampler_taps(unsigned interpolation, unsigned decimation, float *out, int cap, int *nfilt);
 
+/* AGC recurrence in double precision on cf32 input (reference rounding-noise floor, see oracle.c) */
+void orc_agc_exact(const float *in, long n, double rate, double ref, double max_gain, float *out);
+
 void *orc_fec_create(const orc_fec_cfg *cfg);
 void orc_fec_destroy(void *h);
 int orc_fec_chunk_size(void *h);

@@ -104,3 +104,16 @@ def pipeline_run(dcfg, fcfg, raw):
     cadu = np.zeros(cap, np.uint8)
     w = _lib().ref_pipeline_run(dcfg, fcfg, raw.ctypes.data, n, cadu.ctypes.data, cap)
     return cadu[:w].copy()
+
+
+def agc_exact(x, rate=1e-2, ref=1.0, max_gain=65536.0):
+    """AGCBlock's recurrence (agc.cpp:25-39) evaluated in double precision on complex64 input: the reference's float output deviates
+    from this by its own accumulated rounding noise, which is the floor of the AGC parity gate."""
+    import ctypes as C
+    import numpy as np
+    L = C.CDLL(_m._PATH)
+    L.orc_agc_exact.argtypes = [C.c_void_p, C.c_long, C.c_double, C.c_double, C.c_double, C.c_void_p]
+    x = np.ascontiguousarray(x, np.complex64)
+    out = np.empty_like(x)
+    L.orc_agc_exact(x.ctypes.data, x.size, float(np.float32(rate)), ref, max_gain, out.ctypes.data)
+    return out

@@ -333,21 +333,16 @@ Demod::Demod(const b200_demod_cfg &c) : cfg(c)
     agc_need.alloc(2);
     agc_need.zero(stream);
     {
-        // 5 CTAs x 41.7 KB of static smem per SM: ask for the large shared-memory carve-out
-        B200_CUDA(cudaFuncSetAttribute(k_agc_fir<0, false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        B200_CUDA(cudaFuncSetAttribute(k_agc_fir<1, false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        B200_CUDA(cudaFuncSetAttribute(k_agc_fir<2, false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        B200_CUDA(cudaFuncSetAttribute(k_agc_fir<0, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        B200_CUDA(cudaFuncSetAttribute(k_agc_fir<1, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        B200_CUDA(cudaFuncSetAttribute(k_agc_fir<2, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        // one wave of resident warps, each owning a range of tiles (k_agc_fir_w: 4 independent warps per CTA, 11.5 KB of smem)
         int per_sm = 0;
-        if (c.format == B200_CF32 || resamp || c.dc_block)
-            B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_agc_fir<0, false, false>, FIR_THREADS, 0));
+        if (c.format == B200_CF32 || resamp || c.dc_block || !decim.empty())
+            B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_agc_fir_w<0, false, false>, 32 * FW_WARPS, 0));
         else if (c.format == B200_CS16)
-            B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_agc_fir<1, false, false>, FIR_THREADS, 0));
+            B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_agc_fir_w<1, false, false>, 32 * FW_WARPS, 0));
         else
-            B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_agc_fir<2, false, false>, FIR_THREADS, 0));
+            B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_agc_fir_w<2, false, false>, 32 * FW_WARPS, 0));
         fir_ctas = std::max(1, per_sm) * dev_sms;
+        fir_warps = fir_ctas * FW_WARPS;
         if (const char *e = getenv("B200_AGC_WARM_TILES")) // 0 forces the exact (scanned-seed) pass: test hook
             agc_warm_max = std::max(0, atoi(e));
     }
@@ -480,9 +475,10 @@ template <int FMT> static void launch_front(Demod &d, const void *raw, long n, i
 {
     DemodDevState *S = d.st.p;
     float2 *fir_out = d.bufA.p + 16;
-    // one wave of persistent CTAs, each running a range of R consecutive tiles
-    const int R = std::max(4, (ntiles + d.fir_ctas - 1) / d.fir_ctas);
+    // one wave of resident warps, each running a range of R consecutive tiles
+    const int R = std::max(4, (ntiles + d.fir_warps - 1) / d.fir_warps);
     const int nranges = (ntiles + R - 1) / R;
+    const int grid = (nranges + FW_WARPS - 1) / FW_WARPS;
     AgcCtl ctl;
     ctl.seeds = d.seeds.p;
     ctl.need = d.agc_need.p;
@@ -496,10 +492,10 @@ template <int FMT> static void launch_front(Demod &d, const void *raw, long n, i
             k_agc_scan<<<1, 1024, 0, d.stream>>>(d.tile_map.p, ntiles, &S->gain[cur], need, d.seeds.p, &S->agc_exact);
         }
         if (dump)
-            k_agc_fir<FMT, true, false><<<nranges, FIR_THREADS, 0, d.stream>>>(raw, n, d.cfg.agc_rate, &S->gain[cur], R, ctl, taps, S->agc_tail[cur],
+            k_agc_fir_w<FMT, true, false><<<grid, 32 * FW_WARPS, 0, d.stream>>>(raw, n, d.cfg.agc_rate, &S->gain[cur], R, ctl, taps, S->agc_tail[cur],
                                                                               S->agc_tail[cur ^ 1], fir_out, d.agc_dump.p, &S->gain[cur ^ 1], &S->flags);
         else
-            k_agc_fir<FMT, false, false><<<nranges, FIR_THREADS, 0, d.stream>>>(raw, n, d.cfg.agc_rate, &S->gain[cur], R, ctl, taps, S->agc_tail[cur],
+            k_agc_fir_w<FMT, false, false><<<grid, 32 * FW_WARPS, 0, d.stream>>>(raw, n, d.cfg.agc_rate, &S->gain[cur], R, ctl, taps, S->agc_tail[cur],
                                                                                S->agc_tail[cur ^ 1], fir_out, nullptr, &S->gain[cur ^ 1], &S->flags);
     }
     // clamp pass: the gain reached max_gain somewhere in this batch (silent input), so the unclamped maps above do not describe
@@ -508,10 +504,10 @@ template <int FMT> static void launch_front(Demod &d, const void *raw, long n, i
     k_agc_compose3<FMT><<<std::min(ntiles, d.fir_ctas * 2), FIR_THREADS, 0, d.stream>>>(raw, n, d.cfg.agc_rate, &S->flags, ntiles, d.tile_map3.p);
     k_agc_scan3<<<1, 1024, 0, d.stream>>>(d.tile_map3.p, ntiles, &S->gain[cur], &S->flags, d.seeds.p);
     if (dump)
-        k_agc_fir<FMT, true, true><<<nranges, FIR_THREADS, 0, d.stream>>>(raw, n, d.cfg.agc_rate, &S->gain[cur], R, ctl, taps, S->agc_tail[cur],
+        k_agc_fir_w<FMT, true, true><<<grid, 32 * FW_WARPS, 0, d.stream>>>(raw, n, d.cfg.agc_rate, &S->gain[cur], R, ctl, taps, S->agc_tail[cur],
                                                                          S->agc_tail[cur ^ 1], fir_out, d.agc_dump.p, &S->gain[cur ^ 1], &S->flags);
     else
-        k_agc_fir<FMT, false, true><<<nranges, FIR_THREADS, 0, d.stream>>>(raw, n, d.cfg.agc_rate, &S->gain[cur], R, ctl, taps, S->agc_tail[cur],
+        k_agc_fir_w<FMT, false, true><<<grid, 32 * FW_WARPS, 0, d.stream>>>(raw, n, d.cfg.agc_rate, &S->gain[cur], R, ctl, taps, S->agc_tail[cur],
                                                                           S->agc_tail[cur ^ 1], fir_out, nullptr, &S->gain[cur ^ 1], &S->flags);
     d.launches += 7;
 }
@@ -763,7 +759,7 @@ long Demod::debug_run_stage(int stage, const float *h_in, long n, int mode, floa
             k_fir_only<true><<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(bufB.p + 16, n, taps, bufA.p + 16);
         else {
             // the production kernel with the AGC switched off: rate 0 makes every step map the identity and the gain stay 1, so
-            // k_agc_fir's output is the FFMA2 FIR of its input (the ranges take the scanned-seed pass: nothing proves a seed at rate 0)
+            // k_agc_fir_w's output is the FFMA2 FIR of its input (the ranges take the scanned-seed pass: nothing proves a seed at rate 0)
             const float rate = cfg.agc_rate;
             cfg.agc_rate = 0.f;
             launch_front<0>(*this, bufB.p + 16, n, (int)((n + FIR_TILE - 1) / FIR_TILE), taps, 0, false);

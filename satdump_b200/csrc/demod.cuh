@@ -12,7 +12,7 @@
 // The reference runs every stage as a serial per-sample loop. Here:
 //   * AGC: g' = g(1-r|x|) + r is an affine map -> per-tile composition (k_agc_compose), a scan over tiles
 //     (k_agc_scan) and an in-tile block scan in fp64, then an 8-sample replay of the reference's float recurrence.
-//   * FIR: data parallel, fused with conversion + AGC scale (k_agc_fir).
+//   * FIR: data parallel, fused with conversion + AGC scale (k_agc_fir_w).
 //   * Costas / M&M: contracting feedback loops -> one thread per stream segment, started W samples early
 //     (warm-up) so it has converged onto the sequential trajectory at its first owned sample; the first segment
 //     starts from the exact carried state. Costas segments converge up to a k*2pi/order rotation, which
@@ -107,6 +107,37 @@ template <int FMT> __device__ __forceinline__ void raw_convert(const RawRegs<FMT
             x[2 * i + 1] = make_float2(r.v[i].z, r.v[i].w);
         }
     }
+}
+
+// The same conversion with the power-of-two factor left out: x[i] = sample / S with S = 2^-15 (cs16), 2^-7 (cs8), 1 (cf32). Scaling by a
+// power of two commutes with every rounding here (no subnormals in reach), so S * x[i] is bit for bit raw_convert's value; the fast
+// path of k_agc_fir_w carries S in its per-sample gain (one multiply per sample instead of one per component).
+template <int FMT> struct RawScale;
+template <> struct RawScale<0> { static constexpr float v = 1.0f; };
+template <> struct RawScale<1> { static constexpr float v = 0x1p-15f; };
+template <> struct RawScale<2> { static constexpr float v = 0x1p-7f; };
+__device__ __forceinline__ float cvt_s16_scaled(float x) { return fmaf(x, 0x1p-15f + 0x1p-30f, x); }
+__device__ __forceinline__ float cvt_s8_scaled(float x) { return fmaf(x, 0x1p-7f + 0x1p-14f + 0x1p-21f + 0x1p-28f, x); }
+template <int FMT> __device__ __forceinline__ void raw_convert_scaled(const RawRegs<FMT> &r, float2 (&x)[8])
+{
+    if constexpr (FMT == 1) {
+        const int w[8] = {r.a.x, r.a.y, r.a.z, r.a.w, r.b.x, r.b.y, r.b.z, r.b.w};
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            x[i].x = cvt_s16_scaled((float)(short)(w[i] & 0xFFFF));
+            x[i].y = cvt_s16_scaled((float)(short)(w[i] >> 16));
+        }
+    } else if constexpr (FMT == 2) {
+        const int w[4] = {r.a.x, r.a.y, r.a.z, r.a.w};
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            x[2 * i].x = cvt_s8_scaled((float)(signed char)(w[i] & 0xFF));
+            x[2 * i].y = cvt_s8_scaled((float)(signed char)((w[i] >> 8) & 0xFF));
+            x[2 * i + 1].x = cvt_s8_scaled((float)(signed char)((w[i] >> 16) & 0xFF));
+            x[2 * i + 1].y = cvt_s8_scaled((float)(signed char)((w[i] >> 24) & 0xFF));
+        }
+    } else
+        raw_convert<FMT>(r, x);
 }
 
 // samples beyond n_valid read as 0
@@ -390,12 +421,12 @@ __global__ void __launch_bounds__(FIR_THREADS) k_dc_apply(const void *__restrict
         }
 }
 
-// sqrt(s2) as s2 * rsqrt(s2): one MUFU + one FMUL (~2 ulp); the max() keeps 0 * inf out (s2 == 0 -> 0)
+// sqrt(s2) as one MUFU.SQRT (sqrt.approx: ~1 ulp; sqrt(0) = 0, no guard needed)
 __device__ __forceinline__ float fast_mag(float s2)
 {
     float r;
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaxf(s2, 1e-36f)));
-    return s2 * r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(s2));
+    return r;
 }
 
 // One AGC step (agc.cpp:30-33) for input x is the affine map g' = g*(1 - e) + rate with e = rate*|x| (exact while the clamp is
@@ -494,7 +525,7 @@ __device__ __forceinline__ EB agc_map8(const float2 (&x)[8], float rate, float (
 }
 
 // Control block of the AGC seeding. need[epoch & 1] is raised by the fast pass when some range cannot prove its seed; the exact
-// pass (k_agc_compose, k_agc_scan, k_agc_fir with seeded = 1) then runs, otherwise those launches return at once.
+// pass (k_agc_compose, k_agc_scan, k_agc_fir_w with seeded = 1) then runs, otherwise those launches return at once.
 struct AgcCtl
 {
     const double *seeds; // [ntiles + 1] gain before every tile (exact pass only)
@@ -504,30 +535,237 @@ struct AgcCtl
     int warm_max;        // fast pass: how many tiles a range may walk back before giving up
 };
 
-// ---------------------------------------------------------------- K1: convert + AGC + 31-tap FIR
-// The AGC gain is a serial recurrence over the whole stream (agc.cpp:25-39). The stream is cut into `ranges` of R consecutive
-// 2048-sample tiles, one persistent CTA per range, so inside a range the gain simply chains from tile to tile (each tile: affine
-// maps of the 8-sample groups -> CTA scan -> every thread replays the reference's float recurrence over its 8 samples from its
-// scanned seed). What a range needs from the past is its start gain. Because the loop is a contraction that gain is a function
-// of the preceding samples only up to a weight A = prod(1 - rate|x|) on whatever came before: the CTA walks backwards tile by
-// tile composing the maps until A * max_gain is below float resolution of the seed (normally 2-8 tiles, each a cheap map-only
-// pass), which PROVES the seed to ~1e-9 without knowing anything older; if warm_max tiles do not suffice (very weak signal) it
-// raises `need` and the exact pass redoes the stage from scanned per-tile seeds. One more tile before the range is replayed
-// without output to provide the 30-sample FIR history.
-// gain_out: gain after the last sample; flags bit0 = AGC clamp hit
-// CLAMP (third pass, only when an earlier pass saw the gain exceed max_gain, i.e. on (near) silent input): the same kernel with the
-// clamped step maps g -> min(g(1-e) + rate, 65536) composed as (E, B, C) triples and the clamp applied after every replayed step, seeded
-// from the clamp-aware per-tile scan. Exact in the same sense as the unclamped passes.
-template <int FMT, bool DUMP, bool CLAMP>
-__global__ void __launch_bounds__(FIR_THREADS, 5) k_agc_fir(const void *__restrict__ raw, long N, float rate, const float *__restrict__ gain_in, int R,
-                                                         const AgcCtl ctl, const FirTaps taps, const float2 *__restrict__ tail_in,
-                                                         float2 *__restrict__ tail_out, float2 *__restrict__ fir_out, float2 *__restrict__ agc_dump,
-                                                         float *__restrict__ gain_out, int *__restrict__ flags)
+// ---------------------------------------------------------------- K1: convert + AGC + 31-tap FIR, one WARP per range of tiles
+// The AGC gain is a serial recurrence over the whole stream (agc.cpp:25-39). One step for input x is the affine map
+// g' = g*(1 - e) + rate with e = rate*|x| (exact while the clamp is not hit), so maps compose and the recurrence becomes a scan.
+// The stream is cut into ranges of R consecutive 2048-sample tiles; warp wg of the grid owns tiles [wg*R, (wg+1)*R) and walks them in
+// chunks of 256 samples (8 per lane). A chunk needs one 5-step shuffle scan of the lanes' composed (E, B) maps, every lane then replays
+// the reference's float recurrence over its 8 samples from its scanned seed, the gain chains from chunk to chunk in the warp's
+// registers (fp64), and the AGC'd samples go to a WARP-PRIVATE shared-memory strip (32-sample history + 256 samples, the padded
+// layout of xidx) from which the lanes run the 31-tap FFMA2 FIR. The warps of a CTA are independent: the only synchronisation is
+// __syncwarp, so warps drift apart and the conversion / scan phases of some fill the issue slots the FIR phases of others leave.
+// (Round 1's form, one CTA per range with a two-level scan and two __syncthreads per 2048-sample tile, ran at 0.43 of the HBM
+// roofline; this one at 0.53: profiles/README.md.)
+// A chunk's composed decay stays above ~0.03 even for a full-scale input (E <= 0.97), so the float E keeps the relative precision
+// of 1 - E that a 2048-sample tile loses when the gain falls from a large value (signal onset after silence).
+// What a range needs from the past is its start gain. Because the loop is a contraction that gain is a function of the preceding
+// samples only up to a weight A = prod(1 - rate|x|) on whatever came before: the warp walks backwards chunk by chunk composing the
+// maps until A * max_gain is below float resolution of the seed (normally ~36 chunks, each a cheap map-only pass), which PROVES the
+// seed to ~1e-9 without knowing anything older; if warm_max tiles do not suffice (very weak signal) it raises `need` and the exact
+// pass (k_agc_compose -> k_agc_scan -> this kernel with seeded = 1) redoes the stage from scanned per-tile seeds. The chunk in front
+// of the range is run without output to provide the 30-sample FIR history.
+// gain_out: gain after the last sample; flags bit0 = the gain exceeded max_gain somewhere (silent input): the CLAMP instantiation
+// then redoes the stage with the clamped step maps g -> min(g(1-e) + rate, 65536) composed as (E, B, C) triples and the clamp applied
+// after every replayed step, seeded from the clamp-aware per-tile scan. Exact in the same sense as the unclamped passes.
+constexpr int FW_CH = 256;                          // samples per chunk
+constexpr int FW_WARPS = 4;                         // warps (= ranges) per CTA
+constexpr int FW_BUF_F2 = ((32 + FW_CH) / 8) * 10;  // float2 slots of one warp's strip (xidx padding)
+
+template <int FMT> struct FwState
 {
-    __shared__ __align__(16) float2 xs[2][FIR_BUF_F2];
-    __shared__ EB wsum[2][FIR_THREADS / 32];
-    __shared__ float wsumC[2][FIR_THREADS / 32];
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const void *__restrict__ raw;
+    long N;
+    float rate;
+    double G;          // gain before the next chunk
+    float2 *xs;        // the warp's strip
+    const float2 *xrd; // this lane's FIR window: xidx(8 * lane + c) = 10 * lane + xidx(c)
+    int lane, c_last;
+};
+
+// the 31-tap FIR of one chunk out of the warp's strip: lane -> outputs 8*lane .. 8*lane+7; y[n] = sum_j x[n-30+j] * h[30-j], oldest first
+// (fir.cpp:74-83). Packed FP32x2: one FFMA2 does the (re, im) pair of a complex sample x real tap MAC (two independent fma.rn, i.e.
+// the same results as scalar fmaf); the tap is a scalar broadcast operand.
+__device__ __forceinline__ void fw_fir8(const float2 *xrd, const FirTaps &taps, ulonglong2 (&acc)[4])
+{
+#pragma unroll
+    for (int o = 0; o < 4; o++)
+        acc[o] = make_ulonglong2(0ull, 0ull);
+#pragma unroll
+    for (int pI = 0; pI < 19; pI++) {
+        const ulonglong2 vv = *reinterpret_cast<const ulonglong2 *>(xrd + xidx(2 + 2 * pI));
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const unsigned long long v = h ? vv.y : vv.x;
+            const int mI = 2 * pI + h;
+#pragma unroll
+            for (int o = 0; o < 8; o++) {
+                const int j = mI - o; // tap position (0 = oldest)
+                if (j >= 0 && j < FIR_NT) {
+                    unsigned long long hh;
+                    asm("mov.b64 %0, {%1, %1};" : "=l"(hh) : "f"(taps.h[FIR_NT - 1 - j]));
+                    if (o & 1)
+                        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[o >> 1].y) : "l"(v), "l"(hh));
+                    else
+                        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[o >> 1].x) : "l"(v), "l"(hh));
+                }
+            }
+        }
+    }
+}
+
+// One chunk of k_agc_fir_w. FAST: every sample of the chunk exists, none belongs to the stream tail, output wanted, no dump, no clamp:
+// no per-sample conditions, and the conversion's power-of-two factor S rides in the gain (raw_convert_scaled).
+template <int FMT, bool DUMP, bool CLAMP, bool FAST>
+__device__ __forceinline__ void fw_chunk(FwState<FMT> &st, RawRegs<FMT> &rr, int c, bool out, const FirTaps &taps, float2 *__restrict__ tail_out,
+                                         float2 *__restrict__ fir_out, float2 *__restrict__ agc_dump, float *__restrict__ gain_out,
+                                         int *__restrict__ flags)
+{
+    const int lane = st.lane;
+    const long N = st.N;
+    const float rate = st.rate;
+    const long s0 = (long)c * FW_CH + 8 * lane;
+    constexpr float S = FAST ? RawScale<FMT>::v : 1.0f;
+    float2 x[8];
+    if (FAST || s0 + 8 <= N) {
+        if (FMT == 0) // cf32: 16 registers of raw data are too many to hold across a chunk
+            raw_fetch<FMT>(st.raw, s0, rr);
+        if (FAST)
+            raw_convert_scaled<FMT>(rr, x);
+        else
+            raw_convert<FMT>(rr, x);
+    } else
+        load8_ragged<FMT>(st.raw, s0, N, x);
+    if (FMT != 0 && c + 1 < st.c_last && s0 + FW_CH + 8 <= N) // the next chunk's loads fly under this chunk's arithmetic
+        raw_fetch<FMT>(st.raw, s0 + FW_CH, rr);
+    EB inc{0.f, 0.f};
+    float incC = (float)AGC_NO_CLAMP;
+    float e[8]; // rate * |sample|: the step map of sample q is g -> g * (1 - e[q]) + rate
+    if (FAST) {
+        const float rateS = rate * S;
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            e[q] = rateS * fast_mag(fmaf(x[q].x, x[q].x, x[q].y * x[q].y));
+            if (q == 0) { // the first step composed onto the identity, written out (the compiler keeps 0 + x and -0 * x otherwise)
+                inc.B = rate;
+                inc.E = e[0];
+            } else {
+                inc.B = fmaf(-e[q], inc.B, inc.B + rate);
+                inc.E = fmaf(-inc.E, e[q], inc.E + e[q]);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            e[q] = 0.f;
+            if (s0 + q < N) {
+                e[q] = rate * fast_mag(fmaf(x[q].x, x[q].x, x[q].y * x[q].y));
+                inc.B = fmaf(-e[q], inc.B, inc.B + rate);
+                inc.E = fmaf(-inc.E, e[q], inc.E + e[q]);
+                if (CLAMP)
+                    incC = fminf(fmaf(-e[q], incC, incC) + rate, (float)AGC_MAX_GAIN);
+            }
+        }
+    }
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        EB p;
+        p.E = __shfl_up_sync(0xffffffffu, inc.E, off);
+        p.B = __shfl_up_sync(0xffffffffu, inc.B, off);
+        if (CLAMP) {
+            const float pC = __shfl_up_sync(0xffffffffu, incC, off);
+            if (lane >= off)
+                incC = fminf(fmaf(-inc.E, pC, pC) + inc.B, incC); // (p then inc), with inc's E, B before they are updated below
+        }
+        inc = eb_compose_if(lane >= off, p, inc);
+    }
+    const float totE = __shfl_sync(0xffffffffu, inc.E, 31), totB = __shfl_sync(0xffffffffu, inc.B, 31);
+    EB excl;
+    excl.E = __shfl_up_sync(0xffffffffu, inc.E, 1);
+    excl.B = __shfl_up_sync(0xffffffffu, inc.B, 1);
+    excl.E = lane > 0 ? excl.E : 0.f; // identity map in lane 0
+    excl.B = lane > 0 ? excl.B : 0.f;
+    const float Gf = (float)st.G;
+    float g = fmaf(-excl.E, Gf, Gf) + excl.B;
+    st.G = fma(1.0 - (double)totE, st.G, (double)totB);
+    if (CLAMP) {
+        const float totC = __shfl_sync(0xffffffffu, incC, 31);
+        float exclC = __shfl_up_sync(0xffffffffu, incC, 1);
+        exclC = lane > 0 ? exclC : (float)AGC_NO_CLAMP;
+        g = fminf(g, exclC);
+        st.G = fmin(st.G, (double)totC);
+    }
+    // per-sample gains from the scanned seed with the same step maps: g' = g*(1 - e) + rate is the reference's
+    // gain += rate*(1 - |x*gain|) (agc.cpp:30-33) up to the rounding of one step (~1e-9 relative), two orders below the reference's
+    // own accumulated float rounding noise in the gain that no parallel evaluation reproduces anyway.
+    float gmax = g;
+    if (FAST) {
+        // the recurrence runs on gs = g * S (S a power of two: every product and sum rounds exactly as the unscaled one does), so that
+        // (sample / S) * gs is the reference's sample * g without a multiply per sample for the scale
+        const float rateS = rate * S;
+        float gs = g * S, gprev = gs;
+        gmax = gs;
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            x[q] = make_float2(x[q].x * gs, x[q].y * gs);
+            gs = fmaf(-e[q], gs, gs + rateS);
+            if (q & 1)
+                gmax = fmaxf(gmax, fmaxf(gprev, gs)); // (one three-input maximum per two samples)
+            gprev = gs;
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const long s = s0 + q;
+            const float2 o = make_float2(x[q].x * g, x[q].y * g);
+            if (s < N) {
+                g = fmaf(-e[q], g, g + rate);
+                gmax = fmaxf(gmax, g);
+                g = fminf(g, 65536.0f);
+                if (out) {
+                    if (DUMP)
+                        agc_dump[s] = o;
+                    if (s >= N - 32)
+                        tail_out[s - (N - 32)] = o;
+                    if (s == N - 1)
+                        *gain_out = g;
+                }
+            }
+            x[q] = o;
+        }
+    }
+    if (!CLAMP && gmax > 65536.0f * S)
+        atomicOr(flags, 1);
+    {
+        float4 *dst = reinterpret_cast<float4 *>(&st.xs[10 * lane + 40]);
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            dst[q] = make_float4(x[2 * q].x, x[2 * q].y, x[2 * q + 1].x, x[2 * q + 1].y);
+    }
+    __syncwarp();
+    if (FAST || out) {
+        ulonglong2 acc[4]; // (pairs of outputs: each pair leaves as one 16-byte store)
+        fw_fir8(st.xrd, taps, acc);
+        if (FAST || s0 + 8 <= N) {
+            ulonglong2 *p = reinterpret_cast<ulonglong2 *>(fir_out + s0);
+#pragma unroll
+            for (int o = 0; o < 4; o++)
+                p[o] = acc[o];
+        } else {
+#pragma unroll
+            for (int o = 0; o < 8; o++)
+                if (s0 + o < N)
+                    *reinterpret_cast<unsigned long long *>(fir_out + s0 + o) = (o & 1) ? acc[o >> 1].y : acc[o >> 1].x;
+        }
+    }
+    __syncwarp(); // every lane has read its window: the chunk's last 32 samples become the next chunk's history
+    if (lane >= 28) {
+        const float4 *src = reinterpret_cast<const float4 *>(&st.xs[10 * lane + 40]);
+        float4 *dst = reinterpret_cast<float4 *>(&st.xs[10 * (lane - 28)]);
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            dst[q] = src[q];
+    }
+}
+
+template <int FMT, bool DUMP, bool CLAMP>
+__global__ void __launch_bounds__(32 * FW_WARPS, 8) k_agc_fir_w(const void *__restrict__ raw, long N, float rate, const float *__restrict__ gain_in, int R,
+                                                                  const AgcCtl ctl, const FirTaps taps, const float2 *__restrict__ tail_in,
+                                                                  float2 *__restrict__ tail_out, float2 *__restrict__ fir_out,
+                                                                  float2 *__restrict__ agc_dump, float *__restrict__ gain_out, int *__restrict__ flags)
+{
+    __shared__ __align__(16) float2 xs_all[FW_WARPS][FW_BUF_F2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float2 *xs = xs_all[warp];
     int *need = ctl.need + (ctl.epoch & 1);
     if (CLAMP) {
         if ((*flags & 1) == 0)
@@ -535,271 +773,88 @@ __global__ void __launch_bounds__(FIR_THREADS, 5) k_agc_fir(const void *__restri
     } else if (ctl.seeded) {
         if (*need == 0)
             return;
-    } else if (blockIdx.x == 0 && t == 0)
+    } else if (blockIdx.x == 0 && threadIdx.x == 0)
         ctl.need[(ctl.epoch & 1) ^ 1] = 0;
     const int ntiles = (int)((N + FIR_TILE - 1) / FIR_TILE);
-    const int first = blockIdx.x * R;
-    if (first >= ntiles)
+    const long first_t = ((long)blockIdx.x * FW_WARPS + warp) * R;
+    if (first_t >= ntiles)
         return;
-    const int last = min(first + R, ntiles);
-    int par = 0, buf = 0, i0 = first;
-    double G; // gain before the next tile to run
-    if (first == 0) {
+    const int last_t = (int)min(first_t + (long)R, (long)ntiles);
+    const int nch = (int)((N + FW_CH - 1) / FW_CH);
+    const int c_first = (int)first_t * (FIR_TILE / FW_CH), c_last = min(last_t * (FIR_TILE / FW_CH), nch);
+    int c0 = c_first;
+    double G; // gain before the next chunk to run
+    if (first_t == 0) {
         G = (double)*gain_in;
-        if (t < 4) { // FIR history: the previous batch's last 32 AGC outputs
-            float4 *dst = reinterpret_cast<float4 *>(&xs[0][xidx(8 * t)]);
+        if (lane < 4) { // FIR history: the previous batch's last 32 AGC outputs
+            float4 *dst = reinterpret_cast<float4 *>(&xs[10 * lane]);
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                const float2 u = tail_in[8 * t + 2 * i], v = tail_in[8 * t + 2 * i + 1];
+                const float2 u = tail_in[8 * lane + 2 * i], v = tail_in[8 * lane + 2 * i + 1];
                 dst[i] = make_float4(u.x, u.y, v.x, v.y);
             }
         }
+    } else if (ctl.seeded || CLAMP) {
+        c0 = ((int)first_t - 1) * (FIR_TILE / FW_CH); // the whole tile in front, from its scanned seed, without output
+        G = ctl.seeds[first_t - 1];
     } else {
-        i0 = first - 1;
-        if (ctl.seeded)
-            G = ctl.seeds[i0];
-        else {
-            double A = 1.0, Bc = 0.0; // composition of the tiles walked so far: g(i0 start) = A * g(older) + Bc
-            bool ok = false;
-            for (int j = i0 - 1, w = 0;; j--, w++) {
-                if (j < 0) { // reached the batch start: the carried gain is exact
-                    Bc = fma(A, (double)*gain_in, Bc);
-                    ok = true;
-                    break;
-                }
-                if (w >= ctl.warm_max)
-                    break;
-                float2 x[8];
-                load8<FMT>(raw, (long)j * FIR_TILE + 8 * t, N, x);
-                float e[8];
-                EB m = agc_map8(x, rate, e);
-#pragma unroll
-                for (int off = 1; off < 32; off <<= 1) { // lane l <- groups [l, l + 2*off)
-                    EB o;
-                    o.E = __shfl_down_sync(0xffffffffu, m.E, off);
-                    o.B = __shfl_down_sync(0xffffffffu, m.B, off);
-                    if (lane + off < 32)
-                        m = eb_compose(m, o);
-                }
-                if (lane == 0)
-                    wsum[par][warp] = m;
-                __syncthreads();
-                EB tot = wsum[par][0];
-#pragma unroll
-                for (int w2 = 1; w2 < FIR_THREADS / 32; w2++)
-                    tot = eb_compose(tot, wsum[par][w2]);
-                par ^= 1;
-                Bc = fma(A, (double)tot.B, Bc);
-                A *= 1.0 - (double)tot.E;
-                // anything older enters as A * gain with gain <= 2^16: done once that is below float resolution of the seed
-                if (A * 65536.0 <= Bc * 0x1p-30) {
-                    ok = true;
-                    break;
-                }
+        c0 = c_first - 1;
+        double A = 1.0, Bc = 0.0; // composition of the chunks walked so far: g(c0 start) = A * g(older) + Bc
+        bool ok = false;
+        for (int j = c0 - 1, w = 0;; j--, w++) {
+            if (j < 0) { // reached the batch start: the carried gain is exact
+                Bc = fma(A, (double)*gain_in, Bc);
+                ok = true;
+                break;
             }
-            if (!ok) {
-                if (t == 0)
-                    atomicOr(need, 1);
-                return;
+            if (w >= ctl.warm_max * (FIR_TILE / FW_CH))
+                break;
+            float2 x[8];
+            load8<FMT>(raw, (long)j * FW_CH + 8 * lane, N, x);
+            float e[8];
+            EB m = agc_map8(x, rate, e);
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) { // lane l <- groups [l, l + 2*off)
+                EB o;
+                o.E = __shfl_down_sync(0xffffffffu, m.E, off);
+                o.B = __shfl_down_sync(0xffffffffu, m.B, off);
+                if (lane + off < 32)
+                    m = eb_compose(m, o);
             }
-            G = Bc;
+            const float tE = __shfl_sync(0xffffffffu, m.E, 0), tB = __shfl_sync(0xffffffffu, m.B, 0);
+            Bc = fma(A, (double)tB, Bc);
+            A *= 1.0 - (double)tE;
+            // anything older enters as A * gain with gain <= 2^16: done once that is below float resolution of the seed
+            if (A * 65536.0 <= Bc * 0x1p-30) {
+                ok = true;
+                break;
+            }
         }
+        if (!ok) {
+            if (lane == 0)
+                atomicOr(need, 1);
+            return;
+        }
+        G = Bc;
     }
 
     RawRegs<FMT> rr;
-    if (FMT != 0 && (long)i0 * FIR_TILE + 8 * t + 8 <= N)
-        raw_fetch<FMT>(raw, (long)i0 * FIR_TILE + 8 * t, rr);
-    const float2 *xrd0 = &xs[0][10 * t], *xrd1 = &xs[1][10 * t]; // xidx(8t + c) = 10t + xidx(c) for c < 8... see fir loop
-    for (int i = i0; i < last; i++) {
-        const bool out = i >= first; // tile first-1 only provides the FIR history
-        const long s0 = (long)i * FIR_TILE + 8 * t;
-        const bool interior = (long)(i + 1) * FIR_TILE + 32 <= N && !DUMP && !CLAMP; // every sample exists, none is in the stream tail
-        float2 x[8];
-        if (s0 + 8 <= N) {
-            if (FMT == 0) // cf32: 16 registers of raw data are too many to hold across a tile
-                raw_fetch<FMT>(raw, s0, rr);
-            raw_convert<FMT>(rr, x);
-        } else
-            load8_ragged<FMT>(raw, s0, N, x);
-        if (FMT != 0 && i + 1 < last && s0 + FIR_TILE + 8 <= N) // next tile's loads fly under this tile's arithmetic
-            raw_fetch<FMT>(raw, s0 + FIR_TILE, rr);
-        EB inc{0.f, 0.f};
-        float incC = (float)AGC_NO_CLAMP; // CLAMP: third component of the composed map
-        float e[8]; // rate * |x|: the step map of sample q is g -> g * (1 - e[q]) + rate
-        if (interior)
-            inc = agc_map8(x, rate, e);
-        else {
-#pragma unroll
-            for (int q = 0; q < 8; q++) {
-                e[q] = 0.f;
-                if (s0 + q < N) {
-                    e[q] = rate * fast_mag(fmaf(x[q].x, x[q].x, x[q].y * x[q].y));
-                    inc.B = fmaf(-e[q], inc.B, inc.B + rate);
-                    inc.E = fmaf(-inc.E, e[q], inc.E + e[q]);
-                    if (CLAMP)
-                        incC = fminf(fmaf(-e[q], incC, incC) + rate, (float)AGC_MAX_GAIN);
-                }
-            }
-        }
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            EB p;
-            p.E = __shfl_up_sync(0xffffffffu, inc.E, off);
-            p.B = __shfl_up_sync(0xffffffffu, inc.B, off);
-            if (CLAMP) {
-                const float pC = __shfl_up_sync(0xffffffffu, incC, off);
-                if (lane >= off)
-                    incC = fminf(fmaf(-inc.E, pC, pC) + inc.B, incC); // (p then inc), with inc's E, B before they are updated below
-            }
-            inc = eb_compose_if(lane >= off, p, inc);
-        }
-        if (lane == 31) {
-            wsum[par][warp] = inc;
-            if (CLAMP)
-                wsumC[par][warp] = incC;
-        }
-        __syncthreads();
-        // every warp scans the 8 warp aggregates (lanes 0-7 hold them, the rest mirror)
-        EB wv = wsum[par][lane & 7];
-        float wvC = CLAMP ? wsumC[par][lane & 7] : 0.f;
-        par ^= 1;
-#pragma unroll
-        for (int off = 1; off < 8; off <<= 1) {
-            EB p;
-            p.E = __shfl_up_sync(0xffffffffu, wv.E, off, 8);
-            p.B = __shfl_up_sync(0xffffffffu, wv.B, off, 8);
-            if (CLAMP) {
-                const float pC = __shfl_up_sync(0xffffffffu, wvC, off, 8);
-                if ((lane & 7) >= off)
-                    wvC = fminf(fmaf(-wv.E, pC, pC) + wv.B, wvC);
-            }
-            wv = eb_compose_if((lane & 7) >= off, p, wv);
-        }
-        EB tot, excl{0.f, 0.f};
-        float totC = 0.f, exclC = (float)AGC_NO_CLAMP;
-        tot.E = __shfl_sync(0xffffffffu, wv.E, 7);
-        tot.B = __shfl_sync(0xffffffffu, wv.B, 7);
-        if (CLAMP)
-            totC = __shfl_sync(0xffffffffu, wvC, 7);
-        {
-            EB p;
-            p.E = __shfl_sync(0xffffffffu, wv.E, (warp + 7) & 7);
-            p.B = __shfl_sync(0xffffffffu, wv.B, (warp + 7) & 7);
-            excl.E = warp > 0 ? p.E : 0.f;
-            excl.B = warp > 0 ? p.B : 0.f;
-            float pC = (float)AGC_NO_CLAMP, qC = (float)AGC_NO_CLAMP;
-            if (CLAMP) {
-                pC = __shfl_sync(0xffffffffu, wvC, (warp + 7) & 7);
-                pC = warp > 0 ? pC : (float)AGC_NO_CLAMP;
-                qC = __shfl_up_sync(0xffffffffu, incC, 1);
-                qC = lane > 0 ? qC : (float)AGC_NO_CLAMP;
-            }
-            p.E = __shfl_up_sync(0xffffffffu, inc.E, 1);
-            p.B = __shfl_up_sync(0xffffffffu, inc.B, 1);
-            p.E = lane > 0 ? p.E : 0.f; // identity map in lane 0
-            p.B = lane > 0 ? p.B : 0.f;
-            if (CLAMP)
-                exclC = fminf(fmaf(-p.E, pC, pC) + p.B, qC); // (warps before) then (lanes before)
-            excl = eb_compose(excl, p);
-        }
-        // per-sample gains from the scanned seed with the same step maps: g' = g*(1 - e) + rate is the reference's
-        // gain += rate*(1 - |x*gain|) (agc.cpp:30-33) up to the rounding of one step (~1e-9 relative), which is two orders below
-        // the reference's own accumulated float rounding noise in the gain (~1e-7 rms, time constant 100*gain samples) that no
-        // parallel evaluation reproduces anyway.
-        const float Gf = (float)G;
-        float g = fmaf(-excl.E, Gf, Gf) + excl.B;
-        G = fma(1.0 - (double)tot.E, G, (double)tot.B);
-        if (CLAMP) {
-            g = fminf(g, exclC);
-            G = fmin(G, (double)totC);
-        }
-        float gmax = g;
-        if (interior) {
-#pragma unroll
-            for (int q = 0; q < 8; q++) {
-                x[q] = make_float2(x[q].x * g, x[q].y * g);
-                g = fmaf(-e[q], g, g + rate);
-                gmax = fmaxf(gmax, g);
-            }
-        } else {
-#pragma unroll
-            for (int q = 0; q < 8; q++) {
-                const long s = s0 + q;
-                const float2 o = make_float2(x[q].x * g, x[q].y * g);
-                if (s < N) {
-                    g = fmaf(-e[q], g, g + rate);
-                    gmax = fmaxf(gmax, g);
-                    g = fminf(g, 65536.0f);
-                    if (out) {
-                        if (DUMP)
-                            agc_dump[s] = o;
-                        if (s >= N - 32)
-                            tail_out[s - (N - 32)] = o;
-                        if (s == N - 1)
-                            *gain_out = g;
-                    }
-                }
-                x[q] = o;
-            }
-        }
-        if (!CLAMP && gmax > 65536.0f)
-            atomicOr(flags, 1);
-        {
-            float4 *dst = reinterpret_cast<float4 *>(&xs[buf][10 * t + 40]);
-#pragma unroll
-            for (int q = 0; q < 4; q++)
-                dst[q] = make_float4(x[2 * q].x, x[2 * q].y, x[2 * q + 1].x, x[2 * q + 1].y);
-            if (t >= FIR_THREADS - 4) { // the last 32 samples are the next tile's history
-                float4 *h = reinterpret_cast<float4 *>(&xs[buf ^ 1][10 * (t - (FIR_THREADS - 4))]);
-#pragma unroll
-                for (int q = 0; q < 4; q++)
-                    h[q] = make_float4(x[2 * q].x, x[2 * q].y, x[2 * q + 1].x, x[2 * q + 1].y);
-            }
-        }
-        __syncthreads();
-
-        // FIR: thread t -> outputs 8t .. 8t+7 of the tile; y[n] = sum_j x[n-30+j] * h[30-j], oldest first (fir.cpp:74-83)
-        if (out) {
-            // packed FP32x2: one FFMA2 does the (re, im) pair of a complex sample x real tap MAC (two independent fma.rn, i.e. the
-            // same results as scalar fmaf); the tap is a scalar broadcast operand. 31 FFMA2 per output sample instead of 62 FFMA.
-            unsigned long long acc[8];
-#pragma unroll
-            for (int o = 0; o < 8; o++)
-                acc[o] = 0ull;
-            // buffer index of the oldest input of output 0 is 8t + 2 (even: 16-byte aligned pairs); xidx(8t + c) = 10t + xidx(c)
-            const float2 *xrd = buf ? xrd1 : xrd0;
-#pragma unroll
-            for (int pI = 0; pI < 19; pI++) {
-                const ulonglong2 vv = *reinterpret_cast<const ulonglong2 *>(xrd + xidx(2 + 2 * pI));
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const unsigned long long v = h ? vv.y : vv.x;
-                    const int mI = 2 * pI + h;
-#pragma unroll
-                    for (int o = 0; o < 8; o++) {
-                        const int j = mI - o; // tap position (0 = oldest)
-                        if (j >= 0 && j < FIR_NT) {
-                            unsigned long long hh;
-                            asm("mov.b64 %0, {%1, %1};" : "=l"(hh) : "f"(taps.h[FIR_NT - 1 - j]));
-                            asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[o]) : "l"(v), "l"(hh));
-                        }
-                    }
-                }
-            }
-            if (s0 + 8 <= N) {
-                ulonglong2 *p = reinterpret_cast<ulonglong2 *>(fir_out + s0);
-#pragma unroll
-                for (int o = 0; o < 4; o++)
-                    p[o] = make_ulonglong2(acc[2 * o], acc[2 * o + 1]);
-            } else {
-#pragma unroll
-                for (int o = 0; o < 8; o++)
-                    if (s0 + o < N)
-                        *reinterpret_cast<unsigned long long *>(fir_out + s0 + o) = acc[o];
-            }
-        }
-        buf ^= 1;
+    if (FMT != 0 && (long)c0 * FW_CH + 8 * lane + 8 <= N)
+        raw_fetch<FMT>(raw, (long)c0 * FW_CH + 8 * lane, rr);
+    FwState<FMT> st{raw, N, rate, G, xs, &xs[10 * lane], lane, c_last};
+    // [c0, c_first): history only; [c_first, c_fast): every sample exists, none is in the stream tail -> the branch-free body;
+    // the rest (the batch's last chunks; all of them in the dump / clamp instantiations): the general body
+    int c = c0;
+    for (; c < c_first; c++)
+        fw_chunk<FMT, DUMP, CLAMP, false>(st, rr, c, false, taps, tail_out, fir_out, agc_dump, gain_out, flags);
+    if (!DUMP && !CLAMP) {
+        const int c_fast = (int)min((long)c_last, max(0L, (N - 32) / FW_CH)); // (c + 1) * FW_CH + 32 <= N
+#pragma unroll 1
+        for (; c < c_fast; c++)
+            fw_chunk<FMT, false, false, true>(st, rr, c, true, taps, tail_out, fir_out, agc_dump, gain_out, flags);
     }
+    for (; c < c_last; c++)
+        fw_chunk<FMT, DUMP, CLAMP, false>(st, rr, c, true, taps, tail_out, fir_out, agc_dump, gain_out, flags);
 }
 
 // ---------------------------------------------------------------- exact pass (weak signals): per-tile maps -> scan -> seeds
@@ -969,7 +1024,7 @@ __global__ void __launch_bounds__(1024) k_agc_scan(const Affine *__restrict__ ti
 // y[i] = sum_j x[i-30+j] * h[30-j] over a cf32 stream with zero history, oldest sample first (fir.cpp:74-83). STRICT evaluates it
 // the way the generic VOLK dot product the oracle is built with does (separate multiply and add, left to right), so that fed the
 // oracle's own AGC output the result must be BITWISE the oracle's FIR output; !STRICT uses one fma per tap in the same order, i.e.
-// the arithmetic of k_agc_fir's FFMA2 loop.
+// the arithmetic of k_agc_fir_w's FFMA2 loop.
 template <bool STRICT> __global__ void __launch_bounds__(256) k_fir_only(const float2 *__restrict__ in, long N, const FirTaps taps, float2 *__restrict__ out)
 {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;

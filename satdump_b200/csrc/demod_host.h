@@ -76,7 +76,8 @@ class Demod
     DevBuf<double> seeds;          // gain before every tile
     DevBuf<int> agc_need;          // [2] raised by the fast pass when a range cannot prove its seed
     unsigned agc_epoch = 0;
-    int fir_ctas = 0;              // resident k_agc_fir CTAs on the device (one wave of ranges)
+    int fir_ctas = 0;              // resident k_agc_fir_w CTAs on the device
+    int fir_warps = 0;             // ... and their warps: one range of tiles each (one wave)
     // front-end resampler (RationalResamplerBlock) / iq_swap pass
     bool resamp = false;
     int rs_I = 1, rs_D = 1, rs_nt = 1;

@@ -20,3 +20,21 @@ def built():
     if not os.path.exists(capi.LIB_PATH) or not os.path.exists(os.path.join(ROOT, "oracle", "liboracle.so")):
         g.build()
     return True
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _floors_for_this_machines_signals(request):
+    """GPU sessions: the parity floors (tests/floors.py) belong to one realisation of the synthetic signals; on a machine whose torch
+    generator produces another one (CUDA) they are re-measured from the compiled reference before the tests run, in parallel."""
+    if not any(item.get_closest_marker("gpu") for item in request.session.items):
+        return
+    try:
+        import torch
+        from oracle import ref
+        if torch.cuda.is_available() and ref.available():
+            from tests import floors
+            n = floors.warm()
+            if n:
+                print(f"\n[floors] re-measured {n} entries for this machine's signals", flush=True)
+    except Exception as e:  # the tests then measure what they need one by one
+        print(f"\n[floors] warm-up skipped: {e!r}", flush=True)

@@ -95,6 +95,17 @@ def stage_floor(name, log2n, stage, eps=1e-6, seeds=(1, 2, 3, 4, 5, 6, 7, 8), ex
             s |= {"soft_" + k: v for k, v in soft_stats(quantise(got, cfg.constellation == "bpsk" and cfg.decoder != "none"), o["soft"]).items()}
         out.append(s)
     w = _worst(out)
+    if stage == "costas" and eps > 0:
+        # Sign-decision events (a detector input within the deviation of zero flips sgn(v.re) / sgn(v.im): a phase kick of ~alpha that
+        # takes ~1000 samples to decay) are rare and their number scales with the size of the deviation. The segmented evaluation's
+        # junctions are accepted up to 1e-5 rad (typically 2e-6), SURVEY 8c allows the stages in front 1e-5: the event statistics are
+        # therefore also sampled with 16 runs at 3e-6, the largest perturbation that itself stays below the 1e-5 counting threshold at
+        # the loop's output (with eight runs at 1e-6 a configuration shows no event and the GPU one or two, e.g. metop_oversampled: two
+        # kicks of 1.5e-2 in 7e5 samples, both in the middle of a segment).
+        for sd in range(1, 17):
+            d = diff_stats(O.run_stage(oc, stage, perturb(src, 3e-6, sd)), want)
+            for k in ("frac", "max", "mean"):
+                w[k] = max(w[k], d[k])
     if stage == "mm" and eps > 0:
         # The largest deviations are excursions at a few fragile spots of the signal (one or two interpolator arms for a few hundred
         # symbols); which of them a run triggers depends on the perturbation. They are sampled with more seeds and at 1e-5, the
@@ -153,19 +164,53 @@ def chain_floor(name, log2n, eps=1e-6, seeds=(1, 2, 3), extra=()):
     return w
 
 
-# ---- committed cache: the floors are deterministic functions of the committed synthetic signals and the compiled reference, and cost
-# 10-20 s of CPU each; tests/golden/floors.json holds them (tests/golden/make_floors.py regenerates it, tests/test_floors.py re-measures
-# a sample of the entries against it), so the GPU box does not spend its minutes on them.
+# ---- committed cache: the floors are deterministic functions of the synthetic signals and the compiled reference, and cost 10-20 s of
+# CPU each; tests/golden/floors.json holds them for the signals as THIS container generates them (tests/golden/make_floors.py regenerates
+# it, tests/test_floors.py re-measures a sample of the entries against it). A floor belongs to one realisation of the signal: which
+# fragile spots it has and how large the loops' response there is (bpsk_half + post_costas_dc, 2^20 samples: worst M&M excursion 0.0225
+# on the CPU-generated signal, 0.0666 on the one torch's CUDA generator produces on the GPU box, in the reference and on the GPU alike).
+# Every entry therefore carries the CRC of its signal ("sig"); where the signal of the running machine differs (the GPU box) the entries
+# are re-measured there, all at once on the host's cores (warm(), called by the session fixture of the GPU tests).
 _CACHE_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "floors.json")
 _cache = None
+
+GX = (("clock_recovery", "gardner"),)
+PX = (("post_costas_dc", True),)
+CONFIGS = ["metop_ahrpt", "bpsk_half", "jpss_hrd", "dvbs2_front", "hrpt_bpsk", "psk8", "metop_oversampled", "bpsk_decim8"]
+
+
+def all_entries():
+    """(kind, name, log2n, stage, extra) of every floor the GPU tests gate against."""
+    out = []
+    for name in CONFIGS:
+        out.append(("chain", name, 21, None, ()))
+        out.append(("stage", name, 21, "mm", ()))
+        if name != "dvbs2_front":
+            out.append(("stage", name, 21, "costas", ()))
+    for name in ("metop_ahrpt", "bpsk_half"):
+        out.append(("stage", name, 21, "mm", GX))
+        out.append(("chain", name, 21, None, GX))
+    out.append(("chain", "bpsk_half", 20, None, PX))
+    return out
 
 
 def _key(kind, name, log2n, stage, eps, extra):
     return "|".join([kind, name, str(log2n), str(stage), repr(float(eps)), repr(tuple(extra))])
 
 
-def cached(kind, name, log2n, stage=None, eps=1e-6, extra=()):
-    """stage_floor / chain_floor through the committed cache (computed and remembered in memory when the entry is missing)."""
+def signal_crc(name, log2n):
+    import zlib
+    _, raw, _ = signal(name, log2n)
+    return zlib.crc32(np.ascontiguousarray(raw).view(np.uint8))
+
+
+def _measure(kind, name, log2n, stage, extra):
+    w = dict(stage_floor(name, log2n, stage, extra=tuple(extra)) if kind == "stage" else chain_floor(name, log2n, extra=tuple(extra)))
+    w["sig"] = signal_crc(name, log2n)
+    return w
+
+
+def _load():
     global _cache
     if _cache is None:
         try:
@@ -173,10 +218,46 @@ def cached(kind, name, log2n, stage=None, eps=1e-6, extra=()):
                 _cache = json.load(f)
         except Exception:
             _cache = {}
+    return _cache
+
+
+def cached(kind, name, log2n, stage=None, eps=1e-6, extra=()):
+    """stage_floor / chain_floor through the committed cache; measured here (and remembered in memory) when the entry is missing or
+    belongs to another realisation of the signal."""
+    c = _load()
     k = _key(kind, name, log2n, stage, eps, extra)
-    if k not in _cache:
-        _cache[k] = stage_floor(name, log2n, stage, eps, extra=tuple(extra)) if kind == "stage" else chain_floor(name, log2n, eps, extra=tuple(extra))
-    return _cache[k]
+    if k not in c or c[k].get("sig") != signal_crc(name, log2n):
+        c[k] = _measure(kind, name, log2n, stage, tuple(extra))
+    return c[k]
+
+
+def _measure_job(e):
+    return _key(e[0], e[1], e[2], e[3], 1e-6, e[4]), _measure(*e)
+
+
+def warm(entries=None, workers=None):
+    """Re-measures, in parallel processes, every entry whose committed value belongs to another realisation of the signal. Returns the
+    number of entries measured. (The children are forked after the signals were generated: they only run the CPU reference.)"""
+    import multiprocessing as mp
+    c = _load()
+    todo = []
+    for e in (entries or all_entries()):
+        k = _key(e[0], e[1], e[2], e[3], 1e-6, e[4])
+        if k not in c or c[k].get("sig") != signal_crc(e[1], e[2]):
+            todo.append(e)
+    if not todo:
+        return 0
+    for e in todo:
+        reference_run(e[1], e[2], tuple(e[4]))  # shared by the children through fork
+    n = min(len(todo), workers or max(1, (os.cpu_count() or 2) - 2))
+    if n <= 1:
+        res = [_measure_job(e) for e in todo]
+    else:
+        with mp.get_context("fork").Pool(n) as pool:
+            res = pool.map(_measure_job, todo, chunksize=1)
+    for k, w in res:
+        c[k] = w
+    return len(todo)
 
 
 def gate(survey, floor):

@@ -22,7 +22,8 @@ def test_committed_floors_reproduce(built):
     for kind, name, stage in (("stage", "metop_ahrpt", "mm"), ("stage", "jpss_hrd", "costas"), ("chain", "dvbs2_front", None)):
         k = floors._key(kind, name, 21, stage, 1e-6, ())
         now = floors.stage_floor(name, 21, stage) if kind == "stage" else floors.chain_floor(name, 21)
-        assert committed[k] == pytest.approx(now, rel=1e-6, abs=1e-12), k
+        assert committed[k]["sig"] == floors.signal_crc(name, 21), k  # (the floor of THIS realisation of the signal)
+        assert {a: b for a, b in committed[k].items() if a != "sig"} == pytest.approx(now, rel=1e-6, abs=1e-12), k
 
 
 def test_the_reference_is_chaotic_at_the_1e5_level(built):

@@ -132,14 +132,16 @@ def test_pipelined_mode_gives_the_same_frames(built, name):
 
 
 def test_pipelined_decoder_errors_surface(built):
-    """A decoder-side failure on the worker thread (soft FIFO too small for the batch) is reported by the next call, not lost."""
+    """A decoder-side failure on the worker thread (decoded frames piling up because nobody pulls them: the chain sizes the soft FIFO
+    itself now, so that cannot be provoked any more) is reported by a later call, not lost."""
     from satdump_b200 import capi
     cfg, raw, _ = signal("metop_ahrpt", 20)
     n = nsamples(raw, cfg)
     ch = capi.Chain(capi.demod_cfg(cfg.samplerate, cfg.symbolrate, cfg.constellation, cfg.rrc_alpha, cfg.pll_bw, cfg.fmt, max_batch=n),
                     capi.metop_cfg(cfg.ber_thresold, cfg.outsync_after, max_soft=65536)).set_pipelined(True)
-    ch.push(raw)
     with pytest.raises(capi.B200Error) as e:
+        for _ in range(8):  # the frame store holds two batches' worth
+            ch.push(raw)
         ch.sync()
     assert e.value.code == -5
     ch.close()

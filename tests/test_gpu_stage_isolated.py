@@ -2,7 +2,7 @@
 b200_demod_debug_run_stage, so a kernel bug cannot hide behind (or be excused by) the feedback loops' sensitivity:
 
   FIR     strict build (separate multiply / add, the generic VOLK order of fir.cpp:74-83)  -> BITWISE the oracle's output
-          production build (one fma per tap, k_agc_fir with the AGC switched off)          -> <= 1e-6 everywhere
+          production build (one fma per tap, k_agc_fir_w with the AGC switched off)          -> <= 1e-6 everywhere
   M&M     strict build, one sequential segment (clock_recovery_mm.cpp:52-121 as written)   -> BITWISE the oracle's symbols
           production arithmetic (two FMA chains), sequential and segmented                 -> same count, within the gates below
   Costas  sequential (one thread from the initial state)                                   -> <= 1e-5 everywhere
