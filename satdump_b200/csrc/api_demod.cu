@@ -303,7 +303,11 @@ Demod::Demod(const b200_demod_cfg &c) : cfg(c)
         tol_mm = (float)atof(e);
     int dev_sms = 148;
     cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, c.device);
-    seg_cap_threads = dev_sms * 3 * SEG_THREADS;
+    seg_ctas = 3;
+    if (const char *e = getenv("B200_SEG_CTAS")) // tuning hook: resident CTAs of the loop kernels per SM the segment count aims at
+        seg_ctas = std::max(1, atoi(e));
+    seg_cap_threads = dev_sms * seg_ctas * SEG_THREADS;
+
 
     {
         // in a pipelined chain the demodulator of batch i runs next to the decoder of batch i-1 and is the longer of the two: its
@@ -407,7 +411,9 @@ Demod::Demod(const b200_demod_cfg &c) : cfg(c)
     B200_CUDA(cudaFuncSetAttribute(k_mm<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM_BYTES));
     B200_CUDA(cudaFuncSetAttribute(k_mm<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM_BYTES));
     B200_CUDA(cudaFuncSetAttribute(k_mm<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM_BYTES));
-    B200_CUDA(cudaFuncSetAttribute(k_costas, cudaFuncAttributeMaxDynamicSharedMemorySize, COSTAS_SMEM_BYTES));
+    B200_CUDA(cudaFuncSetAttribute(k_costas<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, COSTAS_SMEM_BYTES));
+    B200_CUDA(cudaFuncSetAttribute(k_costas<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, COSTAS_SMEM_BYTES));
+    B200_CUDA(cudaFuncSetAttribute(k_costas<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, COSTAS_SMEM_BYTES));
     B200_CUDA(cudaStreamSynchronize(stream));
 }
 
@@ -535,15 +541,25 @@ float2 *Demod::stage_costas(long n, int L, int nseg, int cur, int nxt, bool mate
         }
         P.fmin = -cfg.costas_max_offset;
         P.fmax = cfg.costas_max_offset;
-        k_costas<<<nblk, SEG_THREADS, COSTAS_SMEM_BYTES, stream>>>(fir_out, n, L, Wc, Gc, nseg, P, S->costas[cur], cos_out, crec.p, nullptr, nullptr);
+#define B200_COSTAS_LAUNCH(grid, ...)                                                                                                       \
+    do {                                                                                                                                    \
+        if (order == 2)                                                                                                                     \
+            k_costas<2><<<grid, SEG_THREADS, COSTAS_SMEM_BYTES, stream>>>(__VA_ARGS__);                                                      \
+        else if (order == 4)                                                                                                                \
+            k_costas<4><<<grid, SEG_THREADS, COSTAS_SMEM_BYTES, stream>>>(__VA_ARGS__);                                                      \
+        else                                                                                                                                \
+            k_costas<8><<<grid, SEG_THREADS, COSTAS_SMEM_BYTES, stream>>>(__VA_ARGS__);                                                      \
+    } while (0)
+        B200_COSTAS_LAUNCH(nblk, fir_out, n, L, Wc, Gc, nseg, P, S->costas[cur], cos_out, crec.p, nullptr, nullptr);
         k_costas_fix<<<1, 1024, 0, stream>>>(crec.p, nseg, order, tol_cphase, tol_cfreq, quad.p, S->costas[nxt], &S->costas_unconv, repair.p + 1, repair.p, 0,
                                              &S->repairs);
         for (int round = 1; round <= REPAIR_ROUNDS; round++) { // both kernels return at once when no junction is flagged
-            k_costas<<<8, SEG_THREADS, COSTAS_SMEM_BYTES, stream>>>(fir_out, n, L, Wc, Gc, nseg, P, S->costas[cur], cos_out, crec.p, repair.p + 1, repair.p);
+            B200_COSTAS_LAUNCH(8, fir_out, n, L, Wc, Gc, nseg, P, S->costas[cur], cos_out, crec.p, repair.p + 1, repair.p);
             k_costas_fix<<<1, 1024, 0, stream>>>(crec.p, nseg, order, tol_cphase, tol_cfreq, quad.p, S->costas[nxt], &S->costas_unconv, repair.p + 1, repair.p,
                                                  round, &S->repairs);
             launches += 2;
         }
+#undef B200_COSTAS_LAUNCH
         if (!materialise && !cfg.post_costas_dc) {
             // fused: the clock recovery rotates (and, for OQPSK, delays) its input rows itself
             k_mm_prep<<<1, 32, 0, stream>>>(bufB.p, n, L, order, quad.p, S->mm_hist[cur], S->mm_hist[nxt]);

@@ -1066,25 +1066,6 @@ struct CostasParams
 struct LoopRec { float ph_start, fr_start, ph_end, fr_end; };
 
 #ifdef B200_DEFINE_KERNELS
-__device__ __forceinline__ float costas_error(float vr, float vi, int order)
-{
-    float err;
-    if (order == 4)
-        err = (vr > 0.0f ? 1.0f : -1.0f) * vi - (vi > 0.0f ? 1.0f : -1.0f) * vr;
-    else if (order == 2)
-        err = vr * vi;
-    else {
-        const float K = 0.41421356237309515f; // sqrtf(2.0) - 1 rounded to float
-        if (fabsf(vr) >= fabsf(vi))
-            err = ((vr > 0.0f ? 1.0f : -1.0f) * vi - (vi > 0.0f ? 1.0f : -1.0f) * vr * K);
-        else
-            err = ((vr > 0.0f ? 1.0f : -1.0f) * vi * K - (vi > 0.0f ? 1.0f : -1.0f) * vr);
-    }
-    return 0.5f * (fabsf(err + 1.0f) - fabsf(err - 1.0f)); // branchless_clip(err, 1)
-}
-
-// in/out: N samples. Segment s owns samples [s*L, min((s+1)L, N)); thread warms up from max(0, s*L - W).
-// state_in = {phase, freq} carried from the previous batch (exact start of segment 0 and of any clipped warm-up).
 // Warp-cooperative staging shared by the two loop kernels. Every thread walks ITS OWN stretch of the stream, so a per-thread
 // load touches 32 different cache lines per instruction (measured: the L1 wavefront rate, not the math, bounded the first version).
 // Instead the warp moves whole 128-byte rows: in instruction i, lanes 8q..8q+7 copy the eight 16-byte chunks of the row of thread
@@ -1126,6 +1107,108 @@ constexpr int COSTAS_SMEM_BYTES = (SEG_THREADS / 32) * (16 + 8) * 32 * 16; // pe
 // gain: a warm-up that starts near an unstable lock point (a hang-up: the detector output is ~0 there) escapes four times faster, so
 // the slow tail of the junction residuals disappears; the remaining W - G samples at the true gains bring the state from the wide
 // loop's jitter down onto the sequential trajectory.
+
+// the loop's state in registers: float phase / frequency exactly as the reference carries them, and (cs, sn) = cos / sin of the phase
+struct CostasRegs { float phase, freq, cs, sn; };
+
+// detector + branchless_clip(err, 1) (costas_loop.cpp:31-56)
+template <int ORDER> __device__ __forceinline__ float costas_err(float vr, float vi)
+{
+    float err;
+    if (ORDER == 4)
+        err = (vr > 0.0f ? vi : -vi) - (vi > 0.0f ? vr : -vr); // sgn(0) = -1, and (+-1) * x is exact
+    else if (ORDER == 2)
+        err = vr * vi;
+    else {
+        const float K = 0.41421356237309515f; // sqrtf(2.0) - 1 rounded to float
+        const float a = vr > 0.0f ? vi : -vi, b = vi > 0.0f ? vr : -vr;
+        err = fabsf(vr) >= fabsf(vi) ? a - b * K : a * K - b;
+    }
+    return 0.5f * (fabsf(err + 1.0f) - fabsf(err - 1.0f));
+}
+
+// sin / cos of a loop phase (|x| <= 2 pi plus one step): three-term Cody-Waite reduction by pi/2 and the usual minimax polynomials on
+// [-pi/4, pi/4]; max error 7e-8 over [-7, 7] (glibc's sinf / cosf, which the reference calls: 3e-8), no slow path to branch around.
+__device__ __forceinline__ void sincos_loop_phase(float x, float &s, float &c)
+{
+    const float q = rintf(x * 0.636619772f);
+    const int iq = (int)q;
+    float t = fmaf(q, -1.57079601e+00f, x);
+    t = fmaf(q, -3.13916473e-07f, t);
+    t = fmaf(q, -5.39030253e-15f, t);
+    const float t2 = t * t;
+    const float sp = fmaf(fmaf(fmaf(-1.95152959e-4f, t2, 8.33216087e-3f), t2, -1.66666546e-1f), t2 * t, t);
+    const float cp = fmaf(fmaf(fmaf(fmaf(2.44331571e-5f, t2, -1.38873163e-3f), t2, 4.16666457e-2f), t2, -0.5f), t2, 1.0f);
+    const float ss = (iq & 1) ? cp : sp, cc = (iq & 1) ? sp : cp;
+    s = (iq & 2) ? -ss : ss;
+    c = ((iq + 1) & 2) ? -cc : cc;
+}
+
+// the rare part of a step, kept out of line (by value: a reference would pin the loop state to local memory): a wrap of the phase into
+// (-2 pi, 2 pi) is due, or the step is too large for the small-angle rotation of (cs, sn). Returns (wrapped phase, flag, sin, cos): with
+// the flag set, (cs, sn) were recomputed from the phase.
+__device__ __noinline__ float4 costas_wrap(float phase, float d)
+{
+    bool refresh = fabsf(d) > 0.05f;
+    // while (phase > 2*M_PI) in double == float compare against the largest float below 2*pi (0x40C90FDA)
+    while (phase > 6.283185005f) {
+        phase = (float)((double)phase - 6.283185307179586);
+        refresh = true;
+    }
+    while (phase < -6.283185005f) {
+        phase = (float)((double)phase + 6.283185307179586);
+        refresh = true;
+    }
+    float sn = 0.f, cs = 0.f;
+    if (refresh)
+        sincos_loop_phase(phase, sn, cs);
+    return make_float4(phase, refresh ? 1.0f : 0.0f, sn, cs);
+}
+
+// one sample of costas_loop.cpp:23-65. ANCHOR: (cs, sn) are recomputed from the float phase afterwards (every 4th sample: bounds the
+// rotation's rounding drift to < 1e-6); otherwise they are rotated by the exact increment the float phase took.
+template <int ORDER, bool ANCHOR>
+__device__ __forceinline__ float2 costas_step(const float2 x, CostasRegs &r, float al, float be, float fmin, float fmax)
+{
+    // in * (cos(-phase) + j sin(-phase))  (costas_loop.cpp:26)
+    const float vr = fmaf(x.y, r.sn, x.x * r.cs);
+    const float vi = fmaf(-x.x, r.sn, x.y * r.cs);
+    const float err = costas_err<ORDER>(vr, vi);
+    r.freq = r.freq + be * err;
+    const float prev = r.phase;
+    r.phase = r.phase + (r.freq + al * err);
+    const float d = r.phase - prev; // the increment the float phase really took (exact difference)
+    r.freq = fminf(fmax, fmaxf(fmin, r.freq));
+    const bool rare = fmaxf(fabsf(r.phase), fabsf(d) * 125.0f) > 6.25f; // a wrap is due or the step is too large to rotate by
+    if (!ANCHOR) {
+        // rotate (cs, sn) by the small increment d: Taylor sin/cos, |d| <= 0.05 -> truncation < 2e-10. Done before the (almost never
+        // taken) branch below so that the branch's condition is long resolved when the rotation's last instruction issues.
+        const float d2 = d * d;
+        const float sd = d * fmaf(d2, fmaf(d2, 8.3333333e-3f, -0.16666667f), 1.0f);
+        const float cd = fmaf(d2, fmaf(d2, 4.1666667e-2f, -0.5f), 1.0f);
+        const float c2 = r.cs * cd - r.sn * sd;
+        r.sn = r.sn * cd + r.cs * sd;
+        r.cs = c2;
+    }
+    if (rare) {
+        const float4 w = costas_wrap(r.phase, d);
+        r.phase = w.x;
+        if (w.y != 0.0f && !ANCHOR) {
+            r.sn = w.z;
+            r.cs = w.w;
+        }
+    }
+    if (ANCHOR)
+        sincos_loop_phase(r.phase, r.sn, r.cs);
+    return make_float2(vr, vi);
+}
+
+// in/out: N samples. Segment s owns samples [s*L, min((s+1)L, N)); thread warms up from max(0, s*L - W).
+// state_in = {phase, freq} carried from the previous batch (exact start of segment 0 and of any clipped warm-up).
+// Rows of 16 samples move between HBM and the warp's shared-memory strip cooperatively (see swz16): lanes 8q..8q+7 carry the eight
+// 16-byte chunks of the row of thread 4i+q in their i-th copy; which row that is (its first row, row count, owned range) is
+// exchanged ONCE before the loop, so a copy costs an add, a compare and the address, no shuffles.
+template <int ORDER>
 __global__ void __launch_bounds__(SEG_THREADS) k_costas(const float2 *__restrict__ in, long N, int L, int W, int G, int nseg, CostasParams P,
                                                          const float *__restrict__ state_in, float2 *__restrict__ out, LoopRec *__restrict__ rec,
                                                          const int *__restrict__ repair_list, const int *__restrict__ repair_count)
@@ -1149,109 +1232,106 @@ __global__ void __launch_bounds__(SEG_THREADS) k_costas(const float2 *__restrict
     const long own0 = (long)s * L;
     const long own1 = active ? min(own0 + L, N) : own0;
     long start = own0 - W, gear_end = own0 - W + G;
-    float phase = 0.f, freq = state_in[1];
+    CostasRegs r;
+    r.phase = 0.f;
+    r.freq = state_in[1];
     if (repair_list && active) {
         start = own0;
-        phase = rec[s - 1].ph_end;
-        freq = rec[s - 1].fr_end;
+        r.phase = rec[s - 1].ph_end;
+        r.freq = rec[s - 1].fr_end;
         gear_end = 0;
     } else if (start <= 0) {
         start = 0;
-        phase = state_in[0];
+        r.phase = state_in[0];
         gear_end = 0;
     }
     const int row0 = (int)(start >> 4), row1 = (int)((own1 + 15) >> 4); // rows of 16 samples, [row0, row1)
-    int nrows = active ? row1 - row0 : 0, maxrows = nrows;
+    const int nrows = active ? row1 - row0 : 0;
+    int maxrows = nrows;
 #pragma unroll
     for (int off = 16; off; off >>= 1)
         maxrows = max(maxrows, __shfl_xor_sync(0xffffffffu, maxrows, off));
     LoopRec lr;
-    lr.ph_start = phase;
-    lr.fr_start = freq;
-    float sn, cs;
-    sincosf(phase, &sn, &cs);
-    warp_load_rows(ring, 0, 15, in, row0, nrows > 0, N, lane);
-    cp_async_commit();
+    lr.ph_start = r.phase;
+    lr.fr_start = r.freq;
+    sincos_loop_phase(r.phase, r.sn, r.cs);
+    // what this lane needs to know about the threads whose rows it carries
+    const int c = lane & 7;
+    int src_row0[8], src_nrows[8], src_orow0[8], src_own1[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int T = 4 * i + (lane >> 3);
+        src_row0[i] = __shfl_sync(0xffffffffu, row0, T);
+        src_nrows[i] = __shfl_sync(0xffffffffu, nrows, T);
+        src_orow0[i] = __shfl_sync(0xffffffffu, (int)(own0 >> 4), T); // first owned row
+        src_own1[i] = __shfl_sync(0xffffffffu, (int)own1, T);
+    }
+    const float2 *in_c = in + 2 * c;
+    auto load_row = [&](int it) { // row `it` of every thread -> input slot group it & 1
+        const int pb = (it & 1) * 8;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int T = 4 * i + (lane >> 3);
+            const int row = src_row0[i] + it;
+            if (it < src_nrows[i] && (long)row * 16 + 2 * c < N)
+                cp_async16(&ring[swz16(pb + c, T)], in_c + (long)row * 16);
+        }
+        cp_async_commit();
+    };
+    load_row(0);
     for (int it = 0; it < maxrows; it++) {
         const int slot = (it & 1) * 8;
-        warp_load_rows(ring, ((it + 1) & 1) * 8, 15, in, row0 + it + 1, it + 1 < nrows, N, lane);
-        cp_async_commit();
+        load_row(it + 1);
         cp_async_wait<1>();
         __syncwarp();
         const bool mine = it < nrows;
         const long b = (long)(row0 + it) << 4;
         // start / own0 are multiples of 16, so a row is entirely warm-up or entirely owned; only the batch's last row can be partial
         if (mine && b == own0) {
-            lr.ph_start = phase;
-            lr.fr_start = freq;
+            lr.ph_start = r.phase;
+            lr.fr_start = r.freq;
         }
-        const int nvalid = mine ? (int)min(16L, own1 - b) : 0;
         const bool gear = b < gear_end;
         const float al = gear ? 4.0f * P.alpha : P.alpha, be = gear ? 0.0f : P.beta;
-        // 4 samples per loop body (the sincosf re-anchor pattern has period 4): a full 16-sample unroll is 59 KB of code and
-        // stalls on instruction fetch (ncu: no_instruction 0.8 cycles per issue)
-#pragma unroll 2
-        for (int p = 0; p < 8; p++) {
-            const float4 v = ring[swz16(slot + p, lane)];
-            float2 o[2];
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const int j = 2 * p + h;
-                const float2 x = h ? make_float2(v.z, v.w) : make_float2(v.x, v.y);
-                o[h] = make_float2(0.f, 0.f);
-                if (j < nvalid) {
-                    // in * (cos(-phase) + j sin(-phase))  (costas_loop.cpp:26); (cs, sn) = cos/sin of the CURRENT float phase
-                    const float vr = x.x * cs + x.y * sn;
-                    const float vi = x.y * cs - x.x * sn;
-                    o[h] = make_float2(vr, vi);
-                    const float err = costas_error(vr, vi, P.order);
-                    freq = freq + be * err;
-                    const float prev = phase;
-                    phase = phase + (freq + al * err);
-                    const float d = phase - prev; // the increment the float phase really took (exact difference)
-                    bool refresh = (j & 3) == 3;
-                    if (fmaxf(fabsf(phase), fabsf(d) * 125.0f) > 6.25f) { // rare: a wrap is due or the step is too large to rotate by
-                        refresh = refresh || fabsf(d) > 0.05f;
-                        // while (phase > 2*M_PI) in double == float compare against the largest float below 2*pi (0x40C90FDA)
-                        while (phase > 6.283185005f) {
-                            phase = (float)((double)phase - 6.283185307179586);
-                            refresh = true;
-                        }
-                        while (phase < -6.283185005f) {
-                            phase = (float)((double)phase + 6.283185307179586);
-                            refresh = true;
-                        }
-                    }
-                    freq = fminf(P.fmax, fmaxf(P.fmin, freq));
-                    if (refresh)
-                        sincosf(phase, &sn, &cs); // exact re-anchor every 4 samples / on a wrap: bounds the rotation's rounding drift to < 1e-6
-                    else {
-                        // rotate (cs, sn) by the small increment d: Taylor sin/cos, |d| <= 0.05 -> truncation < 2e-10
-                        const float d2 = d * d;
-                        const float sd = d * fmaf(d2, fmaf(d2, 8.3333333e-3f, -0.16666667f), 1.0f);
-                        const float cd = fmaf(d2, fmaf(d2, 4.1666667e-2f, -0.5f), 1.0f);
-                        const float c2 = cs * cd - sn * sd;
-                        sn = sn * cd + cs * sd;
-                        cs = c2;
-                    }
-                }
+        if (mine && b + 16 <= own1) {
+            // full row: 4 groups of 4 samples (the re-anchor pattern has period 4; a full 16-sample unroll stalls on instruction fetch)
+#pragma unroll 1
+            for (int p = 0; p < 8; p += 2) {
+                const float4 v0 = ring[swz16(slot + p, lane)], v1 = ring[swz16(slot + p + 1, lane)];
+                const float2 o0 = costas_step<ORDER, false>(make_float2(v0.x, v0.y), r, al, be, P.fmin, P.fmax);
+                const float2 o1 = costas_step<ORDER, false>(make_float2(v0.z, v0.w), r, al, be, P.fmin, P.fmax);
+                const float2 o2 = costas_step<ORDER, false>(make_float2(v1.x, v1.y), r, al, be, P.fmin, P.fmax);
+                const float2 o3 = costas_step<ORDER, true>(make_float2(v1.z, v1.w), r, al, be, P.fmin, P.fmax);
+                obuf[swz16(p, lane)] = make_float4(o0.x, o0.y, o1.x, o1.y);
+                obuf[swz16(p + 1, lane)] = make_float4(o2.x, o2.y, o3.x, o3.y);
             }
-            obuf[swz16(p, lane)] = make_float4(o[0].x, o[0].y, o[1].x, o[1].y);
+        } else if (mine) {
+            const int nvalid = (int)min(16L, own1 - b);
+#pragma unroll 1
+            for (int p = 0; p < 8; p++) {
+                const float4 v = ring[swz16(slot + p, lane)];
+                float2 o0 = make_float2(0.f, 0.f), o1 = o0;
+                if (2 * p < nvalid)
+                    o0 = costas_step<ORDER, false>(make_float2(v.x, v.y), r, al, be, P.fmin, P.fmax);
+                if (2 * p + 1 < nvalid) {
+                    if (p & 1)
+                        o1 = costas_step<ORDER, true>(make_float2(v.z, v.w), r, al, be, P.fmin, P.fmax);
+                    else
+                        o1 = costas_step<ORDER, false>(make_float2(v.z, v.w), r, al, be, P.fmin, P.fmax);
+                }
+                obuf[swz16(p, lane)] = make_float4(o0.x, o0.y, o1.x, o1.y);
+            }
         }
         __syncwarp();
         // transposed copy-out: lanes 8q..8q+7 store the eight chunks of thread 4i+q's row (owned samples only)
-        const int wr0 = (int)min(own0, 0x7fffffffL), wr1 = (int)own1;
-        const int brow = (mine && b >= own0) ? (int)b : -1;
-        if (__any_sync(0xffffffffu, brow >= 0))
 #pragma unroll
         for (int i = 0; i < 8; i++) {
-            const int T = 4 * i + (lane >> 3), c = lane & 7;
-            const int bb = __shfl_sync(0xffffffffu, brow, T);
-            const int o0 = __shfl_sync(0xffffffffu, wr0, T), o1 = __shfl_sync(0xffffffffu, wr1, T);
-            const int n0 = bb + 2 * c;
-            if (bb >= 0 && n0 >= o0 && n0 < o1) {
+            const int T = 4 * i + (lane >> 3);
+            const int row = src_row0[i] + it;
+            const int n0 = row * 16 + 2 * c;
+            if (it < src_nrows[i] && row >= src_orow0[i] && n0 < src_own1[i]) {
                 const float4 v = obuf[swz16(c, T)];
-                if (n0 + 1 < o1)
+                if (n0 + 1 < src_own1[i])
                     *reinterpret_cast<float4 *>(out + n0) = v;
                 else
                     out[n0] = make_float2(v.x, v.y);
@@ -1261,8 +1341,8 @@ __global__ void __launch_bounds__(SEG_THREADS) k_costas(const float2 *__restrict
     }
     cp_async_wait<0>();
     if (active) {
-        lr.ph_end = phase;
-        lr.fr_end = freq;
+        lr.ph_end = r.phase;
+        lr.fr_end = r.freq;
         rec[s] = lr;
     }
 }

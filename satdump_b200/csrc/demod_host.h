@@ -117,6 +117,7 @@ class Demod
     DemodDevState *h_state = nullptr; // pinned snapshot for stats
     cudaEvent_t ev[4];
     int Wc, Wm, Gc = 0, Gm = 0, seg_cap_threads; // warm-up lengths, gear-shift parts of them
+    int seg_ctas = 3; // resident CTAs of the loop kernels per SM the segment count aims at
     long max_batch;
     int slot_cap_for(int L) const;
     int choose_L(long n) const;
