@@ -35,7 +35,7 @@ constexpr int RS_MAX_TAPS = 160;     // taps per polyphase arm
 constexpr int RS_SPAN = 2 * RS_THREADS + RS_MAX_TAPS + 8; // decimation < 2: at most 2 input samples per output
 constexpr int SEG_THREADS = 128;     // threads (= stream segments) per CTA in the loop kernels
 constexpr int MM_HIST = 16;       // inputs of the previous batch kept in the front pad (M&M reaches 7 back, Gardner up to 11)
-constexpr int MM_BANK_STRIDE = 9; // floats per arm row in smem: spreads the per-thread random arm reads over the banks
+constexpr int MM_BANK_STRIDE = 12; // floats per arm row in smem: 16-byte aligned rows (two 128-bit loads per arm), 8 bank groups
 constexpr int MM_SMEM_BYTES = 64 * SEG_THREADS * 8 + 128 * MM_BANK_STRIDE * 4;
 
 struct FirTaps { float h[32]; };
@@ -1562,6 +1562,27 @@ struct MMRec { int u_final, count, skip, pad; float mu_final, omega_final; int h
 // Fused input fix-up (rot_order != 0 or oqpsk): mmin is then the Costas loop's raw output, and every thread applies the exact
 // rotation by its row's quad[] entry (and the OQPSK one-sample delay of the imaginary rail, delay_one_imag.cpp:18-25) to each 16-sample
 // row of its ring right after the row has landed, instead of a separate pass over the whole stream (k_rotate).
+// 8 consecutive samples n0 .. n0+7 of this thread's ring (sample n sits in 16-byte chunk slot (n >> 1) & 31 of the swizzled strip): five
+// 128-bit loads and a select per value on the parity of n0, instead of eight 64-bit loads with their own address arithmetic.
+__device__ __forceinline__ void mm_fetch8(const float4 *__restrict__ ring, int n0, int lane, float2 (&x)[8])
+{
+    const int p0 = n0 >> 1;
+    const bool odd = n0 & 1;
+    float4 v[5];
+#pragma unroll
+    for (int j = 0; j < 5; j++) {
+        const int pp = (p0 + j) & 31;
+        v[j] = ring[pp * 32 + (lane ^ (pp & 7))];
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const float4 a = v[k >> 1], b = v[(k + 1) >> 1];
+        const float2 ev = (k & 1) ? make_float2(a.z, a.w) : make_float2(a.x, a.y);       // start even: sample k = chunk k/2, half k%2
+        const float2 od = ((k + 1) & 1) ? make_float2(b.z, b.w) : make_float2(b.x, b.y); // start odd: chunk (k+1)/2, half (k+1)%2
+        x[k] = make_float2(odd ? od.x : ev.x, odd ? od.y : ev.y);
+    }
+}
+
 template <bool STRICT, bool GARDNER>
 __global__ void __launch_bounds__(SEG_THREADS) k_mm(const float2 *__restrict__ mmin /* 16-sample front pad */, long N, int L, int W, int G, int nseg,
                                                      MMParams P, const MMState *__restrict__ st_in, MMState *__restrict__ st_out,
@@ -1663,7 +1684,11 @@ __global__ void __launch_bounds__(SEG_THREADS) k_mm(const float2 *__restrict__ m
     for (int i = 0; i < 4; i++) { mr.head_u[i] = 0; mr.head_mu[i] = 0.f; }
     const long emit0 = (s == 0 || repair_list) ? min(own0, u) : own0 - MM_ZONE;
     float2 *my = slots + (long)s * cap;
-    const float2 *ringf = reinterpret_cast<const float2 *>(ring);
+    // the symbol loop runs on 32-bit offsets from the thread's start: ur = u - ubase (a segment plus its warm-up is far below 2^31)
+    const long ubase = u;
+    int ur = 0;
+    const int emit32 = (int)max(-0x40000000L, min(0x40000000L, emit0 - ubase)), gear32 = (int)max(-0x40000000L, min(0x40000000L, gear_end - ubase));
+    const int uring = (int)(ubase & 63) + 64; // ring sample index of sample n is (n + 64) mod 64 taken over chunk slots: only (n >> 1) & 31 and n & 1 matter
     bool done = !active;
     for (int it = 0; it < maxit; it++) {
         const int rr = r0 + 1 + it;
@@ -1675,17 +1700,21 @@ __global__ void __launch_bounds__(SEG_THREADS) k_mm(const float2 *__restrict__ m
         fixrow(rr);
         if (!done) {
             const long lim = min((long)(rr + 1) << 4, own1);
-            while (u < lim) {
-                if (u >= emit0 && count < 4) {
-                    if (count == 0) { mr.head_u[0] = (int)u; mr.head_mu[0] = mu; }
-                    else if (count == 1) { mr.head_u[1] = (int)u; mr.head_mu[1] = mu; }
-                    else if (count == 2) { mr.head_u[2] = (int)u; mr.head_mu[2] = mu; }
-                    else { mr.head_u[3] = (int)u; mr.head_mu[3] = mu; }
+            const int lim32 = (int)(lim - ubase);
+            while (ur < lim32) {
+                const bool emit = ur >= emit32;
+                if (emit && count < 4) {
+                    if (count == 0) { mr.head_u[0] = (int)(ubase + ur); mr.head_mu[0] = mu; }
+                    else if (count == 1) { mr.head_u[1] = (int)(ubase + ur); mr.head_mu[1] = mu; }
+                    else if (count == 2) { mr.head_u[2] = (int)(ubase + ur); mr.head_mu[2] = mu; }
+                    else { mr.head_u[3] = (int)(ubase + ur); mr.head_mu[3] = mu; }
                 }
                 p2 = p1; p1 = p0; c2 = c1; c1 = c0;
-                int imu = (int)rintf(mu * 128.0f);
+                int imu = __float2int_rn(mu * 128.0f); // (int)rint(mu * 128)
                 imu = max(0, min(127, imu));
-                const float *tp = &sbank[imu * MM_BANK_STRIDE];
+                const float4 *tp4 = reinterpret_cast<const float4 *>(&sbank[imu * MM_BANK_STRIDE]);
+                const float4 ta = tp4[0], tb = tp4[1];
+                const float tp[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
                 float zr = 0.f, zi = 0.f;
                 if (GARDNER) { // zero-crossing sample (clock_recovery_gardner.cpp:49-63,88)
                     const float muz = (float)((double)mu - (double)omega / 2.0);
@@ -1698,40 +1727,36 @@ __global__ void __launch_bounds__(SEG_THREADS) k_mm(const float2 *__restrict__ m
                     int imuz = (int)rintf(__fmul_rn(mupos, 128.0f));
                     imuz = max(0, min(127, imuz));
                     const float *tz = &sbank[imuz * MM_BANK_STRIDE];
-                    const int z0 = (int)(u - offzc - 7) + 64;
+                    float2 xz[8];
+                    mm_fetch8(ring, uring + ur - offzc - 7, lane, xz);
 #pragma unroll
                     for (int k = 0; k < 8; k++) {
-                        const int na = z0 + k;
-                        const float2 x = ringf[swz16((na >> 1) & 31, lane) * 2 + (na & 1)];
                         if (STRICT) {
-                            zr = __fadd_rn(zr, __fmul_rn(x.x, tz[k]));
-                            zi = __fadd_rn(zi, __fmul_rn(x.y, tz[k]));
+                            zr = __fadd_rn(zr, __fmul_rn(xz[k].x, tz[k]));
+                            zi = __fadd_rn(zi, __fmul_rn(xz[k].y, tz[k]));
                         } else {
-                            zr = fmaf(x.x, tz[k], zr);
-                            zi = fmaf(x.y, tz[k], zi);
+                            zr = fmaf(xz[k].x, tz[k], zr);
+                            zi = fmaf(xz[k].y, tz[k], zi);
                         }
                     }
                 }
-                const int n0 = (int)(u - 7) + 64; // >= 56
+                float2 xw[8];
+                mm_fetch8(ring, uring + ur - 7, lane, xw); // ring index of sample u - 7 (>= 56)
                 float ar = 0.f, ai = 0.f;
                 if (STRICT) {
 #pragma unroll
                     for (int k = 0; k < 8; k++) {
-                        const int na = n0 + k;
-                        const float2 x = ringf[swz16((na >> 1) & 31, lane) * 2 + (na & 1)];
-                        ar = __fadd_rn(ar, __fmul_rn(x.x, tp[k]));
-                        ai = __fadd_rn(ai, __fmul_rn(x.y, tp[k]));
+                        ar = __fadd_rn(ar, __fmul_rn(xw[k].x, tp[k]));
+                        ai = __fadd_rn(ai, __fmul_rn(xw[k].y, tp[k]));
                     }
                 } else {
                     float br = 0.f, bi = 0.f; // two chains (taps 0-3 / 4-7) to halve the dependent-FMA depth
 #pragma unroll
                     for (int k = 0; k < 4; k++) {
-                        const int na = n0 + k, nb = n0 + k + 4;
-                        const float2 x = ringf[swz16((na >> 1) & 31, lane) * 2 + (na & 1)], y = ringf[swz16((nb >> 1) & 31, lane) * 2 + (nb & 1)];
-                        ar = fmaf(x.x, tp[k], ar);
-                        ai = fmaf(x.y, tp[k], ai);
-                        br = fmaf(y.x, tp[k + 4], br);
-                        bi = fmaf(y.y, tp[k + 4], bi);
+                        ar = fmaf(xw[k].x, tp[k], ar);
+                        ai = fmaf(xw[k].y, tp[k], ai);
+                        br = fmaf(xw[k + 4].x, tp[k + 4], br);
+                        bi = fmaf(xw[k + 4].y, tp[k + 4], bi);
                     }
                     ar += br;
                     ai += bi;
@@ -1748,12 +1773,12 @@ __global__ void __launch_bounds__(SEG_THREADS) k_mm(const float2 *__restrict__ m
                     pe = xr - yr;
                 }
                 pe = fminf(1.0f, fmaxf(-1.0f, pe));
-                if (u >= emit0) {
+                if (emit) {
                     if (count < cap)
                         my[count] = p0;
                     count++;
                 }
-                if (u < gear_end)
+                if (ur < gear32)
                     mu = (mu + omega) + 4.0f * P.mu_gain * pe;
                 else {
                     omega = STRICT ? __fadd_rn(omega, __fmul_rn(P.omega_gain, pe)) : omega + P.omega_gain * pe;
@@ -1766,11 +1791,11 @@ __global__ void __launch_bounds__(SEG_THREADS) k_mm(const float2 *__restrict__ m
                     }
                     mu = STRICT ? __fadd_rn(__fadd_rn(mu, omega), __fmul_rn(P.mu_gain, pe)) : (mu + omega) + P.mu_gain * pe;
                 }
-                float fl = floorf(mu);
-                u += (long)fl;
+                const float fl = floorf(mu);
+                ur += (int)fl;
                 mu -= fl;
             }
-            if (u >= own1)
+            if (ubase + ur >= own1)
                 done = true;
         }
         __syncwarp(); // the next iteration's copy overwrites the oldest row of the ring
@@ -1778,6 +1803,7 @@ __global__ void __launch_bounds__(SEG_THREADS) k_mm(const float2 *__restrict__ m
     cp_async_wait<0>();
     if (!active)
         return;
+    u = ubase + ur;
     mr.u_final = (int)u;
     mr.mu_final = mu;
     mr.omega_final = omega;

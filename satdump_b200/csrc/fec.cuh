@@ -1150,62 +1150,96 @@ __device__ __forceinline__ uint8_t log_mul(uint8_t a, uint8_t b) { unsigned r = 
 
 // Sequential part of correct_reed_solomon_decode (decode.c:32-222,340-378) on one lane. r[] is the received polynomial
 // (r[i] = codeword byte 254-i), syn[] its syndromes. Returns false when the locator does not factor (decode failure).
-__device__ bool rs_correct_lane(const RsTables &T, uint8_t *r, const uint8_t *syn, int nroots, int fcr, uint8_t *lam, uint8_t *prev, uint8_t *lamlog,
-                                uint8_t *roots, uint8_t *om, uint8_t *der)
+// libcorrect's decoder after the syndromes (decode.c:32-222), one warp per codeword, results identical to the serial code:
+//   Berlekamp-Massey with its order bookkeeping (:32-118): lane 0 (a data-dependent recurrence over the 32 syndromes);
+//   Chien search over all 256 field elements (:122-145): lane l tests elements 8l .. 8l+7, the roots are written in ascending order
+//     (per-lane bit masks, prefix counts by shuffles) and accepted iff their number equals the locator's order;
+//   error evaluator (polynomial.c: omega = lambda * syndromes mod x^nroots): lane k makes coefficient k;
+//   Forney (:165-196) + the location search (:198-222): lane q handles root q. The reference finds the location by scanning j = 0..255
+//     for j^11 == 1/root; that is j = (1/root)^(11^-1 mod 255), i.e. log j = 116 * log(1/root) mod 255 - except that its scan meets
+//     j = 0 first, whose "power" reads exp[0] = 1: for 1/root == 1 the location is log[0] = 0 (checked against the scan for every value).
+__device__ bool rs_correct_warp(const RsTables &T, uint8_t *r, const uint8_t *syn, int nroots, int fcr, uint8_t *lam, uint8_t *prev, uint8_t *lamlog,
+                                uint8_t *roots, uint8_t *om, uint8_t *der, int lane)
 {
-    const int gap = 11;
-    for (int i = 0; i < 66; i++) lam[i] = prev[i] = 0;
-    lam[0] = prev[0] = 1;
-    unsigned Lr = 0, order = 0, prev_order = 0, delay = 1;
-    uint8_t last_d = 1;
-    for (unsigned i = 0; i < (unsigned)nroots; i++) {
-        uint8_t d = syn[i];
-        for (unsigned j = 1; j <= Lr; j++) d ^= gf_mul(T, lam[j], syn[i - j]);
-        if (!d) { delay++; continue; }
-        if (2 * Lr <= i) {
-            for (int j = (int)prev_order; j >= 0; j--) prev[j + delay] = gf_div(T, gf_mul(T, prev[j], d), last_d);
-            for (int j = (int)delay - 1; j >= 0; j--) prev[j] = 0;
-            for (unsigned j = 0; j <= prev_order + delay; j++) { uint8_t t = lam[j]; lam[j] ^= prev[j]; prev[j] = t; }
-            unsigned t = order; order = prev_order + delay; prev_order = t;
-            Lr = i + 1 - Lr; last_d = d; delay = 1;
-            continue;
+    unsigned order = 0;
+    if (lane == 0) {
+        for (int i = 0; i < 66; i++) lam[i] = prev[i] = 0;
+        lam[0] = prev[0] = 1;
+        unsigned Lr = 0, prev_order = 0, delay = 1;
+        uint8_t last_d = 1;
+        for (unsigned i = 0; i < (unsigned)nroots; i++) {
+            uint8_t d = syn[i];
+            for (unsigned j = 1; j <= Lr; j++) d ^= gf_mul(T, lam[j], syn[i - j]);
+            if (!d) { delay++; continue; }
+            if (2 * Lr <= i) {
+                for (int j = (int)prev_order; j >= 0; j--) prev[j + delay] = gf_div(T, gf_mul(T, prev[j], d), last_d);
+                for (int j = (int)delay - 1; j >= 0; j--) prev[j] = 0;
+                for (unsigned j = 0; j <= prev_order + delay; j++) { uint8_t t = lam[j]; lam[j] ^= prev[j]; prev[j] = t; }
+                unsigned t = order; order = prev_order + delay; prev_order = t;
+                Lr = i + 1 - Lr; last_d = d; delay = 1;
+                continue;
+            }
+            for (int j = (int)prev_order; j >= 0; j--) lam[j + delay] ^= gf_div(T, gf_mul(T, prev[j], d), last_d);
+            if (prev_order + delay > order) order = prev_order + delay;
+            delay++;
         }
-        for (int j = (int)prev_order; j >= 0; j--) lam[j + delay] ^= gf_div(T, gf_mul(T, prev[j], d), last_d);
-        if (prev_order + delay > order) order = prev_order + delay;
-        delay++;
+        for (unsigned i = 0; i <= order; i++) lamlog[i] = T.log[lam[i]];
     }
-    for (unsigned i = 0; i <= order; i++) lamlog[i] = T.log[lam[i]];
-    unsigned nr = 0;
-    for (int e = 0; e < 256; e++) {
+    order = __shfl_sync(0xffffffffu, order, 0);
+    __syncwarp();
+    // Chien: lambda at every field element
+    unsigned mask = 0;
+#pragma unroll 1
+    for (int k = 0; k < 8; k++) {
+        const int e = 8 * lane + k;
         uint8_t v;
         if (e == 0) v = lamlog[0] ? T.exp[lamlog[0]] : 0;
         else {
-            uint8_t el = T.log[e], pw = T.log[1];
+            const uint8_t el = T.log[e];
+            uint8_t pw = T.log[1];
             v = 0;
             for (unsigned i = 0; i <= order; i++) { if (lamlog[i]) v ^= T.exp[lamlog[i] + pw]; pw = log_mul(pw, el); }
         }
-        if (!v) { if (nr < 64) roots[nr] = (uint8_t)e; nr++; }
+        if (!v) mask |= 1u << k;
     }
-    if (nr != order) return false;
-    for (int i = 0; i < 32; i++) om[i] = 0;
-    for (unsigned i = 0; i <= order; i++) {
-        if (i > (unsigned)nroots - 1) continue;
-        unsigned jl = nroots - 1 - i;
-        for (unsigned j = 0; j <= jl; j++) om[i + j] ^= gf_mul(T, lam[i], syn[j]);
+    int pos = __popc(mask), nr;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, pos, off);
+        if (lane >= off) pos += o;
     }
-    for (unsigned i = 0; i + 1 <= order; i++) der[i] = ((i + 1) % 2) ? lam[i + 1] : 0;
-    for (unsigned qi = 0; qi < order; qi++) {
-        uint8_t root = roots[qi];
-        if (root == 0) continue;
-        uint8_t locv = gf_div(T, 1, root), loc = 0;
-        for (int j = 0; j < 256; j++)
-            if (gf_pow(T, (uint8_t)j, gap) == locv) { loc = T.log[j]; break; }
-        uint8_t el = T.log[root], pw = T.log[1], num = 0, den = 0;
-        for (int i = 0; i < nroots; i++) { if (om[i]) num ^= T.exp[T.log[om[i]] + pw]; pw = log_mul(pw, el); }
-        pw = T.log[1];
-        for (unsigned i = 0; i + 1 <= order; i++) { if (der[i]) den ^= T.exp[T.log[der[i]] + pw]; pw = log_mul(pw, el); }
-        r[loc] ^= gf_mul(T, gf_pow(T, root, fcr - 1), gf_div(T, num, den));
+    nr = __shfl_sync(0xffffffffu, pos, 31);
+    pos -= __popc(mask); // exclusive
+    for (int k = 0; k < 8; k++)
+        if (mask >> k & 1) {
+            if (pos < 64) roots[pos] = (uint8_t)(8 * lane + k);
+            pos++;
+        }
+    if ((unsigned)nr != order) return false;
+    // omega and lambda' (nroots <= 32 coefficients: one per lane)
+    if (lane < nroots) {
+        uint8_t acc = 0;
+        const unsigned top = min(order, (unsigned)lane);
+        for (unsigned i = 0; i <= top; i++) acc ^= gf_mul(T, lam[i], syn[lane - i]);
+        om[lane] = acc;
     }
+    if ((unsigned)lane < order) der[lane] = ((lane + 1) % 2) ? lam[lane + 1] : 0;
+    __syncwarp();
+    const int gapinv = 116; // 11 * 116 = 5 * 255 + 1
+    if ((unsigned)lane < order) {
+        const uint8_t root = roots[lane];
+        if (root != 0) {
+            const uint8_t locv = gf_div(T, 1, root);
+            const uint8_t loc = locv == 1 ? 0 : (uint8_t)(((int)T.log[locv] * gapinv) % 255);
+            const uint8_t el = T.log[root];
+            uint8_t pw = T.log[1], num = 0, den = 0;
+            for (int i = 0; i < nroots; i++) { if (om[i]) num ^= T.exp[T.log[om[i]] + pw]; pw = log_mul(pw, el); }
+            pw = T.log[1];
+            for (unsigned i = 0; i + 1 <= order; i++) { if (der[i]) den ^= T.exp[T.log[der[i]] + pw]; pw = log_mul(pw, el); }
+            r[loc] ^= gf_mul(T, gf_pow(T, root, fcr - 1), gf_div(T, num, den)); // (distinct roots -> distinct locations)
+        }
+    }
+    __syncwarp();
     return true;
 }
 
@@ -1269,13 +1303,7 @@ __global__ void __launch_bounds__(256) k_frames(const uint32_t *__restrict__ fif
             __syncwarp();
             int err = 0;
             if (nz) {
-                int ok = 1;
-                if (lane == 0) {
-                    // keep the received message to count changed bytes
-                    ok = rs_correct_lane(T, r, syn, fc.rs_nroots, fc.rs_fcr, lam, prev, lamlog, roots, om, der) ? 1 : 0;
-                }
-                ok = __shfl_sync(0xffffffffu, ok, 0);
-                __syncwarp();
+                const int ok = rs_correct_warp(T, r, syn, fc.rs_nroots, fc.rs_fcr, lam, prev, lamlog, roots, om, der, lane) ? 1 : 0;
                 if (!ok) err = -1;
                 else {
                     // copy back the message bytes only; parity stays as received (reedsolomon.cpp:96-104)
