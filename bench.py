@@ -322,7 +322,8 @@ class ChainPipe:
     def stats(self):
         d, f = self.ch.stats()
         return {"demod": {k: v for k, v in d.items() if k in ("costas_unconverged", "mm_unconverged", "repairs", "agc_clamped")},
-                "fec": {k: v for k, v in f.items() if k in ("replays", "rs_failed", "rs_corrected", "viterbi_state", "deframer_state", "frames_out")}}
+                "fec": {k: v for k, v in f.items() if k in ("replays", "rs_failed", "rs_corrected", "viterbi_state", "deframer_state", "frames_out", "start_redone", "tb_serial",
+                                                         "spec_steps", "tb_overlap")}}
 
 
 class DemodPipe:

@@ -113,6 +113,8 @@ typedef struct b200_demod_stats
     long kernel_launches;     /* CUDA kernels launched by this object so far                     */
     long agc_exact_passes;    /* batches whose AGC seeds needed the scanned (exact) pass: weak signal */
     long last_front_samples;  /* samples that entered the AGC in the last push (= nsamples unless the front-end resampler runs) */
+    float snr, peak_snr;      /* M2M4SNREstimator over the recovered symbols, dB (module stats keys "snr" / "peak_snr", module_psk_demod.cpp:190-194,242-243):
+                                 evaluated at the end of every push; the peak is the maximum of those */
 } b200_demod_stats;
 
 typedef struct b200_fec_stats
@@ -124,6 +126,10 @@ typedef struct b200_fec_stats
     long rs_corrected, rs_failed;
     long replays;             /* slow-path re-decodes (lock changes, start-state mis-speculation) */
     long kernel_launches;
+    long start_redone;        /* chunks decoded again because their speculated Viterbi start state was wrong (part of replays) */
+    long tb_serial;           /* chunks whose parallel chainback blocks disagreed and were chained back serially (part of replays) */
+    int spec_steps;           /* current length of the start-state speculation window (adapts to the channel) */
+    int tb_overlap;           /* current warm-up length of the parallel chainback blocks (adapts to the channel) */
 } b200_fec_stats;
 
 typedef struct b200_demod b200_demod;

@@ -344,3 +344,14 @@ def pipeline_timed(dcfg, fcfg, raw):
     nt = C.c_int(0)
     secs = lib().ref_pipeline_timed(C.byref(dcfg), C.byref(fcfg) if fcfg is not None else None, _p(raw), n, _p(cadu), cap, C.byref(nb), C.byref(nt))
     return secs, cadu[:nb.value].copy(), nt.value
+
+
+def snr_m2m4(symbols, chunk=11667):
+    """M2M4SNREstimator of the reference over complex64 symbols, updated every `chunk` symbols like PSKDemodModule::process; returns
+    (snr after the last update, peak) in dB."""
+    x = np.ascontiguousarray(symbols, np.complex64)
+    out = np.zeros(4, np.float32)
+    L = C.CDLL(_PATH)
+    L.ref_snr_m2m4.argtypes = [C.c_void_p, C.c_long, C.c_long, C.c_void_p]
+    L.ref_snr_m2m4(x.ctypes.data, x.size, chunk, out.ctypes.data)
+    return float(out[0]), float(out[1])

@@ -41,6 +41,7 @@
 #include "common/dsp/block.h"
 #include "common/dsp/utils/agc.h"
 #include "common/dsp/utils/correct_iq.h"
+#include "common/dsp/utils/snr_estimator.h"
 #include "common/dsp/filter/fir.h"
 #include "common/dsp/filter/firdes.h"
 #include "common/dsp/pll/costas_loop.h"
@@ -205,6 +206,24 @@ namespace
 
 extern "C"
 {
+    // M2M4SNREstimator (snr_estimator.cpp) over a symbol stream fed in `chunk`-symbol updates as PSKDemodModule::process does
+    // (module_psk_demod.cpp:190-194): out[0] = snr() after the last update, out[1] = the peak over all updates, out[2], out[3] = y1, y2
+    void ref_snr_m2m4(const float *syms, long n, long chunk, float *out)
+    {
+        M2M4SNREstimator est;
+        float snr = 0, peak = 0;
+        for (long pos = 0; pos < n; pos += chunk)
+        {
+            long m = std::min(chunk, n - pos);
+            est.update((complex_t *)syms + pos, (int)m);
+            snr = est.snr();
+            if (snr > peak)
+                peak = snr;
+        }
+        out[0] = snr;
+        out[1] = peak;
+    }
+
     void *ref_demod_create(const ref_demod_cfg *c)
     {
         RefDemod *d = new RefDemod();

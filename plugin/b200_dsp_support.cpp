@@ -153,8 +153,8 @@ namespace b200plugin
         {
             nlohmann::json v; // keys of PSKDemodModule::getModuleStats (module_psk_demod.cpp:238-246)
             v["progress"] = stage->progress.load();
-            v["snr"] = 0;
-            v["peak_snr"] = 0;
+            v["snr"] = stage->snr.load();
+            v["peak_snr"] = stage->peak_snr.load();
             v["freq"] = stage->freq.load();
             return v;
         }

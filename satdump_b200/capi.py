@@ -51,13 +51,14 @@ class DemodStats(C.Structure):
     _fields_ = [("samples_in", C.c_long), ("symbols_out", C.c_long), ("agc_gain", C.c_float), ("costas_phase", C.c_float),
                 ("costas_freq", C.c_float), ("mm_mu", C.c_float), ("mm_omega", C.c_float), ("costas_unconverged", C.c_long),
                 ("mm_unconverged", C.c_long), ("agc_clamped", C.c_int), ("repairs", C.c_int), ("kernel_launches", C.c_long),
-                ("agc_exact_passes", C.c_long), ("last_front_samples", C.c_long)]
+                ("agc_exact_passes", C.c_long), ("last_front_samples", C.c_long), ("snr", C.c_float), ("peak_snr", C.c_float)]
 
 
 class FecStats(C.Structure):
     _fields_ = [("soft_in", C.c_long), ("chunks", C.c_long), ("bits_out", C.c_long), ("frames_out", C.c_long),
                 ("viterbi_state", C.c_int), ("viterbi_ber", C.c_float), ("deframer_state", C.c_int), ("rs_corrected", C.c_long),
-                ("rs_failed", C.c_long), ("replays", C.c_long), ("kernel_launches", C.c_long)]
+                ("rs_failed", C.c_long), ("replays", C.c_long), ("kernel_launches", C.c_long), ("start_redone", C.c_long), ("tb_serial", C.c_long),
+                ("spec_steps", C.c_int), ("tb_overlap", C.c_int)]
 
 
 class B200Error(RuntimeError):

@@ -628,7 +628,8 @@ void Demod::stage_mm(float2 *mmin, long n, int L, int nseg, int cur, int nxt, in
         launches += 2;
     }
     k_mm_compact<<<std::min(nseg, 148 * 8), 256, 0, stream>>>(slots.p, cap, mrec.p, offs.p, nseg, bps == 1, sym_out.p, sdst);
-    launches += 3;
+    k_snr_m2m4<<<1, 1024, 0, stream>>>(sym_out.p, offs.p + nseg, 0.001f, S->snr_y[cur], S->snr_y[nxt]); // M2M4SNREstimator(alpha = 0.001)
+    launches += 4;
 #undef B200_MM_LAUNCH
 }
 
@@ -745,6 +746,17 @@ long Demod::process(const void *d_raw, long n, int8_t *soft_dst)
     last_syms = *h_total;
     total_in += n_in;
     total_syms += last_syms;
+    {
+        // M2M4SNREstimator::snr (snr_estimator.cpp:41-47), float arithmetic as there
+        const float y1 = h_state->snr_y[nxt][0], y2 = h_state->snr_y[nxt][1];
+        const float y1_2 = y1 * y1;
+        const float sig = (float)sqrt(2 * y1_2 - y2), noise = (float)(y1 - sqrt(2 * y1_2 - y2));
+        snr_now = std::max<float>(0, (float)(10.0 * log10(sig / noise)));
+        if (!(snr_now == snr_now))
+            snr_now = 0.f;
+        if (snr_now > snr_peak)
+            snr_peak = snr_now;
+    }
     if (h_state->flags & 1)
         agc_clamped_batches++; // the clamp pass produced this batch's front stage (silent input): information, not an error
     if (h_state->flags & 2)
@@ -877,6 +889,8 @@ void Demod::stats(b200_demod_stats *o)
     o->kernel_launches = launches;
     o->agc_exact_passes = h_state->agc_exact;
     o->last_front_samples = last_front;
+    o->snr = snr_now;
+    o->peak_snr = snr_peak;
 }
 
 } // namespace b200

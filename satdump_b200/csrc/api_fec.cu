@@ -127,6 +127,8 @@ Fec::Fec(const b200_fec_cfg &c) : cfg(c)
     const long max_new_bits = max_chunks * (long)geom.F;
     fifo.alloc((size_t)((max_new_bits + 2L * cfg.cadu_size + 4096) / 32 + 8));
     start_state.alloc(max_chunks + 1);
+    redo_list.alloc(2 * (size_t)max_chunks + 4); // chunk indices to decode again | chunks whose BER check follows
+    h_start.resize(max_chunks + 2);
     rec.alloc(max_chunks + 1);
     tb_blocks = ((geom.F + 31) / 32 + TB_WORDS - 1) / TB_WORDS;
     tb_edges.alloc(simple ? 1 : (size_t)(max_chunks + 1) * tb_blocks);
@@ -271,33 +273,101 @@ static void viterbi_segment(Fec &f, long c0, long nch, std::vector<OutChunk> &ou
             f.launches++;
         }
         B200_CUDA(cudaEventRecord(f.evm[0], f.stream));
-        k_vit_acs3<true, ACS_DEC_MODE><<<nb_main, 32 * wpb, 0, f.stream>>>(f.softbuf.p, c, n, f.geom, f.hyp, f.start_state.p, f.dec.p, f.rec.p);
+        k_vit_acs3<true, ACS_DEC_MODE><<<nb_main, 32 * wpb, 0, f.stream>>>(f.softbuf.p, c, n, f.geom, f.hyp, f.start_state.p, f.dec.p, f.rec.p, nullptr);
         B200_CUDA(cudaEventRecord(f.evm[1], f.stream));
         {
             const long nthr = (long)n * f.tb_blocks;
             B200_CUDA(cudaMemsetAsync(f.tb_list.p, 0, sizeof(int), f.stream));
-            k_vit_tb<<<(unsigned)((nthr + 127) / 128), 128, 0, f.stream>>>(n, f.tb_blocks, f.geom, f.dec.p, f.chunk_bits.p, out_base, f.rec.p, f.tb_edges.p);
-            k_vit_tb_check<<<(n + 255) / 256, 256, 0, f.stream>>>(n, f.tb_blocks, f.tb_edges.p, f.tb_list.p, n);
+            k_vit_tb<<<(unsigned)((nthr + 127) / 128), 128, 0, f.stream>>>(n, f.tb_blocks, f.geom, f.dec.p, f.chunk_bits.p, out_base, f.rec.p, f.tb_edges.p, nullptr, f.tb_overlap);
+            k_vit_tb_check<<<(n + 255) / 256, 256, 0, f.stream>>>(n, f.tb_blocks, f.tb_edges.p, f.tb_list.p, n, nullptr);
             k_vit_tb_serial<<<(n + 127) / 128, 128, 0, f.stream>>>(f.tb_list.p, n, f.geom, f.dec.p, f.chunk_bits.p, out_base, f.rec.p); // (threads beyond the list return at once)
             f.launches += 3;
         }
-        k_vit_ber<<<nb_main, 32 * wpb, 0, f.stream>>>(f.softbuf.p, c, n, f.geom, f.hyp, f.chunk_bits.p, out_base, f.enc_state, f.rec.p);
+        k_vit_ber<<<nb_main, 32 * wpb, 0, f.stream>>>(f.softbuf.p, c, n, f.geom, f.hyp, f.chunk_bits.p, out_base, f.enc_state, f.rec.p, nullptr);
         f.launches += 2;
         B200_CUDA(cudaMemcpyAsync(f.h_rec, f.rec.p, sizeof(VitRec) * n, cudaMemcpyDeviceToHost, f.stream));
         int tb_redone = 0;
         B200_CUDA(cudaMemcpyAsync(&tb_redone, f.tb_list.p, sizeof(int), cudaMemcpyDeviceToHost, f.stream));
         B200_CUDA(cudaStreamSynchronize(f.stream));
         f.tb_serial_total += tb_redone;
+        if (n > 64) { // the chainback warm-up follows the channel like the speculation window does
+            const double frac = (double)tb_redone / (double)n;
+            if (frac > 0.02) {
+                f.tb_overlap = std::min(TB_OVERLAP_MAX, f.tb_overlap * 2);
+                f.tb_clean = 0;
+            } else if (frac < 0.002 && ++f.tb_clean >= 32) { // (slowly back: one doubling squares the miss probability, so the
+                f.tb_overlap = std::max(TB_OVERLAP, f.tb_overlap / 2); //  shorter window would fail again at once on the same channel)
+                f.tb_clean = 0;
+            }
+        }
         {
             float ms = 0;
             cudaEventElapsedTime(&ms, f.evm[0], f.evm[1]);
             f.t_vit_main += ms;
             f.last_main_chunks += n;
         }
+        // Start states that were speculated wrong (k_vit_spec: common at low SNR, where 768 steps do not always pin the state): those
+        // chunks alone are decoded again from the state their predecessor really left. A chunk's end state almost never depends on its
+        // start state, so one round normally settles it; a round that changes a successor's start state is followed by another.
+        for (int round = 0; round < 6; round++) {
+            f.h_redo.clear();
+            for (int i = 1; i < n; i++)
+                if (f.h_rec[i].start_used != f.h_rec[i - 1].next_start) {
+                    f.h_redo.push_back(i);
+                    f.h_start[i] = f.h_rec[i - 1].next_start;
+                }
+            if (round == 0 && n > 64) {
+                // the speculation window follows the channel: many wrong guesses (low SNR: the survivors of 768 steps have not all
+                // merged) -> twice the window for the next launch; almost none -> back towards the default
+                const double frac = (double)f.h_redo.size() / (double)n;
+                const int base = f.geom.rate34 ? VIT_SPEC_STEPS_34 : VIT_SPEC_STEPS_12, top = (f.geom.F / 32) * 32;
+                if (frac > 0.02) {
+                    f.spec_steps = std::min(top, f.spec_steps * 2);
+                    f.spec_clean = 0;
+                } else if (frac < 0.002 && ++f.spec_clean >= 32) {
+                    f.spec_steps = std::max(base, f.spec_steps / 2);
+                    f.spec_clean = 0;
+                }
+            }
+            if (f.h_redo.empty())
+                break;
+            const int m = (int)f.h_redo.size();
+            f.replays += m;
+            f.start_redone += m;
+            // the BER check of a chunk reads the last test bits of its predecessor: redo it for the successors too
+            f.h_redo_ber = f.h_redo;
+            for (int i : f.h_redo)
+                if (i + 1 < n)
+                    f.h_redo_ber.push_back(i + 1);
+            std::sort(f.h_redo_ber.begin(), f.h_redo_ber.end());
+            f.h_redo_ber.erase(std::unique(f.h_redo_ber.begin(), f.h_redo_ber.end()), f.h_redo_ber.end());
+            const int mb = (int)f.h_redo_ber.size();
+            for (int i : f.h_redo)
+                B200_CUDA(cudaMemcpyAsync(f.start_state.p + i, &f.h_start[i], sizeof(int), cudaMemcpyHostToDevice, f.stream));
+            B200_CUDA(cudaMemcpyAsync(f.redo_list.p, f.h_redo.data(), sizeof(int) * m, cudaMemcpyHostToDevice, f.stream));
+            B200_CUDA(cudaMemcpyAsync(f.redo_list.p + n, f.h_redo_ber.data(), sizeof(int) * mb, cudaMemcpyHostToDevice, f.stream));
+            B200_CUDA(cudaEventRecord(f.evm[0], f.stream));
+            k_vit_acs3<true, ACS_DEC_MODE><<<(m + wpb - 1) / wpb, 32 * wpb, 0, f.stream>>>(f.softbuf.p, c, m, f.geom, f.hyp, f.start_state.p, f.dec.p, f.rec.p, f.redo_list.p);
+            B200_CUDA(cudaEventRecord(f.evm[1], f.stream));
+            const long nthr = (long)m * f.tb_blocks;
+            B200_CUDA(cudaMemsetAsync(f.tb_list.p, 0, sizeof(int), f.stream));
+            k_vit_tb<<<(unsigned)((nthr + 127) / 128), 128, 0, f.stream>>>(m, f.tb_blocks, f.geom, f.dec.p, f.chunk_bits.p, out_base, f.rec.p, f.tb_edges.p, f.redo_list.p, f.tb_overlap);
+            k_vit_tb_check<<<(m + 255) / 256, 256, 0, f.stream>>>(m, f.tb_blocks, f.tb_edges.p, f.tb_list.p, n, f.redo_list.p);
+            k_vit_tb_serial<<<(m + 127) / 128, 128, 0, f.stream>>>(f.tb_list.p, n, f.geom, f.dec.p, f.chunk_bits.p, out_base, f.rec.p);
+            k_vit_ber<<<(mb + wpb - 1) / wpb, 32 * wpb, 0, f.stream>>>(f.softbuf.p, c, mb, f.geom, f.hyp, f.chunk_bits.p, out_base, f.enc_state, f.rec.p, f.redo_list.p + n);
+            f.launches += 5;
+            B200_CUDA(cudaMemcpyAsync(f.h_rec, f.rec.p, sizeof(VitRec) * n, cudaMemcpyDeviceToHost, f.stream));
+            B200_CUDA(cudaMemcpyAsync(&tb_redone, f.tb_list.p, sizeof(int), cudaMemcpyDeviceToHost, f.stream));
+            B200_CUDA(cudaStreamSynchronize(f.stream));
+            f.tb_serial_total += tb_redone;
+            float ms = 0;
+            cudaEventElapsedTime(&ms, f.evm[0], f.evm[1]);
+            f.t_vit_main += ms;
+        }
         int accepted = 0;
         for (int i = 0; i < n; i++) {
             if (i > 0 && f.h_rec[i].start_used != f.h_rec[i - 1].next_start) {
-                f.replays++; // start state mis-speculated: decode again from here with the true state
+                f.replays++; // still inconsistent after the redo rounds above: decode again from here with the true state
                 break;
             }
             accepted = i + 1;
@@ -316,6 +386,9 @@ static void viterbi_segment(Fec &f, long c0, long nch, std::vector<OutChunk> &ou
             if (lost)
                 break;
         }
+        if (getenv("B200_DEBUG_FEC"))
+            fprintf(stderr, "[fec] segment chunks [%ld, %ld): accepted %d, vit_state %d, invalid %d, last ber %.3f, redo rounds list %zu\n", c, c + n, accepted,
+                    f.vit_state, f.invalid, f.last_ber, f.h_redo.size());
         f.main_next_start = f.h_rec[accepted - 1].next_start;
         f.enc_state = f.h_rec[accepted - 1].enc_tail;
         out_base += accepted;
@@ -605,9 +678,10 @@ void Fec::process()
         B200_CUDA(cudaMemcpyAsync(dstate.p + 1, dstate.p, sizeof(DefrState), cudaMemcpyDeviceToDevice, stream));
         const long fifo_bits0 = fifo_bits, out_frames0 = out_frames, total_frames0 = total_frames, rs_c0 = rs_corrected, rs_f0 = rs_failed;
         const int nosync0 = nosync_runs;
-        viterbi_segment(*this, c, nch, outs);
+        const long seg_end = nch;
+        viterbi_segment(*this, c, seg_end, outs);
         const long nout = (long)outs.size();
-        long next_c = nch;
+        long next_c = seg_end;
         if (nout > 0) {
             B200_REQUIRE(((fifo_bits + nout * geom.F + 64) >> 5) + 2 < (long)fifo.n, B200_ESTATE, "internal: bit FIFO too small");
             int last_raw = 0;
@@ -639,6 +713,10 @@ void Fec::process()
                     if (st == 2) {
                         if (++nosync_runs >= 10) {
                             nosync_runs = 0;
+                            // viterbi.reset() after output chunk k. If the decoder had lost lock at exactly this chunk anyway, what
+                            // follows was already decoded from the IDLE state with the same carried registers: nothing to redo.
+                            if (outs[k].state_after == 0)
+                                continue;
                             redo_from = k;
                             break;
                         }
@@ -646,6 +724,8 @@ void Fec::process()
                         nosync_runs = 0;
                 }
             }
+            if (getenv("B200_DEBUG_FEC"))
+                fprintf(stderr, "[fec] process: chunks from %ld: %ld decoded, deframer events %d, redo_from %ld, nosync_runs %d\n", c, nout, h_counters[1], redo_from, nosync_runs);
             if (redo_from >= 0 && redo_from < nout - 1) {
                 // roll back to just after output chunk redo_from, with the Viterbi forced to IDLE
                 replays++;
@@ -726,6 +806,10 @@ void Fec::stats(b200_fec_stats *o)
     o->rs_corrected = rs_corrected;
     o->rs_failed = rs_failed;
     o->replays = replays + tb_serial_total; // start-state mis-speculations + chunks whose parallel chainback had to be redone serially
+    o->start_redone = start_redone;
+    o->tb_serial = tb_serial_total;
+    o->spec_steps = spec_steps;
+    o->tb_overlap = tb_overlap;
     o->kernel_launches = launches;
 }
 

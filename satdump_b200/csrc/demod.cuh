@@ -1948,5 +1948,50 @@ __global__ void __launch_bounds__(256) k_mm_compact(const float2 *__restrict__ s
     }
 }
 
+// ---------------------------------------------------------------- M2M4 SNR estimate over the recovered symbols
+// M2M4SNREstimator::update (common/dsp/utils/snr_estimator.cpp:16-39): two exponential averages y <- alpha * m + beta * y of |s|^2 and
+// |s|^4 over the symbol stream (alpha = 0.001: a memory of ~1000 symbols). Linear with constant coefficients, so the end value of a batch
+// is sum_i beta^(n-1-i) alpha m_i + beta^n y_in; terms older than 2^16 symbols weigh below e^-65 and are left out. One CTA: every thread
+// runs the recurrence over 64 consecutive symbols (fp64), the partial results are combined with their powers of beta.
+__global__ void __launch_bounds__(1024) k_snr_m2m4(const float2 *__restrict__ sym, const long *__restrict__ total, float alpha, const float *__restrict__ yin,
+                                                  float *__restrict__ yout)
+{
+    __shared__ double red[2][32];
+    const long n = *total;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int RUN = 64;
+    const long M = min(n, 1024L * RUN), base = n - M;
+    const double beta = (double)(float)(1.0 - (double)alpha), al = (double)alpha;
+    const long i0 = (long)t * RUN, i1 = min(M, i0 + RUN);
+    double a1 = 0.0, a2 = 0.0;
+    for (long i = i0; i < i1; i++) {
+        const float2 v = sym[base + i];
+        const float ab = hypotf(v.x, v.y);
+        const float m2 = ab * ab, m4 = ab * ab * ab * ab;
+        a1 = fma(a1, beta, al * (double)m2);
+        a2 = fma(a2, beta, al * (double)m4);
+    }
+    const double w = i1 > i0 ? pow(beta, (double)(M - i1)) : 0.0;
+    a1 *= w;
+    a2 *= w;
+#pragma unroll
+    for (int off = 16; off; off >>= 1) {
+        a1 += __shfl_xor_sync(0xffffffffu, a1, off);
+        a2 += __shfl_xor_sync(0xffffffffu, a2, off);
+    }
+    if (lane == 0) { red[0][warp] = a1; red[1][warp] = a2; }
+    __syncthreads();
+    if (t == 0) {
+        double s1 = 0.0, s2 = 0.0;
+        for (int k = 0; k < 32; k++) { s1 += red[0][k]; s2 += red[1][k]; }
+        const double carry = n > 0 ? pow(beta, (double)n) : 1.0;
+        float y1 = (float)(s1 + carry * (double)yin[0]), y2 = (float)(s2 + carry * (double)yin[1]);
+        if (y1 != y1) y1 = 0.f; // snr_estimator.cpp:27-30
+        if (y2 != y2) y2 = 0.f;
+        yout[0] = y1;
+        yout[1] = y2;
+    }
+}
+
 #endif // B200_DEFINE_KERNELS
 } // namespace b200

@@ -26,6 +26,7 @@ struct DemodDevState
     int mm_unconv;
     int repairs;        // segments re-run as exact continuations so far (all batches)
     int agc_exact;      // batches that needed the exact AGC pass so far
+    float snr_y[2][2];  // M2M4 SNR estimator: running averages of |s|^2, |s|^4 (snr_estimator.h:26)
 };
 
 class Demod
@@ -118,6 +119,7 @@ class Demod
     cudaEvent_t ev[4];
     int Wc, Wm, Gc = 0, Gm = 0, seg_cap_threads; // warm-up lengths, gear-shift parts of them
     int seg_ctas = 3; // resident CTAs of the loop kernels per SM the segment count aims at
+    float snr_now = 0.f, snr_peak = 0.f; // M2M4SNREstimator::snr() after the last push / its maximum so far (module_psk_demod.cpp:190-194)
     long max_batch;
     int slot_cap_for(int L) const;
     int choose_L(long n) const;

@@ -346,13 +346,15 @@ __device__ __forceinline__ int acs3_endstate(unsigned xl2, unsigned xh2, int lan
 // as one coalesced 256-byte store per 32 steps.
 template <bool MET_SMEM, int DEC_MODE> // DEC_MODE 0: STS row buffer, 1: lane j keeps step j (SEL), 2: per-lane bit accumulators + warp transpose
 __global__ void __launch_bounds__(128) k_vit_acs3(const int8_t *__restrict__ soft, long chunk0, int nchunks, VitGeom g, VitHyp h,
-                                                   const int *__restrict__ start_state, uint2 *__restrict__ dec, VitRec *__restrict__ rec)
+                                                   const int *__restrict__ start_state, uint2 *__restrict__ dec, VitRec *__restrict__ rec,
+                                                   const int *__restrict__ qlist)
 {
     __shared__ uint2 srow[4][2][32];
     __shared__ __align__(16) unsigned smet[4][2][32];
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q = blockIdx.x * 4 + wib;
-    if (q >= nchunks) return;
+    const int ql = blockIdx.x * 4 + wib;
+    if (ql >= nchunks) return;
+    const int q = qlist ? qlist[ql] : ql; // list mode: re-decode of the chunks whose speculated start state was wrong
     const int8_t *c = soft + (chunk0 + q) * (long)g.chunk;
     uint2 *d = dec + (long)q * g.dec_stride;
     const Acs3Lane L = acs3_lane_consts(lane);
@@ -432,9 +434,10 @@ __global__ void __launch_bounds__(128) k_vit_acs3(const int8_t *__restrict__ sof
 // words): block 0 starts from the true end state, block k>0 warms up over TB_OVERLAP rows and records the state it assumed at
 // its top edge; k_vit_tb_check compares it with the state its upper neighbour really left there. If every edge agrees the
 // result IS the serial chainback; chunks with a disagreeing edge are redone serially by k_vit_tb_serial (rare; counted).
-constexpr int TB_WORDS = 16;     // 512 output bits per block
-constexpr int TB_OVERLAP = 256;  // warm-up rows
 #endif // B200_DEFINE_KERNELS
+constexpr int TB_WORDS = 16;     // 512 output bits per block
+constexpr int TB_OVERLAP = 256;  // warm-up rows (default; the host doubles it up to TB_OVERLAP_MAX when edges disagree often: low SNR)
+constexpr int TB_OVERLAP_MAX = 2048;
 struct TbEdge { unsigned char assumed, left; };
 #ifdef B200_DEFINE_KERNELS
 __device__ __forceinline__ int tb_walk_rows(const uint2 *__restrict__ rowbase, int nrows, int st)
@@ -453,11 +456,12 @@ __device__ __forceinline__ int tb_walk_rows(const uint2 *__restrict__ rowbase, i
 }
 
 __global__ void __launch_bounds__(128) k_vit_tb(int nchunks, int nblocks, VitGeom g, const uint2 *__restrict__ dec, uint32_t *__restrict__ bits,
-                                                 long out_chunk0, VitRec *__restrict__ rec, TbEdge *__restrict__ edges)
+                                                 long out_chunk0, VitRec *__restrict__ rec, TbEdge *__restrict__ edges, const int *__restrict__ qlist, int overlap)
 {
     const long gid = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (long)nchunks * nblocks) return;
-    const int q = (int)(gid / nblocks), k = (int)(gid - (long)q * nblocks);
+    const int ql = (int)(gid / nblocks), k = (int)(gid - (long)ql * nblocks);
+    const int q = qlist ? qlist[ql] : ql;
     const uint2 *d = dec + (long)q * g.dec_stride;
     uint32_t *ob = bits + (out_chunk0 + q) * (long)g.bit_words;
     const int nwords = (g.F + 31) >> 5;
@@ -468,7 +472,7 @@ __global__ void __launch_bounds__(128) k_vit_tb(int nchunks, int nblocks, VitGeo
         st = rec[q].end_state;
     else {
         // top edge of this block = row 6 + 32*w_hi (first row above it); warm up from TB_OVERLAP rows higher
-        const int top = min(g.F, 32 * w_hi + TB_OVERLAP); // output index (exclusive) where the warm-up starts
+        const int top = min(g.F, 32 * w_hi + overlap); // output index (exclusive) where the warm-up starts
         st = tb_walk_rows(d + 6 + 32 * w_hi, top - 32 * w_hi, 0);
         edges[(long)q * nblocks + k].assumed = (unsigned char)st;
     }
@@ -495,10 +499,11 @@ __global__ void __launch_bounds__(128) k_vit_tb(int nchunks, int nblocks, VitGeo
 }
 
 // flags chunks whose blocks disagree at an edge; list[0] = count, list[1..] = chunk indices
-__global__ void k_vit_tb_check(int nchunks, int nblocks, const TbEdge *__restrict__ edges, int *__restrict__ list, int cap)
+__global__ void k_vit_tb_check(int nchunks, int nblocks, const TbEdge *__restrict__ edges, int *__restrict__ list, int cap, const int *__restrict__ qlist)
 {
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= nchunks) return;
+    const int ql = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ql >= nchunks) return;
+    const int q = qlist ? qlist[ql] : ql;
     bool bad = false;
     for (int k = 1; k < nblocks; k++)
         if (edges[(long)q * nblocks + k].assumed != edges[(long)q * nblocks + k - 1].left) bad = true;
@@ -534,10 +539,12 @@ __global__ void __launch_bounds__(128) k_vit_tb_serial(const int *__restrict__ l
 
 // BER pass (separate launch so every chunk's bits are complete): one warp per chunk.
 __global__ void __launch_bounds__(128) k_vit_ber(const int8_t *__restrict__ soft, long chunk0, int nchunks, VitGeom g, VitHyp h,
-                                                  const uint32_t *__restrict__ bits, long out_chunk0, int enc_state_in, VitRec *__restrict__ rec)
+                                                  const uint32_t *__restrict__ bits, long out_chunk0, int enc_state_in, VitRec *__restrict__ rec,
+                                                  const int *__restrict__ qlist)
 {
-    const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (q >= nchunks) return;
+    const int ql = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (ql >= nchunks) return;
+    const int q = qlist ? qlist[ql] : ql;
     const int8_t *c = soft + (chunk0 + q) * (long)g.chunk;
     const uint32_t *ob = bits + (out_chunk0 + q) * (long)g.bit_words;
     const int tb = g.rate34 ? VIT_TESTLEN * 3 / 4 : VIT_TESTLEN / 2;
@@ -1158,7 +1165,7 @@ __device__ __forceinline__ uint8_t log_mul(uint8_t a, uint8_t b) { unsigned r = 
 //   Forney (:165-196) + the location search (:198-222): lane q handles root q. The reference finds the location by scanning j = 0..255
 //     for j^11 == 1/root; that is j = (1/root)^(11^-1 mod 255), i.e. log j = 116 * log(1/root) mod 255 - except that its scan meets
 //     j = 0 first, whose "power" reads exp[0] = 1: for 1/root == 1 the location is log[0] = 0 (checked against the scan for every value).
-__device__ bool rs_correct_warp(const RsTables &T, uint8_t *r, const uint8_t *syn, int nroots, int fcr, uint8_t *lam, uint8_t *prev, uint8_t *lamlog,
+__device__ __noinline__ bool rs_correct_warp(const RsTables &T, uint8_t *r, const uint8_t *syn, int nroots, int fcr, uint8_t *lam, uint8_t *prev, uint8_t *lamlog,
                                 uint8_t *roots, uint8_t *om, uint8_t *der, int lane)
 {
     unsigned order = 0;

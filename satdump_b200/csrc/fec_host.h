@@ -47,8 +47,12 @@ class Fec
     DevBuf<VitRec> rec;
     DevBuf<TbEdge> tb_edges;
     DevBuf<int> tb_list; // [0] count of chunks redone serially in the last launch, [1..] their indices
+    DevBuf<int> redo_list; // chunks decoded again because their speculated start state was wrong (+ the chunks whose BER check follows)
+    std::vector<int> h_redo, h_redo_ber, h_start;
     int tb_blocks = 1;
-    long tb_serial_total = 0;
+    int tb_overlap = TB_OVERLAP; // warm-up rows of the parallel chainback blocks (adapts to the channel)
+    int tb_clean = 0, spec_clean = 0; // consecutive launches without misses (the windows shrink back slowly)
+    long tb_serial_total = 0, start_redone = 0; // chunks chained back serially / decoded again from a corrected start state
     DevBuf<VitIdleOut> idle_out;
     DevBuf<VitIdle2Out> idle2_out;
     VitIdle2Out *h_idle2 = nullptr;

@@ -351,10 +351,12 @@ void PskDemodStage::process()
         done += used;
         progress = filesize ? (double)done / (double)filesize : 0.0;
         b200_demod_stats st;
-        if (b200_demod_get_stats(h, &st) == B200_OK)
+        if (b200_demod_get_stats(h, &st) == B200_OK) {
             warn_unconverged(st);
-        if (b200_demod_get_stats(h, &st) == B200_OK)
             freq = st.costas_freq * (cfg.final_samplerate > 0 ? cfg.final_samplerate : cfg.samplerate) / (2.0 * M_PI); // rad_to_hz(freq, final_samplerate), module_psk_demod.cpp:196
+            snr = st.snr;
+            peak_snr = st.peak_snr;
+        }
     }
     if (fin)
         fclose(fin);

@@ -98,6 +98,7 @@ class PskDemodStage : public StageBase
     std::string getID() const override { return "psk_demod"; }
     // getModuleStats() keys of PSKDemodModule (module_psk_demod.cpp:238-246)
     std::atomic<double> progress{0}, freq{0};
+    std::atomic<float> snr{0}, peak_snr{0}; // M2M4SNREstimator over the recovered symbols (module_psk_demod.cpp:190-194)
     std::atomic<uint64_t> filesize{0};
     b200_demod_cfg cfg{};
     long batch_samples = 1 << 24;

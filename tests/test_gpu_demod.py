@@ -267,6 +267,27 @@ def test_post_costas_dc(built):
         capi.Demod(capi.demod_cfg(30e6, 15e6, "oqpsk", 0.5, post_costas_dc=True, max_batch=65536))
 
 
+def test_snr_estimate_follows_the_references_m2m4(built):
+    """Module stats keys "snr" / "peak_snr" (module_psk_demod.cpp:190-194,242-243): M2M4SNREstimator over the recovered symbols. The two
+    running averages are linear recurrences, evaluated on the GPU in closed form per push; the value after the last symbol equals the
+    reference's (fed its own symbols in its own buffer-sized updates) to a hundredth of a dB, whatever the batching."""
+    O = oracle()
+    if not hasattr(O, "snr_m2m4"):
+        pytest.skip("needs the compiled reference (oracle/_ref)")
+    for name in ("metop_ahrpt", "bpsk_half"):
+        cfg, raw, _ = signal(name, 21)
+        n = nsamples(raw, cfg)
+        want, _ = O.snr_m2m4(oracle_demod(O, cfg).run(raw)["mm"])
+        g = gpu_demod(cfg, n).push(raw)
+        s = g.stats()
+        assert 5.0 < want < 30.0 and abs(s["snr"] - want) <= 0.01 and s["peak_snr"] >= s["snr"], (s["snr"], s["peak_snr"], want)
+        per = 1 if cfg.fmt == "cf32" else 2
+        g2 = gpu_demod(cfg, n)
+        for a, b in ((0, 300001), (300001, 1000000), (1000000, n)):
+            g2.push(raw[a * per:b * per])
+        assert abs(g2.stats()["snr"] - want) <= 0.01, (g2.stats()["snr"], want)
+
+
 def test_errors_are_loud(built):
     from satdump_b200 import capi
     cfg, raw, _ = signal("metop_ahrpt", 16)

@@ -39,11 +39,11 @@ int main(int argc, char **argv)
         for (int rep = 0; rep < 6; rep++) {
             cudaEventRecord(e0);
             if (variant == 0) k_vit_acs<<<nb, 128>>>(d_soft, 0, nchunks, g, h, d_ss, d_dec[0], d_rec[0]);
-            else if (variant == 1) k_vit_acs3<false, 0><<<nb, 128>>>(d_soft, 0, nchunks, g, h, d_ss, d_dec[1], d_rec[1]);
-            else if (variant == 2) k_vit_acs3<true, 0><<<nb, 128>>>(d_soft, 0, nchunks, g, h, d_ss, d_dec[1], d_rec[1]);
-            else if (variant == 3) k_vit_acs3<false, 2><<<nb, 128>>>(d_soft, 0, nchunks, g, h, d_ss, d_dec[1], d_rec[1]);
-            else if (variant == 4) k_vit_acs3<true, 2><<<nb, 128>>>(d_soft, 0, nchunks, g, h, d_ss, d_dec[1], d_rec[1]);
-            else k_vit_acs3<true, 1><<<nb, 128>>>(d_soft, 0, nchunks, g, h, d_ss, d_dec[1], d_rec[1]);
+            else if (variant == 1) k_vit_acs3<false, 0><<<nb, 128>>>(d_soft, 0, nchunks, g, h, d_ss, d_dec[1], d_rec[1], nullptr);
+            else if (variant == 2) k_vit_acs3<true, 0><<<nb, 128>>>(d_soft, 0, nchunks, g, h, d_ss, d_dec[1], d_rec[1], nullptr);
+            else if (variant == 3) k_vit_acs3<false, 2><<<nb, 128>>>(d_soft, 0, nchunks, g, h, d_ss, d_dec[1], d_rec[1], nullptr);
+            else if (variant == 4) k_vit_acs3<true, 2><<<nb, 128>>>(d_soft, 0, nchunks, g, h, d_ss, d_dec[1], d_rec[1], nullptr);
+            else k_vit_acs3<true, 1><<<nb, 128>>>(d_soft, 0, nchunks, g, h, d_ss, d_dec[1], d_rec[1], nullptr);
             cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
             float ms; cudaEventElapsedTime(&ms, e0, e1); if (rep > 0 && ms < best) best = ms;
         }
