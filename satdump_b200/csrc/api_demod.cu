@@ -347,6 +347,8 @@ Demod::Demod(const b200_demod_cfg &c) : cfg(c)
             B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_agc_fir_w<2, false, false>, 32 * FW_WARPS, 0));
         fir_ctas = std::max(1, per_sm) * dev_sms;
         fir_warps = fir_ctas * FW_WARPS;
+        if (const char *e = getenv("B200_FIR_BULK")) // measured variant: raw chunks by 1-D bulk copy (TMA) instead of register prefetch
+            fir_bulk = atoi(e) != 0;
         if (const char *e = getenv("B200_AGC_WARM_TILES")) // 0 forces the exact (scanned-seed) pass: test hook
             agc_warm_max = std::max(0, atoi(e));
     }
@@ -500,6 +502,9 @@ template <int FMT> static void launch_front(Demod &d, const void *raw, long n, i
         if (dump)
             k_agc_fir_w<FMT, true, false><<<grid, 32 * FW_WARPS, 0, d.stream>>>(raw, n, d.cfg.agc_rate, &S->gain[cur], R, ctl, taps, S->agc_tail[cur],
                                                                               S->agc_tail[cur ^ 1], fir_out, d.agc_dump.p, &S->gain[cur ^ 1], &S->flags);
+        else if (d.fir_bulk)
+            k_agc_fir_w<FMT, false, false, true><<<grid, 32 * FW_WARPS, 0, d.stream>>>(raw, n, d.cfg.agc_rate, &S->gain[cur], R, ctl, taps, S->agc_tail[cur],
+                                                                                     S->agc_tail[cur ^ 1], fir_out, nullptr, &S->gain[cur ^ 1], &S->flags);
         else
             k_agc_fir_w<FMT, false, false><<<grid, 32 * FW_WARPS, 0, d.stream>>>(raw, n, d.cfg.agc_rate, &S->gain[cur], R, ctl, taps, S->agc_tail[cur],
                                                                                S->agc_tail[cur ^ 1], fir_out, nullptr, &S->gain[cur ^ 1], &S->flags);

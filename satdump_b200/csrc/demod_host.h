@@ -78,6 +78,7 @@ class Demod
     DevBuf<int> agc_need;          // [2] raised by the fast pass when a range cannot prove its seed
     unsigned agc_epoch = 0;
     int fir_ctas = 0;              // resident k_agc_fir_w CTAs on the device
+    bool fir_bulk = false;         // B200_FIR_BULK=1: the bulk-copy (TMA) variant of the raw prefetch (measured: profiles/README.md)
     int fir_warps = 0;             // ... and their warps: one range of tiles each (one wave)
     // front-end resampler (RationalResamplerBlock) / iq_swap pass
     bool resamp = false;

@@ -1165,7 +1165,7 @@ __device__ __forceinline__ uint8_t log_mul(uint8_t a, uint8_t b) { unsigned r = 
 //   Forney (:165-196) + the location search (:198-222): lane q handles root q. The reference finds the location by scanning j = 0..255
 //     for j^11 == 1/root; that is j = (1/root)^(11^-1 mod 255), i.e. log j = 116 * log(1/root) mod 255 - except that its scan meets
 //     j = 0 first, whose "power" reads exp[0] = 1: for 1/root == 1 the location is log[0] = 0 (checked against the scan for every value).
-__device__ __noinline__ bool rs_correct_warp(const RsTables &T, uint8_t *r, const uint8_t *syn, int nroots, int fcr, uint8_t *lam, uint8_t *prev, uint8_t *lamlog,
+__device__ bool rs_correct_warp(const RsTables &T, uint8_t *r, const uint8_t *syn, int nroots, int fcr, uint8_t *lam, uint8_t *prev, uint8_t *lamlog,
                                 uint8_t *roots, uint8_t *om, uint8_t *der, int lane)
 {
     unsigned order = 0;
@@ -1299,6 +1299,7 @@ __global__ void __launch_bounds__(256) k_frames(const uint32_t *__restrict__ fif
             if (lane < fc.rs_nroots) {
                 const uint8_t rootlog = T.log[T.exp[(11 * (lane + fc.rs_fcr)) % 255]];
                 uint8_t pw = T.log[1];
+#pragma unroll 5
                 for (int i = 0; i < 255; i++) {
                     const uint8_t v = r[i];
                     if (v) s ^= T.exp[T.log[v] + pw];
