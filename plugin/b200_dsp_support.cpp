@@ -73,7 +73,7 @@ namespace b200plugin
         void process() override
         {
             using namespace satdump::pipeline;
-            stage->setInputType(input_data_type == DATA_FILE ? b200host::DataType::FILE : b200host::DataType::STREAM);
+            stage->setInputType(input_data_type == DATA_FILE ? b200host::DataType::FILE : b200host::DataType::STREAM); // (a DSP stream is fed as cf32 bytes)
             stage->setOutputType(output_data_type == DATA_FILE ? b200host::DataType::FILE : b200host::DataType::STREAM);
             std::thread pump_in, pump_out;
             if (input_data_type == DATA_STREAM)
@@ -87,6 +87,25 @@ namespace b200plugin
                         if (input_fifo->read(b.data(), n) < 0)
                             break;
                         if (stage->input_fifo->write(b.data(), n) < 0)
+                            break;
+                    }
+                    stage->input_fifo->stopReader();
+                });
+            }
+            if (input_data_type == DATA_DSP_STREAM)
+            {
+                // dsp::stream<complex_t> (module.h:170; buffer.h:50-107): read() blocks until the writer swapped a buffer in (-1: stopped),
+                // readBuf[0..n) are complex floats, flush() hands the buffer back. The stage sees them as a cf32 byte stream.
+                stage->input_fifo = std::make_shared<b200host::ByteFifo>();
+                pump_in = std::thread([this] {
+                    while (input_active.load())
+                    {
+                        const int n = input_stream->read();
+                        if (n < 0)
+                            break;
+                        const bool ok = n == 0 || stage->input_fifo->write((const uint8_t *)input_stream->readBuf, n * (int)sizeof(complex_t)) >= 0;
+                        input_stream->flush();
+                        if (!ok)
                             break;
                     }
                     stage->input_fifo->stopReader();
@@ -123,6 +142,8 @@ namespace b200plugin
                 }
                 if (input_data_type == DATA_STREAM && input_fifo)
                     input_fifo->stopReader();
+                if (input_data_type == DATA_DSP_STREAM && input_stream)
+                    input_stream->stopReader();
             }
             d_output_file = stage->getOutput();
             if (stage->output_fifo)
@@ -148,6 +169,17 @@ namespace b200plugin
             {
                 throw satdump_exception(e.what());
             }
+        }
+        // BaseDemodModule: inputs {DATA_FILE, DATA_DSP_STREAM} (+ the byte stream this shim also takes), module_demod_base.cpp:210-212
+        std::vector<satdump::pipeline::ModuleDataType> getInputTypes() override
+        {
+            return {satdump::pipeline::DATA_FILE, satdump::pipeline::DATA_DSP_STREAM, satdump::pipeline::DATA_STREAM};
+        }
+        void init() override
+        {
+            if (input_data_type == satdump::pipeline::DATA_DSP_STREAM)
+                stage->cfg.format = B200_CF32; // the DSP stream carries complex floats whatever `baseband_format` says (module_demod_base.cpp:96-103)
+            WrappedModule::init();
         }
         nlohmann::json getModuleStats() override
         {
