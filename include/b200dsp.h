@@ -100,6 +100,8 @@ typedef struct b200_fec_cfg
     int qpsk_swap_iq;         /* simple: "qpsk_swap_iq"   (module_ccsds_simple_psk_decoder.cpp:27)    */
     int qpsk_swap_diff;       /* simple: "qpsk_swap_diff", default true (:28); used with nrzm on QPSK  */
     int oqpsk_delay;          /* simple: "oqpsk_delay" (:29)                                          */
+    int conv_rate;            /* ccsds: "conv_rate" (module_ccsds_conv_concat_decoder.cpp:33,99-117): 0 = "1/2" (Viterbi1_2); 2, 3, 5, 7 = "2/3",
+                                 "3/4", "5/6", "7/8" (Viterbi_Depunc, common/codings/viterbi/viterbi_punc.cpp + depunc.h)           */
 } b200_fec_cfg;
 
 typedef struct b200_demod_stats

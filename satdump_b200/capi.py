@@ -44,7 +44,7 @@ class FecCfg(C.Structure):
                 ("ber_thresold", C.c_float), ("nrzm", C.c_int), ("derandomize", C.c_int), ("derand_after_rs", C.c_int),
                 ("derand_start", C.c_int), ("rs_i", C.c_int), ("rs_dualbasis", C.c_int), ("rs_fill_bytes", C.c_int),
                 ("rs_usecheck", C.c_int), ("rs_type", C.c_int), ("iq_invert", C.c_int), ("asm_sync", C.c_uint),
-                ("device", C.c_int), ("max_soft", C.c_long), ("qpsk_swap_iq", C.c_int), ("qpsk_swap_diff", C.c_int), ("oqpsk_delay", C.c_int)]
+                ("device", C.c_int), ("max_soft", C.c_long), ("qpsk_swap_iq", C.c_int), ("qpsk_swap_diff", C.c_int), ("oqpsk_delay", C.c_int), ("conv_rate", C.c_int)]
 
 
 class DemodStats(C.Structure):
@@ -184,10 +184,10 @@ def simple_cfg(constellation, cadu_size, rs_i, nrzm=False, derandomize=True, rs_
 
 def ccsds_cfg(constellation, cadu_size, ber_thresold, outsync_after, rs_i, nrzm=False, derandomize=True, rs_usecheck=False, rs_dualbasis=True,
               rs_fill_bytes=-1, derand_after_rs=False, derand_start=4, iq_invert=False, rs_type=0, asm_sync=0x1ACFFC1D, device=0,
-              max_soft=1 << 24):
+              max_soft=1 << 24, conv_rate="1/2"):
     return FecCfg(1, CONST[constellation], cadu_size, outsync_after, ber_thresold, int(nrzm), int(derandomize), int(derand_after_rs),
                   derand_start, rs_i, int(rs_dualbasis), rs_fill_bytes, int(rs_usecheck), rs_type, int(iq_invert), asm_sync, device, max_soft,
-                  0, 0, 0)
+                  0, 0, 0, {"1/2": 0, "2/3": 2, "3/4": 3, "5/6": 5, "7/8": 7}[conv_rate])
 
 
 def fec_cfg_for(sig, max_soft, device=0):
@@ -199,7 +199,7 @@ def fec_cfg_for(sig, max_soft, device=0):
         return simple_cfg(sig.constellation, (4 + 255 * sig.interleave) * 8, sig.interleave, nrzm=sig.nrzm, qpsk_swap_iq=sig.constellation == "qpsk",
                           device=device, max_soft=max_soft)
     return ccsds_cfg(sig.constellation, (4 + 255 * sig.interleave) * 8, sig.ber_thresold, sig.outsync_after, sig.interleave, nrzm=sig.nrzm,
-                     rs_usecheck=sig.rs_usecheck, device=device, max_soft=max_soft)
+                     rs_usecheck=sig.rs_usecheck, device=device, max_soft=max_soft, conv_rate=sig.conv[1:] if sig.conv.startswith("p") else "1/2")
 
 
 def demod_cfg_for(sig, max_batch, device=0, **kw):

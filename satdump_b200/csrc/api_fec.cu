@@ -96,6 +96,19 @@ Fec::Fec(const b200_fec_cfg &c) : cfg(c)
         geom.chunk = std::max(c.cadu_size, 8192);
         B200_REQUIRE(geom.chunk % 2 == 0, B200_EINVAL, "chunk size must be even");
         geom.F = geom.chunk / 2;
+        B200_REQUIRE(c.conv_rate == 0 || c.conv_rate == 2 || c.conv_rate == 3 || c.conv_rate == 5 || c.conv_rate == 7, B200_EINVAL,
+                     "conv_rate must be 0 (1/2), 2 (2/3), 3 (3/4), 5 (5/6) or 7 (7/8)");
+        if (c.conv_rate) {
+            // Viterbi_Depunc(depunc, ber, outsync, buffer_size, phases, oqpsk) (module_ccsds_conv_concat_decoder.cpp:108-117): one module call =
+            // buffer_size soft symbols; the decoder works on windows of vit_bufsize = buffer_size DEPUNCTURED symbols (frame buffer_size / 2 bits)
+            punc = true;
+            geom.raw = 1;
+            static const PuncTab tabs[4] = {{3, 4, 3.5f, {1, 2, 1}, {0, 0, 0}, {0, 1, 3, 4}},                                       // depunc.h: Depunc23
+                                            {4, 6, 5.0f, {1, 2, 1, 2}, {0, 0, 0, 0}, {0, 1, 3, 4, 6}},                                // Depunc34
+                                            {6, 10, 8.0f, {1, 2, 1, 2, 2, 2}, {0, 0, 0, 0, 1, 0}, {0, 1, 3, 4, 6, 8, 10}},             // Depunc56
+                                            {8, 14, 10.0f, {1, 2, 2, 2, 1, 2, 2, 2}, {0, 0, 0, 0, 0, 0, 1, 0}, {0, 1, 3, 5, 7, 8, 10, 12, 14}}}; // Depunc78
+            ptab = tabs[c.conv_rate == 2 ? 0 : (c.conv_rate == 3 ? 1 : (c.conv_rate == 5 ? 2 : 3))];
+        }
         if (c.constellation == B200_BPSK) { nphases = 1; ph0 = 0; ph1 = 0; }
         else if (c.constellation == B200_BPSK_90) { nphases = 1; ph0 = 1; ph1 = 1; }
         else if (c.constellation == B200_QPSK || c.constellation == B200_OQPSK) { nphases = 2; ph0 = 0; ph1 = 1; }
@@ -119,6 +132,16 @@ Fec::Fec(const b200_fec_cfg &c) : cfg(c)
     for (auto &e : evf)
         B200_CUDA(cudaEventCreate(&e));
     max_chunks = c.max_soft / geom.chunk + 2;
+    if (punc) { // windows per push: the calls' symbols times Q / P, plus the leftover of the push before
+        const long max_sym = (c.max_soft / geom.chunk + 2) * (long)geom.chunk * ptab.Q / ptab.P + 2L * geom.chunk + 64;
+        max_chunks = max_sym / geom.chunk + 2;
+        vitbuf.alloc((size_t)max_sym + geom.chunk + 64);
+        vitbuf_tmp.alloc((size_t)2 * geom.chunk + 64);
+        bdep.alloc(4 * VIT_TESTLEN);
+        tail_real.alloc(max_chunks + 2);
+        punc_out.alloc(1);
+        B200_CUDA(cudaMallocHost((void **)&h_punc, sizeof(PuncIdleOut)));
+    }
     softbuf.alloc((size_t)c.max_soft + 2 * geom.chunk);
     const bool simple = cfg.kind == B200_FEC_SIMPLE;
     dec.alloc(simple ? (size_t)(c.max_soft / 8 + geom.chunk) : (size_t)max_chunks * geom.dec_stride); // simple: only scratch for the tail move
@@ -164,6 +187,10 @@ Fec::Fec(const b200_fec_cfg &c) : cfg(c)
     B200_CUDA(cudaMemcpyAsync(tables.p, &T, sizeof(T), cudaMemcpyHostToDevice, stream));
     fifo.zero(stream);
     rec.zero(stream);
+    if (punc) {
+        bdep.zero(stream);   // (the reference's member array: zero-initialised by the harness; never cleared afterwards)
+        vitbuf.zero(stream);
+    }
     h_dstate[0].state = 2;
     h_dstate[0].inversion = h_dstate[0].good = h_dstate[0].bad = 0;
     h_dstate[0].pos = 32; // the FIFO starts with 32 zero bits = the deframer's empty shifter
@@ -191,7 +218,7 @@ Fec::~Fec()
         cudaEventDestroy(e);
     for (auto &e : evf)
         cudaEventDestroy(e);
-    for (void *p : {(void *)h_idle2, (void *)h_rec, (void *)h_idle, (void *)h_counters, (void *)h_dstate, (void *)h_events, (void *)h_rs_err})
+    for (void *p : {(void *)h_idle2, (void *)h_rec, (void *)h_idle, (void *)h_counters, (void *)h_dstate, (void *)h_events, (void *)h_rs_err, (void *)h_punc})
         if (p)
             cudaFreeHost(p);
     if (stream)
@@ -218,6 +245,111 @@ void Fec::push_device(const int8_t *d, long n)
 constexpr int ACS_DEC_MODE = 0; // decision store of k_vit_acs3: lane 0 writes each step's two ballot words to a shared-memory row (measured fastest: tests/tools/bench_acs.cu)
 
 struct OutChunk { long soft_chunk; int next_start, enc_tail, invalid_after, state_after; VitIdleState idle_st; };
+
+// Optimistic parallel decode of n consecutive decoder windows (chunks c .. c+n-1 of `src`, f.geom.chunk bytes apart) into chunk_bits[out_base ..]:
+// start-state speculation, ACS, parallel chainback (+ checks and serial fallback), BER counters, and the redo rounds for chunks whose
+// speculated start state was wrong. Leaves the per-chunk records in f.h_rec[0 .. n).
+static void decode_range(Fec &f, const int8_t *src, long c, int n, long out_base)
+{
+    B200_CUDA(cudaMemcpyAsync(f.start_state.p, &f.main_next_start, sizeof(int), cudaMemcpyHostToDevice, f.stream));
+    const int wpb = 4, nb_main = (n + wpb - 1) / wpb;
+    if (n > 1) {
+        k_vit_spec<<<(n - 1 + wpb - 1) / wpb, 32 * wpb, 0, f.stream>>>(src, c, n, f.geom, f.hyp, f.spec_steps, f.start_state.p);
+        f.launches++;
+    }
+    B200_CUDA(cudaEventRecord(f.evm[0], f.stream));
+    k_vit_acs3<true, ACS_DEC_MODE><<<nb_main, 32 * wpb, 0, f.stream>>>(src, c, n, f.geom, f.hyp, f.start_state.p, f.dec.p, f.rec.p, nullptr);
+    B200_CUDA(cudaEventRecord(f.evm[1], f.stream));
+    {
+        const long nthr = (long)n * f.tb_blocks;
+        B200_CUDA(cudaMemsetAsync(f.tb_list.p, 0, sizeof(int), f.stream));
+        k_vit_tb<<<(unsigned)((nthr + 127) / 128), 128, 0, f.stream>>>(n, f.tb_blocks, f.geom, f.dec.p, f.chunk_bits.p, out_base, f.rec.p, f.tb_edges.p, nullptr, f.tb_overlap);
+        k_vit_tb_check<<<(n + 255) / 256, 256, 0, f.stream>>>(n, f.tb_blocks, f.tb_edges.p, f.tb_list.p, n, nullptr);
+        k_vit_tb_serial<<<(n + 127) / 128, 128, 0, f.stream>>>(f.tb_list.p, n, f.geom, f.dec.p, f.chunk_bits.p, out_base, f.rec.p); // (threads beyond the list return at once)
+        f.launches += 3;
+    }
+    k_vit_ber<<<nb_main, 32 * wpb, 0, f.stream>>>(src, c, n, f.geom, f.hyp, f.chunk_bits.p, out_base, f.enc_state, f.rec.p, nullptr);
+    f.launches += 2;
+    B200_CUDA(cudaMemcpyAsync(f.h_rec, f.rec.p, sizeof(VitRec) * n, cudaMemcpyDeviceToHost, f.stream));
+    int tb_redone = 0;
+    B200_CUDA(cudaMemcpyAsync(&tb_redone, f.tb_list.p, sizeof(int), cudaMemcpyDeviceToHost, f.stream));
+    B200_CUDA(cudaStreamSynchronize(f.stream));
+    f.tb_serial_total += tb_redone;
+    if (n > 64) { // the chainback warm-up follows the channel like the speculation window does
+        const double frac = (double)tb_redone / (double)n;
+        if (frac > 0.02) {
+            f.tb_overlap = std::min(TB_OVERLAP_MAX, f.tb_overlap * 2);
+            f.tb_clean = 0;
+        } else if (frac < 0.002 && ++f.tb_clean >= 32) { // (slowly back: one doubling squares the miss probability, so the
+            f.tb_overlap = std::max(TB_OVERLAP, f.tb_overlap / 2); //  shorter window would fail again at once on the same channel)
+            f.tb_clean = 0;
+        }
+    }
+    {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, f.evm[0], f.evm[1]);
+        f.t_vit_main += ms;
+        f.last_main_chunks += n;
+    }
+    // Start states that were speculated wrong (k_vit_spec: common at low SNR, where 768 steps do not always pin the state): those
+    // chunks alone are decoded again from the state their predecessor really left. A chunk's end state almost never depends on its
+    // start state, so one round normally settles it; a round that changes a successor's start state is followed by another.
+    for (int round = 0; round < 6; round++) {
+        f.h_redo.clear();
+        for (int i = 1; i < n; i++)
+            if (f.h_rec[i].start_used != f.h_rec[i - 1].next_start) {
+                f.h_redo.push_back(i);
+                f.h_start[i] = f.h_rec[i - 1].next_start;
+            }
+        if (round == 0 && n > 64) {
+            // the speculation window follows the channel: many wrong guesses (low SNR: the survivors of 768 steps have not all
+            // merged) -> twice the window for the next launch; almost none -> back towards the default
+            const double frac = (double)f.h_redo.size() / (double)n;
+            const int base = f.geom.rate34 ? VIT_SPEC_STEPS_34 : VIT_SPEC_STEPS_12, top = (f.geom.F / 32) * 32;
+            if (frac > 0.02) {
+                f.spec_steps = std::min(top, f.spec_steps * 2);
+                f.spec_clean = 0;
+            } else if (frac < 0.002 && ++f.spec_clean >= 32) {
+                f.spec_steps = std::max(base, f.spec_steps / 2);
+                f.spec_clean = 0;
+            }
+        }
+        if (f.h_redo.empty())
+            break;
+        const int m = (int)f.h_redo.size();
+        f.replays += m;
+        f.start_redone += m;
+        // the BER check of a chunk reads the last test bits of its predecessor: redo it for the successors too
+        f.h_redo_ber = f.h_redo;
+        for (int i : f.h_redo)
+            if (i + 1 < n)
+                f.h_redo_ber.push_back(i + 1);
+        std::sort(f.h_redo_ber.begin(), f.h_redo_ber.end());
+        f.h_redo_ber.erase(std::unique(f.h_redo_ber.begin(), f.h_redo_ber.end()), f.h_redo_ber.end());
+        const int mb = (int)f.h_redo_ber.size();
+        for (int i : f.h_redo)
+            B200_CUDA(cudaMemcpyAsync(f.start_state.p + i, &f.h_start[i], sizeof(int), cudaMemcpyHostToDevice, f.stream));
+        B200_CUDA(cudaMemcpyAsync(f.redo_list.p, f.h_redo.data(), sizeof(int) * m, cudaMemcpyHostToDevice, f.stream));
+        B200_CUDA(cudaMemcpyAsync(f.redo_list.p + n, f.h_redo_ber.data(), sizeof(int) * mb, cudaMemcpyHostToDevice, f.stream));
+        B200_CUDA(cudaEventRecord(f.evm[0], f.stream));
+        k_vit_acs3<true, ACS_DEC_MODE><<<(m + wpb - 1) / wpb, 32 * wpb, 0, f.stream>>>(src, c, m, f.geom, f.hyp, f.start_state.p, f.dec.p, f.rec.p, f.redo_list.p);
+        B200_CUDA(cudaEventRecord(f.evm[1], f.stream));
+        const long nthr = (long)m * f.tb_blocks;
+        B200_CUDA(cudaMemsetAsync(f.tb_list.p, 0, sizeof(int), f.stream));
+        k_vit_tb<<<(unsigned)((nthr + 127) / 128), 128, 0, f.stream>>>(m, f.tb_blocks, f.geom, f.dec.p, f.chunk_bits.p, out_base, f.rec.p, f.tb_edges.p, f.redo_list.p, f.tb_overlap);
+        k_vit_tb_check<<<(m + 255) / 256, 256, 0, f.stream>>>(m, f.tb_blocks, f.tb_edges.p, f.tb_list.p, n, f.redo_list.p);
+        k_vit_tb_serial<<<(m + 127) / 128, 128, 0, f.stream>>>(f.tb_list.p, n, f.geom, f.dec.p, f.chunk_bits.p, out_base, f.rec.p);
+        k_vit_ber<<<(mb + wpb - 1) / wpb, 32 * wpb, 0, f.stream>>>(src, c, mb, f.geom, f.hyp, f.chunk_bits.p, out_base, f.enc_state, f.rec.p, f.redo_list.p + n);
+        f.launches += 5;
+        B200_CUDA(cudaMemcpyAsync(f.h_rec, f.rec.p, sizeof(VitRec) * n, cudaMemcpyDeviceToHost, f.stream));
+        B200_CUDA(cudaMemcpyAsync(&tb_redone, f.tb_list.p, sizeof(int), cudaMemcpyDeviceToHost, f.stream));
+        B200_CUDA(cudaStreamSynchronize(f.stream));
+        f.tb_serial_total += tb_redone;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, f.evm[0], f.evm[1]);
+        f.t_vit_main += ms;
+    }
+}
 
 // Viterbi over soft chunks [c0, nch): lock search while IDLE, optimistic parallel decode while SYNCED. Decoded chunks land in
 // chunk_bits[0 .. nout). Returns per-output-chunk bookkeeping in `outs`.
@@ -266,104 +398,7 @@ static void viterbi_segment(Fec &f, long c0, long nch, std::vector<OutChunk> &ou
             f.enc_state = f.idle_st.enc_state;
         }
         const int n = (int)(nch - c);
-        B200_CUDA(cudaMemcpyAsync(f.start_state.p, &f.main_next_start, sizeof(int), cudaMemcpyHostToDevice, f.stream));
-        const int wpb = 4, nb_main = (n + wpb - 1) / wpb;
-        if (n > 1) {
-            k_vit_spec<<<(n - 1 + wpb - 1) / wpb, 32 * wpb, 0, f.stream>>>(f.softbuf.p, c, n, f.geom, f.hyp, f.spec_steps, f.start_state.p);
-            f.launches++;
-        }
-        B200_CUDA(cudaEventRecord(f.evm[0], f.stream));
-        k_vit_acs3<true, ACS_DEC_MODE><<<nb_main, 32 * wpb, 0, f.stream>>>(f.softbuf.p, c, n, f.geom, f.hyp, f.start_state.p, f.dec.p, f.rec.p, nullptr);
-        B200_CUDA(cudaEventRecord(f.evm[1], f.stream));
-        {
-            const long nthr = (long)n * f.tb_blocks;
-            B200_CUDA(cudaMemsetAsync(f.tb_list.p, 0, sizeof(int), f.stream));
-            k_vit_tb<<<(unsigned)((nthr + 127) / 128), 128, 0, f.stream>>>(n, f.tb_blocks, f.geom, f.dec.p, f.chunk_bits.p, out_base, f.rec.p, f.tb_edges.p, nullptr, f.tb_overlap);
-            k_vit_tb_check<<<(n + 255) / 256, 256, 0, f.stream>>>(n, f.tb_blocks, f.tb_edges.p, f.tb_list.p, n, nullptr);
-            k_vit_tb_serial<<<(n + 127) / 128, 128, 0, f.stream>>>(f.tb_list.p, n, f.geom, f.dec.p, f.chunk_bits.p, out_base, f.rec.p); // (threads beyond the list return at once)
-            f.launches += 3;
-        }
-        k_vit_ber<<<nb_main, 32 * wpb, 0, f.stream>>>(f.softbuf.p, c, n, f.geom, f.hyp, f.chunk_bits.p, out_base, f.enc_state, f.rec.p, nullptr);
-        f.launches += 2;
-        B200_CUDA(cudaMemcpyAsync(f.h_rec, f.rec.p, sizeof(VitRec) * n, cudaMemcpyDeviceToHost, f.stream));
-        int tb_redone = 0;
-        B200_CUDA(cudaMemcpyAsync(&tb_redone, f.tb_list.p, sizeof(int), cudaMemcpyDeviceToHost, f.stream));
-        B200_CUDA(cudaStreamSynchronize(f.stream));
-        f.tb_serial_total += tb_redone;
-        if (n > 64) { // the chainback warm-up follows the channel like the speculation window does
-            const double frac = (double)tb_redone / (double)n;
-            if (frac > 0.02) {
-                f.tb_overlap = std::min(TB_OVERLAP_MAX, f.tb_overlap * 2);
-                f.tb_clean = 0;
-            } else if (frac < 0.002 && ++f.tb_clean >= 32) { // (slowly back: one doubling squares the miss probability, so the
-                f.tb_overlap = std::max(TB_OVERLAP, f.tb_overlap / 2); //  shorter window would fail again at once on the same channel)
-                f.tb_clean = 0;
-            }
-        }
-        {
-            float ms = 0;
-            cudaEventElapsedTime(&ms, f.evm[0], f.evm[1]);
-            f.t_vit_main += ms;
-            f.last_main_chunks += n;
-        }
-        // Start states that were speculated wrong (k_vit_spec: common at low SNR, where 768 steps do not always pin the state): those
-        // chunks alone are decoded again from the state their predecessor really left. A chunk's end state almost never depends on its
-        // start state, so one round normally settles it; a round that changes a successor's start state is followed by another.
-        for (int round = 0; round < 6; round++) {
-            f.h_redo.clear();
-            for (int i = 1; i < n; i++)
-                if (f.h_rec[i].start_used != f.h_rec[i - 1].next_start) {
-                    f.h_redo.push_back(i);
-                    f.h_start[i] = f.h_rec[i - 1].next_start;
-                }
-            if (round == 0 && n > 64) {
-                // the speculation window follows the channel: many wrong guesses (low SNR: the survivors of 768 steps have not all
-                // merged) -> twice the window for the next launch; almost none -> back towards the default
-                const double frac = (double)f.h_redo.size() / (double)n;
-                const int base = f.geom.rate34 ? VIT_SPEC_STEPS_34 : VIT_SPEC_STEPS_12, top = (f.geom.F / 32) * 32;
-                if (frac > 0.02) {
-                    f.spec_steps = std::min(top, f.spec_steps * 2);
-                    f.spec_clean = 0;
-                } else if (frac < 0.002 && ++f.spec_clean >= 32) {
-                    f.spec_steps = std::max(base, f.spec_steps / 2);
-                    f.spec_clean = 0;
-                }
-            }
-            if (f.h_redo.empty())
-                break;
-            const int m = (int)f.h_redo.size();
-            f.replays += m;
-            f.start_redone += m;
-            // the BER check of a chunk reads the last test bits of its predecessor: redo it for the successors too
-            f.h_redo_ber = f.h_redo;
-            for (int i : f.h_redo)
-                if (i + 1 < n)
-                    f.h_redo_ber.push_back(i + 1);
-            std::sort(f.h_redo_ber.begin(), f.h_redo_ber.end());
-            f.h_redo_ber.erase(std::unique(f.h_redo_ber.begin(), f.h_redo_ber.end()), f.h_redo_ber.end());
-            const int mb = (int)f.h_redo_ber.size();
-            for (int i : f.h_redo)
-                B200_CUDA(cudaMemcpyAsync(f.start_state.p + i, &f.h_start[i], sizeof(int), cudaMemcpyHostToDevice, f.stream));
-            B200_CUDA(cudaMemcpyAsync(f.redo_list.p, f.h_redo.data(), sizeof(int) * m, cudaMemcpyHostToDevice, f.stream));
-            B200_CUDA(cudaMemcpyAsync(f.redo_list.p + n, f.h_redo_ber.data(), sizeof(int) * mb, cudaMemcpyHostToDevice, f.stream));
-            B200_CUDA(cudaEventRecord(f.evm[0], f.stream));
-            k_vit_acs3<true, ACS_DEC_MODE><<<(m + wpb - 1) / wpb, 32 * wpb, 0, f.stream>>>(f.softbuf.p, c, m, f.geom, f.hyp, f.start_state.p, f.dec.p, f.rec.p, f.redo_list.p);
-            B200_CUDA(cudaEventRecord(f.evm[1], f.stream));
-            const long nthr = (long)m * f.tb_blocks;
-            B200_CUDA(cudaMemsetAsync(f.tb_list.p, 0, sizeof(int), f.stream));
-            k_vit_tb<<<(unsigned)((nthr + 127) / 128), 128, 0, f.stream>>>(m, f.tb_blocks, f.geom, f.dec.p, f.chunk_bits.p, out_base, f.rec.p, f.tb_edges.p, f.redo_list.p, f.tb_overlap);
-            k_vit_tb_check<<<(m + 255) / 256, 256, 0, f.stream>>>(m, f.tb_blocks, f.tb_edges.p, f.tb_list.p, n, f.redo_list.p);
-            k_vit_tb_serial<<<(m + 127) / 128, 128, 0, f.stream>>>(f.tb_list.p, n, f.geom, f.dec.p, f.chunk_bits.p, out_base, f.rec.p);
-            k_vit_ber<<<(mb + wpb - 1) / wpb, 32 * wpb, 0, f.stream>>>(f.softbuf.p, c, mb, f.geom, f.hyp, f.chunk_bits.p, out_base, f.enc_state, f.rec.p, f.redo_list.p + n);
-            f.launches += 5;
-            B200_CUDA(cudaMemcpyAsync(f.h_rec, f.rec.p, sizeof(VitRec) * n, cudaMemcpyDeviceToHost, f.stream));
-            B200_CUDA(cudaMemcpyAsync(&tb_redone, f.tb_list.p, sizeof(int), cudaMemcpyDeviceToHost, f.stream));
-            B200_CUDA(cudaStreamSynchronize(f.stream));
-            f.tb_serial_total += tb_redone;
-            float ms = 0;
-            cudaEventElapsedTime(&ms, f.evm[0], f.evm[1]);
-            f.t_vit_main += ms;
-        }
+        decode_range(f, f.softbuf.p, c, n, out_base);
         int accepted = 0;
         for (int i = 0; i < n; i++) {
             if (i > 0 && f.h_rec[i].start_used != f.h_rec[i - 1].next_start) {
@@ -393,6 +428,123 @@ static void viterbi_segment(Fec &f, long c0, long nch, std::vector<OutChunk> &ou
         f.enc_state = f.h_rec[accepted - 1].enc_tail;
         out_base += accepted;
         c += accepted;
+    }
+}
+
+// ccsds_conv_concat_decoder with conv_rate 2/3 ... 7/8: Viterbi_Depunc::work (viterbi_punc.cpp:53-145) over the module calls [c0, ncalls) of
+// the soft FIFO (one call = geom.chunk soft symbols). IDLE: lock search call by call (k_punc_idle). SYNCED: all remaining calls at once -
+//   * DepuncXX::depunc_cont of the whole run in closed form into the symbol stream behind the leftover of earlier calls (k_punc_depunc);
+//   * ViterbiSlidingBuffer: window w = symbols [w V, w V + V + 12) of that stream is decoded in the first call j whose even-truncated
+//     running total T_j exceeds (w + 1) V; what it reads beyond T_j are erasures (the buffer's memset after the previous window; the
+//     first window of a call always has its 12 tail symbols, a call makes more than V + 12 symbols at every rate);
+//   * the windows go through the same speculative-start ACS / chainback / BER kernels as the fixed-rate decoders (decode_range);
+//   * the lock machine is replayed per call on the host: d_ber = BER of the last window decoded in the call.
+static void punc_segment(Fec &f, long c0, long ncalls, std::vector<OutChunk> &outs)
+{
+    outs.clear();
+    const int V = f.geom.chunk, size = f.geom.chunk;
+    const PuncTab &P = f.ptab;
+    auto made = [&](long m) { return (m / P.P) * (long)P.Q + P.cum[m % P.P]; };
+    long c = c0, out_base = 0;
+    while (c < ncalls) {
+        if (f.vit_state == 0) {
+            const VitIdleState st{f.pdec_start, f.enc_state};
+            k_punc_idle<<<1, 32, 0, f.stream>>>(f.softbuf.p, c, (int)(ncalls - c), size, P, f.nswap, f.nphases, f.ph0, f.ph1, f.cfg.ber_thresold, st, f.bdep.p,
+                                                f.idle_dec.p, f.punc_out.p);
+            f.launches++;
+            B200_CUDA(cudaMemcpyAsync(f.h_punc, f.punc_out.p, sizeof(PuncIdleOut), cudaMemcpyDeviceToHost, f.stream));
+            B200_CUDA(cudaStreamSynchronize(f.stream));
+            const PuncIdleOut &o = *f.h_punc;
+            f.pdec_start = o.st.dec_start;
+            f.enc_state = o.st.enc_state;
+            f.test_bit_len = o.test_bit_len;
+            f.last_ber = o.ber;
+            if (o.lock_call < 0)
+                break;
+            c += o.lock_call;
+            f.vit_state = 1;
+            f.hyp = VitHyp{o.swap, o.phase, 0};
+            f.invalid = 0;
+            f.changing_shift = o.shift; // set_shift (depunc.h)
+            f.is_first = o.shift > P.P - 1;
+        }
+        const int n = (int)(ncalls - c);
+        // depunc_cont of calls c .. c+n-1. A symbol held back by the previous call (got_extra) already sits at vitbuf[in_buffer].
+        const int held = f.got_extra ? 1 : 0;
+        const int lead = (!f.got_extra && f.is_first) ? 1 : 0; // `buf` emitted in front (its stale value when nothing is held)
+        f.is_first = false;
+        const int a0 = f.changing_shift % P.P;
+        const long nsoft = (long)n * size;
+        B200_REQUIRE((size_t)(f.in_buffer + held + lead + made(a0 + nsoft) - made(a0) + 16) <= f.vitbuf.n, B200_ESTATE, "internal: depunctured stream buffer too small");
+        k_punc_depunc<<<(unsigned)((nsoft + 255) / 256), 256, 0, f.stream>>>(f.softbuf.p + c * (long)size, nsoft, f.hyp, P, a0, lead, f.buf_value,
+                                                                            f.vitbuf.p + f.in_buffer + held);
+        f.launches++;
+        // which call decodes which window, and how much of its 12-symbol tail exists by then
+        f.h_tail.clear();
+        f.h_wcall.clear();
+        long w = 0;
+        for (int j = 1; j <= n; j++) {
+            const long raw = held + lead + made(a0 + (long)j * size) - made(a0);
+            const long T = f.in_buffer + 2 * (raw / 2);
+            while (T - w * V > V) {
+                f.h_wcall.push_back(j);
+                f.h_tail.push_back((int)std::min<long>(12, T - (w + 1) * V));
+                w++;
+            }
+        }
+        const int nw = (int)w;
+        B200_REQUIRE(nw >= 1 && nw <= f.max_chunks, B200_ESTATE, "internal: window count %d out of range", nw);
+        B200_CUDA(cudaMemcpyAsync(f.tail_real.p, f.h_tail.data(), sizeof(int) * nw, cudaMemcpyHostToDevice, f.stream));
+        f.geom.tail_real = f.tail_real.p;
+        f.geom.ber_bits = VIT_TESTLEN;      // cc_encoder_ber.work(output, ...) encodes TEST_BITS_LENGTH bits (viterbi_punc.cpp:124)
+        f.geom.ber_syms = f.test_bit_len;   // get_ber(vit_buffer, ..., test_bit_len, 5) (:125)
+        decode_range(f, reinterpret_cast<const int8_t *>(f.vitbuf.p), 0, nw, out_base);
+        // replay the lock machine call by call
+        int jacc = n, wacc = nw;
+        for (int j = 1, wi = 0; j <= n; j++) {
+            int last = -1;
+            while (wi < nw && f.h_wcall[wi] == j)
+                last = wi++;
+            if (last >= 0)
+                f.last_ber = ((float)f.h_rec[last].ber_errors / (float)f.h_rec[last].ber_total) * 5.0f;
+            if (f.last_ber > f.cfg.ber_thresold) { // viterbi_punc.cpp:133-141
+                f.invalid++;
+                if (f.invalid > f.cfg.outsync_after) {
+                    f.vit_state = 0;
+                    jacc = j;
+                    wacc = wi;
+                    break;
+                }
+            } else
+                f.invalid = 0;
+        }
+        for (int i = 0; i < wacc; i++)
+            outs.push_back(OutChunk{c + f.h_wcall[i] - 1, f.h_rec[i].next_start, f.h_rec[i].enc_tail, f.invalid, f.vit_state, f.idle_st});
+        if (wacc > 0) {
+            f.main_next_start = f.h_rec[wacc - 1].next_start;
+            f.enc_state = f.h_rec[wacc - 1].enc_tail;
+        }
+        // what stays in the sliding buffer: the symbols behind the decoded windows up to the last accepted call's total, plus the one
+        // that call held back (its value is DepuncXX::buf from now on)
+        const long raw = held + lead + made(a0 + (long)jacc * size) - made(a0);
+        const long T = f.in_buffer + 2 * (raw / 2);
+        f.got_extra = raw & 1;
+        f.changing_shift = (int)((a0 + (long)jacc * size) % P.P);
+        const long keep0 = (long)wacc * V, keep = T - keep0 + (f.got_extra ? 1 : 0);
+        B200_REQUIRE(keep >= 0 && (size_t)keep <= f.vitbuf_tmp.n, B200_ESTATE, "internal: sliding buffer leftover %ld", keep);
+        if (f.got_extra) {
+            unsigned char hb = 0;
+            B200_CUDA(cudaMemcpyAsync(&hb, f.vitbuf.p + T, 1, cudaMemcpyDeviceToHost, f.stream));
+            B200_CUDA(cudaStreamSynchronize(f.stream));
+            f.buf_value = hb;
+        }
+        if (keep > 0 && keep0 > 0) {
+            B200_CUDA(cudaMemcpyAsync(f.vitbuf_tmp.p, f.vitbuf.p + keep0, keep, cudaMemcpyDeviceToDevice, f.stream));
+            B200_CUDA(cudaMemcpyAsync(f.vitbuf.p, f.vitbuf_tmp.p, keep, cudaMemcpyDeviceToDevice, f.stream));
+        }
+        f.in_buffer = T - keep0;
+        out_base += wacc;
+        c += jacc;
     }
 }
 
@@ -469,6 +621,11 @@ void Fec::reset()
     soft_have = 0;
     fifo_bits = 32;
     vit_state = 0; invalid = 0; main_next_start = -1; enc_state = 0; nrzm_last = 0; nosync_runs = 0;
+    in_buffer = 0; changing_shift = 0; is_first = got_extra = false; buf_value = 128; test_bit_len = 0; pdec_start = -1;
+    if (punc) {
+        B200_CUDA(cudaMemsetAsync(bdep.p, 0, bdep.n, stream));
+        B200_CUDA(cudaMemsetAsync(vitbuf.p, 0, vitbuf.n, stream));
+    }
     hyp = VitHyp{0, 0, 0};
     idle_st = VitIdleState{-1, 0};
     last_ber = 10.f;
@@ -679,7 +836,10 @@ void Fec::process()
         const long fifo_bits0 = fifo_bits, out_frames0 = out_frames, total_frames0 = total_frames, rs_c0 = rs_corrected, rs_f0 = rs_failed;
         const int nosync0 = nosync_runs;
         const long seg_end = nch;
-        viterbi_segment(*this, c, seg_end, outs);
+        if (punc)
+            punc_segment(*this, c, seg_end, outs);
+        else
+            viterbi_segment(*this, c, seg_end, outs);
         const long nout = (long)outs.size();
         long next_c = seg_end;
         if (nout > 0) {

@@ -35,6 +35,22 @@ struct VitGeom
     int F;        // decoded bits per chunk
     int dec_stride; // decision rows per chunk (F + 6 rounded up to 8)
     int bit_words;  // 32-bit words per chunk in the raw bit store
+    // Viterbi_Depunc (viterbi_punc.cpp): the decoder windows read an already depunctured uint8 symbol stream (raw = 1; `chunk` symbols
+    // per window, window q's symbols beyond chunk + tail_real[q] read as erasures), and the BER check re-encodes ber_bits bits and compares
+    // ber_syms symbols (0: the defaults of the fixed-rate decoders)
+    int raw;
+    int ber_bits, ber_syms;
+    const int *tail_real;
+};
+
+// Puncturing patterns of depunc.h as tables: input position ph of the period makes nout[ph] symbols, the data symbol at datapos[ph] of them
+// (the other one is the erasure 128); cum[ph] = symbols made by positions 0..ph-1, cum[P] = Q symbols per period.
+struct VitIdleState { int dec_start; /* -1 unbiased */ int enc_state; };
+struct PuncTab
+{
+    int P, Q;
+    float berscale;
+    unsigned char nout[8], datapos[8], cum[9];
 };
 
 struct VitHyp { int swap, phase, shift; };
@@ -66,6 +82,13 @@ __device__ __forceinline__ int soft_u8(const int8_t *__restrict__ c, int k, cons
 __device__ __forceinline__ int vit_symbols(const int8_t *__restrict__ c, int t, const VitGeom g, const VitHyp h, int nsoft, int tail_fill)
 {
     int s0, s1;
+    if (g.raw) { // depunctured uint8 stream
+        const unsigned char *u = reinterpret_cast<const unsigned char *>(c);
+        const int k0 = 2 * t;
+        s0 = k0 < nsoft ? u[k0] : tail_fill;
+        s1 = k0 + 1 < nsoft ? u[k0 + 1] : tail_fill;
+        return s0 | (s1 << 8);
+    }
     if (g.rate34) {
         const int grp = t / 3, r = t - 3 * grp, b = 4 * grp;
         if (b + 3 >= nsoft) return tail_fill | (tail_fill << 8);
@@ -198,10 +221,11 @@ __global__ void __launch_bounds__(128) k_vit_spec(const int8_t *__restrict__ sof
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (w >= nchunks - 1) return;
     const int8_t *c = soft + (chunk0 + w) * (long)g.chunk; // chunk w predicts the start of chunk w+1
+    const int nlim = g.raw ? g.chunk + g.tail_real[w] : g.chunk;
     const Acs2Lane L = acs2_lane_consts(lane);
     unsigned xl2 = 0, xh2 = 0, D0 = 0, D1 = 0;
     for (int t0 = g.F - spec; t0 < g.F; t0 += 32) { // spec is a multiple of 32
-        const unsigned mine = metric_table(vit_symbols(c, t0 + lane, g, h, g.chunk, 128));
+        const unsigned mine = metric_table(vit_symbols(c, t0 + lane, g, h, nlim, 128));
 #pragma unroll 8
         for (int j = 0; j < 32; j++)
             acs2_step(__shfl_sync(0xffffffffu, mine, j), L, lane, xl2, xh2, D0, D1);
@@ -210,7 +234,8 @@ __global__ void __launch_bounds__(128) k_vit_spec(const int8_t *__restrict__ sof
     const unsigned wt = metric_table(128 | (128 << 8)); // the six flush steps read erasures (d_veclen = frame + k - 1)
 #pragma unroll
     for (int k = 0; k < 6; k++) {
-        acs2_step(wt, L, lane, xl2, xh2, D0, D1);
+        // (a depunctured window's flush steps read the next window's first symbols, or erasures where the stream ended)
+        acs2_step(g.raw ? metric_table(vit_symbols(c, g.F + k, g, h, nlim, 128)) : wt, L, lane, xl2, xh2, D0, D1);
         d0h[k] = D0;
         d1h[k] = D1;
     }
@@ -362,12 +387,13 @@ __global__ void __launch_bounds__(128) k_vit_acs3(const int8_t *__restrict__ sof
     unsigned xl2, xh2, D0, D1;
     acs3_init(ss, lane, xl2, xh2);
     const int steps = g.F + 6;
+    const int nlim = g.raw ? g.chunk + g.tail_real[q] : g.chunk;
     int par = 0;
-    unsigned next = lane < steps ? metric_table(vit_symbols(c, lane, g, h, g.chunk, 128)) : 0u;
+    unsigned next = lane < steps ? metric_table(vit_symbols(c, lane, g, h, nlim, 128)) : 0u;
     for (int t0 = 0; t0 < steps; t0 += 32, par ^= 1) {
         const unsigned mine = next;
         const int tn = t0 + 32 + lane;
-        next = tn < steps ? metric_table(vit_symbols(c, tn, g, h, g.chunk, 128)) : 0u; // consumed one batch later
+        next = tn < steps ? metric_table(vit_symbols(c, tn, g, h, nlim, 128)) : 0u; // consumed one batch later
         uint2 *row = srow[wib][par];
         unsigned k0 = 0, k1 = 0;
         if (t0 + 32 <= steps) {
@@ -547,7 +573,9 @@ __global__ void __launch_bounds__(128) k_vit_ber(const int8_t *__restrict__ soft
     const int q = qlist ? qlist[ql] : ql;
     const int8_t *c = soft + (chunk0 + q) * (long)g.chunk;
     const uint32_t *ob = bits + (out_chunk0 + q) * (long)g.bit_words;
-    const int tb = g.rate34 ? VIT_TESTLEN * 3 / 4 : VIT_TESTLEN / 2;
+    const int tb = g.ber_bits ? g.ber_bits : (g.rate34 ? VIT_TESTLEN * 3 / 4 : VIT_TESTLEN / 2); // bits re-encoded (the encoder register chains on)
+    const int ns = g.ber_syms ? g.ber_syms : 2 * tb;                                            // symbols compared
+    const int nlim = g.raw ? g.chunk + g.tail_real[q] : g.chunk;
     auto getbit = [&](const uint32_t *p, int k) { return (p[k >> 5] >> (31 - (k & 31))) & 1u; };
     unsigned init = (unsigned)enc_state_in & 63u;
     if (q > 0) {
@@ -556,7 +584,7 @@ __global__ void __launch_bounds__(128) k_vit_ber(const int8_t *__restrict__ soft
         for (int k = tb - 6; k < tb; k++) init = (init << 1) | getbit(pb, k);
     }
     int errors = 0, total = 0;
-    for (int t = lane; t < tb; t += 32) {
+    for (int t = lane; 2 * t < ns; t += 32) {
         // encoder register after shifting in bit t: bits t-6..t, older bits from `init` when t < 6
         unsigned reg = 0;
         for (int k = 6; k >= 0; k--) {
@@ -565,10 +593,10 @@ __global__ void __launch_bounds__(128) k_vit_ber(const int8_t *__restrict__ soft
             reg = (reg << 1) | b;
         }
         const int e0 = parity_u32(reg & 79u), e1 = parity_u32(reg & 109u);
-        const int sy = vit_symbols(c, t, g, h, g.chunk, 128);
+        const int sy = vit_symbols(c, t, g, h, nlim, 128);
         const int s0 = sy & 255, s1 = sy >> 8;
         if (s0 != 128) { errors += ((s0 > 127) != e0); total++; }
-        if (s1 != 128) { errors += ((s1 > 127) != e1); total++; }
+        if (2 * t + 1 < ns && s1 != 128) { errors += ((s1 > 127) != e1); total++; }
     }
     for (int off = 16; off; off >>= 1) {
         errors += __shfl_xor_sync(0xffffffffu, errors, off);
@@ -583,11 +611,153 @@ __global__ void __launch_bounds__(128) k_vit_ber(const int8_t *__restrict__ soft
     }
 }
 
+// ---------------------------------------------------------------- Viterbi_Depunc (rates 2/3, 3/4, 5/6, 7/8): viterbi_punc.cpp, depunc.h
+// symbols made by the first m input positions of the pattern counted from position 0 of a period
+__device__ __forceinline__ long punc_made(const PuncTab &P, long m) { return (m / P.P) * P.Q + P.cum[m % P.P]; }
+
+// DepuncXX::depunc_cont over a run of consecutive module calls, in closed form: input symbol i of the run (pattern position (a0 + i) mod P)
+// lands at out[lead + made(a0 + i) - made(a0)]; rotate_soft / signed_soft_to_unsigned applied on the way (soft_u8). `lead`: the run starts
+// with the symbol the reference still holds in `buf` (set_shift's is_first after a late shift). The symbol a call keeps back when its
+// count is odd stays in place in this stream: holding it back only delays WHEN a window can be decoded (host bookkeeping).
+__global__ void k_punc_depunc(const int8_t *__restrict__ soft, long nsoft, VitHyp h, PuncTab P, int a0, int lead, int lead_value,
+                              unsigned char *__restrict__ out)
+{
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0 && lead)
+        out[0] = (unsigned char)lead_value;
+    if (i >= nsoft)
+        return;
+    const long m = a0 + i;
+    const int ph = (int)(m % P.P);
+    const long o = lead + punc_made(P, m) - punc_made(P, a0);
+    const unsigned char u = (unsigned char)soft_u8(soft, (int)i, h); // (pairs of a call stay pairs: the call size is even)
+    if (P.nout[ph] == 1)
+        out[o] = u;
+    else {
+        out[o + P.datapos[ph]] = u;
+        out[o + 1 - P.datapos[ph]] = 128;
+    }
+}
+
+// Lock search of Viterbi_Depunc::work (viterbi_punc.cpp:55-107), one warp, module call by module call until a hypothesis locks: for every
+// (I/Q swap, phase, shift < 2 P) depunc_static of the first 2048 soft symbols into the PERSISTENT test buffer `bdep` (the reference's
+// member array: the decoder always reads 4108 symbols of it, i.e. beyond the depunctured length whatever an earlier trial left there, or
+// the zeros of a never written tail), decode 2048 bits with the chained test decoder, re-encode lenp/2 bits with the chained encoder,
+// BER over lenp symbols with the rate's scale; lock on the lowest BER below the threshold. test_bit_len is the LAST trial's length.
+#endif // B200_DEFINE_KERNELS
+struct PuncIdleOut { int lock_call, swap, phase, shift, test_bit_len, pad; float ber; VitIdleState st; };
+#ifdef B200_DEFINE_KERNELS
+__global__ void __launch_bounds__(32) k_punc_idle(const int8_t *__restrict__ soft, long call0, int ncalls, int call_size, PuncTab P, int nswap, int nphases,
+                                                   int ph0, int ph1, float thr, VitIdleState st_in, unsigned char *__restrict__ bdep,
+                                                   uint2 *__restrict__ scratch_dec, PuncIdleOut *__restrict__ out)
+{
+    const int lane = threadIdx.x;
+    const AcsLane L = acs_lane_consts(lane);
+    const int F = VIT_TESTLEN, steps = F + 6;
+    int dec_start = st_in.dec_start;
+    unsigned enc = (unsigned)st_in.enc_state;
+    __shared__ uint32_t tbits[VIT_TESTLEN / 32 + 2];
+    float best = 10.f;
+    int lock = -1, lswap = 0, lphase = 0, lshift = 0, tbl = 0;
+    for (int q = 0; q < ncalls && lock < 0; q++) {
+        const int8_t *c = soft + (call0 + q) * (long)call_size;
+        best = 10.f;
+        for (int s = 0; s < nswap; s++)
+            for (int pi = 0; pi < nphases; pi++)
+                for (int shift = 0; shift < 2 * P.P; shift++) {
+                    const VitHyp h{s, pi == 0 ? ph0 : ph1, 0};
+                    const int as = shift % P.P, lead = shift > P.P - 1 ? 1 : 0;
+                    // depunc_static
+                    if (lane == 0 && lead)
+                        bdep[0] = 128;
+                    for (int i = lane; i < VIT_TESTLEN; i += 32) {
+                        const long m = as + i;
+                        const int ph = (int)(m % P.P);
+                        const long o = lead + punc_made(P, m) - punc_made(P, as);
+                        const unsigned char u = (unsigned char)soft_u8(c, i, h);
+                        if (P.nout[ph] == 1)
+                            bdep[o] = u;
+                        else {
+                            bdep[o + P.datapos[ph]] = u;
+                            bdep[o + 1 - P.datapos[ph]] = 128;
+                        }
+                    }
+                    int lenp = lead + (int)(punc_made(P, as + VIT_TESTLEN) - punc_made(P, as));
+                    if (lenp % 2)
+                        lenp--;
+                    tbl = lenp;
+                    __syncwarp();
+                    // the deprecated CCDecoder::work(in, out, size) ignores its size (cc_decoder.cpp:304-314): full 2048-bit frame
+                    int xl, xh;
+                    if (dec_start < 0) xl = xh = 31;
+                    else { xl = (lane == dec_start) ? 0 : 63; xh = (lane + 32 == dec_start) ? 0 : 63; }
+                    unsigned D0, D1;
+                    for (int t0 = 0; t0 < steps; t0 += 32) {
+                        const int tm = t0 + lane;
+                        const int mine = tm < steps ? ((int)bdep[2 * tm] | ((int)bdep[2 * tm + 1] << 8)) : 0;
+                        unsigned k0 = 0, k1 = 0;
+                        const int nn = min(32, steps - t0);
+                        for (int j = 0; j < nn; j++) {
+                            const int sy = __shfl_sync(0xffffffffu, mine, j);
+                            acs_step(sy, L, lane, xl, xh, D0, D1);
+                            if (lane == j) { k0 = D0; k1 = D1; }
+                        }
+                        if (lane < nn) scratch_dec[t0 + lane] = make_uint2(k0, k1);
+                    }
+                    __syncwarp();
+                    int st = acs_endstate(xl, xh, lane), bit;
+                    for (int row = steps - 1, k = 0; row >= 6; row--, k++) {
+                        const uint2 r = scratch_dec[row];
+                        st = tb_step(st, r.x, r.y, bit);
+                        if (k == 5) dec_start = st;
+                        const int i = row - 6;
+                        if (lane == 0) {
+                            if ((i & 31) == 31 || i == F - 1) tbits[i >> 5] = 0; // first touch of this word (walking downwards)
+                            tbits[i >> 5] |= (unsigned)bit << (31 - (i & 31));
+                        }
+                    }
+                    __syncwarp();
+                    // re-encode lenp / 2 bits with the chained encoder and count mismatches over lenp symbols
+                    const int nb = lenp / 2;
+                    int errors = 0, total = 0;
+                    for (int t = lane; t < nb; t += 32) {
+                        unsigned reg = 0;
+                        for (int k = 6; k >= 0; k--) {
+                            const int idx = t - k;
+                            const unsigned b = idx >= 0 ? ((tbits[idx >> 5] >> (31 - (idx & 31))) & 1u) : ((enc >> (-idx - 1)) & 1u);
+                            reg = (reg << 1) | b;
+                        }
+                        const int e0 = parity_u32(reg & 79u), e1 = parity_u32(reg & 109u);
+                        const int s0 = bdep[2 * t], s1 = bdep[2 * t + 1];
+                        if (s0 != 128) { errors += ((s0 > 127) != e0); total++; }
+                        if (s1 != 128) { errors += ((s1 > 127) != e1); total++; }
+                    }
+                    for (int off = 16; off; off >>= 1) {
+                        errors += __shfl_xor_sync(0xffffffffu, errors, off);
+                        total += __shfl_xor_sync(0xffffffffu, total, off);
+                    }
+                    unsigned tail = 0;
+                    for (int k = nb - 6; k < nb; k++) tail = (tail << 1) | ((tbits[k >> 5] >> (31 - (k & 31))) & 1u);
+                    enc = tail;
+                    const float b = ((float)errors / (float)total) * P.berscale;
+                    if (b < thr && b < best) {
+                        best = b; lock = q; lswap = s; lphase = h.phase; lshift = shift;
+                    }
+                    __syncwarp();
+                }
+    }
+    if (lane == 0) {
+        PuncIdleOut o;
+        o.lock_call = lock; o.swap = lswap; o.phase = lphase; o.shift = lshift; o.test_bit_len = tbl; o.pad = 0; o.ber = best;
+        o.st.dec_start = dec_start; o.st.enc_state = (int)enc;
+        *out = o;
+    }
+}
+
 // ---------------------------------------------------------------- lock search (IDLE state), one serial warp
 // Replays Viterbi3_4::work / Viterbi1_2::work in the IDLE state chunk by chunk until a hypothesis locks
 // (viterbi_3_4.cpp:112-144, viterbi_1_2.cpp:54-89), with the chained test decoder / encoder state.
 #endif // B200_DEFINE_KERNELS
-struct VitIdleState { int dec_start; /* -1 unbiased */ int enc_state; };
 struct VitIdleOut { int lock_chunk, swap, phase, shift; float ber; float bers[16]; VitIdleState st; int pad; };
 
 #ifdef B200_DEFINE_KERNELS

@@ -49,6 +49,22 @@ class Fec
     DevBuf<int> tb_list; // [0] count of chunks redone serially in the last launch, [1..] their indices
     DevBuf<int> redo_list; // chunks decoded again because their speculated start state was wrong (+ the chunks whose BER check follows)
     std::vector<int> h_redo, h_redo_ber, h_start;
+    // Viterbi_Depunc (conv_rate 2/3 ... 7/8): the depunctured symbol stream the decoder windows read (leftover of the previous push in
+    // front), the lock search's persistent test buffer, per-window count of real tail symbols, and the DepuncXX / ViterbiSlidingBuffer
+    // state of viterbi_punc.cpp / depunc.h carried between pushes
+    bool punc = false;
+    PuncTab ptab{};
+    DevBuf<unsigned char> vitbuf, vitbuf_tmp, bdep;
+    DevBuf<int> tail_real;
+    DevBuf<PuncIdleOut> punc_out;
+    PuncIdleOut *h_punc = nullptr;
+    std::vector<int> h_tail, h_wcall;
+    long in_buffer = 0;       // symbols waiting in vitbuf (ViterbiSlidingBuffer::in_buffer)
+    int changing_shift = 0;   // DepuncXX::changing_shift
+    bool is_first = false, got_extra = false;
+    int buf_value = 128;      // DepuncXX::buf: the last symbol a call held back
+    int test_bit_len = 0;     // Viterbi_Depunc::test_bit_len
+    int pdec_start = -1;      // start state of the chained test decoder (cc_decoder_ber)
     int tb_blocks = 1;
     int tb_overlap = TB_OVERLAP; // warm-up rows of the parallel chainback blocks (adapts to the channel)
     int tb_clean = 0, spec_clean = 0; // consecutive launches without misses (the windows shrink back slowly)

@@ -249,8 +249,15 @@ b200_fec_cfg fec_cfg_from_params(const std::string &id, const Params &p)
     c.derandomize = p.flag("derandomize", true);
     c.derand_after_rs = p.flag("derand_after_rs", false);
     c.derand_start = (int)p.num("derand_start", 4);
-    if (p.str("conv_rate", "1/2") != "1/2")
-        throw ModuleError("conv_rate " + p.str("conv_rate") + " (Viterbi_Depunc) is not supported by the B200 path");
+    {
+        const std::string cr = p.str("conv_rate", "1/2"); // module_ccsds_conv_concat_decoder.cpp:33,99-117
+        if (cr == "1/2") c.conv_rate = 0;
+        else if (cr == "2/3") c.conv_rate = 2;
+        else if (cr == "3/4") c.conv_rate = 3;
+        else if (cr == "5/6") c.conv_rate = 5;
+        else if (cr == "7/8") c.conv_rate = 7;
+        else throw ModuleError("conv_rate " + cr + " is not one of 1/2, 2/3, 3/4, 5/6, 7/8");
+    }
     c.rs_i = (int)p.num("rs_i");
     c.rs_fill_bytes = (int)p.num("rs_fill_bytes", -1);
     c.rs_dualbasis = p.flag("rs_dualbasis", true);

@@ -27,7 +27,7 @@ def run(pipe, extra, tmp_path):
     ("simple_qpsk", ["--symbolrate", "2400000", "--oqpsk_method2", "true"], "oqpsk_method2"),
     ("simple_bpsk", ["--samplerate", "3e6", "--hard_symbols", "true"], "hard_symbols"),
     ("simple_bpsk", ["--samplerate", "3e6", "--constellation", "8psk"], "invalid constellation"),
-    ("jpss_hrd", ["--samplerate", "50e6", "--conv_rate", "3/4"], "conv_rate"),
+    ("jpss_hrd", ["--samplerate", "50e6", "--conv_rate", "4/5"], "conv_rate"),                  # (2/3 ... 7/8 are the Viterbi_Depunc rates)
 ])
 def test_unsupported_parameters_are_named(built, tmp_path, pipe, extra, needle):
     r = run(pipe, extra, tmp_path)
