@@ -86,7 +86,7 @@ Fec::Fec(const b200_fec_cfg &c) : cfg(c)
         if (cfg.asm_sync == 0)
             cfg.asm_sync = 0x1ACFFC1D;
     } else {
-        // module_ccsds_conv_concat_decoder.cpp:16-131 (conv_rate 1/2 only; the Viterbi_Depunc rates are not built)
+        // module_ccsds_conv_concat_decoder.cpp:16-131
         B200_REQUIRE(c.cadu_size >= 64 && c.cadu_size <= 65536, B200_EINVAL, "cadu_size out of range");
         B200_REQUIRE(c.cadu_size % 8 == 0, B200_EINVAL, "cadu_size must be a multiple of 8 (frame padding is not built)");
         B200_REQUIRE(c.rs_i >= 0 && c.rs_i <= RS_MAX_I, B200_EINVAL, "rs_i out of range (0..%d)", RS_MAX_I);

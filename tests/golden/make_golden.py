@@ -21,7 +21,8 @@ OUT = os.path.dirname(os.path.abspath(__file__))
 def main():
     assert ref.available(), "build oracle/_ref first (python -c 'import __graft_entry__ as g; g.build()')"
     only = sys.argv[1:]
-    for name, lg in [("metop_ahrpt", 17), ("bpsk_half", 16), ("jpss_hrd", 17), ("dvbs2_front", 16), ("hrpt_bpsk", 18), ("metop_oversampled", 19), ("bpsk_decim8", 20), ("qpsk_undersampled", 16), ("psk8", 17), ("bpsk_simple", 17), ("qpsk_simple", 17)]:
+    for name, lg in [("metop_ahrpt", 17), ("bpsk_half", 16), ("jpss_hrd", 17), ("dvbs2_front", 16), ("hrpt_bpsk", 18), ("metop_oversampled", 19), ("bpsk_decim8", 20), ("qpsk_undersampled", 16), ("psk8", 17), ("bpsk_simple", 17), ("qpsk_simple", 17),
+                     ("qpsk_p34", 18), ("qpsk_p78", 18)]:  # Viterbi_Depunc rates (conv_rate 3/4 is the one a shipped pipeline uses, 7/8 the most punctured)
         if only and name not in only:
             continue
         cfg = synth.CONFIGS[name]

@@ -9,7 +9,8 @@ from tests.common import ROOT, oracle_demod, oracle_fec, signal, simple_soft_cas
 from satdump_b200 import synth
 
 GOLD = os.path.join(ROOT, "tests", "golden")
-CONFIGS = ["metop_ahrpt", "bpsk_half", "jpss_hrd", "dvbs2_front", "hrpt_bpsk", "metop_oversampled", "bpsk_decim8", "qpsk_undersampled", "psk8", "bpsk_simple", "qpsk_simple"]
+CONFIGS = ["metop_ahrpt", "bpsk_half", "jpss_hrd", "dvbs2_front", "hrpt_bpsk", "metop_oversampled", "bpsk_decim8", "qpsk_undersampled", "psk8", "bpsk_simple", "qpsk_simple",
+           "qpsk_p34", "qpsk_p78"]  # ccsds_conv_concat_decoder with conv_rate 3/4, 7/8 (Viterbi_Depunc)
 
 
 def _ref():
@@ -242,3 +243,23 @@ def test_resampler_port_equals_reference_over_rates_and_formats(built):
             assert cfg.samplerate / cfg.final_samplerate >= 2
             a, b = ref.resample(cfg, raw), port.resample(cfg, raw)
             assert a.size == b.size > 1000 and bitwise(a, b), (fs, rs, con, fmt)
+
+
+@pytest.mark.parametrize("name", ["qpsk_p23", "qpsk_p34", "qpsk_p56", "qpsk_p78"])
+def test_viterbi_depunc_port_equals_reference(built, name):
+    """Viterbi_Depunc (viterbi_punc.cpp, depunc.h) at its four rates: the C restatement follows the reference bit for bit - decoded bits,
+    lock state and BER per module call, CADUs - also through noise -> signal -> noise (lock search on the persistent test buffer, unlock after
+    viterbi_outsync_after bad calls, a second lock with the sliding buffer's leftover and the held-back symbol carried over)."""
+    from oracle import port
+    ref = _ref()
+    cfg = synth.CONFIGS[name]
+    raw, _ = synth.make_signal(cfg, 1 << 20, seed=0x600D + 1, device="cpu")
+    soft = oracle_demod(ref, cfg).run(raw.numpy(), stages=False)["soft"]
+    rng = np.random.default_rng(5)
+    noise = lambda n: rng.integers(-60, 61, n).astype(np.int8)
+    stream = np.concatenate([noise(8192 * 5 + 16), soft[:400000], noise(8192 * 40 + 2), soft[400000:], noise(8192 * 3)])
+    r, p = oracle_fec(ref, cfg).run(stream), oracle_fec(port, cfg).run(stream)
+    assert (r["vit_state"] == 0).any() and (r["vit_state"] > 0).any() and r["bits"].size > 300000 and r["cadu"].size >= 10 * cfg.cadu_bytes
+    for k in ("bits", "cadu", "vit_state", "defr_state", "rs_err"):
+        assert np.array_equal(r[k], p[k]), k
+    assert np.allclose(r["vit_ber"], p["vit_ber"], rtol=0, atol=0)
