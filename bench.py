@@ -442,14 +442,18 @@ def main():
         step_dev()
     res0 = step_host()
     nres = res0.size // unit
-    frames_ok, first = True, None
+    frames_ok, first, parity_as_received = True, None, None
     if w["kind"] == "chain":
         fr = res0.reshape(-1, unit)
-        first = next((i for i in range(min(256, clear.shape[0])) if np.array_equal(clear[i], fr[0])), None) if nres else None
-        # every CADU must be one of the transmitted frames, in order and without a gap. (At the stress SNR frames RS could not repair
-        # differ from the transmitted ones, and rs_usecheck drops them: then only the repaired ones are compared.)
+        # every CADU must be one of the transmitted frames, in order and without a gap. The comparison is over the ASM + the RS message
+        # bytes: the decoder writes back only the corrected message (reedsolomon.cpp:96-104), a channel error in a codeword's parity bytes
+        # stays in the CADU as received, in the reference as here (`cadus_with_parity_bytes_as_received` counts those frames). (At the
+        # stress SNR frames RS could not repair differ from the transmitted ones, and rs_usecheck drops them: then nothing is compared.)
+        msg = 4 + 223 * cfg.interleave if cfg.interleave else unit
+        first = next((i for i in range(min(256, clear.shape[0])) if np.array_equal(clear[i, :msg], fr[0, :msg])), None) if nres else None
         strict = pipe.stats()["fec"]["rs_failed"] == 0
-        frames_ok = nres > 0 and (not strict or (first is not None and first + nres <= clear.shape[0] and np.array_equal(fr, clear[first:first + nres])))
+        frames_ok = nres > 0 and (not strict or (first is not None and first + nres <= clear.shape[0] and np.array_equal(fr[:, :msg], clear[first:first + nres, :msg])))
+        parity_as_received = int((fr[:, msg:] != clear[first:first + nres, msg:]).any(axis=1).sum()) if (frames_ok and strict and first is not None) else None
 
     # PCIe ceiling of the e2e number: the same pinned batch copied host -> device alone (torch copy engine, CUDA events)
     dst = torch.empty_like(raw)
@@ -545,7 +549,8 @@ def main():
                 "warmup": max(args.warmup, 3), "ms_per_step": wall_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32+u8" if w["kind"] == "chain" else "f32", "data": "synthetic",
                 "config": {"workload": w["label"], "samples_per_step_per_gpu": n, "result_units_per_step_per_gpu": int(nres),
-                           "result_unit_bytes": unit, "cadus_bit_exact_vs_transmitted": bool(all_ok) if w["kind"] == "chain" else None, "first_cadu_is_transmitted_frame": first,
+                           "result_unit_bytes": unit, "cadus_bit_exact_vs_transmitted": bool(all_ok) if w["kind"] == "chain" else None,
+                           "cadus_with_parity_bytes_as_received": parity_as_received if w["kind"] == "chain" else None, "first_cadu_is_transmitted_frame": first,
                            "l2": "input batch (%.0f MiB) larger than L2" % (n * bps / 2 ** 20), "esn0_db": cfg.esn0_db},
                 "e2e": {"value": e2e, "unit": "MS/s", "h2d_bytes_per_step": n * bps * world, "d2h_bytes_per_step": int(nres) * unit * world,
                         "pcie_h2d_GBps_alone": round(h2d_gbps, 2), "pcie_bound_MSps_per_gpu": round(h2d_gbps * 1e9 / bps / 1e6, 1),
