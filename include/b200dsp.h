@@ -43,7 +43,8 @@ enum { B200_CF32 = 0, B200_CS16 = 1, B200_CS8 = 2 };
 /* decoder kind */
 enum { B200_FEC_METOP = 0, B200_FEC_CCSDS = 1, B200_FEC_SIMPLE = 2 };
 /* debug stage ids for b200_demod_debug_stage */
-enum { B200_STAGE_AGC = 0, B200_STAGE_FIR = 1, B200_STAGE_COSTAS = 2, B200_STAGE_RESAMP = 3, B200_STAGE_DC = 4, B200_STAGE_MM = 5 };
+enum { B200_STAGE_AGC = 0, B200_STAGE_FIR = 1, B200_STAGE_COSTAS = 2, B200_STAGE_RESAMP = 3, B200_STAGE_DC = 4, B200_STAGE_MM = 5,
+       B200_STAGE_PLL = 6 /* pm_demod: PLLCarrierTrackingBlock output */, B200_STAGE_PM = 7 /* pm_demod: PMToBPSK output */ };
 /* mode bits of b200_demod_debug_run_stage */
 #define B200_DEBUG_STRICT 1     /* the reference's operation order: separate multiply and add, left to right (generic VOLK, no FMA) */
 #define B200_DEBUG_SEQUENTIAL 2 /* one segment: the feedback loop runs as ONE sequential thread from the initial state */
@@ -80,6 +81,16 @@ typedef struct b200_demod_cfg
     int clock_recovery;       /* 0: MMClockRecoveryBlock<complex_t> (what psk_demod builds, module_psk_demod.cpp:134-135);
                                  1: dsp::GardnerClockRecoveryBlock<complex_t> with the same arguments
                                  (common/dsp/clock_recovery/clock_recovery_gardner.cpp:33-131)                          */
+    /* pm_demod (src-core/pipeline/modules/demod/module_pm_demod.cpp:12-88): AGC -> PLLCarrierTrackingBlock -> PMToBPSK ->
+       [SmartResamplerBlock -> AGCBlock(0.001, 1, 1, 1000)] -> RRC -> Costas loop (order 2) -> M&M, soft = clamp(real * 100).
+       The working-rate window is then [1.1, 10] samples per symbol (MAX_SPS = 10, :56) */
+    int pm_demod;             /* != 0: build PMDemodModule's chain; constellation must be B200_BPSK, pll_bw above is its "costas_bw"  */
+    float pm_pll_bw;          /* "pll_bw": carrier PLL loop bandwidth (required by the module, :21-24)                              */
+    float pm_pll_max_offset;  /* "pll_max_offset", default 0.5 rad/sample (module_pm_demod.h:29)                                    */
+    int pm_resample_after_pll;/* "resample_after_pll": the front-end resampler sits behind PMToBPSK, followed by the second AGC      */
+    double pm_subcarrier_offset; /* "subcarrier_offset" Hz (uint64 in the module); 0 = the symbol rate (:67)                           */
+    double freq_shift;        /* "freq_shift" Hz (long in the module): FreqShiftBlock behind the reader / DC blocker, in front of the
+                                 resampler (module_demod_base.cpp:37,122-123; common/dsp/utils/freq_shift.cpp); 0 = none             */
 } b200_demod_cfg;
 
 typedef struct b200_fec_cfg
@@ -117,6 +128,9 @@ typedef struct b200_demod_stats
     long last_front_samples;  /* samples that entered the AGC in the last push (= nsamples unless the front-end resampler runs) */
     float snr, peak_snr;      /* M2M4SNREstimator over the recovered symbols, dB (module stats keys "snr" / "peak_snr", module_psk_demod.cpp:190-194,242-243):
                                  evaluated at the end of every push; the peak is the maximum of those */
+    float pll_freq;           /* pm_demod: carrier PLL frequency, rad/sample (PLLCarrierTrackingBlock::getFreq; module stats key "freq" =
+                                 rad_to_hz(pll_freq, final_samplerate), module_pm_demod.cpp:138,186) */
+    long pll_unconverged;     /* pm_demod: carrier PLL junctions still inconsistent after the repair rounds of the last push (expected 0) */
 } b200_demod_stats;
 
 typedef struct b200_fec_stats

@@ -5,6 +5,7 @@
  * arithmetic bit for bit (the oracle of record is the generic/scalar VOLK flavour).
  */
 #include "oracle.h"
+#include <stdio.h>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -273,6 +274,13 @@ typedef struct
     cf_t dc_acc;        /* CorrectIQBlock::acc (front) */
     cf_t dc_acc2;       /* CorrectIQBlock::acc (behind the Costas loop) */
     cf_t *rs_in;
+    /* pm_demod (module_pm_demod.cpp:61-88) and freq_shift (module_demod_base.cpp:122-123) */
+    int rs_after;            /* the resampler sits behind PMToBPSK ("resample_after_pll") */
+    float pll_state[2];      /* PLLCarrierTrackingBlock: d_phase, d_freq */
+    float pm_inc[2], pm_phase[2], fs_inc[2], fs_phase[2]; /* rotator steps / phasors of PMToBPSK and FreqShiftBlock */
+    float agc2_gain;         /* AGCBlock(resampler out, 0.001, 1.0, 1.0, 1000.0) (module_pm_demod.cpp:73-74) */
+    long pm_pos;
+    float *pll_dump, *pm_dump;
 } orc_demod;
 
 static float clip_branchless(float x, float c) { return 0.5 * (fabsf(x + c) - fabsf(x - c)); } /* block.cpp:5 */
@@ -289,6 +297,19 @@ void *orc_demod_create(const orc_demod_cfg *c)
     d->buffer_size = c->buffer_size > 0 ? c->buffer_size : def;
     float final_fs = c->final_samplerate > 0 ? (float)c->final_samplerate : (float)fs; /* float final_samplerate, module_demod_base.h:58 */
     d->sps = final_fs / (float)rs;     /* module_demod_base.cpp:81 */
+    if (c->pm) { /* PMToBPSK(pll out, d_resample_after_pll ? d_samplerate : final_samplerate, subcarrier == 0 ? d_symbolrate : subcarrier), float args */
+        const float rate = c->pm_resample_after_pll ? (float)fs : final_fs;
+        const unsigned long sub = (unsigned long)c->pm_subcarrier_offset;
+        const float f = sub == 0 ? (float)rs : (float)sub;
+        orc_rotator_inc(-(double)f, (double)rate, d->pm_inc); /* pm_to_bpsk.cpp:12 */
+        d->pm_phase[0] = 1.0f;
+        d->agc2_gain = 1.0f;
+        d->rs_after = c->pm_resample_after_pll;
+    }
+    if (c->freq_shift != 0) { /* FreqShiftBlock(input, d_samplerate, d_frequency_shift): long parameters (module_demod_base.cpp:122-123) */
+        orc_rotator_inc((double)(long)c->freq_shift, (double)fs, d->fs_inc);
+        d->fs_phase[0] = 1.0f;
+    }
     if (c->final_samplerate > 0 && (long)c->final_samplerate != fs) {
         float decimation_factor = fs / final_fs; /* module_demod_base.cpp:84-87 */
         d->buffer_size *= ceil(decimation_factor);
@@ -301,12 +322,14 @@ void *orc_demod_create(const orc_demod_cfg *c)
     d->ntaps = orc_rrc_taps(1, final_fs, (int)rs, c->rrc_alpha, c->rrc_taps, d->taps);      /* module_psk_demod.cpp:91 */
     d->fir_buf = calloc(2 * STREAM_MAX, sizeof(cf_t));
     d->order = c->constellation == 0 ? 2 : (c->constellation == 3 ? 8 : (c->constellation == 4 ? 0 : 4));
+    if (c->pm) d->order = 2;
     {   /* costas_loop.cpp:5-12 */
         float damping = sqrtf(2.0f) / 2.0f;
         float denom = (1.0 + 2.0 * damping * c->pll_bw + c->pll_bw * c->pll_bw);
         d->alpha = (4 * damping * c->pll_bw) / denom;
         d->beta = (4 * c->pll_bw * c->pll_bw) / denom;
         d->fmin = -c->costas_max_offset; d->fmax = c->costas_max_offset;
+        if (c->pm) { d->fmin = -1.0f; d->fmax = 1.0f; } /* CostasLoopBlock(rrc out, d_loop_bw, 2): freq_limit defaults to 1.0 (module_pm_demod.cpp:84) */
     }
     orc_mm_bank(d->bank);
     d->mu = c->clock_mu; d->omega = d->sps; d->omega_gain = c->clock_gain_omega; d->mu_gain = c->clock_gain_mu;
@@ -348,30 +371,191 @@ static void convert_in(const orc_demod_cfg *c, const void *raw, long off, int n,
 }
 
 /* reader + optional CorrectIQBlock<complex_t>::work (utils/correct_iq.cpp:18-35; alpha = 1e-4 member default, beta = 1 - alpha) */
+void orc_rotator(const float *in, long n, long call, float inc_re, float inc_im, int imag_only, float *phase, float *out);
 static void front_in(orc_demod *d, const void *raw, long off, int n, cf_t *dst)
 {
     convert_in(&d->cfg, raw, off, n, dst);
-    if (!d->cfg.dc_block) return;
-    const float alpha = 0.0001, beta = 1.0f - alpha;
-    for (int i = 0; i < n; i++) {
-        d->dc_acc.re = d->dc_acc.re * beta + dst[i].re * alpha;
-        d->dc_acc.im = d->dc_acc.im * beta + dst[i].im * alpha;
-        dst[i].re = dst[i].re - d->dc_acc.re;
-        dst[i].im = dst[i].im - d->dc_acc.im;
+    if (d->cfg.dc_block) {
+        const float alpha = 0.0001, beta = 1.0f - alpha;
+        for (int i = 0; i < n; i++) {
+            d->dc_acc.re = d->dc_acc.re * beta + dst[i].re * alpha;
+            d->dc_acc.im = d->dc_acc.im * beta + dst[i].im * alpha;
+            dst[i].re = dst[i].re - d->dc_acc.re;
+            dst[i].im = dst[i].im - d->dc_acc.im;
+        }
     }
+    if (d->cfg.freq_shift != 0 && n > 0) /* one rotator call per buffer (freq_shift.cpp:16-37); in place: sample k is read before it is written */
+        orc_rotator((const float *)dst, n, n, d->fs_inc[0], d->fs_inc[1], 0, d->fs_phase, (float *)dst);
 }
 
 /* AGCBlock<complex_t>::work — agc.cpp:25-39. The magnitude goes through ::sqrt(double). */
-static void agc_run(orc_demod *d, const cf_t *in, cf_t *out, int n)
+static void agc_unit(const cf_t *in, cf_t *out, int n, float rate, float ref, float max_gain, float *gain)
 {
-    float g = d->agc_gain;
+    float g = *gain;
     for (int i = 0; i < n; i++) {
         cf_t o = {in[i].re * g, in[i].im * g};
-        g += d->agc_rate * (d->agc_ref - sqrt(o.re * o.re + o.im * o.im));
-        if (d->agc_max > 0.0 && g > d->agc_max) g = d->agc_max;
+        g += rate * (ref - sqrt(o.re * o.re + o.im * o.im));
+        if (max_gain > 0.0 && g > max_gain) g = max_gain;
         out[i] = o;
     }
-    d->agc_gain = g;
+    *gain = g;
+}
+static void agc_run(orc_demod *d, const cf_t *in, cf_t *out, int n) { agc_unit(in, out, n, d->agc_rate, d->agc_ref, d->agc_max, &d->agc_gain); }
+
+/* ================================================================== pm_demod / freq_shift blocks
+ * fast_atan2f: 256-interval table of atan over [0, 1] with linear interpolation (common/dsp/utils/fast_trig.cpp:16-154). The table is
+ * the arctangent of k/255 printed with seven significant digits (the reference lists those literals, taken from GNU Radio); it is
+ * regenerated here from atan() through the same decimal rounding and pinned entry by entry through the function's outputs
+ * (tests/test_oracle.py). Entry 256 repeats entry 255. */
+static float fat_tab[257];
+static int fat_ready;
+static void fat_build(void)
+{
+    char buf[40];
+    for (int k = 0; k < 256; k++) {
+        snprintf(buf, sizeof buf, "%.6e", atan((double)k / 255.0));
+        fat_tab[k] = (float)strtod(buf, NULL);
+    }
+    fat_tab[256] = fat_tab[255];
+    fat_ready = 1;
+}
+const float *orc_fast_atan_table(void)
+{
+    if (!fat_ready)
+        fat_build();
+    return fat_tab;
+}
+
+float orc_fast_atan2f(float y, float x)
+{
+    if (!fat_ready)
+        fat_build();
+    const float ya = fabsf(y), xa = fabsf(x);
+    if (!(ya > 0.0f || xa > 0.0f)) /* fast_trig.cpp:90-91 */
+        return 0.0f;
+    const float z = ya < xa ? ya / xa : xa / ya; /* :93-96 */
+    float base;
+    if ((double)z < 0.003921569) /* :100-101: below the table resolution the angle is the ratio itself */
+        base = z;
+    else { /* :104-111 */
+        float a = z * 255.0f;
+        const int idx = ((int)a) & 0xff;
+        a -= (float)idx;
+        base = fat_tab[idx];
+        base += (fat_tab[idx + 1] - fat_tab[idx]) * a;
+    }
+    float ang;
+    if (xa > ya) { /* :114-131 */
+        if (x >= 0.0f)
+            ang = y >= 0.0f ? base : -base;
+        else {
+            ang = (float)3.14159265358979323846;
+            if (y >= 0.0f)
+                ang -= base;
+            else
+                ang = base - ang;
+        }
+    } else { /* :132-151 */
+        if (y >= 0.0f) {
+            ang = (float)1.57079632679489661923;
+            if (x >= 0.0f)
+                ang -= base;
+            else
+                ang += base;
+        } else {
+            ang = (float)-1.57079632679489661923;
+            if (x >= 0.0f)
+                ang += base;
+            else
+                ang -= base;
+        }
+    }
+    return ang;
+}
+
+/* even / odd minimax polynomials, the powers in float, the Horner sums in double, rounded once on return (fast_trig.cpp:158-180) */
+float orc_fast_cos(float x)
+{
+    const float x2 = x * x, x4 = x2 * x2, x8 = x4 * x4;
+    return (float)((-2.7236370439787708e-7 * x2 + 2.4799852696610628e-5) * x8 + (-1.3888885054799695e-3 * x2 + 4.1666666636943683e-2) * x4 +
+                   (-4.9999999999963024e-1 * x2 + 1.0000000000000000e+0));
+}
+float orc_fast_sin(float x)
+{
+    const float x2 = x * x, x4 = x2 * x2;
+    return (float)(((2.7181216275479732e-6 * x2 - 1.9839312269456257e-4) * x4 + (8.3333293048425631e-3 * x2 - 1.6666666640797048e-1)) * x2 * x + x);
+}
+
+void orc_pll_carrier(const float *in, long n, float loop_bw, float max_freq, float min_freq, float *state, float *out)
+{
+    /* gains: pll_carrier_tracking.cpp:17-21 (damping sqrt(2)/2, the same second-order design as the Costas loop) */
+    const float damping = sqrtf(2.0f) / 2.0f;
+    const float denom = (float)(1.0 + 2.0 * damping * loop_bw + loop_bw * loop_bw);
+    const float alpha = (4 * damping * loop_bw) / denom, beta = (4 * loop_bw * loop_bw) / denom;
+    float phase = state[0], freq = state[1];
+    for (long i = 0; i < n; i++) {
+        const float re = in[2 * i], im = in[2 * i + 1];
+        const float vr = orc_fast_cos(phase), vi = -orc_fast_sin(phase); /* :38 */
+        out[2 * i] = re * vr - im * vi;                                 /* :41, complex.h:68-72 */
+        out[2 * i + 1] = im * vr + re * vi;
+        float err = orc_fast_atan2f(im, re) - phase; /* :44 */
+        while ((double)err < -M_PI)                   /* :45-48: compared and stepped in double, stored as float */
+            err = (float)((double)err + 2 * M_PI);
+        while ((double)err > M_PI)
+            err = (float)((double)err - 2 * M_PI);
+        freq = freq + beta * err; /* :51-55 */
+        if (freq > max_freq)
+            freq = max_freq;
+        else if (freq < min_freq)
+            freq = min_freq;
+        phase = phase + freq + alpha * err; /* :58-62 */
+        while ((double)phase < -M_PI)
+            phase = (float)((double)phase + 2 * M_PI);
+        while ((double)phase > M_PI)
+            phase = (float)((double)phase - 2 * M_PI);
+    }
+    state[0] = phase;
+    state[1] = freq;
+}
+
+void orc_rotator_inc(double freq, double samplerate, float *inc2)
+{
+    const double w = 2.0 * M_PI * (freq / samplerate); /* hz_to_rad, common/dsp/block.cpp:17 */
+    inc2[0] = (float)cos(w);
+    inc2[1] = (float)sin(w);
+}
+
+/* VOLK's rotator (system library, not vendored by the reference; generic flavour of 2.x / 3.x as published): the phasor advances by
+ * one complex multiplication per sample and is brought back to unit length after every 512 samples of a call and at the end of a call
+ * that is not a multiple of 512. Same arithmetic as oracle/shim/volk/volk.h, which the compiled reference blocks call. */
+void orc_rotator(const float *in, long n, long call, float inc_re, float inc_im, int imag_only, float *phase, float *out)
+{
+    float pr = phase[0], pi = phase[1];
+    for (long pos = 0; pos < n; pos += call) {
+        const long m = n - pos < call ? n - pos : call;
+        int since = 0;
+        for (long k = pos; k < pos + m; k++) {
+            const float a = imag_only ? 0.0f : in[2 * k], b = in[2 * k + 1];
+            out[2 * k] = a * pr - b * pi;
+            out[2 * k + 1] = a * pi + b * pr;
+            const float nr = pr * inc_re - pi * inc_im, ni = pr * inc_im + pi * inc_re;
+            pr = nr;
+            pi = ni;
+            if (++since == 512) {
+                const float mag = hypotf(pr, pi);
+                pr /= mag;
+                pi /= mag;
+                since = 0;
+            }
+        }
+        if (since) {
+            const float mag = hypotf(pr, pi);
+            pr /= mag;
+            pi /= mag;
+        }
+    }
+    phase[0] = pr;
+    phase[1] = pi;
 }
 
 /* The same recurrence evaluated in double precision (gain, product and magnitude): what agc.cpp:25-39 computes before its float
@@ -538,16 +722,33 @@ long orc_demod_run(void *h, const void *raw, long nsamples, float *agc_out, floa
 {
     orc_demod *d = h;
     long nsym = 0, pos = 0; /* pos: samples after the (optional) resampler so far in this call */
+    d->pm_pos = 0;
     for (long off = 0; off < nsamples; off += d->buffer_size) {
         int n = (int)(nsamples - off < d->buffer_size ? nsamples - off : d->buffer_size);
-        if (d->rs.active) {
+        if (d->rs.active && !d->rs_after) {
             front_in(d, raw, off, n, d->rs_in);
             n = resamp_run(&d->rs, (const float *)d->rs_in, n, (float *)d->w0);
             if (n <= 0) continue;
         } else
             front_in(d, raw, off, n, d->w0);
         agc_run(d, d->w0, d->w1, n);
-        if (agc_out) memcpy(agc_out + pos * 2, d->w1, n * sizeof(cf_t));
+        if (agc_out) memcpy(agc_out + (d->cfg.pm ? d->pm_pos : pos) * 2, d->w1, n * sizeof(cf_t));
+        if (d->cfg.pm) { /* module_pm_demod.cpp:65-74 */
+            orc_pll_carrier((const float *)d->w1, n, d->cfg.pm_pll_bw, d->cfg.pm_pll_max_offset, -d->cfg.pm_pll_max_offset, d->pll_state, (float *)d->w0);
+            if (d->pll_dump) memcpy(d->pll_dump + d->pm_pos * 2, d->w0, n * sizeof(cf_t));
+            orc_rotator((const float *)d->w0, n, n, d->pm_inc[0], d->pm_inc[1], 1, d->pm_phase, (float *)d->w1); /* PMToBPSK: one call per buffer */
+            if (d->pm_dump) memcpy(d->pm_dump + d->pm_pos * 2, d->w1, n * sizeof(cf_t));
+            d->pm_pos += n;
+            if (d->rs_after) {
+                if (d->rs.active) {
+                    memcpy(d->rs_in, d->w1, n * sizeof(cf_t));
+                    n = resamp_run(&d->rs, (const float *)d->rs_in, n, (float *)d->w0);
+                    if (n <= 0) continue;
+                } else
+                    memcpy(d->w0, d->w1, n * sizeof(cf_t));
+                agc_unit(d->w0, d->w1, n, 0.001f, 1.0f, 1000.0f, &d->agc2_gain);
+            }
+        }
         fir_run(d, d->w1, d->w0, n);
         if (fir_out) memcpy(fir_out + pos * 2, d->w0, n * sizeof(cf_t));
         cf_t *cur = d->w0;
@@ -571,7 +772,9 @@ long orc_demod_run(void *h, const void *raw, long nsamples, float *agc_out, floa
         if (nsym + m > sym_cap) m = (int)(sym_cap - nsym);
         if (mm_out) memcpy(mm_out + nsym * 2, d->w2, m * sizeof(cf_t));
         if (soft_out) { /* module_psk_demod.cpp:199-213 */
-            if (d->cfg.constellation == 0)
+            if (d->cfg.pm) /* module_pm_demod.cpp:141-144 */
+                for (int i = 0; i < m; i++) soft_out[nsym + i] = soft_clamp(d->w2[i].re * 100);
+            else if (d->cfg.constellation == 0)
                 for (int i = 0; i < m; i++) soft_out[nsym + i] = soft_clamp(d->w2[i].re * 50);
             else
                 for (int i = 0; i < m; i++) {
@@ -585,6 +788,8 @@ long orc_demod_run(void *h, const void *raw, long nsamples, float *agc_out, floa
     return nsym;
 }
 long orc_demod_last_front(void *h) { return ((orc_demod *)h)->last_front; }
+void orc_demod_pm_dumps(void *h, float *pll_out, float *pm_out) { orc_demod *d = h; d->pll_dump = pll_out; d->pm_dump = pm_out; }
+void orc_demod_pm_state(void *h, float *o) { orc_demod *d = h; o[0] = d->pll_state[0]; o[1] = d->pll_state[1]; o[2] = d->cfg.pm && d->rs_after ? d->agc2_gain : 0; o[3] = 0; }
 /* ONE stage of the chain on a caller-supplied cf32 input, in reference-sized buffers (stage-isolated parity tests): 1 = FIR,
    2 = Costas loop (+ post-Costas DC blocker / OQPSK delay: what the clock recovery reads), 5 = M&M. Returns the output count. */
 long orc_demod_run_stage(void *h, int stage, const float *in, long nsamples, float *out, long cap)

@@ -31,6 +31,13 @@ typedef struct
     int dc_block;            /* CorrectIQBlock behind the reader (module_demod_base.cpp:113-114) */
     int post_costas_dc;      /* CorrectIQBlock behind the Costas loop (module_psk_demod.cpp:127-134) */
     int clock_recovery;      /* 0 MMClockRecoveryBlock, 1 GardnerClockRecoveryBlock<complex_t> (clock_recovery_gardner.cpp) */
+    /* PMDemodModule (module_pm_demod.cpp:61-88): AGC -> PLLCarrierTrackingBlock -> PMToBPSK -> [SmartResampler -> AGC2] -> RRC -> Costas
+       (order 2, default frequency limit) -> M&M; pll_bw above is then "costas_bw" */
+    int pm;
+    float pm_pll_bw, pm_pll_max_offset;
+    int pm_resample_after_pll;
+    double pm_subcarrier_offset; /* 0 = the symbol rate */
+    double freq_shift;           /* FreqShiftBlock behind the reader / DC blocker (module_demod_base.cpp:122-123); 0 = none */
 } orc_demod_cfg;
 
 typedef struct
@@ -57,6 +64,9 @@ long orc_demod_run(void *h, const void *raw, long nsamples, float *agc_out, floa
                    int8_t *soft_out, long sym_cap);
 void orc_demod_state(void *h, float *out8);
 long orc_demod_last_front(void *h);
+/* pm_demod: where the next orc_demod_run calls dump the PLLCarrierTrackingBlock / PMToBPSK outputs; carrier PLL state + AGC2 gain */
+void orc_demod_pm_dumps(void *h, float *pll_out, float *pm_out);
+void orc_demod_pm_state(void *h, float *out4);
 /* front end alone: conversion (+ iq_swap) + SmartResamplerBlock (rational part) on a fresh resampler; returns output samples */
 long orc_resample(const orc_demod_cfg *cfg, const void *raw, long nsamples, float *out, long cap);
 /* polyphase bank of RationalResamplerBlock(interpolation, decimation): returns taps per arm, *nfilt arms; out[arm*ntaps + k] */
@@ -64,6 +74,18 @@ int orc_resampler_taps(unsigned interpolation, unsigned decimation, float *out, 
 
 /* AGC recurrence in double precision on cf32 input (reference rounding-noise floor, see oracle.c) */
 void orc_agc_exact(const float *in, long n, double rate, double ref, double max_gain, float *out);
+
+/* ---- pm_demod / freq_shift blocks (module_pm_demod.cpp:61-88, module_demod_base.cpp:125-126) */
+float orc_fast_atan2f(float y, float x); /* common/dsp/utils/fast_trig.cpp:80-154 */
+float orc_fast_cos(float x);             /* fast_trig.cpp:158-168 */
+float orc_fast_sin(float x);             /* fast_trig.cpp:170-180 */
+/* PLLCarrierTrackingBlock (common/dsp/pll/pll_carrier_tracking.cpp:8-71) over n cf32 samples; state[2] = {d_phase, d_freq}, in / out */
+void orc_pll_carrier(const float *in, long n, float loop_bw, float max_freq, float min_freq, float *state, float *out);
+/* the VOLK rotator behind FreqShiftBlock / PMToBPSK (freq_shift.cpp:16-50, pm_to_bpsk.cpp:10-35), `call` samples per call;
+   phase[2] in / out (starts at (1, 0)); imag_only: the input is first reduced to (0, imag) as PMToBPSK does (pm_to_bpsk.cpp:24-25) */
+void orc_rotator(const float *in, long n, long call, float inc_re, float inc_im, int imag_only, float *phase, float *out);
+/* phase_delta of FreqShiftBlock::set_freq / PMToBPSK's constructor: (cos, sin)(2 pi freq / samplerate) rounded to float */
+void orc_rotator_inc(double freq, double samplerate, float *inc2);
 
 void *orc_fec_create(const orc_fec_cfg *cfg);
 void orc_fec_destroy(void *h);

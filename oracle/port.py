@@ -33,6 +33,14 @@ def _lib():
         L.ref_demod_run_stage.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_long, C.c_void_p, C.c_long]
         L.ref_demod_last_front.restype = C.c_long
         L.ref_demod_last_front.argtypes = [C.c_void_p]
+        L.ref_demod_pm_dumps.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_demod_pm_state.argtypes = [C.c_void_p, C.c_void_p]
+        L.ref_fast_atan2f.restype = C.c_float
+        L.ref_fast_atan2f.argtypes = [C.c_float, C.c_float]
+        L.ref_fast_cos.restype = C.c_float
+        L.ref_fast_cos.argtypes = [C.c_float]
+        L.ref_fast_sin.restype = C.c_float
+        L.ref_fast_sin.argtypes = [C.c_float]
         L.ref_resample.restype = C.c_long
         L.ref_resample.argtypes = [C.POINTER(_m.DemodCfg), C.c_void_p, C.c_long, C.c_void_p, C.c_long]
         L.ref_resampler_taps.argtypes = [C.c_uint, C.c_uint, C.c_void_p, C.c_int, C.POINTER(C.c_int)]

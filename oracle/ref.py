@@ -20,7 +20,10 @@ class DemodCfg(C.Structure):
                 ("clock_gain_omega", C.c_float), ("clock_mu", C.c_float), ("clock_gain_mu", C.c_float),
                 ("clock_omega_limit", C.c_float), ("costas_max_offset", C.c_float), ("format", C.c_int),
                 ("buffer_size", C.c_int), ("iq_swap", C.c_int), ("final_samplerate", C.c_double), ("dc_block", C.c_int), ("post_costas_dc", C.c_int),
-                ("clock_recovery", C.c_int)]
+                ("clock_recovery", C.c_int),
+                # pm_demod (module_pm_demod.cpp) and the freq_shift option of BaseDemodModule
+                ("pm", C.c_int), ("pm_pll_bw", C.c_float), ("pm_pll_max_offset", C.c_float), ("pm_resample_after_pll", C.c_int),
+                ("pm_subcarrier_offset", C.c_double), ("freq_shift", C.c_double)]
 
 
 class FecCfg(C.Structure):
@@ -75,6 +78,15 @@ def lib():
         L.ref_demod_run_stage.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_long, C.c_void_p, C.c_long]
         L.ref_demod_last_front.restype = C.c_long
         L.ref_demod_last_front.argtypes = [C.c_void_p]
+        L.ref_demod_pm_dumps.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_demod_pm_state.argtypes = [C.c_void_p, C.c_void_p]
+        L.ref_fast_atan2f.restype = C.c_float
+        L.ref_fast_atan2f.argtypes = [C.c_float, C.c_float]
+        L.ref_fast_cos.restype = C.c_float
+        L.ref_fast_cos.argtypes = [C.c_float]
+        L.ref_fast_sin.restype = C.c_float
+        L.ref_fast_sin.argtypes = [C.c_float]
+        L.ref_rotator.argtypes = [C.c_void_p, C.c_long, C.c_long, C.c_double, C.c_double, C.c_void_p]
         L.ref_resample.restype = C.c_long
         L.ref_resample.argtypes = [C.POINTER(DemodCfg), C.c_void_p, C.c_long, C.c_void_p, C.c_long]
         L.ref_resampler_taps.argtypes = [C.c_uint, C.c_uint, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
@@ -106,9 +118,12 @@ def _p(a):
 def demod_cfg(samplerate, symbolrate, constellation, rrc_alpha, pll_bw=0.003, fmt="cs16", rrc_taps=31, agc_rate=1e-2,
               clock_alpha=None, clock_gain_omega=None, clock_mu=0.5, clock_gain_mu=8.7e-3, clock_omega_limit=0.005,
               costas_max_offset=1.0, buffer_size=0, iq_swap=False, final_samplerate=None, min_sps=None, max_sps=None, dc_block=False, post_costas_dc=False,
-              clock_recovery="mm"):
-    """Defaults follow module_psk_demod.h:31-39 and module_demod_base.h:54. final_samplerate=None applies BaseDemodModule::initb's
+              clock_recovery="mm", pm=False, pm_pll_bw=0.01, pm_pll_max_offset=0.5, resample_after_pll=False, subcarrier_offset=0, freq_shift=0.0):
+    """Defaults follow module_psk_demod.h:31-39 and module_demod_base.h:54. pm=True: PMDemodModule's chain (module_pm_demod.cpp:61-88; pll_bw is
+    then its "costas_bw", pm_pll_bw its "pll_bw"; MAX_SPS = 10 unless max_sps is given). final_samplerate=None applies BaseDemodModule::initb's
     rule (resample when samplerate/symbolrate is outside [min_sps, max_sps]); 0 = no resampler."""
+    if pm and max_sps is None:
+        max_sps = 10.0  # module_pm_demod.cpp:56
     if final_samplerate is None:
         final_samplerate = final_samplerate_of(samplerate, symbolrate, constellation, min_sps, max_sps)
         if final_samplerate == float(int(samplerate)):
@@ -120,7 +135,8 @@ def demod_cfg(samplerate, symbolrate, constellation, rrc_alpha, pll_bw=0.003, fm
         clock_gain_omega = float(np.float32(pow(8.7e-3, 2) / 4.0))
     return DemodCfg(float(samplerate), float(symbolrate), CONST[constellation], rrc_alpha, rrc_taps, pll_bw, agc_rate,
                     float(clock_gain_omega), clock_mu, float(clock_gain_mu), clock_omega_limit, costas_max_offset, FMT[fmt],
-                    buffer_size, int(iq_swap), float(final_samplerate), int(dc_block), int(post_costas_dc), {"mm": 0, "gardner": 1}[clock_recovery])
+                    buffer_size, int(iq_swap), float(final_samplerate), int(dc_block), int(post_costas_dc), {"mm": 0, "gardner": 1}[clock_recovery],
+                    int(pm), pm_pll_bw, pm_pll_max_offset, int(resample_after_pll), float(subcarrier_offset), float(freq_shift))
 
 
 def final_samplerate_of(samplerate, symbolrate, constellation, min_sps=None, max_sps=None, custom=None):
@@ -200,7 +216,13 @@ class Demod:
         ratio = self.cfg.final_samplerate / self.cfg.samplerate if self.cfg.final_samplerate > 0 else 1.0
         nf = int(n * ratio) + 64  # samples after the front-end resampler (upper bound)
         cap = int(nf / max(1.0, self.sps) * 1.1) + 64
-        agc = np.zeros(nf, np.complex64) if stages else None
+        pm_after = bool(self.cfg.pm and self.cfg.pm_resample_after_pll)
+        na = n + 64 if pm_after else nf  # pm_demod with resample_after_pll: AGC / PLL / PMToBPSK run at the input rate
+        pll = pmo = None
+        if self.cfg.pm and stages:
+            pll, pmo = np.zeros(na, np.complex64), np.zeros(na, np.complex64)
+            lib().ref_demod_pm_dumps(self.h, _p(pll), _p(pmo))
+        agc = np.zeros(na, np.complex64) if stages else None
         fir = np.zeros(nf, np.complex64) if stages else None
         cos = np.zeros(nf, np.complex64) if (stages and self.cfg.constellation != 4) else None
         mm = np.zeros(cap, np.complex64)
@@ -208,7 +230,24 @@ class Demod:
         ns = lib().ref_demod_run(self.h, _p(raw), n, _p(agc), _p(fir), _p(cos), _p(mm), _p(soft), cap)
         front = lib().ref_demod_last_front(self.h)
         cut = (lambda a: None if a is None else a[:front])
+        if self.cfg.pm:
+            lib().ref_demod_pm_dumps(self.h, None, None)
+            cin = (lambda a: None if a is None else a[:n if pm_after else front])
+            return dict(agc=cin(agc), pll=cin(pll), pm=cin(pmo), fir=cut(fir), costas=cut(cos), mm=mm[:ns].copy(), soft=soft[:ns].copy(), front=front)
         return dict(agc=cut(agc), fir=cut(fir), costas=cut(cos), mm=mm[:ns].copy(), soft=soft[:ns * bps].copy(), front=front)
+
+    def pm_state(self):
+        out = np.zeros(4, np.float32)
+        lib().ref_demod_pm_state(self.h, _p(out))
+        return dict(pll_phase=out[0], pll_freq=out[1], agc2_gain=out[2])
+
+
+def rotator(x, inc, call=8192):
+    """The VOLK rotator (oracle/shim restatement of the generic flavour) as FreqShiftBlock / PMToBPSK call it, in `call`-sample calls."""
+    x = np.ascontiguousarray(x, np.complex64)
+    out = np.zeros_like(x)
+    lib().ref_rotator(_p(x), x.size, call, float(np.real(inc)), float(np.imag(inc)), _p(out))
+    return out
 
 
 def run_stage(cfg, which, x):

@@ -9,6 +9,7 @@
  * Wiring mirrors (reference file:line):
  *   BaseDemodModule::initb            src-core/pipeline/modules/demod/module_demod_base.cpp:59-208
  *   PSKDemodModule::init / process    src-core/pipeline/modules/demod/module_psk_demod.cpp:86-236
+ *   PMDemodModule::init / process     src-core/pipeline/modules/demod/module_pm_demod.cpp:61-160
  *   DVBS2DemodModule front half       plugins/dvb_support/dvbs2/module_dvbs2_demod.cpp:98-102
  *   MetOpAHRPTDecoderModule::process  plugins/noaa_metop_support/metop/module_metop_ahrpt_decoder.cpp:34-90
  *   CCSDSConvConcatDecoderModule      src-core/pipeline/modules/ccsds/module_ccsds_conv_concat_decoder.cpp:16-200
@@ -50,6 +51,10 @@
 #include "common/dsp/clock_recovery/clock_recovery_gardner.h"
 #include "common/dsp/resamp/smart_resampler.h"
 #include "common/dsp/resamp/rational_resampler.h"
+#include "common/dsp/pll/pll_carrier_tracking.h"
+#include "common/dsp/demod/pm_to_bpsk.h"
+#include "common/dsp/utils/freq_shift.h"
+#include "common/dsp/utils/fast_trig.h"
 #undef private
 #undef protected
 #include "common/dsp/resamp/polyphase_bank.h"
@@ -103,6 +108,14 @@ extern "C"
         int post_costas_dc;      /* CorrectIQBlock behind the Costas loop (module_psk_demod.cpp:127-134) */
         int clock_recovery;      /* 0: MMClockRecoveryBlock (psk_demod); 1: dsp::GardnerClockRecoveryBlock<complex_t> with the same arguments
                                     (common/dsp/clock_recovery/clock_recovery_gardner.cpp) */
+        /* PMDemodModule (module_pm_demod.cpp:61-88): AGC -> PLLCarrierTrackingBlock -> PMToBPSK -> [SmartResampler -> AGC2] -> RRC ->
+           Costas(order 2, default frequency limit) -> M&M. `pll_bw` above is then "costas_bw"; constellation must be 0 (bpsk) */
+        int pm;
+        float pm_pll_bw;          /* "pll_bw" */
+        float pm_pll_max_offset;  /* "pll_max_offset" (module_pm_demod.h default) */
+        int pm_resample_after_pll;
+        double pm_subcarrier_offset; /* "subcarrier_offset": 0 = the symbol rate (module_pm_demod.cpp:67) */
+        double freq_shift;        /* "freq_shift": FreqShiftBlock behind the reader / DC blocker (module_demod_base.cpp:125-126); 0 = none */
     } ref_demod_cfg;
 
     typedef struct
@@ -144,6 +157,17 @@ namespace
         std::shared_ptr<dsp::GardnerClockRecoveryBlock<complex_t>> rec_g;
         std::vector<float> rrc_taps;
         long last_front = 0; /* samples that entered the AGC in the last ref_demod_run call */
+        /* pm_demod */
+        std::shared_ptr<dsp::PLLCarrierTrackingBlock> cpll;
+        std::shared_ptr<dsp::PMToBPSK> pm_psk;
+        std::shared_ptr<dsp::SmartResamplerBlock<complex_t>> resampler2;
+        std::shared_ptr<dsp::stream<complex_t>> mid;
+        std::shared_ptr<dsp::AGCBlock<complex_t>> agc2;
+        long pm_pos = 0;
+        float *pll_dump = nullptr, *pm_dump = nullptr; /* optional dumps of the PLL / PMToBPSK outputs (input-rate sample positions) */
+        /* freq_shift */
+        std::shared_ptr<dsp::stream<complex_t>> fs_in;
+        std::shared_ptr<dsp::FreqShiftBlock> fshift;
     };
 
     int8_t soft_clamp(float x) /* module_demod_base.h:106-113 semantics */
@@ -173,15 +197,23 @@ namespace
     void front_block(RefDemod *d, const void *raw, long off, int n, complex_t *dst)
     {
         if (!d->dc)
-        {
             convert_block(d->cfg, raw, off, n, dst);
-            return;
+        else
+        {
+            convert_block(d->cfg, raw, off, n, d->dc_in->writeBuf);
+            d->dc_in->swap(n);
+            d->dc->work();
+            memcpy(dst, d->dc->output_stream->readBuf, n * sizeof(complex_t));
+            d->dc->output_stream->flush();
         }
-        convert_block(d->cfg, raw, off, n, d->dc_in->writeBuf);
-        d->dc_in->swap(n);
-        d->dc->work();
-        memcpy(dst, d->dc->output_stream->readBuf, n * sizeof(complex_t));
-        d->dc->output_stream->flush();
+        if (d->fshift) /* module_demod_base.cpp:125-126: behind the DC blocker, in front of the resampler */
+        {
+            memcpy(d->fs_in->writeBuf, dst, n * sizeof(complex_t));
+            d->fs_in->swap(n);
+            d->fshift->work();
+            memcpy(dst, d->fshift->output_stream->readBuf, n * sizeof(complex_t));
+            d->fshift->output_stream->flush();
+        }
     }
 
     struct RefFec
@@ -238,21 +270,49 @@ extern "C"
             d->dc_in = std::make_shared<dsp::stream<complex_t>>();
             d->dc = std::make_shared<dsp::CorrectIQBlock<complex_t>>(d->dc_in);
         }
-        if (c->final_samplerate > 0 && (long)c->final_samplerate != samplerate)
+        if (c->freq_shift != 0)
+        {
+            d->fs_in = std::make_shared<dsp::stream<complex_t>>();
+            d->fshift = std::make_shared<dsp::FreqShiftBlock>(d->fs_in, (double)samplerate, c->freq_shift);
+        }
+        const bool resample = c->final_samplerate > 0 && (long)c->final_samplerate != samplerate;
+        if (resample)
         {
             /* module_demod_base.cpp:84-87,203-204: buffer scaled by ceil(decimation factor), resampler (final, input) */
             float decimation_factor = samplerate / d->final_samplerate;
             d->buffer_size *= ceil(decimation_factor);
             if (d->buffer_size > 8192 * 20)
                 d->buffer_size = 8192 * 20;
-            d->resampler = std::make_shared<dsp::SmartResamplerBlock<complex_t>>(nullptr, d->final_samplerate, samplerate);
+            if (!(c->pm && c->pm_resample_after_pll)) /* initb(!d_resample_after_pll), module_pm_demod.cpp:63 */
+                d->resampler = std::make_shared<dsp::SmartResamplerBlock<complex_t>>(nullptr, d->final_samplerate, samplerate);
             d->rs_in.resize(d->buffer_size);
         }
         d->agc = std::make_shared<dsp::AGCBlock<complex_t>>(d->in, c->agc_rate, 1.0f, 1.0f, 65536);
         d->rrc_taps = dsp::firdes::root_raised_cosine(1, d->final_samplerate, (int)symbolrate, c->rrc_alpha, c->rrc_taps);
-        d->rrc = std::make_shared<dsp::FIRBlock<complex_t>>(d->agc->output_stream, d->rrc_taps);
+        std::shared_ptr<dsp::stream<complex_t>> rrc_in = d->agc->output_stream;
+        if (c->pm)
+        {
+            /* module_pm_demod.cpp:65-80 */
+            d->cpll = std::make_shared<dsp::PLLCarrierTrackingBlock>(d->agc->output_stream, c->pm_pll_bw, c->pm_pll_max_offset, -c->pm_pll_max_offset);
+            d->pm_psk = std::make_shared<dsp::PMToBPSK>(d->cpll->output_stream, c->pm_resample_after_pll ? (float)samplerate : d->final_samplerate,
+                                                       (unsigned long)c->pm_subcarrier_offset == 0 ? (float)symbolrate : (float)(unsigned long)c->pm_subcarrier_offset);
+            rrc_in = d->pm_psk->output_stream;
+            if (c->pm_resample_after_pll)
+            {
+                d->resampler2 = std::make_shared<dsp::SmartResamplerBlock<complex_t>>(nullptr, d->final_samplerate, samplerate);
+                d->mid = std::make_shared<dsp::stream<complex_t>>();
+                d->agc2 = std::make_shared<dsp::AGCBlock<complex_t>>(d->mid, 0.001, 1.0, 1.0, 1000.0);
+                rrc_in = d->agc2->output_stream;
+            }
+        }
+        d->rrc = std::make_shared<dsp::FIRBlock<complex_t>>(rrc_in, d->rrc_taps);
         std::shared_ptr<dsp::stream<complex_t>> last = d->rrc->output_stream;
-        if (c->constellation != 4)
+        if (c->pm) /* module_pm_demod.cpp:84: CostasLoopBlock(rrc->output_stream, d_loop_bw, 2) */
+        {
+            d->pll = std::make_shared<dsp::CostasLoopBlock>(last, c->pll_bw, 2);
+            last = d->pll->output_stream;
+        }
+        else if (c->constellation != 4)
         {
             int order = c->constellation == 0 ? 2 : (c->constellation == 3 ? 8 : 4);
             d->pll = std::make_shared<dsp::CostasLoopBlock>(last, c->pll_bw, order, c->costas_max_offset);
@@ -321,6 +381,7 @@ extern "C"
     {
         RefDemod *d = (RefDemod *)h;
         long nsym = 0, pos = 0; /* pos: samples after the (optional) resampler so far in this call */
+        d->pm_pos = 0;          /* pm_demod: samples through the carrier PLL so far in this call (the AGC / PLL / PMToBPSK dumps' position) */
         for (long off = 0; off < nsamples; off += d->buffer_size)
         {
             int n = (int)std::min<long>(d->buffer_size, nsamples - off);
@@ -336,7 +397,27 @@ extern "C"
             d->in->swap(n);
             d->agc->work();
             if (agc_out)
-                memcpy(agc_out + pos * 2, d->agc->output_stream->readBuf, n * sizeof(complex_t));
+                memcpy(agc_out + (d->cpll ? d->pm_pos : pos) * 2, d->agc->output_stream->readBuf, n * sizeof(complex_t));
+            if (d->cpll)
+            {
+                d->cpll->work();
+                if (d->pll_dump)
+                    memcpy(d->pll_dump + d->pm_pos * 2, d->cpll->output_stream->readBuf, n * sizeof(complex_t));
+                d->pm_psk->work();
+                if (d->pm_dump)
+                    memcpy(d->pm_dump + d->pm_pos * 2, d->pm_psk->output_stream->readBuf, n * sizeof(complex_t));
+                d->pm_pos += n;
+                if (d->resampler2)
+                {
+                    int m = d->resampler2->process(d->pm_psk->output_stream->readBuf, n, d->mid->writeBuf);
+                    d->pm_psk->output_stream->flush();
+                    n = m;
+                    if (n <= 0)
+                        continue;
+                    d->mid->swap(n);
+                    d->agc2->work();
+                }
+            }
             d->rrc->work();
             if (fir_out)
                 memcpy(fir_out + pos * 2, d->rrc->output_stream->readBuf, n * sizeof(complex_t));
@@ -362,7 +443,10 @@ extern "C"
                 memcpy(mm_out + nsym * 2, sym, m * sizeof(complex_t));
             if (soft_out)
             {
-                if (d->cfg.constellation == 0) /* module_psk_demod.cpp:199-205 */
+                if (d->cfg.pm) /* module_pm_demod.cpp:141-144 */
+                    for (int i = 0; i < m; i++)
+                        soft_out[nsym + i] = soft_clamp(sym[i].real * 100);
+                else if (d->cfg.constellation == 0) /* module_psk_demod.cpp:199-205 */
                     for (int i = 0; i < m; i++)
                         soft_out[nsym + i] = soft_clamp(sym[i].real * 50);
                 else /* module_psk_demod.cpp:207-213 */
@@ -379,6 +463,35 @@ extern "C"
         return nsym;
     }
     long ref_demod_last_front(void *h) { return ((RefDemod *)h)->last_front; }
+    /* pm_demod: where the next ref_demod_run calls dump the PLLCarrierTrackingBlock / PMToBPSK outputs (position restarts at 0) */
+    void ref_demod_pm_dumps(void *h, float *pll_out, float *pm_out)
+    {
+        RefDemod *d = (RefDemod *)h;
+        d->pll_dump = pll_out;
+        d->pm_dump = pm_out;
+    }
+    /* pm_demod loop state: out[0..1] = carrier PLL phase / frequency (pll_carrier_tracking.h: d_phase, d_freq), out[2] = AGC2 gain */
+    void ref_demod_pm_state(void *h, float *out4)
+    {
+        RefDemod *d = (RefDemod *)h;
+        out4[0] = d->cpll ? d->cpll->d_phase : 0;
+        out4[1] = d->cpll ? d->cpll->d_freq : 0;
+        out4[2] = d->agc2 ? d->agc2->gain : 0;
+        out4[3] = 0;
+    }
+    float ref_fast_atan2f(float y, float x) { return dsp::fast_atan2f(y, x); }
+    float ref_fast_cos(float x) { return dsp::fast_cos(x); }
+    float ref_fast_sin(float x) { return dsp::fast_sin(x); }
+    /* the VOLK rotator as the shim restates it (and as FreqShiftBlock / PMToBPSK call it), on `call`-sample calls */
+    void ref_rotator(const float *in, long n, long call, double inc_re, double inc_im, float *out)
+    {
+        lv_32fc_t phase(1, 0), inc((float)inc_re, (float)inc_im);
+        for (long pos = 0; pos < n; pos += call)
+        {
+            long m = std::min(call, n - pos);
+            volk_32fc_s32fc_x2_rotator_32fc((lv_32fc_t *)out + pos, (const lv_32fc_t *)in + pos, inc, &phase, (unsigned)m);
+        }
+    }
 
     /* The front end alone: conversion (+ iq_swap) and SmartResamplerBlock, in reference-sized buffers on a fresh resampler.
        Returns the number of output samples (<= cap). */

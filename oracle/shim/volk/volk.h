@@ -67,6 +67,51 @@ static inline void volk_32i_s32f_convert_32f_u(float *out, const int32_t *in, co
     for (unsigned int k = 0; k < num_points; k++) out[k] = ((float)in[k]) / scalar;
 }
 
+/* Rotator (freq_shift.cpp:26-30, pm_to_bpsk.cpp:27-31): out[k] = in[k] * phase; phase *= phase_inc. VOLK (not vendored by the reference;
+ * 2.x / 3.x generic flavour as published) brings the phasor back to unit length after every 512 samples of a call and once more at the
+ * end of a call whose length is not a multiple of 512. Plain float arithmetic: (a + jb)(c + jd) = (ac - bd) + j(ad + bc), one rounding
+ * per operation. The rounding walk of the phasor's angle depends on the VOLK flavour (the SIMD ones advance several samples at once),
+ * so downstream comparisons against this restatement carry a tolerance (tests/floors.py measures it). */
+#include <math.h>
+static inline void b200_shim_rotate(float *out, const float *in, float inc_re, float inc_im, float *phase /* [2] */, unsigned int num_points)
+{
+    float pr = phase[0], pi = phase[1];
+    unsigned int k = 0, since = 0;
+    for (k = 0; k < num_points; k++) {
+        const float a = in[2 * k], b = in[2 * k + 1];
+        out[2 * k] = a * pr - b * pi;
+        out[2 * k + 1] = a * pi + b * pr;
+        const float nr = pr * inc_re - pi * inc_im, ni = pr * inc_im + pi * inc_re;
+        pr = nr;
+        pi = ni;
+        if (++since == 512) {
+            const float m = hypotf(pr, pi);
+            pr /= m;
+            pi /= m;
+            since = 0;
+        }
+    }
+    if (since) {
+        const float m = hypotf(pr, pi);
+        pr /= m;
+        pi /= m;
+    }
+    phase[0] = pr;
+    phase[1] = pi;
+}
+#ifdef __cplusplus
+} /* (the two entry points take a C++ complex by value) */
+static inline void volk_32fc_s32fc_x2_rotator_32fc(lv_32fc_t *out, const lv_32fc_t *in, const lv_32fc_t phase_inc, lv_32fc_t *phase, unsigned int num_points)
+{
+    b200_shim_rotate((float *)out, (const float *)in, phase_inc.real(), phase_inc.imag(), (float *)phase, num_points);
+}
+static inline void volk_32fc_s32fc_x2_rotator2_32fc(lv_32fc_t *out, const lv_32fc_t *in, const lv_32fc_t *phase_inc, lv_32fc_t *phase, unsigned int num_points)
+{
+    b200_shim_rotate((float *)out, (const float *)in, phase_inc->real(), phase_inc->imag(), (float *)phase, num_points);
+}
+extern "C" {
+#endif
+
 /* Kernel-description query used by CCDecoder to pick an ACS kernel. We advertise only
  * "generic", so the decoder keeps the reference's own vendored fixed kernel. */
 typedef struct volk_func_desc {

@@ -6,7 +6,7 @@
 //
 //   loader()                          the one symbol SatDump dlsym()s (core/plugin.cpp:15-33)
 //   B200DSPSupport::init()            on SatDumpStartedEvent (fired after every plugin registered its modules, init.cpp:163) the
-//                                     entries "psk_demod", "metop_ahrpt_decoder", "ccsds_conv_concat_decoder" and "ccsds_simple_psk_decoder" of
+//                                     entries "psk_demod", "pm_demod", "metop_ahrpt_decoder", "ccsds_conv_concat_decoder" and "ccsds_simple_psk_decoder" of
 //                                     satdump::pipeline::modules_registry (module.h:210, looked up first-match by id, module.cpp:129-135)
 //                                     get their factory replaced, so existing pipelines instantiate the CUDA modules.
 //                                     Set B200_DSP_REGISTER_ONLY=1 to register "<id>_b200" ids instead and leave the originals alone.
@@ -157,13 +157,15 @@ namespace b200plugin
 
     struct PskDemod : WrappedModule<b200host::PskDemodStage>
     {
-        PskDemod(std::string in, std::string hint, nlohmann::json p)
-            : WrappedModule("psk_demod", make(in, hint, p), in, hint, p) {}
-        static std::shared_ptr<b200host::PskDemodStage> make(std::string in, std::string hint, const nlohmann::json &p)
+        // module_id "psk_demod" (PSKDemodModule) or "pm_demod" (PMDemodModule, module_pm_demod.cpp): same BaseDemodModule data planes and
+        // stats keys (progress, snr, peak_snr, freq)
+        PskDemod(std::string module_id, std::string in, std::string hint, nlohmann::json p)
+            : WrappedModule(module_id, make(module_id, in, hint, p), in, hint, p) {}
+        static std::shared_ptr<b200host::PskDemodStage> make(const std::string &module_id, std::string in, std::string hint, const nlohmann::json &p)
         {
             try
             {
-                return std::make_shared<b200host::PskDemodStage>(in, hint, to_params(p));
+                return std::make_shared<b200host::PskDemodStage>(in, hint, to_params(p), module_id);
             }
             catch (const b200host::ModuleError &e)
             {
@@ -237,21 +239,21 @@ public:
     using Factory = std::function<std::shared_ptr<satdump::pipeline::ProcessingModule>(std::string, std::string, nlohmann::json)>;
     static Factory factory(const std::string &id)
     {
-        if (id == "psk_demod")
-            return [](std::string in, std::string hint, nlohmann::json p) { return std::make_shared<b200plugin::PskDemod>(in, hint, p); };
+        if (id == "psk_demod" || id == "pm_demod")
+            return [id](std::string in, std::string hint, nlohmann::json p) { return std::make_shared<b200plugin::PskDemod>(id, in, hint, p); };
         return [id](std::string in, std::string hint, nlohmann::json p) { return std::make_shared<b200plugin::Decoder>(id, in, hint, p); };
     }
 
     static void registerHandler(const satdump::pipeline::RegisterModulesEvent &evt)
     {
-        for (const char *id : {"psk_demod", "metop_ahrpt_decoder", "ccsds_conv_concat_decoder", "ccsds_simple_psk_decoder"})
+        for (const char *id : {"psk_demod", "pm_demod", "metop_ahrpt_decoder", "ccsds_conv_concat_decoder", "ccsds_simple_psk_decoder"})
             evt.modules_registry.push_back({std::string(id) + "_b200", nlohmann::json(), factory(id)});
     }
 
     static void patchHandler(const satdump::SatDumpStartedEvent &)
     {
         for (auto &e : satdump::pipeline::modules_registry)
-            if (e.id == "psk_demod" || e.id == "metop_ahrpt_decoder" || e.id == "ccsds_conv_concat_decoder" || e.id == "ccsds_simple_psk_decoder")
+            if (e.id == "psk_demod" || e.id == "pm_demod" || e.id == "metop_ahrpt_decoder" || e.id == "ccsds_conv_concat_decoder" || e.id == "ccsds_simple_psk_decoder")
             {
                 e.inst = factory(e.id);
                 logger->info("b200_dsp_support: module " + e.id + " now runs on the B200 path");

@@ -36,7 +36,9 @@ class DemodCfg(C.Structure):
                 ("clock_mu", C.c_float), ("clock_gain_mu", C.c_float), ("clock_omega_limit", C.c_float),
                 ("costas_max_offset", C.c_float), ("format", C.c_int), ("device", C.c_int), ("max_batch", C.c_long),
                 ("keep_stages", C.c_int), ("iq_swap", C.c_int), ("final_samplerate", C.c_double), ("dc_block", C.c_int), ("post_costas_dc", C.c_int),
-                ("front_resample", C.c_int), ("clock_recovery", C.c_int)]
+                ("front_resample", C.c_int), ("clock_recovery", C.c_int),
+                ("pm_demod", C.c_int), ("pm_pll_bw", C.c_float), ("pm_pll_max_offset", C.c_float), ("pm_resample_after_pll", C.c_int),
+                ("pm_subcarrier_offset", C.c_double), ("freq_shift", C.c_double)]
 
 
 class FecCfg(C.Structure):
@@ -51,7 +53,8 @@ class DemodStats(C.Structure):
     _fields_ = [("samples_in", C.c_long), ("symbols_out", C.c_long), ("agc_gain", C.c_float), ("costas_phase", C.c_float),
                 ("costas_freq", C.c_float), ("mm_mu", C.c_float), ("mm_omega", C.c_float), ("costas_unconverged", C.c_long),
                 ("mm_unconverged", C.c_long), ("agc_clamped", C.c_int), ("repairs", C.c_int), ("kernel_launches", C.c_long),
-                ("agc_exact_passes", C.c_long), ("last_front_samples", C.c_long), ("snr", C.c_float), ("peak_snr", C.c_float)]
+                ("agc_exact_passes", C.c_long), ("last_front_samples", C.c_long), ("snr", C.c_float), ("peak_snr", C.c_float),
+                ("pll_freq", C.c_float), ("pll_unconverged", C.c_long)]
 
 
 class FecStats(C.Structure):
@@ -139,9 +142,13 @@ def _chk(rc):
 def demod_cfg(samplerate, symbolrate, constellation, rrc_alpha, pll_bw=0.003, fmt="cs16", rrc_taps=31, agc_rate=1e-2, clock_alpha=None,
               clock_gain_omega=None, clock_mu=0.5, clock_gain_mu=8.7e-3, clock_omega_limit=0.005, costas_max_offset=1.0, device=0,
               max_batch=1 << 24, keep_stages=False, iq_swap=False, final_samplerate=None, min_sps=0.0, max_sps=0.0, dc_block=False, post_costas_dc=False,
-              front_resample=0, clock_recovery="mm"):
+              front_resample=0, clock_recovery="mm", pm=False, pm_pll_bw=0.01, pm_pll_max_offset=0.5, resample_after_pll=False, subcarrier_offset=0,
+              freq_shift=0.0):
     """Parameter defaults = module_psk_demod.h:31-39, module_demod_base.h:54. final_samplerate=None applies BaseDemodModule::initb's
-    rule (resample when samplerate/symbolrate is outside [min_sps, max_sps]); 0 forces "no resampler"."""
+    rule (resample when samplerate/symbolrate is outside [min_sps, max_sps]); 0 forces "no resampler". pm=True: pm_demod's chain
+    (module_pm_demod.cpp; pll_bw is then its "costas_bw", pm_pll_bw its "pll_bw", MAX_SPS = 10)."""
+    if pm and not max_sps:
+        max_sps = 10.0  # module_pm_demod.cpp:56
     if final_samplerate is None:
         final_samplerate = final_samplerate_of(samplerate, symbolrate, constellation, min_sps, max_sps)
         if final_samplerate == float(int(samplerate)):
@@ -153,7 +160,8 @@ def demod_cfg(samplerate, symbolrate, constellation, rrc_alpha, pll_bw=0.003, fm
         clock_gain_omega = float(np.float32(pow(8.7e-3, 2) / 4.0))
     return DemodCfg(float(samplerate), float(symbolrate), CONST[constellation], rrc_alpha, rrc_taps, pll_bw, agc_rate, clock_gain_omega,
                     clock_mu, clock_gain_mu, clock_omega_limit, costas_max_offset, FMT[fmt], device, max_batch, int(keep_stages), int(iq_swap),
-                    float(final_samplerate), int(dc_block), int(post_costas_dc), int(front_resample), {"mm": 0, "gardner": 1}[clock_recovery])
+                    float(final_samplerate), int(dc_block), int(post_costas_dc), int(front_resample), {"mm": 0, "gardner": 1}[clock_recovery],
+                    int(pm), pm_pll_bw, pm_pll_max_offset, int(resample_after_pll), float(subcarrier_offset), float(freq_shift))
 
 
 def resampler_bank(samplerate, final_samplerate):
@@ -229,6 +237,7 @@ class Demod:
         if not self.h:
             raise B200Error(-1 if "device" not in last_error().lower() else -2, last_error())
         self.bps = 1 if cfg.constellation == 0 else 2
+        self.pm = bool(cfg.pm_demod)
 
     def close(self):
         if getattr(self, "h", None):
@@ -289,8 +298,10 @@ class Demod:
     def stage(self, which):
         """agc / fir / costas stage outputs, or resamp = what entered the AGC when the front-end resampler / iq_swap runs."""
         n = self._n if which == "dc" else self.stats()["last_front_samples"]
+        if self.pm and self.cfg.pm_resample_after_pll and which in ("agc", "pll", "pm"):
+            n = self._n  # pm_demod with resample_after_pll: the first AGC, the carrier PLL and PMToBPSK run at the input rate
         out = np.zeros(n, np.complex64)
-        _chk(lib().b200_demod_debug_stage(self.h, {"agc": 0, "fir": 1, "costas": 2, "resamp": 3, "dc": 4}[which], out.ctypes.data, n))
+        _chk(lib().b200_demod_debug_stage(self.h, {"agc": 0, "fir": 1, "costas": 2, "resamp": 3, "dc": 4, "pll": 6, "pm": 7}[which], out.ctypes.data, n))
         return out
 
     def run_stage(self, which, x, strict=False, sequential=False):
@@ -298,7 +309,7 @@ class Demod:
         x = np.ascontiguousarray(x, np.complex64)
         out = np.zeros(x.size + 1024, np.complex64)
         n = C.c_long(0)
-        _chk(lib().b200_demod_debug_run_stage(self.h, {"fir": 1, "costas": 2, "mm": 5}[which], x.ctypes.data, x.size,
+        _chk(lib().b200_demod_debug_run_stage(self.h, {"fir": 1, "costas": 2, "mm": 5, "pll": 6, "pm": 7}[which], x.ctypes.data, x.size,
                                               (1 if strict else 0) | (2 if sequential else 0), out.ctypes.data, out.size, C.byref(n)))
         return out[:n.value].copy()
 

@@ -193,7 +193,17 @@ Demod::Demod(const b200_demod_cfg &c) : cfg(c)
     sps = final_fs / (float)rs;
     // the loops are built for the reference's working window (module_demod_base.h:71-72, module_psk_demod.cpp:65-70); outside it
     // the reference resamples first: pass final_samplerate = b200_demod_final_samplerate(...)
-    const float lo = c.constellation == B200_OQPSK ? 1.6f : 1.1f, hi = c.constellation == B200_OQPSK ? 2.4f : 4.0f;
+    pm = c.pm_demod != 0;
+    pm_after = pm && c.pm_resample_after_pll != 0;
+    if (pm) {
+        // PMDemodModule (module_pm_demod.cpp:12-88): BPSK behind a carrier PLL; its Costas loop is order 2 with the default frequency limit
+        B200_REQUIRE(c.constellation == B200_BPSK, B200_EINVAL, "pm_demod recovers BPSK: constellation must be bpsk");
+        B200_REQUIRE(c.pm_pll_bw > 0 && c.pm_pll_bw < 0.5f && c.pm_pll_max_offset > 0, B200_EINVAL, "pm_demod: pll_bw / pll_max_offset out of range");
+        B200_REQUIRE(!c.post_costas_dc && c.clock_recovery == 0, B200_EINVAL, "pm_demod has no post-Costas DC blocker and uses the M&M clock recovery");
+        cfg.costas_max_offset = 1.0f; // CostasLoopBlock(rrc->output_stream, d_loop_bw, 2): freq_limit defaults to 1.0 (costas_loop.h:27)
+    }
+    // MAX_SPS = 10 for pm_demod ("we do NOT want to resample unless really necessary", module_pm_demod.cpp:56)
+    const float lo = c.constellation == B200_OQPSK ? 1.6f : 1.1f, hi = pm ? 10.0f : (c.constellation == B200_OQPSK ? 2.4f : 4.0f);
     B200_REQUIRE(sps >= lo * 0.999f && sps <= hi * 1.001f, B200_EINVAL,
                  "samples per symbol %.4f outside [%.1f, %.1f]: set final_samplerate (b200_demod_final_samplerate) so that the front-end resampler runs", sps, lo,
                  hi);
@@ -239,20 +249,50 @@ Demod::Demod(const b200_demod_cfg &c) : cfg(c)
             rs_nt = design_resampler_bank(I, D, rs_bank);
             B200_REQUIRE(rs_nt <= RS_MAX_TAPS, B200_EUNSUPPORTED, "resampler arm of %d taps exceeds the built maximum %d", rs_nt, RS_MAX_TAPS);
             resamp = true;
-        } else if (c.iq_swap && decim.empty()) {
+        } else if (c.iq_swap && decim.empty() && !pm_after) {
             rs_bank.assign(1, 1.0f);
             resamp = true;
         }
-    } else if (c.iq_swap) { // the plain swap runs as the identity resampler
+    } else if (c.iq_swap && !pm_after) { // the plain swap runs as the identity resampler
         rs_bank.assign(1, 1.0f);
         resamp = true;
     }
     check_device(c.device);
     DeviceGuard g(c.device);
     bps = c.constellation == B200_BPSK ? 1 : 2;
+    {
+        // phasor steps of the two rotators as fractions of a turn (0.64 fixed point): the angle of the FLOAT pair (cos, sin)(2 pi f / fs)
+        // the reference multiplies by (freq_shift.cpp:44-45, pm_to_bpsk.cpp:12)
+        auto turn_step = [](double freq, double rate) -> unsigned long long {
+            const double w = 2.0 * M_PI * (freq / rate); // hz_to_rad (common/dsp/block.cpp:17)
+            const float ir = (float)cos(w), ii = (float)sin(w);
+            long double a = atan2l((long double)ii, (long double)ir) / (2.0L * 3.14159265358979323846264338327950288L);
+            if (a < 0)
+                a += 1.0L;
+            const long double v = a * 18446744073709551616.0L;
+            return v >= 18446744073709551615.0L ? 0ull : (unsigned long long)v;
+        };
+        if (pm) {
+            // PMToBPSK(pll out, d_resample_after_pll ? d_samplerate : final_samplerate, subcarrier_offset == 0 ? d_symbolrate : subcarrier_offset),
+            // float arguments, shifting DOWN by that frequency (module_pm_demod.cpp:67, pm_to_bpsk.cpp:10-13)
+            const float rate = pm_after ? (float)fs : final_fs;
+            const unsigned long sub = (unsigned long)c.pm_subcarrier_offset;
+            const float f = sub == 0 ? (float)rs : (float)sub;
+            pm_dturn = turn_step(-(double)f, (double)rate);
+        }
+        if (c.freq_shift != 0) // FreqShiftBlock(input, d_samplerate, d_frequency_shift): long parameters (module_demod_base.h:56, .cpp:122-123)
+            fs_dturn = turn_step((double)(long)c.freq_shift, (double)fs);
+    }
     order = c.constellation == B200_BPSK ? 2 : (c.constellation == B200_8PSK ? 8 : (c.constellation == B200_NONE ? 0 : 4));
     max_batch = c.max_batch;
     max_work = resamp ? std::max<long>(max_batch, (long)((double)max_batch * rs_I / rs_D) + 64) : max_batch; // (a decimator in front only shrinks it)
+    if (pm) {
+        // carrier PLL warm-up: the loop is linear (its detector is the input's own phase minus the loop phase), two copies approach each
+        // other like exp(-n * bw * 1.5): 24 / bw samples bring any start state below float resolution of the phase
+        Wp = round_up16(24.0 / c.pm_pll_bw);
+        if (const char *e = getenv("B200_PLL_WARMUP_SCALE")) // tuning hook
+            Wp = round_up16(Wp * atof(e));
+    }
     design_rrc(1, final_fs, (double)(int)rs, c.rrc_alpha, c.rrc_taps, rrc);
     design_mm_bank(bank);
     // Costas warm-up: 24 loop time constants for orders 2/4; the order-8 detector has about a third of the gain (measured on the
@@ -372,6 +412,26 @@ Demod::Demod(const b200_demod_cfg &c) : cfg(c)
     }
     if (cfg.dc_block)
         dc_out.alloc(max_batch + 64);
+    if (cfg.freq_shift != 0)
+        fs_out.alloc(max_batch + 64);
+    if (pm) {
+        const long npm = std::max(max_batch, max_work) + 64;
+        pm_agc.alloc(npm);
+        pm_pll.alloc(npm);
+        pm_out.alloc(npm);
+        // fast_atan2f's table (fast_trig.cpp:16-61): the arctangent of k / 255 through seven significant digits, entry 256 = entry 255
+        std::vector<float> tab(260, 0.f);
+        char buf[40];
+        for (int k = 0; k < 256; k++) {
+            snprintf(buf, sizeof buf, "%.6e", atan((double)k / 255.0));
+            tab[k] = (float)strtod(buf, nullptr);
+        }
+        tab[256] = tab[255];
+        d_atan_tab.alloc(260);
+        B200_CUDA(cudaMemcpyAsync(d_atan_tab.p, tab.data(), 260 * sizeof(float), cudaMemcpyHostToDevice, stream));
+        B200_CUDA(cudaStreamSynchronize(stream)); // (tab is a local)
+        B200_CUDA(cudaFuncSetAttribute(k_pll, cudaFuncAttributeMaxDynamicSharedMemorySize, PLL_SMEM_BYTES));
+    }
     if (cfg.post_costas_dc) {
         B200_REQUIRE(order != 0 && c.constellation != B200_OQPSK, B200_EINVAL, "post_costas_dc needs a Costas loop and is not built for OQPSK");
         pdc_out.alloc(max_work + 64);
@@ -402,6 +462,7 @@ Demod::Demod(const b200_demod_cfg &c) : cfg(c)
     // initial loop state: AGC gain 1 (module_demod_base.cpp:207), Costas 0/0, M&M mu / omega (clock_recovery_mm.cpp:11)
     memset(h_state, 0, sizeof(DemodDevState));
     h_state->gain[0] = h_state->gain[1] = 1.0f;
+    h_state->gain2[0] = h_state->gain2[1] = 1.0f;
     for (int i = 0; i < 2; i++) {
         h_state->mm[i].mu = c.clock_mu;
         h_state->mm[i].omega = sps;
@@ -447,6 +508,8 @@ void Demod::reset()
     B200_CUDA(cudaStreamSynchronize(stream));
     memset(h_state, 0, sizeof(DemodDevState));
     h_state->gain[0] = h_state->gain[1] = 1.0f;
+    h_state->gain2[0] = h_state->gain2[1] = 1.0f;
+    pm_pos = fs_pos = 0;
     for (int i = 0; i < 2; i++) {
         h_state->mm[i].mu = cfg.clock_mu;
         h_state->mm[i].omega = sps;
@@ -479,10 +542,9 @@ int Demod::slot_cap_for(int L) const
     return (int)(L / omin) + 16;
 }
 
-template <int FMT> static void launch_front(Demod &d, const void *raw, long n, int ntiles, FirTaps taps, int cur, bool dump)
+template <int FMT> static void launch_front(Demod &d, const void *raw, long n, int ntiles, FirTaps taps, const AgcUnit &u)
 {
     DemodDevState *S = d.st.p;
-    float2 *fir_out = d.bufA.p + 16;
     // one wave of resident warps, each running a range of R consecutive tiles
     const int R = std::max(4, (ntiles + d.fir_warps - 1) / d.fir_warps);
     const int nranges = (ntiles + R - 1) / R;
@@ -492,35 +554,91 @@ template <int FMT> static void launch_front(Demod &d, const void *raw, long n, i
     ctl.need = d.agc_need.p;
     ctl.epoch = ++d.agc_epoch;
     ctl.warm_max = d.agc_warm_max;
+    ctl.max_gain = u.max_gain;
     const int *need = d.agc_need.p + (ctl.epoch & 1);
+    const bool dump = u.dump != nullptr;
     for (int pass = 0; pass < 2; pass++) {
         ctl.seeded = pass;
         if (pass) { // exact pass: returns at once unless the fast pass asked for it
-            k_agc_compose<FMT><<<std::min(ntiles, d.fir_ctas * 2), FIR_THREADS, 0, d.stream>>>(raw, n, d.cfg.agc_rate, need, ntiles, d.tile_map.p);
-            k_agc_scan<<<1, 1024, 0, d.stream>>>(d.tile_map.p, ntiles, &S->gain[cur], need, d.seeds.p, &S->agc_exact);
+            k_agc_compose<FMT><<<std::min(ntiles, d.fir_ctas * 2), FIR_THREADS, 0, d.stream>>>(raw, n, u.rate, need, ntiles, d.tile_map.p);
+            k_agc_scan<<<1, 1024, 0, d.stream>>>(d.tile_map.p, ntiles, u.gain_in, need, d.seeds.p, &S->agc_exact);
         }
         if (dump)
-            k_agc_fir_w<FMT, true, false><<<grid, 32 * FW_WARPS, 0, d.stream>>>(raw, n, d.cfg.agc_rate, &S->gain[cur], R, ctl, taps, S->agc_tail[cur],
-                                                                              S->agc_tail[cur ^ 1], fir_out, d.agc_dump.p, &S->gain[cur ^ 1], &S->flags);
+            k_agc_fir_w<FMT, true, false><<<grid, 32 * FW_WARPS, 0, d.stream>>>(raw, n, u.rate, u.gain_in, R, ctl, taps, u.tail_in, u.tail_out, u.fir_out, u.dump,
+                                                                              u.gain_out, &S->flags);
         else if (d.fir_bulk)
-            k_agc_fir_w<FMT, false, false, true><<<grid, 32 * FW_WARPS, 0, d.stream>>>(raw, n, d.cfg.agc_rate, &S->gain[cur], R, ctl, taps, S->agc_tail[cur],
-                                                                                     S->agc_tail[cur ^ 1], fir_out, nullptr, &S->gain[cur ^ 1], &S->flags);
+            k_agc_fir_w<FMT, false, false, true><<<grid, 32 * FW_WARPS, 0, d.stream>>>(raw, n, u.rate, u.gain_in, R, ctl, taps, u.tail_in, u.tail_out, u.fir_out,
+                                                                                     nullptr, u.gain_out, &S->flags);
         else
-            k_agc_fir_w<FMT, false, false><<<grid, 32 * FW_WARPS, 0, d.stream>>>(raw, n, d.cfg.agc_rate, &S->gain[cur], R, ctl, taps, S->agc_tail[cur],
-                                                                               S->agc_tail[cur ^ 1], fir_out, nullptr, &S->gain[cur ^ 1], &S->flags);
+            k_agc_fir_w<FMT, false, false><<<grid, 32 * FW_WARPS, 0, d.stream>>>(raw, n, u.rate, u.gain_in, R, ctl, taps, u.tail_in, u.tail_out, u.fir_out, nullptr,
+                                                                               u.gain_out, &S->flags);
     }
     // clamp pass: the gain reached max_gain somewhere in this batch (silent input), so the unclamped maps above do not describe
     // the reference's loop; redo the stage with the clamped ones. All three launches return at once otherwise.
     ctl.seeded = 1;
-    k_agc_compose3<FMT><<<std::min(ntiles, d.fir_ctas * 2), FIR_THREADS, 0, d.stream>>>(raw, n, d.cfg.agc_rate, &S->flags, ntiles, d.tile_map3.p);
-    k_agc_scan3<<<1, 1024, 0, d.stream>>>(d.tile_map3.p, ntiles, &S->gain[cur], &S->flags, d.seeds.p);
+    k_agc_compose3<FMT><<<std::min(ntiles, d.fir_ctas * 2), FIR_THREADS, 0, d.stream>>>(raw, n, u.rate, (double)u.max_gain, &S->flags, ntiles, d.tile_map3.p);
+    k_agc_scan3<<<1, 1024, 0, d.stream>>>(d.tile_map3.p, ntiles, u.gain_in, &S->flags, d.seeds.p);
     if (dump)
-        k_agc_fir_w<FMT, true, true><<<grid, 32 * FW_WARPS, 0, d.stream>>>(raw, n, d.cfg.agc_rate, &S->gain[cur], R, ctl, taps, S->agc_tail[cur],
-                                                                         S->agc_tail[cur ^ 1], fir_out, d.agc_dump.p, &S->gain[cur ^ 1], &S->flags);
+        k_agc_fir_w<FMT, true, true><<<grid, 32 * FW_WARPS, 0, d.stream>>>(raw, n, u.rate, u.gain_in, R, ctl, taps, u.tail_in, u.tail_out, u.fir_out, u.dump,
+                                                                         u.gain_out, &S->flags);
     else
-        k_agc_fir_w<FMT, false, true><<<grid, 32 * FW_WARPS, 0, d.stream>>>(raw, n, d.cfg.agc_rate, &S->gain[cur], R, ctl, taps, S->agc_tail[cur],
-                                                                          S->agc_tail[cur ^ 1], fir_out, nullptr, &S->gain[cur ^ 1], &S->flags);
+        k_agc_fir_w<FMT, false, true><<<grid, 32 * FW_WARPS, 0, d.stream>>>(raw, n, u.rate, u.gain_in, R, ctl, taps, u.tail_in, u.tail_out, u.fir_out, nullptr,
+                                                                          u.gain_out, &S->flags);
     d.launches += 7;
+}
+static void launch_front_fmt(Demod &d, int fmt, const void *raw, long n, FirTaps taps, const AgcUnit &u)
+{
+    const int ntiles = (int)((n + FIR_TILE - 1) / FIR_TILE);
+    if (fmt == B200_CF32)
+        launch_front<0>(d, raw, n, ntiles, taps, u);
+    else if (fmt == B200_CS16)
+        launch_front<1>(d, raw, n, ntiles, taps, u);
+    else
+        launch_front<2>(d, raw, n, ntiles, taps, u);
+}
+
+// FreqShiftBlock / PMToBPSK: see k_rotator. pos = samples the rotator has seen before this batch.
+void Demod::run_rotator(const void *src, int fmt, long n, int iq_swap, int imag_only, unsigned long long dturn, unsigned long long pos, float2 *dst)
+{
+    const unsigned grid = (unsigned)((n + 8 * 256 - 1) / (8 * 256));
+    const unsigned long long turn0 = pos * dturn; // mod 2^64 = mod one turn
+    if (fmt == B200_CF32)
+        k_rotator<0><<<grid, 256, 0, stream>>>(src, n, iq_swap, imag_only, turn0, dturn, dst);
+    else if (fmt == B200_CS16)
+        k_rotator<1><<<grid, 256, 0, stream>>>(src, n, iq_swap, imag_only, turn0, dturn, dst);
+    else
+        k_rotator<2><<<grid, 256, 0, stream>>>(src, n, iq_swap, imag_only, turn0, dturn, dst);
+    launches++;
+}
+
+// pm_demod: PLLCarrierTrackingBlock over the AGC output (pm_agc -> pm_pll; junction check / repair rounds as for the Costas loop, with
+// order 1: the lock point is unique), then PMToBPSK (pm_pll -> pm_out)
+void Demod::stage_pll(long n, int cur, int nxt)
+{
+    DemodDevState *S = st.p;
+    const int L = choose_L(n);
+    const int nseg = (int)((n + L - 1) / L);
+    const int nblk = (nseg + SEG_THREADS - 1) / SEG_THREADS;
+    PllParams P;
+    { // pll_carrier_tracking.cpp:17-21
+        float damping = sqrtf(2.0f) / 2.0f;
+        float denom = (float)(1.0 + 2.0 * damping * cfg.pm_pll_bw + cfg.pm_pll_bw * cfg.pm_pll_bw);
+        P.alpha = (4 * damping * cfg.pm_pll_bw) / denom;
+        P.beta = (4 * cfg.pm_pll_bw * cfg.pm_pll_bw) / denom;
+    }
+    P.fmax = cfg.pm_pll_max_offset; // PLLCarrierTrackingBlock(agc->output_stream, d_pll_bw, d_pll_max_offset, -d_pll_max_offset)
+    P.fmin = -cfg.pm_pll_max_offset;
+    k_pll<<<nblk, SEG_THREADS, PLL_SMEM_BYTES, stream>>>(pm_agc.p, n, L, Wp, nseg, P, S->pll[cur], d_atan_tab.p, pm_pll.p, crec.p, nullptr, nullptr);
+    k_costas_fix<<<1, 1024, 0, stream>>>(crec.p, nseg, 1, tol_pphase, tol_pfreq, quad.p, S->pll[nxt], &S->pll_unconv, repair.p + 1, repair.p, 0, &S->repairs);
+    for (int round = 1; round <= REPAIR_ROUNDS; round++) { // both kernels return at once when no junction is flagged
+        k_pll<<<8, SEG_THREADS, PLL_SMEM_BYTES, stream>>>(pm_agc.p, n, L, Wp, nseg, P, S->pll[cur], d_atan_tab.p, pm_pll.p, crec.p, repair.p + 1, repair.p);
+        k_costas_fix<<<1, 1024, 0, stream>>>(crec.p, nseg, 1, tol_pphase, tol_pfreq, quad.p, S->pll[nxt], &S->pll_unconv, repair.p + 1, repair.p, round,
+                                             &S->repairs);
+        launches += 2;
+    }
+    launches += 2;
+    run_rotator(pm_pll.p, B200_CF32, n, 0, 1, pm_dturn, pm_pos, pm_out.p);
+    pm_pos += (unsigned long long)n;
 }
 
 // Costas loop (+ junction fix-up and repair rounds) over the FIR output in bufA, exact rotation / OQPSK delay / optional DC blocker
@@ -632,47 +750,17 @@ void Demod::stage_mm(float2 *mmin, long n, int L, int nseg, int cur, int nxt, in
         k_mm_scan<<<1, 1024, 0, stream>>>(mrec.p, nseg, tol_mm, offs.p, &S->mm_unconv, cap, &S->flags, repair.p + 1, repair.p, round, &S->repairs);
         launches += 2;
     }
-    k_mm_compact<<<std::min(nseg, 148 * 8), 256, 0, stream>>>(slots.p, cap, mrec.p, offs.p, nseg, bps == 1, sym_out.p, sdst);
+    k_mm_compact<<<std::min(nseg, 148 * 8), 256, 0, stream>>>(slots.p, cap, mrec.p, offs.p, nseg, pm ? 2 : (bps == 1), sym_out.p, sdst);
     k_snr_m2m4<<<1, 1024, 0, stream>>>(sym_out.p, offs.p + nseg, 0.001f, S->snr_y[cur], S->snr_y[nxt]); // M2M4SNREstimator(alpha = 0.001)
     launches += 4;
 #undef B200_MM_LAUNCH
 }
 
-long Demod::process(const void *d_raw, long n, int8_t *soft_dst)
+// SmartResamplerBlock (module_demod_base.cpp:203-204; behind PMToBPSK for pm_demod with resample_after_pll): power-of-two decimator
+// stages, then the rational resampler. Updates (d_raw, n, front_fmt) to the stage's output; rs_swap: the reader's iq_swap still to apply.
+void Demod::front_resample(const void *&d_raw, long &n, int &front_fmt, int &rs_swap, long n_in, int cur, int nxt)
 {
-    B200_REQUIRE(n >= 64, B200_ESTATE, "a batch needs at least 64 samples (got %ld)", n);
-    B200_REQUIRE(n <= max_batch, B200_ESTATE, "batch of %ld samples exceeds max_batch %ld", n, max_batch);
-    DeviceGuard g(cfg.device);
-    const int cur = parity, nxt = parity ^ 1;
     DemodDevState *S = st.p;
-    const long n_in = n;
-    last_in = n;
-    int front_fmt = cfg.format;
-    B200_CUDA(cudaMemsetAsync(&S->flags, 0, sizeof(int), stream)); // per-batch conditions (AGC clamp seen, slot overflow)
-    B200_CUDA(cudaEventRecord(ev[0], stream));
-    int rs_swap = cfg.iq_swap;
-    if (cfg.dc_block) {
-        // CorrectIQBlock sits right behind the reader (module_demod_base.cpp:113-120): (iq_swap ->) dc block -> (resampler ->) AGC
-        const int nt = (int)((n + FIR_TILE - 1) / FIR_TILE);
-        const float alpha = 0.0001f, beta = 1.0f - alpha; // correct_iq.h:24, correct_iq.cpp:9
-#define B200_DC(F)                                                                                                                          \
-    do {                                                                                                                                    \
-        k_dc_tile<F><<<nt, FIR_THREADS, 0, stream>>>(d_raw, n, cfg.iq_swap, alpha, beta, dc_map.p);                                         \
-        k_dc_scan<<<1, 1024, 0, stream>>>(dc_map.p, nt, &S->dc_acc[cur], dc_seeds.p);                                                        \
-        k_dc_apply<F><<<nt, FIR_THREADS, 0, stream>>>(d_raw, n, cfg.iq_swap, alpha, beta, dc_seeds.p, dc_out.p, &S->dc_acc[nxt]);            \
-    } while (0)
-        if (cfg.format == B200_CF32)
-            B200_DC(0);
-        else if (cfg.format == B200_CS16)
-            B200_DC(1);
-        else
-            B200_DC(2);
-#undef B200_DC
-        launches += 3;
-        d_raw = dc_out.p;
-        front_fmt = B200_CF32;
-        rs_swap = 0; // already applied
-    }
     for (auto &stg : decim) {
         // outputs of this batch: all j >= 0 with inc + j * D < n (the for loop of decimating_fir.cpp:66-76)
         long J = 0;
@@ -715,19 +803,89 @@ long Demod::process(const void *d_raw, long n, int8_t *soft_dst)
         n = J;
         front_fmt = B200_CF32;
     }
+}
+
+long Demod::process(const void *d_raw, long n, int8_t *soft_dst)
+{
+    B200_REQUIRE(n >= 64, B200_ESTATE, "a batch needs at least 64 samples (got %ld)", n);
+    B200_REQUIRE(n <= max_batch, B200_ESTATE, "batch of %ld samples exceeds max_batch %ld", n, max_batch);
+    DeviceGuard g(cfg.device);
+    const int cur = parity, nxt = parity ^ 1;
+    DemodDevState *S = st.p;
+    const long n_in = n;
+    last_in = n;
+    int front_fmt = cfg.format;
+    B200_CUDA(cudaMemsetAsync(&S->flags, 0, sizeof(int), stream)); // per-batch conditions (AGC clamp seen, slot overflow)
+    B200_CUDA(cudaEventRecord(ev[0], stream));
+    int rs_swap = cfg.iq_swap;
+    if (cfg.dc_block) {
+        // CorrectIQBlock sits right behind the reader (module_demod_base.cpp:113-120): (iq_swap ->) dc block -> (resampler ->) AGC
+        const int nt = (int)((n + FIR_TILE - 1) / FIR_TILE);
+        const float alpha = 0.0001f, beta = 1.0f - alpha; // correct_iq.h:24, correct_iq.cpp:9
+#define B200_DC(F)                                                                                                                          \
+    do {                                                                                                                                    \
+        k_dc_tile<F><<<nt, FIR_THREADS, 0, stream>>>(d_raw, n, cfg.iq_swap, alpha, beta, dc_map.p);                                         \
+        k_dc_scan<<<1, 1024, 0, stream>>>(dc_map.p, nt, &S->dc_acc[cur], dc_seeds.p);                                                        \
+        k_dc_apply<F><<<nt, FIR_THREADS, 0, stream>>>(d_raw, n, cfg.iq_swap, alpha, beta, dc_seeds.p, dc_out.p, &S->dc_acc[nxt]);            \
+    } while (0)
+        if (cfg.format == B200_CF32)
+            B200_DC(0);
+        else if (cfg.format == B200_CS16)
+            B200_DC(1);
+        else
+            B200_DC(2);
+#undef B200_DC
+        launches += 3;
+        d_raw = dc_out.p;
+        front_fmt = B200_CF32;
+        rs_swap = 0; // already applied
+    }
+    if (cfg.freq_shift != 0) {
+        // FreqShiftBlock behind the DC blocker, in front of the resampler (module_demod_base.cpp:122-123,203)
+        run_rotator(d_raw, front_fmt, n, rs_swap, 0, fs_dturn, fs_pos, fs_out.p);
+        fs_pos += (unsigned long long)n;
+        d_raw = fs_out.p;
+        front_fmt = B200_CF32;
+        rs_swap = 0;
+    }
+    if (!pm_after) // initb(!d_resample_after_pll) (module_pm_demod.cpp:63)
+        front_resample(d_raw, n, front_fmt, rs_swap, n_in, cur, nxt);
+    else if (rs_swap) { // the reader's swap, which the front-end kernels would have applied: a plain converting copy
+        run_rotator(d_raw, front_fmt, n, 1, 0, 0ull, 0ull, pm_out.p);
+        d_raw = pm_out.p;
+        front_fmt = B200_CF32;
+        rs_swap = 0;
+    }
     last_front = n;
-    const int ntiles = (int)((n + FIR_TILE - 1) / FIR_TILE);
     FirTaps taps;
     memset(&taps, 0, sizeof(taps));
     for (int i = 0; i < FIR_NT; i++)
         taps.h[i] = rrc[i];
     const bool dump = cfg.keep_stages != 0;
-    if (front_fmt == B200_CF32)
-        launch_front<0>(*this, d_raw, n, ntiles, taps, cur, dump);
-    else if (front_fmt == B200_CS16)
-        launch_front<1>(*this, d_raw, n, ntiles, taps, cur, dump);
-    else
-        launch_front<2>(*this, d_raw, n, ntiles, taps, cur, dump);
+    if (!pm) {
+        const AgcUnit u{cfg.agc_rate, 65536.0f, &S->gain[cur], &S->gain[nxt], S->agc_tail[cur], S->agc_tail[nxt], bufA.p + 16, dump ? agc_dump.p : nullptr};
+        launch_front_fmt(*this, front_fmt, d_raw, n, taps, u);
+    } else {
+        // pm_demod (module_pm_demod.cpp:61-88): AGC -> carrier PLL -> PMToBPSK -> [resampler -> AGC2] -> RRC. The first AGC runs through
+        // the same kernel with its output dumped (the FIR it also computes is not used)
+        const AgcUnit u1{cfg.agc_rate, 65536.0f, &S->gain[cur], &S->gain[nxt], S->agc1_tail[cur], S->agc1_tail[nxt], bufA.p + 16, pm_agc.p};
+        launch_front_fmt(*this, front_fmt, d_raw, n, taps, u1);
+        stage_pll(n, cur, nxt);
+        last_pm = n;
+        d_raw = pm_out.p;
+        front_fmt = B200_CF32;
+        if (pm_after) {
+            front_resample(d_raw, n, front_fmt, rs_swap, n_in, cur, nxt);
+            last_front = n;
+            // agc2 = AGCBlock(resampler->output_stream, 0.001, 1.0, 1.0, 1000.0) (module_pm_demod.cpp:73-74)
+            const AgcUnit u2{0.001f, 1000.0f, &S->gain2[cur], &S->gain2[nxt], S->agc2_tail[cur], S->agc2_tail[nxt], bufA.p + 16, dump ? agc_dump.p : nullptr};
+            launch_front_fmt(*this, front_fmt, d_raw, n, taps, u2);
+        } else {
+            // the RRC reads PMToBPSK's output directly: rate 0 makes every AGC step the identity map and the gain stay 1
+            const AgcUnit u2{0.0f, 65536.0f, &S->gain2[cur], &S->gain2[nxt], S->agc2_tail[cur], S->agc2_tail[nxt], bufA.p + 16, nullptr};
+            launch_front_fmt(*this, front_fmt, d_raw, n, taps, u2);
+        }
+    }
     B200_CUDA(cudaEventRecord(ev[1], stream));
     float2 *fir_out = bufA.p + 16, *cos_out = bufB.p + 16;
     if (dump)
@@ -773,7 +931,8 @@ long Demod::process(const void *d_raw, long n, int8_t *soft_dst)
 long Demod::debug_run_stage(int stage, const float *h_in, long n, int mode, float *h_out, long cap)
 {
     B200_REQUIRE(n >= 64 && n <= max_work, B200_ESTATE, "stage input of %ld samples outside [64, %ld]", n, max_work);
-    B200_REQUIRE(stage == B200_STAGE_FIR || stage == B200_STAGE_COSTAS || stage == B200_STAGE_MM, B200_EINVAL, "stage %d cannot be run alone", stage);
+    B200_REQUIRE(stage == B200_STAGE_FIR || stage == B200_STAGE_COSTAS || stage == B200_STAGE_MM || stage == B200_STAGE_PLL || stage == B200_STAGE_PM, B200_EINVAL,
+                 "stage %d cannot be run alone", stage);
     DeviceGuard g(cfg.device);
     reset();
     const bool strict = mode & B200_DEBUG_STRICT, seq = mode & B200_DEBUG_SEQUENTIAL;
@@ -793,12 +952,21 @@ long Demod::debug_run_stage(int stage, const float *h_in, long n, int mode, floa
         else {
             // the production kernel with the AGC switched off: rate 0 makes every step map the identity and the gain stay 1, so
             // k_agc_fir_w's output is the FFMA2 FIR of its input (the ranges take the scanned-seed pass: nothing proves a seed at rate 0)
-            const float rate = cfg.agc_rate;
-            cfg.agc_rate = 0.f;
-            launch_front<0>(*this, bufB.p + 16, n, (int)((n + FIR_TILE - 1) / FIR_TILE), taps, 0, false);
-            cfg.agc_rate = rate;
+            const AgcUnit u{0.0f, 65536.0f, &S->gain[0], &S->gain[1], S->agc_tail[0], S->agc_tail[1], bufA.p + 16, nullptr};
+            launch_front_fmt(*this, B200_CF32, bufB.p + 16, n, taps, u);
         }
         src = bufA.p + 16;
+    } else if (stage == B200_STAGE_PLL || stage == B200_STAGE_PM) {
+        // pm_demod's carrier PLL on a caller-supplied AGC output (SEQUENTIAL: one segment = the reference's loop, bit for bit), and
+        // PMToBPSK behind it
+        B200_REQUIRE(pm, B200_EINVAL, "this configuration is not a pm_demod");
+        B200_CUDA(cudaMemcpyAsync(pm_agc.p, h_in, n * sizeof(float2), cudaMemcpyHostToDevice, stream));
+        const int keep = seg_cap_threads;
+        if (seq)
+            seg_cap_threads = 1; // choose_L: one segment as long as allowed; longer inputs still split (use <= 16384 samples for the bitwise check)
+        stage_pll(n, 0, 1);
+        seg_cap_threads = keep;
+        src = stage == B200_STAGE_PLL ? pm_pll.p : pm_out.p;
     } else if (stage == B200_STAGE_COSTAS) {
         B200_REQUIRE(order != 0, B200_EINVAL, "this configuration has no Costas loop");
         B200_CUDA(cudaMemcpyAsync(bufA.p + 16, h_in, n * sizeof(float2), cudaMemcpyHostToDevice, stream));
@@ -822,7 +990,7 @@ long Demod::debug_run_stage(int stage, const float *h_in, long n, int mode, floa
     B200_CUDA(cudaMemcpyAsync(h_state, S, sizeof(DemodDevState), cudaMemcpyDeviceToHost, stream));
     B200_CUDA(cudaStreamSynchronize(stream));
     B200_CUDA(cudaGetLastError());
-    dbg_costas_unconv = h_state->costas_unconv;
+    dbg_costas_unconv = (stage == B200_STAGE_PLL || stage == B200_STAGE_PM) ? h_state->pll_unconv : h_state->costas_unconv;
     dbg_mm_unconv = h_state->mm_unconv;
     dbg_repairs = h_state->repairs;
     last_syms = stage == B200_STAGE_MM ? count : 0;
@@ -896,6 +1064,8 @@ void Demod::stats(b200_demod_stats *o)
     o->last_front_samples = last_front;
     o->snr = snr_now;
     o->peak_snr = snr_peak;
+    o->pll_freq = pm ? h_state->pll[parity][1] : 0.f;
+    o->pll_unconverged = pm ? h_state->pll_unconv : 0;
 }
 
 } // namespace b200
@@ -1047,13 +1217,19 @@ int b200_demod_debug_stage(b200_demod *h, int stage, float *out, long cap_sample
         B200_REQUIRE(h && out, B200_EINVAL, "NULL argument");
         Demod &d = *h->d;
         B200_REQUIRE(d.cfg.keep_stages, B200_ESTATE, "create the demodulator with keep_stages=1 to read stage outputs");
-        const long count = stage == B200_STAGE_DC ? d.last_in : d.last_n;
+        // pm_demod: the first AGC, the carrier PLL and PMToBPSK run on last_pm samples (the input rate with resample_after_pll)
+        const bool at_pll = d.pm && (stage == B200_STAGE_AGC || stage == B200_STAGE_PLL || stage == B200_STAGE_PM);
+        const long count = stage == B200_STAGE_DC ? d.last_in : (at_pll ? d.last_pm : d.last_n);
         B200_REQUIRE(count <= cap_samples, B200_ESTATE, "output buffer too small");
         const float2 *src = nullptr;
         if (stage == B200_STAGE_AGC)
-            src = d.agc_dump.p;
+            src = d.pm ? d.pm_agc.p : d.agc_dump.p;
         else if (stage == B200_STAGE_FIR)
             src = d.fir_dump.p;
+        else if (stage == B200_STAGE_PLL && d.pm)
+            src = d.pm_pll.p; // carrier PLL output (as many samples as entered the PLL)
+        else if (stage == B200_STAGE_PM && d.pm)
+            src = d.pm_out.p; // PMToBPSK output
         else if (stage == B200_STAGE_COSTAS)
             src = (d.cfg.post_costas_dc ? d.pdc_out.p : (d.order ? d.bufA.p : d.bufB.p)) + 16; // M&M input = Costas output after rotation fix-up (+ post-Costas DC blocker / OQPSK delay)
         else if (stage == B200_STAGE_RESAMP && (d.resamp || !d.decim.empty()))

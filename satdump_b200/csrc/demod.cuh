@@ -481,7 +481,6 @@ __device__ __forceinline__ Affine3 warp_scan_inclusive3(Affine3 v, int lane)
     }
     return v;
 }
-constexpr double AGC_MAX_GAIN = 65536.0;  // AGCBlock(..., max_gain = 65536) (module_demod_base.cpp:207)
 constexpr double AGC_NO_CLAMP = 1e30;     // "c" of a map without a clamp (finite, so that a * c + b stays a number)
 struct EBC { float E, B, C; };            // g -> min(g*(1 - E) + B, C), the float form used inside a tile
 __device__ __forceinline__ EBC ebc_compose(const EBC first, const EBC second)
@@ -533,6 +532,7 @@ struct AgcCtl
     unsigned epoch;
     int seeded;
     int warm_max;        // fast pass: how many tiles a range may walk back before giving up
+    float max_gain;      // AGCBlock's max_gain: 65536 for BaseDemodModule's AGC (module_demod_base.cpp:207), 1000 for pm_demod's second one
 };
 
 // ---------------------------------------------------------------- K1: convert + AGC + 31-tap FIR, one WARP per range of tiles
@@ -565,7 +565,7 @@ template <int FMT> struct FwState
 {
     const void *__restrict__ raw;
     long N;
-    float rate;
+    float rate, maxg;  // AGC rate, max_gain
     double G;          // gain before the next chunk
     float2 *xs;        // the warp's strip
     const float2 *xrd; // this lane's FIR window: xidx(8 * lane + c) = 10 * lane + xidx(c)
@@ -702,7 +702,7 @@ __device__ __forceinline__ void fw_chunk(FwState<FMT> &st, RawRegs<FMT> &rr, int
                 inc.B = fmaf(-e[q], inc.B, inc.B + rate);
                 inc.E = fmaf(-inc.E, e[q], inc.E + e[q]);
                 if (CLAMP)
-                    incC = fminf(fmaf(-e[q], incC, incC) + rate, (float)AGC_MAX_GAIN);
+                    incC = fminf(fmaf(-e[q], incC, incC) + rate, st.maxg);
             }
         }
     }
@@ -760,7 +760,7 @@ __device__ __forceinline__ void fw_chunk(FwState<FMT> &st, RawRegs<FMT> &rr, int
             if (s < N) {
                 g = fmaf(-e[q], g, g + rate);
                 gmax = fmaxf(gmax, g);
-                g = fminf(g, 65536.0f);
+                g = fminf(g, st.maxg);
                 if (out) {
                     if (DUMP)
                         agc_dump[s] = o;
@@ -773,7 +773,7 @@ __device__ __forceinline__ void fw_chunk(FwState<FMT> &st, RawRegs<FMT> &rr, int
             x[q] = o;
         }
     }
-    if (!CLAMP && gmax > 65536.0f * S)
+    if (!CLAMP && gmax > st.maxg * S)
         atomicOr(flags, 1);
     {
         float4 *dst = reinterpret_cast<float4 *>(&st.xs[10 * lane + 40]);
@@ -877,8 +877,8 @@ __global__ void __launch_bounds__(32 * FW_WARPS, 8) k_agc_fir_w(const void *__re
             const float tE = __shfl_sync(0xffffffffu, m.E, 0), tB = __shfl_sync(0xffffffffu, m.B, 0);
             Bc = fma(A, (double)tB, Bc);
             A *= 1.0 - (double)tE;
-            // anything older enters as A * gain with gain <= 2^16: done once that is below float resolution of the seed
-            if (A * 65536.0 <= Bc * 0x1p-30) {
+            // anything older enters as A * gain with gain <= max_gain (2^16 for the demodulator's AGC): done once that is below float resolution of the seed
+            if (A * (double)ctl.max_gain <= Bc * 0x1p-30) {
                 ok = true;
                 break;
             }
@@ -894,7 +894,7 @@ __global__ void __launch_bounds__(32 * FW_WARPS, 8) k_agc_fir_w(const void *__re
     RawRegs<FMT> rr;
     if (FMT != 0 && (long)c0 * FW_CH + 8 * lane + 8 <= N)
         raw_fetch<FMT>(raw, (long)c0 * FW_CH + 8 * lane, rr);
-    FwState<FMT> st{raw, N, rate, G, xs, &xs[10 * lane], lane, c_last, 0u, 0u, 0, 0};
+    FwState<FMT> st{raw, N, rate, ctl.max_gain, G, xs, &xs[10 * lane], lane, c_last, 0u, 0u, 0, 0};
     if (BULK) {
         st.rawbuf0 = (unsigned)__cvta_generic_to_shared(&rawbuf_all[warp][0][0]);
         st.bar0 = (unsigned)__cvta_generic_to_shared(&bar_all[warp][0]);
@@ -964,8 +964,8 @@ __global__ void __launch_bounds__(FIR_THREADS) k_agc_compose(const void *__restr
 
 // clamp-aware versions of the two kernels above (run only when the flag says the gain hit max_gain in this batch)
 template <int FMT>
-__global__ void __launch_bounds__(FIR_THREADS) k_agc_compose3(const void *__restrict__ raw, long N, float rate, const int *__restrict__ flags, int ntiles,
-                                                              Affine3 *__restrict__ tile_map)
+__global__ void __launch_bounds__(FIR_THREADS) k_agc_compose3(const void *__restrict__ raw, long N, float rate, double max_gain, const int *__restrict__ flags,
+                                                              int ntiles, Affine3 *__restrict__ tile_map)
 {
     if ((*flags & 1) == 0)
         return;
@@ -980,7 +980,7 @@ __global__ void __launch_bounds__(FIR_THREADS) k_agc_compose3(const void *__rest
         for (int i = 0; i < 8; i++)
             if (s0 + i < N) {
                 const float mag = fast_mag(fmaf(x[i].x, x[i].x, x[i].y * x[i].y));
-                m = compose3(m, Affine3{1.0 - (double)rate * (double)mag, (double)rate, AGC_MAX_GAIN});
+                m = compose3(m, Affine3{1.0 - (double)rate * (double)mag, (double)rate, max_gain});
             }
         m = warp_scan_inclusive3(m, lane);
         if (lane == 31)
@@ -1505,6 +1505,240 @@ __global__ void __launch_bounds__(1024) k_costas_fix(const LoopRec *__restrict__
     }
 }
 
+// ---------------------------------------------------------------- pm_demod: carrier PLL (one thread per segment) and the rotator
+// PLLCarrierTrackingBlock (common/dsp/pll/pll_carrier_tracking.cpp:25-70): a second-order loop whose detector is the phase of the
+// INPUT sample minus the loop phase (table-driven fast_atan2f), i.e. linear up to its wrap into (-pi, pi] and the frequency clamp: two
+// copies started from different states approach each other geometrically whatever the noise, so the stream is cut into segments exactly
+// like the Costas loop's (warm-up of W samples from phase 0 and the carried frequency, junction check and repair rounds by
+// k_costas_fix with order 1). The arithmetic is the reference's, operation by operation (separate multiplies and adds, the
+// polynomials of fast_cos / fast_sin in double, the wraps compared and stepped in double): a segment that continues its predecessor
+// exactly (segment 0, repairs) is bit for bit the reference's output; the others inherit the junction tolerance.
+#endif // B200_DEFINE_KERNELS
+struct PllParams
+{
+    float alpha, beta, fmin, fmax;
+};
+#ifdef B200_DEFINE_KERNELS
+// fast_trig.cpp:158-180: powers in float, Horner sums in double, one rounding on return
+__device__ __forceinline__ float pll_fast_cos(float x)
+{
+    const float x2 = __fmul_rn(x, x), x4 = __fmul_rn(x2, x2), x8 = __fmul_rn(x4, x4);
+    const double d2 = x2, d4 = x4, d8 = x8;
+    const double a = __dadd_rn(__dmul_rn(-2.7236370439787708e-7, d2), 2.4799852696610628e-5);
+    const double b = __dadd_rn(__dmul_rn(-1.3888885054799695e-3, d2), 4.1666666636943683e-2);
+    const double c = __dadd_rn(__dmul_rn(-4.9999999999963024e-1, d2), 1.0);
+    return (float)__dadd_rn(__dadd_rn(__dmul_rn(a, d8), __dmul_rn(b, d4)), c);
+}
+__device__ __forceinline__ float pll_fast_sin(float x)
+{
+    const float x2 = __fmul_rn(x, x), x4 = __fmul_rn(x2, x2);
+    const double d2 = x2, d4 = x4, dx = x;
+    const double a = __dadd_rn(__dmul_rn(2.7181216275479732e-6, d2), -1.9839312269456257e-4);
+    const double b = __dadd_rn(__dmul_rn(8.3333293048425631e-3, d2), -1.6666666640797048e-1);
+    const double in = __dadd_rn(__dmul_rn(a, d4), b);
+    return (float)__dadd_rn(__dmul_rn(__dmul_rn(in, d2), dx), dx);
+}
+// fast_trig.cpp:80-154; tab = the 257-entry arctangent table (host-generated: atan(k / 255) through seven significant digits)
+__device__ __forceinline__ float pll_fast_atan2f(float y, float x, const float *__restrict__ tab)
+{
+    const float ya = fabsf(y), xa = fabsf(x);
+    if (!(ya > 0.0f || xa > 0.0f))
+        return 0.0f;
+    const float z = ya < xa ? __fdiv_rn(ya, xa) : __fdiv_rn(xa, ya);
+    float base;
+    if ((double)z < 0.003921569)
+        base = z;
+    else {
+        float a = __fmul_rn(z, 255.0f);
+        const int idx = ((int)a) & 0xff;
+        a = __fsub_rn(a, (float)idx);
+        const float t0 = tab[idx], t1 = tab[idx + 1];
+        base = __fadd_rn(t0, __fmul_rn(__fsub_rn(t1, t0), a));
+    }
+    const float PI_F = 3.14159274101257324f, HPI_F = 1.57079637050628662f; // (float)M_PI, (float)M_PI_2
+    if (xa > ya) {
+        if (x >= 0.0f)
+            return y >= 0.0f ? base : -base;
+        return y >= 0.0f ? __fsub_rn(PI_F, base) : __fsub_rn(base, PI_F);
+    }
+    if (y >= 0.0f)
+        return x >= 0.0f ? __fsub_rn(HPI_F, base) : __fadd_rn(HPI_F, base);
+    return x >= 0.0f ? __fadd_rn(-HPI_F, base) : __fsub_rn(-HPI_F, base);
+}
+// while (v < -M_PI) v += 2 M_PI; while (v > M_PI) v -= 2 M_PI, compared and stepped in double, stored as float (:45-48, :59-62)
+__device__ __forceinline__ float pll_wrap(float v)
+{
+    while ((double)v < -3.14159265358979323846)
+        v = (float)((double)v + 6.28318530717958647692);
+    while ((double)v > 3.14159265358979323846)
+        v = (float)((double)v - 6.28318530717958647692);
+    return v;
+}
+__device__ __forceinline__ float2 pll_step(const float2 x, float &phase, float &freq, const PllParams &P, const float *__restrict__ tab)
+{
+    const float vr = pll_fast_cos(phase), vi = -pll_fast_sin(phase);
+    const float2 o = make_float2(__fsub_rn(__fmul_rn(x.x, vr), __fmul_rn(x.y, vi)), __fadd_rn(__fmul_rn(x.y, vr), __fmul_rn(x.x, vi)));
+    const float err = pll_wrap(__fsub_rn(pll_fast_atan2f(x.y, x.x, tab), phase));
+    freq = __fadd_rn(freq, __fmul_rn(P.beta, err));
+    if (freq > P.fmax)
+        freq = P.fmax;
+    else if (freq < P.fmin)
+        freq = P.fmin;
+    phase = pll_wrap(__fadd_rn(__fadd_rn(phase, freq), __fmul_rn(P.alpha, err)));
+    return o;
+}
+
+// Same staging as k_costas: rows of 16 samples move between HBM and the warp's shared-memory strip cooperatively (swz16).
+// Dynamic shared memory: COSTAS_SMEM_BYTES of strips + the 257-entry table.
+constexpr int PLL_SMEM_BYTES = COSTAS_SMEM_BYTES + 260 * 4;
+__global__ void __launch_bounds__(SEG_THREADS) k_pll(const float2 *__restrict__ in, long N, int L, int W, int nseg, PllParams P,
+                                                      const float *__restrict__ state_in, const float *__restrict__ atan_tab, float2 *__restrict__ out,
+                                                      LoopRec *__restrict__ rec, const int *__restrict__ repair_list, const int *__restrict__ repair_count)
+{
+    extern __shared__ __align__(16) unsigned char pl_smem[];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    float4 *ring = reinterpret_cast<float4 *>(pl_smem) + warp * (24 * 32); // [16 chunk slots][32] in, then [8][32] out
+    float4 *obuf = ring + 16 * 32;
+    float *tab = reinterpret_cast<float *>(pl_smem + COSTAS_SMEM_BYTES);
+    for (int i = t; i < 257; i += SEG_THREADS)
+        tab[i] = atan_tab[i];
+    __syncthreads();
+    int s = blockIdx.x * SEG_THREADS + t;
+    bool active = true;
+    if (repair_list) {
+        if (s >= min(*repair_count, 1024))
+            active = false;
+        else
+            s = repair_list[s];
+    }
+    if (s >= nseg)
+        active = false;
+    if (!active)
+        s = 0;
+    const long own0 = (long)s * L;
+    const long own1 = active ? min(own0 + L, N) : own0;
+    long start = own0 - W;
+    float phase = 0.f, freq = state_in[1];
+    if (repair_list && active) {
+        start = own0;
+        phase = rec[s - 1].ph_end;
+        freq = rec[s - 1].fr_end;
+    } else if (start <= 0) {
+        start = 0;
+        phase = state_in[0];
+    }
+    const int row0 = (int)(start >> 4), row1 = (int)((own1 + 15) >> 4);
+    const int nrows = active ? row1 - row0 : 0;
+    int maxrows = nrows;
+#pragma unroll
+    for (int off = 16; off; off >>= 1)
+        maxrows = max(maxrows, __shfl_xor_sync(0xffffffffu, maxrows, off));
+    LoopRec lr;
+    lr.ph_start = phase;
+    lr.fr_start = freq;
+    const int c = lane & 7;
+    int src_row0[8], src_nrows[8], src_orow0[8], src_own1[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int T = 4 * i + (lane >> 3);
+        src_row0[i] = __shfl_sync(0xffffffffu, row0, T);
+        src_nrows[i] = __shfl_sync(0xffffffffu, nrows, T);
+        src_orow0[i] = __shfl_sync(0xffffffffu, (int)(own0 >> 4), T);
+        src_own1[i] = __shfl_sync(0xffffffffu, (int)own1, T);
+    }
+    const float2 *in_c = in + 2 * c;
+    auto load_row = [&](int it) {
+        const int pb = (it & 1) * 8;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int T = 4 * i + (lane >> 3);
+            const int row = src_row0[i] + it;
+            if (it < src_nrows[i] && (long)row * 16 + 2 * c < N)
+                cp_async16(&ring[swz16(pb + c, T)], in_c + (long)row * 16);
+        }
+        cp_async_commit();
+    };
+    load_row(0);
+    for (int it = 0; it < maxrows; it++) {
+        const int slot = (it & 1) * 8;
+        load_row(it + 1);
+        cp_async_wait<1>();
+        __syncwarp();
+        const bool mine = it < nrows;
+        const long b = (long)(row0 + it) << 4;
+        if (mine && b == own0) {
+            lr.ph_start = phase;
+            lr.fr_start = freq;
+        }
+        if (mine) {
+            const int nvalid = (int)min(16L, own1 - b);
+#pragma unroll 1
+            for (int p = 0; p < 8; p++) {
+                const float4 v = ring[swz16(slot + p, lane)];
+                float2 o0 = make_float2(0.f, 0.f), o1 = o0;
+                if (2 * p < nvalid)
+                    o0 = pll_step(make_float2(v.x, v.y), phase, freq, P, tab);
+                if (2 * p + 1 < nvalid)
+                    o1 = pll_step(make_float2(v.z, v.w), phase, freq, P, tab);
+                obuf[swz16(p, lane)] = make_float4(o0.x, o0.y, o1.x, o1.y);
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int T = 4 * i + (lane >> 3);
+            const int row = src_row0[i] + it;
+            const int n0 = row * 16 + 2 * c;
+            if (it < src_nrows[i] && row >= src_orow0[i] && n0 < src_own1[i]) {
+                const float4 v = obuf[swz16(c, T)];
+                if (n0 + 1 < src_own1[i])
+                    *reinterpret_cast<float4 *>(out + n0) = v;
+                else
+                    out[n0] = make_float2(v.x, v.y);
+            }
+        }
+        __syncwarp();
+    }
+    cp_async_wait<0>();
+    if (active) {
+        lr.ph_end = phase;
+        lr.fr_end = freq;
+        rec[s] = lr;
+    }
+}
+
+// The VOLK rotator behind FreqShiftBlock (freq_shift.cpp:16-50) and PMToBPSK (pm_to_bpsk.cpp:10-35): out[n] = in[n] * e^{j n delta}
+// with delta the angle of the float pair (cos, sin)(2 pi f / fs) the reference multiplies by. The reference advances its phasor by one
+// rounded complex multiplication per sample (renormalised every 512 samples): a serial recurrence whose angle follows n * delta up to a
+// rounding walk that depends on the VOLK flavour. Here the phasor of sample n comes in closed form from a 64-bit fixed-point count of
+// turns (pos * dturn mod 2^64: exact for any stream position), evaluated in double and rounded once. imag_only: PMToBPSK first
+// reduces its input to (0, imag) (pm_to_bpsk.cpp:24-25). iq_swap / FMT: the reader's conversion when the rotator is the first stage.
+template <int FMT>
+__global__ void __launch_bounds__(256) k_rotator(const void *__restrict__ raw, long N, int iq_swap, int imag_only, unsigned long long turn0,
+                                                 unsigned long long dturn, float2 *__restrict__ out)
+{
+    const long s0 = ((long)blockIdx.x * 256 + threadIdx.x) * 8;
+    if (s0 >= N)
+        return;
+    float2 x[8];
+    load8<FMT>(raw, s0, N, x);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        if (s0 + i < N) {
+            float2 v = x[i];
+            if (iq_swap)
+                v = make_float2(v.y, v.x);
+            if (imag_only)
+                v.x = 0.0f;
+            const unsigned long long turn = turn0 + (unsigned long long)(s0 + i) * dturn; // fraction of a turn, 0.64 fixed point
+            double sn, cs;
+            sincospi((double)(long long)turn * 0x1p-63, &sn, &cs); // signed: [-1, 1) half turns
+            const float pr = (float)cs, pi = (float)sn;
+            out[s0 + i] = make_float2(__fsub_rn(__fmul_rn(v.x, pr), __fmul_rn(v.y, pi)), __fadd_rn(__fmul_rn(v.x, pi), __fmul_rn(v.y, pr)));
+        }
+    }
+}
+
 __device__ __forceinline__ float2 rot_steps(float2 v, int q, int order)
 {
     // multiply by e^{+j q 2pi/order}
@@ -2007,8 +2241,8 @@ __global__ void __launch_bounds__(256) k_mm_compact(const float2 *__restrict__ s
             float2 v = src[i];
             if (sym_out)
                 sym_out[o + i] = v;
-            if (bpsk)
-                soft_out[o + i] = soft_quant(v.x * 50.0f);
+            if (bpsk) // 1: psk_demod's BPSK, real * 50 (module_psk_demod.cpp:199-205); 2: pm_demod, real * 100 (module_pm_demod.cpp:141-144)
+                soft_out[o + i] = soft_quant(v.x * (bpsk == 2 ? 100.0f : 50.0f));
             else {
                 char2 q;
                 q.x = soft_quant(v.x * 100.0f);

@@ -27,6 +27,21 @@ struct DemodDevState
     int repairs;        // segments re-run as exact continuations so far (all batches)
     int agc_exact;      // batches that needed the exact AGC pass so far
     float snr_y[2][2];  // M2M4 SNR estimator: running averages of |s|^2, |s|^4 (snr_estimator.h:26)
+    // pm_demod (module_pm_demod.cpp:61-88)
+    float pll[2][2];           // carrier PLL phase, frequency (pll_carrier_tracking.h: d_phase, d_freq)
+    float gain2[2];            // the AGC in front of the RRC: AGCBlock(0.001, 1, 1, 1000) with resample_after_pll, else the identity (rate 0, gain 1)
+    float2 agc2_tail[2][32];   // ... and its FIR history
+    float2 agc1_tail[2][32];   // (the first AGC's kernel also keeps a FIR history; unused in pm mode)
+    int pll_unconv;            // carrier PLL junctions still unconverged after the repair rounds of the last batch
+};
+
+// one AGC (+ RRC) pass of k_agc_fir_w: which carried gain / FIR history it uses and where its outputs go
+struct AgcUnit
+{
+    float rate, max_gain;
+    float *gain_in, *gain_out;
+    const float2 *tail_in;
+    float2 *tail_out, *fir_out, *dump; // dump != nullptr: also write the AGC output there
 };
 
 class Demod
@@ -45,6 +60,11 @@ class Demod
     void reset(); // back to the state of a freshly created demodulator (new stream)
     // stages of process(), also run alone by the stage-isolated parity hook
     float2 *stage_costas(long n, int L, int nseg, int cur, int nxt, bool materialise);
+    // front-end resampler (power-of-two decimator stages + rational resampler) over n samples at d_raw: updates them to its output
+    void front_resample(const void *&d_raw, long &n, int &front_fmt, int &rs_swap, long n_in, int cur, int nxt);
+    // pm_demod: carrier PLL over n AGC'd samples (pm_agc -> pm_pll), then PMToBPSK (-> pm_out)
+    void stage_pll(long n, int cur, int nxt);
+    void run_rotator(const void *src, int fmt, long n, int iq_swap, int imag_only, unsigned long long dturn, unsigned long long pos, float2 *dst);
     const uint8_t *mm_quad = nullptr; // set by stage_costas when the clock recovery applies the rotation (/ OQPSK delay) itself
     int mm_rot = 0, mm_oqpsk = 0;
     void stage_mm(float2 *mmin, long n, int L, int nseg, int cur, int nxt, int8_t *sdst, bool strict);
@@ -120,6 +140,15 @@ class Demod
     cudaEvent_t ev[4];
     int Wc, Wm, Gc = 0, Gm = 0, seg_cap_threads; // warm-up lengths, gear-shift parts of them
     int seg_ctas = 3; // resident CTAs of the loop kernels per SM the segment count aims at
+    // pm_demod / freq_shift
+    bool pm = false, pm_after = false;   // PMDemodModule's chain; its resampler sits behind the PLL ("resample_after_pll")
+    int Wp = 0;                          // carrier PLL warm-up
+    float tol_pphase = 1e-5f, tol_pfreq = 2e-6f;
+    unsigned long long pm_dturn = 0, fs_dturn = 0; // rotator steps of PMToBPSK / FreqShiftBlock: fraction of a turn per sample, 0.64 fixed point
+    unsigned long long pm_pos = 0, fs_pos = 0;     // samples those rotators have seen so far
+    DevBuf<float2> pm_agc, pm_pll, pm_out, fs_out;
+    DevBuf<float> d_atan_tab;
+    long last_pm = 0;                    // samples through the carrier PLL in the last batch
     float snr_now = 0.f, snr_peak = 0.f; // M2M4SNREstimator::snr() after the last push / its maximum so far (module_psk_demod.cpp:190-194)
     long max_batch;
     int slot_cap_for(int L) const;

@@ -10,7 +10,7 @@ using namespace b200host;
 int main(int argc, char **argv)
 {
     if (argc < 5) {
-        fprintf(stderr, "usage: %s <metop_ahrpt|jpss_hrd|npp_hrd> baseband <input> <output_hint> [--fused] [--key value ...]\n", argv[0]);
+        fprintf(stderr, "usage: %s <metop_ahrpt|jpss_hrd|npp_hrd|simple_bpsk|simple_qpsk|pm_bpsk> baseband <input> <output_hint> [--fused] [--key value ...]\n", argv[0]);
         return 2;
     }
     const std::string pipe = argv[1], level = argv[2], in = argv[3], out = argv[4];
@@ -32,6 +32,13 @@ int main(int argc, char **argv)
         fp = Params{{"constellation", con}, {"cadu_size", "8192"}, {"nrzm", pipe == "simple_bpsk" ? "true" : "false"}, {"derandomize", "true"}, {"rs_i", "4"},
                     {"rs_type", "rs223"}};
         dec = "ccsds_simple_psk_decoder";
+    } else if (pipe == "pm_bpsk") { // pm_demod -> ccsds_conv_concat_decoder, the shape of 14 shipped pipelines (residual-carrier PM with a BPSK
+        // subcarrier; symbolrate etc. come from the command line)
+        dp = Params{{"b200_demod_module", "pm_demod"}, {"symbolrate", "500000"}, {"rrc_alpha", "0.5"}, {"pll_bw", "0.01"}, {"pll_max_offset", "3.14"},
+                    {"costas_bw", "0.005"}};
+        fp = Params{{"constellation", "bpsk"}, {"cadu_size", "8192"}, {"viterbi_ber_thresold", "0.3"}, {"viterbi_outsync_after", "20"}, {"derandomize", "true"},
+                    {"rs_i", "4"}, {"rs_type", "rs223"}};
+        dec = "ccsds_conv_concat_decoder";
     } else {
         fprintf(stderr, "unknown pipeline %s\n", pipe.c_str());
         return 2;
@@ -51,7 +58,7 @@ int main(int argc, char **argv)
             m.process();
             printf("wrote %s (%ld frames)\n", m.getOutput().c_str(), m.frames_written.load());
         } else {
-            PskDemodStage m1(in, out, dp);
+            PskDemodStage m1(in, out, dp, dp.str("b200_demod_module", "psk_demod"));
             FecStage m2(dec, "", out, fp);
             run_two_stage(m1, m2);
             printf("wrote %s (%ld frames)\n", m2.getOutput().c_str(), m2.frames_written.load());

@@ -108,8 +108,10 @@ static void reject(const Params &p, const char *key, const char *why)
         throw ModuleError(std::string("parameter '") + key + "' is not supported by the B200 path (" + why + "); there is no CPU fallback");
 }
 
-b200_demod_cfg demod_cfg_from_params(const Params &p, bool &is_bpsk)
+b200_demod_cfg demod_cfg_from_params(const Params &p, bool &is_bpsk, const std::string &module_id)
 {
+    if (module_id == "pm_demod")
+        return pm_demod_cfg_from_params(p, is_bpsk);
     b200_demod_cfg c{};
     if (!p.has("samplerate"))
         throw ModuleError("Samplerate parameter must be present!"); // module_demod_base.cpp:17-20
@@ -155,7 +157,7 @@ b200_demod_cfg demod_cfg_from_params(const Params &p, bool &is_bpsk)
     else if (fmt == "cs8" || fmt == "s8") c.format = B200_CS8;
     else throw ModuleError("baseband_format " + fmt + " is not supported by the B200 path (cf32/cs16/cs8 only)");
     c.dc_block = p.flag("dc_block", false); // module_demod_base.cpp:33-34,113-114
-    reject(p, "freq_shift", "FreqShift block");
+    c.freq_shift = (double)(long)p.num("freq_shift", 0); // module_demod_base.cpp:36-37,122-123 (long)
     c.iq_swap = p.flag("iq_swap", false); // module_demod_base.cpp:41-42 -> FileSourceBlock
     c.post_costas_dc = p.flag("post_costas_dc", false); // module_psk_demod.cpp:36-37,127-134
     reject(p, "has_carrier", "PLL carrier tracking");
@@ -180,6 +182,62 @@ b200_demod_cfg demod_cfg_from_params(const Params &p, bool &is_bpsk)
     if (p.has("costas_max_offset")) // Hz -> rad/sample at the working rate (module_psk_demod.cpp:116-118)
         c.costas_max_offset = (float)(2.0 * M_PI * (p.num("costas_max_offset") / (c.final_samplerate > 0 ? c.final_samplerate : c.samplerate)));
     reject(p, "dump_intermediate", "intermediate dump");
+    c.device = (int)p.num("b200_device", 0);
+    return c;
+}
+
+// pm_demod (module_pm_demod.cpp:12-58): required samplerate, symbolrate, pll_bw (the carrier PLL's), rrc_alpha; optional
+// resample_after_pll, pll_max_offset, rrc_taps, costas_bw, clock_*, subcarrier_offset + BaseDemodModule's options
+b200_demod_cfg pm_demod_cfg_from_params(const Params &p, bool &is_bpsk)
+{
+    b200_demod_cfg c{};
+    if (!p.has("samplerate"))
+        throw ModuleError("Samplerate parameter must be present!"); // module_demod_base.cpp:17-20
+    c.samplerate = (double)(long)p.num("samplerate");
+    if (!p.has("symbolrate"))
+        throw ModuleError("Symbolrate parameter must be present!");
+    c.symbolrate = (double)(long)p.num("symbolrate");
+    c.constellation = B200_BPSK;
+    is_bpsk = true;
+    c.pm_demod = 1;
+    c.pm_resample_after_pll = p.flag("resample_after_pll", false); // module_pm_demod.cpp:18-19
+    if (!p.has("pll_bw"))
+        throw ModuleError("PLL Bw parameter must be present!"); // :21-24
+    c.pm_pll_bw = (float)p.num("pll_bw");
+    c.pm_pll_max_offset = (float)p.num("pll_max_offset", 0.5); // :26-27, module_pm_demod.h:29
+    if (!p.has("rrc_alpha"))
+        throw ModuleError("RRC Alpha parameter must be present!"); // :29-32
+    c.rrc_alpha = (float)p.num("rrc_alpha");
+    c.rrc_taps = (int)p.num("rrc_taps", 31);
+    c.pll_bw = (float)p.num("costas_bw", 0.005); // d_loop_bw (module_pm_demod.h:32, .cpp:37-38)
+    c.agc_rate = (float)p.num("agc_rate", 1e-2);
+    c.clock_gain_omega = (float)p.num("clock_gain_omega", (float)(pow(0.01, 2) / 4.0)); // module_pm_demod.h:34-37
+    c.clock_mu = (float)p.num("clock_mu", 0.5);
+    c.clock_gain_mu = (float)p.num("clock_gain_mu", 0.01);
+    c.clock_omega_limit = (float)p.num("clock_omega_relative_limit", 0.005);
+    c.costas_max_offset = 1.0f;
+    c.pm_subcarrier_offset = (double)(uint64_t)p.num("subcarrier_offset", 0); // :52-53
+    const std::string fmt = p.str("baseband_format", "cf32");
+    if (fmt == "cf32" || fmt == "f32") c.format = B200_CF32;
+    else if (fmt == "cs16" || fmt == "s16") c.format = B200_CS16;
+    else if (fmt == "cs8" || fmt == "s8") c.format = B200_CS8;
+    else throw ModuleError("baseband_format " + fmt + " is not supported by the B200 path (cf32/cs16/cs8 only)");
+    c.dc_block = p.flag("dc_block", false);
+    c.freq_shift = (double)(long)p.num("freq_shift", 0);
+    c.iq_swap = p.flag("iq_swap", false);
+    reject(p, "enable_doppler", "Doppler correction");
+    reject(p, "dump_intermediate", "intermediate dump");
+    // MAX_SPS = 10 unless the pipeline gives "max_sps" (module_pm_demod.cpp:56, module_demod_base.cpp:61-64)
+    const float min_sps = (float)p.num("min_sps", 0), max_sps = (float)p.num("max_sps", 10.0);
+    c.final_samplerate = b200_demod_final_samplerate(c.samplerate, c.symbolrate, c.constellation, min_sps, max_sps,
+                                                     p.has("custom_samplerate") ? (double)(long)p.num("custom_samplerate") : 0.0);
+    if (c.final_samplerate == c.samplerate)
+        c.final_samplerate = 0;
+    else if (!b200_demod_resample_decision(c.samplerate, c.symbolrate, c.constellation, min_sps, max_sps))
+        c.front_resample = 2;
+    if ((float)c.samplerate / (float)c.symbolrate < 1.0f)
+        throw ModuleError("Your sampling rate is too low! Minimum: " +
+                          (c.symbolrate > 1e6 ? std::to_string(c.symbolrate / 1e6) + " Msps" : std::to_string(c.symbolrate / 1e3) + " ksps"));
     c.device = (int)p.num("b200_device", 0);
     return c;
 }
@@ -293,9 +351,12 @@ static void check(int rc, const char *what)
 }
 
 // ------------------------------------------------------------------------------------------------ PskDemodStage
-PskDemodStage::PskDemodStage(std::string in, std::string hint, Params p) : StageBase(std::move(in), std::move(hint), std::move(p))
+PskDemodStage::PskDemodStage(std::string in, std::string hint, Params p, std::string module_id)
+    : StageBase(std::move(in), std::move(hint), std::move(p)), id(std::move(module_id))
 {
-    cfg = demod_cfg_from_params(params, is_bpsk);
+    if (id != "psk_demod" && id != "pm_demod")
+        throw ModuleError("unknown demodulator module " + id);
+    cfg = demod_cfg_from_params(params, is_bpsk, id);
     batch_samples = (long)params.num("b200_batch_samples", (double)batch_samples);
     cfg.max_batch = batch_samples;
 }
@@ -360,7 +421,8 @@ void PskDemodStage::process()
         b200_demod_stats st;
         if (b200_demod_get_stats(h, &st) == B200_OK) {
             warn_unconverged(st);
-            freq = st.costas_freq * (cfg.final_samplerate > 0 ? cfg.final_samplerate : cfg.samplerate) / (2.0 * M_PI); // rad_to_hz(freq, final_samplerate), module_psk_demod.cpp:196
+            // rad_to_hz(freq, final_samplerate) of the Costas loop (module_psk_demod.cpp:196) / of the carrier PLL (module_pm_demod.cpp:138)
+            freq = (cfg.pm_demod ? st.pll_freq : st.costas_freq) * (cfg.final_samplerate > 0 ? cfg.final_samplerate : cfg.samplerate) / (2.0 * M_PI);
             snr = st.snr;
             peak_snr = st.peak_snr;
         }
@@ -445,7 +507,7 @@ FusedStage::FusedStage(const std::string &decoder_id, std::string in, std::strin
     : StageBase(std::move(in), std::move(hint), std::move(fp)), dec_id(decoder_id), dparams(std::move(dp))
 {
     bool bpsk;
-    dcfg = demod_cfg_from_params(dparams, bpsk);
+    dcfg = demod_cfg_from_params(dparams, bpsk, dparams.str("b200_demod_module", "psk_demod")); // "pm_demod": PMDemodModule's chain in front
     fcfg = fec_cfg_from_params(dec_id, params);
     batch_samples = (long)dparams.num("b200_batch_samples", (double)batch_samples);
     dcfg.max_batch = batch_samples;

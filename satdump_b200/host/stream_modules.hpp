@@ -1,6 +1,7 @@
 // Host-side C++ mirror of the reference's module layer for the hot path, written above the C ABI (include/b200dsp.h).
 //
 //   PskDemodStage   <-> satdump::pipeline::demod::PSKDemodModule        (src-core/pipeline/modules/demod/module_psk_demod.cpp)
+//                       satdump::pipeline::demod::PMDemodModule         (src-core/pipeline/modules/demod/module_pm_demod.cpp), module id "pm_demod"
 //   FecStage        <-> metop::MetOpAHRPTDecoderModule                   (plugins/noaa_metop_support/metop/module_metop_ahrpt_decoder.cpp)
 //                       satdump::pipeline::ccsds::CCSDSConvConcatDecoderModule (src-core/pipeline/modules/ccsds/module_ccsds_conv_concat_decoder.cpp)
 //   FusedStage      both, with the soft stream kept in HBM
@@ -86,16 +87,17 @@ class StageBase
 };
 
 // psk_demod: required samplerate, constellation, rrc_alpha, pll_bw (+ symbolrate); optional as in SURVEY.md App. B.
-// Options whose blocks are not part of this build (dc_block, freq_shift, iq_swap, post_costas_dc, has_carrier, doppler,
-// resampling, custom_samplerate) raise ModuleError instead of silently doing something else.
+// Options whose blocks are not part of this build (has_carrier, doppler, dump_intermediate) raise ModuleError instead of silently doing
+// something else. module_id "pm_demod": PMDemodModule's parameter set (pll_bw = the carrier PLL's, costas_bw, pll_max_offset,
+// resample_after_pll, subcarrier_offset), soft = clamp(real * 100), stats key "freq" = the carrier PLL's frequency.
 class PskDemodStage : public StageBase
 {
   public:
-    PskDemodStage(std::string input_file, std::string output_file_hint, Params parameters);
+    PskDemodStage(std::string input_file, std::string output_file_hint, Params parameters, std::string module_id = "psk_demod");
     ~PskDemodStage() override;
     void init() override;
     void process() override;
-    std::string getID() const override { return "psk_demod"; }
+    std::string getID() const override { return id; }
     // getModuleStats() keys of PSKDemodModule (module_psk_demod.cpp:238-246)
     std::atomic<double> progress{0}, freq{0};
     std::atomic<float> snr{0}, peak_snr{0}; // M2M4SNREstimator over the recovered symbols (module_psk_demod.cpp:190-194)
@@ -103,6 +105,7 @@ class PskDemodStage : public StageBase
     b200_demod_cfg cfg{};
     long batch_samples = 1 << 24;
   private:
+    std::string id;
     b200_demod *h = nullptr;
     bool is_bpsk = false;
 };
@@ -147,7 +150,8 @@ class FusedStage : public StageBase
     b200_chain *h = nullptr;
 };
 
-b200_demod_cfg demod_cfg_from_params(const Params &p, bool &is_bpsk);
+b200_demod_cfg demod_cfg_from_params(const Params &p, bool &is_bpsk, const std::string &module_id = "psk_demod");
+b200_demod_cfg pm_demod_cfg_from_params(const Params &p, bool &is_bpsk);
 b200_fec_cfg fec_cfg_from_params(const std::string &module_id, const Params &p);
 
 // Two modules as two threads joined by a 1 000 000-byte FIFO, like Pipeline::run (pipeline_run.cpp:72-104) minus its 1 s polling.

@@ -192,6 +192,13 @@ class SignalCfg:
     ber_thresold: float = 0.28
     outsync_after: int = 10
     rs_usecheck: bool = False
+    # phase-modulated residual-carrier signal for pm_demod (module_pm_demod.cpp): carrier * exp(j * pm_index * d(t) * sin(2 pi f_sc t)) with
+    # d(t) the pulse-shaped BPSK stream and f_sc the subcarrier (0 = the symbol rate, the module's default for "subcarrier_offset")
+    pm_index: float = 0.0           # rad; 0 = not a PM signal
+    subcarrier: float = 0.0
+    pm_pll_bw: float = 0.01         # receiver: carrier PLL bandwidth ("pll_bw" of pm_demod; pll_bw above is its "costas_bw")
+    pm_pll_max_offset: float = 3.14
+    resample_after_pll: bool = False
 
     @property
     def cadu_bytes(self):
@@ -240,6 +247,15 @@ CONFIGS = {
     "qpsk_p34": SignalCfg(name="qpsk_p34", symbolrate=2400000, conv="p3/4", decoder="ccsds", ber_thresold=0.3, outsync_after=20, esn0_db=10.0),
     "qpsk_p56": SignalCfg(name="qpsk_p56", symbolrate=2400000, conv="p5/6", decoder="ccsds", ber_thresold=0.3, outsync_after=20, esn0_db=11.5),
     "qpsk_p78": SignalCfg(name="qpsk_p78", symbolrate=2400000, conv="p7/8", decoder="ccsds", ber_thresold=0.3, outsync_after=20, esn0_db=12.5),
+    # pm_demod -> ccsds_conv_concat_decoder (14 shipped pipelines have this shape): residual-carrier PM, BPSK r=1/2 on a subcarrier at the
+    # symbol rate, 6 samples per symbol (inside pm_demod's [1.1, 10] window: no resampler), RS I=4
+    "pm_bpsk": SignalCfg(name="pm_bpsk", samplerate=3e6, symbolrate=500000, constellation="bpsk", conv="1/2", interleave=4, fmt="cs16",
+                         decoder="ccsds", ber_thresold=0.3, outsync_after=20, esn0_db=20.0, pll_bw=0.005, carrier_rad=2e-2, pm_index=1.0),
+    # the same at 24 samples per symbol with "resample_after_pll" (27 shipped pipelines set it): carrier PLL and PMToBPSK at the input
+    # rate, then SmartResamplerBlock 6 MS/s -> 2 MS/s (decimator /2 + rational 2/3) and the second AGC, 8 samples per symbol
+    "pm_bpsk_after": SignalCfg(name="pm_bpsk_after", samplerate=6e6, symbolrate=250000, constellation="bpsk", conv="1/2", interleave=4, fmt="cf32",
+                               decoder="ccsds", ber_thresold=0.3, outsync_after=20, esn0_db=26.0, pll_bw=0.005, carrier_rad=1e-2, pm_index=1.0,
+                               resample_after_pll=True),
     # C5: DVB-S2 front half AGC->RRC->M&M, cs8, 45 Msym/s @ 90 MS/s (sps 2.0), alpha 0.25 (DVB_Test.json:132-137), REC_ALPHA 1.7e-3
     "dvbs2_front": SignalCfg(name="dvbs2_front", samplerate=90e6, symbolrate=45000000, constellation="qpsk", conv="none", interleave=4,
                              rrc_alpha=0.25, fmt="cs8", decoder="none", clock_alpha=1.7e-3, carrier_rad=0.0, phase0=0.0, esn0_db=12.0),
@@ -339,7 +355,13 @@ def modulate(cfg: SignalCfg, coded, seed, nsamples=None, device="cpu"):
         n = torch.arange(s, e, device=dev, dtype=torch.float64)
         t = n / sps + span + 0.37
         out_i[s:e] = shape(ai, t)
-        if aq is not None:
+        if cfg.pm_index:
+            fsc = cfg.subcarrier if cfg.subcarrier else cfg.symbolrate
+            sub = torch.sin((2 * np.pi * fsc / cfg.samplerate * n) % (2 * np.pi)).float()
+            ph = cfg.pm_index * out_i[s:e] * sub
+            out_i[s:e] = torch.cos(ph)
+            out_q[s:e] = torch.sin(ph)
+        elif aq is not None:
             out_q[s:e] = shape(aq, t - qoff)
         else:
             out_q[s:e] = 0

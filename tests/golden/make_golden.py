@@ -22,7 +22,8 @@ def main():
     assert ref.available(), "build oracle/_ref first (python -c 'import __graft_entry__ as g; g.build()')"
     only = sys.argv[1:]
     for name, lg in [("metop_ahrpt", 17), ("bpsk_half", 16), ("jpss_hrd", 17), ("dvbs2_front", 16), ("hrpt_bpsk", 18), ("metop_oversampled", 19), ("bpsk_decim8", 20), ("qpsk_undersampled", 16), ("psk8", 17), ("bpsk_simple", 17), ("qpsk_simple", 17),
-                     ("qpsk_p34", 18), ("qpsk_p78", 18)]:  # Viterbi_Depunc rates (conv_rate 3/4 is the one a shipped pipeline uses, 7/8 the most punctured)
+                     ("qpsk_p34", 18), ("qpsk_p78", 18),
+                     ("pm_bpsk", 19)]:  # pm_demod (carrier PLL -> PMToBPSK -> RRC -> Costas -> M&M) -> ccsds_conv_concat_decoder  # Viterbi_Depunc rates (conv_rate 3/4 is the one a shipped pipeline uses, 7/8 the most punctured)
         if only and name not in only:
             continue
         cfg = synth.CONFIGS[name]
@@ -32,6 +33,8 @@ def main():
         d = dict(raw=raw, soft=o["soft"], mm_head=o["mm"][:4096], fir_head=o["fir"][:4096], agc_head=o["agc"][:4096], nsym=np.int64(o["mm"].size))
         if o["costas"] is not None:
             d["costas_head"] = o["costas"][:4096]
+        if cfg.pm_index:
+            d.update(pll_head=o["pll"][:4096], pm_head=o["pm"][:4096])
         dc = oracle_demod(ref, cfg).cfg
         if dc.final_samplerate > 0:  # the front-end resampler ran: pin its output and its bank too
             I, D = int(dc.final_samplerate), int(dc.samplerate)

@@ -10,7 +10,8 @@ from satdump_b200 import synth
 
 GOLD = os.path.join(ROOT, "tests", "golden")
 CONFIGS = ["metop_ahrpt", "bpsk_half", "jpss_hrd", "dvbs2_front", "hrpt_bpsk", "metop_oversampled", "bpsk_decim8", "qpsk_undersampled", "psk8", "bpsk_simple", "qpsk_simple",
-           "qpsk_p34", "qpsk_p78"]  # ccsds_conv_concat_decoder with conv_rate 3/4, 7/8 (Viterbi_Depunc)
+           "qpsk_p34", "qpsk_p78",  # ccsds_conv_concat_decoder with conv_rate 3/4, 7/8 (Viterbi_Depunc)
+           "pm_bpsk"]  # pm_demod in front of ccsds_conv_concat_decoder
 
 
 def _ref():
@@ -34,6 +35,8 @@ def test_port_matches_golden(built, name):
     assert bitwise(o["agc"][:4096], g["agc_head"]) and bitwise(o["fir"][:4096], g["fir_head"]) and bitwise(o["mm"][:4096], g["mm_head"])
     if "costas_head" in g:
         assert bitwise(o["costas"][:4096], g["costas_head"])
+    if "pll_head" in g:  # pm_demod: carrier PLL and PMToBPSK outputs
+        assert bitwise(o["pll"][:4096], g["pll_head"]) and bitwise(o["pm"][:4096], g["pm_head"])
     if "resamp_head" in g:  # front-end resampler: output, length and polyphase bank
         dc = oracle_demod(port, cfg).cfg
         assert bitwise(port.resample(dc, g["raw"])[:4096], g["resamp_head"]) and o["front"] == int(g["front"])
@@ -263,3 +266,61 @@ def test_viterbi_depunc_port_equals_reference(built, name):
     for k in ("bits", "cadu", "vit_state", "defr_state", "rs_err"):
         assert np.array_equal(r[k], p[k]), k
     assert np.allclose(r["vit_ber"], p["vit_ber"], rtol=0, atol=0)
+
+
+def test_fast_trig_restatement_equals_reference(built):
+    """fast_atan2f (table regenerated from atan() through seven significant digits), fast_cos, fast_sin of common/dsp/utils/fast_trig.cpp:
+    every table cell, every quadrant, the small-ratio branch and random arguments, bit for bit."""
+    import ctypes as C
+    from oracle import port
+    ref = _ref()
+    R, P = ref.lib(), port.lib()
+    rng = np.random.default_rng(7)
+    zs = np.concatenate([np.linspace(0, 1, 256 * 4 + 1), rng.random(4000), [0.0, 0.0039, 0.00393, 1.0]]).astype(np.float32)
+    for z in zs:
+        for y, x in ((z, 1.0), (1.0, z), (-z, 1.0), (z, -1.0), (-1.0, -z), (-z, -1.0), (1.0, -z), (-1.0, z)):
+            a, b = R.ref_fast_atan2f(float(y), float(x)), P.ref_fast_atan2f(float(y), float(x))
+            assert np.float32(a).tobytes() == np.float32(b).tobytes(), (y, x, a, b)
+    assert R.ref_fast_atan2f(0.0, 0.0) == P.ref_fast_atan2f(0.0, 0.0) == 0.0
+    for v in np.concatenate([np.linspace(-3.3, 3.3, 6001), rng.standard_normal(2000) * 2]).astype(np.float32):
+        assert np.float32(R.ref_fast_cos(float(v))).tobytes() == np.float32(P.ref_fast_cos(float(v))).tobytes()
+        assert np.float32(R.ref_fast_sin(float(v))).tobytes() == np.float32(P.ref_fast_sin(float(v))).tobytes()
+
+
+@pytest.mark.parametrize("name", ["pm_bpsk", "pm_bpsk_after"])
+def test_pm_demod_port_equals_reference(built, name):
+    """pm_demod's chain (AGC -> carrier PLL -> PMToBPSK -> [resampler -> AGC2] -> RRC -> Costas -> M&M), restatement against the
+    compiled reference modules stage by stage, and the decoded CADUs against the transmitted frames."""
+    from oracle import port
+    from tests.common import match_frames
+    ref = _ref()
+    cfg, raw, clear = signal(name, 20, seed=11)
+    a, b = oracle_demod(ref, cfg), oracle_demod(port, cfg)
+    ra, rb = a.run(raw), b.run(raw)
+    for k in ("agc", "pll", "pm", "fir", "costas", "mm"):
+        assert bitwise(ra[k], rb[k]), k
+    assert np.array_equal(ra["soft"], rb["soft"]) and ra["front"] == rb["front"]
+    assert a.pm_state() == b.pm_state()
+    fr = oracle_fec(ref, cfg).run(ra["soft"])["cadu"].reshape(-1, cfg.cadu_bytes)
+    first, ok = match_frames(fr, clear)
+    assert fr.shape[0] >= 2 and ok, (fr.shape, first)
+
+
+def test_freq_shift_port_equals_reference(built):
+    """FreqShiftBlock in front of psk_demod (module_demod_base.cpp:122-123): a carrier 150 kHz off is brought back; restatement against
+    the compiled block (both on the shim's VOLK rotator), and the chain decodes."""
+    import dataclasses
+    from oracle import port
+    from tests.common import demod_kwargs, match_frames
+    ref = _ref()
+    cfg = dataclasses.replace(synth.CONFIGS["metop_ahrpt"], carrier_rad=2 * np.pi * 150e3 / 6e6 + 1e-3)
+    raw, clear = synth.make_signal(cfg, 1 << 19, seed=5)
+    raw = raw.numpy()
+    kw = demod_kwargs(cfg)
+    a, b = ref.Demod(ref.demod_cfg(freq_shift=-150000.0, **kw)), port.Demod(port.demod_cfg(freq_shift=-150000.0, **kw))
+    ra, rb = a.run(raw), b.run(raw)
+    for k in ("agc", "fir", "costas", "mm"):
+        assert bitwise(ra[k], rb[k]), k
+    assert abs(a.state()["freq"] - 1e-3) < 3e-4  # the Costas loop sees only the residual offset
+    fr = oracle_fec(ref, cfg).run(ra["soft"])["cadu"].reshape(-1, cfg.cadu_bytes)
+    assert fr.shape[0] >= 2 and match_frames(fr, clear)[1]
