@@ -246,6 +246,47 @@ int b200_chain_sync(b200_chain *c);
 int b200_chain_span_begin(b200_chain *c);
 int b200_chain_span_end(b200_chain *c, float *ms);
 
+/* ---- CADU -> CCSDS space packets (the step behind the decoder) --------------------------------------------
+ * Replaces, for all selected virtual channels at once, what the instrument modules do per CADU on the host
+ * (plugins/noaa_metop_support/metop/module_metop_instruments.cpp:66-140): ccsds::ccsds_aos::parseVCDU(cadu).vcid
+ * (src-core/common/ccsds/ccsds_aos/vcdu.cpp:10-17) selects one ccsds::ccsds_aos::Demuxer per channel, whose work(cadu)
+ * (ccsds_aos/demuxer.cpp:64-199; M-PDU header mpdu.cpp:9-13) returns the space packets completed by that frame. The packets come
+ * back in exactly that order - frame by frame, inside a frame in the order work() returns them - with exactly the reference's bytes,
+ * including its behaviour on inconsistent frames. */
+typedef struct b200_demux_cfg
+{
+    int cadu_size;                /* bytes per CADU as the decoder writes them (1024 for RS interleaving 4)                          */
+    int mpdu_data_size;           /* Demuxer(mpdu_data_size, ...), demuxer.h:33 (default 884; MetOp: 882 with a 2-byte insert zone)  */
+    int has_insert_zone;          /* Demuxer(.., hasInsertZone, insertZoneSize, ..)                                                  */
+    int insert_zone_size;
+    int secondary_header_extends; /* Demuxer(.., secondaryHeaderExtendsPkt): + 8 payload bytes when the secondary header flag is set */
+    unsigned long long vcid_mask; /* bit v set = virtual channel v is demultiplexed (the modules' `if (vcdu.vcid == N)` chains)      */
+    int device;
+    long max_frames;              /* largest number of CADUs of one push                                                             */
+    long max_packets;             /* room of the packet table of one push; 0 = 8 * max_frames + 1024                                 */
+} b200_demux_cfg;
+typedef struct b200_packet
+{
+    long offset;      /* of the packet's 6 header bytes (CCSDSHeader::raw) in the byte stream of the pull; payload behind them      */
+    int payload_len;  /* CCSDSPacket::payload.size()                                                                                */
+    int frame;        /* stream index (since create / reset) of the CADU whose work() call returned the packet                      */
+    short vcid, apid; /* parseVCDU(cadu).vcid; CCSDSHeader::apid                                                                    */
+} b200_packet;
+typedef struct b200_demux_stats
+{
+    long frames_in, packets_out, kernel_launches;
+} b200_demux_stats;
+typedef struct b200_demuxer b200_demuxer;
+b200_demuxer *b200_demux_create(const b200_demux_cfg *cfg);
+void b200_demux_destroy(b200_demuxer *d);
+/* nframes CADUs of cadu_size bytes from host memory / already on the device (e.g. b200_chain_frames_device) */
+int b200_demux_push_frames(b200_demuxer *d, const uint8_t *host_cadus, long nframes);
+int b200_demux_push_frames_device(b200_demuxer *d, const uint8_t *dev_cadus, long nframes);
+/* packets of the LAST push: `bytes` = [6 header bytes][payload] back to back, `packets` = one record each */
+int b200_demux_pull(b200_demuxer *d, uint8_t *bytes, long cap_bytes, long *nbytes, b200_packet *packets, long cap_packets, long *npackets);
+int b200_demux_reset(b200_demuxer *d);
+int b200_demux_get_stats(b200_demuxer *d, b200_demux_stats *out);
+
 #ifdef __cplusplus
 }
 #endif

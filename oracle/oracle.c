@@ -1606,3 +1606,156 @@ long orc_pipeline_run(const orc_demod_cfg *dc, const orc_fec_cfg *fc, const void
     orc_fec_destroy(f);
     return outp;
 }
+
+
+/* ================================================================== CADU -> CCSDS space packets
+ * ccsds::ccsds_aos::Demuxer::work (common/ccsds/ccsds_aos/demuxer.cpp:64-199), one instance per virtual channel, with all of its
+ * behaviour on inconsistent frames: the packet under construction keeps its bytes until it is pushed or aborted (readPacket does not
+ * clear them, :26-33), the continuation is cut at first_header_pointer + 1 (:101), a continuation in a frame without a header may take
+ * more than what remains (:109) and then never completes, a frame whose pointer lies outside the data zone is skipped whole (:71-74). */
+typedef struct
+{
+    int used;
+    uint8_t hdr[6];  /* currentCCSDSPacket.header.raw */
+    uint8_t *pay;    /* currentCCSDSPacket.payload */
+    long npay, cappay;
+    int cpl, tpl, rem; /* currentPacketPayloadLength, totalPacketLength, remainingPacketLength */
+    int working, in_header, ihb;
+    uint8_t hb[6];
+} orc_dmx_vc;
+typedef struct
+{
+    int mpdu, insert, insert_size, sec_ext;
+    orc_dmx_vc vc[64];
+    /* output cursor of the running call */
+    uint8_t *out;
+    long cap_bytes, nb, np, cap_recs;
+    int *recs;
+    long frame;
+    int vcid, overflow;
+} orc_dmx;
+
+void *orc_demux_create(int mpdu_data_size, int has_insert_zone, int insert_zone_size, int secondary_header_extends)
+{
+    orc_dmx *d = calloc(1, sizeof(*d));
+    d->mpdu = mpdu_data_size; d->insert = has_insert_zone; d->insert_size = insert_zone_size; d->sec_ext = secondary_header_extends;
+    return d;
+}
+void orc_demux_destroy(void *h)
+{
+    orc_dmx *d = h;
+    for (int i = 0; i < 64; i++) free(d->vc[i].pay);
+    free(d);
+}
+static void dmx_read_packet(orc_dmx *d, orc_dmx_vc *v, const uint8_t *h) /* demuxer.cpp:26-33, ccsds.cpp:11-22 */
+{
+    v->working = 1;
+    memcpy(v->hdr, h, 6);
+    const int packet_length = h[4] << 8 | h[5], sec = (h[0] >> 3) & 1;
+    v->cpl = packet_length + 1 + (d->sec_ext ? (sec ? 8 : 0) : 0);
+    v->tpl = v->cpl + 6;
+    v->rem = v->cpl;
+}
+static void dmx_push_payload(orc_dmx_vc *v, const uint8_t *data, int len) /* :47-53 (a negative length adds nothing but is still subtracted) */
+{
+    if (len > 0) {
+        if (v->npay + len > v->cappay) { v->cappay = (v->npay + len) * 2 + 1024; v->pay = realloc(v->pay, v->cappay); }
+        memcpy(v->pay + v->npay, data, len);
+        v->npay += len;
+    }
+    v->rem -= len;
+}
+static void dmx_clear(orc_dmx_vc *v) { v->working = 0; v->npay = 0; v->cpl = 0; v->rem = 0; } /* abortPacket :56-62 / the tail of pushPacket */
+static void dmx_push_packet(orc_dmx *d, orc_dmx_vc *v) /* :36-44 */
+{
+    if (d->np >= d->cap_recs || d->nb + 6 + v->npay > d->cap_bytes)
+        d->overflow = 1;
+    else {
+        memcpy(d->out + d->nb, v->hdr, 6);
+        memcpy(d->out + d->nb + 6, v->pay, v->npay);
+        d->recs[4 * d->np + 0] = (int)d->frame;
+        d->recs[4 * d->np + 1] = d->vcid;
+        d->recs[4 * d->np + 2] = (int)v->npay;
+        d->recs[4 * d->np + 3] = (v->hdr[0] & 7) << 8 | v->hdr[1];
+        d->nb += 6 + v->npay;
+        d->np++;
+    }
+    dmx_clear(v);
+}
+static void dmx_work(orc_dmx *d, orc_dmx_vc *v, const uint8_t *cadu)
+{
+    const int M = d->mpdu, base = d->insert ? 10 + d->insert_size : 10;
+    const int fhp = (cadu[base] & 7) << 8 | cadu[base + 1]; /* mpdu.cpp:11 */
+    const uint8_t *data = cadu + base + 2;
+    if (fhp < 2047 && fhp >= M) /* :71-74 */
+        return;
+    int offset = 0;
+    if (v->in_header) { /* :81-92 */
+        v->in_header = 0;
+        memcpy(v->hb + v->ihb, data, 6 - v->ihb);
+        offset = 6 - v->ihb;
+        v->ihb = 6;
+        dmx_read_packet(d, v, v->hb);
+    }
+    if (v->rem > 0 && v->working) { /* :95-112 */
+        if (fhp < 2047) {
+            const int n = (v->rem + offset) > fhp + 1 ? (fhp + 1) - offset : v->rem;
+            dmx_push_payload(v, data + offset, n);
+            v->rem = 0;
+        } else {
+            const int n = (v->rem + offset) > M - offset ? M - offset : v->rem;
+            dmx_push_payload(v, data + offset, n);
+        }
+    }
+    if (v->rem == 0 && v->working) /* :115-118 */
+        dmx_push_packet(d, v);
+    if (fhp < 2047) { /* :121-195 */
+        if (fhp + 6 < M) {
+            dmx_read_packet(d, v, data + fhp);
+            if (M > fhp + v->tpl) {
+                dmx_push_payload(v, data + fhp + 6, v->cpl); /* (fhp + tpl < M always holds here) */
+                dmx_push_packet(d, v);
+                int next = fhp + v->tpl;
+                while (next < M) {
+                    if (next + 6 < M) {
+                        dmx_read_packet(d, v, data + next);
+                        const int room = M - (next + 6);
+                        dmx_push_payload(v, data + next + 6, v->rem > room ? room : v->rem);
+                    } else {
+                        v->in_header = 1;
+                        memcpy(v->hb, data + next, M - next);
+                        v->ihb = M - next;
+                        break;
+                    }
+                    if (v->rem == 0 && v->working)
+                        dmx_push_packet(d, v);
+                    next += v->tpl;
+                }
+            } else if (v->working) {
+                const int room = M - (fhp + 6);
+                dmx_push_payload(v, data + fhp + 6, v->rem > room ? room : v->rem);
+            }
+        } else if (fhp < M) {
+            v->in_header = 1;
+            memcpy(v->hb, data + fhp, M - fhp);
+            v->ihb = M - fhp;
+        }
+    }
+}
+long orc_demux_run(void *h, const uint8_t *frames, long nframes, int cadu_size, unsigned long long vcid_mask, long frame0, uint8_t *out, long cap_bytes,
+                   long *nbytes, int *recs, long cap_recs)
+{
+    orc_dmx *d = h;
+    d->out = out; d->cap_bytes = cap_bytes; d->nb = 0; d->np = 0; d->cap_recs = cap_recs; d->recs = recs; d->overflow = 0;
+    for (long f = 0; f < nframes; f++) {
+        const uint8_t *cadu = frames + f * cadu_size;
+        const int vcid = cadu[5] & 63; /* vcdu.cpp:14 */
+        if (!((vcid_mask >> vcid) & 1ull)) continue;
+        d->frame = frame0 + f;
+        d->vcid = vcid;
+        dmx_work(d, &d->vc[vcid], cadu);
+        if (d->overflow) return -1;
+    }
+    *nbytes = d->nb;
+    return d->np;
+}

@@ -102,6 +102,14 @@ void orc_rs_decode_interleaved(uint8_t *data, int dual, int interleave, int rs_t
 int orc_deframe(const uint8_t *bits, int nbits, int cadu_size, int state_synced, uint8_t *out);
 void orc_rotate_soft(int8_t *soft, int size, int phase, int iqswap);
 
+/* ---- CADU -> CCSDS space packets: one demultiplexer per virtual channel (common/ccsds/ccsds_aos/demuxer.cpp) behind
+   parseVCDU's channel id (vcdu.cpp:10-17). Packets in the order the reference returns them, [6 header bytes][payload] back to back;
+   recs[4 i + 0..3] = frame index, vcid, payload length, apid. Returns the packet count, or -1 when a capacity is too small. */
+void *orc_demux_create(int mpdu_data_size, int has_insert_zone, int insert_zone_size, int secondary_header_extends);
+void orc_demux_destroy(void *h);
+long orc_demux_run(void *h, const uint8_t *frames, long nframes, int cadu_size, unsigned long long vcid_mask, long frame0, uint8_t *out, long cap_bytes,
+                   long *nbytes, int *recs, long cap_recs);
+
 /* single-thread end-to-end (demod + FEC) used as the CPU "port" baseline; returns CADU bytes */
 long orc_pipeline_run(const orc_demod_cfg *dc, const orc_fec_cfg *fc, const void *raw, long nsamples, uint8_t *cadu_out, long cadu_cap);
 

@@ -59,6 +59,11 @@ def _lib():
         L.ref_deframe.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.ref_rrc_taps.argtypes = [C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_void_p]
         L.ref_mm_bank.argtypes = [C.c_void_p]
+        L.ref_demux_create.restype = C.c_void_p
+        L.ref_demux_create.argtypes = [C.c_int] * 4
+        L.ref_demux_destroy.argtypes = [C.c_void_p]
+        L.ref_demux_run.restype = C.c_long
+        L.ref_demux_run.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_ulonglong, C.c_long, C.c_void_p, C.c_long, C.POINTER(C.c_long), C.c_void_p, C.c_long]
         L.ref_pipeline_run.restype = C.c_long
         L.ref_pipeline_run.argtypes = [C.POINTER(_m.DemodCfg), C.POINTER(_m.FecCfg), C.c_void_p, C.c_long, C.c_void_p, C.c_long]
         _m._lib = L
@@ -77,6 +82,7 @@ DemodCfg, FecCfg = _m.DemodCfg, _m.FecCfg
 demod_cfg, metop_cfg, ccsds_cfg, simple_cfg = _m.demod_cfg, _m.metop_cfg, _m.ccsds_cfg, _m.simple_cfg
 final_samplerate_of, resample, resampler_taps = _m.final_samplerate_of, _m.resample, _m.resampler_taps
 Fec = _m.Fec
+Demux = _m.Demux
 run_stage = _m.run_stage
 rs_decode_interleaved, derand, cc_encode, cc_decode, rotate_soft, deframe = (
     _m.rs_decode_interleaved, _m.derand, _m.cc_encode, _m.cc_decode, _m.rotate_soft, _m.deframe)

@@ -87,6 +87,11 @@ def lib():
         L.ref_fast_sin.restype = C.c_float
         L.ref_fast_sin.argtypes = [C.c_float]
         L.ref_rotator.argtypes = [C.c_void_p, C.c_long, C.c_long, C.c_double, C.c_double, C.c_void_p]
+        L.ref_demux_create.restype = C.c_void_p
+        L.ref_demux_create.argtypes = [C.c_int] * 4
+        L.ref_demux_destroy.argtypes = [C.c_void_p]
+        L.ref_demux_run.restype = C.c_long
+        L.ref_demux_run.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_ulonglong, C.c_long, C.c_void_p, C.c_long, C.POINTER(C.c_long), C.c_void_p, C.c_long]
         L.ref_resample.restype = C.c_long
         L.ref_resample.argtypes = [C.POINTER(DemodCfg), C.c_void_p, C.c_long, C.c_void_p, C.c_long]
         L.ref_resampler_taps.argtypes = [C.c_uint, C.c_uint, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
@@ -240,6 +245,33 @@ class Demod:
         out = np.zeros(4, np.float32)
         lib().ref_demod_pm_state(self.h, _p(out))
         return dict(pll_phase=out[0], pll_freq=out[1], agc2_gain=out[2])
+
+
+class Demux:
+    """One ccsds_aos::Demuxer per virtual channel behind parseVCDU's channel id (module_metop_instruments.cpp:66-140)."""
+
+    def __init__(self, mpdu_data_size=884, insert_zone=0, secondary_header_extends=False, vcid_mask=(1 << 63) - 1):
+        self.h = lib().ref_demux_create(mpdu_data_size, int(insert_zone > 0), insert_zone, int(secondary_header_extends))
+        self.mask, self.frame0 = vcid_mask, 0
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().ref_demux_destroy(self.h)
+            self.h = None
+
+    def run(self, frames):
+        """frames: uint8 [n, cadu_size]. Returns (bytes of all packets back to back: 6 header bytes + payload each, recs int32 [npackets, 4] =
+        frame index, vcid, payload length, apid)."""
+        frames = np.ascontiguousarray(frames, np.uint8)
+        n, size = frames.shape
+        out = np.zeros(n * size + (1 << 20), np.uint8)
+        recs = np.zeros((n * 130 + 16, 4), np.int32)
+        nb = C.c_long(0)
+        k = lib().ref_demux_run(self.h, _p(frames), n, size, self.mask, self.frame0, _p(out), out.size, C.byref(nb), _p(recs), recs.shape[0])
+        if k < 0:
+            raise RuntimeError("demux output capacity too small")
+        self.frame0 += n
+        return out[:nb.value].copy(), recs[:k].copy()
 
 
 def rotator(x, inc, call=8192):

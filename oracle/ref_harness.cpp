@@ -14,6 +14,7 @@
  *   MetOpAHRPTDecoderModule::process  plugins/noaa_metop_support/metop/module_metop_ahrpt_decoder.cpp:34-90
  *   CCSDSConvConcatDecoderModule      src-core/pipeline/modules/ccsds/module_ccsds_conv_concat_decoder.cpp:16-200
  *   Pipeline::run two-module mode     src-core/pipeline/pipeline_run.cpp:44-117
+ *   CADU -> CCSDS packets             plugins/noaa_metop_support/metop/module_metop_instruments.cpp:66-140 (parseVCDU + one Demuxer per VCID)
  *
  * No reference source is copied here: this file only *calls* the reference classes.
  */
@@ -73,6 +74,8 @@
 #include "common/codings/differential/qpsk_diff.h"
 #include "common/dsp/demod/constellation.h"
 #include "common/codings/rotation.h"
+#include "common/ccsds/ccsds_aos/demuxer.h"
+#include "common/ccsds/ccsds_aos/vcdu.h"
 
 #include <atomic>
 #include <chrono>
@@ -1052,5 +1055,67 @@ extern "C"
         if (f)
             ref_fec_destroy(f);
         return secs;
+    }
+}
+
+/* ------------------------------------------------------------------ CADU -> space packets
+ * One ccsds::ccsds_aos::Demuxer per virtual channel, fed the frames of that channel in stream order, exactly like the instrument modules do
+ * (module_metop_instruments.cpp:66-140). Output: every packet the demuxers return, in the order they return them, as
+ * [6 raw header bytes][payload bytes] back to back; recs[4 * i + 0..3] = frame index, vcid, payload length, apid. */
+namespace
+{
+    struct RefDemux
+    {
+        int mpdu, insert, insert_size, sec_ext;
+        std::map<int, std::shared_ptr<ccsds::ccsds_aos::Demuxer>> by_vcid;
+    };
+}
+extern "C"
+{
+    void *ref_demux_create(int mpdu_data_size, int has_insert_zone, int insert_zone_size, int secondary_header_extends)
+    {
+        RefDemux *d = new RefDemux();
+        d->mpdu = mpdu_data_size;
+        d->insert = has_insert_zone;
+        d->insert_size = insert_zone_size;
+        d->sec_ext = secondary_header_extends;
+        return d;
+    }
+    void ref_demux_destroy(void *h) { delete (RefDemux *)h; }
+    /* frames: nframes * cadu_size bytes; vcid_mask bit v = demultiplex virtual channel v. Returns the number of packets (or -1 - needed
+       when a capacity is too small); *nbytes = bytes written. frame0: index of the first frame of this call in the stream. */
+    long ref_demux_run(void *h, const uint8_t *frames, long nframes, int cadu_size, unsigned long long vcid_mask, long frame0, uint8_t *out, long cap_bytes,
+                       long *nbytes, int *recs, long cap_recs)
+    {
+        RefDemux *d = (RefDemux *)h;
+        long np = 0, nb = 0;
+        std::vector<uint8_t> cadu(cadu_size + 16);
+        for (long f = 0; f < nframes; f++)
+        {
+            memcpy(cadu.data(), frames + f * cadu_size, cadu_size);
+            ccsds::ccsds_aos::VCDU v = ccsds::ccsds_aos::parseVCDU(cadu.data());
+            if (!((vcid_mask >> v.vcid) & 1ull))
+                continue;
+            auto &dm = d->by_vcid[v.vcid];
+            if (!dm)
+                dm = std::make_shared<ccsds::ccsds_aos::Demuxer>(d->mpdu, d->insert != 0, d->insert_size, d->sec_ext != 0);
+            std::vector<ccsds::CCSDSPacket> pk = dm->work(cadu.data());
+            for (ccsds::CCSDSPacket &p : pk)
+            {
+                if (np >= cap_recs || nb + 6 + (long)p.payload.size() > cap_bytes)
+                    return -1;
+                memcpy(out + nb, p.header.raw, 6);
+                if (!p.payload.empty())
+                    memcpy(out + nb + 6, p.payload.data(), p.payload.size());
+                recs[4 * np + 0] = (int)(frame0 + f);
+                recs[4 * np + 1] = v.vcid;
+                recs[4 * np + 2] = (int)p.payload.size();
+                recs[4 * np + 3] = p.header.apid;
+                nb += 6 + (long)p.payload.size();
+                np++;
+            }
+        }
+        *nbytes = nb;
+        return np;
     }
 }

@@ -27,6 +27,8 @@ SYMBOLS = [
     "b200_chain_create", "b200_chain_destroy", "b200_chain_push_iq", "b200_chain_push_iq_device", "b200_chain_prefetch_iq", "b200_chain_pull_frames",
     "b200_chain_frames_device", "b200_chain_get_stats", "b200_chain_last_timing", "b200_chain_reset",
     "b200_chain_set_pipelined", "b200_chain_sync", "b200_chain_span_begin", "b200_chain_span_end",
+    "b200_demux_create", "b200_demux_destroy", "b200_demux_push_frames", "b200_demux_push_frames_device", "b200_demux_pull", "b200_demux_reset",
+    "b200_demux_get_stats",
 ]
 
 
@@ -47,6 +49,19 @@ class FecCfg(C.Structure):
                 ("derand_start", C.c_int), ("rs_i", C.c_int), ("rs_dualbasis", C.c_int), ("rs_fill_bytes", C.c_int),
                 ("rs_usecheck", C.c_int), ("rs_type", C.c_int), ("iq_invert", C.c_int), ("asm_sync", C.c_uint),
                 ("device", C.c_int), ("max_soft", C.c_long), ("qpsk_swap_iq", C.c_int), ("qpsk_swap_diff", C.c_int), ("oqpsk_delay", C.c_int), ("conv_rate", C.c_int)]
+
+
+class DemuxCfg(C.Structure):
+    _fields_ = [("cadu_size", C.c_int), ("mpdu_data_size", C.c_int), ("has_insert_zone", C.c_int), ("insert_zone_size", C.c_int),
+                ("secondary_header_extends", C.c_int), ("vcid_mask", C.c_ulonglong), ("device", C.c_int), ("max_frames", C.c_long), ("max_packets", C.c_long)]
+
+
+class Packet(C.Structure):
+    _fields_ = [("offset", C.c_long), ("payload_len", C.c_int), ("frame", C.c_int), ("vcid", C.c_short), ("apid", C.c_short)]
+
+
+class DemuxStats(C.Structure):
+    _fields_ = [("frames_in", C.c_long), ("packets_out", C.c_long), ("kernel_launches", C.c_long)]
 
 
 class DemodStats(C.Structure):
@@ -122,6 +137,14 @@ def lib():
         L.b200_chain_get_stats.argtypes = [vp, C.POINTER(DemodStats), C.POINTER(FecStats)]
         L.b200_chain_last_timing.argtypes = [vp, vp, ci]
         L.b200_chain_reset.argtypes = [vp]
+        L.b200_demux_create.restype = vp
+        L.b200_demux_create.argtypes = [C.POINTER(DemuxCfg)]
+        L.b200_demux_destroy.argtypes = [vp]
+        L.b200_demux_push_frames.argtypes = [vp, vp, cl]
+        L.b200_demux_push_frames_device.argtypes = [vp, vp, cl]
+        L.b200_demux_pull.argtypes = [vp, vp, cl, C.POINTER(cl), vp, cl, C.POINTER(cl)]
+        L.b200_demux_reset.argtypes = [vp]
+        L.b200_demux_get_stats.argtypes = [vp, C.POINTER(DemuxStats)]
         L.b200_chain_set_pipelined.argtypes = [vp, ci]
         L.b200_chain_sync.argtypes = [vp]
         L.b200_chain_span_begin.argtypes = [vp]
@@ -469,3 +492,53 @@ class Chain:
     def reset(self):
         _chk(lib().b200_chain_reset(self.h))
         return self
+
+
+class Demux:
+    """CADUs -> CCSDS space packets: one ccsds_aos::Demuxer per selected virtual channel (module_metop_instruments.cpp:66-140)."""
+
+    def __init__(self, cadu_size=1024, mpdu_data_size=884, insert_zone=0, secondary_header_extends=False, vcid_mask=(1 << 63) - 1, device=0,
+                 max_frames=1 << 16, max_packets=0):
+        self.cfg = DemuxCfg(cadu_size, mpdu_data_size, int(insert_zone > 0), insert_zone, int(secondary_header_extends), vcid_mask, device, max_frames,
+                            max_packets)
+        self.h = lib().b200_demux_create(C.byref(self.cfg))
+        if not self.h:
+            raise B200Error(-1 if "device" not in last_error().lower() else -2, last_error())
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().b200_demux_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def _pull(self, nframes):
+        cap_b = nframes * 2 * self.cfg.mpdu_data_size + (1 << 23) + (self.cfg.max_packets or 8 * self.cfg.max_frames + 1024) * 6
+        cap_p = self.cfg.max_packets or 8 * self.cfg.max_frames + 1024
+        out = np.zeros(cap_b, np.uint8)
+        pk = (Packet * cap_p)()
+        nb, npk = C.c_long(0), C.c_long(0)
+        _chk(lib().b200_demux_pull(self.h, out.ctypes.data, cap_b, C.byref(nb), C.addressof(pk), cap_p, C.byref(npk)))
+        a = np.frombuffer(pk, dtype=np.dtype([("offset", "<i8"), ("payload_len", "<i4"), ("frame", "<i4"), ("vcid", "<i2"), ("apid", "<i2"), ("pad", "<i4")]),
+                          count=npk.value)
+        recs = np.stack([a["frame"], a["vcid"], a["payload_len"], a["apid"], a["offset"]], axis=1).astype(np.int64)  # frame, vcid, payload length, apid, offset
+        return out[:nb.value].copy(), recs
+
+    def run(self, frames):
+        """frames: uint8 [n, cadu_size] on the host. Returns (packet bytes back to back, recs int64 [npackets, 5] = frame, vcid, payload length,
+        apid, offset) like oracle.ref.Demux.run (whose recs carry the first four columns)."""
+        frames = np.ascontiguousarray(frames, np.uint8)
+        _chk(lib().b200_demux_push_frames(self.h, frames.ctypes.data, frames.shape[0]))
+        return self._pull(frames.shape[0])
+
+    def run_device(self, dev_ptr, nframes):
+        _chk(lib().b200_demux_push_frames_device(self.h, dev_ptr, nframes))
+        return self._pull(nframes)
+
+    def reset(self):
+        _chk(lib().b200_demux_reset(self.h))
+
+    def stats(self):
+        s = DemuxStats()
+        _chk(lib().b200_demux_get_stats(self.h, C.byref(s)))
+        return _struct_dict(s)

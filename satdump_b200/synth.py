@@ -402,3 +402,115 @@ def make_signal(cfg: SignalCfg, nsamples, seed=0xB2000000, device="cpu"):
     coded, clear = make_bitstream(cfg, nframes, seed)
     raw = modulate(cfg, coded, seed, nsamples, device)
     return raw, clear
+
+
+# ---------------------------------------------------------------------------------------------------------------- AOS frames with space packets
+def build_aos_frames(nframes, seed, vcids=(9, 12, 3, 34), mpdu=884, insert_zone=0, cadu_size=1024, corrupt=0.0, drop=0.0, idle=0.05):
+    """A CADU stream whose virtual channels carry CCSDS space packets in M-PDUs (the input of ccsds_aos::Demuxer, demuxer.cpp): per channel a
+    byte stream of packets (lengths from 1 byte to several frames, so headers straddle frames and first-header-pointers of 2047 occur),
+    cut into `mpdu`-byte zones with the first header pointer of each; channels interleaved at random, idle frames (VCID 63, pointer 2046)
+    in between. corrupt: fraction of the frames with random damage to the pointer / packet headers / payload (exercises the demuxer's
+    behaviour on inconsistent input); drop: fraction of the frames removed after packing (discontinuities). Returns uint8 [frames, cadu_size]."""
+    rng = np.random.default_rng(seed)
+    base = 10 + (insert_zone if insert_zone else 0)
+    assert base + 2 + mpdu <= cadu_size
+    streams = {}
+
+    def more(v, need):
+        st = streams.setdefault(v, dict(buf=bytearray(), starts=[], pos=0, seq=0))
+        while len(st["buf"]) - st["pos"] < need:
+            r = rng.random()
+            n = int(rng.integers(1, 300)) if r < 0.7 else (int(rng.integers(300, 2000)) if r < 0.9 else int(rng.integers(2000, 14000)))
+            apid = int(rng.choice([34, 39, 103, 104, 130, 384, 6]))
+            sec = int(rng.integers(0, 2))
+            st["seq"] = (st["seq"] + 1) & 0x3FFF
+            hdr = bytes([(sec << 3) | (apid >> 8), apid & 0xFF, 0xC0 | (st["seq"] >> 8), st["seq"] & 0xFF, ((n - 1) >> 8) & 0xFF, (n - 1) & 0xFF])
+            st["starts"].append(len(st["buf"]))
+            st["buf"] += hdr + rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        return st
+
+    out = np.zeros((nframes, cadu_size), np.uint8)
+    out[:] = rng.integers(0, 256, (nframes, cadu_size), dtype=np.uint8)
+    counters = {}
+    for f in range(nframes):
+        v = 63 if rng.random() < idle else int(rng.choice(vcids))
+        fr = out[f]
+        fr[0:4] = (0x1A, 0xCF, 0xFC, 0x1D)
+        scid = 0x0B
+        fr[4] = (1 << 6) | (scid >> 2)
+        fr[5] = ((scid & 3) << 6) | v
+        c = counters.get(v, 0)
+        counters[v] = (c + 1) & 0xFFFFFF
+        fr[6], fr[7], fr[8], fr[9] = (c >> 16) & 0xFF, (c >> 8) & 0xFF, c & 0xFF, 0
+        if v == 63:
+            fhp = 2046
+        else:
+            st = more(v, mpdu)
+            p0 = st["pos"]
+            fr[base + 2:base + 2 + mpdu] = np.frombuffer(bytes(st["buf"][p0:p0 + mpdu]), np.uint8)
+            nxt = [s for s in st["starts"] if p0 <= s < p0 + mpdu]
+            fhp = nxt[0] - p0 if nxt else 2047
+            st["pos"] = p0 + mpdu
+            st["starts"] = [s for s in st["starts"] if s >= p0 + mpdu]
+            if st["pos"] > 1 << 20:  # keep the buffer short
+                st["buf"] = st["buf"][st["pos"]:]
+                st["starts"] = [s - st["pos"] for s in st["starts"]]
+                st["pos"] = 0
+        fr[base] = (int(rng.integers(0, 32)) << 3) | (fhp >> 8)
+        fr[base + 1] = fhp & 0xFF
+    if corrupt:
+        for f in np.nonzero(rng.random(nframes) < corrupt)[0]:
+            kind = int(rng.integers(0, 4))
+            if kind == 0:  # a random first header pointer
+                fhp = int(rng.integers(0, 2048))
+                out[f, base] = (out[f, base] & 0xF8) | (fhp >> 8)
+                out[f, base + 1] = fhp & 0xFF
+            elif kind == 1:  # pointer "no header" although there is one / short pointers
+                fhp = int(rng.choice([2047, 0, 1, 2, 3, 4, 5, mpdu - 1, mpdu - 3, mpdu - 6, mpdu - 7, mpdu, mpdu + 1]))
+                out[f, base] = (out[f, base] & 0xF8) | (fhp >> 8)
+                out[f, base + 1] = fhp & 0xFF
+            elif kind == 2:  # a burst of wrong bytes somewhere in the data zone (packet lengths go wrong)
+                a = int(rng.integers(0, mpdu - 16))
+                out[f, base + 2 + a:base + 2 + a + 16] = rng.integers(0, 256, 16, dtype=np.uint8)
+            else:  # the frame lands in another virtual channel
+                out[f, 5] = (out[f, 5] & 0xC0) | int(rng.choice(vcids))
+    if drop:
+        out = out[rng.random(nframes) >= drop]
+    return np.ascontiguousarray(out)
+
+
+def craft_leftover_frames(mpdu, variant=0, vcid=9, cadu_size=1024):
+    """Six frames that drive ccsds_aos::Demuxer into its rarest corner: a header straddles a frame boundary, the next frame claims to hold no
+    header (pointer 2047) although the packet ends inside it, so the continuation takes more than what remained (demuxer.cpp:109) and the
+    packet never completes; its bytes then stay in front of the next packet (readPacket does not clear them, :26-33). variant 0: that next
+    packet completes inside its frame; variant 1: it runs on into the following frames."""
+    rng = np.random.default_rng(100 + variant)
+    fr = rng.integers(0, 256, (6, cadu_size), dtype=np.uint8)
+    base = 10
+
+    def head(f, fhp):
+        fr[f, 5] = (fr[f, 5] & 0xC0) | vcid
+        fr[f, base] = fhp >> 8
+        fr[f, base + 1] = fhp & 0xFF
+
+    def d(f):
+        return fr[f, base + 2:]
+
+    head(0, mpdu - 3)  # three header bytes at the end of the zone
+    fr[0, base + 2 + mpdu - 3] &= 0xF7
+    head(1, 2047)
+    pl = (mpdu - 3 - 1) - 1  # remaining = mpdu - 4 with offset 3: (rem + 3) > mpdu - 3 but rem < mpdu - 3
+    d(1)[1], d(1)[2] = pl >> 8, pl & 0xFF
+    head(2, 10)
+    n = 20 if variant == 0 else 3000
+    d(2)[10 + 4], d(2)[10 + 5] = (n - 1) >> 8, (n - 1) & 0xFF
+    if variant == 0:
+        d(2)[10 + 6 + n + 4], d(2)[10 + 6 + n + 5] = 0, 49
+    head(3, 2047 if variant else 100)
+    head(4, 50)
+    head(5, 7)
+    for f in (3, 4, 5):
+        p = ((int(fr[f, base]) & 7) << 8) | int(fr[f, base + 1])
+        if p < 2047:
+            d(f)[p + 4], d(f)[p + 5] = 0, 30
+    return fr

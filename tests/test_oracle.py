@@ -324,3 +324,19 @@ def test_freq_shift_port_equals_reference(built):
     assert abs(a.state()["freq"] - 1e-3) < 3e-4  # the Costas loop sees only the residual offset
     fr = oracle_fec(ref, cfg).run(ra["soft"])["cadu"].reshape(-1, cfg.cadu_bytes)
     assert fr.shape[0] >= 2 and match_frames(fr, clear)[1]
+
+
+@pytest.mark.parametrize("mpdu,iz,corrupt,drop", [(884, 0, 0.0, 0.0), (882, 2, 0.2, 0.05), (60, 0, 0.5, 0.1)])
+def test_packet_demux_port_equals_reference(built, mpdu, iz, corrupt, drop):
+    """CADU -> CCSDS space packets (ccsds_aos::Demuxer per virtual channel): restatement against the compiled reference on clean and
+    damaged streams, with the secondary-header option, and on the crafted leftover-bytes corner."""
+    from oracle import port
+    ref = _ref()
+    fr = synth.build_aos_frames(6000, seed=12, mpdu=mpdu, insert_zone=iz, corrupt=corrupt, drop=drop)
+    for ext in (False, True):
+        a, b = ref.Demux(mpdu, iz, ext).run(fr), port.Demux(mpdu, iz, ext).run(fr)
+        assert a[1].shape[0] > 100 and np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    for variant in (0, 1):
+        q = synth.craft_leftover_frames(mpdu, variant)
+        a, b = ref.Demux(mpdu, 0).run(q), port.Demux(mpdu, 0).run(q)
+        assert a[1][0, 2] > mpdu and np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
