@@ -87,7 +87,8 @@ def test_cadus_of_the_chain_go_on_to_packets_on_the_device(built):
     assert nfr >= 20
     g = capi.Demux(1024, 882, 2, max_frames=nfr, max_packets=nfr * 140)
     got = g.run_device(ptr, nfr)
-    cadus = ch.frames()
+    cadus = gpu_chain(cfg, n).push(raw).frames()  # (frames_device hands the frames over: a second, identical run brings them to the host)
+    assert cadus.shape[0] == nfr
     same(got, O.Demux(882, 2).run(cadus))
 
 
