@@ -91,6 +91,11 @@ typedef struct b200_demod_cfg
     double pm_subcarrier_offset; /* "subcarrier_offset" Hz (uint64 in the module); 0 = the symbol rate (:67)                           */
     double freq_shift;        /* "freq_shift" Hz (long in the module): FreqShiftBlock behind the reader / DC blocker, in front of the
                                  resampler (module_demod_base.cpp:37,122-123; common/dsp/utils/freq_shift.cpp); 0 = none             */
+    /* psk_demod "has_carrier" (module_psk_demod.cpp:39-40,93-116): BPSK on a residual carrier: RRC -> PLLCarrierTrackingBlock ->
+       CorrectIQBlock -> Costas loop (whose frequency limit then defaults to 0.2 rad/sample: pass it in costas_max_offset) */
+    int has_carrier;
+    float carrier_pll_bw;         /* "carrier_pll_bw" (required by the module in this mode)   */
+    float carrier_pll_max_offset; /* "carrier_pll_max_offset", default 3.14                    */
 } b200_demod_cfg;
 
 typedef struct b200_fec_cfg

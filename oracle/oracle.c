@@ -279,6 +279,7 @@ typedef struct
     float pll_state[2];      /* PLLCarrierTrackingBlock: d_phase, d_freq */
     float pm_inc[2], pm_phase[2], fs_inc[2], fs_phase[2]; /* rotator steps / phasors of PMToBPSK and FreqShiftBlock */
     float agc2_gain;         /* AGCBlock(resampler out, 0.001, 1.0, 1.0, 1000.0) (module_pm_demod.cpp:73-74) */
+    cf_t dc_acc3;            /* CorrectIQBlock::acc behind the carrier PLL (has_carrier, module_psk_demod.cpp:112) */
     long pm_pos;
     float *pll_dump, *pm_dump;
 } orc_demod;
@@ -752,6 +753,18 @@ long orc_demod_run(void *h, const void *raw, long nsamples, float *agc_out, floa
         fir_run(d, d->w1, d->w0, n);
         if (fir_out) memcpy(fir_out + pos * 2, d->w0, n * sizeof(cf_t));
         cf_t *cur = d->w0;
+        if (d->order && d->cfg.has_carrier) { /* module_psk_demod.cpp:109-112: carrier PLL, then CorrectIQBlock, in front of the Costas loop */
+            orc_pll_carrier((const float *)d->w0, n, d->cfg.carrier_pll_bw, d->cfg.carrier_pll_max_offset, -d->cfg.carrier_pll_max_offset, d->pll_state, (float *)d->w1);
+            if (d->pll_dump) memcpy(d->pll_dump + pos * 2, d->w1, n * sizeof(cf_t));
+            const float alpha = 0.0001, beta = 1.0f - alpha;
+            for (int i = 0; i < n; i++) {
+                d->dc_acc3.re = d->dc_acc3.re * beta + d->w1[i].re * alpha;
+                d->dc_acc3.im = d->dc_acc3.im * beta + d->w1[i].im * alpha;
+                d->w0[i].re = d->w1[i].re - d->dc_acc3.re;
+                d->w0[i].im = d->w1[i].im - d->dc_acc3.im;
+            }
+            if (d->pm_dump) memcpy(d->pm_dump + pos * 2, d->w0, n * sizeof(cf_t));
+        }
         if (d->order) {
             costas_run(d, d->w0, d->w1, n);
             cur = d->w1;

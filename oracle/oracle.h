@@ -38,6 +38,8 @@ typedef struct
     int pm_resample_after_pll;
     double pm_subcarrier_offset; /* 0 = the symbol rate */
     double freq_shift;           /* FreqShiftBlock behind the reader / DC blocker (module_demod_base.cpp:122-123); 0 = none */
+    int has_carrier;             /* psk_demod carrier mode (module_psk_demod.cpp:93-113): RRC -> carrier PLL -> DC blocker -> Costas */
+    float carrier_pll_bw, carrier_pll_max_offset;
 } orc_demod_cfg;
 
 typedef struct

@@ -23,7 +23,8 @@ class DemodCfg(C.Structure):
                 ("clock_recovery", C.c_int),
                 # pm_demod (module_pm_demod.cpp) and the freq_shift option of BaseDemodModule
                 ("pm", C.c_int), ("pm_pll_bw", C.c_float), ("pm_pll_max_offset", C.c_float), ("pm_resample_after_pll", C.c_int),
-                ("pm_subcarrier_offset", C.c_double), ("freq_shift", C.c_double)]
+                ("pm_subcarrier_offset", C.c_double), ("freq_shift", C.c_double),
+                ("has_carrier", C.c_int), ("carrier_pll_bw", C.c_float), ("carrier_pll_max_offset", C.c_float)]
 
 
 class FecCfg(C.Structure):
@@ -123,7 +124,8 @@ def _p(a):
 def demod_cfg(samplerate, symbolrate, constellation, rrc_alpha, pll_bw=0.003, fmt="cs16", rrc_taps=31, agc_rate=1e-2,
               clock_alpha=None, clock_gain_omega=None, clock_mu=0.5, clock_gain_mu=8.7e-3, clock_omega_limit=0.005,
               costas_max_offset=1.0, buffer_size=0, iq_swap=False, final_samplerate=None, min_sps=None, max_sps=None, dc_block=False, post_costas_dc=False,
-              clock_recovery="mm", pm=False, pm_pll_bw=0.01, pm_pll_max_offset=0.5, resample_after_pll=False, subcarrier_offset=0, freq_shift=0.0):
+              clock_recovery="mm", pm=False, pm_pll_bw=0.01, pm_pll_max_offset=0.5, resample_after_pll=False, subcarrier_offset=0, freq_shift=0.0,
+              has_carrier=False, carrier_pll_bw=0.001, carrier_pll_max_offset=3.14):
     """Defaults follow module_psk_demod.h:31-39 and module_demod_base.h:54. pm=True: PMDemodModule's chain (module_pm_demod.cpp:61-88; pll_bw is
     then its "costas_bw", pm_pll_bw its "pll_bw"; MAX_SPS = 10 unless max_sps is given). final_samplerate=None applies BaseDemodModule::initb's
     rule (resample when samplerate/symbolrate is outside [min_sps, max_sps]); 0 = no resampler."""
@@ -138,10 +140,13 @@ def demod_cfg(samplerate, symbolrate, constellation, rrc_alpha, pll_bw=0.003, fm
         clock_gain_mu = clock_alpha
     if clock_gain_omega is None:
         clock_gain_omega = float(np.float32(pow(8.7e-3, 2) / 4.0))
+    if has_carrier and costas_max_offset == 1.0:
+        costas_max_offset = 0.2  # module_psk_demod.cpp:116
     return DemodCfg(float(samplerate), float(symbolrate), CONST[constellation], rrc_alpha, rrc_taps, pll_bw, agc_rate,
                     float(clock_gain_omega), clock_mu, float(clock_gain_mu), clock_omega_limit, costas_max_offset, FMT[fmt],
                     buffer_size, int(iq_swap), float(final_samplerate), int(dc_block), int(post_costas_dc), {"mm": 0, "gardner": 1}[clock_recovery],
-                    int(pm), pm_pll_bw, pm_pll_max_offset, int(resample_after_pll), float(subcarrier_offset), float(freq_shift))
+                    int(pm), pm_pll_bw, pm_pll_max_offset, int(resample_after_pll), float(subcarrier_offset), float(freq_shift),
+                    int(has_carrier), carrier_pll_bw, carrier_pll_max_offset)
 
 
 def final_samplerate_of(samplerate, symbolrate, constellation, min_sps=None, max_sps=None, custom=None):
@@ -224,6 +229,9 @@ class Demod:
         pm_after = bool(self.cfg.pm and self.cfg.pm_resample_after_pll)
         na = n + 64 if pm_after else nf  # pm_demod with resample_after_pll: AGC / PLL / PMToBPSK run at the input rate
         pll = pmo = None
+        if self.cfg.has_carrier and stages:  # psk_demod's carrier mode: carrier PLL / DC blocker outputs (behind the RRC)
+            pll, pmo = np.zeros(nf, np.complex64), np.zeros(nf, np.complex64)
+            lib().ref_demod_pm_dumps(self.h, _p(pll), _p(pmo))
         if self.cfg.pm and stages:
             pll, pmo = np.zeros(na, np.complex64), np.zeros(na, np.complex64)
             lib().ref_demod_pm_dumps(self.h, _p(pll), _p(pmo))
@@ -239,6 +247,9 @@ class Demod:
             lib().ref_demod_pm_dumps(self.h, None, None)
             cin = (lambda a: None if a is None else a[:n if pm_after else front])
             return dict(agc=cin(agc), pll=cin(pll), pm=cin(pmo), fir=cut(fir), costas=cut(cos), mm=mm[:ns].copy(), soft=soft[:ns].copy(), front=front)
+        if self.cfg.has_carrier:
+            lib().ref_demod_pm_dumps(self.h, None, None)
+            return dict(agc=cut(agc), fir=cut(fir), pll=cut(pll), carrier_dc=cut(pmo), costas=cut(cos), mm=mm[:ns].copy(), soft=soft[:ns * bps].copy(), front=front)
         return dict(agc=cut(agc), fir=cut(fir), costas=cut(cos), mm=mm[:ns].copy(), soft=soft[:ns * bps].copy(), front=front)
 
     def pm_state(self):

@@ -119,6 +119,9 @@ extern "C"
         int pm_resample_after_pll;
         double pm_subcarrier_offset; /* "subcarrier_offset": 0 = the symbol rate (module_pm_demod.cpp:67) */
         double freq_shift;        /* "freq_shift": FreqShiftBlock behind the reader / DC blocker (module_demod_base.cpp:125-126); 0 = none */
+        /* psk_demod "has_carrier" (module_psk_demod.cpp:93-113): RRC -> PLLCarrierTrackingBlock -> CorrectIQBlock -> Costas (BPSK, limit 0.2) */
+        int has_carrier;
+        float carrier_pll_bw, carrier_pll_max_offset;
     } ref_demod_cfg;
 
     typedef struct
@@ -153,6 +156,8 @@ namespace
         std::shared_ptr<dsp::AGCBlock<complex_t>> agc;
         std::shared_ptr<dsp::FIRBlock<complex_t>> rrc;
         std::shared_ptr<dsp::CostasLoopBlock> pll;
+        std::shared_ptr<dsp::PLLCarrierTrackingBlock> carrier_pll; /* has_carrier */
+        std::shared_ptr<dsp::CorrectIQBlock<complex_t>> carrier_dc;
         std::shared_ptr<dsp::CorrectIQBlock<complex_t>> post_pll_dc;
         std::shared_ptr<dsp::DelayOneImagBlock> delay;
         std::shared_ptr<dsp::Block<complex_t, complex_t>> rec; /* the clock recovery in use: one of the two below */
@@ -318,6 +323,12 @@ extern "C"
         else if (c->constellation != 4)
         {
             int order = c->constellation == 0 ? 2 : (c->constellation == 3 ? 8 : 4);
+            if (c->has_carrier) /* module_psk_demod.cpp:93-113 (BPSK only; the Costas limit is then the caller's 0.2 default, :116) */
+            {
+                d->carrier_pll = std::make_shared<dsp::PLLCarrierTrackingBlock>(last, c->carrier_pll_bw, c->carrier_pll_max_offset, -c->carrier_pll_max_offset);
+                d->carrier_dc = std::make_shared<dsp::CorrectIQBlock<complex_t>>(d->carrier_pll->output_stream);
+                last = d->carrier_dc->output_stream;
+            }
             d->pll = std::make_shared<dsp::CostasLoopBlock>(last, c->pll_bw, order, c->costas_max_offset);
             last = d->pll->output_stream;
             if (c->post_costas_dc)
@@ -426,6 +437,15 @@ extern "C"
                 memcpy(fir_out + pos * 2, d->rrc->output_stream->readBuf, n * sizeof(complex_t));
             if (d->pll)
             {
+                if (d->carrier_pll)
+                {
+                    d->carrier_pll->work();
+                    if (d->pll_dump)
+                        memcpy(d->pll_dump + pos * 2, d->carrier_pll->output_stream->readBuf, n * sizeof(complex_t));
+                    d->carrier_dc->work();
+                    if (d->pm_dump)
+                        memcpy(d->pm_dump + pos * 2, d->carrier_dc->output_stream->readBuf, n * sizeof(complex_t));
+                }
                 d->pll->work();
                 if (d->post_pll_dc)
                     d->post_pll_dc->work();
@@ -477,8 +497,8 @@ extern "C"
     void ref_demod_pm_state(void *h, float *out4)
     {
         RefDemod *d = (RefDemod *)h;
-        out4[0] = d->cpll ? d->cpll->d_phase : 0;
-        out4[1] = d->cpll ? d->cpll->d_freq : 0;
+        out4[0] = d->cpll ? d->cpll->d_phase : (d->carrier_pll ? d->carrier_pll->d_phase : 0);
+        out4[1] = d->cpll ? d->cpll->d_freq : (d->carrier_pll ? d->carrier_pll->d_freq : 0);
         out4[2] = d->agc2 ? d->agc2->gain : 0;
         out4[3] = 0;
     }

@@ -40,7 +40,8 @@ class DemodCfg(C.Structure):
                 ("keep_stages", C.c_int), ("iq_swap", C.c_int), ("final_samplerate", C.c_double), ("dc_block", C.c_int), ("post_costas_dc", C.c_int),
                 ("front_resample", C.c_int), ("clock_recovery", C.c_int),
                 ("pm_demod", C.c_int), ("pm_pll_bw", C.c_float), ("pm_pll_max_offset", C.c_float), ("pm_resample_after_pll", C.c_int),
-                ("pm_subcarrier_offset", C.c_double), ("freq_shift", C.c_double)]
+                ("pm_subcarrier_offset", C.c_double), ("freq_shift", C.c_double),
+                ("has_carrier", C.c_int), ("carrier_pll_bw", C.c_float), ("carrier_pll_max_offset", C.c_float)]
 
 
 class FecCfg(C.Structure):
@@ -166,12 +167,14 @@ def demod_cfg(samplerate, symbolrate, constellation, rrc_alpha, pll_bw=0.003, fm
               clock_gain_omega=None, clock_mu=0.5, clock_gain_mu=8.7e-3, clock_omega_limit=0.005, costas_max_offset=1.0, device=0,
               max_batch=1 << 24, keep_stages=False, iq_swap=False, final_samplerate=None, min_sps=0.0, max_sps=0.0, dc_block=False, post_costas_dc=False,
               front_resample=0, clock_recovery="mm", pm=False, pm_pll_bw=0.01, pm_pll_max_offset=0.5, resample_after_pll=False, subcarrier_offset=0,
-              freq_shift=0.0):
+              freq_shift=0.0, has_carrier=False, carrier_pll_bw=0.001, carrier_pll_max_offset=3.14):
     """Parameter defaults = module_psk_demod.h:31-39, module_demod_base.h:54. final_samplerate=None applies BaseDemodModule::initb's
     rule (resample when samplerate/symbolrate is outside [min_sps, max_sps]); 0 forces "no resampler". pm=True: pm_demod's chain
     (module_pm_demod.cpp; pll_bw is then its "costas_bw", pm_pll_bw its "pll_bw", MAX_SPS = 10)."""
     if pm and not max_sps:
         max_sps = 10.0  # module_pm_demod.cpp:56
+    if has_carrier and costas_max_offset == 1.0:
+        costas_max_offset = 0.2  # module_psk_demod.cpp:116
     if final_samplerate is None:
         final_samplerate = final_samplerate_of(samplerate, symbolrate, constellation, min_sps, max_sps)
         if final_samplerate == float(int(samplerate)):
@@ -184,7 +187,8 @@ def demod_cfg(samplerate, symbolrate, constellation, rrc_alpha, pll_bw=0.003, fm
     return DemodCfg(float(samplerate), float(symbolrate), CONST[constellation], rrc_alpha, rrc_taps, pll_bw, agc_rate, clock_gain_omega,
                     clock_mu, clock_gain_mu, clock_omega_limit, costas_max_offset, FMT[fmt], device, max_batch, int(keep_stages), int(iq_swap),
                     float(final_samplerate), int(dc_block), int(post_costas_dc), int(front_resample), {"mm": 0, "gardner": 1}[clock_recovery],
-                    int(pm), pm_pll_bw, pm_pll_max_offset, int(resample_after_pll), float(subcarrier_offset), float(freq_shift))
+                    int(pm), pm_pll_bw, pm_pll_max_offset, int(resample_after_pll), float(subcarrier_offset), float(freq_shift),
+                    int(has_carrier), carrier_pll_bw, carrier_pll_max_offset)
 
 
 def resampler_bank(samplerate, final_samplerate):

@@ -202,6 +202,11 @@ Demod::Demod(const b200_demod_cfg &c) : cfg(c)
         B200_REQUIRE(!c.post_costas_dc && c.clock_recovery == 0, B200_EINVAL, "pm_demod has no post-Costas DC blocker and uses the M&M clock recovery");
         cfg.costas_max_offset = 1.0f; // CostasLoopBlock(rrc->output_stream, d_loop_bw, 2): freq_limit defaults to 1.0 (costas_loop.h:27)
     }
+    if (c.has_carrier) { // module_psk_demod.cpp:93-113
+        B200_REQUIRE(!pm, B200_EINVAL, "has_carrier is psk_demod's carrier mode, not pm_demod's");
+        B200_REQUIRE(c.constellation == B200_BPSK, B200_EINVAL, "For carrier mode, constellation must be BPSK!");
+        B200_REQUIRE(c.carrier_pll_bw > 0 && c.carrier_pll_bw < 0.5f && c.carrier_pll_max_offset > 0, B200_EINVAL, "carrier_pll_bw / carrier_pll_max_offset out of range");
+    }
     // MAX_SPS = 10 for pm_demod ("we do NOT want to resample unless really necessary", module_pm_demod.cpp:56)
     const float lo = c.constellation == B200_OQPSK ? 1.6f : 1.1f, hi = pm ? 10.0f : (c.constellation == B200_OQPSK ? 2.4f : 4.0f);
     B200_REQUIRE(sps >= lo * 0.999f && sps <= hi * 1.001f, B200_EINVAL,
@@ -286,10 +291,10 @@ Demod::Demod(const b200_demod_cfg &c) : cfg(c)
     order = c.constellation == B200_BPSK ? 2 : (c.constellation == B200_8PSK ? 8 : (c.constellation == B200_NONE ? 0 : 4));
     max_batch = c.max_batch;
     max_work = resamp ? std::max<long>(max_batch, (long)((double)max_batch * rs_I / rs_D) + 64) : max_batch; // (a decimator in front only shrinks it)
-    if (pm) {
+    if (pm || c.has_carrier) {
         // carrier PLL warm-up: the loop is linear (its detector is the input's own phase minus the loop phase), two copies approach each
         // other like exp(-n * bw * 1.5): 24 / bw samples bring any start state below float resolution of the phase
-        Wp = round_up16(24.0 / c.pm_pll_bw);
+        Wp = round_up16(24.0 / (pm ? c.pm_pll_bw : c.carrier_pll_bw));
         if (const char *e = getenv("B200_PLL_WARMUP_SCALE")) // tuning hook
             Wp = round_up16(Wp * atof(e));
     }
@@ -405,7 +410,7 @@ Demod::Demod(const b200_demod_cfg &c) : cfg(c)
     sym_out.alloc((size_t)(max_work / omin) + 1024);
     soft.alloc(((size_t)(max_work / omin) + 1024) * bps);
     d_bank.alloc(128 * 8);
-    if (cfg.dc_block || cfg.post_costas_dc) {
+    if (cfg.dc_block || cfg.post_costas_dc || cfg.has_carrier) {
         const int nt = (int)((std::max(max_batch, max_work) + FIR_TILE - 1) / FIR_TILE);
         dc_map.alloc(nt + 1);
         dc_seeds.alloc(nt + 2);
@@ -414,11 +419,13 @@ Demod::Demod(const b200_demod_cfg &c) : cfg(c)
         dc_out.alloc(max_batch + 64);
     if (cfg.freq_shift != 0)
         fs_out.alloc(max_batch + 64);
-    if (pm) {
+    if (pm || cfg.has_carrier) {
         const long npm = std::max(max_batch, max_work) + 64;
-        pm_agc.alloc(npm);
+        if (pm) {
+            pm_agc.alloc(npm);
+            pm_out.alloc(npm);
+        }
         pm_pll.alloc(npm);
-        pm_out.alloc(npm);
         // fast_atan2f's table (fast_trig.cpp:16-61): the arctangent of k / 255 through seven significant digits, entry 256 = entry 255
         std::vector<float> tab(260, 0.f);
         char buf[40];
@@ -613,7 +620,7 @@ void Demod::run_rotator(const void *src, int fmt, long n, int iq_swap, int imag_
 
 // pm_demod: PLLCarrierTrackingBlock over the AGC output (pm_agc -> pm_pll; junction check / repair rounds as for the Costas loop, with
 // order 1: the lock point is unique), then PMToBPSK (pm_pll -> pm_out)
-void Demod::stage_pll(long n, int cur, int nxt)
+void Demod::run_pll(const float2 *in, float2 *out, long n, float bw, float max_offset, int cur, int nxt)
 {
     DemodDevState *S = st.p;
     const int L = choose_L(n);
@@ -622,21 +629,26 @@ void Demod::stage_pll(long n, int cur, int nxt)
     PllParams P;
     { // pll_carrier_tracking.cpp:17-21
         float damping = sqrtf(2.0f) / 2.0f;
-        float denom = (float)(1.0 + 2.0 * damping * cfg.pm_pll_bw + cfg.pm_pll_bw * cfg.pm_pll_bw);
-        P.alpha = (4 * damping * cfg.pm_pll_bw) / denom;
-        P.beta = (4 * cfg.pm_pll_bw * cfg.pm_pll_bw) / denom;
+        float denom = (float)(1.0 + 2.0 * damping * bw + bw * bw);
+        P.alpha = (4 * damping * bw) / denom;
+        P.beta = (4 * bw * bw) / denom;
     }
-    P.fmax = cfg.pm_pll_max_offset; // PLLCarrierTrackingBlock(agc->output_stream, d_pll_bw, d_pll_max_offset, -d_pll_max_offset)
-    P.fmin = -cfg.pm_pll_max_offset;
-    k_pll<<<nblk, SEG_THREADS, PLL_SMEM_BYTES, stream>>>(pm_agc.p, n, L, Wp, nseg, P, S->pll[cur], d_atan_tab.p, pm_pll.p, crec.p, nullptr, nullptr);
+    P.fmax = max_offset; // PLLCarrierTrackingBlock(input, bw, max_offset, -max_offset)
+    P.fmin = -max_offset;
+    k_pll<<<nblk, SEG_THREADS, PLL_SMEM_BYTES, stream>>>(in, n, L, Wp, nseg, P, S->pll[cur], d_atan_tab.p, out, crec.p, nullptr, nullptr);
     k_costas_fix<<<1, 1024, 0, stream>>>(crec.p, nseg, 1, tol_pphase, tol_pfreq, quad.p, S->pll[nxt], &S->pll_unconv, repair.p + 1, repair.p, 0, &S->repairs);
     for (int round = 1; round <= REPAIR_ROUNDS; round++) { // both kernels return at once when no junction is flagged
-        k_pll<<<8, SEG_THREADS, PLL_SMEM_BYTES, stream>>>(pm_agc.p, n, L, Wp, nseg, P, S->pll[cur], d_atan_tab.p, pm_pll.p, crec.p, repair.p + 1, repair.p);
+        k_pll<<<8, SEG_THREADS, PLL_SMEM_BYTES, stream>>>(in, n, L, Wp, nseg, P, S->pll[cur], d_atan_tab.p, out, crec.p, repair.p + 1, repair.p);
         k_costas_fix<<<1, 1024, 0, stream>>>(crec.p, nseg, 1, tol_pphase, tol_pfreq, quad.p, S->pll[nxt], &S->pll_unconv, repair.p + 1, repair.p, round,
                                              &S->repairs);
         launches += 2;
     }
     launches += 2;
+}
+
+void Demod::stage_pll(long n, int cur, int nxt)
+{
+    run_pll(pm_agc.p, pm_pll.p, n, cfg.pm_pll_bw, cfg.pm_pll_max_offset, cur, nxt);
     run_rotator(pm_pll.p, B200_CF32, n, 0, 1, pm_dturn, pm_pos, pm_out.p);
     pm_pos += (unsigned long long)n;
 }
@@ -653,6 +665,17 @@ float2 *Demod::stage_costas(long n, int L, int nseg, int cur, int nxt, bool mate
     last_L = L;
     last_nseg = nseg;
     float2 *mmin;
+    if (order && cfg.has_carrier) {
+        // psk_demod carrier mode (module_psk_demod.cpp:109-112,121): carrier PLL on the RRC output, then CorrectIQBlock; the Costas loop
+        // reads the result (written back over the RRC output)
+        run_pll(fir_out, pm_pll.p, n, cfg.carrier_pll_bw, cfg.carrier_pll_max_offset, cur, nxt);
+        const int nt = (int)((n + FIR_TILE - 1) / FIR_TILE);
+        const float alpha = 0.0001f, beta = 1.0f - alpha; // correct_iq.h:24, correct_iq.cpp:9
+        k_dc_tile<0><<<nt, FIR_THREADS, 0, stream>>>(pm_pll.p, n, 0, alpha, beta, dc_map.p);
+        k_dc_scan<<<1, 1024, 0, stream>>>(dc_map.p, nt, &S->dc_acc3[cur], dc_seeds.p);
+        k_dc_apply<0><<<nt, FIR_THREADS, 0, stream>>>(pm_pll.p, n, 0, alpha, beta, dc_seeds.p, fir_out, &S->dc_acc3[nxt]);
+        launches += 3;
+    }
     if (order) {
         CostasParams P;
         P.order = order;
@@ -1064,8 +1087,8 @@ void Demod::stats(b200_demod_stats *o)
     o->last_front_samples = last_front;
     o->snr = snr_now;
     o->peak_snr = snr_peak;
-    o->pll_freq = pm ? h_state->pll[parity][1] : 0.f;
-    o->pll_unconverged = pm ? h_state->pll_unconv : 0;
+    o->pll_freq = (pm || cfg.has_carrier) ? h_state->pll[parity][1] : 0.f;
+    o->pll_unconverged = (pm || cfg.has_carrier) ? h_state->pll_unconv : 0;
 }
 
 } // namespace b200
@@ -1226,7 +1249,7 @@ int b200_demod_debug_stage(b200_demod *h, int stage, float *out, long cap_sample
             src = d.pm ? d.pm_agc.p : d.agc_dump.p;
         else if (stage == B200_STAGE_FIR)
             src = d.fir_dump.p;
-        else if (stage == B200_STAGE_PLL && d.pm)
+        else if (stage == B200_STAGE_PLL && (d.pm || d.cfg.has_carrier))
             src = d.pm_pll.p; // carrier PLL output (as many samples as entered the PLL)
         else if (stage == B200_STAGE_PM && d.pm)
             src = d.pm_out.p; // PMToBPSK output

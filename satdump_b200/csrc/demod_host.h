@@ -33,6 +33,7 @@ struct DemodDevState
     float2 agc2_tail[2][32];   // ... and its FIR history
     float2 agc1_tail[2][32];   // (the first AGC's kernel also keeps a FIR history; unused in pm mode)
     int pll_unconv;            // carrier PLL junctions still unconverged after the repair rounds of the last batch
+    float2 dc_acc3[2];         // psk_demod carrier mode: accumulator of the DC blocker behind the carrier PLL (module_psk_demod.cpp:112)
 };
 
 // one AGC (+ RRC) pass of k_agc_fir_w: which carried gain / FIR history it uses and where its outputs go
@@ -64,6 +65,8 @@ class Demod
     void front_resample(const void *&d_raw, long &n, int &front_fmt, int &rs_swap, long n_in, int cur, int nxt);
     // pm_demod: carrier PLL over n AGC'd samples (pm_agc -> pm_pll), then PMToBPSK (-> pm_out)
     void stage_pll(long n, int cur, int nxt);
+    // PLLCarrierTrackingBlock (segmented, junction check + repair rounds) over n samples: in -> out
+    void run_pll(const float2 *in, float2 *out, long n, float bw, float max_offset, int cur, int nxt);
     void run_rotator(const void *src, int fmt, long n, int iq_swap, int imag_only, unsigned long long dturn, unsigned long long pos, float2 *dst);
     const uint8_t *mm_quad = nullptr; // set by stage_costas when the clock recovery applies the rotation (/ OQPSK delay) itself
     int mm_rot = 0, mm_oqpsk = 0;

@@ -227,12 +227,26 @@ __global__ void __launch_bounds__(32) k_dmx_walk(const FrameSum *__restrict__ su
             npay += len;
         }
     };
-    for (long c0 = 0; c0 < nframes; c0 += 32) {
+    // four groups of 32 summaries are loaded at once (four independent loads in flight per lane), then walked in order
+    for (long c00 = 0; c00 < nframes; c00 += 128) {
+      FrameSum s4[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+          const long fq = c00 + 32 * q + lane;
+          s4[q].w0 = 0;
+          if (fq < nframes)
+              s4[q] = sums[fq];
+      }
+#pragma unroll 1
+      for (int q = 0; q < 4; q++) {
+        const long c0 = c00 + 32 * q;
+        if (c0 >= nframes)
+            break;
         const long fi = c0 + lane;
-        FrameSum s;
-        s.w0 = 0;
-        if (fi < nframes)
-            s = sums[fi];
+        FrameSum s = s4[0];
+        if (q == 1) s = s4[1];
+        if (q == 2) s = s4[2];
+        if (q == 3) s = s4[3];
         const unsigned myfl = s.w0 >> 24;
         const bool mine = fi < nframes && ((s.w0 >> 16) & 63) == (unsigned)v && (myfl & FS_SELECTED) && (myfl & FS_VALID);
         unsigned mask = __ballot_sync(0xffffffffu, mine);
@@ -347,6 +361,7 @@ __global__ void __launch_bounds__(32) k_dmx_walk(const FrameSum *__restrict__ su
                 fx[f] = (uint8_t)((pre + skip) | skip << 2);
             }
         }
+      }
     }
     if (lane == 0) {
         // the header of an open packet must outlive the frame buffer: make it inline

@@ -160,7 +160,16 @@ b200_demod_cfg demod_cfg_from_params(const Params &p, bool &is_bpsk, const std::
     c.freq_shift = (double)(long)p.num("freq_shift", 0); // module_demod_base.cpp:36-37,122-123 (long)
     c.iq_swap = p.flag("iq_swap", false); // module_demod_base.cpp:41-42 -> FileSourceBlock
     c.post_costas_dc = p.flag("post_costas_dc", false); // module_psk_demod.cpp:36-37,127-134
-    reject(p, "has_carrier", "PLL carrier tracking");
+    if (p.flag("has_carrier", false)) { // module_psk_demod.cpp:39-40,93-116
+        if (c.constellation != B200_BPSK)
+            throw ModuleError("For carrier mode, constellation must be BPSK!");
+        if (!p.has("carrier_pll_bw"))
+            throw ModuleError("Carrier PLL Bw parameter must be present!");
+        c.has_carrier = 1;
+        c.carrier_pll_bw = (float)p.num("carrier_pll_bw");
+        c.carrier_pll_max_offset = (float)p.num("carrier_pll_max_offset", 3.14);
+        c.costas_max_offset = 0.2f; // "the offset in frequency should already be resolved" (:116)
+    }
     reject(p, "enable_doppler", "Doppler correction");
     // BaseDemodModule::initb (module_demod_base.cpp:59-87): outside [min_sps, max_sps] the front-end resampler converts to this rate
     if (p.has("clock_recovery")) { // B200 extension (no reference module parameter): "gardner" swaps the clock recovery block

@@ -199,6 +199,10 @@ class SignalCfg:
     pm_pll_bw: float = 0.01         # receiver: carrier PLL bandwidth ("pll_bw" of pm_demod; pll_bw above is its "costas_bw")
     pm_pll_max_offset: float = 3.14
     resample_after_pll: bool = False
+    # psk_demod's carrier mode ("has_carrier", module_psk_demod.cpp:93-113): BPSK phase-modulated directly onto a residual carrier
+    # (pm_index * d(t), no subcarrier): carrier PLL -> DC blocker -> Costas loop
+    has_carrier: bool = False
+    carrier_pll_bw: float = 0.001
 
     @property
     def cadu_bytes(self):
@@ -256,6 +260,10 @@ CONFIGS = {
     "pm_bpsk_after": SignalCfg(name="pm_bpsk_after", samplerate=6e6, symbolrate=250000, constellation="bpsk", conv="1/2", interleave=4, fmt="cf32",
                                decoder="ccsds", ber_thresold=0.3, outsync_after=20, esn0_db=26.0, pll_bw=0.005, carrier_rad=1e-2, pm_index=1.0,
                                resample_after_pll=True),
+    # psk_demod with "has_carrier" (ODIN.json:16-24): BPSK r=1/2 phase-modulated onto a residual carrier, 2.5 samples per symbol
+    "bpsk_carrier": SignalCfg(name="bpsk_carrier", samplerate=6e6, symbolrate=2400000, constellation="bpsk", conv="1/2", interleave=4, fmt="cs16",
+                              decoder="ccsds", ber_thresold=0.3, outsync_after=20, esn0_db=10.0, pll_bw=0.001, carrier_rad=5e-3, pm_index=1.2,
+                              has_carrier=True, carrier_pll_bw=0.001, rrc_alpha=0.35),
     # C5: DVB-S2 front half AGC->RRC->M&M, cs8, 45 Msym/s @ 90 MS/s (sps 2.0), alpha 0.25 (DVB_Test.json:132-137), REC_ALPHA 1.7e-3
     "dvbs2_front": SignalCfg(name="dvbs2_front", samplerate=90e6, symbolrate=45000000, constellation="qpsk", conv="none", interleave=4,
                              rrc_alpha=0.25, fmt="cs8", decoder="none", clock_alpha=1.7e-3, carrier_rad=0.0, phase0=0.0, esn0_db=12.0),
@@ -356,9 +364,12 @@ def modulate(cfg: SignalCfg, coded, seed, nsamples=None, device="cpu"):
         t = n / sps + span + 0.37
         out_i[s:e] = shape(ai, t)
         if cfg.pm_index:
-            fsc = cfg.subcarrier if cfg.subcarrier else cfg.symbolrate
-            sub = torch.sin((2 * np.pi * fsc / cfg.samplerate * n) % (2 * np.pi)).float()
-            ph = cfg.pm_index * out_i[s:e] * sub
+            if cfg.has_carrier:
+                ph = cfg.pm_index * out_i[s:e]
+            else:
+                fsc = cfg.subcarrier if cfg.subcarrier else cfg.symbolrate
+                sub = torch.sin((2 * np.pi * fsc / cfg.samplerate * n) % (2 * np.pi)).float()
+                ph = cfg.pm_index * out_i[s:e] * sub
             out_i[s:e] = torch.cos(ph)
             out_q[s:e] = torch.sin(ph)
         elif aq is not None:

@@ -30,7 +30,9 @@ def demod_kwargs(cfg):
               fmt=cfg.fmt)
     if cfg.clock_alpha:
         kw["clock_alpha"] = cfg.clock_alpha
-    if cfg.pm_index:
+    if cfg.has_carrier:
+        kw.update(has_carrier=True, carrier_pll_bw=cfg.carrier_pll_bw)
+    elif cfg.pm_index:
         kw.update(pm=True, pm_pll_bw=cfg.pm_pll_bw, pm_pll_max_offset=cfg.pm_pll_max_offset, resample_after_pll=cfg.resample_after_pll,
                   subcarrier_offset=cfg.subcarrier)
     return kw

@@ -1,5 +1,5 @@
 """GPU: pm_demod (module_pm_demod.cpp: AGC -> PLLCarrierTrackingBlock -> PMToBPSK -> [SmartResampler -> AGC2] -> RRC -> Costas -> M&M)
-and the freq_shift option of BaseDemodModule, through the C ABI against the oracle.
+the freq_shift option of BaseDemodModule and psk_demod's carrier mode ("has_carrier"), through the C ABI against the oracle.
 
 Gates (measured distances on B200 in brackets, tools/probe_pm.py):
   carrier PLL, one segment            : bit for bit the reference (the kernel does the reference's operations in the reference's order)
@@ -88,6 +88,40 @@ def test_pm_demod_chain_against_the_reference(built, name):
     ds = np.abs(sp.astype(np.int16) - gsoft.astype(np.int16))
     assert (ds > 0).mean() <= 5e-3 and ds.max() <= 1
     assert all(g2.stats()[k] == 0 for k in ("pll_unconverged", "costas_unconverged", "mm_unconverged"))
+
+
+def test_psk_demod_carrier_mode(built):
+    """psk_demod with "has_carrier" (module_psk_demod.cpp:93-116, ODIN.json): RRC -> carrier PLL -> DC blocker -> Costas (limit 0.2) -> M&M."""
+    O = oracle()
+    cfg, raw, clear = signal("bpsk_carrier", 21, seed=1)
+    n = nsamples(raw, cfg)
+    d = oracle_demod(O, cfg)
+    o = d.run(raw)
+    g = gpu_demod(cfg, n, keep_stages=True)
+    g.push(raw)
+    st = g.stats()
+    assert st["pll_unconverged"] == 0 and st["costas_unconverged"] == 0 and st["mm_unconverged"] == 0
+    assert abs(st["pll_freq"] - float(d.pm_state()["pll_freq"])) <= 1e-6
+    assert np.abs(g.stage("fir") - o["fir"]).max() <= 1e-5
+    assert np.abs(g.stage("pll") - o["pll"]).max() <= 2e-5  # the carrier PLL's output (its input, the RRC output, is itself within 1e-5)
+    gs, gsoft = g.symbols(), g.soft()
+    assert gs.size == o["mm"].size
+    dm = np.abs(gs - o["mm"])
+    assert (dm > 1e-3).mean() <= 0.02 and dm.max() <= 3e-2, (float((dm > 1e-3).mean()), float(dm.max()))
+    ds = np.abs(gsoft.astype(np.int16) - o["soft"].astype(np.int16))
+    assert (ds > 0).mean() <= 5e-3 and (ds > 1).mean() <= 2e-5, (float((ds > 0).mean()), int(ds.max()))
+    ref_cadus = oracle_fec(O, cfg).run(o["soft"])["cadu"].reshape(-1, cfg.cadu_bytes)
+    got = oracle_fec(O, cfg).run(gsoft)["cadu"].reshape(-1, cfg.cadu_bytes)
+    assert ref_cadus.shape[0] >= 20 and np.array_equal(got, ref_cadus) and match_frames(got, clear)[1]
+    fused = gpu_chain(cfg, n).push(raw).frames()
+    assert np.array_equal(fused, ref_cadus)
+    # two ragged pushes: carried PLL state and DC accumulator
+    g2 = gpu_demod(cfg, n)
+    cut = (n // 3) | 1
+    sp = np.concatenate([g2.push(raw[:2 * cut]).soft(), g2.push(raw[2 * cut:]).soft()])
+    assert sp.size == gsoft.size
+    d2 = np.abs(sp.astype(np.int16) - gsoft.astype(np.int16))
+    assert (d2 > 0).mean() <= 5e-3 and (d2 > 1).mean() <= 2e-5
 
 
 def test_pm_demod_through_the_fused_chain(built):

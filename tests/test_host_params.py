@@ -21,7 +21,8 @@ def run(pipe, extra, tmp_path):
 @pytest.mark.parametrize("pipe,extra,needle", [
     ("pm_bpsk", ["--samplerate", "3e6", "--pll_bw", "0.9"], "pll_bw"),                         # pm_demod's carrier PLL bandwidth out of range
     ("metop_ahrpt", ["--enable_doppler", "true"], "enable_doppler"),
-    ("metop_ahrpt", ["--has_carrier", "true"], "has_carrier"),
+    ("metop_ahrpt", ["--has_carrier", "true"], "carrier mode, constellation must be BPSK"),     # module_psk_demod.cpp:95-96
+    ("simple_bpsk", ["--samplerate", "3e6", "--has_carrier", "true"], "Carrier PLL Bw"),          # :98-102
     ("metop_ahrpt", ["--baseband_format", "cu8"], "baseband_format"),
     ("metop_ahrpt", ["--samplerate", "1e6"], "sampling rate is too low"),         # module_demod_base.cpp:96-105
     ("simple_qpsk", ["--symbolrate", "2400000", "--oqpsk_method2", "true"], "oqpsk_method2"),
@@ -40,6 +41,7 @@ def test_valid_parameters_reach_the_device_check(built, tmp_path):
         pytest.skip("GPU present")
     for pipe, extra in [("metop_ahrpt", []), ("metop_ahrpt", ["--samplerate", "12e6"]), ("metop_ahrpt", ["--dc_block", "true", "--iq_swap", "true"]),
                         ("simple_bpsk", ["--samplerate", "3e6", "--post_costas_dc", "true"]), ("metop_ahrpt", ["--freq_shift", "-100000"]),
+                        ("simple_bpsk", ["--samplerate", "3e6", "--has_carrier", "true", "--carrier_pll_bw", "0.001"]),
                         ("pm_bpsk", ["--samplerate", "3e6"]), ("pm_bpsk", ["--samplerate", "6e6", "--symbolrate", "250000", "--resample_after_pll", "true"])]:
         r = run(pipe, extra, tmp_path)
         assert r.returncode == 1 and "no cpu fallback" in r.stderr.lower() and "cuda" in r.stderr.lower(), (pipe, extra, r.stderr)

@@ -287,6 +287,21 @@ def test_fast_trig_restatement_equals_reference(built):
         assert np.float32(R.ref_fast_sin(float(v))).tobytes() == np.float32(P.ref_fast_sin(float(v))).tobytes()
 
 
+def test_psk_demod_carrier_mode_port_equals_reference(built):
+    """psk_demod with "has_carrier" (module_psk_demod.cpp:93-116): RRC -> PLLCarrierTrackingBlock -> CorrectIQBlock -> Costas (limit 0.2)."""
+    from oracle import port
+    from tests.common import match_frames
+    ref = _ref()
+    cfg, raw, clear = signal("bpsk_carrier", 20, seed=11)
+    a, b = oracle_demod(ref, cfg), oracle_demod(port, cfg)
+    ra, rb = a.run(raw), b.run(raw)
+    for k in ("agc", "fir", "pll", "carrier_dc", "costas", "mm"):
+        assert bitwise(ra[k], rb[k]), k
+    assert np.array_equal(ra["soft"], rb["soft"]) and a.pm_state() == b.pm_state()
+    fr = oracle_fec(ref, cfg).run(ra["soft"])["cadu"].reshape(-1, cfg.cadu_bytes)
+    assert fr.shape[0] >= 10 and match_frames(fr, clear)[1]
+
+
 @pytest.mark.parametrize("name", ["pm_bpsk", "pm_bpsk_after"])
 def test_pm_demod_port_equals_reference(built, name):
     """pm_demod's chain (AGC -> carrier PLL -> PMToBPSK -> [resampler -> AGC2] -> RRC -> Costas -> M&M), restatement against the
