@@ -98,6 +98,6 @@ def test_errors_are_loud(built):
     g = capi.Demux(1024, 884, 0, max_frames=16)
     with pytest.raises(capi.B200Error, match="max_frames"):
         g.run(np.zeros((17, 1024), np.uint8))
-    tiny = capi.Demux(1024, 40, 0, max_frames=64, max_packets=8)
+    tiny = capi.Demux(1024, 884, 0, max_frames=64, max_packets=8)  # 64 frames of 884-byte zones hold far more than 8 packets
     with pytest.raises(capi.B200Error, match="packet table"):
-        tiny.run(synth.build_aos_frames(64, seed=1, mpdu=40, idle=0.0))
+        tiny.run(synth.build_aos_frames(64, seed=1, mpdu=884, idle=0.0))

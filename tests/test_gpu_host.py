@@ -29,11 +29,29 @@ def test_metop_cli_writes_reference_cadu_file(built, tmp_path, mode):
     assert got.size == want.size and np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("mode", ["two_stage", "fused"])
+def test_pm_demod_cli_writes_reference_cadu_file(built, tmp_path, mode):
+    """module id pm_demod (PMDemodModule's parameter set) -> ccsds_conv_concat_decoder through the host module layer."""
+    O = oracle()
+    cfg, raw, _ = signal("pm_bpsk", 22)
+    inp = tmp_path / "pm.cs16"
+    raw.tofile(inp)
+    want = oracle_fec(O, cfg).run(oracle_demod(O, cfg).run(raw, stages=False)["soft"])["cadu"]
+    hint = str(tmp_path / f"pm_{mode}")
+    # (the oracle configuration of the test signal carries psk_demod's clock-recovery gains; pm_demod's own defaults are 0.01 / 0.01^2/4)
+    gains = ["--clock_gain_mu", "8.7e-3", "--clock_gain_omega", repr(float(np.float32(pow(8.7e-3, 2) / 4.0)))]
+    cmd = [TOOL, "pm_bpsk", "baseband", str(inp), hint, "--samplerate", "3e6", "--baseband_format", "cs16"] + gains + (["--fused"] if mode == "fused" else [])
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    got = np.fromfile(hint + ".cadu", np.uint8)
+    assert want.size >= 20 * 1024 and got.size == want.size and np.array_equal(got, want)
+
+
 def test_cli_rejects_unsupported_options_loudly(built, tmp_path):
     inp = tmp_path / "x.cs16"
     np.zeros(4096, np.int16).tofile(inp)
-    for extra in (["--freq_shift", "1000"], ["--baseband_format", "cu8"], ["--baseband_format", "ziq"]):  # (60e6 used to be here: the
-        # power-of-two decimator takes it now)
+    for extra in (["--enable_doppler", "true"], ["--baseband_format", "cu8"], ["--baseband_format", "ziq"]):  # (60e6 and freq_shift used to be
+        # here: the power-of-two decimator / the rotator take them now)
         base = ["--samplerate", "6e6", "--baseband_format", "cs16"]
         r = subprocess.run([TOOL, "metop_ahrpt", "baseband", str(inp), str(tmp_path / "o")] + base + extra, capture_output=True, text=True, timeout=120)
         assert r.returncode == 1 and "error" in r.stderr.lower(), (extra, r.stderr)
