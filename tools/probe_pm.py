@@ -88,8 +88,10 @@ def main():
         t = g.timing()
         print(name, "timing ms", t)
 
-    # freq_shift in front of psk_demod
-    cfg = synth.CONFIGS["metop_ahrpt"]
+    # freq_shift in front of psk_demod: a carrier 150 kHz off centre, shifted back (shifting a centred signal AWAY instead makes the
+    # reference's Costas loop chase 0.157 rad/sample for the whole stream: not a parity case)
+    import dataclasses
+    cfg = dataclasses.replace(synth.CONFIGS["metop_ahrpt"], carrier_rad=2 * np.pi * 150e3 / 6e6 + 1e-3)
     raw, _ = synth.make_signal(cfg, 1 << lg, seed=1)
     raw = raw.numpy()
     n = common.nsamples(raw, cfg)
