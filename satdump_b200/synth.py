@@ -260,6 +260,10 @@ CONFIGS = {
     "pm_bpsk_after": SignalCfg(name="pm_bpsk_after", samplerate=6e6, symbolrate=250000, constellation="bpsk", conv="1/2", interleave=4, fmt="cf32",
                                decoder="ccsds", ber_thresold=0.3, outsync_after=20, esn0_db=26.0, pll_bw=0.005, carrier_rad=1e-2, pm_index=1.0,
                                resample_after_pll=True),
+    # the same 24 samples per symbol WITHOUT resample_after_pll: BaseDemodModule resamples 6 MS/s -> 2 MS/s in front (decimator /2 + rational
+    # 2/3), the carrier PLL and PMToBPSK run at the working rate
+    "pm_bpsk_front": SignalCfg(name="pm_bpsk_front", samplerate=6e6, symbolrate=250000, constellation="bpsk", conv="1/2", interleave=4, fmt="cs16",
+                               decoder="ccsds", ber_thresold=0.3, outsync_after=20, esn0_db=26.0, pll_bw=0.005, carrier_rad=1e-2, pm_index=1.0),
     # psk_demod with "has_carrier" (ODIN.json:16-24): BPSK r=1/2 phase-modulated onto a residual carrier, 2.5 samples per symbol
     "bpsk_carrier": SignalCfg(name="bpsk_carrier", samplerate=6e6, symbolrate=2400000, constellation="bpsk", conv="1/2", interleave=4, fmt="cs16",
                               decoder="ccsds", ber_thresold=0.3, outsync_after=20, esn0_db=10.0, pll_bw=0.001, carrier_rad=5e-3, pm_index=1.2,

@@ -23,7 +23,7 @@ from satdump_b200 import capi, synth
 from tests.common import demod_kwargs, gpu_chain, gpu_demod, match_frames, nsamples, oracle, oracle_demod, oracle_fec, signal
 
 pytestmark = pytest.mark.gpu
-PM = ["pm_bpsk", "pm_bpsk_after"]
+PM = ["pm_bpsk", "pm_bpsk_after", "pm_bpsk_front"]  # 6 samples/symbol; resampler behind the PLL; resampler in front
 
 
 def rotation_gates(g, o, n_total):
@@ -160,6 +160,22 @@ def test_freq_shift_brings_an_offset_carrier_back(built):
     f = oracle_fec(O, cfg)
     got = f.run(gsoft)["cadu"].reshape(-1, cfg.cadu_bytes)
     assert got.shape[0] >= 4 and np.array_equal(got, oracle_fec(O, cfg).run(o["soft"])["cadu"].reshape(-1, cfg.cadu_bytes)) and match_frames(got, clear)[1]
+
+
+@pytest.mark.parametrize("name", ["pm_bpsk", "pm_bpsk_after"])
+def test_pm_demod_iq_swap_is_applied_at_the_reader(built, name):
+    """iq_swap (FileSourceBlock, module_demod_base.cpp:41-42) in front of pm_demod: a recording with I and Q exchanged gives the same soft
+    symbols bit for bit (with resample_after_pll nothing in front of the AGC applies the swap: a converting copy does)."""
+    cfg, raw, _ = signal(name, 20, seed=8)
+    n = nsamples(raw, cfg)
+    if cfg.fmt == "cf32":
+        swapped = (raw.imag + 1j * raw.real).astype(np.complex64)
+    else:
+        swapped = np.ascontiguousarray(raw.reshape(-1, 2)[:, ::-1]).reshape(-1)
+    kw = demod_kwargs(cfg)
+    a = capi.Demod(capi.demod_cfg(max_batch=n, **kw)).push(raw).soft()
+    b = capi.Demod(capi.demod_cfg(max_batch=n, iq_swap=True, **kw)).push(swapped).soft()
+    assert a.size > 1000 and np.array_equal(a, b)
 
 
 def test_pm_demod_errors_are_loud(built):

@@ -302,7 +302,7 @@ def test_psk_demod_carrier_mode_port_equals_reference(built):
     assert fr.shape[0] >= 10 and match_frames(fr, clear)[1]
 
 
-@pytest.mark.parametrize("name", ["pm_bpsk", "pm_bpsk_after"])
+@pytest.mark.parametrize("name", ["pm_bpsk", "pm_bpsk_after", "pm_bpsk_front"])
 def test_pm_demod_port_equals_reference(built, name):
     """pm_demod's chain (AGC -> carrier PLL -> PMToBPSK -> [resampler -> AGC2] -> RRC -> Costas -> M&M), restatement against the
     compiled reference modules stage by stage, and the decoded CADUs against the transmitted frames."""
@@ -318,7 +318,7 @@ def test_pm_demod_port_equals_reference(built, name):
     assert a.pm_state() == b.pm_state()
     fr = oracle_fec(ref, cfg).run(ra["soft"])["cadu"].reshape(-1, cfg.cadu_bytes)
     first, ok = match_frames(fr, clear)
-    assert fr.shape[0] >= 2 and ok, (fr.shape, first)
+    assert fr.shape[0] >= 1 and ok, (fr.shape, first)  # (24 samples per symbol: 2^20 samples hold two to three CADUs)
 
 
 def test_freq_shift_port_equals_reference(built):
