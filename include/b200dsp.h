@@ -11,11 +11,15 @@
  *                    src-core/pipeline/modules/demod/module_psk_demod.cpp:86-236   (init / process)
  *                    src-core/pipeline/modules/demod/module_demod_base.cpp:59-208   (initb: source, AGC)
  *                    plugins/dvb_support/dvbs2/module_dvbs2_demod.cpp:98-102        (AGC->RRC->M&M front half; constellation NONE)
+ *                    src-core/pipeline/modules/demod/module_pm_demod.cpp:61-160      (PMDemodModule: cfg.pm_demod = 1)
  *   b200_fec_*     the decoder modules
  *                    plugins/noaa_metop_support/metop/module_metop_ahrpt_decoder.cpp:34-90      (kind METOP)
  *                    src-core/pipeline/modules/ccsds/module_ccsds_conv_concat_decoder.cpp:140-200 (kind CCSDS, r=1/2)
  *   b200_chain_*   both modules joined the way Pipeline::run joins them with a byte FIFO
  *                    src-core/pipeline/pipeline_run.cpp:44-117 — here the int8 soft stream never leaves HBM.
+ *   b200_demux_*   the step behind the decoder: CADUs -> CCSDS space packets
+ *                    src-core/common/ccsds/ccsds_aos/demuxer.cpp:64-199 (one Demuxer per virtual channel), vcdu.cpp:10-17, mpdu.cpp:9-13,
+ *                    as plugins/noaa_metop_support/metop/module_metop_instruments.cpp:66-140 calls them
  *
  * All functions return 0 on success or a negative B200_E* code; b200_last_error() gives the text.
  * There is no CPU fallback: without a CUDA device every create() fails with B200_ENODEV.

@@ -8,6 +8,8 @@
 //   OQPSK delay         src-core/common/dsp/demod/delay_one_imag.cpp:18-25
 //   M&M clock recovery  src-core/common/dsp/clock_recovery/clock_recovery_mm.cpp:52-121
 //   soft quantiser      src-core/pipeline/modules/demod/module_psk_demod.cpp:199-213
+//   pm_demod / carrier mode: carrier PLL  src-core/common/dsp/pll/pll_carrier_tracking.cpp:25-70 (+ utils/fast_trig.cpp), PMToBPSK
+//                       src-core/common/dsp/demod/pm_to_bpsk.cpp:10-35, FreqShiftBlock src-core/common/dsp/utils/freq_shift.cpp:16-50
 //
 // The reference runs every stage as a serial per-sample loop. Here:
 //   * AGC: g' = g(1-r|x|) + r is an affine map -> per-tile composition (k_agc_compose), a scan over tiles
