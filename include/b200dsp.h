@@ -284,6 +284,8 @@ typedef struct b200_packet
 typedef struct b200_demux_stats
 {
     long frames_in, packets_out, kernel_launches;
+    long redone_channels; /* virtual channels walked a second time, serially, because leftover bytes of an unfinished packet crossed a window
+                             boundary of the parallel walk (inconsistent frames only; expected 0) */
 } b200_demux_stats;
 typedef struct b200_demuxer b200_demuxer;
 b200_demuxer *b200_demux_create(const b200_demux_cfg *cfg);

@@ -62,7 +62,7 @@ class Packet(C.Structure):
 
 
 class DemuxStats(C.Structure):
-    _fields_ = [("frames_in", C.c_long), ("packets_out", C.c_long), ("kernel_launches", C.c_long)]
+    _fields_ = [("frames_in", C.c_long), ("packets_out", C.c_long), ("kernel_launches", C.c_long), ("redone_channels", C.c_long)]
 
 
 class DemodStats(C.Structure):

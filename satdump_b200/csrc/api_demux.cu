@@ -16,9 +16,10 @@ struct Demux
     long max_frames = 0, cap_recs = 0, cap_bytes = 0, frame0 = 0;
     int carry_cap = 1 << 17; // bytes of a packet under construction carried between pushes (a packet holds at most 65 550)
     int parity = 0;
-    DevBuf<uint8_t> frames, fx, carry[2], out;
+    DevBuf<uint8_t> frames, fxa, fxb, carry[2], out;
     DevBuf<FrameSum> sums;
-    DevBuf<int> hist, cnt, nwp, tailseg, flags, sizes;
+    DevBuf<int> cnt, tailseg, flags, sizes;
+    DevBuf<unsigned long long> redo_mask;
     DevBuf<long> base, offs;
     DevBuf<WalkPkt> wp;
     DevBuf<DmxSeg> segs;
@@ -27,6 +28,8 @@ struct Demux
     DevBuf<DmxCarry> st[2];
     long *h_counts = nullptr; // pinned: packets, bytes
     int *h_flags = nullptr;
+    unsigned long long *h_redo = nullptr;
+    long redone_channels = 0; // channels walked again by one warp because a guess at a window boundary was wrong (so far)
     long last_packets = 0, last_bytes = 0, total_packets = 0, total_frames = 0, launches = 0;
 
     explicit Demux(const b200_demux_cfg &c) : cfg(c)
@@ -48,15 +51,15 @@ struct Demux
         cap_bytes = max_frames * (2L * G.M) + cap_recs * 6 + 64L * carry_cap;
         frames.alloc((size_t)max_frames * G.stride);
         sums.alloc(max_frames);
-        fx.alloc(max_frames);
+        fxa.alloc(max_frames);
+        fxb.alloc(max_frames);
         cnt.alloc(max_frames);
         base.alloc(max_frames + 1);
-        hist.alloc(64);
-        nwp.alloc(64);
         tailseg.alloc(128);
         flags.alloc(1);
-        wp.alloc(3 * max_frames + 2 * 64 + 8);
-        segs.alloc(3 * max_frames + 2 * 64 + 8);
+        redo_mask.alloc(1);
+        wp.alloc(2 * max_frames);       // two walk-packet slots per frame
+        segs.alloc(3 * max_frames + 64); // three segment slots per frame + one carry segment per channel
         recs.alloc(cap_recs);
         orec.alloc(cap_recs);
         sizes.alloc(cap_recs);
@@ -69,6 +72,7 @@ struct Demux
         }
         B200_CUDA(cudaMallocHost((void **)&h_counts, 2 * sizeof(long)));
         B200_CUDA(cudaMallocHost((void **)&h_flags, sizeof(int)));
+        B200_CUDA(cudaMallocHost((void **)&h_redo, sizeof(unsigned long long)));
         B200_CUDA(cudaStreamSynchronize(stream));
     }
     ~Demux()
@@ -82,6 +86,8 @@ struct Demux
             cudaFreeHost(h_counts);
         if (h_flags)
             cudaFreeHost(h_flags);
+        if (h_redo)
+            cudaFreeHost(h_redo);
     }
     void reset()
     {
@@ -97,16 +103,20 @@ struct Demux
         B200_REQUIRE(n >= 1 && n <= max_frames, B200_ESTATE, "%ld frames outside [1, max_frames %ld]", n, max_frames);
         DeviceGuard g(cfg.device);
         const int cur = parity, nxt = parity ^ 1;
-        B200_CUDA(cudaMemsetAsync(hist.p, 0, 64 * sizeof(int), stream));
-        B200_CUDA(cudaMemsetAsync(cnt.p, 0, n * sizeof(int), stream));
-        B200_CUDA(cudaMemsetAsync(fx.p, 0, n, stream));
+        B200_CUDA(cudaMemsetAsync(fxa.p, 0, n, stream));
+        B200_CUDA(cudaMemsetAsync(fxb.p, 0, n, stream));
         B200_CUDA(cudaMemsetAsync(flags.p, 0, sizeof(int), stream));
+        B200_CUDA(cudaMemsetAsync(redo_mask.p, 0, sizeof(unsigned long long), stream));
         const unsigned fb = (unsigned)((n + 255) / 256);
-        k_dmx_frames<false><<<fb, 256, 0, stream>>>(d_frames, n, frame0, G, cfg.vcid_mask, sums.p, hist.p, nullptr, nullptr, nullptr, 0, flags.p);
-        k_dmx_walk<<<64, 32, 0, stream>>>(sums.p, n, frame0, G, hist.p, d_frames, st[cur].p, st[nxt].p, cnt.p, fx.p, wp.p, nwp.p, segs.p, tailseg.p);
+        k_dmx_frames<false><<<fb, 256, 0, stream>>>(d_frames, n, frame0, G, cfg.vcid_mask, sums.p, nullptr, nullptr, nullptr, nullptr, 0, flags.p);
+        // the walk: DMX_K guessing warps per channel, then one warp for every channel whose guess at a window boundary was wrong
+        k_dmx_walk<<<dim3(DMX_K, 64), 32, 0, stream>>>(sums.p, n, frame0, G, 0, redo_mask.p, d_frames, st[cur].p, st[nxt].p, fxa.p, fxb.p, wp.p, segs.p, tailseg.p);
+        k_dmx_walk<<<dim3(1, 64), 32, 0, stream>>>(sums.p, n, frame0, G, 1, redo_mask.p, d_frames, st[cur].p, st[nxt].p, fxa.p, fxb.p, wp.p, segs.p, tailseg.p);
+        k_dmx_cnt<<<fb, 256, 0, stream>>>(sums.p, fxa.p, n, cnt.p);
         k_dmx_scan<<<1, 1024, 0, stream>>>(cnt.p, n, nullptr, base.p);
-        k_dmx_frames<true><<<fb, 256, 0, stream>>>(d_frames, n, frame0, G, cfg.vcid_mask, nullptr, nullptr, base.p, fx.p, recs.p, cap_recs, flags.p);
-        k_dmx_place<<<dim3(32, 64), 128, 0, stream>>>(wp.p, nwp.p, hist.p, frame0, base.p, recs.p, cap_recs, flags.p);
+        k_dmx_frames<true><<<fb, 256, 0, stream>>>(d_frames, n, frame0, G, cfg.vcid_mask, nullptr, base.p, fxa.p, fxb.p, recs.p, cap_recs, flags.p);
+        k_dmx_place<<<fb, 256, 0, stream>>>(wp.p, sums.p, fxa.p, fxb.p, n, base.p, recs.p, cap_recs, flags.p);
+        B200_CUDA(cudaMemcpyAsync(h_redo, redo_mask.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
         B200_CUDA(cudaMemcpyAsync(&h_counts[0], base.p + n, sizeof(long), cudaMemcpyDeviceToHost, stream));
         B200_CUDA(cudaMemcpyAsync(h_flags, flags.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
         B200_CUDA(cudaStreamSynchronize(stream));
@@ -122,7 +132,9 @@ struct Demux
         B200_CUDA(cudaMemcpyAsync(h_flags, flags.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
         B200_CUDA(cudaStreamSynchronize(stream));
         B200_CUDA(cudaGetLastError());
-        launches += 10;
+        launches += 12;
+        if (*h_redo)
+            redone_channels += __builtin_popcountll(*h_redo);
         B200_REQUIRE(!(*h_flags & 2), B200_ESTATE, "internal: packet byte buffer too small");
         B200_REQUIRE(!(*h_flags & 4), B200_EUNSUPPORTED, "a packet under construction grew beyond %d bytes (inconsistent frames)", carry_cap);
         parity = nxt;
@@ -212,6 +224,7 @@ int b200_demux_get_stats(b200_demuxer *h, b200_demux_stats *out)
         out->frames_in = d.total_frames;
         out->packets_out = d.total_packets;
         out->kernel_launches = d.launches;
+        out->redone_channels = d.redone_channels;
     });
 }
 }
