@@ -155,7 +155,8 @@ b200_demod_cfg demod_cfg_from_params(const Params &p, bool &is_bpsk, const std::
     if (fmt == "cf32" || fmt == "f32") c.format = B200_CF32;
     else if (fmt == "cs16" || fmt == "s16") c.format = B200_CS16;
     else if (fmt == "cs8" || fmt == "s8") c.format = B200_CS8;
-    else throw ModuleError("baseband_format " + fmt + " is not supported by the B200 path (cf32/cs16/cs8 only)");
+    else if (fmt == "ziq") c.format = -1; // uncompressed ZIQ: the sample type comes from the file header (resolve_ziq, at init)
+    else throw ModuleError("baseband_format " + fmt + " is not supported by the B200 path (cf32/cs16/cs8, uncompressed ziq)");
     c.dc_block = p.flag("dc_block", false); // module_demod_base.cpp:33-34,113-114
     c.freq_shift = (double)(long)p.num("freq_shift", 0); // module_demod_base.cpp:36-37,122-123 (long)
     c.iq_swap = p.flag("iq_swap", false); // module_demod_base.cpp:41-42 -> FileSourceBlock
@@ -230,7 +231,8 @@ b200_demod_cfg pm_demod_cfg_from_params(const Params &p, bool &is_bpsk)
     if (fmt == "cf32" || fmt == "f32") c.format = B200_CF32;
     else if (fmt == "cs16" || fmt == "s16") c.format = B200_CS16;
     else if (fmt == "cs8" || fmt == "s8") c.format = B200_CS8;
-    else throw ModuleError("baseband_format " + fmt + " is not supported by the B200 path (cf32/cs16/cs8 only)");
+    else if (fmt == "ziq") c.format = -1; // uncompressed ZIQ: the sample type comes from the file header (resolve_ziq, at init)
+    else throw ModuleError("baseband_format " + fmt + " is not supported by the B200 path (cf32/cs16/cs8, uncompressed ziq)");
     c.dc_block = p.flag("dc_block", false);
     c.freq_shift = (double)(long)p.num("freq_shift", 0);
     c.iq_swap = p.flag("iq_swap", false);
@@ -353,6 +355,32 @@ static uint64_t file_size(const std::string &path)
     fclose(f);
     return n;
 }
+// ZIQ header (src-core/common/ziq.cpp:115-153, docs/pages/ZIQ.md): "ZIQ_", is_compressed (1 byte), bits_per_sample (1 byte), samplerate
+// (uint64), annotation length (uint64), annotation; then the samples: int8 / int16 / float32 I,Q pairs, converted exactly like cs8 / cs16 /
+// cf32 (ziq.cpp:258-303). Uncompressed files are read here; ZSTD-compressed ones need libzstd, which this build does not link: error.
+// Returns the byte offset of the first sample and sets `format`.
+static size_t resolve_ziq(const std::string &path, int &format)
+{
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f)
+        throw ModuleError("cannot open " + path);
+    unsigned char h[22];
+    const size_t got = fread(h, 1, sizeof h, f);
+    fclose(f);
+    if (got != sizeof h || memcmp(h, "ZIQ_", 4) != 0)
+        throw ModuleError("This file is not a valid ZIQ file!"); // ziq.cpp:128-132
+    if (h[4])
+        throw ModuleError("ZSTD-compressed ZIQ input is not supported by the B200 path (no libzstd in this build): decompress it, or record uncompressed");
+    const int bits = h[5];
+    if (bits == 8) format = B200_CS8;
+    else if (bits == 16) format = B200_CS16;
+    else if (bits == 32) format = B200_CF32;
+    else throw ModuleError("ZIQ file with " + std::to_string(bits) + " bits per sample");
+    uint64_t alen = 0;
+    memcpy(&alen, h + 14, 8);
+    return (size_t)(22 + alen); // ziq.cpp:178,200: annotation_size + 22
+}
+
 static void check(int rc, const char *what)
 {
     if (rc != B200_OK)
@@ -372,6 +400,11 @@ PskDemodStage::PskDemodStage(std::string in, std::string hint, Params p, std::st
 PskDemodStage::~PskDemodStage() { b200_demod_destroy(h); }
 void PskDemodStage::init()
 {
+    if (cfg.format < 0) { // baseband_format "ziq"
+        if (in_type != DataType::FILE)
+            throw ModuleError("ziq input needs a file");
+        data_offset = resolve_ziq(input_file, cfg.format);
+    }
     h = b200_demod_create(&cfg);
     if (!h)
         throw ModuleError(b200_last_error());
@@ -389,6 +422,8 @@ void PskDemodStage::process()
         if (!fin)
             throw std::runtime_error("cannot open " + input_file);
         filesize = file_size(input_file);
+        if (data_offset)
+            fseek(fin, (long)data_offset, SEEK_SET);
     }
     if (out_type == DataType::FILE) {
         output_file = output_hint + ".soft"; // module_psk_demod.cpp:147-151
@@ -526,6 +561,8 @@ FusedStage::FusedStage(const std::string &decoder_id, std::string in, std::strin
 FusedStage::~FusedStage() { b200_chain_destroy(h); }
 void FusedStage::init()
 {
+    if (dcfg.format < 0) // baseband_format "ziq"
+        data_offset = resolve_ziq(input_file, dcfg.format);
     h = b200_chain_create(&dcfg, &fcfg);
     if (!h)
         throw ModuleError(b200_last_error());
@@ -540,6 +577,8 @@ void FusedStage::process()
     if (!fin)
         throw std::runtime_error("cannot open " + input_file);
     const uint64_t fsz = file_size(input_file);
+    if (data_offset)
+        fseek(fin, (long)data_offset, SEEK_SET);
     output_file = output_hint + ".cadu";
     FILE *fout = fopen(output_file.c_str(), "wb");
     uint64_t done = 0;

@@ -108,6 +108,7 @@ class PskDemodStage : public StageBase
     std::string id;
     b200_demod *h = nullptr;
     bool is_bpsk = false;
+    size_t data_offset = 0; // first sample of the input file (behind a ZIQ header)
 };
 
 // metop_ahrpt_decoder (params viterbi_outsync_after, viterbi_ber_thresold) and ccsds_conv_concat_decoder (App. B list).
@@ -148,6 +149,7 @@ class FusedStage : public StageBase
     b200_demod_cfg dcfg{};
     b200_fec_cfg fcfg{};
     b200_chain *h = nullptr;
+    size_t data_offset = 0; // first sample of the input file (behind a ZIQ header)
 };
 
 b200_demod_cfg demod_cfg_from_params(const Params &p, bool &is_bpsk, const std::string &module_id = "psk_demod");

@@ -30,6 +30,25 @@ def test_metop_cli_writes_reference_cadu_file(built, tmp_path, mode):
 
 
 @pytest.mark.parametrize("mode", ["two_stage", "fused"])
+def test_uncompressed_ziq_input(built, tmp_path, mode):
+    """baseband_format ziq, uncompressed (docs/pages/ZIQ.md, src-core/common/ziq.cpp:115-153,258-303): a 22-byte header + annotation in front of
+    the cs16 samples; same CADUs as the raw file."""
+    import struct
+    O = oracle()
+    cfg, raw, _ = signal("metop_ahrpt", 22)
+    note = b'{"recorder": "test"}'
+    inp = tmp_path / "metop.ziq"
+    inp.write_bytes(b"ZIQ_" + bytes([0, 16]) + struct.pack("<Q", 6000000) + struct.pack("<Q", len(note)) + note + raw.tobytes())
+    want = oracle_fec(O, cfg).run(oracle_demod(O, cfg).run(raw, stages=False)["soft"])["cadu"]
+    hint = str(tmp_path / f"ziq_{mode}")
+    cmd = [TOOL, "metop_ahrpt", "baseband", str(inp), hint, "--samplerate", "6e6", "--baseband_format", "ziq"] + (["--fused"] if mode == "fused" else [])
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    got = np.fromfile(hint + ".cadu", np.uint8)
+    assert got.size == want.size and np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("mode", ["two_stage", "fused"])
 def test_pm_demod_cli_writes_reference_cadu_file(built, tmp_path, mode):
     """module id pm_demod (PMDemodModule's parameter set) -> ccsds_conv_concat_decoder through the host module layer."""
     O = oracle()
@@ -50,7 +69,7 @@ def test_pm_demod_cli_writes_reference_cadu_file(built, tmp_path, mode):
 def test_cli_rejects_unsupported_options_loudly(built, tmp_path):
     inp = tmp_path / "x.cs16"
     np.zeros(4096, np.int16).tofile(inp)
-    for extra in (["--enable_doppler", "true"], ["--baseband_format", "cu8"], ["--baseband_format", "ziq"]):  # (60e6 and freq_shift used to be
+    for extra in (["--enable_doppler", "true"], ["--baseband_format", "cu8"], ["--baseband_format", "w16"]):  # (60e6 and freq_shift used to be
         # here: the power-of-two decimator / the rotator take them now)
         base = ["--samplerate", "6e6", "--baseband_format", "cs16"]
         r = subprocess.run([TOOL, "metop_ahrpt", "baseband", str(inp), str(tmp_path / "o")] + base + extra, capture_output=True, text=True, timeout=120)

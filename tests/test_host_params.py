@@ -45,3 +45,28 @@ def test_valid_parameters_reach_the_device_check(built, tmp_path):
                         ("pm_bpsk", ["--samplerate", "3e6"]), ("pm_bpsk", ["--samplerate", "6e6", "--symbolrate", "250000", "--resample_after_pll", "true"])]:
         r = run(pipe, extra, tmp_path)
         assert r.returncode == 1 and "no cpu fallback" in r.stderr.lower() and "cuda" in r.stderr.lower(), (pipe, extra, r.stderr)
+
+
+def _ziq(path, payload, bits=16, compressed=0, signature=b"ZIQ_", annotation=b'{"note": "x"}'):
+    import struct
+    path.write_bytes(signature + bytes([compressed, bits]) + struct.pack("<Q", 6000000) + struct.pack("<Q", len(annotation)) + annotation + payload)
+
+
+def test_ziq_header_is_read_before_the_device_is_touched(built, tmp_path):
+    """baseband_format ziq (src-core/common/ziq.cpp:115-153): uncompressed files are accepted (their samples are cs8 / cs16 / cf32 behind the
+    header), ZSTD-compressed ones and files without the signature are refused by name."""
+    import torch
+    out = str(tmp_path / "o")
+    good, comp, bad = tmp_path / "a.ziq", tmp_path / "b.ziq", tmp_path / "c.ziq"
+    _ziq(good, b"\0" * 65536)
+    _ziq(comp, b"\0" * 65536, compressed=1)
+    _ziq(bad, b"\0" * 65536, signature=b"RIFF")
+    for fused in ([], ["--fused"]):
+        args = ["--samplerate", "6e6", "--baseband_format", "ziq"] + fused
+        r = subprocess.run([TOOL, "metop_ahrpt", "baseband", str(comp), out] + args, capture_output=True, text=True, timeout=60)
+        assert r.returncode == 1 and "zstd" in r.stderr.lower(), r.stderr
+        r = subprocess.run([TOOL, "metop_ahrpt", "baseband", str(bad), out] + args, capture_output=True, text=True, timeout=60)
+        assert r.returncode == 1 and "not a valid ziq" in r.stderr.lower(), r.stderr
+        if not torch.cuda.is_available():
+            r = subprocess.run([TOOL, "metop_ahrpt", "baseband", str(good), out] + args, capture_output=True, text=True, timeout=60)
+            assert r.returncode == 1 and "no cpu fallback" in r.stderr.lower(), r.stderr
